@@ -1,0 +1,430 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the UNMODIFIED
+reference (iffiX/machin mounted at /root/reference) in the build container.
+
+    python -m oracle.make_golden            # from the repo root
+
+The fixtures travel to the GPU box; the reference does not.  Every array saved here is
+an input or an output of reference code -- nothing is produced by the oracle restatement
+or by the CUDA path.  Seeds follow the reference test-suite convention
+(test/util_fixtures.py:50-55).
+"""
+import os
+import random
+import sys
+
+import numpy as np
+import torch as t
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import ref_shim  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def seed_all(s=0):
+    t.manual_seed(s)
+    np.random.seed(s)
+    random.seed(s)
+
+
+# --------------------------------------------------------------------------- tree
+def gen_tree():
+    from machin.frame.buffers import WeightTree
+
+    out = {}
+    rng = np.random.RandomState(1234)
+    for size in (1, 2, 3, 5, 8, 1000, 1025, 4096):
+        tree = WeightTree(size)
+        leaves = rng.exponential(size=size)
+        leaves[rng.rand(size) < 0.1] = 0.0
+        tree.update_all_leaves(leaves)
+        out[f"n{size}_leaves"] = leaves
+        out[f"n{size}_built"] = tree.weights.copy()
+        out[f"n{size}_built_max"] = np.float64(tree.max_leaf)
+        total = tree.get_weight_sum()
+        q = np.concatenate((rng.uniform(-0.5, total * 1.1 + 0.5, size=257),
+                            [0.0, total, total - 1e-6, -1.0, total * 2 + 1],
+                            np.cumsum(leaves)[: min(size, 64)]))
+        out[f"n{size}_query"] = q
+        out[f"n{size}_found"] = np.asarray(tree.find_leaf_index(q)).reshape(-1)
+        # batched update with duplicates (last write wins) then a second, float32 one
+        nb = max(1, min(size * 2, 300))
+        idx = rng.randint(0, size, size=nb).astype(np.int64)
+        w = rng.exponential(size=nb)
+        tree.update_leaf_batch(w, idx)
+        out[f"n{size}_upd_idx"] = idx
+        out[f"n{size}_upd_w"] = w
+        out[f"n{size}_after_upd"] = tree.weights.copy()
+        out[f"n{size}_after_upd_max"] = np.float64(tree.max_leaf)
+        idx2 = rng.randint(0, size, size=nb).astype(np.int64)
+        w2 = rng.exponential(size=nb).astype(np.float32)
+        tree.update_leaf_batch(w2, idx2)
+        out[f"n{size}_upd2_idx"] = idx2
+        out[f"n{size}_upd2_w"] = w2
+        out[f"n{size}_after_upd2"] = tree.weights.copy()
+        # single-leaf updates
+        # (size 1: the reference's update_leaf raises IndexError at :140 -- quirk, not pinned)
+        for k in range(3 if size > 1 else 0):
+            i = int(rng.randint(0, size))
+            v = float(rng.exponential())
+            tree.update_leaf(v, i)
+            out[f"n{size}_single{k}"] = np.array([i, v])
+        out[f"n{size}_after_single"] = tree.weights.copy()
+        out[f"n{size}_found2"] = np.asarray(tree.find_leaf_index(q)).reshape(-1)
+    np.savez_compressed(os.path.join(OUT, "ref_tree.npz"), **out)
+
+
+# --------------------------------------------------------------------------- PER
+def _episode(n, state_dim, rng, reward_int=False):
+    ep = []
+    for _ in range(n):
+        ep.append(dict(
+            state={"state": t.from_numpy(rng.randn(1, state_dim).astype(np.float32))},
+            action={"action": t.tensor([[int(rng.randint(0, 6))]], dtype=t.long)},
+            next_state={"state": t.from_numpy(rng.randn(1, state_dim).astype(np.float32))},
+            reward=float(np.float32(rng.randn())),
+            terminal=bool(rng.rand() < 0.1),
+        ))
+    return ep
+
+
+def gen_per():
+    from machin.frame.buffers import PrioritizedBuffer
+
+    out = {}
+    rng = np.random.RandomState(99)
+    for tag, cap, n_store in (("small", 50, 37), ("wrap", 64, 150), ("big", 5000, 5000)):
+        buf = PrioritizedBuffer(buffer_size=cap, buffer_device="cpu")
+        stored = 0
+        pri_all = []
+        len_all = []
+        while stored < n_store:
+            n = int(rng.randint(1, 12))
+            n = min(n, n_store - stored)
+            pri = rng.exponential(size=n)
+            buf.store_episode(_episode(n, 4, rng), priorities=list(pri))
+            pri_all.append(pri)
+            len_all.append(n)
+            stored += n
+        out[f"{tag}_cap"] = np.int64(cap)
+        out[f"{tag}_ep_len"] = np.array(len_all, dtype=np.int64)
+        out[f"{tag}_ep_pri"] = np.concatenate(pri_all)
+        out[f"{tag}_tree"] = buf.wt_tree.weights.copy()
+        out[f"{tag}_max_leaf"] = np.float64(buf.wt_tree.max_leaf)
+        seed_all(7)
+        for step in range(4):
+            b = (16, 32, 5, 100)[step]
+            state = np.random.get_state()
+            uni = np.random.uniform(size=b)
+            np.random.set_state(state)
+            beta_before = float(buf.curr_beta)
+            index, isw = buf.sample_index_and_weight(b)
+            out[f"{tag}_s{step}_uniform"] = uni
+            out[f"{tag}_s{step}_beta"] = np.float64(beta_before)
+            out[f"{tag}_s{step}_nstored"] = np.int64(len(buf.storage))
+            out[f"{tag}_s{step}_index"] = np.asarray(index).reshape(-1)
+            out[f"{tag}_s{step}_isw"] = np.asarray(isw).reshape(-1)
+            # priority write-back, float32 like abs_error from torch (dqn_per.py:132-139)
+            new_p = rng.exponential(size=b).astype(np.float32)
+            buf.update_priority(new_p, np.asarray(index).reshape(-1))
+            out[f"{tag}_s{step}_newp"] = new_p
+            out[f"{tag}_s{step}_tree_after"] = buf.wt_tree.weights.copy()
+        # store without priorities -> normalize(max_leaf)   (prioritized_buffer.py:302-305)
+        buf.store_episode(_episode(3, 4, rng))
+        out[f"{tag}_tree_after_default_store"] = buf.wt_tree.weights.copy()
+    np.savez_compressed(os.path.join(OUT, "ref_per.npz"), **out)
+
+
+# --------------------------------------------------------------------------- TD (DQNPer / DDPGPer)
+class _QNet(t.nn.Module):
+    def __init__(self, s, a, h=16):
+        super().__init__()
+        self.fc1 = t.nn.Linear(s, h)
+        self.fc2 = t.nn.Linear(h, h)
+        self.fc3 = t.nn.Linear(h, a)
+
+    def forward(self, state):
+        x = t.relu(self.fc1(state))
+        return self.fc3(t.relu(self.fc2(x)))
+
+
+class _Actor(t.nn.Module):
+    def __init__(self, s, a, h=16):
+        super().__init__()
+        self.fc1 = t.nn.Linear(s, h)
+        self.fc2 = t.nn.Linear(h, a)
+
+    def forward(self, state):
+        return t.tanh(self.fc2(t.relu(self.fc1(state))))
+
+
+class _Critic(t.nn.Module):
+    def __init__(self, s, a, h=16):
+        super().__init__()
+        self.fc1 = t.nn.Linear(s + a, h)
+        self.fc2 = t.nn.Linear(h, 1)
+
+    def forward(self, state, action):
+        return self.fc2(t.relu(self.fc1(t.cat([state, action], dim=1))))
+
+
+def _flat_params(m):
+    return np.concatenate([p.detach().numpy().reshape(-1) for p in m.parameters()])
+
+
+def gen_td():
+    from machin.frame.algorithms import DQNPer, DDPGPer
+    from machin.model.nets.base import static_module_wrapper as smw
+
+    out = {}
+    # ---- double-DQN with PER; SGD so that the whole step is reproducible elsewhere
+    seed_all(0)
+    S, A, N, B = 6, 4, 200, 32
+    qnet, qtgt = _QNet(S, A), _QNet(S, A)
+    dqn = DQNPer(smw(qnet, "cpu", "cpu"), smw(qtgt, "cpu", "cpu"), t.optim.SGD,
+                 t.nn.MSELoss(reduction="sum"), batch_size=B, learning_rate=0.01,
+                 discount=0.97, update_rate=0.05, replay_size=N, mode="double")
+    # the ctor copies the TARGET net into the online net (dqn.py:198-200), so save after it
+    out["dqn_init_q"] = _flat_params(dqn.qnet)
+    out["dqn_init_qt"] = _flat_params(dqn.qnet_target)
+    rng = np.random.RandomState(5)
+    st = rng.randn(N, S).astype(np.float32)
+    nst = rng.randn(N, S).astype(np.float32)
+    act = rng.randint(0, A, size=N).astype(np.int64)
+    rew = rng.randn(N).astype(np.float32)
+    term = rng.rand(N) < 0.2
+    pri = rng.exponential(size=N)
+    ep = [dict(state={"state": t.from_numpy(st[i:i + 1])}, action={"action": t.tensor([[act[i]]])},
+               next_state={"state": t.from_numpy(nst[i:i + 1])}, reward=float(rew[i]),
+               terminal=bool(term[i])) for i in range(N)]
+    dqn.replay_buffer.store_episode(ep, priorities=list(pri))
+    out.update(dqn_state=st, dqn_next_state=nst, dqn_action=act, dqn_reward=rew,
+               dqn_terminal=term, dqn_priority=pri, dqn_tree0=dqn.replay_buffer.wt_tree.weights.copy())
+    seed_all(11)
+    for step in range(3):
+        s0 = np.random.get_state()
+        out[f"dqn_u{step}"] = np.random.uniform(size=B)
+        np.random.set_state(s0)
+        loss = dqn.update()
+        out[f"dqn_loss{step}"] = np.float64(loss)
+        out[f"dqn_tree{step + 1}"] = dqn.replay_buffer.wt_tree.weights.copy()
+        out[f"dqn_q{step + 1}"] = _flat_params(dqn.qnet)
+        out[f"dqn_qt{step + 1}"] = _flat_params(dqn.qnet_target)
+
+    # ---- DDPG with PER
+    seed_all(0)
+    S, A, N, B = 5, 2, 150, 16
+    actor, actor_t, critic, critic_t = _Actor(S, A), _Actor(S, A), _Critic(S, A), _Critic(S, A)
+    ddpg = DDPGPer(smw(actor, "cpu", "cpu"), smw(actor_t, "cpu", "cpu"),
+                   smw(critic, "cpu", "cpu"), smw(critic_t, "cpu", "cpu"), t.optim.SGD,
+                   t.nn.MSELoss(reduction="sum"), batch_size=B, actor_learning_rate=0.005,
+                   critic_learning_rate=0.01, discount=0.95, update_rate=0.1, replay_size=N)
+    # ctor copies target -> online (ddpg.py:160-162)
+    out["ddpg_init_actor"] = _flat_params(ddpg.actor)
+    out["ddpg_init_critic"] = _flat_params(ddpg.critic)
+    out["ddpg_init_actor_t"] = _flat_params(ddpg.actor_target)
+    out["ddpg_init_critic_t"] = _flat_params(ddpg.critic_target)
+    rng = np.random.RandomState(6)
+    st = rng.randn(N, S).astype(np.float32)
+    nst = rng.randn(N, S).astype(np.float32)
+    act = rng.uniform(-1, 1, size=(N, A)).astype(np.float32)
+    rew = rng.randn(N).astype(np.float32)
+    term = rng.rand(N) < 0.2
+    pri = rng.exponential(size=N)
+    ep = [dict(state={"state": t.from_numpy(st[i:i + 1])}, action={"action": t.from_numpy(act[i:i + 1])},
+               next_state={"state": t.from_numpy(nst[i:i + 1])}, reward=float(rew[i]),
+               terminal=bool(term[i])) for i in range(N)]
+    ddpg.replay_buffer.store_episode(ep, priorities=list(pri))
+    out.update(ddpg_state=st, ddpg_next_state=nst, ddpg_action=act, ddpg_reward=rew,
+               ddpg_terminal=term, ddpg_priority=pri)
+    seed_all(12)
+    for step in range(3):
+        s0 = np.random.get_state()
+        out[f"ddpg_u{step}"] = np.random.uniform(size=B)
+        np.random.set_state(s0)
+        pol, val = ddpg.update()
+        out[f"ddpg_loss{step}"] = np.array([pol, val], dtype=np.float64)
+        out[f"ddpg_tree{step + 1}"] = ddpg.replay_buffer.wt_tree.weights.copy()
+        out[f"ddpg_actor{step + 1}"] = _flat_params(ddpg.actor)
+        out[f"ddpg_critic{step + 1}"] = _flat_params(ddpg.critic)
+        out[f"ddpg_actor_t{step + 1}"] = _flat_params(ddpg.actor_target)
+        out[f"ddpg_critic_t{step + 1}"] = _flat_params(ddpg.critic_target)
+    np.savez_compressed(os.path.join(OUT, "ref_td.npz"), **out)
+
+
+# --------------------------------------------------------------------------- V-trace (IMPALA)
+class _FakeFuture:
+    def __init__(self, v):
+        self.v = v
+
+    def wait(self):
+        return self.v
+
+
+class FakeGroup:
+    """In-process stand-in for RpcGroup: numeric comparison only."""
+
+    def __init__(self):
+        self.services = {}
+
+    def is_member(self, target=None):
+        return True
+
+    def get_cur_name(self):
+        return "0"
+
+    def get_group_members(self):
+        return ["0"]
+
+    def size(self):
+        return 1
+
+    def register(self, key, fn):
+        self.services[key] = fn
+
+    def registered_async(self, key, args=(), kwargs=None):
+        return _FakeFuture(self.services[key](*args, **(kwargs or {})))
+
+    def registered_sync(self, key, args=(), kwargs=None):
+        return self.services[key](*args, **(kwargs or {}))
+
+
+class _NoServer:
+    def push(self, model, pull_on_fail=True):
+        return True
+
+    def pull(self, model):
+        return True
+
+
+class _PolicyNet(t.nn.Module):
+    def __init__(self, s, a, h=16):
+        super().__init__()
+        self.fc1 = t.nn.Linear(s, h)
+        self.fc2 = t.nn.Linear(h, a)
+
+    def forward(self, state, action=None):
+        from torch.distributions import Categorical
+        probs = t.softmax(self.fc2(t.relu(self.fc1(state))), dim=1)
+        dist = Categorical(probs=probs)
+        act = action if action is not None else dist.sample()
+        ent = dist.entropy()
+        logp = dist.log_prob(act.flatten())
+        return act.view(-1, 1), logp.view(-1, 1), ent.view(-1, 1)
+
+
+class _ValueNet(t.nn.Module):
+    def __init__(self, s, h=16):
+        super().__init__()
+        self.fc1 = t.nn.Linear(s, h)
+        self.fc2 = t.nn.Linear(h, 1)
+
+    def forward(self, state):
+        return self.fc2(t.relu(self.fc1(state)))
+
+
+def gen_vtrace():
+    from machin.frame.algorithms import IMPALA
+    from machin.model.nets.base import static_module_wrapper as smw
+
+    out = {}
+    for tag, lengths, clip_c, clip_rho in (("fixed", [20] * 12, 1.0, 1.0),
+                                           ("ragged", [1, 7, 2, 33, 5, 1, 12, 40, 3], 0.9, 1.3)):
+        seed_all(0)
+        S, A = 8, 3
+        actor, critic = _PolicyNet(S, A), _ValueNet(S)
+        out[f"{tag}_actor0"] = _flat_params(actor)
+        out[f"{tag}_critic0"] = _flat_params(critic)
+        captured = {}
+
+        def criterion(value, vs, _c=captured):
+            _c["value"] = value.detach().clone()
+            _c["vs"] = vs.detach().clone()
+            return ((value - vs) ** 2).sum()
+
+        imp = IMPALA(smw(actor, "cpu", "cpu"), smw(critic, "cpu", "cpu"), t.optim.SGD, criterion,
+                     FakeGroup(), (_NoServer(),), batch_size=len(lengths), learning_rate=0.01,
+                     isw_clip_c=clip_c, isw_clip_rho=clip_rho, discount=0.98,
+                     replay_size=4 * sum(lengths))
+        rng = np.random.RandomState(21)
+        total = sum(lengths)
+        st = rng.randn(total, S).astype(np.float32)
+        nst = rng.randn(total, S).astype(np.float32)
+        act = rng.randint(0, A, size=total).astype(np.int64)
+        rew = rng.randn(total).astype(np.float32)
+        logmu = (-rng.exponential(size=total)).astype(np.float32)
+        term = np.zeros(total, dtype=bool)
+        pos = 0
+        episodes = []
+        for n in lengths:
+            term[pos + n - 1] = True
+            episodes.append([dict(state={"state": t.from_numpy(st[i:i + 1])},
+                                  action={"action": t.tensor([[act[i]]])},
+                                  next_state={"state": t.from_numpy(nst[i:i + 1])},
+                                  reward=float(rew[i]), action_log_prob=float(logmu[i]),
+                                  terminal=bool(term[i])) for i in range(pos, pos + n)])
+            pos += n
+        for ep in episodes:
+            imp.store_episode(ep)
+        # IMPALABuffer samples episodes with random.choices (impala.py:58): record the picks
+        seed_all(3)
+        s0 = random.getstate()
+        picks = random.choices(range(len(lengths)), k=len(lengths))
+        random.setstate(s0)
+        pol, val = imp.update()
+        out.update({f"{tag}_lengths": np.array(lengths), f"{tag}_state": st, f"{tag}_next_state": nst,
+                    f"{tag}_action": act, f"{tag}_reward": rew, f"{tag}_logmu": logmu,
+                    f"{tag}_terminal": term, f"{tag}_picks": np.array(picks),
+                    f"{tag}_clip": np.array([clip_c, clip_rho, 0.98]),
+                    f"{tag}_value": captured["value"].numpy().reshape(-1),
+                    f"{tag}_vs": captured["vs"].numpy().reshape(-1),
+                    f"{tag}_losses": np.array([pol, val], dtype=np.float64),
+                    f"{tag}_actor1": _flat_params(imp.actor), f"{tag}_critic1": _flat_params(imp.critic)})
+    np.savez_compressed(os.path.join(OUT, "ref_vtrace.npz"), **out)
+
+
+# --------------------------------------------------------------------------- GAE (A2C / A3C)
+def gen_gae():
+    from machin.frame.algorithms import A2C
+    from machin.model.nets.base import static_module_wrapper as smw
+
+    out = {}
+    for lam in (1.0, 0.0, 0.95):
+        seed_all(0)
+        S, A = 8, 3
+        actor, critic = _PolicyNet(S, A), _ValueNet(S)
+        out[f"critic0"] = _flat_params(critic)
+        a2c = A2C(smw(actor, "cpu", "cpu"), smw(critic, "cpu", "cpu"), t.optim.SGD,
+                  t.nn.MSELoss(reduction="sum"), batch_size=8, discount=0.97, gae_lambda=lam)
+        rng = np.random.RandomState(31)
+        for e, n in enumerate((1, 2, 9, 30)):
+            st = rng.randn(n, S).astype(np.float32)
+            nst = rng.randn(n, S).astype(np.float32)
+            rew = rng.randn(n).astype(np.float32)
+            term = np.zeros(n, dtype=bool)
+            term[-1] = e % 2 == 0
+            ep = [dict(state={"state": t.from_numpy(st[i:i + 1])}, action={"action": t.tensor([[0]])},
+                       next_state={"state": t.from_numpy(nst[i:i + 1])}, reward=float(rew[i]),
+                       terminal=bool(term[i])) for i in range(n)]
+            a2c.store_episode(ep)
+            key = f"lam{lam}_ep{e}"
+            out[f"{key}_state"] = st
+            out[f"{key}_next_state"] = nst
+            out[f"{key}_reward"] = rew
+            out[f"{key}_terminal"] = term
+            out[f"{key}_value"] = np.array([tr["value"] for tr in ep], dtype=np.float64)
+            out[f"{key}_gae"] = np.array([tr["gae"] for tr in ep], dtype=np.float64)
+            with t.no_grad():
+                out[f"{key}_critic_v"] = critic(t.from_numpy(st)).numpy().reshape(-1)
+                out[f"{key}_critic_nv"] = critic(t.from_numpy(nst)).numpy().reshape(-1)
+    np.savez_compressed(os.path.join(OUT, "ref_gae.npz"), **out)
+
+
+if __name__ == "__main__":
+    ref_shim.load()
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ["tree", "per", "td", "vtrace", "gae"]
+    for name in which:
+        globals()["gen_" + name]()
+        print("wrote", name)
