@@ -1,0 +1,216 @@
+/*
+ * machin_b200.h -- C ABI of libmachin_b200.so: the B200 (sm_100a) learner hot path of
+ * iffiX/machin's massively parallel algorithms (APEX-DQN / APEX-DDPG / IMPALA / A3C).
+ *
+ * The reference has no FFI: the path lives behind Python classes.
+ * Each entry point below is what a binding for that class/method would call; the
+ * reference interface it replaces is cited as file:line relative to the reference root.
+ * INTEGRATION.md shows the ctypes stub a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary
+ *   - every function returns an int status: MB_OK (0) or a negative mb_status
+ *   - pointers named d_* are DEVICE pointers (on the device the handle / call names),
+ *     pointers named h_* are HOST pointers
+ *   - device entry points are asynchronous on `stream` (a cudaStream_t passed as void*;
+ *     NULL = the legacy default stream) and never synchronise unless stated
+ *   - *_host entry points take host buffers, stage them through pinned memory, run the same
+ *     kernels and block until the results are in the caller's host buffers
+ *   - no internal locking: callers serialise access to one handle (the reference keeps an
+ *     RLock around buffer mutation, prioritized_buffer_d.py:109)
+ */
+#ifndef MACHIN_B200_H
+#define MACHIN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_ABI_VERSION 1
+
+typedef enum mb_status {
+    MB_OK = 0,
+    MB_ERR_CUDA = -1,          /* a CUDA runtime call failed; see mb_last_cuda_error()             */
+    MB_ERR_INDEX_OOB = -2,     /* ValueError("Index has elements out of boundary!")   :90,136,173  */
+    MB_ERR_DIM_MISMATCH = -3,  /* ValueError("Dimension of weights and indexes doesn't match!") :165 */
+    MB_ERR_SIZE_MISMATCH = -4, /* ValueError("Weights size must match tree size!")    :197         */
+    MB_ERR_INVALID = -5,       /* bad argument (NULL handle, negative count, unsupported dtype)     */
+    MB_ERR_NOMEM = -6,         /* device or pinned allocation failed                               */
+    MB_ERR_NO_DEVICE = -7      /* no CUDA device: the product path never falls back to the CPU      */
+} mb_status;
+
+typedef enum mb_dtype { MB_F32 = 0, MB_F64 = 1 } mb_dtype;
+
+int mb_abi_version(void);
+const char *mb_status_string(int status);
+const char *mb_last_cuda_error(void);
+int mb_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Sum tree  (machin/frame/buffers/prioritized_buffer.py:8-231, class WeightTree)
+ *
+ * Device-resident float64 tree in the reference's flattened layout: level 0 (leaves, padded
+ * to a power of two) first, root last; depth = ceil(log2(size)) + 1; 2^depth - 1 nodes.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mb_tree mb_tree;
+
+/* WeightTree.__init__ (:13-52).  Allocates and zeroes the tree on `device`. */
+int mb_tree_create(int64_t size, int device, mb_tree **out);
+int mb_tree_destroy(mb_tree *tree);
+/* depth / padded leaf count / node count of the flattened array (attributes depth, sizes, offsets). */
+int mb_tree_geometry(const mb_tree *tree, int64_t *size, int *depth, int64_t *n_leaf_padded,
+                     int64_t *n_nodes);
+/* device pointer to the flattened float64 node array (attribute `weights`, :52) */
+double *mb_tree_weights(mb_tree *tree);
+/* get_weight_sum / get_leaf_max (:54-66).  Blocks on `stream`, then returns both scalars. */
+int mb_tree_stats(mb_tree *tree, double *h_weight_sum, double *h_max_leaf, void *stream);
+/* device pointers to the root node and to the running leaf maximum (no sync) */
+const double *mb_tree_root_ptr(mb_tree *tree);
+const double *mb_tree_max_leaf_ptr(mb_tree *tree);
+/* Deferred error of asynchronous device-side index validation: returns MB_OK or
+ * MB_ERR_INDEX_OOB (and clears it).  Blocks on `stream`. */
+int mb_tree_check(mb_tree *tree, void *stream);
+/* zero all nodes, max_leaf = 0 (PrioritizedBuffer.clear builds a fresh tree, :311-317) */
+int mb_tree_clear(mb_tree *tree, void *stream);
+
+/* update_all_leaves + _build (:188-199, :216-231).  d_leaves: f64[n], n must equal size
+ * (else MB_ERR_SIZE_MISMATCH).  d_leaves == NULL rebuilds from the leaves already in place. */
+int mb_tree_build(mb_tree *tree, const double *d_leaves, int64_t n, void *stream);
+/* find_leaf_index (:96-125).  d_query f64[n] -> d_index i64[n]. */
+int mb_tree_find(mb_tree *tree, const double *d_query, int64_t n, int64_t *d_index, void *stream);
+/* get_leaf_weight (:76-94).  d_index i64[n] -> d_weight f64[n]; out-of-range indexes raise the
+ * deferred MB_ERR_INDEX_OOB (see mb_tree_check) and read as 0. */
+int mb_tree_leaf_weight(mb_tree *tree, const int64_t *d_index, int64_t n, double *d_weight,
+                        void *stream);
+/* update_leaf_batch (:152-186).  d_weight is f32[n] or f64[n] (weight_dtype); duplicates in
+ * d_index resolve last-write-wins like NumPy fancy assignment (:178); parents are recomputed
+ * as left + right (:184-186), so the node array is bit-identical to the reference's.
+ * If any index is out of [0, size) nothing is written and the deferred error is raised.
+ * d_valid (nullable, u8[n]): entries with 0 are skipped -- the version filter of
+ * DistributedPrioritizedBuffer._update_priority_service (prioritized_buffer_d.py:282-291). */
+int mb_tree_update_batch(mb_tree *tree, const int64_t *d_index, const void *d_weight,
+                         int weight_dtype, const uint8_t *d_valid, int64_t n, void *stream);
+/* PrioritizedBuffer.update_priority (:319-328): w = (|p| + epsilon) ** alpha evaluated in the
+ * dtype of p (_normalize_priority, :430-434), then update_leaf_batch.  */
+int mb_tree_update_priority(mb_tree *tree, const int64_t *d_index, const void *d_priority,
+                            int priority_dtype, const uint8_t *d_valid, int64_t n, double epsilon,
+                            double alpha, void *stream);
+/* update_leaf (:127-150): one leaf, path to root.  Host scalars; asynchronous. */
+int mb_tree_update_leaf(mb_tree *tree, double weight, int64_t index, void *stream);
+
+/* PrioritizedBuffer.sample_index_and_weight (:397-428), fused: stratified query from the
+ * caller's uniforms (the reference draws them with np.random.uniform, :411), descent, leaf
+ * weight, importance weight (n_stored * p / total) ** -beta, max-normalised.
+ *   d_uniform   f64[n] in [0,1)        d_index i64[n]      d_is_weight f64[n]
+ *   all_weight_sum <= 0 means "use the local root" (`all_weight_sum or ...`, :421)
+ *   d_params (nullable) overrides the three scalars from device memory so that the call can be
+ *   replayed inside a CUDA graph while beta / n_stored change. */
+typedef struct mb_per_params {
+    double beta;
+    double all_weight_sum;
+    int64_t n_stored;
+    int64_t step; /* which row of a [steps, n] uniform table to read (graph replay), else 0 */
+} mb_per_params;
+int mb_per_sample(mb_tree *tree, const double *d_uniform, int64_t n, int64_t n_stored,
+                  double all_weight_sum, double beta, const mb_per_params *d_params,
+                  int64_t *d_index, double *d_is_weight, void *stream);
+
+/* Host-buffer variants (same kernels; H2D + launch + D2H + synchronise inside the call). */
+int mb_tree_build_host(mb_tree *tree, const double *h_leaves, int64_t n);
+int mb_tree_find_host(mb_tree *tree, const double *h_query, int64_t n, int64_t *h_index);
+int mb_tree_leaf_weight_host(mb_tree *tree, const int64_t *h_index, int64_t n, double *h_weight);
+int mb_tree_update_batch_host(mb_tree *tree, const int64_t *h_index, const void *h_weight,
+                              int weight_dtype, int64_t n);
+int mb_tree_read_host(mb_tree *tree, int64_t first_node, int64_t n_nodes, double *h_out);
+int mb_per_sample_host(mb_tree *tree, const double *h_uniform, int64_t n, int64_t n_stored,
+                       double all_weight_sum, double beta, int64_t *h_index, double *h_is_weight);
+
+/* ------------------------------------------------------------------------------------------
+ * Replay rows  (batch assembly: prioritized_buffer.py:390-394 + buffer.py:261-353,380-413;
+ *               ring insert: storage.py:85-114)
+ *
+ * The device ring is an array of packed rows, `pitch` bytes apart (multiple of 16).  A field is
+ * one attribute of the transition (state["k"], action["k"], reward, terminal, ...).
+ * ------------------------------------------------------------------------------------------ */
+#define MB_MAX_FIELDS 16
+typedef struct mb_field {
+    int64_t row_offset; /* byte offset of the field inside a packed row                       */
+    int64_t nbytes;     /* bytes of the field per transition                                   */
+    void *d_dense;      /* dense [n, nbytes] tensor: gather destination / scatter source       */
+    int64_t dense_pitch;/* bytes between consecutive rows of d_dense (normally == nbytes)      */
+} mb_field;
+
+/* dense[i, :] = ring[index[i], field]   for every field ("[storage[i] for i in index]" + t.cat) */
+int mb_rows_gather(const void *d_ring, int64_t pitch, int64_t capacity, const int64_t *d_index,
+                   int64_t n, const mb_field *fields, int n_fields, void *stream);
+/* ring[(first_slot + i) % capacity, field] = dense[i, :]   (TransitionStorageBasic.store_episode) */
+int mb_rows_scatter(void *d_ring, int64_t pitch, int64_t capacity, int64_t first_slot, int64_t n,
+                    const mb_field *fields, int n_fields, void *stream);
+/* whole packed rows: out[i, :pitch] = ring[index[i], :]  (wire format of the shard exchange) */
+int mb_rows_gather_packed(const void *d_ring, int64_t pitch, int64_t capacity,
+                          const int64_t *d_index, int64_t n, void *d_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * TD target / priority math
+ * ------------------------------------------------------------------------------------------ */
+/* DQNPer.update value block (dqn_per.py:105-139, dqn.py:497-501), float32:
+ *   a* = argmax_a q_next[b,:] (first maximum) ; y = reward + (discount * !terminal) * q_tgt_next[b,a*]
+ *   action_value = q[b, action[b]] ; abs_error = |action_value - y|
+ *   loss_elem = (action_value - y)^2 * is_weight (float64, MSE criterion) ; d_q = dloss/dq for
+ *   loss = mean(loss_elem) (nullable).  mode: 0 = "double", 1 = "fixed_target"/"vanilla"
+ *   (a* = argmax of q_tgt_next).  Any output pointer may be NULL. */
+int mb_td_dqn(const float *d_q, const float *d_q_next, const float *d_q_tgt_next, int64_t batch,
+              int n_actions, const int64_t *d_action, const float *d_reward,
+              const uint8_t *d_terminal, const double *d_is_weight, float discount, int mode,
+              float *d_y, float *d_action_value, float *d_abs_error, double *d_loss_elem,
+              float *d_grad_q, void *stream);
+/* DDPGPer target + priority (ddpg_per.py:117-160, ddpg.py:506-510):
+ *   y = reward + (discount * !terminal) * next_value ; abs_error = |value - y| (value nullable) */
+int mb_td_target(const float *d_next_value, const float *d_reward, const uint8_t *d_terminal,
+                 int64_t batch, float discount, const float *d_value, float *d_y,
+                 float *d_abs_error, void *stream);
+/* soft_update (algorithms/utils.py:8-27): target = target * (1 - rate) + source * rate, over a
+ * flat float32 parameter block */
+int mb_soft_update(float *d_target, const float *d_source, int64_t n, double rate, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Trajectory reverse scans
+ * ------------------------------------------------------------------------------------------ */
+/* IMPALA V-trace (impala.py:322-362), float32.  Steps are flattened episode-major; episode e
+ * covers [d_offsets[e], d_offsets[e+1]).  d_offsets == NULL means n_episodes equal episodes of
+ * n_steps / n_episodes steps.
+ *   sim = exp(log_pi - log_mu) ; c = min(clip_c, sim) ; rho = min(clip_rho, sim)
+ *   delta = rho * (reward + discount * (terminal ? 0 : next_value) - value)
+ *   vs[i] = value[i] + delta[i] + discount * c[i] * (vs[i+1] - value[i+1]),  vs[last] = 0
+ *   vss[i] = vs[i+1], vss[last] = 0 ; adv = reward + discount * vss - value
+ * Outputs (each nullable): vs, vss, rho, adv. */
+int mb_vtrace(const int64_t *d_offsets, int64_t n_episodes, int64_t n_steps, const float *d_value,
+              const float *d_next_value, const float *d_reward, const uint8_t *d_terminal,
+              const float *d_log_pi, const float *d_log_mu, float discount, float clip_c,
+              float clip_rho, float *d_vs, float *d_vss, float *d_rho, float *d_adv, void *stream);
+/* A2C/A3C discounted return + GAE (a2c.py:275-313), float64 like the reference's Python floats:
+ *   ret[last] = r[last] ; ret[i-1] = ret[i] * discount + r[i-1]
+ *   lambda == 1: gae = ret - V(s) ; lambda == 0: gae = r + discount*(1-term)*V(s') - V(s)
+ *   else reverse recurrence with V_prev / A_prev (a2c.py:296-313).
+ * critic values are float32 (what critic(state).item() widens).  */
+int mb_gae(const int64_t *d_offsets, int64_t n_episodes, int64_t n_steps, const double *d_reward,
+           const uint8_t *d_terminal, const float *d_critic_value,
+           const float *d_next_critic_value, double discount, double gae_lambda,
+           double *d_returns, double *d_gae, void *stream);
+
+int mb_vtrace_host(int device, const int64_t *h_offsets, int64_t n_episodes, int64_t n_steps,
+                   const float *h_value, const float *h_next_value, const float *h_reward,
+                   const uint8_t *h_terminal, const float *h_log_pi, const float *h_log_mu,
+                   float discount, float clip_c, float clip_rho, float *h_vs, float *h_vss,
+                   float *h_rho, float *h_adv);
+int mb_gae_host(int device, const int64_t *h_offsets, int64_t n_episodes, int64_t n_steps,
+                const double *h_reward, const uint8_t *h_terminal, const float *h_critic_value,
+                const float *h_next_critic_value, double discount, double gae_lambda,
+                double *h_returns, double *h_gae);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MACHIN_B200_H */

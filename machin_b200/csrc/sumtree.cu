@@ -1,0 +1,732 @@
+// Device-resident sum tree + fused PER draw for sm_100a.
+//
+// Replaces machin/frame/buffers/prioritized_buffer.py:8-231 (WeightTree) and :397-434
+// (PrioritizedBuffer.sample_index_and_weight / _normalize_priority) on the learner hot path.
+//
+// HBM layout: ONE float64 array in the reference's flattened order -- level 0 (leaves, padded
+// to 2^(depth-1)) first, root last.  With T = 2^depth, level l starts at T - (T >> l) and has
+// T >> (l+1) nodes, so every level start is a multiple of 2^(depth-l) elements: any 2^J-child
+// group is naturally 8*2^J-byte aligned and a 16-child group is exactly one 128-byte line.
+//
+// Invariant kept by every mutator here (and by every mutator of the reference): each parent
+// holds fl(left + right) of its stored children.  The descent kernel relies on it to jump
+// several levels per dependent load: it fetches the 2^J descendants of the current node and
+// re-derives the intermediate sums with the same pairwise additions, which reproduces the
+// stored intermediate nodes bit-for-bit, then applies the reference's per-level comparisons.
+#include <cooperative_groups.h>
+
+#include <new>
+
+#include "mb_common.cuh"
+
+namespace cg = cooperative_groups;
+
+struct TreeState {
+    double max_leaf;   // running maximum leaf weight (WeightTree.max_leaf)
+    double isw_max;    // scratch: max importance weight of the draw in flight
+    int err;           // deferred device-side validation error (mb_status), sticky until checked
+    int err_gen;       // launch generation that raised it (so later launches are not skipped)
+};
+
+struct TreeDev {
+    double *W;
+    int *owner;        // per-leaf "last writer" stamp used to resolve duplicate indexes
+    TreeState *st;
+    int64_t size;      // number of real leaves
+    int64_t total;     // 2^depth
+    int depth;
+};
+
+struct mb_tree {
+    int device;
+    TreeDev dev;
+    int64_t n_leaf_pad;
+    int64_t n_nodes;
+    TreeState *h_state;  // pinned mirror for mb_tree_stats / mb_tree_check
+    int coop_blocks;     // co-resident CTAs for the cooperative update kernel
+    int gen;             // update-launch generation counter
+};
+
+namespace {
+
+__device__ __forceinline__ int64_t level_off(const TreeDev &t, int l) { return t.total - (t.total >> l); }
+
+__device__ __forceinline__ void atomic_max_f64(double *addr, double v) {
+    unsigned long long *a = reinterpret_cast<unsigned long long *>(addr);
+    unsigned long long old = *a;
+    while (v > __longlong_as_double((long long)old)) {
+        unsigned long long assumed = old;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+
+__device__ __forceinline__ double2 ld_nc2(const double *p) {
+    return __ldg(reinterpret_cast<const double2 *>(p));
+}
+
+// ---------------------------------------------------------------------------------------------
+// build  (update_all_leaves + _build, prioritized_buffer.py:188-199, 216-231)
+// ---------------------------------------------------------------------------------------------
+__global__ void tree_state_reset(TreeState *st, double max_leaf) { st->max_leaf = max_leaf; }
+
+// One pass lifts 11 levels.  CTA = 256 threads x 8 source nodes = 2048 nodes of level `lv`.
+// Reads 8 B/node once, writes every produced level once: ~16 B per source node in total.
+__global__ void __launch_bounds__(256) tree_build_pass(TreeDev t, int lv, const double *src_leaves) {
+    __shared__ double warp_tot[8];
+    __shared__ double warp_mx[8];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t gthread = (int64_t)blockIdx.x * 256 + tid;
+    const int64_t base = gthread * 8;
+    double *src = t.W + level_off(t, lv) + base;
+    double v[8];
+    if (lv == 0 && src_leaves != nullptr) {
+        double mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int64_t i = base + k;
+            v[k] = (i < t.size) ? __ldg(src_leaves + i) : src[k];
+            if (i < t.size) mx = fmax(mx, v[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) *reinterpret_cast<double2 *>(src + k) = make_double2(v[k], v[k + 1]);
+        mx = mb::warp_max(mx);
+        if (lane == 0) warp_mx[wid] = mx;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            double2 a = __ldcg(reinterpret_cast<const double2 *>(src + k));
+            v[k] = a.x;
+            v[k + 1] = a.y;
+        }
+        if (lv == 0) {
+            double mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (base + k < t.size) mx = fmax(mx, v[k]);
+            mx = mb::warp_max(mx);
+            if (lane == 0) warp_mx[wid] = mx;
+        }
+    }
+    // levels lv+1 .. lv+3 inside the thread
+    double a1[4], a2[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a1[k] = v[2 * k] + v[2 * k + 1];
+    a2[0] = a1[0] + a1[1];
+    a2[1] = a1[2] + a1[3];
+    double x = a2[0] + a2[1];
+    double *l1 = t.W + level_off(t, lv + 1) + gthread * 4;
+    *reinterpret_cast<double2 *>(l1) = make_double2(a1[0], a1[1]);
+    *reinterpret_cast<double2 *>(l1 + 2) = make_double2(a1[2], a1[3]);
+    *reinterpret_cast<double2 *>(t.W + level_off(t, lv + 2) + gthread * 2) = make_double2(a2[0], a2[1]);
+    t.W[level_off(t, lv + 3) + gthread] = x;
+    // levels lv+4 .. lv+8 across the warp (a + b == b + a bitwise, so every lane gets the node)
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        x = x + __shfl_xor_sync(0xffffffffu, x, 1 << s);
+        if ((lane & ((2 << s) - 1)) == 0) t.W[level_off(t, lv + 4 + s) + (gthread >> (s + 1))] = x;
+    }
+    if (lane == 0) warp_tot[wid] = x;
+    __syncthreads();
+    if (tid == 0) {
+        // levels lv+9 .. lv+11 across the 8 warps
+        const int64_t cta = blockIdx.x;
+        double b0 = warp_tot[0] + warp_tot[1], b1 = warp_tot[2] + warp_tot[3];
+        double b2 = warp_tot[4] + warp_tot[5], b3 = warp_tot[6] + warp_tot[7];
+        double *l9 = t.W + level_off(t, lv + 9) + cta * 4;
+        l9[0] = b0; l9[1] = b1; l9[2] = b2; l9[3] = b3;
+        double c0 = b0 + b1, c1 = b2 + b3;
+        double *l10 = t.W + level_off(t, lv + 10) + cta * 2;
+        l10[0] = c0; l10[1] = c1;
+        t.W[level_off(t, lv + 11) + cta] = c0 + c1;
+        if (lv == 0) {
+            double mx = warp_mx[0];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) mx = fmax(mx, warp_mx[k]);
+            atomic_max_f64(&t.st->max_leaf, mx);
+        }
+    }
+}
+
+// Remaining levels (fewer than 2048 source nodes): one CTA, level by level.
+__global__ void __launch_bounds__(1024) tree_build_top(TreeDev t, int lv, const double *src_leaves) {
+    __shared__ double red[32];
+    const int tid = threadIdx.x;
+    if (lv == 0) {
+        double mx = -INFINITY;
+        for (int64_t i = tid; i < t.size; i += blockDim.x) {
+            double x = src_leaves ? __ldg(src_leaves + i) : __ldcg(t.W + i);
+            if (src_leaves) t.W[i] = x;
+            mx = fmax(mx, x);
+        }
+        mx = mb::warp_max(mx);
+        if ((tid & 31) == 0) red[tid >> 5] = mx;
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 1; k < (int)(blockDim.x >> 5); ++k) mx = fmax(mx, red[k]);
+            atomic_max_f64(&t.st->max_leaf, mx);
+        }
+    }
+    for (int l = lv + 1; l < t.depth; ++l) {
+        __syncthreads();
+        const int64_t n = t.total >> (l + 1);
+        const double *below = t.W + level_off(t, l - 1);
+        double *here = t.W + level_off(t, l);
+        for (int64_t j = tid; j < n; j += blockDim.x) here[j] = __ldcg(below + 2 * j) + __ldcg(below + 2 * j + 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// descent  (find_leaf_index, prioritized_buffer.py:96-125)
+// ---------------------------------------------------------------------------------------------
+// Descend J levels from node `idx` whose 2^J descendants start at W[child_off + idx * 2^J].
+template <int J>
+__device__ __forceinline__ void descend(const double *__restrict__ W, int64_t child_off, int64_t &idx, double &w) {
+    constexpr int N = 1 << J;
+    double tr[2 * N];  // heap order: tr[1] = current node, tr[N + k] = k-th descendant
+    const double *p = W + child_off + idx * N;
+#pragma unroll
+    for (int k = 0; k < N; k += 2) {
+        double2 a = ld_nc2(p + k);
+        tr[N + k] = a.x;
+        tr[N + k + 1] = a.y;
+    }
+#pragma unroll
+    for (int i = N - 1; i >= 2; --i) tr[i] = tr[2 * i] + tr[2 * i + 1];
+    int rel = 0;  // position inside the current level of the mini tree
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        double left = 0.0;
+#pragma unroll
+        for (int m = 0; m < (1 << j); ++m)
+            if (m == rel) left = tr[2 * ((1 << j) + m)];
+        const bool right = w > left;  // strict, like `weight > left_wt` (:117)
+        if (right) w = w - left;      // `weight - left_wt * select` (:119)
+        rel = 2 * rel + (right ? 1 : 0);
+    }
+    idx = idx * N + rel;
+}
+
+__device__ __forceinline__ int64_t tree_find_one(const TreeDev &t, double w) {
+    int64_t idx = 0;
+    int remaining = t.depth - 1;  // levels to descend
+    const int head = remaining & 3;
+    if (head == 1) descend<1>(t.W, level_off(t, remaining - 1), idx, w);
+    else if (head == 2) descend<2>(t.W, level_off(t, remaining - 2), idx, w);
+    else if (head == 3) descend<3>(t.W, level_off(t, remaining - 3), idx, w);
+    remaining -= head;
+    while (remaining > 0) {
+        remaining -= 4;
+        descend<4>(t.W, level_off(t, remaining), idx, w);
+    }
+    return min(max(idx, (int64_t)0), t.size - 1);  // np.clip(index, 0, size - 1) (:120)
+}
+
+__global__ void __launch_bounds__(256) tree_find_kernel(TreeDev t, const double *__restrict__ q, int64_t n,
+                                                        int64_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = tree_find_one(t, q[i]);
+}
+
+__global__ void tree_leaf_weight_kernel(TreeDev t, const int64_t *__restrict__ idx, int64_t n,
+                                        double *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t k = idx[i];
+    if (k < 0 || k >= t.size) {
+        t.st->err = MB_ERR_INDEX_OOB;
+        out[i] = 0.0;
+    } else {
+        out[i] = __ldcg(t.W + k);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched update  (update_leaf_batch, prioritized_buffer.py:152-186; _normalize_priority :430-434)
+// ---------------------------------------------------------------------------------------------
+struct Normalize {
+    int enabled;
+    double epsilon, alpha;
+};
+
+// (|p| + eps) ** alpha in the dtype of p.  float32: NumPy evaluates |p| + f32(eps) in float32 and
+// powf(x, f32(alpha)); we evaluate pow in float64 on the float32-rounded operands and round once,
+// which equals a correctly rounded powf except within ~2^-29 of a rounding boundary.
+__device__ __forceinline__ double normalized_weight(float p, const Normalize &nz) {
+    if (!nz.enabled) return (double)p;
+    const float x = fabsf(p) + (float)nz.epsilon;
+    return (double)(float)pow((double)x, (double)(float)nz.alpha);
+}
+__device__ __forceinline__ double normalized_weight(double p, const Normalize &nz) {
+    if (!nz.enabled) return p;
+    return pow(fabs(p) + nz.epsilon, nz.alpha);
+}
+
+template <bool kCoop>
+__device__ __forceinline__ void phase_sync() {
+    if (kCoop) cg::this_grid().sync();
+    else __syncthreads();
+}
+
+// Phases (each separated by a CTA-wide or grid-wide barrier):
+//   0  validate indexes, stamp owner[idx] = max(position)        -> last write wins
+//   1  winners store their leaf; max_leaf = max(max_leaf, max(w)) over ALL entries (:175)
+//   l  for every level l = 1..depth-1: parent(idx >> l) = left + right   (idempotent, so the
+//      duplicates that np.unique removes in the reference are simply recomputed)
+//   e  clear the stamps
+template <typename WT, bool kCoop>
+__global__ void __launch_bounds__(1024) tree_update_kernel(TreeDev t, const int64_t *__restrict__ idx,
+                                                           const WT *__restrict__ w,
+                                                           const uint8_t *__restrict__ valid, int64_t n,
+                                                           Normalize nz, int gen) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < n; i += stride) {
+        if (valid && !valid[i]) continue;
+        const int64_t k = idx[i];
+        if (k < 0 || k >= t.size) {
+            t.st->err = MB_ERR_INDEX_OOB;
+            t.st->err_gen = gen;
+        } else {
+            atomicMax(t.owner + k, (int)i);
+        }
+    }
+    __threadfence();
+    phase_sync<kCoop>();
+    const bool bad = *((volatile int *)&t.st->err_gen) == gen;
+    if (!bad) {
+        double mx = -INFINITY;
+        for (int64_t i = tid; i < n; i += stride) {
+            if (valid && !valid[i]) continue;
+            const int64_t k = idx[i];
+            const double x = normalized_weight(w[i], nz);
+            mx = fmax(mx, x);
+            if (__ldcg(t.owner + k) == (int)i) t.W[k] = x;
+        }
+        mx = mb::warp_max(mx);
+        if ((threadIdx.x & 31) == 0 && mx > -INFINITY) atomic_max_f64(&t.st->max_leaf, mx);
+        for (int l = 1; l < t.depth; ++l) {
+            phase_sync<kCoop>();
+            const double *below = t.W + level_off(t, l - 1);
+            double *here = t.W + level_off(t, l);
+            for (int64_t i = tid; i < n; i += stride) {
+                if (valid && !valid[i]) continue;
+                const int64_t node = idx[i] >> l;
+                const double2 c = __ldcg(reinterpret_cast<const double2 *>(below + 2 * node));
+                here[node] = c.x + c.y;
+            }
+        }
+    }
+    phase_sync<kCoop>();
+    for (int64_t i = tid; i < n; i += stride) {
+        if (valid && !valid[i]) continue;
+        const int64_t k = idx[i];
+        if (k >= 0 && k < t.size) t.owner[k] = -1;
+    }
+}
+
+// update_leaf (:127-150): one path to the root.  The reference's bound check admits
+// index == size (:135); that slot is a padding leaf whenever size is not a power of two.
+__global__ void tree_update_one_kernel(TreeDev t, double weight, int64_t index) {
+    if (threadIdx.x != 0) return;
+    atomic_max_f64(&t.st->max_leaf, weight);
+    t.W[index] = weight;
+    int64_t node = index;
+    for (int l = 1; l < t.depth; ++l) {
+        node >>= 1;
+        const double2 c = __ldcg(reinterpret_cast<const double2 *>(t.W + level_off(t, l - 1) + 2 * node));
+        t.W[level_off(t, l) + node] = c.x + c.y;
+        __threadfence_block();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused PER draw  (sample_index_and_weight, prioritized_buffer.py:397-428)
+// ---------------------------------------------------------------------------------------------
+struct PerArgs {
+    int64_t n_stored;
+    double all_weight_sum;
+    double beta;
+    const mb_per_params *d_params;
+};
+
+__device__ __forceinline__ void per_one(const TreeDev &t, const double *__restrict__ u, int64_t n, int64_t i,
+                                        const PerArgs &a, int64_t &index, double &isw) {
+    double beta = a.beta, total = a.all_weight_sum;
+    int64_t n_stored = a.n_stored, row = 0;
+    if (a.d_params) {
+        beta = a.d_params->beta;
+        total = a.d_params->all_weight_sum;
+        n_stored = a.d_params->n_stored;
+        row = a.d_params->step;
+    }
+    const double root = __ldcg(t.W + t.total - 2);
+    // three separately rounded float64 ops, no FMA contraction (:409-412)
+    const double seg = __ddiv_rn(root, (double)n);
+    double q = __dadd_rn(__dmul_rn(u[row * n + i], seg), __dmul_rn((double)i, seg));
+    const double hi = (root - 1e-6 > 0.0) ? root - 1e-6 : 0.0;  // max(sum - 1e-6, 0) (:414)
+    q = fmin(fmax(q, 0.0), hi);                                  // np.clip (:413)
+    index = tree_find_one(t, q);
+    const double p = __ldg(t.W + index);
+    if (!(total > 0.0) && !(total < 0.0)) total = root;          // `all_weight_sum or root` (:421)
+    const double prob = __ddiv_rn(p, total);
+    isw = pow(__dmul_rn((double)n_stored, prob), -beta);         // (:423)
+}
+
+// n <= 1024: one CTA does the draw and the max-normalisation (:424).
+__global__ void __launch_bounds__(1024) per_sample_small(TreeDev t, const double *__restrict__ u, int64_t n,
+                                                         PerArgs a, int64_t *__restrict__ out_idx,
+                                                         double *__restrict__ out_isw) {
+    __shared__ double red[32];
+    const int tid = threadIdx.x;
+    int64_t index = 0;
+    double isw = -INFINITY;
+    if (tid < n) per_one(t, u, n, tid, a, index, isw);
+    double mx = mb::warp_max(isw);
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int k = 1; k < (int)((blockDim.x + 31) >> 5); ++k) mx = fmax(mx, red[k]);
+    if (tid < n) {
+        out_idx[tid] = index;
+        out_isw[tid] = __ddiv_rn(isw, mx);
+    }
+}
+
+__global__ void __launch_bounds__(256) per_sample_large(TreeDev t, const double *__restrict__ u, int64_t n,
+                                                        PerArgs a, int64_t *__restrict__ out_idx,
+                                                        double *__restrict__ out_isw) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t index = 0;
+    double isw = -INFINITY;
+    if (i < n) {
+        per_one(t, u, n, i, a, index, isw);
+        out_idx[i] = index;
+        out_isw[i] = isw;
+    }
+    const double mx = mb::warp_max(isw);
+    if ((threadIdx.x & 31) == 0 && mx > -INFINITY) atomic_max_f64(&t.st->isw_max, mx);
+}
+
+__global__ void per_isw_reset(TreeState *st) { st->isw_max = -INFINITY; }
+
+__global__ void per_normalize(const TreeState *st, double *__restrict__ isw, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) isw[i] = __ddiv_rn(isw[i], st->isw_max);
+}
+
+int ceil_log2_i64(int64_t x) {
+    int l = 0;
+    while (((int64_t)1 << l) < x) ++l;
+    return l;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int mb_tree_create(int64_t size, int device, mb_tree **out) {
+    if (!out || size < 1 || size > ((int64_t)1 << 31)) return MB_ERR_INVALID;
+    if (mb_device_count() <= device || device < 0) return MB_ERR_NO_DEVICE;
+    mb::DeviceGuard g(device);
+    if (!g.ok) return MB_ERR_CUDA;
+    mb_tree *t = new (std::nothrow) mb_tree();
+    if (!t) return MB_ERR_NOMEM;
+    t->device = device;
+    const int depth = ceil_log2_i64(size) + 1;  // int(ceil(log2(size))) + 1 (:48)
+    t->dev.size = size;
+    t->dev.depth = depth;
+    t->dev.total = (int64_t)1 << depth;
+    t->n_leaf_pad = (int64_t)1 << (depth - 1);
+    t->n_nodes = t->dev.total - 1;
+    t->h_state = nullptr;
+    t->gen = 0;
+    t->dev.W = nullptr;
+    t->dev.owner = nullptr;
+    t->dev.st = nullptr;
+    if (cudaMalloc((void **)&t->dev.W, sizeof(double) * (size_t)t->dev.total) != cudaSuccess ||
+        cudaMalloc((void **)&t->dev.owner, sizeof(int) * (size_t)size) != cudaSuccess ||
+        cudaMalloc((void **)&t->dev.st, sizeof(TreeState)) != cudaSuccess ||
+        cudaMallocHost((void **)&t->h_state, sizeof(TreeState)) != cudaSuccess) {
+        cudaGetLastError();
+        mb_tree_destroy(t);
+        return MB_ERR_NOMEM;
+    }
+    MB_CUDA(cudaMemset(t->dev.W, 0, sizeof(double) * (size_t)t->dev.total));
+    MB_CUDA(cudaMemset(t->dev.owner, 0xff, sizeof(int) * (size_t)size));
+    MB_CUDA(cudaMemset(t->dev.st, 0, sizeof(TreeState)));
+    int per_sm = 0;
+    MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_update_kernel<double, true>, 1024, 0));
+    int sms = mb::kNumSMs;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    t->coop_blocks = (per_sm > 0 ? per_sm : 1) * sms;
+    MB_CUDA(cudaDeviceSynchronize());
+    *out = t;
+    return MB_OK;
+}
+
+int mb_tree_destroy(mb_tree *t) {
+    if (!t) return MB_OK;
+    mb::DeviceGuard g(t->device);
+    if (t->dev.W) cudaFree(t->dev.W);
+    if (t->dev.owner) cudaFree(t->dev.owner);
+    if (t->dev.st) cudaFree(t->dev.st);
+    if (t->h_state) cudaFreeHost(t->h_state);
+    delete t;
+    return MB_OK;
+}
+
+int mb_tree_geometry(const mb_tree *t, int64_t *size, int *depth, int64_t *n_leaf_padded, int64_t *n_nodes) {
+    if (!t) return MB_ERR_INVALID;
+    if (size) *size = t->dev.size;
+    if (depth) *depth = t->dev.depth;
+    if (n_leaf_padded) *n_leaf_padded = t->n_leaf_pad;
+    if (n_nodes) *n_nodes = t->n_nodes;
+    return MB_OK;
+}
+
+double *mb_tree_weights(mb_tree *t) { return t ? t->dev.W : nullptr; }
+const double *mb_tree_root_ptr(mb_tree *t) { return t ? t->dev.W + t->n_nodes - 1 : nullptr; }
+const double *mb_tree_max_leaf_ptr(mb_tree *t) { return t ? &t->dev.st->max_leaf : nullptr; }
+
+int mb_tree_stats(mb_tree *t, double *h_weight_sum, double *h_max_leaf, void *stream) {
+    if (!t) return MB_ERR_INVALID;
+    mb::DeviceGuard g(t->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    MB_CUDA(cudaMemcpyAsync(&t->h_state->isw_max, t->dev.W + t->n_nodes - 1, sizeof(double),
+                            cudaMemcpyDeviceToHost, s));
+    MB_CUDA(cudaMemcpyAsync(&t->h_state->max_leaf, &t->dev.st->max_leaf, sizeof(double),
+                            cudaMemcpyDeviceToHost, s));
+    MB_CUDA(cudaStreamSynchronize(s));
+    if (h_weight_sum) *h_weight_sum = t->h_state->isw_max;
+    if (h_max_leaf) *h_max_leaf = t->h_state->max_leaf;
+    return MB_OK;
+}
+
+int mb_tree_check(mb_tree *t, void *stream) {
+    if (!t) return MB_ERR_INVALID;
+    mb::DeviceGuard g(t->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    MB_CUDA(cudaMemcpyAsync(&t->h_state->err, &t->dev.st->err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MB_CUDA(cudaStreamSynchronize(s));
+    const int err = t->h_state->err;
+    if (err != MB_OK) {
+        MB_CUDA(cudaMemsetAsync(&t->dev.st->err, 0, sizeof(int), s));
+        MB_CUDA(cudaStreamSynchronize(s));
+    }
+    return err;
+}
+
+int mb_tree_clear(mb_tree *t, void *stream) {
+    if (!t) return MB_ERR_INVALID;
+    mb::DeviceGuard g(t->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    MB_CUDA(cudaMemsetAsync(t->dev.W, 0, sizeof(double) * (size_t)t->dev.total, s));
+    MB_CUDA(cudaMemsetAsync(t->dev.st, 0, sizeof(TreeState), s));
+    return MB_OK;
+}
+
+int mb_tree_build(mb_tree *t, const double *d_leaves, int64_t n, void *stream) {
+    if (!t) return MB_ERR_INVALID;
+    if (d_leaves && n != t->dev.size) return MB_ERR_SIZE_MISMATCH;
+    mb::DeviceGuard g(t->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    tree_state_reset<<<1, 1, 0, s>>>(t->dev.st, -INFINITY);  // _build replaces max_leaf (:220)
+    int lv = 0;
+    while (t->dev.depth - 1 - lv >= 11) {
+        const int64_t n_src = t->dev.total >> (lv + 1);
+        tree_build_pass<<<(unsigned)(n_src / 2048), 256, 0, s>>>(t->dev, lv, lv == 0 ? d_leaves : nullptr);
+        lv += 11;
+    }
+    if (lv < t->dev.depth - 1 || lv == 0)
+        tree_build_top<<<1, 1024, 0, s>>>(t->dev, lv, lv == 0 ? d_leaves : nullptr);
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
+
+int mb_tree_find(mb_tree *t, const double *d_query, int64_t n, int64_t *d_index, void *stream) {
+    if (!t || n < 0) return MB_ERR_INVALID;
+    if (n == 0) return MB_OK;
+    mb::DeviceGuard g(t->device);
+    tree_find_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(t->dev, d_query, n, d_index);
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
+
+int mb_tree_leaf_weight(mb_tree *t, const int64_t *d_index, int64_t n, double *d_weight, void *stream) {
+    if (!t || n < 0) return MB_ERR_INVALID;
+    if (n == 0) return MB_OK;
+    mb::DeviceGuard g(t->device);
+    tree_leaf_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(t->dev, d_index, n, d_weight);
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
+
+static int launch_update(mb_tree *t, const int64_t *d_index, const void *d_weight, int dtype,
+                         const uint8_t *d_valid, int64_t n, Normalize nz, cudaStream_t s) {
+    if (!t || n < 0 || (dtype != MB_F32 && dtype != MB_F64)) return MB_ERR_INVALID;
+    if (n == 0) return MB_OK;
+    if (n > 0x7fffffff) return MB_ERR_INVALID;
+    mb::DeviceGuard g(t->device);
+    const int gen = ++t->gen;
+    if (n <= 4096) {
+        const int threads = (int)(n <= 1024 ? ((n + 31) / 32) * 32 : 1024);
+        if (dtype == MB_F32)
+            tree_update_kernel<float, false><<<1, threads, 0, s>>>(t->dev, d_index, (const float *)d_weight, d_valid, n, nz, gen);
+        else
+            tree_update_kernel<double, false><<<1, threads, 0, s>>>(t->dev, d_index, (const double *)d_weight, d_valid, n, nz, gen);
+        MB_LAUNCH_CHECK();
+        return MB_OK;
+    }
+    int64_t blocks = (n + 1023) / 1024;
+    if (blocks > t->coop_blocks) blocks = t->coop_blocks;
+    void *args[] = {&t->dev, &d_index, &d_weight, &d_valid, &n, &nz, (void *)&gen};
+    const void *fn = dtype == MB_F32 ? (const void *)tree_update_kernel<float, true>
+                                     : (const void *)tree_update_kernel<double, true>;
+    MB_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(1024), args, 0, s));
+    return MB_OK;
+}
+
+int mb_tree_update_batch(mb_tree *t, const int64_t *d_index, const void *d_weight, int weight_dtype,
+                         const uint8_t *d_valid, int64_t n, void *stream) {
+    Normalize nz{0, 0.0, 0.0};
+    return launch_update(t, d_index, d_weight, weight_dtype, d_valid, n, nz, (cudaStream_t)stream);
+}
+
+int mb_tree_update_priority(mb_tree *t, const int64_t *d_index, const void *d_priority, int priority_dtype,
+                            const uint8_t *d_valid, int64_t n, double epsilon, double alpha, void *stream) {
+    Normalize nz{1, epsilon, alpha};
+    return launch_update(t, d_index, d_priority, priority_dtype, d_valid, n, nz, (cudaStream_t)stream);
+}
+
+int mb_tree_update_leaf(mb_tree *t, double weight, int64_t index, void *stream) {
+    if (!t) return MB_ERR_INVALID;
+    // reference check is `0 <= index <= size` (:135); index == size only exists as a padding leaf
+    if (index < 0 || index > t->dev.size || index >= t->n_leaf_pad) return MB_ERR_INDEX_OOB;
+    mb::DeviceGuard g(t->device);
+    tree_update_one_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(t->dev, weight, index);
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
+
+int mb_per_sample(mb_tree *t, const double *d_uniform, int64_t n, int64_t n_stored, double all_weight_sum,
+                  double beta, const mb_per_params *d_params, int64_t *d_index, double *d_is_weight,
+                  void *stream) {
+    if (!t || n < 0) return MB_ERR_INVALID;
+    if (n == 0) return MB_OK;
+    mb::DeviceGuard g(t->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    PerArgs a{n_stored, all_weight_sum, beta, d_params};
+    if (n <= 1024) {
+        per_sample_small<<<1, (unsigned)(((n + 31) / 32) * 32), 0, s>>>(t->dev, d_uniform, n, a, d_index, d_is_weight);
+    } else {
+        per_isw_reset<<<1, 1, 0, s>>>(t->dev.st);
+        per_sample_large<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t->dev, d_uniform, n, a, d_index, d_is_weight);
+        per_normalize<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t->dev.st, d_is_weight, n);
+    }
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------------------ host variants
+#define MB_STAGE(t, hb, db)                                   \
+    mb::DeviceGuard g((t)->device);                           \
+    mb::Staging *st = mb::staging_for((t)->device);           \
+    if (!st) return MB_ERR_CUDA;                              \
+    {                                                         \
+        int _r = st->ensure((hb), (db));                      \
+        if (_r != MB_OK) return _r;                           \
+    }
+
+int mb_tree_build_host(mb_tree *t, const double *h_leaves, int64_t n) {
+    if (!t || !h_leaves) return MB_ERR_INVALID;
+    if (n != t->dev.size) return MB_ERR_SIZE_MISMATCH;
+    const size_t bytes = sizeof(double) * (size_t)n;
+    MB_STAGE(t, bytes, bytes);
+    memcpy(st->h, h_leaves, bytes);
+    MB_CUDA(cudaMemcpyAsync(st->d, st->h, bytes, cudaMemcpyHostToDevice, st->stream));
+    int r = mb_tree_build(t, (const double *)st->d, n, st->stream);
+    if (r != MB_OK) return r;
+    MB_CUDA(cudaStreamSynchronize(st->stream));
+    return MB_OK;
+}
+
+int mb_tree_find_host(mb_tree *t, const double *h_query, int64_t n, int64_t *h_index) {
+    if (!t || n < 0) return MB_ERR_INVALID;
+    if (n == 0) return MB_OK;
+    const size_t bytes = 8 * (size_t)n;
+    MB_STAGE(t, 2 * bytes, 2 * bytes);
+    memcpy(st->h, h_query, bytes);
+    MB_CUDA(cudaMemcpyAsync(st->d, st->h, bytes, cudaMemcpyHostToDevice, st->stream));
+    int r = mb_tree_find(t, (const double *)st->d, n, (int64_t *)(st->d + bytes), st->stream);
+    if (r != MB_OK) return r;
+    MB_CUDA(cudaMemcpyAsync(st->h + bytes, st->d + bytes, bytes, cudaMemcpyDeviceToHost, st->stream));
+    MB_CUDA(cudaStreamSynchronize(st->stream));
+    memcpy(h_index, st->h + bytes, bytes);
+    return MB_OK;
+}
+
+int mb_tree_leaf_weight_host(mb_tree *t, const int64_t *h_index, int64_t n, double *h_weight) {
+    if (!t || n < 0) return MB_ERR_INVALID;
+    if (n == 0) return MB_OK;
+    for (int64_t i = 0; i < n; ++i)
+        if (h_index[i] < 0 || h_index[i] >= t->dev.size) return MB_ERR_INDEX_OOB;  // (:89-90)
+    const size_t bytes = 8 * (size_t)n;
+    MB_STAGE(t, 2 * bytes, 2 * bytes);
+    memcpy(st->h, h_index, bytes);
+    MB_CUDA(cudaMemcpyAsync(st->d, st->h, bytes, cudaMemcpyHostToDevice, st->stream));
+    int r = mb_tree_leaf_weight(t, (const int64_t *)st->d, n, (double *)(st->d + bytes), st->stream);
+    if (r != MB_OK) return r;
+    MB_CUDA(cudaMemcpyAsync(st->h + bytes, st->d + bytes, bytes, cudaMemcpyDeviceToHost, st->stream));
+    MB_CUDA(cudaStreamSynchronize(st->stream));
+    memcpy(h_weight, st->h + bytes, bytes);
+    return MB_OK;
+}
+
+int mb_tree_update_batch_host(mb_tree *t, const int64_t *h_index, const void *h_weight, int weight_dtype,
+                              int64_t n) {
+    if (!t || n < 0 || (weight_dtype != MB_F32 && weight_dtype != MB_F64)) return MB_ERR_INVALID;
+    if (n == 0) return MB_OK;
+    for (int64_t i = 0; i < n; ++i)
+        if (h_index[i] < 0 || h_index[i] >= t->dev.size) return MB_ERR_INDEX_OOB;  // (:172-173)
+    const size_t ib = 8 * (size_t)n, wb = (weight_dtype == MB_F32 ? 4 : 8) * (size_t)n;
+    MB_STAGE(t, ib + wb, ib + wb);
+    memcpy(st->h, h_index, ib);
+    memcpy(st->h + ib, h_weight, wb);
+    MB_CUDA(cudaMemcpyAsync(st->d, st->h, ib + wb, cudaMemcpyHostToDevice, st->stream));
+    int r = mb_tree_update_batch(t, (const int64_t *)st->d, st->d + ib, weight_dtype, nullptr, n, st->stream);
+    if (r != MB_OK) return r;
+    MB_CUDA(cudaStreamSynchronize(st->stream));
+    return MB_OK;
+}
+
+int mb_tree_read_host(mb_tree *t, int64_t first_node, int64_t n_nodes, double *h_out) {
+    if (!t || first_node < 0 || n_nodes < 0 || first_node + n_nodes > t->n_nodes) return MB_ERR_INVALID;
+    if (n_nodes == 0) return MB_OK;
+    mb::DeviceGuard g(t->device);
+    MB_CUDA(cudaMemcpy(h_out, t->dev.W + first_node, sizeof(double) * (size_t)n_nodes, cudaMemcpyDeviceToHost));
+    return MB_OK;
+}
+
+int mb_per_sample_host(mb_tree *t, const double *h_uniform, int64_t n, int64_t n_stored, double all_weight_sum,
+                       double beta, int64_t *h_index, double *h_is_weight) {
+    if (!t || n < 0) return MB_ERR_INVALID;
+    if (n == 0) return MB_OK;
+    const size_t bytes = 8 * (size_t)n;
+    MB_STAGE(t, 3 * bytes, 3 * bytes);
+    memcpy(st->h, h_uniform, bytes);
+    MB_CUDA(cudaMemcpyAsync(st->d, st->h, bytes, cudaMemcpyHostToDevice, st->stream));
+    int r = mb_per_sample(t, (const double *)st->d, n, n_stored, all_weight_sum, beta, nullptr,
+                          (int64_t *)(st->d + bytes), (double *)(st->d + 2 * bytes), st->stream);
+    if (r != MB_OK) return r;
+    MB_CUDA(cudaMemcpyAsync(st->h + bytes, st->d + bytes, 2 * bytes, cudaMemcpyDeviceToHost, st->stream));
+    MB_CUDA(cudaStreamSynchronize(st->stream));
+    memcpy(h_index, st->h + bytes, bytes);
+    memcpy(h_is_weight, st->h + 2 * bytes, bytes);
+    return MB_OK;
+}
+
+}  // extern "C"

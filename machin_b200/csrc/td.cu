@@ -1,0 +1,110 @@
+// TD-target / priority math for sm_100a: one fused pass instead of ~10 eager [B,1] ops.
+//
+// Replaces the arithmetic of DQNPer.update (dqn_per.py:105-139 + dqn.py:497-501), DDPGPer.update
+// (ddpg_per.py:117-160 + ddpg.py:506-510) and soft_update (algorithms/utils.py:8-27).  float32 with
+// each operation rounded separately (no FMA contraction) in the reference's order, so y, the
+// gathered action value and abs_error are bit-identical to CPU torch given the same Q values.
+#include "mb_common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256) td_dqn_kernel(const float *__restrict__ q, const float *__restrict__ qn,
+                                                     const float *__restrict__ qtn, int64_t batch, int A,
+                                                     const int64_t *__restrict__ action,
+                                                     const float *__restrict__ reward,
+                                                     const uint8_t *__restrict__ terminal,
+                                                     const double *__restrict__ isw, float discount, int mode,
+                                                     float *__restrict__ y_out, float *__restrict__ av_out,
+                                                     float *__restrict__ abs_out, double *__restrict__ loss_out,
+                                                     float *__restrict__ grad_q) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    // a* = argmax (first maximum, like t.max(...)[1]) over the online net ("double") or the target net
+    const float *sel = (mode == 0 ? qn : qtn) + b * A;
+    int best = 0;
+    float best_v = sel[0];
+    for (int a = 1; a < A; ++a) {
+        const float v = sel[a];
+        if (v > best_v) { best_v = v; best = a; }
+    }
+    const float next_value = qtn[b * A + best];
+    // reward + discount * ~terminal * next_value  (dqn.py:501): (discount * mask) * next, then + reward
+    const float mask = terminal[b] ? 0.0f : 1.0f;
+    const float y = __fadd_rn(reward[b], __fmul_rn(__fmul_rn(discount, mask), next_value));
+    if (y_out) y_out[b] = y;
+    if (!q) return;
+    int64_t act = action[b];
+    act = act < 0 ? 0 : (act >= A ? A - 1 : act);
+    const float av = q[b * A + act];
+    const float diff = __fsub_rn(av, y);
+    if (av_out) av_out[b] = av;
+    if (abs_out) abs_out[b] = fabsf(diff);                       // sum(|q - y|, dim=1) with one column
+    const double w = isw ? isw[b] : 1.0;
+    if (loss_out) loss_out[b] = (double)__fmul_rn(diff, diff) * w;  // MSE(reduction="none") * is_weight (f64)
+    if (grad_q) {
+        // d mean_b(loss_elem) / d q[b, a]
+        const float g = (float)(2.0 * (double)diff * w / (double)batch);
+        for (int a = 0; a < A; ++a) grad_q[b * A + a] = (a == act) ? g : 0.0f;
+    }
+}
+
+__global__ void __launch_bounds__(256) td_target_kernel(const float *__restrict__ next_value,
+                                                        const float *__restrict__ reward,
+                                                        const uint8_t *__restrict__ terminal, int64_t batch,
+                                                        float discount, const float *__restrict__ value,
+                                                        float *__restrict__ y_out, float *__restrict__ abs_out) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const float mask = terminal[b] ? 0.0f : 1.0f;
+    const float y = __fadd_rn(reward[b], __fmul_rn(__fmul_rn(discount, mask), next_value[b]));
+    if (y_out) y_out[b] = y;
+    if (value && abs_out) abs_out[b] = fabsf(__fsub_rn(value[b], y));
+}
+
+// target * (1 - rate) + source * rate, evaluated like torch: scalars rounded to float32 first
+__global__ void __launch_bounds__(256) soft_update_kernel(float *__restrict__ target, const float *__restrict__ source,
+                                                          int64_t n, float keep, float rate) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) target[i] = __fadd_rn(__fmul_rn(target[i], keep), __fmul_rn(source[i], rate));
+}
+
+}  // namespace
+
+extern "C" {
+
+int mb_td_dqn(const float *d_q, const float *d_q_next, const float *d_q_tgt_next, int64_t batch, int n_actions,
+              const int64_t *d_action, const float *d_reward, const uint8_t *d_terminal,
+              const double *d_is_weight, float discount, int mode, float *d_y, float *d_action_value,
+              float *d_abs_error, double *d_loss_elem, float *d_grad_q, void *stream) {
+    if (batch < 0 || n_actions < 1 || !d_q_tgt_next || !d_reward || !d_terminal) return MB_ERR_INVALID;
+    if (mode == 0 && !d_q_next) return MB_ERR_INVALID;
+    if (d_q && !d_action) return MB_ERR_INVALID;
+    if (batch == 0) return MB_OK;
+    td_dqn_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_q, d_q_next, d_q_tgt_next, batch, n_actions, d_action, d_reward, d_terminal, d_is_weight, discount, mode,
+        d_y, d_action_value, d_abs_error, d_loss_elem, d_grad_q);
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
+
+int mb_td_target(const float *d_next_value, const float *d_reward, const uint8_t *d_terminal, int64_t batch,
+                 float discount, const float *d_value, float *d_y, float *d_abs_error, void *stream) {
+    if (batch < 0 || !d_next_value || !d_reward || !d_terminal) return MB_ERR_INVALID;
+    if (batch == 0) return MB_OK;
+    td_target_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_next_value, d_reward, d_terminal, batch, discount, d_value, d_y, d_abs_error);
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
+
+int mb_soft_update(float *d_target, const float *d_source, int64_t n, double rate, void *stream) {
+    if (n < 0 || !d_target || !d_source) return MB_ERR_INVALID;
+    if (n == 0) return MB_OK;
+    // python: target * (1.0 - update_rate) + param * update_rate ; both scalars become float32
+    soft_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_target, d_source, n, (float)(1.0 - rate), (float)rate);
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+"""Functional CUDA-tensor front end of the C ABI (TD target math, soft update, V-trace, GAE).
+
+Each function takes contiguous CUDA tensors, launches the corresponding kernel of
+libmachin_b200.so on torch's current stream and returns CUDA tensors.  No CPU path.
+"""
+from typing import Dict, Optional
+
+import torch as t
+
+from . import _lib
+from ._lib import lib
+
+
+def _c(x: Optional[t.Tensor], dtype=None):
+    if x is None:
+        return None
+    if not x.is_cuda:
+        raise RuntimeError("machin_b200.ops works on CUDA tensors only (no CPU fallback)")
+    if dtype is not None and x.dtype != dtype:
+        x = x.to(dtype)
+    return x.contiguous()
+
+
+def _u8(x: t.Tensor):
+    x = _c(x)
+    return x.view(t.uint8) if x.dtype == t.bool else x.to(t.uint8)
+
+
+def td_dqn(q, q_next, q_tgt_next, action, reward, terminal, discount: float, is_weight=None,
+           mode: str = "double", want_grad: bool = False) -> Dict[str, t.Tensor]:
+    """Double-DQN target + priority math (dqn_per.py:105-139, dqn.py:497-501).
+
+    q, q_next, q_tgt_next: f32[B, A]; action: int[B,1]; reward f32[B,1]; terminal bool[B,1];
+    is_weight f64[B].  Returns y, action_value, abs_error (f32[B,1] / f32[B]), loss_elem f64[B,1]
+    (MSE * is_weight) and, if ``want_grad``, grad_q = d mean(loss_elem) / d q."""
+    q, q_next, q_tgt_next = _c(q, t.float32), _c(q_next, t.float32), _c(q_tgt_next, t.float32)
+    B, A = q_tgt_next.shape
+    dev = q_tgt_next.device
+    action, reward = _c(action, t.int64), _c(reward, t.float32)
+    term = _u8(terminal)
+    isw = _c(is_weight, t.float64)
+    y = t.empty((B, 1), dtype=t.float32, device=dev)
+    av = t.empty((B, 1), dtype=t.float32, device=dev) if q is not None else None
+    ae = t.empty((B,), dtype=t.float32, device=dev) if q is not None else None
+    le = t.empty((B, 1), dtype=t.float64, device=dev) if q is not None else None
+    gq = t.empty((B, A), dtype=t.float32, device=dev) if (want_grad and q is not None) else None
+    with t.cuda.device(dev):
+        _lib.check(lib.mb_td_dqn(_lib.ptr(q), _lib.ptr(q_next), _lib.ptr(q_tgt_next), B, A, _lib.ptr(action),
+                                 _lib.ptr(reward), _lib.ptr(term), _lib.ptr(isw), float(discount),
+                                 0 if mode == "double" else 1, _lib.ptr(y), _lib.ptr(av), _lib.ptr(ae),
+                                 _lib.ptr(le), _lib.ptr(gq), _lib.stream_ptr()))
+    return {"y": y, "action_value": av, "abs_error": ae, "loss_elem": le, "grad_q": gq}
+
+
+def td_target(next_value, reward, terminal, discount: float, value=None) -> Dict[str, t.Tensor]:
+    """y = reward + discount * ~terminal * next_value (ddpg.py:506-510); abs_error = |value - y|."""
+    next_value, reward = _c(next_value, t.float32), _c(reward, t.float32)
+    B = reward.shape[0]
+    dev = reward.device
+    term = _u8(terminal)
+    value = _c(value, t.float32)
+    y = t.empty((B, 1), dtype=t.float32, device=dev)
+    ae = t.empty((B,), dtype=t.float32, device=dev) if value is not None else None
+    with t.cuda.device(dev):
+        _lib.check(lib.mb_td_target(_lib.ptr(next_value), _lib.ptr(reward), _lib.ptr(term), B, float(discount),
+                                    _lib.ptr(value), _lib.ptr(y), _lib.ptr(ae), _lib.stream_ptr()))
+    return {"y": y, "abs_error": ae}
+
+
+def soft_update_flat(target: t.Tensor, source: t.Tensor, rate: float):
+    """In place: target = target * (1 - rate) + source * rate over a flat float32 block (utils.py:8-27)."""
+    assert target.is_cuda and target.is_contiguous() and target.dtype == t.float32
+    source = _c(source, t.float32)
+    with t.cuda.device(target.device):
+        _lib.check(lib.mb_soft_update(_lib.ptr(target), _lib.ptr(source), target.numel(), float(rate),
+                                      _lib.stream_ptr()))
+
+
+def soft_update(target_net: t.nn.Module, source_net: t.nn.Module, rate: float):
+    for tp, sp in zip(target_net.parameters(), source_net.parameters()):
+        if tp.is_cuda and tp.dtype == t.float32 and tp.is_contiguous():
+            soft_update_flat(tp.data, sp.data.to(tp.device), rate)
+        else:
+            raise RuntimeError("soft_update: parameters must be contiguous float32 CUDA tensors")
+
+
+def vtrace(value, next_value, reward, terminal, log_pi, log_mu, discount: float, clip_c: float = 1.0,
+           clip_rho: float = 1.0, offsets: Optional[t.Tensor] = None, n_episodes: Optional[int] = None
+           ) -> Dict[str, t.Tensor]:
+    """IMPALA V-trace (impala.py:322-362) over flattened episode-major steps.  ``offsets``: int64
+    [n_episodes + 1] CSR episode boundaries on the device, or None for equal-length episodes."""
+    value = _c(value, t.float32)
+    shape, dev = value.shape, value.device
+    S = value.numel()
+    args = [_c(x, t.float32) for x in (next_value, reward)]
+    term = _u8(terminal)
+    lp, lm = _c(log_pi, t.float32), _c(log_mu, t.float32)
+    if offsets is not None:
+        offsets = _c(offsets, t.int64)
+        n_episodes = offsets.numel() - 1
+    out = {k: t.empty(shape, dtype=t.float32, device=dev) for k in ("vs", "vss", "rho", "adv")}
+    with t.cuda.device(dev):
+        _lib.check(lib.mb_vtrace(_lib.ptr(offsets), int(n_episodes), S, _lib.ptr(value), _lib.ptr(args[0]),
+                                 _lib.ptr(args[1]), _lib.ptr(term), _lib.ptr(lp), _lib.ptr(lm), float(discount),
+                                 float(clip_c), float(clip_rho), _lib.ptr(out["vs"]), _lib.ptr(out["vss"]),
+                                 _lib.ptr(out["rho"]), _lib.ptr(out["adv"]), _lib.stream_ptr()))
+    return out
+
+
+def gae(reward, terminal, critic_value, next_critic_value, discount: float, gae_lambda: float,
+        offsets: Optional[t.Tensor] = None, n_episodes: Optional[int] = None) -> Dict[str, t.Tensor]:
+    """Discounted returns + GAE (a2c.py:275-313), float64 like the reference's Python floats."""
+    reward = _c(reward, t.float64)
+    dev, S = reward.device, reward.numel()
+    term = _u8(terminal)
+    cv, ncv = _c(critic_value, t.float32), _c(next_critic_value, t.float32)
+    if offsets is not None:
+        offsets = _c(offsets, t.int64)
+        n_episodes = offsets.numel() - 1
+    out = {k: t.empty(reward.shape, dtype=t.float64, device=dev) for k in ("returns", "gae")}
+    with t.cuda.device(dev):
+        _lib.check(lib.mb_gae(_lib.ptr(offsets), int(n_episodes), S, _lib.ptr(reward), _lib.ptr(term), _lib.ptr(cv),
+                              _lib.ptr(ncv), float(discount), float(gae_lambda), _lib.ptr(out["returns"]),
+                              _lib.ptr(out["gae"]), _lib.stream_ptr()))
+    return out
