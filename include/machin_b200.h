@@ -64,8 +64,12 @@ int mb_tree_geometry(const mb_tree *tree, int64_t *size, int *depth, int64_t *n_
                      int64_t *n_nodes);
 /* device pointer to the flattened float64 node array (attribute `weights`, :52) */
 double *mb_tree_weights(mb_tree *tree);
-/* get_weight_sum / get_leaf_max (:54-66).  Blocks on `stream`, then returns both scalars. */
-int mb_tree_stats(mb_tree *tree, double *h_weight_sum, double *h_max_leaf, void *stream);
+/* get_weight_sum / get_leaf_max (:54-66).  Blocks on `stream`, then returns the scalars.
+ * h_max_leaf_dtype (nullable) receives MB_F32 when the running maximum was set by a float32
+ * batch: the reference then holds it as np.float32, which decides the dtype in which
+ * normalize(max_leaf) is evaluated for default-priority stores (:302-303). */
+int mb_tree_stats(mb_tree *tree, double *h_weight_sum, double *h_max_leaf, int *h_max_leaf_dtype,
+                  void *stream);
 /* device pointers to the root node and to the running leaf maximum (no sync) */
 const double *mb_tree_root_ptr(mb_tree *tree);
 const double *mb_tree_max_leaf_ptr(mb_tree *tree);

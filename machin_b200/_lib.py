@@ -50,7 +50,7 @@ SIGNATURES = {
     "mb_tree_destroy": (i32, [vp]),
     "mb_tree_geometry": (i32, [vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]),
     "mb_tree_weights": (vp, [vp]),
-    "mb_tree_stats": (i32, [vp, C.POINTER(f64), C.POINTER(f64), vp]),
+    "mb_tree_stats": (i32, [vp, C.POINTER(f64), C.POINTER(f64), C.POINTER(i32), vp]),
     "mb_tree_root_ptr": (vp, [vp]),
     "mb_tree_max_leaf_ptr": (vp, [vp]),
     "mb_tree_check": (i32, [vp, vp]),

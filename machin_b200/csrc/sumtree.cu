@@ -24,8 +24,12 @@ namespace cg = cooperative_groups;
 struct TreeState {
     double max_leaf;   // running maximum leaf weight (WeightTree.max_leaf)
     double isw_max;    // scratch: max importance weight of the draw in flight
+    double batch_max;  // scratch: max weight of the update batch in flight (-inf between launches)
     int err;           // deferred device-side validation error (mb_status), sticky until checked
     int err_gen;       // launch generation that raised it (so later launches are not skipped)
+    int max_is_f32;    // max_leaf came from a float32 batch (the reference keeps it as np.float32 then,
+                       // which changes the dtype of normalize(max_leaf) for default-priority stores)
+    int pad;
 };
 
 struct TreeDev {
@@ -68,7 +72,11 @@ __device__ __forceinline__ double2 ld_nc2(const double *p) {
 // ---------------------------------------------------------------------------------------------
 // build  (update_all_leaves + _build, prioritized_buffer.py:188-199, 216-231)
 // ---------------------------------------------------------------------------------------------
-__global__ void tree_state_reset(TreeState *st, double max_leaf) { st->max_leaf = max_leaf; }
+__global__ void tree_state_reset(TreeState *st, double max_leaf) {
+    st->max_leaf = max_leaf;
+    st->batch_max = -INFINITY;
+    st->max_is_f32 = 0;
+}
 
 // One pass lifts 11 levels.  CTA = 256 threads x 8 source nodes = 2048 nodes of level `lv`.
 // Reads 8 B/node once, writes every produced level once: ~16 B per source node in total.
@@ -304,7 +312,7 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(TreeDev t, const int6
             if (__ldcg(t.owner + k) == (int)i) t.W[k] = x;
         }
         mx = mb::warp_max(mx);
-        if ((threadIdx.x & 31) == 0 && mx > -INFINITY) atomic_max_f64(&t.st->max_leaf, mx);
+        if ((threadIdx.x & 31) == 0 && mx > -INFINITY) atomic_max_f64(&t.st->batch_max, mx);
         for (int l = 1; l < t.depth; ++l) {
             phase_sync<kCoop>();
             const double *below = t.W + level_off(t, l - 1);
@@ -323,13 +331,25 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(TreeDev t, const int6
         const int64_t k = idx[i];
         if (k >= 0 && k < t.size) t.owner[k] = -1;
     }
+    if (tid == 0) {
+        // max_leaf = max(np.max(weights), max_leaf): the new value (and its dtype) wins ties (:175)
+        const double bm = __ldcg(&t.st->batch_max);
+        if (bm > -INFINITY && !(t.st->max_leaf > bm)) {
+            t.st->max_leaf = bm;
+            t.st->max_is_f32 = sizeof(WT) == 4 ? 1 : 0;
+        }
+        t.st->batch_max = -INFINITY;
+    }
 }
 
 // update_leaf (:127-150): one path to the root.  The reference's bound check admits
 // index == size (:135); that slot is a padding leaf whenever size is not a power of two.
 __global__ void tree_update_one_kernel(TreeDev t, double weight, int64_t index) {
     if (threadIdx.x != 0) return;
-    atomic_max_f64(&t.st->max_leaf, weight);
+    if (!(t.st->max_leaf > weight)) {  // max(weight, max_leaf): a Python float wins ties (:137)
+        t.st->max_leaf = weight;
+        t.st->max_is_f32 = 0;
+    }
     t.W[index] = weight;
     int64_t node = index;
     for (int l = 1; l < t.depth; ++l) {
@@ -458,6 +478,7 @@ int mb_tree_create(int64_t size, int device, mb_tree **out) {
     MB_CUDA(cudaMemset(t->dev.W, 0, sizeof(double) * (size_t)t->dev.total));
     MB_CUDA(cudaMemset(t->dev.owner, 0xff, sizeof(int) * (size_t)size));
     MB_CUDA(cudaMemset(t->dev.st, 0, sizeof(TreeState)));
+    tree_state_reset<<<1, 1>>>(t->dev.st, 0.0);
     int per_sm = 0;
     MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_update_kernel<double, true>, 1024, 0));
     int sms = mb::kNumSMs;
@@ -492,7 +513,7 @@ double *mb_tree_weights(mb_tree *t) { return t ? t->dev.W : nullptr; }
 const double *mb_tree_root_ptr(mb_tree *t) { return t ? t->dev.W + t->n_nodes - 1 : nullptr; }
 const double *mb_tree_max_leaf_ptr(mb_tree *t) { return t ? &t->dev.st->max_leaf : nullptr; }
 
-int mb_tree_stats(mb_tree *t, double *h_weight_sum, double *h_max_leaf, void *stream) {
+int mb_tree_stats(mb_tree *t, double *h_weight_sum, double *h_max_leaf, int *h_max_leaf_dtype, void *stream) {
     if (!t) return MB_ERR_INVALID;
     mb::DeviceGuard g(t->device);
     cudaStream_t s = (cudaStream_t)stream;
@@ -500,9 +521,12 @@ int mb_tree_stats(mb_tree *t, double *h_weight_sum, double *h_max_leaf, void *st
                             cudaMemcpyDeviceToHost, s));
     MB_CUDA(cudaMemcpyAsync(&t->h_state->max_leaf, &t->dev.st->max_leaf, sizeof(double),
                             cudaMemcpyDeviceToHost, s));
+    MB_CUDA(cudaMemcpyAsync(&t->h_state->max_is_f32, &t->dev.st->max_is_f32, sizeof(int),
+                            cudaMemcpyDeviceToHost, s));
     MB_CUDA(cudaStreamSynchronize(s));
     if (h_weight_sum) *h_weight_sum = t->h_state->isw_max;
     if (h_max_leaf) *h_max_leaf = t->h_state->max_leaf;
+    if (h_max_leaf_dtype) *h_max_leaf_dtype = t->h_state->max_is_f32 ? MB_F32 : MB_F64;
     return MB_OK;
 }
 
@@ -526,6 +550,8 @@ int mb_tree_clear(mb_tree *t, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     MB_CUDA(cudaMemsetAsync(t->dev.W, 0, sizeof(double) * (size_t)t->dev.total, s));
     MB_CUDA(cudaMemsetAsync(t->dev.st, 0, sizeof(TreeState), s));
+    tree_state_reset<<<1, 1, 0, s>>>(t->dev.st, 0.0);
+    MB_LAUNCH_CHECK();
     return MB_OK;
 }
 

@@ -1,0 +1,163 @@
+"""Double DQN with prioritized replay on the device: reference ``DQNPer`` surface.
+
+Mirror of machin/frame/algorithms/dqn_per.py:15-195 (+ dqn.py for act*/store_episode).  The
+learner step keeps every tensor in HBM:
+
+    PER draw (sumtree.cu) -> row gather (rows.cu) -> user Q-net forward x3 (torch) ->
+    target / |delta| / IS-weighted loss (td.cu) -> priority write-back (sumtree.cu) ->
+    backward, clip, optimizer step (torch) -> soft update (td.cu)
+
+and only ``value_loss.item()`` -- which the reference also returns -- touches the host.
+"""
+from typing import Any, Callable, Dict, List, Tuple, Union
+
+import numpy as np
+import torch as t
+import torch.nn as nn
+
+from ... import ops
+from ..buffers import PrioritizedBuffer
+from ..transition import Transition
+from .base import TorchFramework
+from .utils import hard_update, model_device, safe_call, soft_update
+
+
+class DQNPer(TorchFramework):
+    _is_top = ["qnet", "qnet_target"]
+    _is_restorable = ["qnet_target"]
+
+    def __init__(self, qnet: nn.Module, qnet_target: nn.Module, optimizer: Callable, criterion: Callable, *_,
+                 lr_scheduler: Callable = None, lr_scheduler_args: Tuple[Tuple] = None,
+                 lr_scheduler_kwargs: Tuple[Dict] = None, batch_size: int = 100, epsilon_decay: float = 0.9999,
+                 update_rate: Union[float, None] = 0.005, update_steps: Union[int, None] = None,
+                 learning_rate: float = 0.001, discount: float = 0.99, gradient_max: float = np.inf,
+                 replay_size: int = 500000, replay_device: Union[str, t.device] = None,
+                 replay_buffer: PrioritizedBuffer = None, visualize: bool = False, visualize_dir: str = "", **__):
+        self.batch_size = batch_size
+        self.epsilon_decay = epsilon_decay
+        self.update_rate = update_rate
+        self.update_steps = update_steps
+        self.discount = discount
+        self.grad_max = gradient_max
+        self.visualize = visualize
+        self.visualize_dir = visualize_dir
+        self.mode = "double"
+        self.epsilon = 1
+        self._update_counter = 0
+        if update_rate is not None and update_steps is not None:
+            raise ValueError("You can only specify one target network update scheme, either by update_rate or "
+                             "update_steps, but not both.")
+        self.qnet = qnet
+        self.qnet_target = qnet_target
+        self.qnet_optim = optimizer(self.qnet.parameters(), lr=learning_rate)
+        device = model_device(qnet)
+        self.replay_buffer = (PrioritizedBuffer(replay_size, replay_device if replay_device is not None else device)
+                              if replay_buffer is None else replay_buffer)
+        # "Make sure target and online networks have the same weight" -- the reference copies the
+        # TARGET into the online net here (dqn.py:198-200, hard_update(self.qnet, self.qnet_target))
+        with t.no_grad():
+            hard_update(self.qnet, self.qnet_target)
+        if lr_scheduler is not None:
+            self.qnet_lr_sch = lr_scheduler(self.qnet_optim, *((lr_scheduler_args or ((),))[0]),
+                                            **((lr_scheduler_kwargs or ({},))[0]))
+        self.criterion = criterion
+        if not hasattr(self.criterion, "reduction"):
+            raise RuntimeError("Criterion does not have the 'reduction' property, are you using a custom criterion?")
+        if getattr(self.criterion, "reduction") != "none":
+            self.criterion.reduction = "none"   # dqn_per.py:76-87
+        # MSELoss: loss, |delta| and dloss/dq all come out of one kernel (td.cu)
+        self._fused_mse = isinstance(self.criterion, nn.MSELoss)
+        super().__init__()
+
+    # ------------------------------------------------------------------ properties / acting (dqn.py:213-331)
+    @property
+    def optimizers(self):
+        return [self.qnet_optim]
+
+    @optimizers.setter
+    def optimizers(self, optimizers):
+        self.qnet_optim = optimizers[0]
+
+    @property
+    def lr_schedulers(self):
+        return [self.qnet_lr_sch] if hasattr(self, "qnet_lr_sch") else []
+
+    def act_discrete(self, state: Dict[str, Any], use_target: bool = False, **__):
+        result, *others = safe_call(self.qnet_target if use_target else self.qnet, state)
+        result = t.argmax(result, dim=1).view(-1, 1)
+        return result if len(others) == 0 else (result, *others)
+
+    def act_discrete_with_noise(self, state: Dict[str, Any], use_target: bool = False, decay_epsilon: bool = True, **__):
+        result, *others = safe_call(self.qnet_target if use_target else self.qnet, state)
+        action_dim = result.shape[1]
+        result = t.argmax(result, dim=1).view(-1, 1)
+        if t.rand([1]).item() < self.epsilon:
+            result = t.randint(0, action_dim, [result.shape[0], 1])
+        if decay_epsilon:
+            self.epsilon *= self.epsilon_decay
+        return result if len(others) == 0 else (result, *others)
+
+    def _criticize(self, state: Dict[str, Any], use_target: bool = False, **__):
+        return safe_call(self.qnet_target if use_target else self.qnet, state)[0]
+
+    def store_episode(self, episode: List[Union[Transition, Dict]]):
+        self.replay_buffer.store_episode(
+            episode, required_attrs=("state", "action", "reward", "next_state", "terminal"))
+
+    @staticmethod
+    def action_get_function(sampled_actions):
+        return sampled_actions["action"]
+
+    # ------------------------------------------------------------------ learner step (dqn_per.py:89-161)
+    def _sample(self, uniform=None):
+        n, fields, d_index, d_isw = self.replay_buffer.sample_device(self.batch_size, uniform=uniform)
+        group = lambda attr: {f.key: fields[f.name] for f in self.replay_buffer.storage.fields.values()
+                              if f.attr == attr and f.kind == "major"}
+        return n, group("state"), group("action"), fields["reward"], group("next_state"), fields["terminal"], d_index, d_isw
+
+    def update_device(self, update_value=True, update_target=True, uniform: t.Tensor = None) -> t.Tensor:
+        """One learner update without any host synchronisation; returns the loss as a CUDA scalar."""
+        self.qnet.train()
+        batch_size, state, action, reward, next_state, terminal, d_index, d_isw = self._sample(uniform)
+        with t.no_grad():
+            next_q_value = self._criticize(next_state)
+            target_next_q_value = self._criticize(next_state, True)
+        q_value = self._criticize(state)
+        act = self.action_get_function(action)
+        td = ops.td_dqn(q_value.detach(), next_q_value, target_next_q_value, act, reward, terminal, self.discount,
+                        is_weight=d_isw, mode=self.mode, want_grad=self._fused_mse)
+        if self._fused_mse:
+            value_loss = td["loss_elem"].mean()
+        else:
+            action_value = q_value.gather(dim=1, index=act.to(dtype=t.long))
+            value_loss = (self.criterion(action_value, td["y"]) * d_isw.view(batch_size, 1)).mean()
+        self.replay_buffer.update_priority(td["abs_error"], d_index)
+        if update_value:
+            self.qnet.zero_grad()
+            if self._fused_mse:
+                q_value.backward(td["grad_q"])
+            else:
+                self._backward(value_loss)
+            nn.utils.clip_grad_norm_(self.qnet.parameters(), self.grad_max)
+            self.qnet_optim.step()
+        if update_target:
+            if self.update_rate is not None:
+                soft_update(self.qnet_target, self.qnet, self.update_rate)
+            else:
+                self._update_counter += 1
+                if self._update_counter % self.update_steps == 0:
+                    hard_update(self.qnet_target, self.qnet)
+        self.qnet.eval()
+        return value_loss
+
+    def update(self, update_value=True, update_target=True, concatenate_samples=True, **__):
+        return self.update_device(update_value, update_target).item()
+
+    def update_lr_scheduler(self):
+        if hasattr(self, "qnet_lr_sch"):
+            self.qnet_lr_sch.step()
+
+    def load(self, model_dir, network_map=None, version=-1):
+        super().load(model_dir, network_map, version)
+        with t.no_grad():
+            hard_update(self.qnet, self.qnet_target)

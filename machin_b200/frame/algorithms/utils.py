@@ -1,0 +1,70 @@
+"""Helpers shared by the algorithm mirrors (machin/frame/algorithms/utils.py:8-161)."""
+import inspect
+from typing import Dict
+
+import torch as t
+import torch.nn as nn
+
+from ... import ops
+
+_SPEC_CACHE: Dict[int, tuple] = {}
+
+
+def _unwrap(model):
+    if isinstance(model, (nn.parallel.DistributedDataParallel, nn.parallel.DataParallel)):
+        return model.module
+    return model
+
+
+def model_device(model) -> t.device:
+    model = _unwrap(model)
+    if hasattr(model, "input_device"):
+        return t.device(model.input_device)
+    devices = {p.device for p in model.parameters()}
+    if len(devices) != 1:
+        raise RuntimeError(f"Failed to automatically determine i/o device of your model: {type(model)}; "
+                           f"detected devices: {devices}")
+    return next(iter(devices))
+
+
+def safe_call(model, *named_args, method="__call__"):
+    """Call ``model`` with the dict entries its forward() names, moved to the model's input device;
+    always returns a tuple (utils.py:52-161)."""
+    inner = _unwrap(model)
+    fn = inner.forward if method == "__call__" else getattr(inner, method)
+    key = (id(type(inner)), method)
+    spec = _SPEC_CACHE.get(key)
+    if spec is None:
+        s = inspect.getfullargspec(fn)
+        args = s.args[1:] + s.kwonlyargs
+        with_defaults = args[len(s.args[1:]) - len(s.defaults):len(s.args[1:])] if s.defaults else []
+        required = set(args) - set(with_defaults) - set((s.kwonlydefaults or {}).keys())
+        spec = (set(args), required, s.varargs is not None or s.varkw is not None)
+        _SPEC_CACHE[key] = spec
+    args, required, open_ended = spec
+    dev = model_device(model)
+    call_args = {}
+    for na in named_args:
+        for k, v in na.items():
+            if k in args or open_ended:
+                call_args[k] = v.to(dev) if t.is_tensor(v) else v
+    missing = required - set(call_args)
+    if missing:
+        raise RuntimeError(f"Required arguments of the forward function of Model {type(inner)} is {required}, "
+                           f"missing required arguments: {missing}\n\nCheck your storage functions.")
+    result = (model if method == "__call__" else getattr(model, method))(**call_args)
+    return result if isinstance(result, tuple) else (result,)
+
+
+def hard_update(target_net: nn.Module, source_net: nn.Module) -> None:
+    with t.no_grad():
+        for tb, b in zip(target_net.buffers(), source_net.buffers()):
+            tb.data.copy_(b.data)
+        for tp, p in zip(target_net.parameters(), source_net.parameters()):
+            tp.data.copy_(p.data)
+
+
+def soft_update(target_net: nn.Module, source_net: nn.Module, update_rate) -> None:
+    """target = target * (1 - rate) + source * rate, one kernel per parameter block (csrc/td.cu)."""
+    with t.no_grad():
+        ops.soft_update(target_net, source_net, update_rate)

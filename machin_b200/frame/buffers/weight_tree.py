@@ -58,9 +58,11 @@ class WeightTree:
         return _lib.stream_ptr(t.cuda.current_stream(self.device))
 
     def _stats(self):
-        s, m = C.c_double(), C.c_double()
-        _lib.check(lib.mb_tree_stats(self._h, C.byref(s), C.byref(m), self._stream()))
-        return s.value, m.value
+        s, m, d = C.c_double(), C.c_double(), C.c_int()
+        _lib.check(lib.mb_tree_stats(self._h, C.byref(s), C.byref(m), C.byref(d), self._stream()))
+        # the reference keeps max_leaf in the dtype of the batch that set it (np.float32 after a
+        # float32 priority write-back), and normalize(max_leaf) is evaluated in that dtype
+        return s.value, (np.float32(m.value) if d.value == _lib.MB_F32 else m.value)
 
     def check(self):
         """Raise the deferred ``ValueError`` of an asynchronous (CUDA tensor) call, if any."""
