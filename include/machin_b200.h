@@ -47,6 +47,9 @@ int mb_abi_version(void);
 const char *mb_status_string(int status);
 const char *mb_last_cuda_error(void);
 int mb_device_count(void);
+/* number of CUDA kernels this library has launched in this process (monotonic; bench.py reports
+ * the difference over its timed region as gpu_launches) */
+long long mb_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Sum tree  (machin/frame/buffers/prioritized_buffer.py:8-231, class WeightTree)

@@ -46,6 +46,7 @@ SIGNATURES = {
     "mb_status_string": (C.c_char_p, [i32]),
     "mb_last_cuda_error": (C.c_char_p, []),
     "mb_device_count": (i32, []),
+    "mb_launch_count": (C.c_longlong, []),
     "mb_tree_create": (i32, [i64, i32, C.POINTER(vp)]),
     "mb_tree_destroy": (i32, [vp]),
     "mb_tree_geometry": (i32, [vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]),

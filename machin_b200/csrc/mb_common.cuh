@@ -10,6 +10,7 @@
 namespace mb {
 
 void set_cuda_error(cudaError_t e, const char *file, int line);
+void count_launch(int n);  // kernels launched by this library (mb_launch_count)
 
 #define MB_CUDA(expr)                                        \
     do {                                                     \
@@ -21,6 +22,12 @@ void set_cuda_error(cudaError_t e, const char *file, int line);
     } while (0)
 
 #define MB_LAUNCH_CHECK() MB_CUDA(cudaGetLastError())
+// record n kernel launches, then check the launch status
+#define MB_LAUNCHED(n)       \
+    do {                     \
+        mb::count_launch(n); \
+        MB_LAUNCH_CHECK();   \
+    } while (0)
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 

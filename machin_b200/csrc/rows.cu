@@ -79,7 +79,7 @@ int launch_rows(bool gather, void *ring, int64_t pitch, int64_t capacity, const 
         rows_move_kernel<true><<<(unsigned)blocks, 256, 0, s>>>((char *)ring, pitch, capacity, index, 0, n, fl);
     else
         rows_move_kernel<false><<<(unsigned)blocks, 256, 0, s>>>((char *)ring, pitch, capacity, nullptr, first_slot, n, fl);
-    MB_LAUNCH_CHECK();
+    MB_LAUNCHED(1);
     return MB_OK;
 }
 

@@ -1,4 +1,5 @@
 // Status strings, CUDA error capture and per-device staging for the *_host entry points.
+#include <atomic>
 #include <mutex>
 
 #include "mb_common.cuh"
@@ -12,6 +13,10 @@ void set_cuda_error(cudaError_t e, const char *file, int line) {
              cudaGetErrorString(e), file, line);
     cudaGetLastError();  // clear the sticky-less error so later calls can proceed
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 static std::mutex g_staging_mu;
 static Staging g_staging[64];
@@ -51,7 +56,11 @@ int Staging::ensure(size_t host_bytes, size_t dev_bytes) {
 
 extern "C" {
 
+
+
 int mb_abi_version(void) { return MB_ABI_VERSION; }
+
+long long mb_launch_count(void) { return mb::launches(); }
 
 const char *mb_status_string(int status) {
     switch (status) {

@@ -175,7 +175,7 @@ int mb_vtrace(const int64_t *d_offsets, int64_t n_episodes, int64_t n_steps, con
     vtrace_kernel<<<blocks, kEpisodesPerCta, 0, (cudaStream_t)stream>>>(
         d_offsets, n_episodes, n_steps, d_value, d_next_value, d_reward, d_terminal, d_log_pi, d_log_mu, discount,
         clip_c, clip_rho, d_vs, d_vss, d_rho, d_adv);
-    MB_LAUNCH_CHECK();
+    MB_LAUNCHED(1);
     return MB_OK;
 }
 
@@ -191,7 +191,7 @@ int mb_gae(const int64_t *d_offsets, int64_t n_episodes, int64_t n_steps, const 
     gae_kernel<<<(unsigned)((n_episodes + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         d_offsets, n_episodes, n_steps, d_reward, d_terminal, d_critic_value, d_next_critic_value, discount,
         gae_lambda, d_returns, d_gae);
-    MB_LAUNCH_CHECK();
+    MB_LAUNCHED(1);
     return MB_OK;
 }
 

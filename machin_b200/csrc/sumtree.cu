@@ -569,7 +569,7 @@ int mb_tree_build(mb_tree *t, const double *d_leaves, int64_t n, void *stream) {
     }
     if (lv < t->dev.depth - 1 || lv == 0)
         tree_build_top<<<1, 1024, 0, s>>>(t->dev, lv, lv == 0 ? d_leaves : nullptr);
-    MB_LAUNCH_CHECK();
+    MB_LAUNCHED(2 + (t->dev.depth - 1) / 11);
     return MB_OK;
 }
 
@@ -578,7 +578,7 @@ int mb_tree_find(mb_tree *t, const double *d_query, int64_t n, int64_t *d_index,
     if (n == 0) return MB_OK;
     mb::DeviceGuard g(t->device);
     tree_find_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(t->dev, d_query, n, d_index);
-    MB_LAUNCH_CHECK();
+    MB_LAUNCHED(1);
     return MB_OK;
 }
 
@@ -587,7 +587,7 @@ int mb_tree_leaf_weight(mb_tree *t, const int64_t *d_index, int64_t n, double *d
     if (n == 0) return MB_OK;
     mb::DeviceGuard g(t->device);
     tree_leaf_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(t->dev, d_index, n, d_weight);
-    MB_LAUNCH_CHECK();
+    MB_LAUNCHED(1);
     return MB_OK;
 }
 
@@ -604,7 +604,7 @@ static int launch_update(mb_tree *t, const int64_t *d_index, const void *d_weigh
             tree_update_kernel<float, false><<<1, threads, 0, s>>>(t->dev, d_index, (const float *)d_weight, d_valid, n, nz, gen);
         else
             tree_update_kernel<double, false><<<1, threads, 0, s>>>(t->dev, d_index, (const double *)d_weight, d_valid, n, nz, gen);
-        MB_LAUNCH_CHECK();
+        MB_LAUNCHED(1);
         return MB_OK;
     }
     int64_t blocks = (n + 1023) / 1024;
@@ -613,6 +613,7 @@ static int launch_update(mb_tree *t, const int64_t *d_index, const void *d_weigh
     const void *fn = dtype == MB_F32 ? (const void *)tree_update_kernel<float, true>
                                      : (const void *)tree_update_kernel<double, true>;
     MB_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(1024), args, 0, s));
+    mb::count_launch(1);
     return MB_OK;
 }
 
@@ -634,7 +635,7 @@ int mb_tree_update_leaf(mb_tree *t, double weight, int64_t index, void *stream) 
     if (index < 0 || index > t->dev.size || index >= t->n_leaf_pad) return MB_ERR_INDEX_OOB;
     mb::DeviceGuard g(t->device);
     tree_update_one_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(t->dev, weight, index);
-    MB_LAUNCH_CHECK();
+    MB_LAUNCHED(1);
     return MB_OK;
 }
 
@@ -652,8 +653,9 @@ int mb_per_sample(mb_tree *t, const double *d_uniform, int64_t n, int64_t n_stor
         per_isw_reset<<<1, 1, 0, s>>>(t->dev.st);
         per_sample_large<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t->dev, d_uniform, n, a, d_index, d_is_weight);
         per_normalize<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t->dev.st, d_is_weight, n);
+        mb::count_launch(2);
     }
-    MB_LAUNCH_CHECK();
+    MB_LAUNCHED(1);
     return MB_OK;
 }
 

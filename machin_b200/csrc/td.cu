@@ -83,7 +83,7 @@ int mb_td_dqn(const float *d_q, const float *d_q_next, const float *d_q_tgt_next
     td_dqn_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         d_q, d_q_next, d_q_tgt_next, batch, n_actions, d_action, d_reward, d_terminal, d_is_weight, discount, mode,
         d_y, d_action_value, d_abs_error, d_loss_elem, d_grad_q);
-    MB_LAUNCH_CHECK();
+    MB_LAUNCHED(1);
     return MB_OK;
 }
 
@@ -93,7 +93,7 @@ int mb_td_target(const float *d_next_value, const float *d_reward, const uint8_t
     if (batch == 0) return MB_OK;
     td_target_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         d_next_value, d_reward, d_terminal, batch, discount, d_value, d_y, d_abs_error);
-    MB_LAUNCH_CHECK();
+    MB_LAUNCHED(1);
     return MB_OK;
 }
 
@@ -103,7 +103,7 @@ int mb_soft_update(float *d_target, const float *d_source, int64_t n, double rat
     // python: target * (1.0 - update_rate) + param * update_rate ; both scalars become float32
     soft_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         d_target, d_source, n, (float)(1.0 - rate), (float)rate);
-    MB_LAUNCH_CHECK();
+    MB_LAUNCHED(1);
     return MB_OK;
 }
 
