@@ -48,6 +48,7 @@ def parse():
     p.add_argument("--cpu-storage-rows", type=int, default=50_000)
     p.add_argument("--cpu-steps", type=int, default=1500)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per update")
     return p.parse_args()
 
 
@@ -57,32 +58,50 @@ def workload_name(a):
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
-def cpu_learner_rate(a, steps, warmup):
-    """Oracle port of the reference learner on the host cores -> (transitions/s, ms/step, threads)."""
+def cpu_learner_rate(a, steps, warmup, budget_s=25.0):
+    """Oracle port of the reference learner on the host cores -> (transitions/s, ms/step, threads, steps).
+
+    The MLP is tiny, so "all cores" is not the fastest setting (128 threads is ~500x slower than 8 on
+    the GPU box): the thread count is calibrated over {1,2,4,8,16,32,all} and the best one is timed.
+    The run stops after ``steps`` updates or ``budget_s`` seconds, whichever comes first."""
     import torch as t
     from oracle.learner import CpuDqnPerLearner
 
-    t.set_num_threads(os.cpu_count() or 1)
     np.random.seed(0)
     learner = CpuDqnPerLearner(a.replay_rows, a.cpu_storage_rows, STATE_DIM, N_ACTIONS, a.batch, hidden=HIDDEN)
+    ncpu = os.cpu_count() or 1
+    best, best_dt = 1, float("inf")
+    for th in [c for c in (1, 2, 4, 8, 16, 32) if c <= ncpu] + ([ncpu] if ncpu <= 64 else []):
+        t.set_num_threads(th)
+        learner.step()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            learner.step()
+        dt = time.perf_counter() - t0
+        if dt < best_dt:
+            best, best_dt = th, dt
+    t.set_num_threads(best)
     for _ in range(warmup):
         learner.step()
     t0 = time.perf_counter()
-    for _ in range(steps):
+    done = 0
+    while done < steps and time.perf_counter() - t0 < budget_s:
         learner.step()
+        done += 1
     dt = time.perf_counter() - t0
-    return a.batch * steps / dt, dt / steps * 1e3, t.get_num_threads()
+    return a.batch * done / dt, dt / done * 1e3, best, done
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, ms, threads = cpu_learner_rate(a, a.steps, max(a.warmup, 3))
-    sample = (f"{a.steps} updates of the full algorithm; float64 sum tree at full size ({a.replay_rows} leaves), "
+    value, ms, threads, done = cpu_learner_rate(a, a.steps, max(a.warmup, 3), budget_s=120.0)
+    sample = (f"{done} updates of the full algorithm, best of thread counts 1..32 -> {threads} threads "
+              f"({os.cpu_count()} cores present); float64 sum tree at full size ({a.replay_rows} leaves), "
               f"Python-object storage capped at {a.cpu_storage_rows} rows (slots folded with index % rows)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": done,
         "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64 tree + f32 TD", "data": "synthetic",
         "learner_updates_per_sec": value / a.batch,
@@ -196,41 +215,74 @@ KERNELS = {  # C entry point -> (label, algorithmic bytes per launch as f(batch,
 }
 
 
-def time_kernels(learner, uniforms, steps):
-    """Event-time every libmachin_b200 kernel inside the real step sequence (torch's current stream)."""
+def time_kernels(learner, table, reps=20, per_graph=16):
+    """Average device time per launch of each libmachin_b200 kernel of the step.
+
+    Eager launches are CPU-launch-bound (the kernels take microseconds), so each kernel is captured
+    ``per_graph`` times into a CUDA graph -- with a different, really sampled index set per launch -- and
+    the graph is replayed ``reps`` times between CUDA events on the launching stream."""
     import torch as t
-    from machin_b200 import _lib
+    from machin_b200 import _lib, ops
+    from machin_b200._lib import lib
 
-    records = {k: [] for k in KERNELS}
-    originals = {}
+    buf = learner.replay_buffer
+    dev, B = buf.buffer_device, learner.batch_size
+    tree = buf.wt_tree.handle
+    n_stored = len(buf.storage)
+    idx = [t.empty(B, dtype=t.int64, device=dev) for _ in range(per_graph)]
+    isw = [t.empty(B, dtype=t.float64, device=dev) for _ in range(per_graph)]
+    err = [t.rand(B, device=dev) for _ in range(per_graph)]
+    q = [t.randn(B, N_ACTIONS, device=dev) for _ in range(3)]
+    sp = lambda: _lib.stream_ptr()
 
-    def wrap(name):
-        fn = getattr(_lib.lib, name)
-        originals[name] = fn
+    def k_sample(i):
+        _lib.check(lib.mb_per_sample(tree, _lib.ptr(table[i]), B, n_stored, 0.0, 0.4, None, _lib.ptr(idx[i]),
+                                     _lib.ptr(isw[i]), sp()))
 
-        def timed(*args):
-            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
-            e0.record()
-            r = fn(*args)
-            e1.record()
-            records[name].append((e0, e1))
-            return r
-        return timed
+    for i in range(per_graph):
+        k_sample(i)
+    fields = buf.storage.gather(idx[0])
+    names = list(buf.storage.fields)
+    arr = buf.storage._field_array(names, fields)
 
-    for k in KERNELS:
-        setattr(_lib.lib, k, wrap(k))
-    try:
-        for s in range(steps):
-            learner.update_device(uniform=uniforms[s])
-        t.cuda.synchronize()
-    finally:
-        for k, fn in originals.items():
-            setattr(_lib.lib, k, fn)
+    def k_gather(i):
+        _lib.check(lib.mb_rows_gather(_lib.ptr(buf.storage.data), buf.storage.pitch, buf.storage.max_size,
+                                      _lib.ptr(idx[i]), B, arr, len(names), sp()))
+
+    def k_td(i):
+        ops.td_dqn(q[0], q[1], q[2], fields["action/action"], fields["reward"], fields["terminal"], 0.99,
+                   is_weight=isw[i], want_grad=True)
+
+    def k_update(i):
+        _lib.check(lib.mb_tree_update_priority(tree, _lib.ptr(idx[i]), _lib.ptr(err[i]), _lib.MB_F32, None, B,
+                                               buf.epsilon, buf.alpha, sp()))
+
+    def k_soft(i):
+        ops.soft_update(learner.qnet_target, learner.qnet, 0.0)  # rate 0: same traffic, weights unchanged
+
     out = {}
-    for k, ev in records.items():
-        if ev:
-            ms = [a.elapsed_time(b) for a, b in ev]
-            out[k] = {"launches": len(ms), "avg_us": float(np.mean(ms)) * 1e3, "per_step": len(ms) / steps}
+    for name, fn in (("mb_per_sample", k_sample), ("mb_rows_gather", k_gather), ("mb_td_dqn", k_td),
+                     ("mb_tree_update_priority", k_update), ("mb_soft_update", k_soft)):
+        side = t.cuda.Stream(device=dev)
+        side.wait_stream(t.cuda.current_stream(dev))
+        with t.cuda.stream(side):
+            fn(0)
+        t.cuda.current_stream(dev).wait_stream(side)
+        t.cuda.synchronize(dev)
+        g = t.cuda.CUDAGraph()
+        with t.cuda.graph(g):
+            for i in range(per_graph):
+                fn(i)
+        g.replay()
+        t.cuda.synchronize(dev)
+        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        t.cuda.synchronize(dev)
+        out[name] = {"avg_us": e0.elapsed_time(e1) * 1e3 / (reps * per_graph), "launches_timed": reps * per_graph,
+                     "per_step": 1.0}
     return out
 
 
@@ -249,6 +301,8 @@ def run_b200(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     learner = build_learner(a, device, seed=rank)
+    if not a.no_graph:
+        learner.enable_cuda_graph()
     K, W, B = a.steps, max(a.warmup, 3), a.batch
     depth = learner.replay_buffer.wt_tree.depth
     n_params = sum(p.numel() for p in learner.qnet.parameters())
@@ -289,7 +343,7 @@ def run_b200(a):
     barrier()
     e2e_ms = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3)
     # ---- per-kernel event timing inside the step
-    kern = time_kernels(learner, table, min(K, 500)) if rank == 0 else {}
+    kern = time_kernels(learner, table) if rank == 0 else {}
     clocks = sampler.stop()
     tt = t.tensor([ms_total, e2e_ms], device=device, dtype=t.float64)
     if world > 1:
@@ -310,7 +364,7 @@ def run_b200(a):
     roofline = None
     if dom:
         label, fbytes = KERNELS[dom]
-        bytes_per_launch = fbytes(B, n_params, depth) / max(1.0, kern[dom]["per_step"]) if dom == "mb_soft_update" else fbytes(B, n_params, depth)
+        bytes_per_launch = fbytes(B, n_params, depth)
         achieved = bytes_per_launch / (kern[dom]["avg_us"] * 1e-6) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -323,10 +377,11 @@ def run_b200(a):
                             "(DESIGN.md section 5 reports the saturated-throughput figures per kernel)"}
     cpu = None
     if not a.no_cpu_baseline and world == 1:
-        v, ms, threads = cpu_learner_rate(a, a.cpu_steps, 5)
+        v, ms, threads, done = cpu_learner_rate(a, a.cpu_steps, 5)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": ms,
-               "sample": (f"{a.cpu_steps} full learner updates of oracle/learner.py (NumPy float64 tree at full size, "
-                          f"Python-object storage capped at {a.cpu_storage_rows} rows, CPU torch MLP)")}
+               "sample": (f"{done} full learner updates of oracle/learner.py (NumPy float64 tree at full size, "
+                          f"Python-object storage capped at {a.cpu_storage_rows} rows, CPU torch MLP); best of thread "
+                          f"counts 1..32 -> {threads} threads, {os.cpu_count()} cores present")}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -334,6 +389,7 @@ def run_b200(a):
         "learner_updates_per_sec": K / (ms_total * 1e-3),
         "config": {"workload": workload_name(a), "batch": B, "replay_rows": a.replay_rows, "optimizer": "Adam",
                    "parallelism": f"{world} learner(s), one replay shard each",
+                   "launch": "eager" if a.no_graph else "one CUDA graph per update",
                    "l2": "inputs larger than L2: 268 MB tree + 6.9 GB ring, randomly addressed every step"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 8,
                 "ms_per_step": e2e_ms / K, "last_loss": last},

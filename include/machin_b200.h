@@ -76,6 +76,9 @@ int mb_tree_stats(mb_tree *tree, double *h_weight_sum, double *h_max_leaf, int *
 /* device pointers to the root node and to the running leaf maximum (no sync) */
 const double *mb_tree_root_ptr(mb_tree *tree);
 const double *mb_tree_max_leaf_ptr(mb_tree *tree);
+/* device address + size of the tree's scalar state (running max and its dtype flag, deferred
+ * error): with mb_tree_weights() this is everything needed to snapshot / restore a tree in place */
+void *mb_tree_state_blob(mb_tree *tree, int64_t *nbytes);
 /* Deferred error of asynchronous device-side index validation: returns MB_OK or
  * MB_ERR_INDEX_OOB (and clears it).  Blocks on `stream`. */
 int mb_tree_check(mb_tree *tree, void *stream);
@@ -181,6 +184,11 @@ int mb_td_target(const float *d_next_value, const float *d_reward, const uint8_t
 /* soft_update (algorithms/utils.py:8-27): target = target * (1 - rate) + source * rate, over a
  * flat float32 parameter block */
 int mb_soft_update(float *d_target, const float *d_source, int64_t n, double rate, void *stream);
+/* the same over every parameter tensor of a network in one launch per MB_MAX_SOFT_TENSORS tensors;
+ * d_targets / d_sources / sizes are HOST arrays of n_tensors device pointers / element counts */
+#define MB_MAX_SOFT_TENSORS 24
+int mb_soft_update_multi(float *const *d_targets, const float *const *d_sources, const int64_t *sizes,
+                         int n_tensors, double rate, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Trajectory reverse scans

@@ -54,6 +54,7 @@ SIGNATURES = {
     "mb_tree_stats": (i32, [vp, C.POINTER(f64), C.POINTER(f64), C.POINTER(i32), vp]),
     "mb_tree_root_ptr": (vp, [vp]),
     "mb_tree_max_leaf_ptr": (vp, [vp]),
+    "mb_tree_state_blob": (vp, [vp, C.POINTER(i64)]),
     "mb_tree_check": (i32, [vp, vp]),
     "mb_tree_clear": (i32, [vp, vp]),
     "mb_tree_build": (i32, [vp, vp, i64, vp]),
@@ -75,6 +76,7 @@ SIGNATURES = {
     "mb_td_dqn": (i32, [vp, vp, vp, i64, i32, vp, vp, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]),
     "mb_td_target": (i32, [vp, vp, vp, i64, f32, vp, vp, vp, vp]),
     "mb_soft_update": (i32, [vp, vp, i64, f64, vp]),
+    "mb_soft_update_multi": (i32, [C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i32, f64, vp]),
     "mb_vtrace": (i32, [vp, i64, i64, vp, vp, vp, vp, vp, vp, f32, f32, f32, vp, vp, vp, vp, vp]),
     "mb_gae": (i32, [vp, i64, i64, vp, vp, vp, vp, f64, f64, vp, vp, vp]),
     "mb_vtrace_host": (i32, [i32, vp, i64, i64, vp, vp, vp, vp, vp, vp, f32, f32, f32, vp, vp, vp, vp]),

@@ -512,6 +512,10 @@ int mb_tree_geometry(const mb_tree *t, int64_t *size, int *depth, int64_t *n_lea
 double *mb_tree_weights(mb_tree *t) { return t ? t->dev.W : nullptr; }
 const double *mb_tree_root_ptr(mb_tree *t) { return t ? t->dev.W + t->n_nodes - 1 : nullptr; }
 const double *mb_tree_max_leaf_ptr(mb_tree *t) { return t ? &t->dev.st->max_leaf : nullptr; }
+void *mb_tree_state_blob(mb_tree *t, int64_t *nbytes) {
+    if (nbytes) *nbytes = (int64_t)sizeof(TreeState);
+    return t ? (void *)t->dev.st : nullptr;
+}
 
 int mb_tree_stats(mb_tree *t, double *h_weight_sum, double *h_max_leaf, int *h_max_leaf_dtype, void *stream) {
     if (!t) return MB_ERR_INVALID;

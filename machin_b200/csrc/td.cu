@@ -68,6 +68,24 @@ __global__ void __launch_bounds__(256) soft_update_kernel(float *__restrict__ ta
     if (i < n) target[i] = __fadd_rn(__fmul_rn(target[i], keep), __fmul_rn(source[i], rate));
 }
 
+struct SoftList {
+    float *target[MB_MAX_SOFT_TENSORS];
+    const float *source[MB_MAX_SOFT_TENSORS];
+    int64_t start[MB_MAX_SOFT_TENSORS + 1];  // prefix sums of element counts
+    int n;
+};
+
+// All parameter blocks of a network in one launch (one launch per tensor is launch-latency bound).
+__global__ void __launch_bounds__(256) soft_update_multi_kernel(SoftList l, float keep, float rate) {
+    const int64_t total = l.start[l.n];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int k = 0;
+        while (i >= l.start[k + 1]) ++k;
+        const int64_t j = i - l.start[k];
+        l.target[k][j] = __fadd_rn(__fmul_rn(l.target[k][j], keep), __fmul_rn(l.source[k][j], rate));
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -104,6 +122,29 @@ int mb_soft_update(float *d_target, const float *d_source, int64_t n, double rat
     soft_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         d_target, d_source, n, (float)(1.0 - rate), (float)rate);
     MB_LAUNCHED(1);
+    return MB_OK;
+}
+
+int mb_soft_update_multi(float *const *d_targets, const float *const *d_sources, const int64_t *sizes,
+                         int n_tensors, double rate, void *stream) {
+    if (n_tensors < 0 || (n_tensors > 0 && (!d_targets || !d_sources || !sizes))) return MB_ERR_INVALID;
+    for (int base = 0; base < n_tensors; base += MB_MAX_SOFT_TENSORS) {
+        SoftList l;
+        l.n = n_tensors - base < MB_MAX_SOFT_TENSORS ? n_tensors - base : MB_MAX_SOFT_TENSORS;
+        l.start[0] = 0;
+        for (int k = 0; k < l.n; ++k) {
+            if (sizes[base + k] < 0 || !d_targets[base + k] || !d_sources[base + k]) return MB_ERR_INVALID;
+            l.target[k] = d_targets[base + k];
+            l.source[k] = d_sources[base + k];
+            l.start[k + 1] = l.start[k] + sizes[base + k];
+        }
+        const int64_t total = l.start[l.n];
+        if (total == 0) continue;
+        int64_t blocks = (total + 255) / 256;
+        if (blocks > (int64_t)mb::kNumSMs * 8) blocks = (int64_t)mb::kNumSMs * 8;
+        soft_update_multi_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(l, (float)(1.0 - rate), (float)rate);
+        MB_LAUNCHED(1);
+    }
     return MB_OK;
 }
 

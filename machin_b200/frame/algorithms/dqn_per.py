@@ -67,6 +67,7 @@ class DQNPer(TorchFramework):
             self.criterion.reduction = "none"   # dqn_per.py:76-87
         # MSELoss: loss, |delta| and dloss/dq all come out of one kernel (td.cu)
         self._fused_mse = isinstance(self.criterion, nn.MSELoss)
+        self._graph = None
         super().__init__()
 
     # ------------------------------------------------------------------ properties / acting (dqn.py:213-331)
@@ -109,16 +110,89 @@ class DQNPer(TorchFramework):
         return sampled_actions["action"]
 
     # ------------------------------------------------------------------ learner step (dqn_per.py:89-161)
-    def _sample(self, uniform=None):
-        n, fields, d_index, d_isw = self.replay_buffer.sample_device(self.batch_size, uniform=uniform)
+    def _sample(self, uniform=None, use_device_params=False):
+        n, fields, d_index, d_isw = self.replay_buffer.sample_device(self.batch_size, uniform=uniform,
+                                                                     use_device_params=use_device_params)
         group = lambda attr: {f.key: fields[f.name] for f in self.replay_buffer.storage.fields.values()
                               if f.attr == attr and f.kind == "major"}
         return n, group("state"), group("action"), fields["reward"], group("next_state"), fields["terminal"], d_index, d_isw
 
+    # ---- CUDA graph: the whole update is captured once and replayed; only the uniforms change
+    def enable_cuda_graph(self, warmup: int = 3):
+        """Capture :meth:`update_device` (draw -> gather -> forward -> TD -> priority write-back ->
+        backward -> optimizer -> target update) into one CUDA graph.  Needs a capturable optimizer
+        (SGD, or Adam/AdamW with ``capturable=True``, which is switched on here) and a Q-net without
+        data-dependent Python control flow.  torch's capture protocol needs ``warmup`` real updates
+        first; networks, optimizer state, tree and beta are snapshotted before and restored in place
+        after, so enabling the graph does not change the training trajectory."""
+        buf = self.replay_buffer
+        dev = buf.buffer_device
+        fresh_optim = len(self.qnet_optim.state) == 0
+        saved_nets = [[x.detach().clone() for x in list(m.parameters()) + list(m.buffers())]
+                      for m in (self.qnet, self.qnet_target)]
+        saved_optim = {id(p): {k: (v.clone() if t.is_tensor(v) else v) for k, v in st.items()}
+                       for p, st in self.qnet_optim.state.items()}
+        saved_tree, saved_beta, saved_counter = buf.wt_tree.snapshot(), buf.curr_beta, self._update_counter
+        for group in self.qnet_optim.param_groups:
+            if "capturable" in group:
+                group["capturable"] = True
+        for st in self.qnet_optim.state.values():
+            if "step" in st and t.is_tensor(st["step"]) and not st["step"].is_cuda:
+                st["step"] = st["step"].to(dev)
+        buf.enable_graph_params()
+        self._u_static = t.rand(self.batch_size, dtype=t.float64, device=dev)
+        self._u_pinned = t.empty(self.batch_size, dtype=t.float64).pin_memory()
+        self._h2d_done = t.cuda.Event()
+        cur = t.cuda.current_stream(dev)
+        side = t.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with t.cuda.stream(side):
+            for _ in range(warmup):
+                self._step(True, True, self._u_static, True)
+                self._u_static.uniform_()
+        cur.wait_stream(side)
+        t.cuda.synchronize(dev)
+        graph = t.cuda.CUDAGraph()
+        self.qnet_optim.zero_grad(set_to_none=True)
+        with t.cuda.graph(graph):
+            self._static_loss = self._step(True, True, self._u_static, True)
+        self._graph = graph
+        # restore everything the warm-up touched, in place (the graph holds these addresses)
+        with t.no_grad():
+            for m, saved in zip((self.qnet, self.qnet_target), saved_nets):
+                for x, v in zip(list(m.parameters()) + list(m.buffers()), saved):
+                    x.copy_(v)
+            for p, st in self.qnet_optim.state.items():
+                for k, v in st.items():
+                    if t.is_tensor(v):
+                        if fresh_optim:
+                            v.zero_()
+                        elif id(p) in saved_optim:
+                            v.copy_(saved_optim[id(p)][k])
+        buf.wt_tree.restore(saved_tree)
+        buf.curr_beta, self._update_counter = saved_beta, saved_counter
+        buf.sync_graph_params()
+        t.cuda.synchronize(dev)
+
     def update_device(self, update_value=True, update_target=True, uniform: t.Tensor = None) -> t.Tensor:
         """One learner update without any host synchronisation; returns the loss as a CUDA scalar."""
+        if self._graph is not None and update_value and update_target:
+            buf = self.replay_buffer
+            if uniform is None:
+                self._h2d_done.synchronize()
+                self._u_pinned.numpy()[:] = np.random.uniform(size=self.batch_size)   # same stream as :411
+                self._u_static.copy_(self._u_pinned, non_blocking=True)
+                self._h2d_done.record()
+            else:
+                self._u_static.copy_(uniform)
+            self._graph.replay()
+            buf.curr_beta = np.min([1.0, buf.curr_beta + buf.beta_increment_per_sampling])
+            return self._static_loss
+        return self._step(update_value, update_target, uniform, False)
+
+    def _step(self, update_value, update_target, uniform, use_device_params) -> t.Tensor:
         self.qnet.train()
-        batch_size, state, action, reward, next_state, terminal, d_index, d_isw = self._sample(uniform)
+        batch_size, state, action, reward, next_state, terminal, d_index, d_isw = self._sample(uniform, use_device_params)
         with t.no_grad():
             next_q_value = self._criticize(next_state)
             target_next_q_value = self._criticize(next_state, True)
@@ -133,7 +207,7 @@ class DQNPer(TorchFramework):
             value_loss = (self.criterion(action_value, td["y"]) * d_isw.view(batch_size, 1)).mean()
         self.replay_buffer.update_priority(td["abs_error"], d_index)
         if update_value:
-            self.qnet.zero_grad()
+            self.qnet_optim.zero_grad(set_to_none=True)
             if self._fused_mse:
                 q_value.backward(td["grad_q"])
             else:

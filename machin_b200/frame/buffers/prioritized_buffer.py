@@ -102,8 +102,36 @@ class PrioritizedBuffer(Buffer):
         d_index, d_isw = self._draw(batch_size, all_weight_sum)
         return d_index.cpu().numpy(), d_isw.cpu().numpy()
 
-    def _draw(self, batch_size: int, all_weight_sum: float = None, uniform: t.Tensor = None):
+    # ------------------------------------------------------------------ CUDA-graph support
+    def enable_graph_params(self):
+        """Keep (beta, all_weight_sum, n_stored) in a device-side ``mb_per_params`` block so that the
+        draw can be replayed inside a CUDA graph while they change.  ``curr_beta`` is advanced on the
+        device by the captured step (:meth:`advance_beta_device`) and mirrored on the host."""
+        if getattr(self, "_params_raw", None) is None:
+            self._params_raw = t.zeros(32, dtype=t.uint8, device=self.buffer_device)
+            self._params_f64 = self._params_raw.view(t.float64)
+            self._params_i64 = self._params_raw.view(t.int64)
+        self.sync_graph_params()
+
+    def sync_graph_params(self):
+        host = t.tensor([float(self.curr_beta), 0.0], dtype=t.float64).view(t.uint8)
+        ints = t.tensor([len(self.storage), 0], dtype=t.int64).view(t.uint8)
+        self._params_raw.copy_(t.cat([host, ints]))
+
+    def advance_beta_device(self):
+        self._params_f64[0:1].add_(self.beta_increment_per_sampling).clamp_(max=1.0)
+
+    def _draw(self, batch_size: int, all_weight_sum: float = None, uniform: t.Tensor = None,
+              use_device_params: bool = False):
         """Fused stratified draw on the device (csrc/sumtree.cu: per_sample_*)."""
+        if use_device_params:
+            d_index = t.empty(batch_size, dtype=t.int64, device=self.buffer_device)
+            d_isw = t.empty(batch_size, dtype=t.float64, device=self.buffer_device)
+            _lib.check(lib.mb_per_sample(self.wt_tree.handle, _lib.ptr(uniform), batch_size, 0, 0.0, 0.0,
+                                         _lib.ptr(self._params_raw), _lib.ptr(d_index), _lib.ptr(d_isw),
+                                         _lib.stream_ptr()))
+            self.advance_beta_device()
+            return d_index, d_isw
         if uniform is None:
             # same call and same stream as the reference (:411): B doubles from np.random
             uniform = t.from_numpy(np.random.uniform(size=batch_size)).to(self.buffer_device, non_blocking=True)
@@ -115,9 +143,9 @@ class PrioritizedBuffer(Buffer):
         self.curr_beta = np.min([1.0, self.curr_beta + self.beta_increment_per_sampling])
         return d_index, d_isw
 
-    def sample_device(self, batch_size: int, uniform: t.Tensor = None, names=None
+    def sample_device(self, batch_size: int, uniform: t.Tensor = None, names=None, use_device_params=False
                       ) -> Tuple[int, Dict[str, t.Tensor], t.Tensor, t.Tensor]:
         """Device path: returns (n, {field: tensor}, index i64[n], is_weight f64[n]) without any
         host synchronisation.  ``uniform``: optional f64[n] CUDA tensor of U[0,1) draws."""
-        d_index, d_isw = self._draw(batch_size, uniform=uniform)
+        d_index, d_isw = self._draw(batch_size, uniform=uniform, use_device_params=use_device_params)
         return batch_size, self.storage.gather(d_index, names=names), d_index, d_isw

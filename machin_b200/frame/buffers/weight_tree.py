@@ -84,18 +84,30 @@ class WeightTree:
     def max_leaf(self) -> float:
         return self._stats()[1]
 
-    def weights_tensor(self) -> t.Tensor:
-        """Zero-copy CUDA view of the node array (read-only by convention)."""
+    def _view(self, address: int, shape, typestr: str) -> t.Tensor:
         class _Iface:
             pass
 
         obj = _Iface()
-        obj.__cuda_array_interface__ = {
-            "shape": (self.n_nodes,), "typestr": "<f8", "version": 3,
-            "data": (lib.mb_tree_weights(self._h), False),
-        }
+        obj.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "version": 3, "data": (address, False)}
         with t.cuda.device(self.device):
             return t.as_tensor(obj, device=self.device)
+
+    def weights_tensor(self) -> t.Tensor:
+        """Zero-copy CUDA view of the node array (read-only by convention)."""
+        return self._view(lib.mb_tree_weights(self._h), (self.n_nodes,), "<f8")
+
+    def snapshot(self):
+        """Copies of (node array, scalar state) for :meth:`restore` (used around CUDA-graph warm-up)."""
+        n = C.c_int64()
+        addr = lib.mb_tree_state_blob(self._h, C.byref(n))
+        return self.weights_tensor().clone(), self._view(addr, (n.value,), "|u1").clone()
+
+    def restore(self, snap):
+        n = C.c_int64()
+        addr = lib.mb_tree_state_blob(self._h, C.byref(n))
+        self.weights_tensor().copy_(snap[0])
+        self._view(addr, (n.value,), "|u1").copy_(snap[1])
 
     # ------------------------------------------------------------------ reference surface
     def get_weight_sum(self) -> float:

@@ -77,11 +77,25 @@ def soft_update_flat(target: t.Tensor, source: t.Tensor, rate: float):
 
 
 def soft_update(target_net: t.nn.Module, source_net: t.nn.Module, rate: float):
-    for tp, sp in zip(target_net.parameters(), source_net.parameters()):
-        if tp.is_cuda and tp.dtype == t.float32 and tp.is_contiguous():
-            soft_update_flat(tp.data, sp.data.to(tp.device), rate)
-        else:
+    """soft_update over all parameters of a network: one launch (mb_soft_update_multi)."""
+    import ctypes as C
+    tps, sps = list(target_net.parameters()), list(source_net.parameters())
+    n = len(tps)
+    if n == 0:
+        return
+    srcs = []
+    for tp, sp in zip(tps, sps):
+        if not (tp.is_cuda and tp.dtype == t.float32 and tp.is_contiguous()):
             raise RuntimeError("soft_update: parameters must be contiguous float32 CUDA tensors")
+        sp = sp.data
+        if sp.device != tp.device or sp.dtype != t.float32 or not sp.is_contiguous():
+            sp = sp.to(device=tp.device, dtype=t.float32).contiguous()
+        srcs.append(sp)
+    tgt = (C.c_void_p * n)(*[tp.data_ptr() for tp in tps])
+    src = (C.c_void_p * n)(*[sp.data_ptr() for sp in srcs])
+    sizes = (C.c_int64 * n)(*[tp.numel() for tp in tps])
+    with t.cuda.device(tps[0].device):
+        _lib.check(lib.mb_soft_update_multi(tgt, src, sizes, n, float(rate), _lib.stream_ptr()))
 
 
 def vtrace(value, next_value, reward, terminal, log_pi, log_mu, discount: float, clip_c: float = 1.0,

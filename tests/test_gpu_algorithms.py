@@ -36,7 +36,7 @@ def _flat(module):
     return np.concatenate([p.detach().cpu().numpy().reshape(-1) for p in module.parameters()])
 
 
-@pytest.mark.parametrize("criterion", ["mse_fused", "mse_generic"])
+@pytest.mark.parametrize("criterion", ["mse_fused", "mse_generic", "mse_fused_graph"])
 def test_dqn_per_update_vs_reference(criterion):
     from machin_b200.frame.algorithms import DQNPer
     g = np.load(os.path.join(GOLDEN, "ref_td.npz"))
@@ -54,6 +54,10 @@ def test_dqn_per_update_vs_reference(criterion):
                terminal=bool(g["dqn_terminal"][i])) for i in range(N)]
     dqn.replay_buffer.store_episode(ep, priorities=list(g["dqn_priority"]))
     assert np.array_equal(dqn.replay_buffer.wt_tree.weights, g["dqn_tree0"])
+    if criterion == "mse_fused_graph":
+        dqn.enable_cuda_graph()          # whole update replayed as one CUDA graph; state restored after warm-up
+        assert np.array_equal(dqn.replay_buffer.wt_tree.weights, g["dqn_tree0"])
+        assert np.array_equal(_flat(dqn.qnet), g["dqn_init_q"])
     np.random.seed(11)
     for step in range(3):
         loss = dqn.update()

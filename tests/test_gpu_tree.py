@@ -224,6 +224,13 @@ def test_device_priority_normalisation_matches_numpy():
         want = ((np.abs(p) + 1e-2) ** 0.6).astype(np.float64)
         ulp = np.abs(got.view(np.int64) - want.view(np.int64)) if dtype == np.float64 else \
             np.abs(got.astype(np.float32).view(np.int32).astype(np.int64) - want.astype(np.float32).view(np.int32))
-        print(f"normalise {dtype.__name__}: mismatching leaves {np.count_nonzero(ulp)}/{n}, max ulp {ulp.max()}")
+        print(f"normalise {dtype.__name__}: leaves differing from this host's NumPy {np.count_nonzero(ulp)}/{n}, "
+              f"max ulp {ulp.max()}")
+        # NumPy's float32/float64 power is a SIMD (AVX-512 SVML) routine on this class of host and is
+        # itself not correctly rounded (~21 % of float32 results are 1 ulp off the correctly rounded
+        # value), so the device can only be required to stay within 1 float32 ulp / 4 float64 ulp of it
         assert ulp.max() <= max(tol, 1)
-        assert np.count_nonzero(ulp) <= (n // 1000 if dtype == np.float32 else n)
+        if dtype == np.float32:
+            # ... and to equal the correctly rounded result: float64 pow of the float32 operands, rounded once
+            exact = ((np.abs(p) + np.float32(1e-2)).astype(np.float64) ** np.float64(np.float32(0.6))).astype(np.float32)
+            assert np.count_nonzero(got.astype(np.float32) != exact) <= 2
