@@ -342,6 +342,122 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(TreeDev t, const int6
     }
 }
 
+// ---- small batches (n <= 512: the learner's priority write-back), one CTA, latency-optimised ----
+// The generic kernel above pays two dependent L2/HBM round trips per level (24 levels at 10 M leaves).
+// Here every thread owns one entry and (1) prefetches, up front and all at once, the STORED sibling of
+// every node on its leaf-to-root path, (2) walks up keeping the fresh value of its node in a register;
+// at each level the touched nodes are published in a shared-memory hash table so that a thread whose
+// sibling is also touched takes the fresh value instead of the stale prefetched one.  Threads that
+// reach the same node merge (one survivor), so contention is at most two-way.  Parents are still
+// fl(left + right) of the current children: the node array is bit-identical to the generic kernel's.
+constexpr int kSmallN = 512;
+constexpr int kHash = 1024;
+constexpr unsigned kEmpty = 0xffffffffu;
+constexpr int kMaxLevels = 31;
+
+__device__ __forceinline__ unsigned hash_slot(unsigned key) { return (key * 2654435761u) >> 22; }  // 10 bits
+
+template <typename WT>
+__global__ void __launch_bounds__(kSmallN) tree_update_small(TreeDev t, const int64_t *__restrict__ idx,
+                                                             const WT *__restrict__ w,
+                                                             const uint8_t *__restrict__ valid, int n,
+                                                             Normalize nz, int gen) {
+    __shared__ unsigned keys[2][kHash];
+    __shared__ double vals[2][kHash];
+    __shared__ double red[kSmallN / 32];
+    __shared__ int s_bad;
+    const int tid = threadIdx.x;
+    for (int j = tid; j < kHash; j += blockDim.x) {
+        keys[0][j] = kEmpty;
+        keys[1][j] = kEmpty;
+        reinterpret_cast<int *>(&vals[0][j])[0] = -1;  // leaf phase: "last writer" position
+    }
+    if (tid == 0) s_bad = 0;
+    bool alive = tid < n && (!valid || valid[tid]);
+    int64_t k = alive ? idx[tid] : 0;
+    const bool oob = alive && (k < 0 || k >= t.size);
+    double sib[kMaxLevels];
+    if (alive && !oob) {
+#pragma unroll
+        for (int l = 0; l < kMaxLevels; ++l)
+            if (l < t.depth - 1) sib[l] = __ldcg(t.W + level_off(t, l) + ((k >> l) ^ 1));
+    }
+    double val = alive && !oob ? normalized_weight(w[tid], nz) : -INFINITY;
+    __syncthreads();
+    if (oob) s_bad = 1;
+    unsigned slot = 0;
+    if (alive && !oob) {  // leaf dedupe: the highest batch position wins (NumPy fancy assignment)
+        slot = hash_slot((unsigned)k);
+        while (true) {
+            const unsigned prev = atomicCAS(&keys[0][slot], kEmpty, (unsigned)k);
+            if (prev == kEmpty || prev == (unsigned)k) break;
+            slot = (slot + 1) & (kHash - 1);
+        }
+        atomicMax(reinterpret_cast<int *>(&vals[0][slot]), tid);
+    }
+    // max over ALL entries, losers included (:175)
+    double mx = mb::warp_max(val);
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    if (s_bad) {
+        if (tid == 0) {
+            t.st->err = MB_ERR_INDEX_OOB;
+            t.st->err_gen = gen;
+        }
+        return;
+    }
+    if (tid == 0) {
+        for (int j = 1; j < (int)(blockDim.x >> 5); ++j) mx = fmax(mx, red[j]);
+        if (mx > -INFINITY && !(t.st->max_leaf > mx)) {
+            t.st->max_leaf = mx;
+            t.st->max_is_f32 = sizeof(WT) == 4 ? 1 : 0;
+        }
+    }
+    if (alive) {
+        alive = reinterpret_cast<int *>(&vals[0][slot])[0] == tid;
+        if (alive) t.W[k] = val;
+    }
+    __syncthreads();
+    // the leaf table becomes the level-0 table: survivors re-publish (node, value); clear first
+    for (int j = tid; j < kHash; j += blockDim.x) keys[0][j] = kEmpty;
+    __syncthreads();
+    unsigned node = (unsigned)k;
+#pragma unroll
+    for (int l = 0; l < kMaxLevels; ++l) {
+        if (l < t.depth - 1) {
+            unsigned *K = keys[l & 1];
+            double *V = vals[l & 1];
+            if (alive) {
+                unsigned s2 = hash_slot(node);
+                while (true) {
+                    const unsigned prev = atomicCAS(&K[s2], kEmpty, node);
+                    if (prev == kEmpty) { V[s2] = val; break; }
+                    if (prev == node) { alive = false; break; }   // another thread carries this node
+                    s2 = (s2 + 1) & (kHash - 1);
+                }
+            }
+            __syncthreads();
+            if (alive) {
+                const unsigned want = node ^ 1u;
+                unsigned s2 = hash_slot(want);
+                double other = sib[l];
+                while (true) {
+                    const unsigned key = K[s2];
+                    if (key == kEmpty) break;
+                    if (key == want) { other = V[s2]; break; }
+                    s2 = (s2 + 1) & (kHash - 1);
+                }
+                val = val + other;  // left + right (IEEE addition is commutative)
+                node >>= 1;
+                t.W[level_off(t, l + 1) + node] = val;
+            }
+            unsigned *Kn = keys[(l + 1) & 1];
+            for (int j = tid; j < kHash; j += blockDim.x) Kn[j] = kEmpty;
+            __syncthreads();
+        }
+    }
+}
+
 // update_leaf (:127-150): one path to the root.  The reference's bound check admits
 // index == size (:135); that slot is a padding leaf whenever size is not a power of two.
 __global__ void tree_update_one_kernel(TreeDev t, double weight, int64_t index) {
@@ -602,6 +718,15 @@ static int launch_update(mb_tree *t, const int64_t *d_index, const void *d_weigh
     if (n > 0x7fffffff) return MB_ERR_INVALID;
     mb::DeviceGuard g(t->device);
     const int gen = ++t->gen;
+    if (n <= kSmallN && t->dev.depth - 1 <= kMaxLevels) {
+        const int threads = (int)(((n + 31) / 32) * 32);
+        if (dtype == MB_F32)
+            tree_update_small<float><<<1, threads, 0, s>>>(t->dev, d_index, (const float *)d_weight, d_valid, (int)n, nz, gen);
+        else
+            tree_update_small<double><<<1, threads, 0, s>>>(t->dev, d_index, (const double *)d_weight, d_valid, (int)n, nz, gen);
+        MB_LAUNCHED(1);
+        return MB_OK;
+    }
     if (n <= 4096) {
         const int threads = (int)(n <= 1024 ? ((n + 31) / 32) * 32 : 1024);
         if (dtype == MB_F32)
