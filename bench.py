@@ -329,6 +329,8 @@ def run_b200(a):
     e1.record()
     barrier()
     launches = _lib.lib.mb_launch_count() - launches0
+    if learner._graph is not None:   # graph replays do not pass through the C entry points: count per replay
+        launches = K * learner.graph_launches
     ms_total = e0.elapsed_time(e1)
     # ---- e2e: public API, host uniforms in, loss out, every step
     for _ in range(W):

@@ -15,6 +15,8 @@
 // stored intermediate nodes bit-for-bit, then applies the reference's per-level comparisons.
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+
 #include <new>
 
 #include "mb_common.cuh"
@@ -49,6 +51,7 @@ struct mb_tree {
     TreeState *h_state;  // pinned mirror for mb_tree_stats / mb_tree_check
     int coop_blocks;     // co-resident CTAs for the cooperative update kernel
     int gen;             // update-launch generation counter
+    int force_generic;   // MB_FORCE_GENERIC_UPDATE=1: never take the small-batch kernel (A/B timing)
 };
 
 namespace {
@@ -345,43 +348,49 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(TreeDev t, const int6
 // ---- small batches (n <= 512: the learner's priority write-back), one CTA, latency-optimised ----
 // The generic kernel above pays two dependent L2/HBM round trips per level (24 levels at 10 M leaves).
 // Here every thread owns one entry and (1) prefetches, up front and all at once, the STORED sibling of
-// every node on its leaf-to-root path, (2) walks up keeping the fresh value of its node in a register;
-// at each level the touched nodes are published in a shared-memory hash table so that a thread whose
-// sibling is also touched takes the fresh value instead of the stale prefetched one.  Threads that
-// reach the same node merge (one survivor), so contention is at most two-way.  Parents are still
-// fl(left + right) of the current children: the node array is bit-identical to the generic kernel's.
+// every node on its leaf-to-root path into shared memory (cp.async, no register staging), (2) walks
+// up keeping the fresh value of its node in a register; at each level the touched nodes are published
+// in a shared-memory hash table so that a thread whose sibling is also touched takes the fresh value
+// instead of the stale prefetched one.  Threads that reach the same node merge (one survivor), so
+// contention is at most two-way.  Parents are still fl(left + right) of the current children: the node
+// array is bit-identical to the generic kernel's.  The level loop is deliberately NOT unrolled (a
+// fully unrolled body is ~50 KB of straight-line SASS executed once: instruction-fetch bound).
 constexpr int kSmallN = 512;
 constexpr int kHash = 1024;
 constexpr unsigned kEmpty = 0xffffffffu;
-constexpr int kMaxLevels = 31;
 
 __device__ __forceinline__ unsigned hash_slot(unsigned key) { return (key * 2654435761u) >> 22; }  // 10 bits
+
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src));
+}
 
 template <typename WT>
 __global__ void __launch_bounds__(kSmallN) tree_update_small(TreeDev t, const int64_t *__restrict__ idx,
                                                              const WT *__restrict__ w,
                                                              const uint8_t *__restrict__ valid, int n,
                                                              Normalize nz, int gen) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    double *sib = reinterpret_cast<double *>(dyn);  // [depth - 1][kSmallN] stored siblings along each path
     __shared__ unsigned keys[2][kHash];
     __shared__ double vals[2][kHash];
     __shared__ double red[kSmallN / 32];
     __shared__ int s_bad;
     const int tid = threadIdx.x;
+    bool alive = tid < n && (!valid || valid[tid]);
+    int64_t k = alive ? idx[tid] : 0;
+    const bool oob = alive && (k < 0 || k >= t.size);
+    const int levels = t.depth - 1;
+    if (alive && !oob)
+        for (int l = 0; l < levels; ++l) cp_async_8(sib + l * kSmallN + tid, t.W + level_off(t, l) + ((k >> l) ^ 1));
+    asm volatile("cp.async.commit_group;\n" ::);
     for (int j = tid; j < kHash; j += blockDim.x) {
         keys[0][j] = kEmpty;
         keys[1][j] = kEmpty;
         reinterpret_cast<int *>(&vals[0][j])[0] = -1;  // leaf phase: "last writer" position
     }
     if (tid == 0) s_bad = 0;
-    bool alive = tid < n && (!valid || valid[tid]);
-    int64_t k = alive ? idx[tid] : 0;
-    const bool oob = alive && (k < 0 || k >= t.size);
-    double sib[kMaxLevels];
-    if (alive && !oob) {
-#pragma unroll
-        for (int l = 0; l < kMaxLevels; ++l)
-            if (l < t.depth - 1) sib[l] = __ldcg(t.W + level_off(t, l) + ((k >> l) ^ 1));
-    }
     double val = alive && !oob ? normalized_weight(w[tid], nz) : -INFINITY;
     __syncthreads();
     if (oob) s_bad = 1;
@@ -398,6 +407,7 @@ __global__ void __launch_bounds__(kSmallN) tree_update_small(TreeDev t, const in
     // max over ALL entries, losers included (:175)
     double mx = mb::warp_max(val);
     if ((tid & 31) == 0) red[tid >> 5] = mx;
+    asm volatile("cp.async.wait_all;\n" ::);
     __syncthreads();
     if (s_bad) {
         if (tid == 0) {
@@ -418,43 +428,40 @@ __global__ void __launch_bounds__(kSmallN) tree_update_small(TreeDev t, const in
         if (alive) t.W[k] = val;
     }
     __syncthreads();
-    // the leaf table becomes the level-0 table: survivors re-publish (node, value); clear first
-    for (int j = tid; j < kHash; j += blockDim.x) keys[0][j] = kEmpty;
+    for (int j = tid; j < kHash; j += blockDim.x) keys[0][j] = kEmpty;  // leaf table -> level-0 table
     __syncthreads();
     unsigned node = (unsigned)k;
-#pragma unroll
-    for (int l = 0; l < kMaxLevels; ++l) {
-        if (l < t.depth - 1) {
-            unsigned *K = keys[l & 1];
-            double *V = vals[l & 1];
-            if (alive) {
-                unsigned s2 = hash_slot(node);
-                while (true) {
-                    const unsigned prev = atomicCAS(&K[s2], kEmpty, node);
-                    if (prev == kEmpty) { V[s2] = val; break; }
-                    if (prev == node) { alive = false; break; }   // another thread carries this node
-                    s2 = (s2 + 1) & (kHash - 1);
-                }
+#pragma unroll 1
+    for (int l = 0; l < levels; ++l) {
+        unsigned *K = keys[l & 1];
+        double *V = vals[l & 1];
+        if (alive) {
+            unsigned s2 = hash_slot(node);
+            while (true) {
+                const unsigned prev = atomicCAS(&K[s2], kEmpty, node);
+                if (prev == kEmpty) { V[s2] = val; break; }
+                if (prev == node) { alive = false; break; }   // another thread carries this node
+                s2 = (s2 + 1) & (kHash - 1);
             }
-            __syncthreads();
-            if (alive) {
-                const unsigned want = node ^ 1u;
-                unsigned s2 = hash_slot(want);
-                double other = sib[l];
-                while (true) {
-                    const unsigned key = K[s2];
-                    if (key == kEmpty) break;
-                    if (key == want) { other = V[s2]; break; }
-                    s2 = (s2 + 1) & (kHash - 1);
-                }
-                val = val + other;  // left + right (IEEE addition is commutative)
-                node >>= 1;
-                t.W[level_off(t, l + 1) + node] = val;
-            }
-            unsigned *Kn = keys[(l + 1) & 1];
-            for (int j = tid; j < kHash; j += blockDim.x) Kn[j] = kEmpty;
-            __syncthreads();
         }
+        __syncthreads();
+        if (alive) {
+            const unsigned want = node ^ 1u;
+            unsigned s2 = hash_slot(want);
+            double other = sib[l * kSmallN + tid];
+            while (true) {
+                const unsigned key = K[s2];
+                if (key == kEmpty) break;
+                if (key == want) { other = V[s2]; break; }
+                s2 = (s2 + 1) & (kHash - 1);
+            }
+            val = val + other;  // left + right (IEEE addition is commutative)
+            node >>= 1;
+            t.W[level_off(t, l + 1) + node] = val;
+        }
+        unsigned *Kn = keys[(l + 1) & 1];
+        for (int j = tid; j < kHash; j += blockDim.x) Kn[j] = kEmpty;
+        __syncthreads();
     }
 }
 
@@ -529,6 +536,39 @@ __global__ void __launch_bounds__(1024) per_sample_small(TreeDev t, const double
     }
 }
 
+// n <= 1024, B200 path: the batch is spread over a thread-block CLUSTER of up to 8 CTAs (8 SMs), because
+// a single SM's L1 serves ~1 wavefront per cycle and thread-per-query descent issues 32 distinct lines per
+// load instruction (4096 wavefronts per jump for 512 queries on one SM).  The max-normalisation crosses
+// CTAs through distributed shared memory: each CTA publishes its maximum, cluster.sync(), every CTA reads
+// the others' maxima over DSMEM.
+__global__ void __launch_bounds__(128) per_sample_cluster(TreeDev t, const double *__restrict__ u, int64_t n,
+                                                          PerArgs a, int64_t *__restrict__ out_idx,
+                                                          double *__restrict__ out_isw) {
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ double red[4];
+    __shared__ double cta_max;
+    const int tid = threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + tid;
+    int64_t index = 0;
+    double isw = -INFINITY;
+    if (i < n) per_one(t, u, n, i, a, index, isw);
+    double mx = mb::warp_max(isw);
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) mx = fmax(mx, red[k]);
+        cta_max = mx;
+    }
+    cluster.sync();
+    mx = -INFINITY;
+    for (unsigned r = 0; r < cluster.num_blocks(); ++r) mx = fmax(mx, *cluster.map_shared_rank(&cta_max, r));
+    cluster.sync();  // nobody exits (and frees its shared memory) while a peer may still read it
+    if (i < n) {
+        out_idx[i] = index;
+        out_isw[i] = __ddiv_rn(isw, mx);
+    }
+}
+
 __global__ void __launch_bounds__(256) per_sample_large(TreeDev t, const double *__restrict__ u, int64_t n,
                                                         PerArgs a, int64_t *__restrict__ out_idx,
                                                         double *__restrict__ out_isw) {
@@ -580,6 +620,10 @@ int mb_tree_create(int64_t size, int device, mb_tree **out) {
     t->n_nodes = t->dev.total - 1;
     t->h_state = nullptr;
     t->gen = 0;
+    {
+        const char *e = getenv("MB_FORCE_GENERIC_UPDATE");
+        t->force_generic = (e && e[0] == '1') ? 1 : 0;
+    }
     t->dev.W = nullptr;
     t->dev.owner = nullptr;
     t->dev.st = nullptr;
@@ -595,6 +639,8 @@ int mb_tree_create(int64_t size, int device, mb_tree **out) {
     MB_CUDA(cudaMemset(t->dev.owner, 0xff, sizeof(int) * (size_t)size));
     MB_CUDA(cudaMemset(t->dev.st, 0, sizeof(TreeState)));
     tree_state_reset<<<1, 1>>>(t->dev.st, 0.0);
+    MB_CUDA(cudaFuncSetAttribute(tree_update_small<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    MB_CUDA(cudaFuncSetAttribute(tree_update_small<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     int per_sm = 0;
     MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_update_kernel<double, true>, 1024, 0));
     int sms = mb::kNumSMs;
@@ -718,12 +764,13 @@ static int launch_update(mb_tree *t, const int64_t *d_index, const void *d_weigh
     if (n > 0x7fffffff) return MB_ERR_INVALID;
     mb::DeviceGuard g(t->device);
     const int gen = ++t->gen;
-    if (n <= kSmallN && t->dev.depth - 1 <= kMaxLevels) {
+    if (n <= kSmallN && !t->force_generic) {
         const int threads = (int)(((n + 31) / 32) * 32);
+        const size_t dyn = sizeof(double) * (size_t)kSmallN * (size_t)(t->dev.depth - 1);
         if (dtype == MB_F32)
-            tree_update_small<float><<<1, threads, 0, s>>>(t->dev, d_index, (const float *)d_weight, d_valid, (int)n, nz, gen);
+            tree_update_small<float><<<1, threads, dyn, s>>>(t->dev, d_index, (const float *)d_weight, d_valid, (int)n, nz, gen);
         else
-            tree_update_small<double><<<1, threads, 0, s>>>(t->dev, d_index, (const double *)d_weight, d_valid, (int)n, nz, gen);
+            tree_update_small<double><<<1, threads, dyn, s>>>(t->dev, d_index, (const double *)d_weight, d_valid, (int)n, nz, gen);
         MB_LAUNCHED(1);
         return MB_OK;
     }
@@ -776,7 +823,22 @@ int mb_per_sample(mb_tree *t, const double *d_uniform, int64_t n, int64_t n_stor
     mb::DeviceGuard g(t->device);
     cudaStream_t s = (cudaStream_t)stream;
     PerArgs a{n_stored, all_weight_sum, beta, d_params};
-    if (n <= 1024) {
+    if (n <= 1024 && n > 64 && !t->force_generic) {
+        const unsigned threads = n <= 256 ? 32 : (n <= 512 ? 64 : 128);
+        const unsigned ctas = (unsigned)((n + threads - 1) / threads);  // <= 8: one cluster
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ctas);
+        cfg.blockDim = dim3(threads);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = ctas;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MB_CUDA(cudaLaunchKernelEx(&cfg, per_sample_cluster, t->dev, d_uniform, n, a, d_index, d_is_weight));
+    } else if (n <= 1024) {
         per_sample_small<<<1, (unsigned)(((n + 31) / 32) * 32), 0, s>>>(t->dev, d_uniform, n, a, d_index, d_is_weight);
     } else {
         per_isw_reset<<<1, 1, 0, s>>>(t->dev.st);

@@ -154,9 +154,12 @@ class DQNPer(TorchFramework):
         t.cuda.synchronize(dev)
         graph = t.cuda.CUDAGraph()
         self.qnet_optim.zero_grad(set_to_none=True)
+        from ..._lib import lib
+        launched = lib.mb_launch_count()
         with t.cuda.graph(graph):
             self._static_loss = self._step(True, True, self._u_static, True)
         self._graph = graph
+        self.graph_launches = lib.mb_launch_count() - launched   # libmachin_b200 kernels per replay
         # restore everything the warm-up touched, in place (the graph holds these addresses)
         with t.no_grad():
             for m, saved in zip((self.qnet, self.qnet_target), saved_nets):
