@@ -51,7 +51,7 @@ struct mb_tree {
     TreeState *h_state;  // pinned mirror for mb_tree_stats / mb_tree_check
     int coop_blocks;     // co-resident CTAs for the cooperative update kernel
     int gen;             // update-launch generation counter
-    int force_generic;   // MB_FORCE_GENERIC_UPDATE=1: never take the small-batch kernel (A/B timing)
+    int force_generic;   // MB_FORCE_GENERIC_UPDATE=1: single-CTA PER draw instead of the cluster kernel (A/B timing)
 };
 
 namespace {
@@ -345,126 +345,6 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(TreeDev t, const int6
     }
 }
 
-// ---- small batches (n <= 512: the learner's priority write-back), one CTA, latency-optimised ----
-// The generic kernel above pays two dependent L2/HBM round trips per level (24 levels at 10 M leaves).
-// Here every thread owns one entry and (1) prefetches, up front and all at once, the STORED sibling of
-// every node on its leaf-to-root path into shared memory (cp.async, no register staging), (2) walks
-// up keeping the fresh value of its node in a register; at each level the touched nodes are published
-// in a shared-memory hash table so that a thread whose sibling is also touched takes the fresh value
-// instead of the stale prefetched one.  Threads that reach the same node merge (one survivor), so
-// contention is at most two-way.  Parents are still fl(left + right) of the current children: the node
-// array is bit-identical to the generic kernel's.  The level loop is deliberately NOT unrolled (a
-// fully unrolled body is ~50 KB of straight-line SASS executed once: instruction-fetch bound).
-constexpr int kSmallN = 512;
-constexpr int kHash = 1024;
-constexpr unsigned kEmpty = 0xffffffffu;
-
-__device__ __forceinline__ unsigned hash_slot(unsigned key) { return (key * 2654435761u) >> 22; }  // 10 bits
-
-__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src));
-}
-
-template <typename WT>
-__global__ void __launch_bounds__(kSmallN) tree_update_small(TreeDev t, const int64_t *__restrict__ idx,
-                                                             const WT *__restrict__ w,
-                                                             const uint8_t *__restrict__ valid, int n,
-                                                             Normalize nz, int gen) {
-    extern __shared__ __align__(16) unsigned char dyn[];
-    double *sib = reinterpret_cast<double *>(dyn);  // [depth - 1][kSmallN] stored siblings along each path
-    __shared__ unsigned keys[2][kHash];
-    __shared__ double vals[2][kHash];
-    __shared__ double red[kSmallN / 32];
-    __shared__ int s_bad;
-    const int tid = threadIdx.x;
-    bool alive = tid < n && (!valid || valid[tid]);
-    int64_t k = alive ? idx[tid] : 0;
-    const bool oob = alive && (k < 0 || k >= t.size);
-    const int levels = t.depth - 1;
-    if (alive && !oob)
-        for (int l = 0; l < levels; ++l) cp_async_8(sib + l * kSmallN + tid, t.W + level_off(t, l) + ((k >> l) ^ 1));
-    asm volatile("cp.async.commit_group;\n" ::);
-    for (int j = tid; j < kHash; j += blockDim.x) {
-        keys[0][j] = kEmpty;
-        keys[1][j] = kEmpty;
-        reinterpret_cast<int *>(&vals[0][j])[0] = -1;  // leaf phase: "last writer" position
-    }
-    if (tid == 0) s_bad = 0;
-    double val = alive && !oob ? normalized_weight(w[tid], nz) : -INFINITY;
-    __syncthreads();
-    if (oob) s_bad = 1;
-    unsigned slot = 0;
-    if (alive && !oob) {  // leaf dedupe: the highest batch position wins (NumPy fancy assignment)
-        slot = hash_slot((unsigned)k);
-        while (true) {
-            const unsigned prev = atomicCAS(&keys[0][slot], kEmpty, (unsigned)k);
-            if (prev == kEmpty || prev == (unsigned)k) break;
-            slot = (slot + 1) & (kHash - 1);
-        }
-        atomicMax(reinterpret_cast<int *>(&vals[0][slot]), tid);
-    }
-    // max over ALL entries, losers included (:175)
-    double mx = mb::warp_max(val);
-    if ((tid & 31) == 0) red[tid >> 5] = mx;
-    asm volatile("cp.async.wait_all;\n" ::);
-    __syncthreads();
-    if (s_bad) {
-        if (tid == 0) {
-            t.st->err = MB_ERR_INDEX_OOB;
-            t.st->err_gen = gen;
-        }
-        return;
-    }
-    if (tid == 0) {
-        for (int j = 1; j < (int)(blockDim.x >> 5); ++j) mx = fmax(mx, red[j]);
-        if (mx > -INFINITY && !(t.st->max_leaf > mx)) {
-            t.st->max_leaf = mx;
-            t.st->max_is_f32 = sizeof(WT) == 4 ? 1 : 0;
-        }
-    }
-    if (alive) {
-        alive = reinterpret_cast<int *>(&vals[0][slot])[0] == tid;
-        if (alive) t.W[k] = val;
-    }
-    __syncthreads();
-    for (int j = tid; j < kHash; j += blockDim.x) keys[0][j] = kEmpty;  // leaf table -> level-0 table
-    __syncthreads();
-    unsigned node = (unsigned)k;
-#pragma unroll 1
-    for (int l = 0; l < levels; ++l) {
-        unsigned *K = keys[l & 1];
-        double *V = vals[l & 1];
-        if (alive) {
-            unsigned s2 = hash_slot(node);
-            while (true) {
-                const unsigned prev = atomicCAS(&K[s2], kEmpty, node);
-                if (prev == kEmpty) { V[s2] = val; break; }
-                if (prev == node) { alive = false; break; }   // another thread carries this node
-                s2 = (s2 + 1) & (kHash - 1);
-            }
-        }
-        __syncthreads();
-        if (alive) {
-            const unsigned want = node ^ 1u;
-            unsigned s2 = hash_slot(want);
-            double other = sib[l * kSmallN + tid];
-            while (true) {
-                const unsigned key = K[s2];
-                if (key == kEmpty) break;
-                if (key == want) { other = V[s2]; break; }
-                s2 = (s2 + 1) & (kHash - 1);
-            }
-            val = val + other;  // left + right (IEEE addition is commutative)
-            node >>= 1;
-            t.W[level_off(t, l + 1) + node] = val;
-        }
-        unsigned *Kn = keys[(l + 1) & 1];
-        for (int j = tid; j < kHash; j += blockDim.x) Kn[j] = kEmpty;
-        __syncthreads();
-    }
-}
-
 // update_leaf (:127-150): one path to the root.  The reference's bound check admits
 // index == size (:135); that slot is a padding leaf whenever size is not a power of two.
 __global__ void tree_update_one_kernel(TreeDev t, double weight, int64_t index) {
@@ -639,8 +519,6 @@ int mb_tree_create(int64_t size, int device, mb_tree **out) {
     MB_CUDA(cudaMemset(t->dev.owner, 0xff, sizeof(int) * (size_t)size));
     MB_CUDA(cudaMemset(t->dev.st, 0, sizeof(TreeState)));
     tree_state_reset<<<1, 1>>>(t->dev.st, 0.0);
-    MB_CUDA(cudaFuncSetAttribute(tree_update_small<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    MB_CUDA(cudaFuncSetAttribute(tree_update_small<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     int per_sm = 0;
     MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_update_kernel<double, true>, 1024, 0));
     int sms = mb::kNumSMs;
@@ -764,16 +642,6 @@ static int launch_update(mb_tree *t, const int64_t *d_index, const void *d_weigh
     if (n > 0x7fffffff) return MB_ERR_INVALID;
     mb::DeviceGuard g(t->device);
     const int gen = ++t->gen;
-    if (n <= kSmallN && !t->force_generic) {
-        const int threads = (int)(((n + 31) / 32) * 32);
-        const size_t dyn = sizeof(double) * (size_t)kSmallN * (size_t)(t->dev.depth - 1);
-        if (dtype == MB_F32)
-            tree_update_small<float><<<1, threads, dyn, s>>>(t->dev, d_index, (const float *)d_weight, d_valid, (int)n, nz, gen);
-        else
-            tree_update_small<double><<<1, threads, dyn, s>>>(t->dev, d_index, (const double *)d_weight, d_valid, (int)n, nz, gen);
-        MB_LAUNCHED(1);
-        return MB_OK;
-    }
     if (n <= 4096) {
         const int threads = (int)(n <= 1024 ? ((n + 31) / 32) * 32 : 1024);
         if (dtype == MB_F32)

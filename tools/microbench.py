@@ -55,7 +55,7 @@ def graphed(fns, reps=20):
     return timed(g.replay, reps=reps) / len(fns)
 
 
-def main():
+def main():  # noqa: C901
     out = {"peak_hbm_gbs": PEAK, "results": {}}
     R = out["results"]
     N = 10_000_000
