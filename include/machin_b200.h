@@ -152,7 +152,8 @@ typedef struct mb_field {
     int64_t dense_pitch;/* bytes between consecutive rows of d_dense (normally == nbytes)      */
 } mb_field;
 
-/* dense[i, :] = ring[index[i], field]   for every field ("[storage[i] for i in index]" + t.cat) */
+/* dense[i, :] = ring[index[i], field]   for every field ("[storage[i] for i in index]" + t.cat).
+ * d_index == NULL means the identity (unpack n packed rows, e.g. rows received from a peer shard). */
 int mb_rows_gather(const void *d_ring, int64_t pitch, int64_t capacity, const int64_t *d_index,
                    int64_t n, const mb_field *fields, int n_fields, void *stream);
 /* ring[(first_slot + i) % capacity, field] = dense[i, :]   (TransitionStorageBasic.store_episode) */

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) rows_move_kernel(char *ring, int64_t pitc
     for (int64_t i = warp; i < n; i += n_warps) {
         int64_t slot;
         if (kGather) {
-            slot = index[i];
+            slot = index ? index[i] : i;  // NULL index: identity (unpacking rows received from a peer shard)
             slot = slot < 0 ? 0 : (slot >= capacity ? capacity - 1 : slot);  // never read outside the ring
         } else {
             slot = (first_slot + i) % capacity;
@@ -89,7 +89,6 @@ extern "C" {
 
 int mb_rows_gather(const void *d_ring, int64_t pitch, int64_t capacity, const int64_t *d_index, int64_t n,
                    const mb_field *fields, int n_fields, void *stream) {
-    if (!d_index && n > 0) return MB_ERR_INVALID;
     return launch_rows(true, (void *)d_ring, pitch, capacity, d_index, 0, n, fields, n_fields, (cudaStream_t)stream);
 }
 

@@ -1,6 +1,7 @@
 from .buffer import Buffer
 from .device_ring import DeviceRing
 from .prioritized_buffer import PrioritizedBuffer
+from .prioritized_buffer_d import DistributedPrioritizedBuffer
 from .weight_tree import WeightTree
 
-__all__ = ["Buffer", "DeviceRing", "PrioritizedBuffer", "WeightTree"]
+__all__ = ["Buffer", "DeviceRing", "PrioritizedBuffer", "DistributedPrioritizedBuffer", "WeightTree"]

@@ -192,13 +192,17 @@ class Buffer:
         return len(keys), keys
 
     def post_process_batch(self, handles, device, concatenate, sample_attrs, additional_concat_custom_attrs,
-                           index_tensor: t.Tensor = None):
+                           index_tensor: t.Tensor = None, packed_rows: t.Tensor = None):
         """``handles``: slot list / array (host).  ``index_tensor``: the same slots already on
-        the device (PER path) -- avoids the host round trip."""
-        n = len(handles) if handles is not None else int(index_tensor.shape[0])
+        the device (PER path) -- avoids the host round trip.  ``packed_rows``: rows that were
+        already gathered elsewhere (sharded buffers) -- only unpacked here."""
+        if packed_rows is not None:
+            n = int(packed_rows.shape[0])
+        else:
+            n = len(handles) if handles is not None else int(index_tensor.shape[0])
         if n == 0:
             return None
-        if index_tensor is None:
+        if index_tensor is None and packed_rows is None:
             index_tensor = t.as_tensor(np.asarray(handles, dtype=np.int64)).to(self.buffer_device)
         out_device = self.buffer_device if device is None else t.device(device)
         if sample_attrs is None:
@@ -216,7 +220,10 @@ class Buffer:
                 want.append(attr)
             elif attr == "*":
                 want += [a for a in self._custom_attr if a in fields and concatenate and a in additional_concat_custom_attrs]
-        dense = self.storage.gather(index_tensor, names=list(dict.fromkeys(want)))
+        if packed_rows is not None:
+            dense = self.storage.unpack(packed_rows, names=list(dict.fromkeys(want)))
+        else:
+            dense = self.storage.gather(index_tensor, names=list(dict.fromkeys(want)))
         host_idx = None
 
         def finish(attr, key, tensor):
@@ -231,9 +238,13 @@ class Buffer:
                 if attr not in dense:
                     raise ValueError(f"Batch not concatenable: custom attribute {attr!r} is not numeric")
                 return self.post_process_attribute(attr, None, dense[attr].view(n, -1).to(out_device))
-            if attr not in self._host_custom:
-                col = self.storage.gather(index_tensor, names=[attr])[attr].view(-1).tolist()
-                return self.post_process_attribute(attr, None, col)
+            if attr not in self._host_custom or packed_rows is not None:
+                if attr not in self.storage.fields:
+                    raise ValueError(f"custom attribute {attr!r} is not numeric and cannot be sampled from a "
+                                     "device / sharded buffer")
+                src = (self.storage.unpack(packed_rows, names=[attr]) if packed_rows is not None
+                       else self.storage.gather(index_tensor, names=[attr]))
+                return self.post_process_attribute(attr, None, src[attr].view(-1).tolist())
             if host_idx is None:
                 host_idx = np.asarray(handles) if handles is not None else index_tensor.cpu().numpy()
             return self.post_process_attribute(attr, None, list(self._host_custom[attr][host_idx]))

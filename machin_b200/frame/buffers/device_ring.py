@@ -112,6 +112,18 @@ class DeviceRing:
                                           arr, len(names), _lib.stream_ptr(stream)))
         return out
 
+    def unpack(self, rows: t.Tensor, names=None, stream=None) -> Dict[str, t.Tensor]:
+        """Split ``n`` packed rows (u8[n, pitch], e.g. received from a peer shard) into dense fields."""
+        names = list(self.fields) if names is None else [n for n in names if n in self.fields]
+        n = int(rows.shape[0])
+        assert rows.is_contiguous() and rows.shape[1] == self.pitch
+        out = {k: t.empty((n,) + self.fields[k].shape, dtype=self.fields[k].dtype, device=rows.device) for k in names}
+        if n and names:
+            arr = self._field_array(names, out)
+            _lib.check(lib.mb_rows_gather(_lib.ptr(rows), self.pitch, n, None, n, arr, len(names),
+                                          _lib.stream_ptr(stream)))
+        return out
+
     def gather_packed(self, index: t.Tensor, out: Optional[t.Tensor] = None, stream=None) -> t.Tensor:
         n = int(index.shape[0])
         if out is None:

@@ -1,0 +1,135 @@
+"""Weight and gradient movement between learners and actors over NCCL.
+
+Replaces, on the data path, machin/parallel/server/param_server.py:21-493 and ordered_server.py
+(push: deepcopy(state_dict) -> CPU -> RPC into a versioned KV; pull: RPC fetch + load_state_dict).
+Here the parameters travel as ONE flat byte buffer ``[all tensors of state_dict | version i64]`` in a
+single broadcast from the pushing member; the ordered server's version chain
+(ordered_server.py:112-128: a push is accepted iff the stored newest version equals ``prev_version``)
+becomes a monotonically increasing ``pp_version`` that rides in the same message.
+
+SPMD convention: in a synchronisation round the pushing member calls :meth:`push` and every other
+member calls :meth:`pull`; both enter the same broadcast.
+"""
+from typing import List
+
+import torch as t
+
+
+def _state_tensors(model: t.nn.Module) -> List[t.Tensor]:
+    return [v for v in model.state_dict().values() if t.is_tensor(v)]
+
+
+class PushPullModelServer:
+    def __init__(self, model_name: str, group, src_index: int = 0):
+        self.model_name, self.group, self.src_index = model_name, group, int(src_index)
+        self._flat = None
+
+    @staticmethod
+    def _layout(tensors):
+        """[version i64 | pad] then every tensor at a 16-byte aligned offset."""
+        offs, o = [], 16
+        for x in tensors:
+            offs.append(o)
+            o += (x.numel() * x.element_size() + 15) // 16 * 16
+        return offs, o
+
+    def _buffer(self, nbytes):
+        if self._flat is None or self._flat.numel() != nbytes:
+            self._flat = t.zeros(nbytes, dtype=t.uint8, device=self.group.device)
+        return self._flat
+
+    def push(self, model: t.nn.Module, pull_on_fail=True) -> bool:
+        """param_server.py:36-71.  Always succeeds here: there is one pusher per round."""
+        if not hasattr(model, "pp_version"):
+            model.pp_version = 0
+        tensors = _state_tensors(model)
+        offs, total = self._layout(tensors)
+        flat = self._buffer(total)
+        for x, o in zip(tensors, offs):
+            n = x.numel() * x.element_size()
+            flat[o:o + n].view(x.dtype).copy_(x.detach().reshape(-1))
+        model.pp_version += 1
+        flat[0:8].view(t.int64).fill_(model.pp_version)
+        self.group.broadcast(flat, self.src_index)
+        return True
+
+    def pull(self, model: t.nn.Module) -> bool:
+        """param_server.py:73-91: load the newest parameters iff they are newer than ``pp_version``."""
+        tensors = _state_tensors(model)
+        offs, total = self._layout(tensors)
+        flat = self._buffer(total)
+        self.group.broadcast(flat, self.src_index)
+        version = int(flat[0:8].view(t.int64).item())
+        if hasattr(model, "pp_version") and version <= model.pp_version:
+            return False
+        with t.no_grad():
+            for x, o in zip(tensors, offs):
+                n = x.numel() * x.element_size()
+                x.copy_(flat[o:o + n].view(x.dtype).view(x.shape))
+        model.pp_version = version
+        return True
+
+
+class PushPullGradServer:
+    """A3C gradient reduction (param_server.py:148-493): workers push gradients, the reduce tree sums or
+    averages ``reduce_batch_size`` of them per reducer, the primary applies its optimizer and publishes
+    the parameters.  Over NCCL: every worker accumulates ``pushes_per_reduce`` local pushes, one
+    all-reduce combines all workers, the primary member steps and broadcasts.
+
+    With W workers pushing k times each, ``reduce_method="sum"`` applies sum over all W*k gradients and
+    ``"mean"`` their mean -- the values the reference's two-level tree produces
+    (test/parallel/server/test_param_server.py:108-173)."""
+
+    def __init__(self, server_name: str, group, primary_index: int = 0, reduce_method: str = "sum",
+                 pushes_per_reduce: int = 1):
+        assert reduce_method in ("mean", "sum")
+        self.server_name, self.group, self.primary_index = server_name, group, int(primary_index)
+        self.reduce_method, self.pushes_per_reduce = reduce_method, int(pushes_per_reduce)
+        self.model = self.optimizer = self.lr_scheduler = None
+        self._acc, self._count = None, 0
+        self._model_server = PushPullModelServer(server_name + "_params", group, primary_index)
+
+    def manage_model(self, model: t.nn.Module, optimizer, lr_scheduler=None):
+        """Primary member only (param_server.py:207-226)."""
+        self.model, self.optimizer, self.lr_scheduler = model, optimizer, lr_scheduler
+        model.pp_version = 0
+
+    def push(self, model: t.nn.Module, pull_on_fail=True) -> bool:
+        """Collective.  Members without gradients (e.g. a pure server process) pass ``model=None``."""
+        dev = self.group.device
+        ref = model if model is not None else self.model
+        params = list(ref.parameters())
+        n = sum(p.numel() for p in params)
+        if self._acc is None:
+            self._acc = t.zeros(n + 1, dtype=t.float32, device=dev)   # last element counts pushes
+        if model is not None:
+            o = 0
+            for p in params:
+                if p.grad is not None:
+                    self._acc[o:o + p.numel()] += p.grad.detach().reshape(-1).to(dev)
+                o += p.numel()
+            self._acc[n] += 1
+        self._count += 1
+        if self._count < self.pushes_per_reduce:
+            return True
+        self.group.all_reduce_sum(self._acc)
+        total = self._acc[n].clamp(min=1)
+        if self.model is not None and self.group.index == self.primary_index:
+            o = 0
+            for p in self.model.parameters():
+                g = self._acc[o:o + p.numel()].view_as(p)
+                p.grad = (g / total if self.reduce_method == "mean" else g.clone()).to(p.device)
+                o += p.numel()
+            self.optimizer.step()
+            if self.lr_scheduler is not None:
+                self.lr_scheduler.step()
+            self._model_server.push(self.model)
+        else:
+            self._model_server.pull(ref)
+        self._acc.zero_()
+        self._count = 0
+        return True
+
+    def pull(self, model: t.nn.Module) -> bool:
+        """The reduced parameters were already loaded at the end of the reducing :meth:`push`."""
+        return True
