@@ -168,9 +168,9 @@ class QNet:
     pass
 
 
-def build_learner(a, device, seed):
+def build_learner(a, device, seed, world=1):
     import torch as t
-    from machin_b200.frame.algorithms import DQNPer
+    from machin_b200.frame.algorithms import DQNApex, DQNPer
     from machin_b200.frame.buffers import PrioritizedBuffer
 
     class Q(t.nn.Module):
@@ -185,9 +185,22 @@ def build_learner(a, device, seed):
 
     t.manual_seed(seed)
     qnet, qtgt = Q().to(device), Q().to(device)
-    buf = PrioritizedBuffer(buffer_size=a.replay_rows, buffer_device=device)
-    learner = DQNPer(qnet, qtgt, t.optim.Adam, t.nn.MSELoss(reduction="none"), batch_size=a.batch,
-                     learning_rate=1e-3, discount=0.99, update_rate=0.005, replay_buffer=buf)
+    if world > 1:
+        # every process = one replay shard + one learner (APEX with the nets data-parallel over the
+        # learner group): global PER draw across shards, gradient all-reduce, weight broadcast per update
+        from machin_b200.parallel import ShardGroup
+        from machin_b200.parallel.server import PushPullModelServer
+        group = ShardGroup("apex", device=device)
+        t.manual_seed(0)   # identical initial weights on every learner
+        qnet, qtgt = Q().to(device), Q().to(device)
+        learner = DQNApex(qnet, qtgt, t.optim.Adam, t.nn.MSELoss(reduction="none"), group,
+                          (PushPullModelServer("qnet", group, 0),), batch_size=a.batch, learning_rate=1e-3,
+                          discount=0.99, update_rate=0.005, replay_size=a.replay_rows, learner_group=group)
+        buf = learner.replay_buffer
+    else:
+        buf = PrioritizedBuffer(buffer_size=a.replay_rows, buffer_device=device)
+        learner = DQNPer(qnet, qtgt, t.optim.Adam, t.nn.MSELoss(reduction="none"), batch_size=a.batch,
+                         learning_rate=1e-3, discount=0.99, update_rate=0.005, replay_buffer=buf)
     gen = t.Generator(device=device).manual_seed(seed)
     chunk = 1_000_000
     done = 0
@@ -300,8 +313,9 @@ def run_b200(a):
     device = t.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    learner = build_learner(a, device, seed=rank)
-    if not a.no_graph:
+    learner = build_learner(a, device, seed=rank, world=world)
+    graph = not a.no_graph and world == 1   # N > 1: collectives + host-side shard apportioning -> eager
+    if graph:
         learner.enable_cuda_graph()
     K, W, B = a.steps, max(a.warmup, 3), a.batch
     depth = learner.replay_buffer.wt_tree.depth
@@ -317,15 +331,22 @@ def run_b200(a):
     table = t.from_numpy(np.random.uniform(size=(K + W, B))).to(device)  # resident in HBM before timing
     sampler = ClockSampler(local)
     # ---- value: device-resident inputs, no host round trip inside the timed region
+    def dev_step(s):
+        if world == 1:
+            return learner.update_device(uniform=table[s])
+        loss = learner.update_device()
+        learner.push_weights()
+        return loss
+
     for s in range(W):
-        learner.update_device(uniform=table[s])
+        dev_step(s)
     barrier()
     sampler.start()
     launches0 = _lib.lib.mb_launch_count()
     e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(K):
-        loss = learner.update_device(uniform=table[W + s])
+        loss = dev_step(W + s)
     e1.record()
     barrier()
     launches = _lib.lib.mb_launch_count() - launches0
@@ -345,7 +366,7 @@ def run_b200(a):
     barrier()
     e2e_ms = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3)
     # ---- per-kernel event timing inside the step
-    kern = time_kernels(learner, table) if rank == 0 else {}
+    kern = time_kernels(learner, table) if (rank == 0 and world == 1) else {}
     clocks = sampler.stop()
     tt = t.tensor([ms_total, e2e_ms], device=device, dtype=t.float64)
     if world > 1:
@@ -391,7 +412,9 @@ def run_b200(a):
         "learner_updates_per_sec": K / (ms_total * 1e-3),
         "config": {"workload": workload_name(a), "batch": B, "replay_rows": a.replay_rows, "optimizer": "Adam",
                    "parallelism": f"{world} learner(s), one replay shard each",
-                   "launch": "eager" if a.no_graph else "one CUDA graph per update",
+                   "launch": "one CUDA graph per update" if graph else "eager",
+                   "exchange": None if world == 1 else "per update: all-gather of shard sums, all-to-all of sampled rows, "
+                               "all-to-all of priority write-backs, all-reduce of gradients, broadcast of weights (NCCL)",
                    "l2": "inputs larger than L2: 268 MB tree + 6.9 GB ring, randomly addressed every step"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 8,
                 "ms_per_step": e2e_ms / K, "last_loss": last},

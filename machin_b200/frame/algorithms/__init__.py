@@ -1,3 +1,4 @@
+from .apex import DQNApex
 from .dqn_per import DQNPer
 
-__all__ = ["DQNPer"]
+__all__ = ["DQNPer", "DQNApex"]

@@ -203,6 +203,7 @@ class DQNPer(TorchFramework):
         act = self.action_get_function(action)
         td = ops.td_dqn(q_value.detach(), next_q_value, target_next_q_value, act, reward, terminal, self.discount,
                         is_weight=d_isw, mode=self.mode, want_grad=self._fused_mse)
+        batch_size = int(reward.shape[0])  # a sharded buffer may return more than batch_size rows
         if self._fused_mse:
             value_loss = td["loss_elem"].mean()
         else:
@@ -215,6 +216,7 @@ class DQNPer(TorchFramework):
                 q_value.backward(td["grad_q"])
             else:
                 self._backward(value_loss)
+            self._sync_grads()
             nn.utils.clip_grad_norm_(self.qnet.parameters(), self.grad_max)
             self.qnet_optim.step()
         if update_target:
@@ -226,6 +228,9 @@ class DQNPer(TorchFramework):
                     hard_update(self.qnet_target, self.qnet)
         self.qnet.eval()
         return value_loss
+
+    def _sync_grads(self):
+        """Hook: gradient averaging across learner processes (see DQNApex)."""
 
     def update(self, update_value=True, update_target=True, concatenate_samples=True, **__):
         return self.update_device(update_value, update_target).item()

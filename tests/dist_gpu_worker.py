@@ -56,7 +56,10 @@ def main():
                               {"reward": t.from_numpy(pri.astype(np.float32)).view(-1, 1), "terminal": t.zeros(n_rows, 1, dtype=t.bool)},
                               priorities=pri)
     ora = OracleTree(cap)
-    ora.update_leaf_batch(oper.normalize_priority(pri), np.arange(n_rows))
+    # the distributed store normalises ONE priority at a time (prioritized_buffer_d.py:132-136): NumPy's
+    # scalar pow and its SIMD array pow can differ in the last ulp, so the oracle takes the scalar path too
+    leaf0 = np.array([oper.normalize_priority(p) for p in pri])
+    ora.update_leaf_batch(leaf0, np.arange(n_rows))
     assert np.array_equal(buf.wt_tree.weights, ora.weights)
     sums = group.all_gather_f64(t.tensor([ora.get_weight_sum()], dtype=t.float64, device=group.device)).view(-1).tolist()
     ssize, total = oper.shard_sample_sizes(sums, 512)
@@ -96,7 +99,7 @@ def main():
         ora.update_leaf_batch(oper.normalize_priority(pr[keep]), ix[keep])
     got, want = buf.wt_tree.weights, ora.weights
     assert np.allclose(got, want, rtol=1e-6, atol=0), np.abs(got - want).max()
-    assert got[victim] == oper.normalize_priority(pri)[victim]
+    assert got[victim] == leaf0[victim]
     # ---- 3. weight broadcast with version
     server = PushPullModelServer("m", group, 0)
     net = t.nn.Linear(8, 4).cuda()
