@@ -1,4 +1,7 @@
-from .apex import DQNApex
+from .a2c import A2C, A3C
+from .apex import DDPGApex, DQNApex
+from .ddpg_per import DDPGPer
 from .dqn_per import DQNPer
+from .impala import IMPALA
 
-__all__ = ["DQNPer", "DQNApex"]
+__all__ = ["DQNPer", "DQNApex", "DDPGPer", "DDPGApex", "IMPALA", "A2C", "A3C"]

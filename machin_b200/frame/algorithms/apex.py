@@ -109,3 +109,64 @@ class DQNApex(DQNPer):
             srv.push(net, pull_on_fail=False)
         else:
             srv.pull(net)
+
+
+from .ddpg_per import DDPGPer  # noqa: E402
+
+
+class DDPGApex(DDPGPer):
+    """apex.py:256-532: DDPGPer over the sharded buffer; pushes the ACTOR after every update."""
+
+    def __init__(self, actor: nn.Module, actor_target: nn.Module, critic: nn.Module, critic_target: nn.Module,
+                 optimizer: Callable, criterion: Callable, apex_group, model_server: Tuple, *_,
+                 lr_scheduler: Callable = None, lr_scheduler_args=(), lr_scheduler_kwargs=(), batch_size: int = 100,
+                 update_rate: float = 0.005, update_steps: Union[int, None] = None,
+                 actor_learning_rate: float = 0.0005, critic_learning_rate: float = 0.001, discount: float = 0.99,
+                 gradient_max: float = np.inf, replay_size: int = 500000, learner_group=None, requesters=None, **__):
+        buffer = DistributedPrioritizedBuffer(buffer_name="buffer", group=apex_group, buffer_size=replay_size,
+                                              requesters=requesters)
+        super().__init__(actor, actor_target, critic, critic_target, optimizer, criterion, lr_scheduler=lr_scheduler,
+                         lr_scheduler_args=lr_scheduler_args or None, lr_scheduler_kwargs=lr_scheduler_kwargs or None,
+                         batch_size=batch_size, update_rate=update_rate, update_steps=update_steps,
+                         actor_learning_rate=actor_learning_rate, critic_learning_rate=critic_learning_rate,
+                         discount=discount, gradient_max=gradient_max, replay_buffer=buffer)
+        self._is_using_DP_or_DDP = isinstance(self.actor, (nn.parallel.DataParallel, nn.parallel.DistributedDataParallel))
+        self.apex_group, self.learner_group = apex_group, learner_group
+        self.actor_model_server = model_server[0] if model_server else None
+        self.is_syncing = True
+
+    @classmethod
+    def is_distributed(cls):
+        return True
+
+    def set_sync(self, is_syncing):
+        self.is_syncing = is_syncing
+
+    def manual_sync(self):
+        if not self._is_using_DP_or_DDP and self.actor_model_server is not None:
+            self.actor_model_server.pull(self.actor)
+
+    def act(self, state: Dict[str, Any], use_target: bool = False, **kw):
+        if self.is_syncing and not use_target and not self._is_using_DP_or_DDP and self.actor_model_server is not None:
+            self.actor_model_server.pull(self.actor)
+        return super().act(state, use_target, **kw)
+
+    def _sync_grads(self, params):
+        _flat_grad_all_reduce(params, self.learner_group)
+
+    def serve_update(self):
+        self.replay_buffer.sample_device(self.batch_size)
+        self.replay_buffer.update_priority(None, None)
+        if self.actor_model_server is not None:
+            self.actor_model_server.pull(self.actor)
+
+    def update(self, update_value=True, update_policy=True, update_target=True, concatenate_samples=True, **__):
+        result = super().update(update_value, update_policy, update_target, concatenate_samples)
+        srv = self.actor_model_server
+        if srv is not None:
+            net = self.actor.module if self._is_using_DP_or_DDP else self.actor
+            if self.apex_group.index == srv.src_index:
+                srv.push(net, pull_on_fail=False)
+            else:
+                srv.pull(net)
+        return result

@@ -1,7 +1,9 @@
 from .buffer import Buffer
+from .buffer_d import DistributedBuffer, IMPALABuffer
 from .device_ring import DeviceRing
 from .prioritized_buffer import PrioritizedBuffer
 from .prioritized_buffer_d import DistributedPrioritizedBuffer
 from .weight_tree import WeightTree
 
-__all__ = ["Buffer", "DeviceRing", "PrioritizedBuffer", "DistributedPrioritizedBuffer", "WeightTree"]
+__all__ = ["Buffer", "DistributedBuffer", "IMPALABuffer", "DeviceRing", "PrioritizedBuffer",
+           "DistributedPrioritizedBuffer", "WeightTree"]

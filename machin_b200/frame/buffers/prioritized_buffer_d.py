@@ -68,6 +68,10 @@ class DistributedPrioritizedBuffer(PrioritizedBuffer):
     def _agree_on_schema(self):
         """Collective, once: members that never stored anything (pure learners) adopt the row layout of
         the first member that has one, so that every shard packs / unpacks the same byte rows."""
+        if self.group.size() == 1:
+            if self.storage.data is None:
+                raise RuntimeError("the buffer is empty: store an episode before sampling")
+            return
         import torch.distributed as dist
         from .device_ring import Field
         mine = None

@@ -1,3 +1,3 @@
-from .group import ShardGroup
+from .group import LocalGroup, ShardGroup
 
-__all__ = ["ShardGroup"]
+__all__ = ["ShardGroup", "LocalGroup"]

@@ -96,3 +96,46 @@ class ShardGroup:
 
     def all_reduce_sum(self, tensor: t.Tensor):
         dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.pg)
+
+
+class LocalGroup:
+    """A group of one: the same interface without torch.distributed (single-GPU runs and tests)."""
+
+    def __init__(self, name: str = "group", device=None):
+        self.group_name, self.ranks, self.rank, self.pg = name, [0], 0, None
+        self.device = t.device(device) if device is not None else t.device("cuda", t.cuda.current_device())
+
+    def size(self):
+        return 1
+
+    def is_member(self, target=None):
+        return True
+
+    def get_group_name(self):
+        return self.group_name
+
+    def get_group_members(self):
+        return ["0"]
+
+    def get_cur_name(self):
+        return "0"
+
+    def barrier(self):
+        pass
+
+    def destroy(self):
+        pass
+
+    index = 0
+
+    def all_gather_f64(self, value):
+        return value.unsqueeze(0)
+
+    def all_to_all_bytes(self, send, send_counts, recv_counts):
+        return send
+
+    def broadcast(self, tensor, src_index):
+        pass
+
+    def all_reduce_sum(self, tensor):
+        pass

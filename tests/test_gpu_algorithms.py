@@ -66,3 +66,136 @@ def test_dqn_per_update_vs_reference(criterion):
         np.testing.assert_allclose(dqn.replay_buffer.wt_tree.weights, g[f"dqn_tree{step + 1}"], rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(_flat(dqn.qnet), g[f"dqn_q{step + 1}"], rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(_flat(dqn.qnet_target), g[f"dqn_qt{step + 1}"], rtol=1e-5, atol=1e-6)
+
+
+class Actor(t.nn.Module):
+    def __init__(self, s, a, h=16):
+        super().__init__()
+        self.fc1 = t.nn.Linear(s, h)
+        self.fc2 = t.nn.Linear(h, a)
+
+    def forward(self, state):
+        return t.tanh(self.fc2(t.relu(self.fc1(state))))
+
+
+class Critic(t.nn.Module):
+    def __init__(self, s, a, h=16):
+        super().__init__()
+        self.fc1 = t.nn.Linear(s + a, h)
+        self.fc2 = t.nn.Linear(h, 1)
+
+    def forward(self, state, action):
+        return self.fc2(t.relu(self.fc1(t.cat([state, action], dim=1))))
+
+
+def test_ddpg_per_update_vs_reference():
+    from machin_b200.frame.algorithms import DDPGPer
+    g = np.load(os.path.join(GOLDEN, "ref_td.npz"))
+    S, A, N, B = 5, 2, 150, 16
+    actor, actor_t, critic, critic_t = Actor(S, A).cuda(), Actor(S, A).cuda(), Critic(S, A).cuda(), Critic(S, A).cuda()
+    _load_flat(actor_t, g["ddpg_init_actor_t"])
+    _load_flat(critic_t, g["ddpg_init_critic_t"])
+    ddpg = DDPGPer(actor, actor_t, critic, critic_t, t.optim.SGD, t.nn.MSELoss(reduction="sum"), batch_size=B,
+                   actor_learning_rate=0.005, critic_learning_rate=0.01, discount=0.95, update_rate=0.1, replay_size=N)
+    assert np.array_equal(_flat(ddpg.actor), g["ddpg_init_actor"]) and np.array_equal(_flat(ddpg.critic), g["ddpg_init_critic"])
+    ep = [dict(state={"state": t.from_numpy(g["ddpg_state"][i:i + 1])}, action={"action": t.from_numpy(g["ddpg_action"][i:i + 1])},
+               next_state={"state": t.from_numpy(g["ddpg_next_state"][i:i + 1])}, reward=float(g["ddpg_reward"][i]),
+               terminal=bool(g["ddpg_terminal"][i])) for i in range(N)]
+    ddpg.replay_buffer.store_episode(ep, priorities=list(g["ddpg_priority"]))
+    np.random.seed(12)
+    for step in range(3):
+        pol, val = ddpg.update()
+        ref_pol, ref_val = g[f"ddpg_loss{step}"]
+        assert abs(pol - ref_pol) <= 1e-5 * max(1.0, abs(ref_pol)) and abs(val - ref_val) <= 1e-5 * max(1.0, abs(ref_val))
+        np.testing.assert_allclose(ddpg.replay_buffer.wt_tree.weights, g[f"ddpg_tree{step + 1}"], rtol=1e-5, atol=1e-7)
+        for name, net in (("actor", ddpg.actor), ("critic", ddpg.critic), ("actor_t", ddpg.actor_target),
+                          ("critic_t", ddpg.critic_target)):
+            np.testing.assert_allclose(_flat(net), g[f"ddpg_{name}{step + 1}"], rtol=1e-5, atol=1e-6)
+
+
+class PolicyNet(t.nn.Module):
+    def __init__(self, s, a, h=16):
+        super().__init__()
+        self.fc1 = t.nn.Linear(s, h)
+        self.fc2 = t.nn.Linear(h, a)
+
+    def forward(self, state, action=None):
+        probs = t.softmax(self.fc2(t.relu(self.fc1(state))), dim=1)
+        dist = t.distributions.Categorical(probs=probs)
+        act = action if action is not None else dist.sample()
+        return act.view(-1, 1), dist.log_prob(act.flatten()).view(-1, 1), dist.entropy().view(-1, 1)
+
+
+class ValueNet(t.nn.Module):
+    def __init__(self, s, h=16):
+        super().__init__()
+        self.fc1 = t.nn.Linear(s, h)
+        self.fc2 = t.nn.Linear(h, 1)
+
+    def forward(self, state):
+        return self.fc2(t.relu(self.fc1(state)))
+
+
+@pytest.mark.parametrize("tag", ["fixed", "ragged"])
+def test_impala_update_vs_reference(tag):
+    """Whole IMPALA.update() (episode sampling with Python's random, V-trace kernel, losses, SGD step)
+    against the unmodified reference (tests/golden/ref_vtrace.npz)."""
+    import random
+    from machin_b200.frame.algorithms import IMPALA
+    from machin_b200.parallel import LocalGroup
+    g = np.load(os.path.join(GOLDEN, "ref_vtrace.npz"))
+    lengths = [int(x) for x in g[f"{tag}_lengths"]]
+    clip_c, clip_rho, discount = (float(x) for x in g[f"{tag}_clip"])
+    S, A = 8, 3
+    actor, critic = PolicyNet(S, A).cuda(), ValueNet(S).cuda()
+    _load_flat(actor, g[f"{tag}_actor0"])
+    _load_flat(critic, g[f"{tag}_critic0"])
+    captured = {}
+
+    def criterion(value, vs):
+        captured["vs"] = vs.detach().clone()
+        return ((value - vs) ** 2).sum()
+
+    imp = IMPALA(actor, critic, t.optim.SGD, criterion, LocalGroup(device="cuda:0"), (), batch_size=len(lengths),
+                 learning_rate=0.01, isw_clip_c=clip_c, isw_clip_rho=clip_rho, discount=discount,
+                 replay_size=4 * sum(lengths))
+    pos = 0
+    for n in lengths:
+        imp.store_episode([dict(state={"state": t.from_numpy(g[f"{tag}_state"][i:i + 1])},
+                                action={"action": t.tensor([[int(g[f"{tag}_action"][i])]])},
+                                next_state={"state": t.from_numpy(g[f"{tag}_next_state"][i:i + 1])},
+                                reward=float(g[f"{tag}_reward"][i]), action_log_prob=float(g[f"{tag}_logmu"][i]),
+                                terminal=bool(g[f"{tag}_terminal"][i])) for i in range(pos, pos + n)])
+        pos += n
+    t.manual_seed(3); np.random.seed(3); random.seed(3)
+    pol, val = imp.update()
+    ref_pol, ref_val = g[f"{tag}_losses"]
+    np.testing.assert_allclose(captured["vs"].cpu().numpy().reshape(-1), g[f"{tag}_vs"], rtol=1e-5, atol=1e-6)
+    assert abs(pol - ref_pol) <= 1e-5 * max(1.0, abs(ref_pol)) and abs(val - ref_val) <= 1e-5 * max(1.0, abs(ref_val))
+    np.testing.assert_allclose(_flat(imp.actor), g[f"{tag}_actor1"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(_flat(imp.critic), g[f"{tag}_critic1"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("lam", [1.0, 0.0, 0.95])
+def test_a2c_store_episode_vs_reference(lam):
+    """value / gae attached by store_episode (batched critic + reverse-scan kernel) vs the reference's
+    per-step Python loop (tests/golden/ref_gae.npz)."""
+    from machin_b200.frame.algorithms import A2C
+    g = np.load(os.path.join(GOLDEN, "ref_gae.npz"))
+    S, A = 8, 3
+    actor, critic = PolicyNet(S, A).cuda(), ValueNet(S).cuda()
+    _load_flat(critic, g["critic0"])
+    a2c = A2C(actor, critic, t.optim.SGD, t.nn.MSELoss(reduction="sum"), batch_size=8, discount=0.97, gae_lambda=lam)
+    for e in range(4):
+        k = f"lam{lam}_ep{e}_"
+        n = len(g[k + "reward"])
+        ep = [dict(state={"state": t.from_numpy(g[k + "state"][i:i + 1])}, action={"action": t.tensor([[0]])},
+                   next_state={"state": t.from_numpy(g[k + "next_state"][i:i + 1])}, reward=float(g[k + "reward"][i]),
+                   terminal=bool(g[k + "terminal"][i])) for i in range(n)]
+        a2c.store_episode(ep)
+        assert [tr["value"] for tr in ep] == list(g[k + "value"])              # float64 returns: bit-exact
+        np.testing.assert_allclose([tr["gae"] for tr in ep], g[k + "gae"], rtol=1e-5, atol=2e-6)
+    bs, (state, adv) = a2c.replay_buffer.sample_batch(16, sample_attrs=["state", "gae"], additional_concat_custom_attrs=["gae"])
+    assert adv.shape == (bs, 1) and adv.dtype == t.float32
+    pol, val = a2c.update()
+    assert np.isfinite(pol) and np.isfinite(val) and a2c.replay_buffer.size() == 0
