@@ -1,0 +1,85 @@
+"""CPU: the C-ABI library loads and exports every symbol declared in include/machin_b200.h; handle
+constructors fail loudly without a GPU (no CPU fallback); the oracle is not imported by the product."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "machin_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from machin_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 35
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert set(_lib.SIGNATURES) == set(names), set(names) ^ set(_lib.SIGNATURES)
+    assert lib.mb_abi_version() == 1
+    lib.mb_status_string.restype = ctypes.c_char_p
+    assert lib.mb_status_string(-2) == b"Index has elements out of boundary!"
+    assert lib.mb_status_string(-3) == b"Dimension of weights and indexes doesn't match!"
+    assert lib.mb_status_string(-4) == b"Weights size must match tree size!"
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from machin_b200.frame.buffers import PrioritizedBuffer, WeightTree
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        WeightTree(5)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        PrioritizedBuffer(buffer_size=5)
+    with pytest.raises(ValueError, match="device-resident"):
+        PrioritizedBuffer(buffer_size=5, buffer_device="cpu")
+    from machin_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.td_target(torch.zeros(2, 1), torch.zeros(2, 1), torch.zeros(2, 1, dtype=torch.bool), 0.9)
+
+
+def test_product_never_imports_the_oracle():
+    out = subprocess.run([sys.executable, "-c",
+                          "import sys; import machin_b200, machin_b200.ops, machin_b200.frame.buffers, "
+                          "machin_b200.frame.algorithms, machin_b200.parallel.server; "
+                          "print(sorted(m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')))"],
+                         cwd=ROOT, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip() == "[]"
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "machin_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_host_logic_ring_layout_and_transition():
+    import torch as t
+    from machin_b200.frame.buffers.device_ring import Field, layout
+    from machin_b200.frame.transition import Transition
+    fields = [Field("state/state", "state", "state", t.float32, (84,), "major"),
+              Field("action/action", "action", "action", t.int64, (1,), "major"),
+              Field("next_state/state", "next_state", "state", t.float32, (84,), "major"),
+              Field("reward", "reward", None, t.float32, (1,), "sub"),
+              Field("terminal", "terminal", None, t.bool, (1,), "sub")]
+    pitch = layout(fields)
+    assert pitch == 688 and sum(f.nbytes for f in fields) == 685         # 685 B per C2 row
+    assert all(f.offset % 16 == 0 for f in fields if f.nbytes >= 16)
+    spans = sorted((f.offset, f.offset + f.nbytes) for f in fields)
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+    tr = Transition(state={"s": t.zeros(1, 3)}, action={"a": t.zeros(1, 1)}, next_state={"s": t.zeros(1, 3)},
+                    reward=1.0, terminal=False, zeta=1, alpha=2)
+    assert tr.keys() == ["state", "action", "next_state", "reward", "terminal", "alpha", "zeta"]
+    with pytest.raises(ValueError):
+        Transition(state={"s": t.zeros(2, 3)}, action={"a": t.zeros(2, 1)}, next_state={"s": t.zeros(2, 3)},
+                   reward=1.0, terminal=False)

@@ -36,7 +36,7 @@ for rep in range(4):
     buf.update_priority(out["abs_error"], idx)
     big_i = t.randint(0, N, (1_000_000,), device=dev)
     buf.update_priority(t.rand(1_000_000, device=dev), big_i)
-    qs = t.rand(1 << 20, dtype=t.float64, device=dev) * 1000.0
+    qs = t.rand(1 << 20, dtype=t.float64, device=dev) * buf.wt_tree.get_weight_sum()
     buf.wt_tree.find_leaf_index(qs)
     S = 1024 * 20
     v, nv, r = (t.randn(S, device=dev) for _ in range(3))
