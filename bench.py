@@ -49,6 +49,7 @@ def parse():
     p.add_argument("--cpu-steps", type=int, default=1500)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per update")
+    p.add_argument("--foreach-adam", action="store_true", help="torch's foreach Adam instead of its fused multi-tensor kernel")
     return p.parse_args()
 
 
@@ -199,7 +200,9 @@ def build_learner(a, device, seed, world=1):
         buf = learner.replay_buffer
     else:
         buf = PrioritizedBuffer(buffer_size=a.replay_rows, buffer_device=device)
-        learner = DQNPer(qnet, qtgt, t.optim.Adam, t.nn.MSELoss(reduction="none"), batch_size=a.batch,
+        import functools
+        adam = t.optim.Adam if a.foreach_adam else functools.partial(t.optim.Adam, fused=True)
+        learner = DQNPer(qnet, qtgt, adam, t.nn.MSELoss(reduction="none"), batch_size=a.batch,
                          learning_rate=1e-3, discount=0.99, update_rate=0.005, replay_buffer=buf)
     gen = t.Generator(device=device).manual_seed(seed)
     chunk = 1_000_000

@@ -217,7 +217,8 @@ class DQNPer(TorchFramework):
             else:
                 self._backward(value_loss)
             self._sync_grads()
-            nn.utils.clip_grad_norm_(self.qnet.parameters(), self.grad_max)
+            if np.isfinite(self.grad_max):   # with max_norm = inf the reference's clip multiplies by exactly 1.0
+                nn.utils.clip_grad_norm_(self.qnet.parameters(), self.grad_max)
             self.qnet_optim.step()
         if update_target:
             if self.update_rate is not None:
