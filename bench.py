@@ -49,7 +49,8 @@ def parse():
     p.add_argument("--cpu-steps", type=int, default=1500)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per update")
-    p.add_argument("--foreach-adam", action="store_true", help="torch's foreach Adam instead of its fused multi-tensor kernel")
+    p.add_argument("--torch-net", action="store_true",
+                   help="generic path: nn.Sequential Q-net + torch.optim.Adam(fused=True) instead of FusedMLP + FusedAdam")
     return p.parse_args()
 
 
@@ -184,6 +185,9 @@ def build_learner(a, device, seed, world=1):
         def forward(self, state):
             return self.fc3(t.relu(self.fc2(t.relu(self.fc1(state)))))
 
+    from machin_b200.model import FusedAdam, FusedMLP
+    if not a.torch_net:
+        Q = lambda: FusedMLP([STATE_DIM, HIDDEN, HIDDEN, N_ACTIONS])  # noqa: E731  same layers, fused kernels
     t.manual_seed(seed)
     qnet, qtgt = Q().to(device), Q().to(device)
     if world > 1:
@@ -194,14 +198,14 @@ def build_learner(a, device, seed, world=1):
         group = ShardGroup("apex", device=device)
         t.manual_seed(0)   # identical initial weights on every learner
         qnet, qtgt = Q().to(device), Q().to(device)
-        learner = DQNApex(qnet, qtgt, t.optim.Adam, t.nn.MSELoss(reduction="none"), group,
+        learner = DQNApex(qnet, qtgt, t.optim.Adam if a.torch_net else FusedAdam, t.nn.MSELoss(reduction="none"), group,
                           (PushPullModelServer("qnet", group, 0),), batch_size=a.batch, learning_rate=1e-3,
                           discount=0.99, update_rate=0.005, replay_size=a.replay_rows, learner_group=group)
         buf = learner.replay_buffer
     else:
         buf = PrioritizedBuffer(buffer_size=a.replay_rows, buffer_device=device)
         import functools
-        adam = t.optim.Adam if a.foreach_adam else functools.partial(t.optim.Adam, fused=True)
+        adam = functools.partial(t.optim.Adam, fused=True) if a.torch_net else FusedAdam
         learner = DQNPer(qnet, qtgt, adam, t.nn.MSELoss(reduction="none"), batch_size=a.batch,
                          learning_rate=1e-3, discount=0.99, update_rate=0.005, replay_buffer=buf)
     gen = t.Generator(device=device).manual_seed(seed)
@@ -416,6 +420,7 @@ def run_b200(a):
         "config": {"workload": workload_name(a), "batch": B, "replay_rows": a.replay_rows, "optimizer": "Adam",
                    "parallelism": f"{world} learner(s), one replay shard each",
                    "launch": "one CUDA graph per update" if graph else "eager",
+                   "net": "nn.Module + torch Adam(fused)" if a.torch_net else "FusedMLP + FusedAdam (csrc/mlp.cu)",
                    "exchange": None if world == 1 else "per update: all-gather of shard sums, all-to-all of sampled rows, "
                                "all-to-all of priority write-backs, all-reduce of gradients, broadcast of weights (NCCL)",
                    "l2": "inputs larger than L2: 268 MB tree + 6.9 GB ring, randomly addressed every step"},

@@ -192,6 +192,31 @@ int mb_soft_update_multi(float *const *d_targets, const float *const *d_sources,
                          int n_tensors, double rate, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Value-network math for plain Linear+ReLU stacks (float32, fixed summation order).  The reference
+ * leaves Q / critic networks to the user's nn.Module (dqn_per.py:105-113); this is the optional fused
+ * path for the MLPs its tests and examples use (test_apex.py:25-40).  All matrices row-major.
+ * d_workspace (floats) / d_counters (zeroed ints, one per 64x64 output tile) enable split-K; pass NULL to
+ * disable it.
+ * ------------------------------------------------------------------------------------------ */
+/* y[M,N] = x[M,K] * w[N,K]^T + b[N], optional ReLU          (nn.Linear + ReLU) */
+int mb_mlp_linear_forward(const float *d_x, const float *d_w, const float *d_b, float *d_y, int M, int N,
+                          int K, int relu, float *d_workspace, int64_t workspace_floats, int *d_counters,
+                          int n_counters, void *stream);
+/* dx[M,K] = dy[M,N] * w[N,K], zeroed where d_act_mask[M,K] <= 0 (ReLU backward; mask nullable) */
+int mb_mlp_linear_backward_input(const float *d_dy, const float *d_w, const float *d_act_mask, float *d_dx,
+                                 int M, int N, int K, float *d_workspace, int64_t workspace_floats,
+                                 int *d_counters, int n_counters, void *stream);
+/* dw[N,K] = dy[M,N]^T * x[M,K] ; db[N] = column sums of dy (nullable) */
+int mb_mlp_linear_backward_weight(const float *d_dy, const float *d_x, float *d_dw, float *d_db, int M, int N,
+                                  int K, float *d_workspace, int64_t workspace_floats, int *d_counters,
+                                  int n_counters, void *stream);
+/* torch.optim.Adam step (amsgrad off) over n_tensors parameter tensors in one launch; d_step_count is a
+ * device float incremented by the call (capturable in a CUDA graph).  Pointer arrays live on the HOST. */
+int mb_adam_step_multi(float *const *d_params, const float *const *d_grads, float *const *d_exp_avg,
+                       float *const *d_exp_avg_sq, const int64_t *sizes, int n_tensors, float *d_step_count,
+                       double lr, double beta1, double beta2, double eps, double weight_decay, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Trajectory reverse scans
  * ------------------------------------------------------------------------------------------ */
 /* IMPALA V-trace (impala.py:322-362), float32.  Steps are flattened episode-major; episode e

@@ -1,0 +1,129 @@
+"""Fused value networks and optimizer for the learner step (optional fast path).
+
+``FusedMLP`` is an ``nn.Module`` for plain ``Linear -> ReLU -> ... -> Linear`` stacks whose forward and
+backward run one libmachin_b200 kernel per layer per direction (csrc/mlp.cu) instead of ~8 library
+launches per layer; parameters are ordinary ``nn.Linear`` weights/biases, so ``state_dict``, soft/hard
+target updates, model servers and checkpoints see a normal module.  ``FusedAdam`` is
+``torch.optim.Adam`` (amsgrad off) as one multi-tensor kernel, CUDA-graph capturable.
+Any other ``nn.Module`` / optimizer keeps working through the generic autograd path.
+"""
+import ctypes as C
+from typing import List, Sequence
+
+import torch as t
+import torch.nn as nn
+
+from . import _lib
+from ._lib import lib
+
+
+class _Workspace:
+    """Split-K scratch shared by the layers of one network (launches are stream-ordered)."""
+
+    def __init__(self, device, floats=1 << 21, counters=256):
+        self.buf = t.empty(floats, dtype=t.float32, device=device)
+        self.cnt = t.zeros(counters, dtype=t.int32, device=device)
+
+    def args(self):
+        return _lib.ptr(self.buf), self.buf.numel(), _lib.ptr(self.cnt), self.cnt.numel()
+
+
+def _linear_fwd(x, w, b, relu, ws):
+    M, K = x.shape
+    N = w.shape[0]
+    y = t.empty((M, N), dtype=t.float32, device=x.device)
+    _lib.check(lib.mb_mlp_linear_forward(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), M, N, K, int(relu),
+                                         *ws.args(), _lib.stream_ptr()))
+    return y
+
+
+class _MLPFunction(t.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ws, *params):
+        x = x.contiguous().float()
+        n_layers = len(params) // 2
+        acts = [x]
+        for l in range(n_layers):
+            acts.append(_linear_fwd(acts[-1], params[2 * l], params[2 * l + 1], l < n_layers - 1, ws))
+        ctx.ws = ws
+        ctx.n_layers = n_layers
+        ctx.save_for_backward(*acts[:-1], *params[0::2])
+        return acts[-1]
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, ws = ctx.n_layers, ctx.ws
+        saved = ctx.saved_tensors
+        inputs, weights = saved[:n], saved[n:]
+        dy = dy.contiguous().float()
+        grads = [None] * (2 * n)
+        dx = None
+        for l in range(n - 1, -1, -1):
+            x, w = inputs[l], weights[l]
+            M, K = x.shape
+            N = w.shape[0]
+            dw = t.empty_like(w)
+            db = t.empty(N, dtype=t.float32, device=w.device)
+            _lib.check(lib.mb_mlp_linear_backward_weight(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(dw), _lib.ptr(db), M, N, K,
+                                                         *ws.args(), _lib.stream_ptr()))
+            grads[2 * l], grads[2 * l + 1] = dw, db
+            if l > 0 or ctx.needs_input_grad[0]:
+                dxl = t.empty((M, K), dtype=t.float32, device=w.device)
+                _lib.check(lib.mb_mlp_linear_backward_input(_lib.ptr(dy), _lib.ptr(w), _lib.ptr(x) if l > 0 else None,
+                                                            _lib.ptr(dxl), M, N, K, *ws.args(), _lib.stream_ptr()))
+                dy = dxl
+                if l == 0:
+                    dx = dxl
+        return (dx, None, *grads)
+
+
+class FusedMLP(nn.Module):
+    def __init__(self, sizes: Sequence[int]):
+        """``sizes`` = [in, hidden..., out]; ReLU between layers, none after the last."""
+        super().__init__()
+        self.sizes = list(sizes)
+        self.layers = nn.ModuleList([nn.Linear(a, b) for a, b in zip(sizes[:-1], sizes[1:])])
+        self._ws = None
+
+    def _workspace(self, device):
+        if self._ws is None or self._ws.buf.device != device:
+            self._ws = _Workspace(device)
+        return self._ws
+
+    def forward(self, state, action=None):
+        x = state if action is None else t.cat([state, action.to(state.dtype)], dim=1)
+        if not x.is_cuda:
+            raise RuntimeError("FusedMLP runs on CUDA tensors only (no CPU fallback)")
+        params = [p for layer in self.layers for p in (layer.weight, layer.bias)]
+        with t.cuda.device(x.device):
+            return _MLPFunction.apply(x, self._workspace(x.device), *params)
+
+
+class FusedAdam(t.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    @t.no_grad()
+    def step(self, closure=None):
+        for group in self.param_groups:
+            ps = [p for p in group["params"] if p.grad is not None]
+            if not ps:
+                continue
+            for p in ps:
+                st = self.state[p]
+                if not st:
+                    st["exp_avg"] = t.zeros_like(p)
+                    st["exp_avg_sq"] = t.zeros_like(p)
+            first = self.state[group["params"][0]]
+            if "step" not in first:
+                first["step"] = t.zeros((), dtype=t.float32, device=ps[0].device)
+            n = len(ps)
+            arr = lambda xs: (C.c_void_p * n)(*[x.data_ptr() for x in xs])
+            sizes = (C.c_int64 * n)(*[p.numel() for p in ps])
+            b1, b2 = group["betas"]
+            with t.cuda.device(ps[0].device):
+                _lib.check(lib.mb_adam_step_multi(arr(ps), arr([p.grad for p in ps]),
+                                                  arr([self.state[p]["exp_avg"] for p in ps]),
+                                                  arr([self.state[p]["exp_avg_sq"] for p in ps]), sizes, n,
+                                                  _lib.ptr(first["step"]), float(group["lr"]), float(b1), float(b2),
+                                                  float(group["eps"]), float(group["weight_decay"]), _lib.stream_ptr()))

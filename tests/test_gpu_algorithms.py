@@ -199,3 +199,72 @@ def test_a2c_store_episode_vs_reference(lam):
     assert adv.shape == (bs, 1) and adv.dtype == t.float32
     pol, val = a2c.update()
     assert np.isfinite(pol) and np.isfinite(val) and a2c.replay_buffer.size() == 0
+
+
+# ----------------------------------------------------------------------------- fused MLP / Adam
+@pytest.mark.parametrize("sizes,batch", [([84, 256, 256, 6], 512), ([6, 16, 16, 4], 32), ([393, 300, 1], 100), ([5, 7], 3)])
+def test_fused_mlp_matches_torch(sizes, batch):
+    from machin_b200.model import FusedMLP
+    t.manual_seed(0)
+    net = FusedMLP(sizes).cuda()
+    ref = t.nn.Sequential()
+    for i, layer in enumerate(net.layers):
+        lin = t.nn.Linear(layer.in_features, layer.out_features).cuda()
+        lin.load_state_dict(layer.state_dict())
+        ref.append(lin)
+        if i < len(net.layers) - 1:
+            ref.append(t.nn.ReLU())
+    x = t.randn(batch, sizes[0], device="cuda", requires_grad=True)
+    x2 = x.detach().clone().requires_grad_()
+    y, y2 = net(x), ref(x2)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), y2.detach().cpu().numpy(), rtol=1e-5, atol=1e-6)
+    gy = t.randn_like(y)
+    y.backward(gy)
+    y2.backward(gy)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), x2.grad.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    for a, b in zip(net.parameters(), ref.parameters()):
+        np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    with t.no_grad():
+        assert net(x).shape == (batch, sizes[-1])
+
+
+def test_fused_adam_matches_torch():
+    from machin_b200.model import FusedAdam
+    t.manual_seed(1)
+    ps = [t.randn(s, device="cuda") for s in ((256, 84), (256,), (6, 256), (6,))]
+    a = [p.clone().requires_grad_() for p in ps]
+    b = [p.clone().requires_grad_() for p in ps]
+    oa, ob = FusedAdam(a, lr=1e-3, weight_decay=0.01), t.optim.Adam(b, lr=1e-3, weight_decay=0.01)
+    for step in range(5):
+        gs = [t.randn_like(p) for p in ps]
+        for x, y, g_ in zip(a, b, gs):
+            x.grad, y.grad = g_.clone(), g_.clone()
+        oa.step()
+        ob.step()
+    for x, y in zip(a, b):
+        np.testing.assert_allclose(x.detach().cpu().numpy(), y.detach().cpu().numpy(), rtol=2e-6, atol=1e-7)
+
+
+def test_dqn_per_fused_net_vs_reference():
+    """The reference fixture again, with the Q-nets as FusedMLP (csrc/mlp.cu) and the update in a CUDA graph."""
+    from machin_b200.frame.algorithms import DQNPer
+    from machin_b200.model import FusedMLP
+    g = np.load(os.path.join(GOLDEN, "ref_td.npz"))
+    S, A, N, B = 6, 4, 200, 32
+    qnet, qtgt = FusedMLP([S, 16, 16, A]).cuda(), FusedMLP([S, 16, 16, A]).cuda()
+    _load_flat(qtgt, g["dqn_init_qt"])
+    dqn = DQNPer(qnet, qtgt, t.optim.SGD, t.nn.MSELoss(reduction="sum"), batch_size=B, learning_rate=0.01,
+                 discount=0.97, update_rate=0.05, replay_size=N)
+    ep = [dict(state={"state": t.from_numpy(g["dqn_state"][i:i + 1])}, action={"action": t.tensor([[g["dqn_action"][i]]])},
+               next_state={"state": t.from_numpy(g["dqn_next_state"][i:i + 1])}, reward=float(g["dqn_reward"][i]),
+               terminal=bool(g["dqn_terminal"][i])) for i in range(N)]
+    dqn.replay_buffer.store_episode(ep, priorities=list(g["dqn_priority"]))
+    dqn.enable_cuda_graph()
+    np.random.seed(11)
+    for step in range(3):
+        loss = dqn.update()
+        ref = float(g[f"dqn_loss{step}"])
+        assert abs(loss - ref) <= 1e-5 * abs(ref), (step, loss, ref)
+        np.testing.assert_allclose(dqn.replay_buffer.wt_tree.weights, g[f"dqn_tree{step + 1}"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(_flat(dqn.qnet), g[f"dqn_q{step + 1}"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(_flat(dqn.qnet_target), g[f"dqn_qt{step + 1}"], rtol=1e-5, atol=1e-6)
