@@ -210,6 +210,21 @@ int mb_mlp_linear_backward_input(const float *d_dy, const float *d_w, const floa
 int mb_mlp_linear_backward_weight(const float *d_dy, const float *d_x, float *d_dw, float *d_db, int M, int N,
                                   int K, float *d_workspace, int64_t workspace_floats, int *d_counters,
                                   int n_counters, void *stream);
+/* The whole double-DQN value math of one learner update for Linear+ReLU Q-nets -- forward of Q(s), Q(s'),
+ * Q_target(s'), the TD row math of mb_td_dqn, and the backward pass into d_grads -- as ONE cooperative
+ * launch (a persistent kernel walks a list of GEMM work items; phases are separated by grid syncs).
+ * sizes: n_layers + 1 widths; d_params / d_target_params / d_grads: HOST arrays of 2 * n_layers device
+ * pointers (w0, b0, w1, b1, ...).  All device pointers are captured at creation and must stay valid
+ * (static batch buffers: CUDA-graph friendly).  Replaces dqn_per.py:105-139 + the user MLP's autograd. */
+typedef struct mb_mlp_program mb_mlp_program;
+int mb_dqn_mlp_program_create(int device, int n_layers, const int *sizes, int batch, float *const *d_params,
+                              float *const *d_target_params, float *const *d_grads, const float *d_state,
+                              const float *d_next_state, const int64_t *d_action, const float *d_reward,
+                              const uint8_t *d_terminal, const double *d_is_weight, float discount, int mode,
+                              float *d_y, float *d_action_value, float *d_abs_error, double *d_loss_elem,
+                              mb_mlp_program **out);
+int mb_mlp_program_run(mb_mlp_program *program, void *stream);
+int mb_mlp_program_destroy(mb_mlp_program *program);
 /* torch.optim.Adam step (amsgrad off) over n_tensors parameter tensors in one launch; d_step_count is a
  * device float incremented by the call (capturable in a CUDA graph).  Pointer arrays live on the HOST. */
 int mb_adam_step_multi(float *const *d_params, const float *const *d_grads, float *const *d_exp_avg,

@@ -14,11 +14,19 @@
 //   weight grad    dw[n, k] = sum_m dy[m, n] * x[m, k]   ;  db[n] = sum_m dy[m, n]  (virtual column of ones)
 // Tile 64x64, 256 threads, 4x4 micro-tile per thread, K-step 16; split-K over gridDim.z so that the grid
 // reaches ~1 CTA per SM even though the matrices are small.
+#include <cooperative_groups.h>
+
+#include <new>
+#include <vector>
+
 #include "mb_common.cuh"
+#include "td_device.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int TM = 64, TN = 64, TK = 16, NT = 256;
+constexpr int TM = 64, TN = 64, TK = 32, NT = 256;
 
 struct GemmArgs {
     const float *A;
@@ -50,14 +58,20 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs &g, int i, int j, 
     g.C[(int64_t)i * g.c_i + j] = v;
 }
 
+struct GemmSmem {
+    float As[TK][TM + 4];
+    float Bs[TK][TN + 4];
+    int last;
+};
+
+// One work item = one 64x64 output tile x one K-split.  Called by the stand-alone GEMM kernels and by
+// the persistent program executor below.
 template <bool kAKfast, bool kBKfast>
-__global__ void __launch_bounds__(NT) gemm_kernel(GemmArgs g) {
-    __shared__ float As[TK][TM + 4];
-    __shared__ float Bs[TK][TN + 4];
-    __shared__ int s_last;
+__device__ __forceinline__ void gemm_item(const GemmArgs &g, GemmSmem &sm, int tile_x, int tile_y, int tiles_x,
+                                          int split, int splits) {
     const int tid = threadIdx.x;
-    const int i0 = blockIdx.y * TM, j0 = blockIdx.x * TN;
-    const int k_begin = blockIdx.z * g.k_per_split;
+    const int i0 = tile_y * TM, j0 = tile_x * TN;
+    const int k_begin = split * g.k_per_split;
     const int k_end = min(g.K, k_begin + g.k_per_split);
     const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads, 4 x 4 outputs each
     float acc[4][4];
@@ -71,7 +85,7 @@ __global__ void __launch_bounds__(NT) gemm_kernel(GemmArgs g) {
             int i, k;
             if (kAKfast) { i = e / TK; k = e % TK; } else { k = e / TM; i = e % TM; }
             const int gi = i0 + i, gk = k0 + k;
-            As[k][i] = (gi < g.M && gk < k_end) ? g.A[(int64_t)gi * g.a_i + (int64_t)gk * g.a_k] : 0.0f;
+            sm.As[k][i] = (gi < g.M && gk < k_end) ? __ldcg(g.A + (int64_t)gi * g.a_i + (int64_t)gk * g.a_k) : 0.0f;
         }
 #pragma unroll
         for (int e = tid; e < TN * TK; e += NT) {
@@ -79,14 +93,15 @@ __global__ void __launch_bounds__(NT) gemm_kernel(GemmArgs g) {
             if (kBKfast) { j = e / TK; k = e % TK; } else { k = e / TN; j = e % TN; }
             const int gj = j0 + j, gk = k0 + k;
             float v = 0.0f;
-            if (gj < g.N && gk < k_end) v = (gj == g.ones_col) ? 1.0f : g.B[(int64_t)gj * g.b_j + (int64_t)gk * g.b_k];
-            Bs[k][j] = v;
+            if (gj < g.N && gk < k_end)
+                v = (gj == g.ones_col) ? 1.0f : __ldcg(g.B + (int64_t)gj * g.b_j + (int64_t)gk * g.b_k);
+            sm.Bs[k][j] = v;
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < TK; ++k) {
-            const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+            const float4 a = *reinterpret_cast<const float4 *>(&sm.As[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&sm.Bs[k][tx * 4]);
             const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int x = 0; x < 4; ++x)
@@ -95,7 +110,6 @@ __global__ void __launch_bounds__(NT) gemm_kernel(GemmArgs g) {
         }
         __syncthreads();
     }
-    const int splits = gridDim.z;
     if (splits == 1) {
 #pragma unroll
         for (int x = 0; x < 4; ++x)
@@ -105,7 +119,7 @@ __global__ void __launch_bounds__(NT) gemm_kernel(GemmArgs g) {
     }
     // split-K: park the partial tile, the last CTA of this tile sums the partials in split order
     const int64_t MN = (int64_t)g.M * g.N;
-    float *mine = g.partial + (int64_t)blockIdx.z * MN;
+    float *mine = g.partial + (int64_t)split * MN;
 #pragma unroll
     for (int x = 0; x < 4; ++x)
 #pragma unroll
@@ -115,10 +129,10 @@ __global__ void __launch_bounds__(NT) gemm_kernel(GemmArgs g) {
         }
     __threadfence();
     __syncthreads();
-    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-    if (tid == 0) s_last = (atomicAdd(g.tile_counter + tile, 1) == splits - 1);
+    const int tile = tile_y * tiles_x + tile_x;
+    if (tid == 0) sm.last = (atomicAdd(g.tile_counter + tile, 1) == splits - 1);
     __syncthreads();
-    if (!s_last) return;
+    if (!sm.last) return;
     __threadfence();
 #pragma unroll
     for (int x = 0; x < 4; ++x)
@@ -132,11 +146,18 @@ __global__ void __launch_bounds__(NT) gemm_kernel(GemmArgs g) {
             }
         }
     if (tid == 0) g.tile_counter[tile] = 0;
+    __syncthreads();
+}
+
+template <bool kAKfast, bool kBKfast>
+__global__ void __launch_bounds__(NT) gemm_kernel(GemmArgs g) {
+    __shared__ GemmSmem sm;
+    gemm_item<kAKfast, kBKfast>(g, sm, blockIdx.x, blockIdx.y, gridDim.x, blockIdx.z, gridDim.z);
 }
 
 int pick_splits(int tiles, int K) {
     int s = 1;
-    while (tiles * s * 2 <= 160 && (K / (s * 2)) >= 32 && s < 16) s *= 2;
+    while (tiles * s * 2 <= 2 * mb::kNumSMs && (K / (s * 2)) >= 64 && s < 16) s *= 2;
     return s;
 }
 
@@ -153,6 +174,54 @@ int launch(GemmArgs g, float *workspace, int64_t workspace_floats, int *counters
     gemm_kernel<kA, kB><<<dim3(tx, ty, splits), NT, 0, s>>>(g);
     MB_LAUNCHED(1);
     return MB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent "program" executor: the whole double-DQN value math of one learner update -- three forward
+// passes (Q(s), Q(s'), Q_target(s')), the TD target / |delta| / loss / dloss/dq row math and the full
+// backward pass -- in ONE cooperative launch.  A program is a list of ops grouped in phases; within a
+// phase the CTAs of the grid pull work items (64x64 tile x K-split, or 256 TD rows) round-robin, phases
+// are separated by grid.sync().  Replaces ~75 dependent library launches (or 16 of the stand-alone GEMM
+// launches above) whose cost is launch gaps and single-wave latency, not arithmetic.
+// ---------------------------------------------------------------------------------------------
+enum OpKind { OP_GEMM_KK = 0, OP_GEMM_KJ = 1, OP_GEMM_IJ = 2, OP_TD_DQN = 3 };
+
+struct ProgOp {
+    GemmArgs g;
+    TdDqnArgs td;
+    int kind, phase, tiles_x, tiles_y, splits, items;
+};
+
+__global__ void __launch_bounds__(NT) mlp_program_kernel(const ProgOp *__restrict__ ops, int n_ops, int n_phases) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ GemmSmem sm;
+    __shared__ ProgOp s_op;
+    int op0 = 0;
+    for (int ph = 0; ph < n_phases; ++ph) {
+        int op1 = op0, total = 0;
+        while (op1 < n_ops && ops[op1].phase == ph) total += ops[op1++].items;
+        for (int item = blockIdx.x; item < total; item += gridDim.x) {
+            int o = op0, local = item;
+            while (local >= ops[o].items) local -= ops[o++].items;
+            __syncthreads();  // previous item's readers of s_op are done
+            for (int e = threadIdx.x; e < (int)(sizeof(ProgOp) / 4); e += NT)
+                reinterpret_cast<int *>(&s_op)[e] = reinterpret_cast<const int *>(ops + o)[e];
+            __syncthreads();
+            if (s_op.kind == OP_TD_DQN) {
+                const int64_t b = (int64_t)local * NT + threadIdx.x;
+                if (b < s_op.td.batch) td_dqn_row(s_op.td, b);
+            } else {
+                const int tiles = s_op.tiles_x * s_op.tiles_y;
+                const int split = local / tiles, tl = local % tiles;
+                const int tyi = tl / s_op.tiles_x, txi = tl % s_op.tiles_x;
+                if (s_op.kind == OP_GEMM_KK) gemm_item<true, true>(s_op.g, sm, txi, tyi, s_op.tiles_x, split, s_op.splits);
+                else if (s_op.kind == OP_GEMM_KJ) gemm_item<true, false>(s_op.g, sm, txi, tyi, s_op.tiles_x, split, s_op.splits);
+                else gemm_item<false, false>(s_op.g, sm, txi, tyi, s_op.tiles_x, split, s_op.splits);
+            }
+        }
+        op0 = op1;
+        if (ph + 1 < n_phases) grid.sync();
+    }
 }
 
 // fused multi-tensor Adam (torch.optim.Adam semantics, amsgrad = False, maximize = False)
@@ -230,6 +299,154 @@ int mb_mlp_linear_backward_weight(const float *d_dy, const float *d_x, float *d_
     g.M = N; g.N = d_db ? K + 1 : K; g.K = M;
     g.ones_col = d_db ? K : -1; g.extra = d_db;
     return launch<false, false>(g, d_workspace, workspace_floats, d_counters, n_counters, (cudaStream_t)stream);
+}
+
+struct mb_mlp_program {
+    int device;
+    ProgOp *d_ops;
+    int n_ops, n_phases, grid;
+    std::vector<void *> owned;   // device allocations (activations, partials, counters)
+};
+
+namespace {
+
+struct Builder {
+    std::vector<ProgOp> ops;
+    std::vector<void *> *owned;
+    int grid;
+    bool failed = false;
+
+    void *alloc(size_t bytes, bool zero) {
+        void *p = nullptr;
+        if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) { failed = true; cudaGetLastError(); return nullptr; }
+        if (zero) cudaMemset(p, 0, bytes ? bytes : 16);
+        owned->push_back(p);
+        return p;
+    }
+    void add_gemm(int phase, int kind, GemmArgs g) {
+        ProgOp op{};
+        op.kind = kind; op.phase = phase;
+        op.tiles_x = (g.N + TN - 1) / TN; op.tiles_y = (g.M + TM - 1) / TM;
+        const int tiles = op.tiles_x * op.tiles_y;
+        int splits = 1;   // enough K-splits that a phase offers ~2 items per CTA, each with >= 32 of K
+        while (tiles * splits * 2 <= 2 * grid && g.K / (splits * 2) >= TK && splits < 32) splits *= 2;
+        g.k_per_split = ((g.K + splits - 1) / splits + TK - 1) / TK * TK;
+        splits = (g.K + g.k_per_split - 1) / g.k_per_split;
+        if (splits > 1) {
+            g.partial = (float *)alloc(sizeof(float) * (size_t)splits * g.M * g.N, false);
+            g.tile_counter = (int *)alloc(sizeof(int) * (size_t)tiles, true);
+        }
+        op.g = g; op.splits = splits; op.items = tiles * splits;
+        ops.push_back(op);
+    }
+};
+
+}  // namespace
+
+int mb_dqn_mlp_program_create(int device, int n_layers, const int *sizes, int batch, float *const *d_params,
+                              float *const *d_target_params, float *const *d_grads, const float *d_state,
+                              const float *d_next_state, const int64_t *d_action, const float *d_reward,
+                              const uint8_t *d_terminal, const double *d_is_weight, float discount, int mode,
+                              float *d_y, float *d_action_value, float *d_abs_error, double *d_loss_elem,
+                              mb_mlp_program **out) {
+    if (!out || n_layers < 1 || n_layers > 8 || batch < 1 || !sizes || !d_params || !d_target_params || !d_grads)
+        return MB_ERR_INVALID;
+    if (mb_device_count() <= device || device < 0) return MB_ERR_NO_DEVICE;
+    mb::DeviceGuard guard(device);
+    mb_mlp_program *P = new (std::nothrow) mb_mlp_program();
+    if (!P) return MB_ERR_NOMEM;
+    P->device = device;
+    int per_sm = 0, sms = mb::kNumSMs;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mlp_program_kernel, NT, 0);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    P->grid = sms * (per_sm >= 2 ? 2 : 1);
+    Builder B;
+    B.owned = &P->owned;
+    B.grid = P->grid;
+    const int L = n_layers, A = sizes[L];
+    const int64_t Bn = batch;
+    // activations: pass 0 = Q(s) online, 1 = Q(s') online, 2 = Q_target(s')
+    float *act[3][9];
+    const float *in[3] = {d_state, d_next_state, d_next_state};
+    for (int p = 0; p < 3; ++p)
+        for (int l = 0; l < L; ++l) act[p][l] = (float *)B.alloc(sizeof(float) * Bn * sizes[l + 1], false);
+    float *dz[9];
+    for (int l = 0; l < L; ++l) dz[l] = (float *)B.alloc(sizeof(float) * Bn * sizes[l + 1], false);  // grad wrt layer-l output
+    int phase = 0;
+    for (int l = 0; l < L; ++l, ++phase)
+        for (int p = 0; p < 3; ++p) {
+            float *const *prm = (p == 2) ? d_target_params : d_params;
+            GemmArgs g{};
+            g.A = l == 0 ? in[p] : act[p][l - 1]; g.a_i = sizes[l]; g.a_k = 1;
+            g.B = prm[2 * l]; g.b_j = sizes[l]; g.b_k = 1;
+            g.C = act[p][l]; g.c_i = sizes[l + 1];
+            g.M = batch; g.N = sizes[l + 1]; g.K = sizes[l];
+            g.ones_col = -1; g.bias = prm[2 * l + 1]; g.relu = l < L - 1;
+            B.add_gemm(phase, OP_GEMM_KK, g);
+        }
+    {   // TD row math: q = act[0][L-1], qn = act[1][L-1], qtn = act[2][L-1]; dloss/dq -> dz[L-1]
+        ProgOp op{};
+        op.kind = OP_TD_DQN; op.phase = phase++;
+        op.td = TdDqnArgs{act[0][L - 1], act[1][L - 1], act[2][L - 1], Bn, A, d_action, d_reward, d_terminal, d_is_weight,
+                          discount, mode, d_y, d_action_value, d_abs_error, d_loss_elem, dz[L - 1]};
+        op.items = (batch + NT - 1) / NT;
+        B.ops.push_back(op);
+    }
+    for (int l = L - 1; l >= 0; --l, ++phase) {
+        const float *x = l == 0 ? d_state : act[0][l - 1];
+        GemmArgs w{};   // dW_l[N, K] = dz_l^T x ; db_l = column sums of dz_l
+        w.A = dz[l]; w.a_i = 1; w.a_k = sizes[l + 1];
+        w.B = x; w.b_j = 1; w.b_k = sizes[l];
+        w.C = d_grads[2 * l]; w.c_i = sizes[l];
+        w.M = sizes[l + 1]; w.N = sizes[l] + 1; w.K = batch;
+        w.ones_col = sizes[l]; w.extra = d_grads[2 * l + 1];
+        B.add_gemm(phase, OP_GEMM_IJ, w);
+        if (l > 0) {    // dz_{l-1}[M, K] = (dz_l W_l) * (act_{l-1} > 0)
+            GemmArgs d{};
+            d.A = dz[l]; d.a_i = sizes[l + 1]; d.a_k = 1;
+            d.B = d_params[2 * l]; d.b_j = 1; d.b_k = sizes[l];
+            d.C = dz[l - 1]; d.c_i = sizes[l];
+            d.M = batch; d.N = sizes[l]; d.K = sizes[l + 1];
+            d.ones_col = -1; d.mask = act[0][l - 1];
+            B.add_gemm(phase, OP_GEMM_KJ, d);
+        }
+    }
+    if (!B.failed) P->d_ops = (ProgOp *)B.alloc(sizeof(ProgOp) * B.ops.size(), false);
+    if (B.failed || cudaMemcpy(P->d_ops, B.ops.data(), sizeof(ProgOp) * B.ops.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError();
+        mb_mlp_program_destroy(P);
+        return MB_ERR_NOMEM;
+    }
+    P->n_ops = (int)B.ops.size();
+    P->n_phases = phase;
+    int max_items = 1;
+    for (int ph = 0; ph < phase; ++ph) {
+        int tot = 0;
+        for (const ProgOp &op : B.ops) if (op.phase == ph) tot += op.items;
+        if (tot > max_items) max_items = tot;
+    }
+    if (P->grid > max_items) P->grid = max_items;
+    MB_CUDA(cudaDeviceSynchronize());
+    *out = P;
+    return MB_OK;
+}
+
+int mb_mlp_program_run(mb_mlp_program *P, void *stream) {
+    if (!P) return MB_ERR_INVALID;
+    mb::DeviceGuard guard(P->device);
+    void *args[] = {&P->d_ops, &P->n_ops, &P->n_phases};
+    MB_CUDA(cudaLaunchCooperativeKernel((const void *)mlp_program_kernel, dim3((unsigned)P->grid), dim3(NT), args, 0,
+                                        (cudaStream_t)stream));
+    mb::count_launch(1);
+    return MB_OK;
+}
+
+int mb_mlp_program_destroy(mb_mlp_program *P) {
+    if (!P) return MB_OK;
+    mb::DeviceGuard guard(P->device);
+    for (void *p : P->owned) cudaFree(p);
+    delete P;
+    return MB_OK;
 }
 
 int mb_adam_step_multi(float *const *d_params, const float *const *d_grads, float *const *d_exp_avg,

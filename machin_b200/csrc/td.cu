@@ -5,47 +5,13 @@
 // each operation rounded separately (no FMA contraction) in the reference's order, so y, the
 // gathered action value and abs_error are bit-identical to CPU torch given the same Q values.
 #include "mb_common.cuh"
+#include "td_device.cuh"
 
 namespace {
 
-__global__ void __launch_bounds__(256) td_dqn_kernel(const float *__restrict__ q, const float *__restrict__ qn,
-                                                     const float *__restrict__ qtn, int64_t batch, int A,
-                                                     const int64_t *__restrict__ action,
-                                                     const float *__restrict__ reward,
-                                                     const uint8_t *__restrict__ terminal,
-                                                     const double *__restrict__ isw, float discount, int mode,
-                                                     float *__restrict__ y_out, float *__restrict__ av_out,
-                                                     float *__restrict__ abs_out, double *__restrict__ loss_out,
-                                                     float *__restrict__ grad_q) {
+__global__ void __launch_bounds__(256) td_dqn_kernel(TdDqnArgs t) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= batch) return;
-    // a* = argmax (first maximum, like t.max(...)[1]) over the online net ("double") or the target net
-    const float *sel = (mode == 0 ? qn : qtn) + b * A;
-    int best = 0;
-    float best_v = sel[0];
-    for (int a = 1; a < A; ++a) {
-        const float v = sel[a];
-        if (v > best_v) { best_v = v; best = a; }
-    }
-    const float next_value = qtn[b * A + best];
-    // reward + discount * ~terminal * next_value  (dqn.py:501): (discount * mask) * next, then + reward
-    const float mask = terminal[b] ? 0.0f : 1.0f;
-    const float y = __fadd_rn(reward[b], __fmul_rn(__fmul_rn(discount, mask), next_value));
-    if (y_out) y_out[b] = y;
-    if (!q) return;
-    int64_t act = action[b];
-    act = act < 0 ? 0 : (act >= A ? A - 1 : act);
-    const float av = q[b * A + act];
-    const float diff = __fsub_rn(av, y);
-    if (av_out) av_out[b] = av;
-    if (abs_out) abs_out[b] = fabsf(diff);                       // sum(|q - y|, dim=1) with one column
-    const double w = isw ? isw[b] : 1.0;
-    if (loss_out) loss_out[b] = (double)__fmul_rn(diff, diff) * w;  // MSE(reduction="none") * is_weight (f64)
-    if (grad_q) {
-        // d mean_b(loss_elem) / d q[b, a]
-        const float g = (float)(2.0 * (double)diff * w / (double)batch);
-        for (int a = 0; a < A; ++a) grad_q[b * A + a] = (a == act) ? g : 0.0f;
-    }
+    if (b < t.batch) td_dqn_row(t, b);
 }
 
 __global__ void __launch_bounds__(256) td_target_kernel(const float *__restrict__ next_value,
@@ -98,9 +64,9 @@ int mb_td_dqn(const float *d_q, const float *d_q_next, const float *d_q_tgt_next
     if (mode == 0 && !d_q_next) return MB_ERR_INVALID;
     if (d_q && !d_action) return MB_ERR_INVALID;
     if (batch == 0) return MB_OK;
-    td_dqn_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        d_q, d_q_next, d_q_tgt_next, batch, n_actions, d_action, d_reward, d_terminal, d_is_weight, discount, mode,
-        d_y, d_action_value, d_abs_error, d_loss_elem, d_grad_q);
+    TdDqnArgs a{d_q, d_q_next, d_q_tgt_next, batch, n_actions, d_action, d_reward, d_terminal, d_is_weight,
+                discount, mode, d_y, d_action_value, d_abs_error, d_loss_elem, d_grad_q};
+    td_dqn_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
     MB_LAUNCHED(1);
     return MB_OK;
 }

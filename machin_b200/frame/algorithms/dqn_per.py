@@ -68,6 +68,7 @@ class DQNPer(TorchFramework):
         # MSELoss: loss, |delta| and dloss/dq all come out of one kernel (td.cu)
         self._fused_mse = isinstance(self.criterion, nn.MSELoss)
         self._graph = None
+        self._program = None
         super().__init__()
 
     # ------------------------------------------------------------------ properties / acting (dqn.py:213-331)
@@ -153,7 +154,8 @@ class DQNPer(TorchFramework):
         cur.wait_stream(side)
         t.cuda.synchronize(dev)
         graph = t.cuda.CUDAGraph()
-        self.qnet_optim.zero_grad(set_to_none=True)
+        if not self._program:
+            self.qnet_optim.zero_grad(set_to_none=True)
         from ..._lib import lib
         launched = lib.mb_launch_count()
         with t.cuda.graph(graph):
@@ -193,7 +195,78 @@ class DQNPer(TorchFramework):
             return self._static_loss
         return self._step(update_value, update_target, uniform, False)
 
+    # ---- fused value math: FusedMLP Q-nets + MSE -> one persistent kernel for forward x3, TD, backward
+    def _fused_program(self):
+        """Build (once) the mb_dqn_mlp_program for this learner, or return None if the nets / buffer do not
+        qualify (then the generic autograd path runs)."""
+        if self._program is not None:
+            return self._program or None
+        from ...model import FusedMLP
+        from ..buffers import PrioritizedBuffer
+        buf = self.replay_buffer
+        self._program = False
+        fields = buf.storage.fields if buf.storage.data is not None else {}
+        sk = [f for f in fields.values() if f.attr == "state" and f.kind == "major"]
+        nk = [f for f in fields.values() if f.attr == "next_state" and f.kind == "major"]
+        ak = [f for f in fields.values() if f.attr == "action" and f.kind == "major"]
+        ok = (type(buf) is PrioritizedBuffer and isinstance(self.qnet, FusedMLP) and isinstance(self.qnet_target, FusedMLP)
+              and self._fused_mse and self.qnet.sizes == self.qnet_target.sizes and len(sk) == len(nk) == len(ak) == 1
+              and sk[0].dtype == t.float32 and sk[0].shape == (self.qnet.sizes[0],) and ak[0].dtype == t.int64
+              and fields["reward"].dtype == t.float32 and fields["terminal"].dtype == t.bool
+              and type(self)._criticize is DQNPer._criticize)
+        if not ok:
+            return None
+        import ctypes as C
+        from ..._lib import lib, ptr, check
+        dev, B, sizes = buf.buffer_device, self.batch_size, self.qnet.sizes
+        L = len(sizes) - 1
+        names = [sk[0].name, ak[0].name, "reward", nk[0].name, "terminal"]
+        st = {"names": names, "index": t.empty(B, dtype=t.int64, device=dev), "isw": t.empty(B, dtype=t.float64, device=dev),
+              "fields": {n: t.empty((B,) + fields[n].shape, dtype=fields[n].dtype, device=dev) for n in names},
+              "y": t.empty((B, 1), dtype=t.float32, device=dev), "av": t.empty((B, 1), dtype=t.float32, device=dev),
+              "abs": t.empty(B, dtype=t.float32, device=dev), "loss": t.empty((B, 1), dtype=t.float64, device=dev)}
+        plist = lambda net: [p for layer in net.layers for p in (layer.weight, layer.bias)]
+        for p in plist(self.qnet):
+            p.grad = t.zeros_like(p)       # static gradient buffers, fully overwritten by every run
+        arr = lambda xs: (C.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
+        handle = C.c_void_p()
+        with t.cuda.device(dev):
+            check(lib.mb_dqn_mlp_program_create(
+                dev.index, L, (C.c_int * (L + 1))(*sizes), B, arr(plist(self.qnet)), arr(plist(self.qnet_target)),
+                arr([p.grad for p in plist(self.qnet)]), ptr(st["fields"][names[0]]), ptr(st["fields"][names[3]]),
+                ptr(st["fields"][names[1]]), ptr(st["fields"]["reward"]), ptr(st["fields"]["terminal"]), ptr(st["isw"]),
+                float(self.discount), 0 if self.mode == "double" else 1, ptr(st["y"]), ptr(st["av"]), ptr(st["abs"]),
+                ptr(st["loss"]), C.byref(handle)))
+        st["handle"] = handle
+        self._program = st
+        return st
+
+    def _step_fused(self, st, update_value, update_target, uniform, use_device_params) -> t.Tensor:
+        from ..._lib import lib, check, stream_ptr
+        buf = self.replay_buffer
+        buf._draw(self.batch_size, uniform=uniform, use_device_params=use_device_params, out=(st["index"], st["isw"]))
+        buf.storage.gather(st["index"], names=st["names"], out=st["fields"])
+        with t.cuda.device(buf.buffer_device):
+            check(lib.mb_mlp_program_run(st["handle"], stream_ptr()))
+        buf.update_priority(st["abs"], st["index"])
+        if update_value:
+            self._sync_grads()
+            if np.isfinite(self.grad_max):
+                nn.utils.clip_grad_norm_(self.qnet.parameters(), self.grad_max)
+            self.qnet_optim.step()
+        if update_target:
+            if self.update_rate is not None:
+                soft_update(self.qnet_target, self.qnet, self.update_rate)
+            else:
+                self._update_counter += 1
+                if self._update_counter % self.update_steps == 0:
+                    hard_update(self.qnet_target, self.qnet)
+        return st["loss"].mean()
+
     def _step(self, update_value, update_target, uniform, use_device_params) -> t.Tensor:
+        st = self._fused_program()
+        if st is not None:
+            return self._step_fused(st, update_value, update_target, uniform, use_device_params)
         self.qnet.train()
         batch_size, state, action, reward, next_state, terminal, d_index, d_isw = self._sample(uniform, use_device_params)
         with t.no_grad():

@@ -101,11 +101,13 @@ class DeviceRing:
         _lib.check(lib.mb_rows_scatter(_lib.ptr(self.data), self.pitch, self.max_size, first_slot, n,
                                        arr, len(names), _lib.stream_ptr(stream)))
 
-    def gather(self, index: t.Tensor, names=None, stream=None) -> Dict[str, t.Tensor]:
+    def gather(self, index: t.Tensor, names=None, stream=None, out: Dict[str, t.Tensor] = None) -> Dict[str, t.Tensor]:
+        """``out``: optional pre-allocated dense tensors to fill (static batch buffers)."""
         names = list(self.fields) if names is None else [n for n in names if n in self.fields]
         n = int(index.shape[0])
-        out = {k: t.empty((n,) + self.fields[k].shape, dtype=self.fields[k].dtype, device=self.device)
-               for k in names}
+        if out is None:
+            out = {k: t.empty((n,) + self.fields[k].shape, dtype=self.fields[k].dtype, device=self.device)
+                   for k in names}
         if n and names:
             arr = self._field_array(names, out)
             _lib.check(lib.mb_rows_gather(_lib.ptr(self.data), self.pitch, self.max_size, _lib.ptr(index), n,

@@ -122,11 +122,13 @@ class PrioritizedBuffer(Buffer):
         self._params_f64[0:1].add_(self.beta_increment_per_sampling).clamp_(max=1.0)
 
     def _draw(self, batch_size: int, all_weight_sum: float = None, uniform: t.Tensor = None,
-              use_device_params: bool = False):
-        """Fused stratified draw on the device (csrc/sumtree.cu: per_sample_*)."""
+              use_device_params: bool = False, out=None):
+        """Fused stratified draw on the device (csrc/sumtree.cu: per_sample_*).  ``out``: optional
+        pre-allocated (index i64[n], is_weight f64[n]) tensors."""
         if use_device_params:
-            d_index = t.empty(batch_size, dtype=t.int64, device=self.buffer_device)
-            d_isw = t.empty(batch_size, dtype=t.float64, device=self.buffer_device)
+            d_index, d_isw = out if out is not None else (
+                t.empty(batch_size, dtype=t.int64, device=self.buffer_device),
+                t.empty(batch_size, dtype=t.float64, device=self.buffer_device))
             _lib.check(lib.mb_per_sample(self.wt_tree.handle, _lib.ptr(uniform), batch_size, 0, 0.0, 0.0,
                                          _lib.ptr(self._params_raw), _lib.ptr(d_index), _lib.ptr(d_isw),
                                          _lib.stream_ptr()))
@@ -135,8 +137,9 @@ class PrioritizedBuffer(Buffer):
         if uniform is None:
             # same call and same stream as the reference (:411): B doubles from np.random
             uniform = t.from_numpy(np.random.uniform(size=batch_size)).to(self.buffer_device, non_blocking=True)
-        d_index = t.empty(batch_size, dtype=t.int64, device=self.buffer_device)
-        d_isw = t.empty(batch_size, dtype=t.float64, device=self.buffer_device)
+        d_index, d_isw = out if out is not None else (
+            t.empty(batch_size, dtype=t.int64, device=self.buffer_device),
+            t.empty(batch_size, dtype=t.float64, device=self.buffer_device))
         _lib.check(lib.mb_per_sample(self.wt_tree.handle, _lib.ptr(uniform), batch_size, len(self.storage),
                                      float(all_weight_sum or 0.0), float(self.curr_beta), None,
                                      _lib.ptr(d_index), _lib.ptr(d_isw), _lib.stream_ptr()))
