@@ -49,8 +49,10 @@ def parse():
     p.add_argument("--cpu-steps", type=int, default=1500)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per update")
-    p.add_argument("--torch-net", action="store_true",
-                   help="generic path: nn.Sequential Q-net + torch.optim.Adam(fused=True) instead of FusedMLP + FusedAdam")
+    p.add_argument("--net", default="torch", choices=["torch", "fused", "fused-program"],
+                   help="Q-net implementation: nn.Module over cuBLAS (default, fastest measured), FusedMLP autograd "
+                        "(csrc/mlp.cu), or FusedMLP + the persistent fused forward/TD/backward program")
+    p.add_argument("--adam", default="fused", choices=["fused", "torch"], help="FusedAdam (csrc/mlp.cu) or torch.optim.Adam(fused=True)")
     return p.parse_args()
 
 
@@ -186,7 +188,7 @@ def build_learner(a, device, seed, world=1):
             return self.fc3(t.relu(self.fc2(t.relu(self.fc1(state)))))
 
     from machin_b200.model import FusedAdam, FusedMLP
-    if not a.torch_net:
+    if a.net != "torch":
         Q = lambda: FusedMLP([STATE_DIM, HIDDEN, HIDDEN, N_ACTIONS])  # noqa: E731  same layers, fused kernels
     t.manual_seed(seed)
     qnet, qtgt = Q().to(device), Q().to(device)
@@ -198,16 +200,17 @@ def build_learner(a, device, seed, world=1):
         group = ShardGroup("apex", device=device)
         t.manual_seed(0)   # identical initial weights on every learner
         qnet, qtgt = Q().to(device), Q().to(device)
-        learner = DQNApex(qnet, qtgt, t.optim.Adam if a.torch_net else FusedAdam, t.nn.MSELoss(reduction="none"), group,
+        learner = DQNApex(qnet, qtgt, FusedAdam if a.adam == "fused" else t.optim.Adam, t.nn.MSELoss(reduction="none"), group,
                           (PushPullModelServer("qnet", group, 0),), batch_size=a.batch, learning_rate=1e-3,
                           discount=0.99, update_rate=0.005, replay_size=a.replay_rows, learner_group=group)
         buf = learner.replay_buffer
     else:
         buf = PrioritizedBuffer(buffer_size=a.replay_rows, buffer_device=device)
         import functools
-        adam = functools.partial(t.optim.Adam, fused=True) if a.torch_net else FusedAdam
+        adam = FusedAdam if a.adam == "fused" else functools.partial(t.optim.Adam, fused=True)
         learner = DQNPer(qnet, qtgt, adam, t.nn.MSELoss(reduction="none"), batch_size=a.batch,
                          learning_rate=1e-3, discount=0.99, update_rate=0.005, replay_buffer=buf)
+        learner.use_fused_program = a.net == "fused-program"
     gen = t.Generator(device=device).manual_seed(seed)
     chunk = 1_000_000
     done = 0
@@ -420,7 +423,7 @@ def run_b200(a):
         "config": {"workload": workload_name(a), "batch": B, "replay_rows": a.replay_rows, "optimizer": "Adam",
                    "parallelism": f"{world} learner(s), one replay shard each",
                    "launch": "one CUDA graph per update" if graph else "eager",
-                   "net": "nn.Module + torch Adam(fused)" if a.torch_net else "FusedMLP + FusedAdam (csrc/mlp.cu)",
+                   "net": a.net, "adam": a.adam,
                    "exchange": None if world == 1 else "per update: all-gather of shard sums, all-to-all of sampled rows, "
                                "all-to-all of priority write-backs, all-reduce of gradients, broadcast of weights (NCCL)",
                    "l2": "inputs larger than L2: 268 MB tree + 6.9 GB ring, randomly addressed every step"},

@@ -27,6 +27,7 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int TM = 64, TN = 64, TK = 32, NT = 256;
+constexpr int MT = TM / 16;   // register tile per thread (16 x 16 threads): 4 x 4 for 64-wide tiles, 8 x 8 for 128
 
 struct GemmArgs {
     const float *A;
@@ -73,58 +74,91 @@ __device__ __forceinline__ void gemm_item(const GemmArgs &g, GemmSmem &sm, int t
     const int i0 = tile_y * TM, j0 = tile_x * TN;
     const int k_begin = split * g.k_per_split;
     const int k_end = min(g.K, k_begin + g.k_per_split);
-    const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads, 4 x 4 outputs each
-    float acc[4][4];
+    // 16 x 16 threads, 8 x 8 outputs each, as two 4-wide halves 64 apart: with an 8 x 8 register tile the
+    // inner loop needs 4 LDS.128 per 64 FFMA and is FFMA-bound (a 4 x 4 tile is shared-memory-bandwidth bound:
+    // measured 86 cycles per k for 8 warps); the 64-apart halves keep every LDS.128 contiguous across lanes.
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[MT][MT];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < MT; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
-    for (int k0 = k_begin; k0 < k_end; k0 += TK) {
+        for (int b = 0; b < MT; ++b) acc[a][b] = 0.0f;
+    // Global -> register -> shared staging, software-pipelined: all loads of a K-step are issued back to
+    // back (one memory latency per step), and the next step's loads are in flight while this one is multiplied.
+    constexpr int UA = TM * TK / NT, UB = TN * TK / NT;
+    float ra[UA], rb[UB];
+    auto fetch = [&](int k0) {
 #pragma unroll
-        for (int e = tid; e < TM * TK; e += NT) {
+        for (int u = 0; u < UA; ++u) {
+            const int e = tid + u * NT;
             int i, k;
             if (kAKfast) { i = e / TK; k = e % TK; } else { k = e / TM; i = e % TM; }
             const int gi = i0 + i, gk = k0 + k;
-            sm.As[k][i] = (gi < g.M && gk < k_end) ? __ldcg(g.A + (int64_t)gi * g.a_i + (int64_t)gk * g.a_k) : 0.0f;
+            ra[u] = (gi < g.M && gk < k_end) ? __ldcg(g.A + (int64_t)gi * g.a_i + (int64_t)gk * g.a_k) : 0.0f;
         }
 #pragma unroll
-        for (int e = tid; e < TN * TK; e += NT) {
+        for (int u = 0; u < UB; ++u) {
+            const int e = tid + u * NT;
             int j, k;
             if (kBKfast) { j = e / TK; k = e % TK; } else { k = e / TN; j = e % TN; }
             const int gj = j0 + j, gk = k0 + k;
             float v = 0.0f;
             if (gj < g.N && gk < k_end)
                 v = (gj == g.ones_col) ? 1.0f : __ldcg(g.B + (int64_t)gj * g.b_j + (int64_t)gk * g.b_k);
-            sm.Bs[k][j] = v;
+            rb[u] = v;
         }
+    };
+    auto park = [&]() {
+#pragma unroll
+        for (int u = 0; u < UA; ++u) {
+            const int e = tid + u * NT;
+            if (kAKfast) sm.As[e % TK][e / TK] = ra[u]; else sm.As[e / TM][e % TM] = ra[u];
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int e = tid + u * NT;
+            if (kBKfast) sm.Bs[e % TK][e / TK] = rb[u]; else sm.Bs[e / TN][e % TN] = rb[u];
+        }
+    };
+    if (k_begin < k_end) fetch(k_begin);
+    for (int k0 = k_begin; k0 < k_end; k0 += TK) {
+        park();
         __syncthreads();
+        if (k0 + TK < k_end) fetch(k0 + TK);
 #pragma unroll
         for (int k = 0; k < TK; ++k) {
-            const float4 a = *reinterpret_cast<const float4 *>(&sm.As[k][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4 *>(&sm.Bs[k][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+            float av[MT], bv[MT];
 #pragma unroll
-            for (int x = 0; x < 4; ++x)
+            for (int h = 0; h < MT / 4; ++h) {
+                const float4 a = *reinterpret_cast<const float4 *>(&sm.As[k][h * 64 + ty * 4]);
+                const float4 b = *reinterpret_cast<const float4 *>(&sm.Bs[k][h * 64 + tx * 4]);
+                av[4 * h] = a.x; av[4 * h + 1] = a.y; av[4 * h + 2] = a.z; av[4 * h + 3] = a.w;
+                bv[4 * h] = b.x; bv[4 * h + 1] = b.y; bv[4 * h + 2] = b.z; bv[4 * h + 3] = b.w;
+            }
 #pragma unroll
-                for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(av[x], bv[y], acc[x][y]);
+            for (int x = 0; x < MT; ++x)
+#pragma unroll
+                for (int y = 0; y < MT; ++y) acc[x][y] = fmaf(av[x], bv[y], acc[x][y]);
         }
         __syncthreads();
     }
+    auto row_of = [&](int x) { return i0 + (x / 4) * 64 + ty * 4 + (x & 3); };
+    auto col_of = [&](int y) { return j0 + (y / 4) * 64 + tx * 4 + (y & 3); };
     if (splits == 1) {
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
+        for (int x = 0; x < MT; ++x)
 #pragma unroll
-            for (int y = 0; y < 4; ++y) epilogue_store(g, i0 + ty * 4 + x, j0 + tx * 4 + y, acc[x][y]);
+            for (int y = 0; y < MT; ++y) epilogue_store(g, row_of(x), col_of(y), acc[x][y]);
         return;
     }
     // split-K: park the partial tile, the last CTA of this tile sums the partials in split order
     const int64_t MN = (int64_t)g.M * g.N;
     float *mine = g.partial + (int64_t)split * MN;
 #pragma unroll
-    for (int x = 0; x < 4; ++x)
+    for (int x = 0; x < MT; ++x)
 #pragma unroll
-        for (int y = 0; y < 4; ++y) {
-            const int i = i0 + ty * 4 + x, j = j0 + tx * 4 + y;
+        for (int y = 0; y < MT; ++y) {
+            const int i = row_of(x), j = col_of(y);
             if (i < g.M && j < g.N) mine[(int64_t)i * g.N + j] = acc[x][y];
         }
     __threadfence();
@@ -134,17 +168,26 @@ __device__ __forceinline__ void gemm_item(const GemmArgs &g, GemmSmem &sm, int t
     __syncthreads();
     if (!sm.last) return;
     __threadfence();
+    // splits outermost: the MT*MT loads of one split are independent and in flight together (with the
+    // outputs outermost this was splits * MT * MT dependent L2 round trips: ~20 us for a 4-way split)
 #pragma unroll
-    for (int x = 0; x < 4; ++x)
+    for (int x = 0; x < MT; ++x)
 #pragma unroll
-        for (int y = 0; y < 4; ++y) {
-            const int i = i0 + ty * 4 + x, j = j0 + tx * 4 + y;
-            if (i < g.M && j < g.N) {
-                float v = 0.0f;
-                for (int s = 0; s < splits; ++s) v = __fadd_rn(v, __ldcg(g.partial + (int64_t)s * MN + (int64_t)i * g.N + j));
-                epilogue_store(g, i, j, v);
+        for (int y = 0; y < MT; ++y) acc[x][y] = 0.0f;
+    for (int sp = 0; sp < splits; ++sp) {
+        const float *part = g.partial + (int64_t)sp * MN;
+#pragma unroll
+        for (int x = 0; x < MT; ++x)
+#pragma unroll
+            for (int y = 0; y < MT; ++y) {
+                const int i = row_of(x), j = col_of(y);
+                if (i < g.M && j < g.N) acc[x][y] = __fadd_rn(acc[x][y], __ldcg(part + (int64_t)i * g.N + j));
             }
-        }
+    }
+#pragma unroll
+    for (int x = 0; x < MT; ++x)
+#pragma unroll
+        for (int y = 0; y < MT; ++y) epilogue_store(g, row_of(x), col_of(y), acc[x][y]);
     if (tid == 0) g.tile_counter[tile] = 0;
     __syncthreads();
 }
@@ -157,7 +200,7 @@ __global__ void __launch_bounds__(NT) gemm_kernel(GemmArgs g) {
 
 int pick_splits(int tiles, int K) {
     int s = 1;
-    while (tiles * s * 2 <= 2 * mb::kNumSMs && (K / (s * 2)) >= 64 && s < 16) s *= 2;
+    while (tiles * s * 2 <= mb::kNumSMs + mb::kNumSMs / 4 && (K / (s * 2)) >= 2 * TK && s < 32) s *= 2;
     return s;
 }
 
@@ -192,7 +235,7 @@ struct ProgOp {
     int kind, phase, tiles_x, tiles_y, splits, items;
 };
 
-__global__ void __launch_bounds__(NT) mlp_program_kernel(const ProgOp *__restrict__ ops, int n_ops, int n_phases) {
+__global__ void __launch_bounds__(NT, 1) mlp_program_kernel(const ProgOp *__restrict__ ops, int n_ops, int n_phases) {
     cg::grid_group grid = cg::this_grid();
     __shared__ GemmSmem sm;
     __shared__ ProgOp s_op;
@@ -328,8 +371,8 @@ struct Builder {
         op.kind = kind; op.phase = phase;
         op.tiles_x = (g.N + TN - 1) / TN; op.tiles_y = (g.M + TM - 1) / TM;
         const int tiles = op.tiles_x * op.tiles_y;
-        int splits = 1;   // enough K-splits that a phase offers ~2 items per CTA, each with >= 32 of K
-        while (tiles * splits * 2 <= 2 * grid && g.K / (splits * 2) >= TK && splits < 32) splits *= 2;
+        int splits = 1;   // enough K-splits that one op offers up to ~1 item per CTA, each with >= 2 K-steps
+        while (tiles * splits * 2 <= grid + grid / 4 && g.K / (splits * 2) >= 2 * TK && splits < 32) splits *= 2;
         g.k_per_split = ((g.K + splits - 1) / splits + TK - 1) / TK * TK;
         splits = (g.K + g.k_per_split - 1) / g.k_per_split;
         if (splits > 1) {

@@ -69,6 +69,9 @@ class DQNPer(TorchFramework):
         self._fused_mse = isinstance(self.criterion, nn.MSELoss)
         self._graph = None
         self._program = None
+        # opt-in: FusedMLP nets + MSE -> forward x3, TD and backward as ONE persistent cooperative kernel
+        # (csrc/mlp.cu).  Correct (tests) but currently slower than cuBLAS-backed autograd, see DESIGN.md 8.
+        self.use_fused_program = False
         super().__init__()
 
     # ------------------------------------------------------------------ properties / acting (dqn.py:213-331)
@@ -199,6 +202,8 @@ class DQNPer(TorchFramework):
     def _fused_program(self):
         """Build (once) the mb_dqn_mlp_program for this learner, or return None if the nets / buffer do not
         qualify (then the generic autograd path runs)."""
+        if not self.use_fused_program:
+            return None
         if self._program is not None:
             return self._program or None
         from ...model import FusedMLP

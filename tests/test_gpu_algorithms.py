@@ -245,7 +245,8 @@ def test_fused_adam_matches_torch():
         np.testing.assert_allclose(x.detach().cpu().numpy(), y.detach().cpu().numpy(), rtol=2e-6, atol=1e-7)
 
 
-def test_dqn_per_fused_net_vs_reference():
+@pytest.mark.parametrize("use_program", [False, True])
+def test_dqn_per_fused_net_vs_reference(use_program):
     """The reference fixture again, with the Q-nets as FusedMLP (csrc/mlp.cu) and the update in a CUDA graph."""
     from machin_b200.frame.algorithms import DQNPer
     from machin_b200.model import FusedMLP
@@ -259,7 +260,9 @@ def test_dqn_per_fused_net_vs_reference():
                next_state={"state": t.from_numpy(g["dqn_next_state"][i:i + 1])}, reward=float(g["dqn_reward"][i]),
                terminal=bool(g["dqn_terminal"][i])) for i in range(N)]
     dqn.replay_buffer.store_episode(ep, priorities=list(g["dqn_priority"]))
+    dqn.use_fused_program = use_program
     dqn.enable_cuda_graph()
+    assert (dqn._program is not None and dqn._program is not False) == use_program
     np.random.seed(11)
     for step in range(3):
         loss = dqn.update()
