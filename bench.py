@@ -324,9 +324,9 @@ def run_b200(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     learner = build_learner(a, device, seed=rank, world=world)
-    graph = not a.no_graph and world == 1   # N > 1: collectives + host-side shard apportioning -> eager
+    graph = not a.no_graph
     if graph:
-        learner.enable_cuda_graph()
+        learner.enable_cuda_graph()   # N > 1: compute is graph-captured, the NCCL exchanges stay eager
     K, W, B = a.steps, max(a.warmup, 3), a.batch
     depth = learner.replay_buffer.wt_tree.depth
     n_params = sum(p.numel() for p in learner.qnet.parameters())
@@ -422,7 +422,8 @@ def run_b200(a):
         "learner_updates_per_sec": K / (ms_total * 1e-3),
         "config": {"workload": workload_name(a), "batch": B, "replay_rows": a.replay_rows, "optimizer": "Adam",
                    "parallelism": f"{world} learner(s), one replay shard each",
-                   "launch": "one CUDA graph per update" if graph else "eager",
+                   "launch": ("one CUDA graph per update" if world == 1 else "two CUDA graphs per update around eager NCCL exchanges")
+                             if graph else "eager",
                    "net": a.net, "adam": a.adam,
                    "exchange": None if world == 1 else "per update: all-gather of shard sums, all-to-all of sampled rows, "
                                "all-to-all of priority write-backs, all-reduce of gradients, broadcast of weights (NCCL)",

@@ -16,14 +16,23 @@ import numpy as np
 import torch as t
 import torch.nn as nn
 
+from ... import ops
 from ..buffers import DistributedPrioritizedBuffer
 from .dqn_per import DQNPer
+from .utils import soft_update
 
 
-def _flat_grad_all_reduce(params, group):
-    """Average gradients over the learner group: one NCCL all-reduce of one flat buffer."""
+def _flat_grad_all_reduce(params, group, flat=None):
+    """Average gradients over the learner group: one NCCL all-reduce of one flat buffer (``flat``: the
+    buffer the gradients already live in as views -- then there is nothing to pack or unpack)."""
+    if group is None or group.size() == 1:
+        return
+    if flat is not None:
+        group.all_reduce_sum(flat)
+        flat /= group.size()
+        return
     grads = [p.grad for p in params if p.grad is not None]
-    if not grads or group is None or group.size() == 1:
+    if not grads:
         return
     flat = t.cat([g.reshape(-1) for g in grads])
     group.all_reduce_sum(flat)
@@ -83,7 +92,7 @@ class DQNApex(DQNPer):
         return n, group("state"), group("action"), fields["reward"], group("next_state"), fields["terminal"], index, d_isw
 
     def _sync_grads(self):
-        _flat_grad_all_reduce(list(self.qnet.parameters()), self.learner_group)
+        _flat_grad_all_reduce(list(self.qnet.parameters()), self.learner_group, getattr(self, "_flat_grad", None))
 
     def serve_update(self):
         """For members of ``apex_group`` that hold a replay shard but do not learn (the samplers of
@@ -92,6 +101,98 @@ class DQNApex(DQNPer):
         self.replay_buffer.update_priority(None, None)
         if self.qnet_model_server is not None:
             self.qnet_model_server.pull(self.qnet)
+
+    # ---- CUDA graphs around the collectives: [unpack, forward x3, TD, backward] and [optimizer, soft update]
+    # are captured; the row exchange, the gradient all-reduce, the priority write-back and the weight
+    # broadcast stay eager NCCL calls between the replays.  The merged batch has a data-dependent size
+    # n in [B, B + P - 1] (ceil apportioning), so the graphs run on B + P padded rows whose IS weight is 0.
+    def enable_cuda_graph(self, warmup: int = 3):
+        buf = self.replay_buffer
+        dev = buf.buffer_device
+        buf._exchange()                                   # collective: agree on the row layout
+        cap = self.batch_size + self.apex_group.size()
+        params = [p for p in self.qnet.parameters()]
+        self._flat_grad = t.zeros(sum(p.numel() for p in params), dtype=t.float32, device=dev)
+        o = 0
+        for p in params:
+            p.grad = self._flat_grad[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        for group in self.qnet_optim.param_groups:
+            if "capturable" in group:
+                group["capturable"] = True
+        st = {"cap": cap, "rows": t.zeros((cap, buf.storage.pitch), dtype=t.uint8, device=dev),
+              "isw": t.zeros(cap, dtype=t.float64, device=dev)}
+        fields = buf.storage.fields
+        grp = lambda fl, attr: {f.key: fl[f.name] for f in fields.values() if f.attr == attr and f.kind == "major"}
+
+        def compute():
+            fl = buf.storage.unpack(st["rows"])
+            state, action, next_state = grp(fl, "state"), grp(fl, "action"), grp(fl, "next_state")
+            with t.no_grad():
+                nq = self._criticize(next_state)
+                tq = self._criticize(next_state, True)
+            q = self._criticize(state)
+            td = ops.td_dqn(q.detach(), nq, tq, self.action_get_function(action), fl["reward"], fl["terminal"],
+                            self.discount, is_weight=st["isw"], mode=self.mode, want_grad=True)
+            self._flat_grad.zero_()
+            q.backward(td["grad_q"])
+            return td["abs_error"], td["loss_elem"].mean()
+
+        def apply():
+            if np.isfinite(self.grad_max):
+                nn.utils.clip_grad_norm_(self.qnet.parameters(), self.grad_max)
+            self.qnet_optim.step()
+            if self.update_rate is not None:
+                soft_update(self.qnet_target, self.qnet, self.update_rate)
+
+        if not self._fused_mse or self.update_rate is None:
+            raise RuntimeError("DQNApex.enable_cuda_graph needs an MSELoss criterion and soft target updates")
+        saved = [[x.detach().clone() for x in list(m.parameters()) + list(m.buffers())] for m in (self.qnet, self.qnet_target)]
+        fresh = len(self.qnet_optim.state) == 0
+        self.qnet.train()
+        cur, side = t.cuda.current_stream(dev), t.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with t.cuda.stream(side):
+            for _ in range(warmup):
+                compute()
+                apply()
+        cur.wait_stream(side)
+        t.cuda.synchronize(dev)
+        g1, g2 = t.cuda.CUDAGraph(), t.cuda.CUDAGraph()
+        with t.cuda.graph(g1):
+            st["abs"], st["loss"] = compute()
+        with t.cuda.graph(g2):
+            apply()
+        with t.no_grad():
+            for m, sv in zip((self.qnet, self.qnet_target), saved):
+                for x, v in zip(list(m.parameters()) + list(m.buffers()), sv):
+                    x.copy_(v)
+            if fresh:
+                for pst in self.qnet_optim.state.values():
+                    for v in pst.values():
+                        if t.is_tensor(v):
+                            v.zero_()
+        st["g1"], st["g2"] = g1, g2
+        self._apex_graph = st
+        t.cuda.synchronize(dev)
+
+    def update_device(self, update_value=True, update_target=True, uniform=None):
+        st = getattr(self, "_apex_graph", None)
+        if st is None or not (update_value and update_target):
+            return super().update_device(update_value, update_target, uniform)
+        buf = self.replay_buffer
+        rows, index, isw, _ = buf._exchange().sample(self.batch_size)
+        n = int(rows.shape[0])
+        if n > st["cap"]:
+            raise RuntimeError("merged batch larger than the captured capacity")
+        st["rows"][:n].copy_(rows)
+        st["isw"].zero_()
+        st["isw"][:n].copy_(isw * (st["cap"] / n))   # graphs average over cap rows; padded rows weigh 0
+        st["g1"].replay()
+        self._sync_grads()
+        st["g2"].replay()
+        buf.update_priority(st["abs"][:n], index)
+        return st["loss"]
 
     def update(self, update_value=True, update_target=True, concatenate_samples=True, **__):
         result = super().update(update_value, update_target, concatenate_samples)

@@ -54,6 +54,7 @@ class ShardedSampler:
         process is a learner that also holds a shard, BASELINE config C4)."""
         self.group, self.shard, self.row_width = group, shard, int(row_width)
         self.requesters = list(range(group.size())) if requesters is None else list(requesters)
+        self._last_served = 0
 
     # ------------------------------------------------------------------ sample
     def sample(self, batch_size: int):
@@ -78,6 +79,7 @@ class ShardedSampler:
         width = self.row_width + META
         send = t.cat(parts, dim=0) if parts else t.empty((0, width), dtype=t.uint8, device=dev)
         recv_counts = [ssize[m] if me in self.requesters else 0 for m in range(P)]
+        self._last_served = ssize[me]
         recv = g.all_to_all_bytes(send, send_counts, recv_counts)
         if me not in self.requesters or recv.shape[0] == 0:
             return None, None, None, None
@@ -115,10 +117,10 @@ class ShardedSampler:
                     send_counts[m] = n
                     o += n
         send = t.cat(parts, dim=0) if parts else t.empty((0, META), dtype=t.uint8, device=dev)
-        # how many entries each requester sends me = how many rows I served it
-        counts = t.tensor(send_counts, dtype=t.float64, device=dev)
-        matrix = g.all_gather_f64(counts)                      # [P, P]: matrix[r][m] = r -> m
-        recv_counts = [int(matrix[r][me].item()) for r in range(P)]
+        # how many entries each requester sends me = how many rows I served it in the matching sample()
+        # (every member computed the same apportioning, so no extra collective / host sync is needed)
+        served = self._last_served
+        recv_counts = [served if r in self.requesters else 0 for r in range(P)]
         recv = g.all_to_all_bytes(send, send_counts, recv_counts)
         if recv.shape[0]:
             _, idx, ver, p64 = _split_meta(recv)

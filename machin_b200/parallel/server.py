@@ -45,9 +45,8 @@ class PushPullModelServer:
         tensors = _state_tensors(model)
         offs, total = self._layout(tensors)
         flat = self._buffer(total)
-        for x, o in zip(tensors, offs):
-            n = x.numel() * x.element_size()
-            flat[o:o + n].view(x.dtype).copy_(x.detach().reshape(-1))
+        views = [flat[o:o + x.numel() * x.element_size()].view(x.dtype).view(x.shape) for x, o in zip(tensors, offs)]
+        t._foreach_copy_(views, [x.detach() for x in tensors])     # one multi-tensor launch
         model.pp_version += 1
         flat[0:8].view(t.int64).fill_(model.pp_version)
         self.group.broadcast(flat, self.src_index)
@@ -63,9 +62,8 @@ class PushPullModelServer:
         if hasattr(model, "pp_version") and version <= model.pp_version:
             return False
         with t.no_grad():
-            for x, o in zip(tensors, offs):
-                n = x.numel() * x.element_size()
-                x.copy_(flat[o:o + n].view(x.dtype).view(x.shape))
+            views = [flat[o:o + x.numel() * x.element_size()].view(x.dtype).view(x.shape) for x, o in zip(tensors, offs)]
+            t._foreach_copy_(tensors, views)
         model.pp_version = version
         return True
 
