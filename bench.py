@@ -322,6 +322,8 @@ def run_b200(a):
     t.cuda.set_device(local)
     device = t.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=device)
     learner = build_learner(a, device, seed=rank, world=world)
     graph = not a.no_graph
