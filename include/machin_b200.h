@@ -163,6 +163,16 @@ int mb_rows_scatter(void *d_ring, int64_t pitch, int64_t capacity, int64_t first
 int mb_rows_gather_packed(const void *d_ring, int64_t pitch, int64_t capacity,
                           const int64_t *d_index, int64_t n, void *d_out, void *stream);
 
+/* Shard-exchange wire rows: [payload | index i64 | version i64 | value f64], `width` bytes apart, the three
+ * metadata columns starting at `meta_offset`.  pack: version comes from d_version or is looked up as
+ * d_version_table[index] (_sample_service, prioritized_buffer_d.py:300); value is the IS weight (f64) or a
+ * priority (f32, widened exactly).  unpack: the inverse on the receiving member. */
+int mb_rows_pack_meta(void *d_wire, int64_t width, int64_t meta_offset, int64_t n, const int64_t *d_index,
+                      const int64_t *d_version, const int64_t *d_version_table, const double *d_value_f64,
+                      const float *d_value_f32, void *stream);
+int mb_rows_unpack_meta(const void *d_wire, int64_t width, int64_t meta_offset, int64_t n, int64_t *d_index,
+                        int64_t *d_version, double *d_value_f64, float *d_value_f32, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * TD target / priority math
  * ------------------------------------------------------------------------------------------ */

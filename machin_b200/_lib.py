@@ -73,6 +73,8 @@ SIGNATURES = {
     "mb_rows_gather": (i32, [vp, i64, i64, vp, i64, C.POINTER(MbField), i32, vp]),
     "mb_rows_scatter": (i32, [vp, i64, i64, i64, i64, C.POINTER(MbField), i32, vp]),
     "mb_rows_gather_packed": (i32, [vp, i64, i64, vp, i64, vp, vp]),
+    "mb_rows_pack_meta": (i32, [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp]),
+    "mb_rows_unpack_meta": (i32, [vp, i64, i64, i64, vp, vp, vp, vp, vp]),
     "mb_td_dqn": (i32, [vp, vp, vp, i64, i32, vp, vp, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]),
     "mb_td_target": (i32, [vp, vp, vp, i64, f32, vp, vp, vp, vp]),
     "mb_soft_update": (i32, [vp, vp, i64, f64, vp]),

@@ -59,6 +59,38 @@ __global__ void __launch_bounds__(256) rows_move_kernel(char *ring, int64_t pitc
     }
 }
 
+// Shard-exchange metadata: every wire row carries [index i64 | version i64 | value f64] behind its payload
+// (prioritized_buffer_d.py:293-303 returns index, version and is_weight next to the batch; :184-202 sends
+// index, version and priority back).  One launch packs / unpacks all three columns.
+__global__ void __launch_bounds__(256) rows_pack_meta_kernel(char *__restrict__ wire, int64_t width, int64_t meta_off,
+                                                             int64_t n, const int64_t *__restrict__ index,
+                                                             const int64_t *__restrict__ version,
+                                                             const int64_t *__restrict__ version_table,
+                                                             const double *__restrict__ v64,
+                                                             const float *__restrict__ v32) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    char *m = wire + i * width + meta_off;
+    const int64_t k = index[i];
+    reinterpret_cast<int64_t *>(m)[0] = k;
+    reinterpret_cast<int64_t *>(m)[1] = version ? version[i] : version_table[k];
+    reinterpret_cast<double *>(m)[2] = v64 ? v64[i] : (double)v32[i];
+}
+
+__global__ void __launch_bounds__(256) rows_unpack_meta_kernel(const char *__restrict__ wire, int64_t width,
+                                                               int64_t meta_off, int64_t n, int64_t *__restrict__ index,
+                                                               int64_t *__restrict__ version, double *__restrict__ v64,
+                                                               float *__restrict__ v32) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const char *m = wire + i * width + meta_off;
+    index[i] = reinterpret_cast<const int64_t *>(m)[0];
+    version[i] = reinterpret_cast<const int64_t *>(m)[1];
+    const double v = reinterpret_cast<const double *>(m)[2];
+    if (v64) v64[i] = v;
+    if (v32) v32[i] = (float)v;
+}
+
 int launch_rows(bool gather, void *ring, int64_t pitch, int64_t capacity, const int64_t *index,
                 int64_t first_slot, int64_t n, const mb_field *fields, int n_fields, cudaStream_t s) {
     if (!ring || pitch <= 0 || capacity <= 0 || n < 0 || n_fields < 0 || n_fields > MB_MAX_FIELDS ||
@@ -102,6 +134,30 @@ int mb_rows_gather_packed(const void *d_ring, int64_t pitch, int64_t capacity, c
                           void *d_out, void *stream) {
     mb_field f{0, pitch, d_out, pitch};
     return mb_rows_gather(d_ring, pitch, capacity, d_index, n, &f, 1, stream);
+}
+
+int mb_rows_pack_meta(void *d_wire, int64_t width, int64_t meta_offset, int64_t n, const int64_t *d_index,
+                      const int64_t *d_version, const int64_t *d_version_table, const double *d_value_f64,
+                      const float *d_value_f32, void *stream) {
+    if (!d_wire || n < 0 || !d_index || (!d_version && !d_version_table) || (!d_value_f64 && !d_value_f32) ||
+        meta_offset % 8 || width % 8 || meta_offset + 24 > width)
+        return MB_ERR_INVALID;
+    if (n == 0) return MB_OK;
+    rows_pack_meta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (char *)d_wire, width, meta_offset, n, d_index, d_version, d_version_table, d_value_f64, d_value_f32);
+    MB_LAUNCHED(1);
+    return MB_OK;
+}
+
+int mb_rows_unpack_meta(const void *d_wire, int64_t width, int64_t meta_offset, int64_t n, int64_t *d_index,
+                        int64_t *d_version, double *d_value_f64, float *d_value_f32, void *stream) {
+    if (!d_wire || n < 0 || !d_index || !d_version || meta_offset % 8 || width % 8 || meta_offset + 24 > width)
+        return MB_ERR_INVALID;
+    if (n == 0) return MB_OK;
+    rows_unpack_meta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const char *)d_wire, width, meta_offset, n, d_index, d_version, d_value_f64, d_value_f32);
+    MB_LAUNCHED(1);
+    return MB_OK;
 }
 
 }  // extern "C"

@@ -120,7 +120,7 @@ class DQNApex(DQNPer):
         for group in self.qnet_optim.param_groups:
             if "capturable" in group:
                 group["capturable"] = True
-        st = {"cap": cap, "rows": t.zeros((cap, buf.storage.pitch), dtype=t.uint8, device=dev),
+        st = {"cap": cap, "rows": t.zeros((cap, buf.storage.pitch + 24), dtype=t.uint8, device=dev),   # wire rows
               "isw": t.zeros(cap, dtype=t.float64, device=dev)}
         fields = buf.storage.fields
         grp = lambda fl, attr: {f.key: fl[f.name] for f in fields.values() if f.attr == attr and f.kind == "major"}

@@ -115,16 +115,25 @@ class DeviceRing:
         return out
 
     def unpack(self, rows: t.Tensor, names=None, stream=None) -> Dict[str, t.Tensor]:
-        """Split ``n`` packed rows (u8[n, pitch], e.g. received from a peer shard) into dense fields."""
+        """Split ``n`` packed rows (u8[n, >= pitch], e.g. wire rows received from a peer shard, which carry
+        metadata behind the payload) into dense fields."""
         names = list(self.fields) if names is None else [n for n in names if n in self.fields]
         n = int(rows.shape[0])
-        assert rows.is_contiguous() and rows.shape[1] == self.pitch
+        assert rows.is_contiguous() and rows.shape[1] >= self.pitch
         out = {k: t.empty((n,) + self.fields[k].shape, dtype=self.fields[k].dtype, device=rows.device) for k in names}
         if n and names:
             arr = self._field_array(names, out)
-            _lib.check(lib.mb_rows_gather(_lib.ptr(rows), self.pitch, n, None, n, arr, len(names),
+            _lib.check(lib.mb_rows_gather(_lib.ptr(rows), int(rows.shape[1]), n, None, n, arr, len(names),
                                           _lib.stream_ptr(stream)))
         return out
+
+    def gather_into_wire(self, index: t.Tensor, wire: t.Tensor, stream=None):
+        """wire[i, :pitch] = ring[index[i]] for a wide (pitch + metadata) contiguous wire buffer."""
+        n = int(index.shape[0])
+        if n:
+            arr = (MbField * 1)(MbField(0, self.pitch, wire.data_ptr(), int(wire.shape[1])))
+            _lib.check(lib.mb_rows_gather(_lib.ptr(self.data), self.pitch, self.max_size, _lib.ptr(index), n, arr, 1,
+                                          _lib.stream_ptr(stream)))
 
     def gather_packed(self, index: t.Tensor, out: Optional[t.Tensor] = None, stream=None) -> t.Tensor:
         n = int(index.shape[0])

@@ -17,6 +17,8 @@ from typing import Dict, List, Union
 import numpy as np
 import torch as t
 
+from ... import _lib
+from ..._lib import lib
 from ...parallel.exchange import ShardedSampler
 from ..transition import TransitionBase
 from .buffer import Buffer
@@ -53,6 +55,42 @@ class DistributedPrioritizedBuffer(PrioritizedBuffer):
             d_index, d_isw = self._draw(n, all_weight_sum)
             version = self.buffer_version_table[d_index]
             return self.storage.gather_packed(d_index), d_index, version, d_isw
+
+    # wire protocol (parallel/exchange.py::_sample_wire): payload + metadata written in place
+    def serve_into(self, n: int, all_weight_sum: float, wire: t.Tensor):
+        with self.wr_lock:
+            if n <= 0:
+                return
+            d_index, d_isw = self._draw(n, all_weight_sum)
+            self.storage.gather_into_wire(d_index, wire)
+            _lib.check(lib.mb_rows_pack_meta(_lib.ptr(wire), int(wire.shape[1]), self.storage.pitch, n, _lib.ptr(d_index),
+                                             None, _lib.ptr(self.buffer_version_table), _lib.ptr(d_isw), None,
+                                             _lib.stream_ptr()))
+
+    def unpack_meta(self, recv: t.Tensor, row_width: int):
+        n, dev = int(recv.shape[0]), recv.device
+        index = t.empty(n, dtype=t.int64, device=dev)
+        version = t.empty(n, dtype=t.int64, device=dev)
+        isw = t.empty(n, dtype=t.float64, device=dev)
+        _lib.check(lib.mb_rows_unpack_meta(_lib.ptr(recv), int(recv.shape[1]), row_width, n, _lib.ptr(index),
+                                           _lib.ptr(version), _lib.ptr(isw), None, _lib.stream_ptr()))
+        return index, version, isw
+
+    def pack_update(self, index: t.Tensor, version: t.Tensor, priority_f32: t.Tensor) -> t.Tensor:
+        n = int(index.shape[0])
+        send = t.empty((n, 24), dtype=t.uint8, device=index.device)
+        _lib.check(lib.mb_rows_pack_meta(_lib.ptr(send), 24, 0, n, _lib.ptr(index.contiguous()), _lib.ptr(version.contiguous()),
+                                         None, None, _lib.ptr(priority_f32), _lib.stream_ptr()))
+        return send
+
+    def apply_wire(self, recv: t.Tensor):
+        n, dev = int(recv.shape[0]), recv.device
+        index = t.empty(n, dtype=t.int64, device=dev)
+        version = t.empty(n, dtype=t.int64, device=dev)
+        pri = t.empty(n, dtype=t.float32, device=dev)
+        _lib.check(lib.mb_rows_unpack_meta(_lib.ptr(recv), 24, 0, n, _lib.ptr(index), _lib.ptr(version), None,
+                                           _lib.ptr(pri), _lib.stream_ptr()))
+        self.apply(index, version, pri)
 
     def apply(self, index: t.Tensor, version: t.Tensor, priority: t.Tensor):
         with self.wr_lock:                                           # _update_priority_service (:282-291)
@@ -150,7 +188,7 @@ class DistributedPrioritizedBuffer(PrioritizedBuffer):
         rows, index, isw, _ = self._exchange().sample(batch_size)
         if rows is None:
             return 0, None, None, None
-        return int(rows.shape[0]), self.storage.unpack(rows.contiguous(), names=names), index, isw
+        return int(rows.shape[0]), self.storage.unpack(rows, names=names), index, isw
 
     def sample_batch(self, batch_size: int, concatenate: bool = True, device: Union[str, t.device] = None,
                      sample_attrs: List[str] = None, additional_concat_custom_attrs: List[str] = None, *_, **__):
@@ -160,7 +198,7 @@ class DistributedPrioritizedBuffer(PrioritizedBuffer):
         if rows is None:
             return 0, None, None, None
         result = self.post_process_batch(None, device, concatenate, sample_attrs, additional_concat_custom_attrs,
-                                         packed_rows=rows.contiguous())
+                                         packed_rows=rows)
         host_index = OrderedDict((m, (i.cpu().numpy(), v.cpu().numpy().astype(np.uint64))) for m, (i, v) in index.items())
         return int(rows.shape[0]), result, host_index, isw.cpu().numpy()
 

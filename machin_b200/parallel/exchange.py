@@ -58,8 +58,11 @@ class ShardedSampler:
 
     # ------------------------------------------------------------------ sample
     def sample(self, batch_size: int):
-        """Collective.  Returns (rows u8[n, row_width], index OrderedDict{member: (index, version)},
-        is_weight f64[n], counts per shard) on requesters; (None, None, None, None) elsewhere."""
+        """Collective.  Returns (rows u8[n, row_width (+ META on the CUDA path)], index
+        OrderedDict{member: (index, version)}, is_weight f64[n], counts per shard) on requesters;
+        (None, None, None, None) elsewhere."""
+        if hasattr(self.shard, "serve_into"):
+            return self._sample_wire(batch_size)
         g = self.group
         dev = g.device
         me = g.index
@@ -91,10 +94,68 @@ class ShardedSampler:
                 o += recv_counts[m]
         return rows, all_index, isw, recv_counts
 
+    # CUDA shards: payload and metadata are written straight into one wire buffer by two kernels per
+    # requester (gather with a wide output pitch + pack_meta); nothing is concatenated or re-copied.
+    def _sample_wire(self, batch_size: int):
+        g, dev = self.group, self.group.device
+        me, P = g.index, g.size()
+        local_sum = t.tensor([float(self.shard.weight_sum())], dtype=t.float64, device=dev)
+        sums = g.all_gather_f64(local_sum).view(-1).tolist()
+        ssize, total = shard_sample_sizes(sums, batch_size)
+        if batch_size <= 0:
+            ssize = [0] * P
+        W = self.row_width + META
+        n_mine = ssize[me]
+        wire = t.empty((n_mine * len(self.requesters), W), dtype=t.uint8, device=dev)
+        send_counts, o = [0] * P, 0
+        for r in self.requesters:                      # one independent draw per requester, member order
+            self.shard.serve_into(n_mine, total, wire[o:o + n_mine])
+            send_counts[r] = n_mine
+            o += n_mine
+        recv_counts = [ssize[m] if me in self.requesters else 0 for m in range(P)]
+        self._last_served = n_mine
+        recv = g.all_to_all_bytes(wire, send_counts, recv_counts)
+        if me not in self.requesters or recv.shape[0] == 0:
+            self._last = None
+            return None, None, None, None
+        index, version, isw = self.shard.unpack_meta(recv, self.row_width)
+        all_index, o = OrderedDict(), 0
+        for m, name in enumerate(g.get_group_members()):
+            if recv_counts[m]:
+                all_index[name] = (index[o:o + recv_counts[m]], version[o:o + recv_counts[m]])
+                o += recv_counts[m]
+        self._last = (all_index, index, version, recv_counts)
+        return recv, all_index, isw, recv_counts
+
+    def _update_wire(self, priorities, indexes):
+        g, dev = self.group, self.group.device
+        P, me = g.size(), g.index
+        send_counts = [0] * P
+        if indexes is not None:
+            last = getattr(self, "_last", None)
+            if last is not None and last[0] is indexes:          # the dict handed out by sample(): no re-packing
+                index, version, send_counts = last[1], last[2], list(last[3])
+            else:
+                names = g.get_group_members()
+                index = t.cat([indexes[nm][0].to(dev).to(t.int64) for nm in names if nm in indexes])
+                version = t.cat([t.as_tensor(indexes[nm][1]).to(dev).to(t.int64) for nm in names if nm in indexes])
+                send_counts = [len(indexes[nm][0]) if nm in indexes else 0 for nm in names]
+            pri = (priorities if t.is_tensor(priorities) else t.as_tensor(np.asarray(priorities))).to(dev).reshape(-1)
+            send = self.shard.pack_update(index, version, pri.to(t.float32).contiguous())
+        else:
+            send = t.empty((0, META), dtype=t.uint8, device=dev)
+        served = self._last_served
+        recv_counts = [served if r in self.requesters else 0 for r in range(P)]
+        recv = g.all_to_all_bytes(send, send_counts, recv_counts)
+        if recv.shape[0]:
+            self.shard.apply_wire(recv)
+
     # ------------------------------------------------------------------ priority write-back
     def update_priority(self, priorities, indexes: "OrderedDict"):
         """Collective.  ``priorities``: tensor/array [n] in merged order; ``indexes``: the OrderedDict
         returned by :meth:`sample` (None on non-requesters)."""
+        if hasattr(self.shard, "serve_into"):
+            return self._update_wire(priorities, indexes)
         g = self.group
         dev = g.device
         P = g.size()
