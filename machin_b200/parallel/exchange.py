@@ -137,8 +137,9 @@ class ShardedSampler:
                 index, version, send_counts = last[1], last[2], list(last[3])
             else:
                 names = g.get_group_members()
-                index = t.cat([indexes[nm][0].to(dev).to(t.int64) for nm in names if nm in indexes])
-                version = t.cat([t.as_tensor(indexes[nm][1]).to(dev).to(t.int64) for nm in names if nm in indexes])
+                as_i64 = lambda x: (x if t.is_tensor(x) else t.as_tensor(np.asarray(x).astype(np.int64))).to(dev).to(t.int64)
+                index = t.cat([as_i64(indexes[nm][0]) for nm in names if nm in indexes])
+                version = t.cat([as_i64(indexes[nm][1]) for nm in names if nm in indexes])
                 send_counts = [len(indexes[nm][0]) if nm in indexes else 0 for nm in names]
             pri = (priorities if t.is_tensor(priorities) else t.as_tensor(np.asarray(priorities))).to(dev).reshape(-1)
             send = self.shard.pack_update(index, version, pri.to(t.float32).contiguous())
