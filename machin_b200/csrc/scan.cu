@@ -120,42 +120,97 @@ __global__ void __launch_bounds__(kEpisodesPerCta) vtrace_kernel(
     }
 }
 
-// a2c.py:275-313 in float64 (the reference uses Python floats).  One thread per episode.
-__global__ void __launch_bounds__(128) gae_kernel(const int64_t *__restrict__ offsets, int64_t n_ep,
-                                                  int64_t n_steps, const double *__restrict__ reward,
-                                                  const uint8_t *__restrict__ terminal,
-                                                  const float *__restrict__ cv, const float *__restrict__ ncv,
-                                                  double g, double lam, double *__restrict__ ret_out,
-                                                  double *__restrict__ gae_out) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_ep) return;
+// a2c.py:275-313 in float64 (the reference uses Python floats).  Same three-phase structure as V-trace:
+// a CTA owns 64 consecutive episodes (one contiguous slice), streams it into shared memory with coalesced
+// loads, runs the dependent recurrence one thread per episode out of shared memory, streams the results out.
+constexpr int kGaeEpisodes = 64;
+constexpr int kGaeTile = 1664;  // steps staged per CTA: (8 + 8 + 4 + 4 + 1) B per step -> ~42 KB
+
+struct GaeStep {
+    double ret, adv;
+};
+
+__device__ __forceinline__ GaeStep gae_step(double r, double v, double nv, bool term, bool last, double g, double lam,
+                                            double &ret, double &last_v, double &last_a) {
+    ret = last ? r : __dadd_rn(__dmul_rn(ret, g), r);                            // value[i-1] = value[i]*g + r
+    const double live = 1.0 - (term ? 1.0 : 0.0);
+    double a;
+    if (lam == 1.0) {
+        a = __dsub_rn(ret, v);                                                     // (:284-286)
+    } else if (lam == 0.0) {
+        a = __dsub_rn(__dadd_rn(r, __dmul_rn(__dmul_rn(g, live), nv)), v);         // (:287-295)
+    } else {
+        // delta = r + g * last_v * (1 - term) - v ; A = last_a * g * (1 - term) * lam + delta (:296-313)
+        const double delta = __dsub_rn(__dadd_rn(r, __dmul_rn(__dmul_rn(g, last_v), live)), v);
+        a = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(last_a, g), live), lam), delta);
+        last_v = v;
+        last_a = a;
+    }
+    return {ret, a};
+}
+
+__global__ void __launch_bounds__(kGaeEpisodes) gae_kernel(const int64_t *__restrict__ offsets, int64_t n_ep,
+                                                           int64_t n_steps, const double *__restrict__ reward,
+                                                           const uint8_t *__restrict__ terminal,
+                                                           const float *__restrict__ cv, const float *__restrict__ ncv,
+                                                           double g, double lam, double *__restrict__ ret_out,
+                                                           double *__restrict__ gae_out) {
+    __shared__ double sR[kGaeTile + kGaeTile / 32 + 1];   // reward, then return
+    __shared__ double sA[kGaeTile + kGaeTile / 32 + 1];   // advantage
+    __shared__ float sV[kGaeTile + kGaeTile / 32 + 1];
+    __shared__ float sN[kGaeTile + kGaeTile / 32 + 1];
+    __shared__ uint8_t sT[kGaeTile + kGaeTile / 32 + 1];
+    const int tid = threadIdx.x;
+    const int64_t e0 = (int64_t)blockIdx.x * kGaeEpisodes;
+    const int64_t e1 = min(e0 + kGaeEpisodes, n_ep);
     const int64_t fixed_len = offsets ? 0 : n_steps / n_ep;
-    const int64_t b = offsets ? offsets[e] : e * fixed_len;
-    const int64_t len = (offsets ? offsets[e + 1] : b + fixed_len) - b;
-    if (len <= 0) return;
-    double ret = 0.0, last_v = 0.0, last_a = 0.0;
-    for (int64_t k = len - 1; k >= 0; --k) {
-        const int64_t s = b + k;
-        const double r = reward[s];
-        ret = (k == len - 1) ? r : __dadd_rn(__dmul_rn(ret, g), r);           // value[i-1] = value[i]*g + r
-        if (ret_out) ret_out[s] = ret;
-        if (!gae_out) continue;
-        const double v = (double)cv[s];
-        const double live = 1.0 - (terminal[s] ? 1.0 : 0.0);
-        double a;
-        if (lam == 1.0) {
-            a = __dsub_rn(ret, v);                                              // (:284-286)
-        } else if (lam == 0.0) {
-            // r + g * (1 - term) * V(s') - V(s)                                 (:287-295)
-            a = __dsub_rn(__dadd_rn(r, __dmul_rn(__dmul_rn(g, live), (double)ncv[s])), v);
-        } else {
-            // delta = r + g * last_v * (1 - term) - v ; A = last_a * g * (1 - term) * lam + delta (:296-313)
-            const double delta = __dsub_rn(__dadd_rn(r, __dmul_rn(__dmul_rn(g, last_v), live)), v);
-            a = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(last_a, g), live), lam), delta);
-            last_v = v;
-            last_a = a;
+    const int64_t s0 = offsets ? offsets[e0] : e0 * fixed_len;
+    const int64_t s1 = offsets ? offsets[e1] : e1 * fixed_len;
+    const int64_t e = e0 + tid;
+    int64_t b = 0, len = 0;
+    if (e < e1) {
+        b = offsets ? offsets[e] : e * fixed_len;
+        len = (offsets ? offsets[e + 1] : b + fixed_len) - b;
+    }
+    const bool need_next = gae_out && lam == 0.0;
+    if (s1 - s0 <= kGaeTile) {
+        const int m = (int)(s1 - s0);
+        for (int j = tid; j < m; j += kGaeEpisodes) {
+            const int64_t s = s0 + j;
+            sR[sw(j)] = reward[s];
+            if (gae_out) {
+                sV[sw(j)] = cv[s];
+                sT[sw(j)] = terminal[s];
+                if (need_next) sN[sw(j)] = ncv[s];
+            }
         }
-        gae_out[s] = a;
+        __syncthreads();
+        if (len > 0) {
+            const int lb = (int)(b - s0);
+            double ret = 0.0, last_v = 0.0, last_a = 0.0;
+            for (int k = (int)len - 1; k >= 0; --k) {
+                const int j = sw(lb + k);
+                const GaeStep o = gae_step(sR[j], gae_out ? (double)sV[j] : 0.0, need_next ? (double)sN[j] : 0.0,
+                                           gae_out ? sT[j] != 0 : false, k == (int)len - 1, g, lam, ret, last_v, last_a);
+                sR[j] = o.ret;
+                sA[j] = o.adv;
+            }
+        }
+        __syncthreads();
+        for (int j = tid; j < m; j += kGaeEpisodes) {
+            const int64_t s = s0 + j;
+            if (ret_out) ret_out[s] = sR[sw(j)];
+            if (gae_out) gae_out[s] = sA[sw(j)];
+        }
+    } else if (len > 0) {
+        double ret = 0.0, last_v = 0.0, last_a = 0.0;
+        for (int64_t k = len - 1; k >= 0; --k) {
+            const int64_t s = b + k;
+            const GaeStep o = gae_step(reward[s], gae_out ? (double)cv[s] : 0.0, need_next ? (double)ncv[s] : 0.0,
+                                       gae_out ? terminal[s] != 0 : false, k == len - 1, g, lam, ret, last_v, last_a);
+            if (ret_out) ret_out[s] = o.ret;
+            if (gae_out) gae_out[s] = o.adv;
+        }
     }
 }
 
@@ -188,7 +243,7 @@ int mb_gae(const int64_t *d_offsets, int64_t n_episodes, int64_t n_steps, const 
     if (d_gae && (!d_terminal || !d_critic_value)) return MB_ERR_INVALID;
     if (d_gae && gae_lambda == 0.0 && !d_next_critic_value) return MB_ERR_INVALID;
     if (!d_offsets && n_steps % n_episodes != 0) return MB_ERR_INVALID;
-    gae_kernel<<<(unsigned)((n_episodes + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+    gae_kernel<<<(unsigned)((n_episodes + kGaeEpisodes - 1) / kGaeEpisodes), kGaeEpisodes, 0, (cudaStream_t)stream>>>(
         d_offsets, n_episodes, n_steps, d_reward, d_terminal, d_critic_value, d_next_critic_value, discount,
         gae_lambda, d_returns, d_gae);
     MB_LAUNCHED(1);

@@ -286,10 +286,9 @@ __device__ __forceinline__ void phase_sync() {
 //      duplicates that np.unique removes in the reference are simply recomputed)
 //   e  clear the stamps
 template <typename WT, bool kCoop>
-__global__ void __launch_bounds__(1024) tree_update_kernel(TreeDev t, const int64_t *__restrict__ idx,
-                                                           const WT *__restrict__ w,
-                                                           const uint8_t *__restrict__ valid, int64_t n,
-                                                           Normalize nz, int gen) {
+__device__ __forceinline__ void tree_update_body(const TreeDev &t, const int64_t *__restrict__ idx,
+                                                 const WT *__restrict__ w, const uint8_t *__restrict__ valid,
+                                                 int64_t n, const Normalize &nz, int gen) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = tid; i < n; i += stride) {
@@ -342,6 +341,139 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(TreeDev t, const int6
             t.st->max_is_f32 = sizeof(WT) == 4 ? 1 : 0;
         }
         t.st->batch_max = -INFINITY;
+    }
+}
+
+template <typename WT, bool kCoop>
+__global__ void __launch_bounds__(1024) tree_update_kernel(TreeDev t, const int64_t *__restrict__ idx,
+                                                           const WT *__restrict__ w,
+                                                           const uint8_t *__restrict__ valid, int64_t n,
+                                                           Normalize nz, int gen) {
+    tree_update_body<WT, kCoop>(t, idx, w, valid, n, nz, gen);
+}
+
+// ---- small SORTED batches (n <= 512): the learner's priority write-back -------------------------------
+// Indexes that come out of the stratified PER draw are ascending.  For a sorted batch the set of touched
+// nodes on every level, who merges with whom and on which level, is known up front from neighbouring keys:
+// entry i (after dropping all but the last of equal keys) represents its ancestor up to level
+// hb(i) = highest bit in which its key differs from its predecessor's; an entry whose hb equals the
+// current level hands its node value to the entry on its left and retires.  So the walk needs no hash
+// table and no atomics: per level one barrier, one shared-memory read, one add.  The stored sibling of
+// every node a thread will represent is prefetched up front (all loads in flight at once), results are
+// parked in shared memory and written out after the walk (a barrier after a global store waits for L2).
+// Parents are fl(left + right) of the current children: bit-identical to the level-synchronous kernel.
+// Unsorted input (or a validity mask) takes the generic body in the same launch.
+constexpr int kSortedN = 512;
+constexpr int kSortedLevels = 31;
+
+template <typename WT>
+__global__ void __launch_bounds__(kSortedN) tree_update_sorted(TreeDev t, const int64_t *__restrict__ idx,
+                                                               const WT *__restrict__ w,
+                                                               const uint8_t *__restrict__ valid, int n,
+                                                               Normalize nz, int gen) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    double *park = reinterpret_cast<double *>(dyn);   // [levels][kSortedN]: stored siblings, then new node values
+    __shared__ double s_val[kSortedN];                // value handed to the left neighbour
+    __shared__ unsigned s_key[kSortedN];              // compacted (distinct, ascending) leaf indexes
+    __shared__ double s_w[kSortedN];                  // their new leaf weights
+    __shared__ short s_hb[kSortedN];
+    __shared__ short s_next[kSortedN];
+    __shared__ int s_warp[kSortedN / 32];
+    __shared__ double s_red[kSortedN / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int levels = t.depth - 1;
+    const bool in = tid < n;
+    const int64_t k = in ? idx[tid] : 0;
+    const bool oob = in && (k < 0 || k >= t.size);
+    const bool unsorted = in && tid > 0 && idx[tid - 1] > k;
+    const int bad = __syncthreads_or((oob ? 1 : 0) | (unsorted || valid != nullptr ? 2 : 0));
+    if (bad & 1) {
+        if (tid == 0) {
+            t.st->err = MB_ERR_INDEX_OOB;
+            t.st->err_gen = gen;
+        }
+        return;
+    }
+    if (bad & 2) {
+        tree_update_body<WT, false>(t, idx, w, valid, n, nz, gen);
+        return;
+    }
+    // leaf winners: the last entry of a run of equal keys (highest batch position); max over ALL entries
+    const double x = in ? normalized_weight(w[tid], nz) : -INFINITY;
+    const bool winner = in && (tid == n - 1 || idx[tid + 1] != k);
+    double mx = mb::warp_max(x);
+    const unsigned ballot = __ballot_sync(0xffffffffu, winner);
+    if (lane == 0) {
+        s_warp[wid] = __popc(ballot);
+        s_red[wid] = mx;
+    }
+    __syncthreads();
+    int base = 0, m = 0;
+    for (int j = 0; j < (int)(blockDim.x >> 5); ++j) {
+        if (j < wid) base += s_warp[j];
+        m += s_warp[j];
+    }
+    if (tid == 0) {
+        for (int j = 1; j < (int)(blockDim.x >> 5); ++j) mx = fmax(mx, s_red[j]);
+        if (mx > -INFINITY && !(t.st->max_leaf > mx)) {
+            t.st->max_leaf = mx;
+            t.st->max_is_f32 = sizeof(WT) == 4 ? 1 : 0;
+        }
+    }
+    if (winner) {
+        const int pos = base + __popc(ballot & ((1u << lane) - 1u));
+        s_key[pos] = (unsigned)k;
+        s_w[pos] = x;
+    }
+    __syncthreads();
+    // from here on thread `tid` owns compacted entry `tid` (tid < m)
+    bool alive = tid < m;
+    unsigned key = 0;
+    double val = 0.0;
+    int hb = -1;
+    if (alive) {
+        key = s_key[tid];
+        val = s_w[tid];
+        hb = tid == 0 ? levels : 31 - __clz(s_key[tid - 1] ^ key);  // representative of its ancestor up to level hb
+        s_hb[tid] = (short)hb;
+        s_next[tid] = (short)(tid + 1);
+        const int lim = hb < levels ? hb : levels - 1;               // siblings needed for steps 0..lim
+        double pre[kSortedLevels];
+#pragma unroll
+        for (int l = 0; l < kSortedLevels; ++l)
+            if (l <= lim) pre[l] = __ldcg(t.W + level_off(t, l) + ((key >> l) ^ 1u));
+#pragma unroll
+        for (int l = 0; l < kSortedLevels; ++l)
+            if (l <= lim) park[l * kSortedN + tid] = pre[l];
+    }
+    const double leaf_val = val;
+    unsigned wrote = 0;
+    __syncthreads();
+#pragma unroll 1
+    for (int l = 0; l < levels; ++l) {
+        if (alive && hb == l) {          // my node is a right child whose left sibling is touched: hand over, retire
+            s_val[tid] = val;
+            alive = false;
+        }
+        __syncthreads();
+        if (alive) {
+            const int j = s_next[tid];
+            double other;
+            if (j < m && s_hb[j] == l) {
+                other = s_val[j];
+                s_next[tid] = s_next[j];
+            } else {
+                other = park[l * kSortedN + tid];
+            }
+            val = val + other;           // left + right (IEEE addition is commutative)
+            park[l * kSortedN + tid] = val;
+            wrote |= 1u << l;
+        }
+    }
+    if (tid < m) {
+        t.W[key] = leaf_val;
+        for (int l = 0; l < levels; ++l)
+            if (wrote & (1u << l)) t.W[level_off(t, l + 1) + (key >> (l + 1))] = park[l * kSortedN + tid];
     }
 }
 
@@ -582,6 +714,8 @@ int mb_tree_create(int64_t size, int device, mb_tree **out) {
     MB_CUDA(cudaMemset(t->dev.owner, 0xff, sizeof(int) * (size_t)size));
     MB_CUDA(cudaMemset(t->dev.st, 0, sizeof(TreeState)));
     tree_state_reset<<<1, 1>>>(t->dev.st, 0.0);
+    MB_CUDA(cudaFuncSetAttribute(tree_update_sorted<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    MB_CUDA(cudaFuncSetAttribute(tree_update_sorted<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     int per_sm = 0;
     MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_update_kernel<double, true>, 1024, 0));
     int sms = mb::kNumSMs;
@@ -705,6 +839,16 @@ static int launch_update(mb_tree *t, const int64_t *d_index, const void *d_weigh
     if (n > 0x7fffffff) return MB_ERR_INVALID;
     mb::DeviceGuard g(t->device);
     const int gen = ++t->gen;
+    if (n <= kSortedN && !t->force_generic) {
+        const int threads = (int)(((n + 31) / 32) * 32);
+        const size_t dyn = sizeof(double) * (size_t)kSortedN * (size_t)(t->dev.depth - 1);
+        if (dtype == MB_F32)
+            tree_update_sorted<float><<<1, threads, dyn, s>>>(t->dev, d_index, (const float *)d_weight, d_valid, (int)n, nz, gen);
+        else
+            tree_update_sorted<double><<<1, threads, dyn, s>>>(t->dev, d_index, (const double *)d_weight, d_valid, (int)n, nz, gen);
+        MB_LAUNCHED(1);
+        return MB_OK;
+    }
     if (n <= 1024 || (t->force_generic && n <= 4096)) {
         const int threads = (int)(n <= 1024 ? ((n + 31) / 32) * 32 : 1024);
         if (dtype == MB_F32)

@@ -234,3 +234,38 @@ def test_device_priority_normalisation_matches_numpy():
             # ... and to equal the correctly rounded result: float64 pow of the float32 operands, rounded once
             exact = ((np.abs(p) + np.float32(1e-2)).astype(np.float64) ** np.float64(np.float32(0.6))).astype(np.float32)
             assert np.count_nonzero(got.astype(np.float32) != exact) <= 2
+
+
+@pytest.mark.parametrize("size", [7, 1000, 1 << 20, 10_000_000])
+def test_sorted_small_batch_update_vs_oracle(WT, size):
+    """The sorted fast path (csrc/sumtree.cu: tree_update_sorted) that the learner's priority write-back
+    takes: ascending indexes with duplicates, all batch sizes up to 512, float32 and float64 weights."""
+    rng = np.random.RandomState(size % 97)
+    leaves = rng.exponential(size=size)
+    tree, ora = WT(size), OracleTree(size)
+    tree.update_all_leaves(leaves)
+    ora.update_all_leaves(leaves)
+    for n in (1, 2, 31, 32, 33, 200, 511, 512):
+        for dtype in (np.float32, np.float64):
+            idx = np.sort(rng.randint(0, size, size=n)).astype(np.int64)          # duplicates: last write wins
+            if n > 3:
+                idx[n // 2] = idx[n // 2 - 1]                                       # force at least one run
+                idx = np.sort(idx)
+            w = rng.exponential(size=n).astype(dtype)
+            tree.update_leaf_batch(t.from_numpy(w).cuda(), t.from_numpy(idx).cuda())
+            ora.update_leaf_batch(w, idx)
+            assert np.array_equal(tree.weights, ora.weights), (n, dtype)
+            assert tree.max_leaf == ora.max_leaf
+    # clustered keys (neighbouring leaves share almost all ancestors)
+    start = int(rng.randint(0, max(1, size - 600)))
+    idx = np.arange(start, min(size, start + 512), dtype=np.int64)
+    w = rng.exponential(size=len(idx))
+    tree.update_leaf_batch(t.from_numpy(w).cuda(), t.from_numpy(idx).cuda())
+    ora.update_leaf_batch(w, idx)
+    assert np.array_equal(tree.weights, ora.weights)
+    # out-of-range entry in a sorted batch: rejected, nothing written
+    bad = np.array([0, 1, size], dtype=np.int64)
+    tree.update_leaf_batch(t.ones(3, dtype=t.float64).cuda(), t.from_numpy(bad).cuda())
+    with pytest.raises(ValueError, match="out of boundary"):
+        tree.check()
+    assert np.array_equal(tree.weights, ora.weights)
