@@ -386,15 +386,17 @@ __global__ void __launch_bounds__(kSortedN) tree_update_sorted(TreeDev t, const 
     const int64_t k = in ? idx[tid] : 0;
     const bool oob = in && (k < 0 || k >= t.size);
     const bool unsorted = in && tid > 0 && idx[tid - 1] > k;
-    const int bad = __syncthreads_or((oob ? 1 : 0) | (unsorted || valid != nullptr ? 2 : 0));
-    if (bad & 1) {
+    // (__syncthreads_or returns a truth value, not the bitwise OR: two separate votes)
+    const int any_oob = __syncthreads_or(oob ? 1 : 0);
+    const int generic = __syncthreads_or((unsorted || valid != nullptr) ? 1 : 0);
+    if (any_oob && !generic) {
         if (tid == 0) {
             t.st->err = MB_ERR_INDEX_OOB;
             t.st->err_gen = gen;
         }
         return;
     }
-    if (bad & 2) {
+    if (generic) {   // also validates (a masked-out entry may legitimately be out of range)
         tree_update_body<WT, false>(t, idx, w, valid, n, nz, gen);
         return;
     }
