@@ -201,7 +201,7 @@ def build_learner(a, device, seed, world=1):
         t.manual_seed(0)   # identical initial weights on every learner
         qnet, qtgt = Q().to(device), Q().to(device)
         learner = DQNApex(qnet, qtgt, FusedAdam if a.adam == "fused" else t.optim.Adam, t.nn.MSELoss(reduction="none"), group,
-                          (PushPullModelServer("qnet", group, 0),), batch_size=a.batch, learning_rate=1e-3,
+                          (PushPullModelServer("qnet", group, 0, lockstep=True),), batch_size=a.batch, learning_rate=1e-3,
                           discount=0.99, update_rate=0.005, replay_size=a.replay_rows, learner_group=group)
         buf = learner.replay_buffer
     else:

@@ -45,6 +45,12 @@ class DistributedPrioritizedBuffer(PrioritizedBuffer):
         with self.wr_lock:
             return self.wt_tree.get_weight_sum()                     # _weight_sum_service (:278-280)
 
+    def weight_sum_tensor(self) -> t.Tensor:
+        """f64[1] CUDA view of the tree root (no host round trip)."""
+        if getattr(self, "_root_view", None) is None:
+            self._root_view = self.wt_tree._view(lib.mb_tree_root_ptr(self.wt_tree.handle), (1,), "<f8")
+        return self._root_view
+
     def draw(self, n: int, all_weight_sum: float):
         with self.wr_lock:                                           # _sample_service (:293-303)
             dev = self.buffer_device

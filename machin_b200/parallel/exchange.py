@@ -99,8 +99,9 @@ class ShardedSampler:
     def _sample_wire(self, batch_size: int):
         g, dev = self.group, self.group.device
         me, P = g.index, g.size()
-        local_sum = t.tensor([float(self.shard.weight_sum())], dtype=t.float64, device=dev)
-        sums = g.all_gather_f64(local_sum).view(-1).tolist()
+        # the root of the local tree is gathered straight from device memory: the only host
+        # synchronisation of the exchange is reading the P sums back for the ceil apportioning
+        sums = g.all_gather_f64(self.shard.weight_sum_tensor()).view(-1).tolist()
         ssize, total = shard_sample_sizes(sums, batch_size)
         if batch_size <= 0:
             ssize = [0] * P

@@ -20,8 +20,11 @@ def _state_tensors(model: t.nn.Module) -> List[t.Tensor]:
 
 
 class PushPullModelServer:
-    def __init__(self, model_name: str, group, src_index: int = 0):
+    def __init__(self, model_name: str, group, src_index: int = 0, lockstep: bool = False):
+        """``lockstep``: every round has exactly one push and every other member pulls it, so the version
+        is known without reading it back from the device (no host synchronisation in :meth:`pull`)."""
         self.model_name, self.group, self.src_index = model_name, group, int(src_index)
+        self.lockstep = bool(lockstep)
         self._flat = None
 
     @staticmethod
@@ -58,9 +61,12 @@ class PushPullModelServer:
         offs, total = self._layout(tensors)
         flat = self._buffer(total)
         self.group.broadcast(flat, self.src_index)
-        version = int(flat[0:8].view(t.int64).item())
-        if hasattr(model, "pp_version") and version <= model.pp_version:
-            return False
+        if self.lockstep:
+            version = getattr(model, "pp_version", 0) + 1
+        else:
+            version = int(flat[0:8].view(t.int64).item())
+            if hasattr(model, "pp_version") and version <= model.pp_version:
+                return False
         with t.no_grad():
             views = [flat[o:o + x.numel() * x.element_size()].view(x.dtype).view(x.shape) for x, o in zip(tensors, offs)]
             t._foreach_copy_(tensors, views)

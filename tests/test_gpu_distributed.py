@@ -16,6 +16,6 @@ def test_sharded_buffer_over_nccl(world):
     if t.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
+           "--master-addr", "127.0.0.1", "--master-port", str(29611 + world), os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "dist ok" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
