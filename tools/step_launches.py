@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""One graph-replayed learner update between cudaProfilerStart/Stop, for
+`ncu --profile-from-start off --metrics gpu__time_duration.sum` (the launch list of ONE step)."""
+import argparse
+import os
+import sys
+
+import torch as t
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+a = argparse.Namespace(gpus=1, steps=3, warmup=3, impl="b200", replay_rows=int(os.environ.get("ROWS", "2000000")),
+                       batch=512, cpu_storage_rows=1000, cpu_steps=1, no_cpu_baseline=True, no_graph=False,
+                       net="torch", adam="fused")
+dev = t.device("cuda", 0)
+learner = bench.build_learner(a, dev, seed=0)
+learner.enable_cuda_graph()
+for _ in range(5):
+    learner.update()
+t.cuda.synchronize()
+t.cuda.cudart().cudaProfilerStart()
+for _ in range(2):
+    learner.update()
+t.cuda.synchronize()
+t.cuda.cudart().cudaProfilerStop()
+print("done")
