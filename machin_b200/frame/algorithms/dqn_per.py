@@ -72,6 +72,9 @@ class DQNPer(TorchFramework):
         # opt-in: FusedMLP nets + MSE -> forward x3, TD and backward as ONE persistent cooperative kernel
         # (csrc/mlp.cu).  Correct (tests) but currently slower than cuBLAS-backed autograd, see DESIGN.md 8.
         self.use_fused_program = False
+        # opt-in: evaluate Q(s) and Q(s') of the ONLINE net in one forward over [s; s'] (they share weights;
+        # only valid for row-wise networks, i.e. no BatchNorm/Dropout): 3 fewer GEMM + epilogue launches
+        self.fuse_online_forwards = False
         super().__init__()
 
     # ------------------------------------------------------------------ properties / acting (dqn.py:213-331)
@@ -274,12 +277,18 @@ class DQNPer(TorchFramework):
             return self._step_fused(st, update_value, update_target, uniform, use_device_params)
         self.qnet.train()
         batch_size, state, action, reward, next_state, terminal, d_index, d_isw = self._sample(uniform, use_device_params)
-        with t.no_grad():
-            next_q_value = self._criticize(next_state)
-            target_next_q_value = self._criticize(next_state, True)
-        q_value = self._criticize(state)
+        if self.fuse_online_forwards and state.keys() == next_state.keys():
+            both = self._criticize({k: t.cat([state[k], next_state[k]], dim=0) for k in state})
+            q_value, next_q_value = both[:batch_size], both[batch_size:].detach()
+            with t.no_grad():
+                target_next_q_value = self._criticize(next_state, True)
+        else:
+            with t.no_grad():
+                next_q_value = self._criticize(next_state)
+                target_next_q_value = self._criticize(next_state, True)
+            q_value = self._criticize(state)
         act = self.action_get_function(action)
-        td = ops.td_dqn(q_value.detach(), next_q_value, target_next_q_value, act, reward, terminal, self.discount,
+        td = ops.td_dqn(q_value.detach().contiguous(), next_q_value.contiguous(), target_next_q_value, act, reward, terminal, self.discount,
                         is_weight=d_isw, mode=self.mode, want_grad=self._fused_mse)
         batch_size = int(reward.shape[0])  # a sharded buffer may return more than batch_size rows
         if self._fused_mse:

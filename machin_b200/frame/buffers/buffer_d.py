@@ -136,12 +136,9 @@ class IMPALABuffer(DistributedBuffer):
     def sample_method_episode(self, batch_size: int):
         batch_size = min(len(self.episode_transition_handles), batch_size)
         episodes = random.choices(list(self.episode_transition_handles.keys()), k=batch_size)   # impala.py:58
-        handles, sizes = [], []
-        for episode in episodes:
-            h = self.episode_transition_handles[episode]
-            handles.extend(int(x) for x in h)
-            sizes.append(len(h))
-        return batch_size, handles, sizes
+        parts = [np.asarray(self.episode_transition_handles[episode], dtype=np.int64) for episode in episodes]
+        handles = np.concatenate(parts) if parts else np.empty(0, dtype=np.int64)
+        return batch_size, handles, [len(p) for p in parts]
 
     def sample_episodes_device(self, batch_size: int, names=None):
         """Collective device path: (n_episodes, {field: tensor}, lengths list) on requesters."""

@@ -48,6 +48,7 @@ def test_dqn_per_update_vs_reference(criterion):
                  update_rate=0.05, replay_size=N)
     if criterion == "mse_generic":
         dqn._fused_mse = False
+        dqn.fuse_online_forwards = True     # one forward over [s; s'] must not change the trajectory
     assert np.array_equal(_flat(dqn.qnet), g["dqn_init_q"])
     ep = [dict(state={"state": t.from_numpy(g["dqn_state"][i:i + 1])}, action={"action": t.tensor([[g["dqn_action"][i]]])},
                next_state={"state": t.from_numpy(g["dqn_next_state"][i:i + 1])}, reward=float(g["dqn_reward"][i]),
