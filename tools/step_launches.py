@@ -12,7 +12,7 @@ import bench  # noqa: E402
 
 a = argparse.Namespace(gpus=1, steps=3, warmup=3, impl="b200", replay_rows=int(os.environ.get("ROWS", "2000000")),
                        batch=512, cpu_storage_rows=1000, cpu_steps=1, no_cpu_baseline=True, no_graph=False,
-                       net="torch", adam="fused", split_forwards=False)
+                       net="torch", adam="fused", fuse_forwards=False)
 dev = t.device("cuda", 0)
 learner = bench.build_learner(a, dev, seed=0)
 learner.enable_cuda_graph()
