@@ -205,6 +205,10 @@ class DQNApex(DQNPer):
         srv = self.qnet_model_server
         if srv is None:
             return
+        if self.learner_group is not None and self.learner_group.size() == self.apex_group.size():
+            # every member is a learner applying the same averaged gradients: the weights are already
+            # identical everywhere and nobody would consume the broadcast (no actor-only members)
+            return
         net = self.qnet.module if self._is_using_DP_or_DDP else self.qnet
         if self.apex_group.index == srv.src_index:
             srv.push(net, pull_on_fail=False)

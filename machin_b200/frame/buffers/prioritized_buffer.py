@@ -121,6 +121,23 @@ class PrioritizedBuffer(Buffer):
     def advance_beta_device(self):
         self._params_f64[0:1].add_(self.beta_increment_per_sampling).clamp_(max=1.0)
 
+    def _stage_uniform(self, values: np.ndarray) -> t.Tensor:
+        n = values.shape[0]
+        ring = getattr(self, "_u_ring", None)
+        if ring is None or ring["host"][0].shape[0] < n:
+            cap = max(n, 1024)
+            ring = {"host": [t.empty(cap, dtype=t.float64).pin_memory() for _ in range(8)],
+                    "dev": [t.empty(cap, dtype=t.float64, device=self.buffer_device) for _ in range(8)],
+                    "ev": [t.cuda.Event() for _ in range(8)], "i": 0}
+            self._u_ring = ring
+        i = ring["i"] = (ring["i"] + 1) % 8
+        ring["ev"][i].synchronize()                       # the copy that last used this slot has finished
+        ring["host"][i].numpy()[:n] = values
+        dev = ring["dev"][i][:n]
+        dev.copy_(ring["host"][i][:n], non_blocking=True)
+        ring["ev"][i].record()
+        return dev
+
     def _draw(self, batch_size: int, all_weight_sum: float = None, uniform: t.Tensor = None,
               use_device_params: bool = False, out=None):
         """Fused stratified draw on the device (csrc/sumtree.cu: per_sample_*).  ``out``: optional
@@ -135,8 +152,9 @@ class PrioritizedBuffer(Buffer):
             self.advance_beta_device()
             return d_index, d_isw
         if uniform is None:
-            # same call and same stream as the reference (:411): B doubles from np.random
-            uniform = t.from_numpy(np.random.uniform(size=batch_size)).to(self.buffer_device, non_blocking=True)
+            # same call and same stream as the reference (:411): B doubles from np.random, staged through a
+            # small ring of pinned buffers so that the copy is a true asynchronous H2D
+            uniform = self._stage_uniform(np.random.uniform(size=batch_size))
         d_index, d_isw = out if out is not None else (
             t.empty(batch_size, dtype=t.int64, device=self.buffer_device),
             t.empty(batch_size, dtype=t.float64, device=self.buffer_device))
