@@ -50,7 +50,8 @@ def test_tree_and_per_host_entry_points():
     assert np.array_equal(out, ora.weights)
     s, m, d = C.c_double(), C.c_double(), C.c_int()
     assert lib.mb_tree_stats(h, C.byref(s), C.byref(m), C.byref(d), None) == 0
-    assert s.value == ora.get_weight_sum() and m.value == float(ora.max_leaf) and d.value == 0   # MB_F32
+    assert s.value == ora.get_weight_sum() and m.value == float(ora.max_leaf)
+    assert d.value == (0 if isinstance(ora.max_leaf, np.float32) else 1)   # MB_F32 / MB_F64, like the reference's max_leaf
     for B, beta in ((512, 0.4), (4096, 0.7), (5, 1.0)):
         u = rng.uniform(size=B)
         oi, ow = np.empty(B, dtype=np.int64), np.empty(B)
