@@ -1,9 +1,9 @@
-from .buffer import Buffer
+from .buffer import Buffer, EpisodeBook
 from .buffer_d import DistributedBuffer, IMPALABuffer
 from .device_ring import DeviceRing
 from .prioritized_buffer import PrioritizedBuffer
 from .prioritized_buffer_d import DistributedPrioritizedBuffer
 from .weight_tree import WeightTree
 
-__all__ = ["Buffer", "DistributedBuffer", "IMPALABuffer", "DeviceRing", "PrioritizedBuffer",
+__all__ = ["Buffer", "EpisodeBook", "DistributedBuffer", "IMPALABuffer", "DeviceRing", "PrioritizedBuffer",
            "DistributedPrioritizedBuffer", "WeightTree"]

@@ -27,6 +27,52 @@ def _scalar_dtype(v):
     return t.tensor([v]).dtype
 
 
+class EpisodeBook:
+    """Host-side episode bookkeeping of ``Buffer`` (buffer.py:41-44, :93-109) plus the ring cursor of
+    ``TransitionStorageBasic`` (storage.py:97-114), without any storage behind it.
+
+    ``handles``: episode -> slots in stored order; a slot overwritten by a newer episode evicts the WHOLE older
+    episode from the sampleable set.  ``sampleable()`` lists live slots exactly in the order of the
+    reference's ``transition_episode_number`` dict (episodes ascending, slots in stored order)."""
+
+    def __init__(self, capacity: int):
+        self.capacity = int(capacity)
+        self.count = 0                      # len(storage)
+        self.cursor = 0                     # storage.index
+        self.episode_counter = 0
+        self.handles = {}                   # type: Dict[int, np.ndarray]
+        self.slot_episode = np.full(self.capacity, -1, dtype=np.int64)
+
+    def assign(self, n: int):
+        """Reserve ``n`` consecutive ring slots -> (first_slot, positions)."""
+        if n > self.capacity:
+            raise ValueError("Failed to store episode.")
+        first = self.count if self.count < self.capacity else self.cursor
+        positions = (first + np.arange(n, dtype=np.int64)) % self.capacity
+        self.count = min(self.capacity, self.count + n)
+        self.cursor = int((positions[-1] + 1) % self.capacity)
+        return int(first), positions
+
+    def record(self, positions: np.ndarray) -> int:
+        episode_number = self.episode_counter
+        self.episode_counter += 1
+        old = np.unique(self.slot_episode[positions])
+        for ep in old[old >= 0]:            # evict whole older episodes (buffer.py:95-105)
+            slots = np.asarray(self.handles.pop(int(ep)))
+            self.slot_episode[slots[self.slot_episode[slots] == ep]] = -1
+        self.slot_episode[positions] = episode_number
+        self.handles[episode_number] = positions
+        return episode_number
+
+    def sampleable(self) -> List[int]:
+        return [int(s) for slots in self.handles.values() for s in slots]
+
+    def clear(self):
+        self.count = 0
+        self.handles = {}
+        self.slot_episode.fill(-1)
+
+
 class Buffer:
     def __init__(self, buffer_size: int = 1000000, buffer_device: Union[str, t.device] = "cuda",
                  storage=None, **__):
@@ -40,38 +86,36 @@ class Buffer:
         self.buffer_device = t.device("cuda", dev.index if dev.index is not None else 0)
         _lib.require_device(self.buffer_device.index)
         self.storage = DeviceRing(int(buffer_size), self.buffer_device)
-        self.episode_transition_handles = {}  # type: Dict[int, Any]   episode -> slots (array / range)
-        self._slot_episode = np.full(int(buffer_size), -1, dtype=np.int64)
-        self.episode_counter = 0
+        self.book = EpisodeBook(int(buffer_size))
         self._major_attr: List[str] = []
         self._sub_attr: List[str] = []
         self._custom_attr: List[str] = []
         self._host_custom: Dict[str, np.ndarray] = {}
 
-    # ------------------------------------------------------------------ bookkeeping
+    # ------------------------------------------------------------------ bookkeeping (host side: EpisodeBook)
+    @property
+    def episode_transition_handles(self) -> Dict[int, Any]:
+        return self.book.handles
+
+    @property
+    def episode_counter(self) -> int:
+        return self.book.episode_counter
+
     @property
     def transition_episode_number(self) -> Dict[int, int]:
         """slot -> owning episode, in the reference's dict order (buffer.py:42)."""
-        out = {}
-        for ep, slots in self.episode_transition_handles.items():
-            for s in slots:
-                out[int(s)] = ep
-        return out
+        return {int(s): ep for ep, slots in self.book.handles.items() for s in slots}
 
     def _sampleable_handles(self) -> List[int]:
-        return [int(s) for slots in self.episode_transition_handles.values() for s in slots]
+        return self.book.sampleable()
 
     def _record_episode(self, positions: np.ndarray) -> int:
-        episode_number = self.episode_counter
-        self.episode_counter += 1
-        old = np.unique(self._slot_episode[positions])
-        for ep in old[old >= 0]:  # evict whole older episodes (buffer.py:95-105)
-            slots = np.asarray(self.episode_transition_handles.pop(int(ep)))
-            stale = slots[self._slot_episode[slots] == ep]
-            self._slot_episode[stale] = -1
-        self._slot_episode[positions] = episode_number
-        self.episode_transition_handles[episode_number] = positions
-        return episode_number
+        return self.book.record(positions)
+
+    def _assign_slots(self, n: int):
+        first, positions = self.book.assign(n)
+        self.storage.count, self.storage.index = self.book.count, self.book.cursor
+        return first, positions
 
     # ------------------------------------------------------------------ schema
     def _make_schema(self, tr: TransitionBase):
@@ -109,7 +153,7 @@ class Buffer:
         if self.storage.data is None:
             self._make_schema(episode[0])
         n = len(episode)
-        first, positions = self.storage.assign_slots(n)
+        first, positions = self._assign_slots(n)
         dense = {}
         for f in self.storage.fields.values():
             if f.kind == "major":
@@ -145,7 +189,7 @@ class Buffer:
             fields += [Field(a, a, None, v.dtype, v.shape[1:] if v.dim() > 1 else (1,), "custom") for a, v in custom.items()]
             self._major_attr, self._sub_attr, self._custom_attr = list(major), list(sub), sorted(custom)
             self.storage.set_schema(fields)
-        first, positions = self.storage.assign_slots(n)
+        first, positions = self._assign_slots(n)
         dense = {}
         for f in self.storage.fields.values():
             src = major[f.attr][f.key] if f.kind == "major" else (sub[f.attr] if f.kind == "sub" else custom[f.attr])
@@ -161,8 +205,7 @@ class Buffer:
         # The reference only empties the storage (buffer.py:117-121) and leaves stale handles in its
         # dicts (sampling them raises IndexError); here the bookkeeping is dropped as well.
         self.storage.clear()
-        self.episode_transition_handles = {}
-        self._slot_episode.fill(-1)
+        self.book.clear()
 
     # ------------------------------------------------------------------ sample
     def sample_batch(self, batch_size: int, concatenate: bool = True, device: Union[str, t.device] = None,

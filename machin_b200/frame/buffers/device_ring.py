@@ -83,17 +83,6 @@ class DeviceRing:
             arr[i] = MbField(f.offset, f.nbytes, d.data_ptr(), f.nbytes)
         return arr
 
-    # ------------------------------------------------------------------ slots
-    def assign_slots(self, n: int) -> Tuple[int, np.ndarray]:
-        """Reserve ``n`` consecutive ring slots; returns (first_slot, positions)."""
-        if n > self.max_size:
-            raise ValueError("Failed to store episode.")
-        first = self.count if self.count < self.max_size else self.index
-        positions = (first + np.arange(n, dtype=np.int64)) % self.max_size
-        self.count = min(self.max_size, self.count + n)
-        self.index = int((positions[-1] + 1) % self.max_size)
-        return int(first), positions
-
     # ------------------------------------------------------------------ data movement
     def write(self, first_slot: int, n: int, dense: Dict[str, t.Tensor], stream=None):
         names = [k for k in self.fields if k in dense]

@@ -421,10 +421,41 @@ def gen_gae():
     np.savez_compressed(os.path.join(OUT, "ref_gae.npz"), **out)
 
 
+# --------------------------------------------------------------------------- uniform Buffer bookkeeping
+def gen_buffer():
+    """Slot assignment, whole-episode eviction and the order in which the reference's Buffer offers
+    slots to random.sample / random.choices (buffer.py:46-109, :224-252; storage.py:85-114)."""
+    from machin.frame.buffers import Buffer
+
+    out = {}
+    for tag, cap, lens in (("a", 10, [3, 4, 2, 5, 1, 6, 2, 2, 7, 1]), ("b", 64, [9, 30, 17, 25, 3, 11, 40, 8, 5, 22, 1, 13])):
+        buf = Buffer(buffer_size=cap)
+        rng = np.random.RandomState(4)
+        keys, picks_u, picks_r, sizes = [], [], [], []
+        for n in lens:
+            buf.store_episode(_episode(n, 2, rng))
+            ks = list(buf.transition_episode_number.keys())
+            keys.append(np.array(ks + [-1] * (cap - len(ks)), dtype=np.int64))
+            sizes.append(buf.size())
+            random.seed(5)
+            bs, batch = buf.sample_method_random_unique(4)
+            random.seed(5)
+            picks_u.append(np.array(random.sample(list(buf.transition_episode_number.keys()), k=bs) + [-1] * (4 - bs)))
+            random.seed(6)
+            picks_r.append(np.array(random.choices(list(buf.transition_episode_number.keys()), k=min(len(ks), 4)) + [-1] * (4 - min(len(ks), 4))))
+        out[f"{tag}_cap"] = np.int64(cap)
+        out[f"{tag}_lens"] = np.array(lens, dtype=np.int64)
+        out[f"{tag}_keys"] = np.stack(keys)
+        out[f"{tag}_size"] = np.array(sizes, dtype=np.int64)
+        out[f"{tag}_pick_unique"] = np.stack(picks_u)
+        out[f"{tag}_pick_random"] = np.stack(picks_r)
+    np.savez_compressed(os.path.join(OUT, "ref_buffer.npz"), **out)
+
+
 if __name__ == "__main__":
     ref_shim.load()
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["tree", "per", "td", "vtrace", "gae"]
+    which = sys.argv[1:] or ["tree", "per", "td", "vtrace", "gae", "buffer"]
     for name in which:
         globals()["gen_" + name]()
         print("wrote", name)

@@ -83,3 +83,31 @@ def test_host_logic_ring_layout_and_transition():
     with pytest.raises(ValueError):
         Transition(state={"s": t.zeros(2, 3)}, action={"a": t.zeros(2, 1)}, next_state={"s": t.zeros(2, 3)},
                    reward=1.0, terminal=False)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_episode_book_vs_reference_buffer(tag):
+    """Slot assignment, whole-episode eviction and sampling order of the host-side bookkeeping against the
+    unmodified reference Buffer (tests/golden/ref_buffer.npz; buffer.py:46-109,224-252, storage.py:85-114)."""
+    import random
+    import numpy as np
+    from conftest import GOLDEN
+    from machin_b200.frame.buffers import EpisodeBook
+    g = np.load(os.path.join(GOLDEN, "ref_buffer.npz"))
+    cap = int(g[f"{tag}_cap"])
+    book = EpisodeBook(cap)
+    for i, n in enumerate(g[f"{tag}_lens"]):
+        first, pos = book.assign(int(n))
+        book.record(pos)
+        keys = book.sampleable()
+        want = [int(k) for k in g[f"{tag}_keys"][i] if k >= 0]
+        assert keys == want, (i, keys, want)
+        assert book.count == int(g[f"{tag}_size"][i])
+        random.seed(5)
+        got = random.sample(keys, k=min(len(keys), 4))
+        assert got == [int(k) for k in g[f"{tag}_pick_unique"][i] if k >= 0]
+        random.seed(6)
+        got = random.choices(keys, k=min(len(keys), 4))
+        assert got == [int(k) for k in g[f"{tag}_pick_random"][i] if k >= 0]
+    with pytest.raises(ValueError, match="Failed to store episode"):
+        book.assign(cap + 1)
