@@ -121,7 +121,9 @@ typedef struct mb_per_params {
     double beta;
     double all_weight_sum;
     int64_t n_stored;
-    int64_t step; /* which row of a [steps, n] uniform table to read (graph replay), else 0 */
+    int64_t step;   /* which row of a [steps, n] uniform table to read (graph replay), else 0 */
+    int64_t n_draw; /* > 0: draw this many samples (<= the n of the call, which then only sizes the launch):
+                     * the shard exchange replays a fixed-shape graph while the apportioned count changes */
 } mb_per_params;
 int mb_per_sample(mb_tree *tree, const double *d_uniform, int64_t n, int64_t n_stored,
                   double all_weight_sum, double beta, const mb_per_params *d_params,
@@ -172,6 +174,22 @@ int mb_rows_pack_meta(void *d_wire, int64_t width, int64_t meta_offset, int64_t 
                       const float *d_value_f32, void *stream);
 int mb_rows_unpack_meta(const void *d_wire, int64_t width, int64_t meta_offset, int64_t n, int64_t *d_index,
                         int64_t *d_version, double *d_value_f64, float *d_value_f32, void *stream);
+/* Fixed-shape shard exchange (every (shard, requester) pair always moves `cap` wire rows; d_counts[m] of the
+ * rows of block m are real).  All counts are read on the device, so the calls can be replayed in a CUDA graph.
+ *  compact:  recv[P][cap][width] -> merged[sum(counts)][width] in member order, rows beyond the sum zeroed up
+ *            to merged_rows; metadata split out; is_weight multiplied by *d_scale (0 for padding rows)
+ *  scatter:  the write-back of merged row j (block m, position i) -> send[m][i] = (index, version, priority)
+ *  mask:     recv[P][cap][24] -> flat index / priority / valid, valid = i < d_counts[self] (rows this shard
+ *            served to requester r) and version_table[index] == version (prioritized_buffer_d.py:282-291) */
+int mb_wire_compact(const void *d_recv, int n_blocks, int64_t cap, int64_t width, int64_t meta_offset,
+                    const int64_t *d_counts, void *d_merged, int64_t merged_rows, int64_t *d_index,
+                    int64_t *d_version, double *d_is_weight, const double *d_scale, void *stream);
+int mb_wire_scatter_update(void *d_send, int n_blocks, int64_t cap, const int64_t *d_counts,
+                           const int64_t *d_index, const int64_t *d_version, const float *d_priority,
+                           int64_t merged_rows, void *stream);
+int mb_wire_update_mask(const void *d_recv, int n_blocks, int64_t cap, const int64_t *d_counts, int self_block,
+                        const int64_t *d_version_table, int64_t table_size, int64_t *d_index, float *d_priority,
+                        uint8_t *d_valid, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * TD target / priority math

@@ -37,7 +37,7 @@ class MbField(C.Structure):
 
 
 class MbPerParams(C.Structure):
-    _fields_ = [("beta", f64), ("all_weight_sum", f64), ("n_stored", i64), ("step", i64)]
+    _fields_ = [("beta", f64), ("all_weight_sum", f64), ("n_stored", i64), ("step", i64), ("n_draw", i64)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/machin_b200.h
@@ -75,6 +75,9 @@ SIGNATURES = {
     "mb_rows_gather_packed": (i32, [vp, i64, i64, vp, i64, vp, vp]),
     "mb_rows_pack_meta": (i32, [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp]),
     "mb_rows_unpack_meta": (i32, [vp, i64, i64, i64, vp, vp, vp, vp, vp]),
+    "mb_wire_compact": (i32, [vp, i32, i64, i64, i64, vp, vp, i64, vp, vp, vp, vp, vp]),
+    "mb_wire_scatter_update": (i32, [vp, i32, i64, vp, vp, vp, vp, i64, vp]),
+    "mb_wire_update_mask": (i32, [vp, i32, i64, vp, i32, vp, i64, vp, vp, vp, vp]),
     "mb_td_dqn": (i32, [vp, vp, vp, i64, i32, vp, vp, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]),
     "mb_td_target": (i32, [vp, vp, vp, i64, f32, vp, vp, vp, vp]),
     "mb_soft_update": (i32, [vp, vp, i64, f64, vp]),

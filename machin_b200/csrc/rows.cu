@@ -91,6 +91,70 @@ __global__ void __launch_bounds__(256) rows_unpack_meta_kernel(const char *__res
     if (v32) v32[i] = (float)v;
 }
 
+// ---- fixed-shape exchange helpers (counts are read on the device: graph-replayable) --------------------
+__global__ void __launch_bounds__(256) wire_compact_kernel(const char *__restrict__ recv, int P, int64_t cap,
+                                                           int64_t width, int64_t meta_off,
+                                                           const int64_t *__restrict__ counts, char *__restrict__ merged,
+                                                           int64_t merged_rows, int64_t *__restrict__ index,
+                                                           int64_t *__restrict__ version, double *__restrict__ isw,
+                                                           const double *__restrict__ scale) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // merged row handled by this warp
+    if (j >= merged_rows) return;
+    int64_t base = 0;
+    int m = 0;
+    while (m < P && j >= base + counts[m]) base += counts[m++];
+    char *dst = merged + j * width;
+    if (m == P) {                                  // padding row: zero payload, weight 0
+        for (int64_t k = lane * 16; k < width; k += 512) *reinterpret_cast<uint4 *>(dst + k) = make_uint4(0, 0, 0, 0);
+        if (lane == 0) { index[j] = 0; version[j] = -1; isw[j] = 0.0; }
+        return;
+    }
+    const char *src = recv + ((int64_t)m * cap + (j - base)) * width;
+    for (int64_t k = lane * 16; k < width; k += 512) *reinterpret_cast<uint4 *>(dst + k) = __ldcs(reinterpret_cast<const uint4 *>(src + k));
+    if (lane == 0) {
+        const char *meta = src + meta_off;
+        index[j] = reinterpret_cast<const int64_t *>(meta)[0];
+        version[j] = reinterpret_cast<const int64_t *>(meta)[1];
+        isw[j] = reinterpret_cast<const double *>(meta)[2] * (scale ? *scale : 1.0);
+    }
+}
+
+__global__ void __launch_bounds__(256) wire_scatter_update_kernel(char *__restrict__ send, int P, int64_t cap,
+                                                                  const int64_t *__restrict__ counts,
+                                                                  const int64_t *__restrict__ index,
+                                                                  const int64_t *__restrict__ version,
+                                                                  const float *__restrict__ priority,
+                                                                  int64_t merged_rows) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= merged_rows) return;
+    int64_t base = 0;
+    int m = 0;
+    while (m < P && j >= base + counts[m]) base += counts[m++];
+    if (m == P) return;
+    char *dst = send + ((int64_t)m * cap + (j - base)) * 24;
+    reinterpret_cast<int64_t *>(dst)[0] = index[j];
+    reinterpret_cast<int64_t *>(dst)[1] = version[j];
+    reinterpret_cast<double *>(dst)[2] = (double)priority[j];
+}
+
+__global__ void __launch_bounds__(256) wire_update_mask_kernel(const char *__restrict__ recv, int P, int64_t cap,
+                                                               const int64_t *__restrict__ counts, int self_block,
+                                                               const int64_t *__restrict__ table, int64_t table_size,
+                                                               int64_t *__restrict__ index, float *__restrict__ priority,
+                                                               uint8_t *__restrict__ valid) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)P * cap) return;
+    const int64_t i = e % cap;
+    const char *src = recv + e * 24;
+    const int64_t k = reinterpret_cast<const int64_t *>(src)[0];
+    const int64_t v = reinterpret_cast<const int64_t *>(src)[1];
+    const bool real = i < counts[self_block] && k >= 0 && k < table_size;
+    index[e] = real ? k : 0;
+    priority[e] = real ? (float)reinterpret_cast<const double *>(src)[2] : 0.0f;
+    valid[e] = (real && table[k] == v) ? 1 : 0;
+}
+
 int launch_rows(bool gather, void *ring, int64_t pitch, int64_t capacity, const int64_t *index,
                 int64_t first_slot, int64_t n, const mb_field *fields, int n_fields, cudaStream_t s) {
     if (!ring || pitch <= 0 || capacity <= 0 || n < 0 || n_fields < 0 || n_fields > MB_MAX_FIELDS ||
@@ -156,6 +220,45 @@ int mb_rows_unpack_meta(const void *d_wire, int64_t width, int64_t meta_offset, 
     if (n == 0) return MB_OK;
     rows_unpack_meta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const char *)d_wire, width, meta_offset, n, d_index, d_version, d_value_f64, d_value_f32);
+    MB_LAUNCHED(1);
+    return MB_OK;
+}
+
+int mb_wire_compact(const void *d_recv, int n_blocks, int64_t cap, int64_t width, int64_t meta_offset,
+                    const int64_t *d_counts, void *d_merged, int64_t merged_rows, int64_t *d_index, int64_t *d_version,
+                    double *d_is_weight, const double *d_scale, void *stream) {
+    if (!d_recv || !d_counts || !d_merged || !d_index || !d_version || !d_is_weight || n_blocks < 1 || cap < 1 ||
+        width % 16 || meta_offset % 8 || meta_offset + 24 > width || merged_rows < 0)
+        return MB_ERR_INVALID;
+    if (merged_rows == 0) return MB_OK;
+    wire_compact_kernel<<<(unsigned)((merged_rows * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const char *)d_recv, n_blocks, cap, width, meta_offset, d_counts, (char *)d_merged, merged_rows, d_index,
+        d_version, d_is_weight, d_scale);
+    MB_LAUNCHED(1);
+    return MB_OK;
+}
+
+int mb_wire_scatter_update(void *d_send, int n_blocks, int64_t cap, const int64_t *d_counts, const int64_t *d_index,
+                           const int64_t *d_version, const float *d_priority, int64_t merged_rows, void *stream) {
+    if (!d_send || !d_counts || !d_index || !d_version || !d_priority || n_blocks < 1 || cap < 1 || merged_rows < 0)
+        return MB_ERR_INVALID;
+    if (merged_rows == 0) return MB_OK;
+    wire_scatter_update_kernel<<<(unsigned)((merged_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (char *)d_send, n_blocks, cap, d_counts, d_index, d_version, d_priority, merged_rows);
+    MB_LAUNCHED(1);
+    return MB_OK;
+}
+
+int mb_wire_update_mask(const void *d_recv, int n_blocks, int64_t cap, const int64_t *d_counts, int self_block,
+                        const int64_t *d_version_table, int64_t table_size, int64_t *d_index, float *d_priority,
+                        uint8_t *d_valid, void *stream) {
+    if (!d_recv || !d_counts || !d_version_table || !d_index || !d_priority || !d_valid || n_blocks < 1 || cap < 1 ||
+        self_block < 0 || self_block >= n_blocks)
+        return MB_ERR_INVALID;
+    const int64_t total = (int64_t)n_blocks * cap;
+    wire_update_mask_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const char *)d_recv, n_blocks, cap, d_counts, self_block, d_version_table, table_size, d_index, d_priority,
+        d_valid);
     MB_LAUNCHED(1);
     return MB_OK;
 }

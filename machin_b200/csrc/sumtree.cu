@@ -580,6 +580,7 @@ __device__ __forceinline__ void per_one(const TreeDev &t, const double *__restri
         n_stored = a.d_params->n_stored;
         row = a.d_params->step;
     }
+    // (n is the number of draws actually made: callers pass per_draws(a, launch n))
     const double root = __ldcg(t.W + t.total - 2);
     // three separately rounded float64 ops, no FMA contraction (:409-412)
     const double seg = __ddiv_rn(root, (double)n);
@@ -593,12 +594,22 @@ __device__ __forceinline__ void per_one(const TreeDev &t, const double *__restri
     isw = pow(__dmul_rn((double)n_stored, prob), -beta);         // (:423)
 }
 
+// number of draws: the launch's n, or a device-side override (fixed-shape graph replay, see mb_per_params)
+__device__ __forceinline__ int64_t per_draws(const PerArgs &a, int64_t n) {
+    if (a.d_params) {
+        const int64_t d = a.d_params->n_draw;
+        if (d > 0 && d < n) return d;
+    }
+    return n;
+}
+
 // n <= 1024: one CTA does the draw and the max-normalisation (:424).
 __global__ void __launch_bounds__(1024) per_sample_small(TreeDev t, const double *__restrict__ u, int64_t n,
                                                          PerArgs a, int64_t *__restrict__ out_idx,
                                                          double *__restrict__ out_isw) {
     __shared__ double red[32];
     const int tid = threadIdx.x;
+    n = per_draws(a, n);
     int64_t index = 0;
     double isw = -INFINITY;
     if (tid < n) per_one(t, u, n, tid, a, index, isw);
@@ -626,6 +637,7 @@ __global__ void __launch_bounds__(128) per_sample_cluster(TreeDev t, const doubl
     __shared__ double cta_max;
     const int tid = threadIdx.x;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + tid;
+    n = per_draws(a, n);
     int64_t index = 0;
     double isw = -INFINITY;
     if (i < n) per_one(t, u, n, i, a, index, isw);

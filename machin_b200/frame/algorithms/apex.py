@@ -106,7 +106,14 @@ class DQNApex(DQNPer):
     # are captured; the row exchange, the gradient all-reduce, the priority write-back and the weight
     # broadcast stay eager NCCL calls between the replays.  The merged batch has a data-dependent size
     # n in [B, B + P - 1] (ceil apportioning), so the graphs run on B + P padded rows whose IS weight is 0.
-    def enable_cuda_graph(self, warmup: int = 3):
+    def enable_cuda_graph(self, warmup: int = 3, static_exchange: bool = False):
+        """``static_exchange``: fixed-shape variant -- every (shard, requester) pair always moves ``batch_size``
+        wire rows and the kernels read the apportioned counts from device memory, so draw, both all-to-alls,
+        compute, the gradient all-reduce, the optimizer and the tree write-back are ONE graph replay per
+        update; the host only reads the shard sums (the reference's own synchronisation point,
+        prioritized_buffer_d.py:221-234), draws the uniforms and refreshes ~100 bytes of parameters."""
+        if static_exchange:
+            return self._enable_static_graph(warmup)
         buf = self.replay_buffer
         dev = buf.buffer_device
         buf._exchange()                                   # collective: agree on the row layout
@@ -176,7 +183,147 @@ class DQNApex(DQNPer):
         self._apex_graph = st
         t.cuda.synchronize(dev)
 
+    # ------------------------------------------------------------------ fixed-shape, single-graph update
+    def _enable_static_graph(self, warmup: int = 3):
+        import struct
+        import torch.distributed as dist
+        from ..._lib import lib, ptr, check, stream_ptr
+        from ..buffers import PrioritizedBuffer
+        buf, grp = self.replay_buffer, self.apex_group
+        dev, P, me, B = buf.buffer_device, grp.size(), grp.index, self.batch_size
+        if not self._fused_mse or self.update_rate is None or B > 1024 or list(buf._exchange().requesters) != list(range(P)):
+            raise RuntimeError("static exchange needs MSELoss, soft target updates, batch <= 1024 and every member learning")
+        pitch = buf.storage.pitch
+        W, cap, capB = pitch + 24, B, B + P
+        z = lambda shape, dt: t.zeros(shape, dtype=dt, device=dev)
+        st = {"P": P, "cap": cap, "capB": capB, "W": W,
+              "counts": z(P, t.int64), "counts_pin": t.zeros(P, dtype=t.int64).pin_memory(),
+              "params": z((P, 40), t.uint8), "params_pin": t.zeros((P, 40), dtype=t.uint8).pin_memory(),
+              "uni": z((P, cap), t.float64), "uni_pin": t.zeros((P, cap), dtype=t.float64).pin_memory(),
+              "scale": z(1, t.float64), "scale_pin": t.zeros(1, dtype=t.float64).pin_memory(),
+              "send": z((P * cap, W), t.uint8), "recv": z((P * cap, W), t.uint8),
+              "merged": z((capB, W), t.uint8), "idx": z(capB, t.int64), "ver": z(capB, t.int64), "isw": z(capB, t.float64),
+              "send2": z((P * cap, 24), t.uint8), "recv2": z((P * cap, 24), t.uint8),
+              "u_idx": z(P * cap, t.int64), "u_pri": z(P * cap, t.float32), "u_valid": z(P * cap, t.uint8),
+              "d_idx": [z(cap, t.int64) for _ in range(P)], "d_isw": [z(cap, t.float64) for _ in range(P)],
+              "struct": struct}
+        params = list(self.qnet.parameters())
+        self._flat_grad = t.zeros(sum(p.numel() for p in params), dtype=t.float32, device=dev)
+        o = 0
+        for p in params:
+            p.grad = self._flat_grad[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        for group in self.qnet_optim.param_groups:
+            if "capturable" in group:
+                group["capturable"] = True
+        fields = buf.storage.fields
+        grp_f = lambda fl, attr: {f.key: fl[f.name] for f in fields.values() if f.attr == attr and f.kind == "major"}
+        tree, table = buf.wt_tree.handle, buf.buffer_version_table
+
+        def body():
+            for name in ("counts", "params", "uni", "scale"):
+                st[name].copy_(st[name + "_pin"], non_blocking=True)
+            for r in range(P):                           # this shard serves every requester, member order
+                wire = st["send"][r * cap:(r + 1) * cap]
+                check(lib.mb_per_sample(tree, ptr(st["uni"][r]), cap, 0, 0.0, 0.0, ptr(st["params"][r]), ptr(st["d_idx"][r]),
+                                        ptr(st["d_isw"][r]), stream_ptr()))
+                buf.storage.gather_into_wire(st["d_idx"][r], wire)
+                check(lib.mb_rows_pack_meta(ptr(wire), W, pitch, cap, ptr(st["d_idx"][r]), None, ptr(table),
+                                            ptr(st["d_isw"][r]), None, stream_ptr()))
+            if P > 1:
+                dist.all_to_all_single(st["recv"], st["send"], group=grp.pg)
+            else:
+                st["recv"].copy_(st["send"])
+            check(lib.mb_wire_compact(ptr(st["recv"]), P, cap, W, pitch, ptr(st["counts"]), ptr(st["merged"]), capB,
+                                      ptr(st["idx"]), ptr(st["ver"]), ptr(st["isw"]), ptr(st["scale"]), stream_ptr()))
+            fl = buf.storage.unpack(st["merged"])
+            state, action, next_state = grp_f(fl, "state"), grp_f(fl, "action"), grp_f(fl, "next_state")
+            with t.no_grad():
+                nq = self._criticize(next_state)
+                tq = self._criticize(next_state, True)
+            q = self._criticize(state)
+            td = ops.td_dqn(q.detach(), nq, tq, self.action_get_function(action), fl["reward"], fl["terminal"],
+                            self.discount, is_weight=st["isw"], mode=self.mode, want_grad=True)
+            self._flat_grad.zero_()
+            q.backward(td["grad_q"])
+            if P > 1:
+                dist.all_reduce(self._flat_grad, group=self.learner_group.pg if self.learner_group is not None else grp.pg)
+                self._flat_grad.div_(P)
+            if np.isfinite(self.grad_max):
+                nn.utils.clip_grad_norm_(self.qnet.parameters(), self.grad_max)
+            self.qnet_optim.step()
+            soft_update(self.qnet_target, self.qnet, self.update_rate)
+            check(lib.mb_wire_scatter_update(ptr(st["send2"]), P, cap, ptr(st["counts"]), ptr(st["idx"]), ptr(st["ver"]),
+                                             ptr(td["abs_error"]), capB, stream_ptr()))
+            if P > 1:
+                dist.all_to_all_single(st["recv2"], st["send2"], group=grp.pg)
+            else:
+                st["recv2"].copy_(st["send2"])
+            check(lib.mb_wire_update_mask(ptr(st["recv2"]), P, cap, ptr(st["counts"]), me, ptr(table), table.numel(),
+                                          ptr(st["u_idx"]), ptr(st["u_pri"]), ptr(st["u_valid"]), stream_ptr()))
+            PrioritizedBuffer.update_priority(buf, st["u_pri"], st["u_idx"], valid=st["u_valid"])
+            return td["loss_elem"].mean()
+
+        # snapshot everything the warm-up replays will touch
+        saved = [[x.detach().clone() for x in list(m.parameters()) + list(m.buffers())] for m in (self.qnet, self.qnet_target)]
+        fresh = len(self.qnet_optim.state) == 0
+        tree_snap, beta0 = buf.wt_tree.snapshot(), buf.curr_beta
+        np_state = np.random.get_state()
+        self.qnet.train()
+        self._static = st
+        self._static_prepare()                           # collective: real counts / uniforms for the warm-up
+        cur, side = t.cuda.current_stream(dev), t.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with t.cuda.stream(side):
+            for _ in range(warmup):
+                body()
+        cur.wait_stream(side)
+        t.cuda.synchronize(dev)
+        graph = t.cuda.CUDAGraph()
+        with t.cuda.graph(graph, capture_error_mode="thread_local"):
+            st["loss"] = body()
+        st["graph"] = graph
+        with t.no_grad():
+            for m, sv in zip((self.qnet, self.qnet_target), saved):
+                for x, v in zip(list(m.parameters()) + list(m.buffers()), sv):
+                    x.copy_(v)
+            if fresh:
+                for pst in self.qnet_optim.state.values():
+                    for v in pst.values():
+                        if t.is_tensor(v):
+                            v.zero_()
+        buf.wt_tree.restore(tree_snap)
+        buf.curr_beta = beta0
+        np.random.set_state(np_state)
+        t.cuda.synchronize(dev)
+        if P > 1:
+            grp.barrier()
+
+    def _static_prepare(self):
+        """Host part of a fixed-shape update: read the shard sums (one sync), apportion, draw this shard's
+        uniforms from np.random in the reference's order, refresh the pinned parameter blocks."""
+        from ...parallel.exchange import shard_sample_sizes
+        st, buf, grp = self._static, self.replay_buffer, self.apex_group
+        P, me, cap = st["P"], grp.index, st["cap"]
+        sums = grp.all_gather_f64(buf.weight_sum_tensor()).view(-1).tolist()
+        ssize, total = shard_sample_sizes(sums, self.batch_size)
+        n, n_mine = int(sum(ssize)), int(ssize[me])
+        st["counts_pin"].numpy()[:] = ssize
+        st["scale_pin"].numpy()[0] = st["capB"] / n
+        raw = st["params_pin"].numpy()
+        for r in range(P):                                # one draw per requester; beta advances per draw (:425-427)
+            raw[r] = np.frombuffer(st["struct"].pack("<ddqqq", float(buf.curr_beta), float(total), len(buf.storage), 0, n_mine),
+                                   dtype=np.uint8)
+            if n_mine > 0:
+                st["uni_pin"].numpy()[r, :n_mine] = np.random.uniform(size=n_mine)
+                buf.curr_beta = np.min([1.0, buf.curr_beta + buf.beta_increment_per_sampling])
+        return n
+
     def update_device(self, update_value=True, update_target=True, uniform=None):
+        if getattr(self, "_static", None) is not None and "graph" in self._static and update_value and update_target:
+            self._static_prepare()
+            self._static["graph"].replay()
+            return self._static["loss"]
         st = getattr(self, "_apex_graph", None)
         if st is None or not (update_value and update_target):
             return super().update_device(update_value, update_target, uniform)

@@ -272,3 +272,38 @@ def test_dqn_per_fused_net_vs_reference(use_program):
         np.testing.assert_allclose(dqn.replay_buffer.wt_tree.weights, g[f"dqn_tree{step + 1}"], rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(_flat(dqn.qnet), g[f"dqn_q{step + 1}"], rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(_flat(dqn.qnet_target), g[f"dqn_qt{step + 1}"], rtol=1e-5, atol=1e-6)
+
+
+def test_apex_static_exchange_matches_dynamic_single_member():
+    """The fixed-shape single-graph update (padded wire blocks, device-side counts) against the dynamic
+    exchange, on a group of one: same seeds -> same draws, same losses, same trees, same weights."""
+    from machin_b200.frame.algorithms import DQNApex
+    from machin_b200.parallel import LocalGroup
+    S, A, N, B = 12, 5, 3000, 64
+
+    def make(seed):
+        t.manual_seed(seed)
+        q, qt = QNet(S, A, 32).cuda(), QNet(S, A, 32).cuda()
+        learner = DQNApex(q, qt, t.optim.SGD, t.nn.MSELoss(reduction="none"), LocalGroup(device="cuda:0"), (), batch_size=B,
+                          learning_rate=0.05, discount=0.9, update_rate=0.1, replay_size=4096)
+        rng = np.random.RandomState(3)
+        learner.replay_buffer.store_episode_tensors(
+            {"state": {"state": t.from_numpy(rng.randn(N, S).astype(np.float32))},
+             "action": {"action": t.from_numpy(rng.randint(0, A, size=(N, 1)))},
+             "next_state": {"state": t.from_numpy(rng.randn(N, S).astype(np.float32))}},
+            {"reward": t.from_numpy(rng.randn(N, 1).astype(np.float32)), "terminal": t.from_numpy(rng.rand(N, 1) < 0.1)},
+            priorities=rng.exponential(size=N))
+        return learner
+
+    a, b = make(0), make(0)
+    b.enable_cuda_graph(static_exchange=True)
+    assert np.array_equal(a.replay_buffer.wt_tree.weights, b.replay_buffer.wt_tree.weights)
+    for step in range(6):
+        np.random.seed(100 + step)
+        la = a.update_device().item()
+        np.random.seed(100 + step)
+        lb = b.update_device().item()
+        assert abs(la - lb) <= 1e-6 * max(1.0, abs(la)), (step, la, lb)
+        np.testing.assert_allclose(b.replay_buffer.wt_tree.weights, a.replay_buffer.wt_tree.weights, rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(_flat(b.qnet), _flat(a.qnet), rtol=1e-5, atol=1e-7)
+        assert a.replay_buffer.curr_beta == b.replay_buffer.curr_beta
