@@ -106,12 +106,13 @@ __global__ void __launch_bounds__(256) wire_compact_kernel(const char *__restric
     while (m < P && j >= base + counts[m]) base += counts[m++];
     char *dst = merged + j * width;
     if (m == P) {                                  // padding row: zero payload, weight 0
-        for (int64_t k = lane * 16; k < width; k += 512) *reinterpret_cast<uint4 *>(dst + k) = make_uint4(0, 0, 0, 0);
+        for (int64_t k = lane * 8; k < width; k += 256) *reinterpret_cast<uint2 *>(dst + k) = make_uint2(0, 0);
         if (lane == 0) { index[j] = 0; version[j] = -1; isw[j] = 0.0; }
         return;
     }
     const char *src = recv + ((int64_t)m * cap + (j - base)) * width;
-    for (int64_t k = lane * 16; k < width; k += 512) *reinterpret_cast<uint4 *>(dst + k) = __ldcs(reinterpret_cast<const uint4 *>(src + k));
+    // wire rows are payload (multiple of 16) + 24 bytes of metadata: 8-byte granularity
+    for (int64_t k = lane * 8; k < width; k += 256) *reinterpret_cast<uint2 *>(dst + k) = __ldcs(reinterpret_cast<const uint2 *>(src + k));
     if (lane == 0) {
         const char *meta = src + meta_off;
         index[j] = reinterpret_cast<const int64_t *>(meta)[0];
@@ -228,7 +229,7 @@ int mb_wire_compact(const void *d_recv, int n_blocks, int64_t cap, int64_t width
                     const int64_t *d_counts, void *d_merged, int64_t merged_rows, int64_t *d_index, int64_t *d_version,
                     double *d_is_weight, const double *d_scale, void *stream) {
     if (!d_recv || !d_counts || !d_merged || !d_index || !d_version || !d_is_weight || n_blocks < 1 || cap < 1 ||
-        width % 16 || meta_offset % 8 || meta_offset + 24 > width || merged_rows < 0)
+        width % 8 || meta_offset % 8 || meta_offset + 24 > width || merged_rows < 0)
         return MB_ERR_INVALID;
     if (merged_rows == 0) return MB_OK;
     wire_compact_kernel<<<(unsigned)((merged_rows * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
