@@ -52,7 +52,7 @@ def parse():
     p.add_argument("--net", default="torch", choices=["torch", "fused", "fused-program"],
                    help="Q-net implementation: nn.Module over cuBLAS (default, fastest measured), FusedMLP autograd "
                         "(csrc/mlp.cu), or FusedMLP + the persistent fused forward/TD/backward program")
-    p.add_argument("--dynamic-exchange", action="store_true", help="N > 1: exactly-sized eager NCCL exchanges between two graphs")
+    p.add_argument("--static-exchange", action="store_true", help="N > 1, EXPERIMENTAL: fixed-shape exchange, whole update as one graph")
     p.add_argument("--fuse-forwards", action="store_true", help="one online forward over [s; s'] instead of two passes like the "
                    "reference (measured: no gain, 0.204 vs 0.205 ms/update)")
     p.add_argument("--adam", default="fused", choices=["fused", "torch"], help="FusedAdam (csrc/mlp.cu) or torch.optim.Adam(fused=True)")
@@ -332,9 +332,10 @@ def run_b200(a):
     learner = build_learner(a, device, seed=rank, world=world)
     graph = not a.no_graph
     if graph and world > 1:
-        # N > 1: fixed-shape exchange, the whole update incl. the NCCL collectives is one graph (--dynamic-exchange:
-        # two compute graphs around eager, exactly-sized NCCL exchanges)
-        learner.enable_cuda_graph(static_exchange=not a.dynamic_exchange)
+        # N > 1: two compute graphs around eager, exactly-sized NCCL exchanges (validated at N = 2, 4).
+        # --static-exchange: fixed-shape exchange with the NCCL collectives captured too -- one graph per update;
+        # equivalent to the dynamic path on a group of one (tests), but its 2-GPU run hung and is not debugged yet
+        learner.enable_cuda_graph(static_exchange=a.static_exchange)
     elif graph:
         learner.enable_cuda_graph()
     K, W, B = a.steps, max(a.warmup, 3), a.batch
@@ -432,7 +433,7 @@ def run_b200(a):
         "learner_updates_per_sec": K / (ms_total * 1e-3),
         "config": {"workload": workload_name(a), "batch": B, "replay_rows": a.replay_rows, "optimizer": "Adam",
                    "parallelism": f"{world} learner(s), one replay shard each",
-                   "launch": ("one CUDA graph per update" if (world == 1 or not a.dynamic_exchange) else
+                   "launch": ("one CUDA graph per update" if (world == 1 or a.static_exchange) else
                               "two CUDA graphs per update around eager NCCL exchanges") if graph else "eager",
                    "net": a.net, "adam": a.adam, "online_forwards": "one pass over [s; s']" if a.fuse_forwards else "split (as the reference)",
                    "exchange": None if world == 1 else "per update: all-gather of shard sums, all-to-all of sampled rows, "
