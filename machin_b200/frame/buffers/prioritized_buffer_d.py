@@ -25,6 +25,19 @@ from .buffer import Buffer
 from .prioritized_buffer import PrioritizedBuffer
 
 
+def compounding_default_weights(max_leaf, n: int, epsilon: float, alpha: float) -> np.ndarray:
+    """Leaf weights the reference assigns to an episode stored WITHOUT priorities in the distributed
+    buffer (prioritized_buffer_d.py:123-131): one ``update_leaf(normalize(get_leaf_max()))`` per transition,
+    with the running maximum re-read every time -- it is already normalised, gets normalised again and can
+    grow inside the episode.  ``max_leaf`` keeps its dtype (np.float32 after a float32 write-back)."""
+    cur, weights = max_leaf, []
+    for _ in range(n):
+        w = (np.abs(cur) + epsilon) ** alpha
+        weights.append(w)
+        cur = max(w, cur)              # update_leaf: self.max_leaf = max(weight, self.max_leaf)
+    return np.array(weights)
+
+
 class DistributedPrioritizedBuffer(PrioritizedBuffer):
     def __init__(self, buffer_name: str, group, buffer_size: int = 1000000, epsilon: float = 1e-2,
                  alpha: float = 0.6, beta: float = 0.4, beta_increment_per_sampling: float = 0.001,
@@ -157,13 +170,7 @@ class DistributedPrioritizedBuffer(PrioritizedBuffer):
         if priorities is None:
             # one update_leaf per transition with normalize(get_leaf_max()) re-read every time (:123-131):
             # the (already normalised) maximum is normalised again and can grow inside the episode
-            cur = self.wt_tree.get_leaf_max()
-            weights = []
-            for _ in positions:
-                w = self._normalize_priority(cur)
-                weights.append(w)
-                cur = max(w, cur)
-            weights = np.array(weights)
+            weights = compounding_default_weights(self.wt_tree.get_leaf_max(), len(positions), self.epsilon, self.alpha)
         else:
             weights = np.array([self._normalize_priority(p) for p in priorities])
         self.wt_tree.update_leaf_batch(weights, positions)

@@ -452,10 +452,38 @@ def gen_buffer():
     np.savez_compressed(os.path.join(OUT, "ref_buffer.npz"), **out)
 
 
+# --------------------------------------------------------------------------- sharded PER: default priorities
+def gen_per_d():
+    """DistributedPrioritizedBuffer.store_episode without priorities (prioritized_buffer_d.py:123-131): one
+    update_leaf per transition with normalize(get_leaf_max()) re-read every time -- the maximum compounds
+    inside an episode -- plus the version ("taint") counters (:131)."""
+    from machin.frame.buffers import DistributedPrioritizedBuffer
+
+    out = {}
+    rng = np.random.RandomState(8)
+    buf = DistributedPrioritizedBuffer("buffer", FakeGroup(), 40)
+    trees, versions, lens = [], [], []
+    for step, n in enumerate((4, 7, 3, 12, 9, 20)):
+        buf.store_episode(_episode(n, 2, rng))
+        lens.append(n)
+        trees.append(buf.wt_tree.weights.copy())
+        versions.append(buf.buffer_version_table.astype(np.int64).copy())
+        if step == 1:   # a float32 write-back in between changes the dtype of max_leaf (np.float32)
+            idx = np.array([0, 3, 5], dtype=np.int64)
+            pri = np.array([2.5, 0.1, 7.25], dtype=np.float32)
+            buf._update_priority_service(pri, idx, buf.buffer_version_table[idx])
+            out["wb_idx"], out["wb_pri"] = idx, pri
+            out["tree_after_wb"] = buf.wt_tree.weights.copy()
+    out["lens"] = np.array(lens)
+    out["trees"] = np.stack(trees)
+    out["versions"] = np.stack(versions)
+    np.savez_compressed(os.path.join(OUT, "ref_per_d.npz"), **out)
+
+
 if __name__ == "__main__":
     ref_shim.load()
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["tree", "per", "td", "vtrace", "gae", "buffer"]
+    which = sys.argv[1:] or ["tree", "per", "td", "vtrace", "gae", "buffer", "per_d"]
     for name in which:
         globals()["gen_" + name]()
         print("wrote", name)

@@ -111,3 +111,29 @@ def test_episode_book_vs_reference_buffer(tag):
         assert got == [int(k) for k in g[f"{tag}_pick_random"][i] if k >= 0]
     with pytest.raises(ValueError, match="Failed to store episode"):
         book.assign(cap + 1)
+
+
+def test_distributed_default_priorities_vs_reference():
+    """Compounding default priorities + taint counters of the sharded buffer against the unmodified reference
+    (tests/golden/ref_per_d.npz; prioritized_buffer_d.py:123-137, 282-291), replayed on the oracle tree."""
+    import numpy as np
+    from conftest import GOLDEN
+    from machin_b200.frame.buffers import EpisodeBook
+    from machin_b200.frame.buffers.prioritized_buffer_d import compounding_default_weights
+    from oracle import per as oper
+    from oracle.sumtree import OracleTree
+    g = np.load(os.path.join(GOLDEN, "ref_per_d.npz"))
+    cap = g["versions"].shape[1]
+    tree, book, version = OracleTree(cap), EpisodeBook(cap), np.zeros(cap, dtype=np.int64)
+    for step, n in enumerate(g["lens"]):
+        _, pos = book.assign(int(n))
+        book.record(pos)
+        w = compounding_default_weights(tree.get_leaf_max(), int(n), 1e-2, 0.6)
+        tree.update_leaf_batch(w, pos)
+        version[pos] += 1
+        assert np.array_equal(tree.weights, g["trees"][step]), step
+        assert np.array_equal(version, g["versions"][step]), step
+        if step == 1:
+            tree.update_leaf_batch(oper.normalize_priority(g["wb_pri"]), g["wb_idx"])
+            assert np.array_equal(tree.weights, g["tree_after_wb"])
+            assert isinstance(tree.get_leaf_max(), np.float32)      # the float32 write-back now owns max_leaf
