@@ -1,0 +1,99 @@
+"""CPU: host-side logic of the path -- Transition validation (mirrors the cases of the reference's
+test/frame/test_transition.py), row layout properties, shard apportioning (prioritized_buffer_d.py:229-234),
+safe_call argument routing (algorithms/utils.py:52-161)."""
+import numpy as np
+import pytest
+import torch as t
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from machin_b200.frame.buffers.device_ring import Field, layout
+from machin_b200.frame.transition import Transition
+from machin_b200.parallel.exchange import shard_sample_sizes
+from oracle import per as oper
+
+
+def _tr(**kw):
+    base = dict(state={"s": t.zeros(1, 3)}, action={"a": t.zeros(1, 2)}, next_state={"s": t.zeros(1, 3)},
+                reward=1.0, terminal=False)
+    base.update(kw)
+    return base
+
+
+def test_transition_surface():
+    tr = Transition(**_tr(extra=5, another="x"))
+    assert tr.major_attr == ["state", "action", "next_state"] and tr.sub_attr == ["reward", "terminal"]
+    assert tr.custom_attr == ["another", "extra"] and len(tr) == 7
+    assert tr.has_keys(["state", "extra"]) and not tr.has_keys(["nope"])
+    assert tr["reward"] == 1.0 and tr.extra == 5
+    assert [k for k, _ in tr.items()] == tr.keys()
+    tr["reward"] = 2.0
+    assert tr["reward"] == 2.0
+    with pytest.raises(RuntimeError, match="dynamically set"):
+        tr["new_key"] = 1
+    assert tr.to("cpu") is tr
+    grad = t.zeros(1, 3, requires_grad=True) * 2
+    assert not Transition(**_tr(state={"s": grad}))["state"]["s"].requires_grad     # detached, like :150-169
+    assert Transition(**_tr(reward=t.ones(1, 1), terminal=t.zeros(1, 1, dtype=t.bool)))["reward"].shape == (1, 1)
+
+
+@pytest.mark.parametrize("bad,match", [
+    (dict(state={"s": t.zeros(2, 3)}, action={"a": t.zeros(2, 2)}, next_state={"s": t.zeros(2, 3)}), "must be 1|scalar, but batch size"),
+    (dict(state={"s": t.zeros(1, 3)}, action={"a": t.zeros(2, 2)}), "invalid batch size"),
+    (dict(state={"s": t.tensor(3.0)}), "invalid tensor"),          # 0-dim tensor (a bare float has no .detach in the reference either)
+    (dict(reward=[1.0]), "requires scalar or tensor"),
+    (dict(reward=t.ones(2, 1)), "invalid batch size"),
+])
+def test_transition_validation(bad, match):
+    with pytest.raises(ValueError, match=match):
+        Transition(**_tr(**bad))
+
+
+def test_transition_terminal_must_be_bool():
+    with pytest.raises(AssertionError):
+        Transition(**_tr(terminal=1))
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.tuples(st.sampled_from([t.float32, t.float64, t.int64, t.bool, t.uint8, t.float16]),
+                          st.integers(1, 400)), min_size=1, max_size=12))
+def test_row_layout_properties(spec):
+    fields = [Field(f"f{i}", "a", None, dt, (n,), "sub") for i, (dt, n) in enumerate(spec)]
+    pitch = layout(fields)
+    assert pitch % 16 == 0 and pitch >= 16
+    spans = sorted((f.offset, f.offset + f.nbytes) for f in fields)
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] <= pitch
+    for f in fields:
+        esz = t.empty((), dtype=f.dtype).element_size()
+        assert f.offset % (16 if f.nbytes >= 16 else esz) == 0
+    assert pitch - sum(f.nbytes for f in fields) < 16 * (len(fields) + 1)       # padding stays small
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.lists(st.floats(0, 1e9, allow_nan=False), min_size=1, max_size=16), st.integers(1, 4096))
+def test_shard_apportioning_matches_oracle_and_covers_batch(sums, batch):
+    ssize, total = shard_sample_sizes(sums, batch)
+    assert (ssize, total) == tuple(oper.shard_sample_sizes(sums, batch))
+    assert total == sum(sums) + 1e-6
+    assert all(0 <= s <= batch + 1 for s in ssize)
+    if sum(sums) > 1e-3:
+        assert batch <= sum(ssize) <= batch + len(sums)        # ceil: at most one extra row per shard
+    assert all(s == 0 for s, w in zip(ssize, sums) if w == 0)
+
+
+def test_safe_call_routes_named_arguments():
+    from machin_b200.frame.algorithms.utils import safe_call
+
+    class Critic(t.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = t.nn.Linear(5, 1)
+
+        def forward(self, state, action, scale=1.0):
+            return self.fc(t.cat([state, action], dim=1)) * scale
+
+    net = Critic()
+    out = safe_call(net, {"state": t.zeros(4, 3), "ignored": 1}, {"action": t.zeros(4, 2)})
+    assert isinstance(out, tuple) and out[0].shape == (4, 1)
+    with pytest.raises(RuntimeError, match="missing required arguments"):
+        safe_call(net, {"state": t.zeros(4, 3)})
