@@ -171,10 +171,6 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- our arm
-class QNet:
-    pass
-
-
 def build_learner(a, device, seed, world=1):
     import torch as t
     from machin_b200.frame.algorithms import DQNApex, DQNPer
@@ -393,9 +389,19 @@ def run_b200(a):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)  # max over ranks
     ms_total, e2e_ms = float(tt[0]), float(tt[1])
-    if rank != 0:
+    def leave():
         if world > 1:
+            if getattr(a, "static_exchange", False):
+                # NCCL collectives captured in a CUDA graph: destroy_process_group() hangs while the graph is
+                # alive (tools/nccl_graph_repro.py) -- flush and leave without the teardown
+                sys.stdout.flush()
+                sys.stderr.flush()
+                dist.barrier()
+                os._exit(0)
             dist.destroy_process_group()
+
+    if rank != 0:
+        leave()
         return
     value = world * B * K / (ms_total * 1e-3)
     e2e = world * B * K / (e2e_ms * 1e-3)
@@ -446,8 +452,7 @@ def run_b200(a):
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
     }
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 if __name__ == "__main__":
