@@ -269,3 +269,43 @@ def test_sorted_small_batch_update_vs_oracle(WT, size):
     with pytest.raises(ValueError, match="out of boundary"):
         tree.check()
     assert np.array_equal(tree.weights, ora.weights)
+
+
+@pytest.mark.parametrize("n", [700, 2048, 4096, 20000])
+def test_masked_update_multi_launch_and_graph_replay(WT, n):
+    """Priority write-back with a validity mask (version filter of the sharded buffer) at the sizes the
+    fixed-shape exchange produces (P * batch entries): single-CTA path, multi-launch sparse/dense path, and
+    the same call replayed from a CUDA graph."""
+    size = 1 << 20
+    rng = np.random.RandomState(n)
+    leaves = rng.exponential(size=size)
+    tree, ora = WT(size), OracleTree(size)
+    tree.update_all_leaves(leaves)
+    ora.update_all_leaves(leaves)
+    idx = rng.randint(0, size, size=n).astype(np.int64)
+    idx[n // 3] = idx[n // 3 + 1]                      # duplicates, one of them possibly masked out
+    valid = (rng.rand(n) < 0.7)
+    w = rng.exponential(size=n).astype(np.float32)
+    d_idx, d_w, d_v = t.from_numpy(idx).cuda(), t.from_numpy(w).cuda(), t.from_numpy(valid).cuda()
+    tree.update_leaf_batch(d_w, d_idx, valid=d_v)
+    ora.update_leaf_batch(w[valid], idx[valid])
+    tree.check()
+    assert np.array_equal(tree.weights, ora.weights)
+    # same launch sequence captured once and replayed with new contents in the static buffers
+    side = t.cuda.Stream()
+    side.wait_stream(t.cuda.current_stream())
+    with t.cuda.stream(side):
+        tree.update_leaf_batch(d_w, d_idx, valid=d_v)
+    t.cuda.current_stream().wait_stream(side)
+    t.cuda.synchronize()
+    g = t.cuda.CUDAGraph()
+    with t.cuda.graph(g):
+        tree.update_leaf_batch(d_w, d_idx, valid=d_v)
+    for rep in range(3):
+        idx2 = rng.randint(0, size, size=n).astype(np.int64)
+        valid2 = rng.rand(n) < 0.5
+        w2 = rng.exponential(size=n).astype(np.float32)
+        d_idx.copy_(t.from_numpy(idx2)); d_w.copy_(t.from_numpy(w2)); d_v.copy_(t.from_numpy(valid2))
+        g.replay()
+        ora.update_leaf_batch(w2[valid2], idx2[valid2])
+        assert np.array_equal(tree.weights, ora.weights), rep
