@@ -1,0 +1,79 @@
+"""torchrun worker for tests/test_gpu_zz_static_exchange.py: the fixed-shape single-graph APEX update
+(NCCL collectives captured) against the dynamic exchange, every member a learner, same seeds."""
+import os
+import sys
+
+import numpy as np
+import torch as t
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+class QNet(t.nn.Module):
+    def __init__(self, s, a, h):
+        super().__init__()
+        self.fc1, self.fc2, self.fc3 = t.nn.Linear(s, h), t.nn.Linear(h, h), t.nn.Linear(h, a)
+
+    def forward(self, state):
+        return self.fc3(t.relu(self.fc2(t.relu(self.fc1(state)))))
+
+
+def flat(m):
+    return t.cat([p.detach().reshape(-1) for p in m.parameters()]).cpu().numpy()
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    t.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=t.device("cuda", local))
+    from machin_b200.frame.algorithms import DQNApex
+    from machin_b200.parallel import ShardGroup
+    S, A, B = 12, 5, 64
+    N = 3000 + 400 * rank
+    group = ShardGroup("group")
+
+    def make():
+        t.manual_seed(0)                                  # identical initial weights on every member
+        q, qt = QNet(S, A, 32).cuda(), QNet(S, A, 32).cuda()
+        learner = DQNApex(q, qt, t.optim.SGD, t.nn.MSELoss(reduction="none"), group, (), batch_size=B,
+                          learning_rate=0.05, discount=0.9, update_rate=0.1, replay_size=4096, learner_group=group)
+        rng = np.random.RandomState(3 + rank)             # a different shard on every member
+        learner.replay_buffer.store_episode_tensors(
+            {"state": {"state": t.from_numpy(rng.randn(N, S).astype(np.float32))},
+             "action": {"action": t.from_numpy(rng.randint(0, A, size=(N, 1)))},
+             "next_state": {"state": t.from_numpy(rng.randn(N, S).astype(np.float32))}},
+            {"reward": t.from_numpy(rng.randn(N, 1).astype(np.float32)), "terminal": t.from_numpy(rng.rand(N, 1) < 0.1)},
+            priorities=rng.exponential(size=N))
+        return learner
+
+    a, b = make(), make()
+    b.enable_cuda_graph(static_exchange=True)
+    assert np.array_equal(a.replay_buffer.wt_tree.weights, b.replay_buffer.wt_tree.weights)
+    for step in range(6):
+        np.random.seed(100 * rank + step)
+        la = a.update_device().item()
+        np.random.seed(100 * rank + step)
+        lb = b.update_device().item()
+        assert abs(la - lb) <= 1e-5 * max(1.0, abs(la)), (step, la, lb)
+        np.testing.assert_allclose(b.replay_buffer.wt_tree.weights, a.replay_buffer.wt_tree.weights, rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(flat(b.qnet), flat(a.qnet), rtol=1e-4, atol=1e-6)
+        assert a.replay_buffer.curr_beta == b.replay_buffer.curr_beta
+    # every member holds the same weights after averaged gradients
+    w = t.from_numpy(flat(b.qnet)).cuda()
+    ws = [t.empty_like(w) for _ in range(world)]
+    dist.all_gather(ws, w)
+    assert all(t.equal(ws[0], x) for x in ws)
+    t.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        print("static ok")
+    sys.stdout.flush()
+    # destroy_process_group() blocks while a graph holding captured NCCL work is alive: leave directly
+    os._exit(0)
+
+
+if __name__ == "__main__":
+    main()
