@@ -480,10 +480,111 @@ def gen_per_d():
     np.savez_compressed(os.path.join(OUT, "ref_per_d.npz"), **out)
 
 
+# --------------------------------------------------------------------------- RNN (sequence) buffers
+def _indexed_episode(n, state_dim, rng, counter):
+    ep = _episode(n, state_dim, rng)
+    for i, tr in enumerate(ep):
+        tr["index"] = counter + i
+    return ep
+
+
+def gen_rnn():
+    """RNNBuffer window selection (rnn_buffers.py:78-167) and RNNPrioritizedBuffer store / sample
+    (:343-413), driven through the unmodified reference."""
+    from machin.frame.buffers import PrioritizedBuffer
+    from machin.frame.buffers.rnn_buffers import RNNBuffer, RNNPrioritizedBuffer
+
+    out = {}
+    # ---- uniform: which windows the three sample methods return, after every store
+    for tag, cap, L, lens in (("a", 30, 3, [5, 2, 7, 3, 9, 4, 1, 6, 8, 3]), ("b", 200, 5, [12, 4, 30, 5, 17, 9, 41, 6, 25, 3, 50, 14])):
+        buf = RNNBuffer(sample_length=L, buffer_size=cap)
+        rng = np.random.RandomState(11)
+        counter = 0
+        uniq, rand, allw, nall = [], [], [], []
+        for n in lens:
+            buf.store_episode(_indexed_episode(n, 2, rng, counter))
+            counter += n
+            random.seed(5)
+            bs, batch = buf.sample_method_random_unique(4)
+            uniq.append(np.array([tr["index"] for tr in batch] + [-1] * (4 * L - bs * L), dtype=np.int64))
+            random.seed(6)
+            bs, batch = buf.sample_method_random(4)
+            rand.append(np.array([tr["index"] for tr in batch] + [-1] * (4 * L - bs * L), dtype=np.int64))
+            bs, batch = buf.sample_method_all(0)
+            nall.append(bs)
+            allw.append(np.array([tr["index"] for tr in batch], dtype=np.int64))
+        out[f"u{tag}_cap"], out[f"u{tag}_L"] = np.int64(cap), np.int64(L)
+        out[f"u{tag}_lens"] = np.array(lens, dtype=np.int64)
+        out[f"u{tag}_unique"], out[f"u{tag}_random"] = np.stack(uniq), np.stack(rand)
+        out[f"u{tag}_all_count"] = np.array(nall, dtype=np.int64)
+        for k, a in enumerate(allw):
+            out[f"u{tag}_all{k}"] = a
+        # a concatenated batch: window axis after the batch axis (:169-182)
+        random.seed(9)
+        bs, (state, reward, idx) = buf.sample_batch(3, sample_method="random_unique", sample_attrs=["state", "reward", "index"],
+                                                    additional_concat_custom_attrs=["index"])
+        out[f"u{tag}_batch_state"] = state["state"].numpy()
+        out[f"u{tag}_batch_reward"] = reward.numpy()
+        out[f"u{tag}_batch_index"] = idx.numpy()
+    # ---- prioritized: leaf weights after each store (given / default priorities), draws, write-back
+    for tag, cap, L, lens in (("a", 64, 4, [10, 3, 12, 8, 2, 9, 20]), ("b", 40, 3, [10, 10, 12, 8, 9, 11, 5, 15])):
+        # RNNPrioritizedBuffer(...) itself raises TypeError in the reference (RNNBuffer.__init__ forwards
+        # storage=None to PrioritizedBuffer.__init__, which passes storage again, rnn_buffers.py:71 /
+        # prioritized_buffer.py:269): initialise the instance through the base initialiser and set the two
+        # attributes RNNBuffer.__init__ would have set; every method under test is the unmodified one
+        buf = RNNPrioritizedBuffer.__new__(RNNPrioritizedBuffer)
+        PrioritizedBuffer.__init__(buf, buffer_size=cap)
+        buf.sample_length, buf.sample_dimension = L, 1
+        rng = np.random.RandomState(12)
+        counter = 0
+        trees, pri_in, states = [], [], []
+        for k, n in enumerate(lens):
+            ep = _indexed_episode(n, 3, rng, counter)
+            states.append(np.concatenate([tr["state"]["state"].numpy() for tr in ep]))
+            counter += n
+            if k % 3 == 2:
+                buf.store_episode(ep)                       # default priority
+                pri_in.append(np.full(n, -1.0))
+            else:
+                pri = rng.exponential(size=n)
+                pri_in.append(pri.copy())
+                buf.store_episode(ep, priorities=pri)       # ndarray: the reference slices / zeroes it
+            trees.append(buf.wt_tree.weights.copy())
+            if k == 3:                                      # float32 write-back: max_leaf becomes np.float32
+                seed_all(21)
+                n_s, _, index, isw = buf.sample_batch(6, sample_attrs=["index"], additional_concat_custom_attrs=["index"])
+                new_p = rng.exponential(size=n_s).astype(np.float32) * 5
+                buf.update_priority(new_p, index)
+                out[f"p{tag}_mid_index"], out[f"p{tag}_mid_newp"] = np.asarray(index), new_p
+                out[f"p{tag}_mid_tree"] = buf.wt_tree.weights.copy()
+        out[f"p{tag}_cap"], out[f"p{tag}_L"] = np.int64(cap), np.int64(L)
+        out[f"p{tag}_lens"] = np.array(lens, dtype=np.int64)
+        out[f"p{tag}_pri"] = np.concatenate(pri_in)
+        out[f"p{tag}_states"] = np.concatenate(states)
+        out[f"p{tag}_trees"] = np.stack(trees)
+        seed_all(7)
+        for step, b in enumerate((8, 3, 16)):
+            st = np.random.get_state()
+            out[f"p{tag}_s{step}_uniform"] = np.random.uniform(size=b)
+            np.random.set_state(st)
+            out[f"p{tag}_s{step}_beta"] = np.float64(buf.curr_beta)
+            n_s, (state, reward, idx), index, isw = buf.sample_batch(
+                b, sample_attrs=["state", "reward", "index"], additional_concat_custom_attrs=["index"])
+            out[f"p{tag}_s{step}_index"], out[f"p{tag}_s{step}_isw"] = np.asarray(index), np.asarray(isw)
+            out[f"p{tag}_s{step}_state"] = state["state"].numpy()
+            out[f"p{tag}_s{step}_reward"] = reward.numpy()
+            out[f"p{tag}_s{step}_seq"] = idx.numpy()
+            new_p = rng.exponential(size=n_s).astype(np.float32)
+            buf.update_priority(new_p, index)
+            out[f"p{tag}_s{step}_newp"] = new_p
+            out[f"p{tag}_s{step}_tree_after"] = buf.wt_tree.weights.copy()
+    np.savez_compressed(os.path.join(OUT, "ref_rnn.npz"), **out)
+
+
 if __name__ == "__main__":
     ref_shim.load()
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["tree", "per", "td", "vtrace", "gae", "buffer", "per_d"]
+    which = sys.argv[1:] or ["tree", "per", "td", "vtrace", "gae", "buffer", "per_d", "rnn"]
     for name in which:
         globals()["gen_" + name]()
         print("wrote", name)
