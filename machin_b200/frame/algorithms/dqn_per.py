@@ -75,6 +75,12 @@ class DQNPer(TorchFramework):
         # opt-in: evaluate Q(s) and Q(s') of the ONLINE net in one forward over [s; s'] (they share weights;
         # only valid for row-wise networks, i.e. no BatchNorm/Dropout): 3 fewer GEMM + epilogue launches
         self.fuse_online_forwards = False
+        # opt-in: the priority write-back (one small CTA, ~20 us) only feeds the NEXT draw, so it can run on a
+        # second stream beside backward + optimizer + target update; in a captured update this becomes a
+        # parallel branch of the graph.  Same kernels, same inputs -> same trajectory.  Single-process buffers only
+        # (the sharded write-back is a collective and must stay ordered with the other NCCL calls).
+        self.overlap_priority_update = False
+        self._side_stream = None
         super().__init__()
 
     # ------------------------------------------------------------------ properties / acting (dqn.py:213-331)
@@ -296,7 +302,17 @@ class DQNPer(TorchFramework):
         else:
             action_value = q_value.gather(dim=1, index=act.to(dtype=t.long))
             value_loss = (self.criterion(action_value, td["y"]) * d_isw.view(batch_size, 1)).mean()
-        self.replay_buffer.update_priority(td["abs_error"], d_index)
+        forked = None
+        if self.overlap_priority_update and type(self.replay_buffer) is PrioritizedBuffer:
+            dev = self.replay_buffer.buffer_device
+            if self._side_stream is None:
+                self._side_stream = t.cuda.Stream(device=dev)
+            forked = (t.cuda.current_stream(dev), self._side_stream)
+            forked[1].wait_stream(forked[0])
+            with t.cuda.stream(forked[1]):
+                self.replay_buffer.update_priority(td["abs_error"], d_index)
+        else:
+            self.replay_buffer.update_priority(td["abs_error"], d_index)
         if update_value:
             self.qnet_optim.zero_grad(set_to_none=True)
             if self._fused_mse:
@@ -314,6 +330,8 @@ class DQNPer(TorchFramework):
                 self._update_counter += 1
                 if self._update_counter % self.update_steps == 0:
                     hard_update(self.qnet_target, self.qnet)
+        if forked is not None:
+            forked[0].wait_stream(forked[1])     # join before the next draw reads the tree (td / d_index still alive here)
         self.qnet.eval()
         return value_loss
 
