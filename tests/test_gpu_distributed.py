@@ -1,12 +1,11 @@
 """GPU, >= 2 devices: sharded prioritized replay over NCCL (torchrun, one process per GPU)."""
 import os
-import subprocess
 import sys
 
 import pytest
 import torch as t
 
-from conftest import ROOT
+from conftest import ROOT, run_group
 
 pytestmark = pytest.mark.gpu
 
@@ -17,5 +16,5 @@ def test_sharded_buffer_over_nccl(world):
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29611 + world), os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    out = run_group(cmd, timeout=600)
     assert out.returncode == 0 and "dist ok" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

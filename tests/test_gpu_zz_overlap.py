@@ -4,7 +4,9 @@ import numpy as np
 import pytest
 import torch as t
 
-pytestmark = pytest.mark.gpu
+from conftest import first_hardware_run_pending
+
+pytestmark = [pytest.mark.gpu, first_hardware_run_pending]
 
 
 class QNet(t.nn.Module):
