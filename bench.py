@@ -60,6 +60,8 @@ def parse():
                         "(a stuck collective must not hold the box)")
     p.add_argument("--fuse-forwards", action="store_true", help="one online forward over [s; s'] instead of two passes like the "
                    "reference (measured: no gain, 0.204 vs 0.205 ms/update)")
+    p.add_argument("--parallel-forwards", action="store_true",
+                   help="N = 1, opt-in: the two no-grad forwards on side streams (parallel graph branches)")
     p.add_argument("--overlap-update", action="store_true",
                    help="N = 1, opt-in: priority write-back on a parallel graph branch beside backward + optimizer")
     p.add_argument("--adam", default="fused", choices=["fused", "torch"], help="FusedAdam (csrc/mlp.cu) or torch.optim.Adam(fused=True)")
@@ -221,6 +223,7 @@ def build_learner(a, device, seed, world=1):
         learner.use_fused_program = a.net == "fused-program"
         learner.fuse_online_forwards = a.fuse_forwards
         learner.overlap_priority_update = a.overlap_update and world == 1
+        learner.parallel_forwards = a.parallel_forwards and world == 1
     gen = t.Generator(device=device).manual_seed(seed)
     chunk = 1_000_000
     done = 0
@@ -462,7 +465,7 @@ def run_b200(a):
                    "launch": ("one CUDA graph per update" if (world == 1 or a.static_exchange) else
                               "two CUDA graphs per update around eager NCCL exchanges") if graph else "eager",
                    "net": a.net, "adam": a.adam, "priority_update": "parallel graph branch" if (a.overlap_update and world == 1) else "in line",
-                   "online_forwards": "one pass over [s; s']" if a.fuse_forwards else "split (as the reference)",
+                   "online_forwards": "one pass over [s; s']" if a.fuse_forwards else ("split, no-grad ones on parallel branches" if (a.parallel_forwards and world == 1) else "split (as the reference)"),
                    "exchange": None if world == 1 else "per update: all-gather of shard sums, all-to-all of sampled rows, "
                                "all-to-all of priority write-backs, all-reduce of gradients, broadcast of weights (NCCL)",
                    "l2": "inputs larger than L2: 268 MB tree + 6.9 GB ring, randomly addressed every step"},

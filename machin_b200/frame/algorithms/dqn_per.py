@@ -81,6 +81,10 @@ class DQNPer(TorchFramework):
         # (the sharded write-back is a collective and must stay ordered with the other NCCL calls).
         self.overlap_priority_update = False
         self._side_stream = None
+        # opt-in: the three forwards of an update (online Q(s'), target Q(s'), online Q(s)) are independent and each
+        # is a chain of sub-10-us kernels; run the two no-grad ones on side streams (parallel graph branches)
+        self.parallel_forwards = False
+        self._fwd_streams = None
         super().__init__()
 
     # ------------------------------------------------------------------ properties / acting (dqn.py:213-331)
@@ -288,6 +292,20 @@ class DQNPer(TorchFramework):
             q_value, next_q_value = both[:batch_size], both[batch_size:].detach()
             with t.no_grad():
                 target_next_q_value = self._criticize(next_state, True)
+        elif self.parallel_forwards:
+            dev = reward.device
+            if self._fwd_streams is None:
+                self._fwd_streams = (t.cuda.Stream(device=dev), t.cuda.Stream(device=dev))
+            cur = t.cuda.current_stream(dev)
+            outs = []
+            for side, use_target in zip(self._fwd_streams, (False, True)):
+                side.wait_stream(cur)
+                with t.cuda.stream(side), t.no_grad():
+                    outs.append(self._criticize(next_state, use_target))
+            q_value = self._criticize(state)
+            for side in self._fwd_streams:
+                cur.wait_stream(side)
+            next_q_value, target_next_q_value = outs    # (kept alive until after the join; freed on `cur`'s side)
         else:
             with t.no_grad():
                 next_q_value = self._criticize(next_state)

@@ -1,5 +1,6 @@
-"""GPU: the opt-in parallel-branch priority write-back (DQNPer.overlap_priority_update) must not change the
-trajectory -- eager and captured."""
+"""GPU: the opt-in stream-level parallelism of one update (DQNPer.overlap_priority_update: priority write-back
+beside backward + optimizer; DQNPer.parallel_forwards: the two no-grad forwards beside the online one) must not
+change the trajectory -- eager and captured."""
 import numpy as np
 import pytest
 import torch as t
@@ -22,8 +23,10 @@ def _flat(m):
     return t.cat([p.detach().reshape(-1) for p in m.parameters()]).cpu().numpy()
 
 
+@pytest.mark.parametrize("flags", [("overlap_priority_update",), ("parallel_forwards",),
+                                   ("overlap_priority_update", "parallel_forwards")])
 @pytest.mark.parametrize("graph", [False, True])
-def test_overlapped_priority_update_same_trajectory(graph):
+def test_stream_parallel_update_same_trajectory(graph, flags):
     from machin_b200.frame.algorithms import DQNPer
     from machin_b200.model import FusedAdam
     S, A, N, B = 12, 5, 3000, 64
@@ -40,7 +43,9 @@ def test_overlapped_priority_update_same_trajectory(graph):
              "next_state": {"state": t.from_numpy(rng.randn(N, S).astype(np.float32))}},
             {"reward": t.from_numpy(rng.randn(N, 1).astype(np.float32)), "terminal": t.from_numpy(rng.rand(N, 1) < 0.1)},
             priorities=rng.exponential(size=N))
-        learner.overlap_priority_update = overlap
+        for f in flags:
+            assert hasattr(learner, f)
+            setattr(learner, f, overlap)
         if graph:
             learner.enable_cuda_graph()
         return learner
