@@ -51,6 +51,7 @@ struct mb_tree {
     TreeState *h_state;  // pinned mirror for mb_tree_stats / mb_tree_check
     int coop_blocks;     // co-resident CTAs for the cooperative update kernel
     int gen;             // update-launch generation counter
+    int sorted_cluster;  // MB_SORTED_CLUSTER=1: small sorted updates on a cluster of 8 CTAs (opt-in until measured)
     int force_generic;   // MB_FORCE_GENERIC_UPDATE=1: single-CTA PER draw instead of the cluster kernel (A/B timing)
 };
 
@@ -479,6 +480,158 @@ __global__ void __launch_bounds__(kSortedN) tree_update_sorted(TreeDev t, const 
     }
 }
 
+// ---- the same walk spread over a thread-block cluster (opt-in: MB_SORTED_CLUSTER=1) ---------------------
+// tree_update_sorted is bound by ONE SM's load/store unit: ~8.7 k scattered 8-byte loads (stored siblings) and
+// as many scattered stores for 512 entries of a 2^24-leaf tree, ~1 sector request per cycle.  Here the tree is
+// cut at level ls = levels - 3 into 8 subtrees, CTA r of a cluster of 8 owns the entries whose leaf index lies
+// in subtree r (a contiguous run of the sorted batch; entries of different subtrees never meet below level ls),
+// runs the same merge walk for levels 0..ls-1 on its own SM -- prefetch and write-out now use 8 load/store
+// units -- and publishes the value of its subtree root (the stored one if it has no entry) in shared memory;
+// after cluster.sync() the leader reads the 8 roots over DSMEM and computes the 7 nodes above them.  Parents
+// stay fl(left + right) of the current children: bit-identical to the single-CTA kernel.
+constexpr int kClusterBits = 3;
+constexpr int kClusterCtas = 1 << kClusterBits;
+
+template <typename WT>
+__global__ void __launch_bounds__(kSortedN) tree_update_sorted_cluster(TreeDev t, const int64_t *__restrict__ idx,
+                                                                       const WT *__restrict__ w,
+                                                                       const uint8_t *__restrict__ valid, int n,
+                                                                       Normalize nz, int gen) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char dyn[];
+    double *park = reinterpret_cast<double *>(dyn);
+    __shared__ double s_val[kSortedN];
+    __shared__ unsigned s_key[kSortedN];
+    __shared__ double s_w[kSortedN];
+    __shared__ short s_hb[kSortedN];
+    __shared__ short s_next[kSortedN];
+    __shared__ int s_warp[kSortedN / 32];
+    __shared__ double s_red[kSortedN / 32];
+    __shared__ double s_top;                          // value of this CTA's subtree root (level ls)
+    __shared__ double s_max;                          // largest new leaf weight among this CTA's entries
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned rank = cluster.block_rank();
+    const int levels = t.depth - 1;
+    const int ls = levels - kClusterBits;
+    const bool in = tid < n;
+    const int64_t k = in ? idx[tid] : 0;
+    const bool oob = in && (k < 0 || k >= t.size);
+    const bool unsorted = in && tid > 0 && idx[tid - 1] > k;
+    // every CTA looks at the whole batch, so all of them take the same branch (no cluster barrier is skipped)
+    const int any_oob = __syncthreads_or(oob ? 1 : 0);
+    const int generic = __syncthreads_or((unsorted || valid != nullptr) ? 1 : 0);
+    if (any_oob && !generic) {
+        if (rank == 0 && tid == 0) {
+            t.st->err = MB_ERR_INDEX_OOB;
+            t.st->err_gen = gen;
+        }
+        return;
+    }
+    if (generic) {   // CTA 0 alone: blockIdx.x == 0 and gridDim.x * blockDim.x >= n, so the body sees one CTA
+        if (rank == 0) tree_update_body<WT, false>(t, idx, w, valid, n, nz, gen);
+        return;
+    }
+    const bool mine = in && (unsigned)(k >> ls) == rank;
+    const double x = mine ? normalized_weight(w[tid], nz) : -INFINITY;
+    const bool winner = mine && (tid == n - 1 || idx[tid + 1] != k);
+    double mx = mb::warp_max(x);
+    const unsigned ballot = __ballot_sync(0xffffffffu, winner);
+    if (lane == 0) {
+        s_warp[wid] = __popc(ballot);
+        s_red[wid] = mx;
+    }
+    __syncthreads();
+    int base = 0, m = 0;
+    for (int j = 0; j < (int)(blockDim.x >> 5); ++j) {
+        if (j < wid) base += s_warp[j];
+        m += s_warp[j];
+    }
+    if (tid == 0) {
+        for (int j = 1; j < (int)(blockDim.x >> 5); ++j) mx = fmax(mx, s_red[j]);
+        s_max = mx;
+    }
+    if (winner) {
+        const int pos = base + __popc(ballot & ((1u << lane) - 1u));
+        s_key[pos] = (unsigned)k;
+        s_w[pos] = x;
+    }
+    __syncthreads();
+    bool alive = tid < m;
+    unsigned key = 0;
+    double val = 0.0;
+    int hb = -1;
+    if (alive) {
+        key = s_key[tid];
+        val = s_w[tid];
+        hb = tid == 0 ? ls : 31 - __clz(s_key[tid - 1] ^ key);      // < ls for tid > 0: same subtree
+        s_hb[tid] = (short)hb;
+        s_next[tid] = (short)(tid + 1);
+        const int lim = hb < ls ? hb : ls - 1;
+        double pre[kSortedLevels];
+#pragma unroll
+        for (int l = 0; l < kSortedLevels; ++l)
+            if (l <= lim) pre[l] = __ldcg(t.W + level_off(t, l) + ((key >> l) ^ 1u));
+#pragma unroll
+        for (int l = 0; l < kSortedLevels; ++l)
+            if (l <= lim) park[l * kSortedN + tid] = pre[l];
+    }
+    const double leaf_val = val;
+    unsigned wrote = 0;
+    __syncthreads();
+#pragma unroll 1
+    for (int l = 0; l < ls; ++l) {
+        if (alive && hb == l) {
+            s_val[tid] = val;
+            alive = false;
+        }
+        __syncthreads();
+        if (alive) {
+            const int j = s_next[tid];
+            double other;
+            if (j < m && s_hb[j] == l) {
+                other = s_val[j];
+                s_next[tid] = s_next[j];
+            } else {
+                other = park[l * kSortedN + tid];
+            }
+            val = val + other;
+            park[l * kSortedN + tid] = val;
+            wrote |= 1u << l;
+        }
+    }
+    if (tid == 0) s_top = m > 0 ? val : __ldcg(t.W + level_off(t, ls) + rank);
+    if (tid < m) {
+        t.W[key] = leaf_val;
+        for (int l = 0; l < ls; ++l)
+            if (wrote & (1u << l)) t.W[level_off(t, l + 1) + (key >> (l + 1))] = park[l * kSortedN + tid];
+    }
+    cluster.sync();
+    if (rank == 0 && tid == 0) {
+        double v[kClusterCtas], bm = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < kClusterCtas; ++r) {
+            v[r] = *cluster.map_shared_rank(&s_top, r);
+            bm = fmax(bm, *cluster.map_shared_rank(&s_max, r));
+        }
+        int cnt = kClusterCtas;
+#pragma unroll
+        for (int b = 1; b <= kClusterBits; ++b) {
+            cnt >>= 1;
+#pragma unroll
+            for (int j = 0; j < kClusterCtas / 2; ++j)
+                if (j < cnt) {
+                    v[j] = v[2 * j] + v[2 * j + 1];
+                    t.W[level_off(t, ls + b) + j] = v[j];
+                }
+        }
+        if (bm > -INFINITY && !(t.st->max_leaf > bm)) {
+            t.st->max_leaf = bm;
+            t.st->max_is_f32 = sizeof(WT) == 4 ? 1 : 0;
+        }
+    }
+    cluster.sync();   // nobody exits (and frees its shared memory) while the leader may still read it
+}
+
 // ---- large batches: the same algorithm as separate launches, sparse at the bottom, dense at the top ----
 // The cooperative kernel above makes every entry recompute its ancestor on EVERY level: above the level
 // where the tree has fewer nodes than the batch has entries, a million threads hammer a handful of
@@ -712,6 +865,8 @@ int mb_tree_create(int64_t size, int device, mb_tree **out) {
     {
         const char *e = getenv("MB_FORCE_GENERIC_UPDATE");
         t->force_generic = (e && e[0] == '1') ? 1 : 0;
+        const char *c = getenv("MB_SORTED_CLUSTER");
+        t->sorted_cluster = (c && c[0] == '1') ? 1 : 0;
     }
     t->dev.W = nullptr;
     t->dev.owner = nullptr;
@@ -730,6 +885,8 @@ int mb_tree_create(int64_t size, int device, mb_tree **out) {
     tree_state_reset<<<1, 1>>>(t->dev.st, 0.0);
     MB_CUDA(cudaFuncSetAttribute(tree_update_sorted<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     MB_CUDA(cudaFuncSetAttribute(tree_update_sorted<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    MB_CUDA(cudaFuncSetAttribute(tree_update_sorted_cluster<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    MB_CUDA(cudaFuncSetAttribute(tree_update_sorted_cluster<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     int per_sm = 0;
     MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_update_kernel<double, true>, 1024, 0));
     int sms = mb::kNumSMs;
@@ -856,6 +1013,27 @@ static int launch_update(mb_tree *t, const int64_t *d_index, const void *d_weigh
     if (n <= kSortedN && !t->force_generic) {
         const int threads = (int)(((n + 31) / 32) * 32);
         const size_t dyn = sizeof(double) * (size_t)kSortedN * (size_t)(t->dev.depth - 1);
+        if (t->sorted_cluster && n > 64 && t->dev.depth - 1 >= kClusterBits + 4) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(kClusterCtas);
+            cfg.blockDim = dim3(threads);
+            cfg.dynamicSmemBytes = dyn;
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = kClusterCtas;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            const int ni = (int)n;
+            if (dtype == MB_F32)
+                MB_CUDA(cudaLaunchKernelEx(&cfg, tree_update_sorted_cluster<float>, t->dev, d_index, (const float *)d_weight, d_valid, ni, nz, gen));
+            else
+                MB_CUDA(cudaLaunchKernelEx(&cfg, tree_update_sorted_cluster<double>, t->dev, d_index, (const double *)d_weight, d_valid, ni, nz, gen));
+            mb::count_launch(1);
+            return MB_OK;
+        }
         if (dtype == MB_F32)
             tree_update_sorted<float><<<1, threads, dyn, s>>>(t->dev, d_index, (const float *)d_weight, d_valid, (int)n, nz, gen);
         else
