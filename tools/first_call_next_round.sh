@@ -1,0 +1,39 @@
+#!/bin/bash
+# First GPU call of the next round (one GPU, ~12 minutes): everything written after round 1's GPU budget ran
+# out -- run the pending tests, then A/B the opt-in variants against the default on the bench workload.
+#   gpurun --timeout 1200 -- 'bash tools/first_call_next_round.sh'
+# Results land in gpurun_out/next_*.  Nothing here changes clocks or kills by pattern.
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -q -rxXs -p no:cacheprovider > gpurun_out/next_pytest.txt 2>&1
+tail -25 gpurun_out/next_pytest.txt
+run() {   # name, env, flags
+    env $2 timeout 240 python bench.py --steps 3000 --warmup 50 --no-cpu-baseline $3 \
+        > gpurun_out/next_bench_$1.json 2> gpurun_out/next_bench_$1.err
+    python - "$1" <<'PY'
+import json, sys
+name = sys.argv[1]
+try:
+    j = json.loads(open(f"gpurun_out/next_bench_{name}.json").read().strip().splitlines()[-1])
+    print(f"{name:28s} {j['ms_per_step']*1e3:8.1f} us/update  value {j['value']:.3e}  e2e {j['e2e']['value']:.3e}  "
+          f"dominant {j['roofline'].get('kernel')} {j['roofline'].get('avg_launch_us')} us")
+except Exception as e:
+    print(name, "FAILED", e)
+PY
+}
+run default            "MB_X=0"               ""
+run overlap_update     "MB_X=0"               "--overlap-update"
+run parallel_forwards  "MB_X=0"               "--parallel-forwards"
+run both               "MB_X=0"               "--overlap-update --parallel-forwards"
+run cluster_update     "MB_SORTED_CLUSTER=1"  ""
+run all                "MB_SORTED_CLUSTER=1"  "--overlap-update --parallel-forwards"
+timeout 300 python tools/microbench.py > gpurun_out/next_microbench_single.json 2>/dev/null
+MB_SORTED_CLUSTER=1 timeout 300 python tools/microbench.py > gpurun_out/next_microbench_cluster.json 2>/dev/null
+python - <<'PY'
+import json
+for v in ("single", "cluster"):
+    try:
+        r = json.load(open(f"gpurun_out/next_microbench_{v}.json"))["results"]
+        print(v, {k: round(x["us"], 2) for k, x in r.items() if k.startswith("tree_update_sorted")})
+    except Exception as e:
+        print(v, "FAILED", e)
+PY

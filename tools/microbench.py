@@ -90,6 +90,17 @@ def main():  # noqa: C901
         byt = (20 + 24 * (D - 1)) * nu
         R[f"tree_update_{nu}"] = {"us": s * 1e6, "Mleaves_per_s": nu / s / 1e6, "alg_bytes_upper": byt,
                                   "GBps": byt / s / 1e9, "frac": byt / s / 1e9 / PEAK}
+    # the learner's write-back: ascending indexes (what the stratified draw produces) -> tree_update_sorted
+    # (or its cluster variant under MB_SORTED_CLUSTER=1)
+    for nu in (512, 256, 128):
+        sets = [(t.sort(t.randint(0, N, (nu,), device=dev))[0], t.rand(nu, device=dev)) for _ in range(16)]
+        mk = lambda iw: (lambda: _lib.check(lib.mb_tree_update_priority(
+            tree.handle, _lib.ptr(iw[0]), _lib.ptr(iw[1]), _lib.MB_F32, None, nu, 1e-2, 0.6, sp())))
+        s = graphed([mk(x) for x in sets])
+        byt = (20 + 24 * (D - 1)) * nu
+        R[f"tree_update_sorted_{nu}"] = {"us": s * 1e6, "alg_bytes_upper": byt, "GBps": byt / s / 1e9,
+                                         "frac": byt / s / 1e9 / PEAK,
+                                         "variant": "cluster" if os.environ.get("MB_SORTED_CLUSTER") == "1" else "single CTA"}
     tree.check()
 
     # ---- fused PER draw
