@@ -330,6 +330,11 @@ def run_b200(a):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries ONE JSON line: keep a private handle to it and point fd 1 at stderr, so that nothing a
+    # library writes to the C-level stdout (NCCL's version banner showed up there in one 2-GPU run) can precede it
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not t.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     t.cuda.set_device(local)
@@ -475,7 +480,7 @@ def run_b200(a):
         "kernels": {KERNELS[k][0]: v for k, v in kern.items()},
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
     }
-    print(json.dumps(line))
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     leave()
 
 
