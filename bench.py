@@ -395,8 +395,10 @@ def run_b200(a):
     e1.record()
     barrier()
     launches = _lib.lib.mb_launch_count() - launches0
-    if learner._graph is not None:   # graph replays do not pass through the C entry points: count per replay
-        launches = K * learner.graph_launches
+    if graph:   # graph replays do not pass through the C entry points: add the captured kernels per replay
+        # (N = 1 and the fixed-shape exchange: everything is captured; dynamic exchange: the draws, gathers and
+        # tree updates around the two graphs were counted eagerly above)
+        launches += K * int(getattr(learner, "graph_launches", 0))
     ms_total = e0.elapsed_time(e1)
     # ---- e2e: public API, host uniforms in, loss out, every step
     for _ in range(W):

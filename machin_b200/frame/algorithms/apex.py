@@ -165,11 +165,16 @@ class DQNApex(DQNPer):
                 apply()
         cur.wait_stream(side)
         t.cuda.synchronize(dev)
+        from ..._lib import lib
         g1, g2 = t.cuda.CUDAGraph(), t.cuda.CUDAGraph()
+        launched = lib.mb_launch_count()
         with t.cuda.graph(g1):
             st["abs"], st["loss"] = compute()
         with t.cuda.graph(g2):
             apply()
+        # libmachin_b200 kernels per update that run from the two graphs (replays bypass the C entry points,
+        # which count the eager launches of the exchange themselves)
+        self.graph_launches = lib.mb_launch_count() - launched
         with t.no_grad():
             for m, sv in zip((self.qnet, self.qnet_target), saved):
                 for x, v in zip(list(m.parameters()) + list(m.buffers()), sv):
@@ -280,9 +285,11 @@ class DQNApex(DQNPer):
         cur.wait_stream(side)
         t.cuda.synchronize(dev)
         graph = t.cuda.CUDAGraph()
+        launched = lib.mb_launch_count()
         with t.cuda.graph(graph, capture_error_mode="thread_local"):
             st["loss"] = body()
         st["graph"] = graph
+        self.graph_launches = lib.mb_launch_count() - launched     # libmachin_b200 kernels per replayed update
         with t.no_grad():
             for m, sv in zip((self.qnet, self.qnet_target), saved):
                 for x, v in zip(list(m.parameters()) + list(m.buffers()), sv):
