@@ -49,7 +49,7 @@ def parse():
     p.add_argument("--cpu-steps", type=int, default=1500)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per update")
-    p.add_argument("--net", default="torch", choices=["torch", "fused", "fused-program"],
+    p.add_argument("--net", default="torch", choices=["torch", "fused", "fused-program", "fused-rows"],
                    help="Q-net implementation: nn.Module over cuBLAS (default, fastest measured), FusedMLP autograd "
                         "(csrc/mlp.cu), or FusedMLP + the persistent fused forward/TD/backward program")
     p.add_argument("--dynamic-exchange", action="store_true",
@@ -220,7 +220,8 @@ def build_learner(a, device, seed, world=1):
         adam = FusedAdam if a.adam == "fused" else functools.partial(t.optim.Adam, fused=True)
         learner = DQNPer(qnet, qtgt, adam, t.nn.MSELoss(reduction="none"), batch_size=a.batch,
                          learning_rate=1e-3, discount=0.99, update_rate=0.005, replay_buffer=buf)
-        learner.use_fused_program = a.net == "fused-program"
+        learner.use_fused_program = a.net in ("fused-program", "fused-rows")
+        learner.fused_kind = "rows" if a.net == "fused-rows" else "program"
         learner.fuse_online_forwards = a.fuse_forwards
         learner.overlap_priority_update = a.overlap_update and world == 1
         learner.parallel_forwards = a.parallel_forwards and world == 1

@@ -251,6 +251,17 @@ int mb_dqn_mlp_program_create(int device, int n_layers, const int *sizes, int ba
                               const uint8_t *d_terminal, const double *d_is_weight, float discount, int mode,
                               float *d_y, float *d_action_value, float *d_abs_error, double *d_loss_elem,
                               mb_mlp_program **out);
+/* Same contract and arguments, no grid-wide barrier: the forward passes, the TD row math and the backward-input
+ * chain of a batch row depend on that row only, so one CTA per 8 batch rows runs them back to back with the
+ * activations in shared memory and the weights streaming from L2; dW / db follow as one launch of independent
+ * tile x K-split items.  mb_mlp_program_run issues three launches (weight transposes, row tiles, dW).  Layer
+ * outputs wider than 256 are rejected with MB_ERR_INVALID (use mb_dqn_mlp_program_create). */
+int mb_dqn_mlp_rows_create(int device, int n_layers, const int *sizes, int batch, float *const *d_params,
+                           float *const *d_target_params, float *const *d_grads, const float *d_state,
+                           const float *d_next_state, const int64_t *d_action, const float *d_reward,
+                           const uint8_t *d_terminal, const double *d_is_weight, float discount, int mode,
+                           float *d_y, float *d_action_value, float *d_abs_error, double *d_loss_elem,
+                           mb_mlp_program **out);
 int mb_mlp_program_run(mb_mlp_program *program, void *stream);
 int mb_mlp_program_destroy(mb_mlp_program *program);
 /* torch.optim.Adam step (amsgrad off) over n_tensors parameter tensors in one launch; d_step_count is a

@@ -72,6 +72,9 @@ class DQNPer(TorchFramework):
         # opt-in: FusedMLP nets + MSE -> forward x3, TD and backward as ONE persistent cooperative kernel
         # (csrc/mlp.cu).  Correct (tests) but currently slower than cuBLAS-backed autograd, see DESIGN.md 8.
         self.use_fused_program = False
+        # which fused executor: "program" (one cooperative launch, grid barriers between layers) or "rows" (row-tile
+        # kernel without grid barriers + one dW launch; layer outputs <= 256 wide) -- csrc/mlp.cu
+        self.fused_kind = "program"
         # opt-in: evaluate Q(s) and Q(s') of the ONLINE net in one forward over [s; s'] (they share weights;
         # only valid for row-wise networks, i.e. no BatchNorm/Dropout): 3 fewer GEMM + epilogue launches
         self.fuse_online_forwards = False
@@ -249,7 +252,8 @@ class DQNPer(TorchFramework):
         arr = lambda xs: (C.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
         handle = C.c_void_p()
         with t.cuda.device(dev):
-            check(lib.mb_dqn_mlp_program_create(
+            create = lib.mb_dqn_mlp_rows_create if self.fused_kind == "rows" else lib.mb_dqn_mlp_program_create
+            check(create(
                 dev.index, L, (C.c_int * (L + 1))(*sizes), B, arr(plist(self.qnet)), arr(plist(self.qnet_target)),
                 arr([p.grad for p in plist(self.qnet)]), ptr(st["fields"][names[0]]), ptr(st["fields"][names[3]]),
                 ptr(st["fields"][names[1]]), ptr(st["fields"]["reward"]), ptr(st["fields"]["terminal"]), ptr(st["isw"]),
