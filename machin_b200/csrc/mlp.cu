@@ -788,8 +788,9 @@ int mb_dqn_mlp_rows_create(int device, int n_layers, const int *sizes, int batch
     const int xp = ((sizes[0] + 3) & ~3) + 4;
     P->rows_smem = sizeof(float) * (size_t)(2 * RB) * (size_t)(xp + 2 * RP);
     P->rows_grid = (batch + RB - 1) / RB;
-    if (P->rows_smem > 200 * 1024 ||
-        cudaFuncSetAttribute(dqn_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->rows_smem) != cudaSuccess) {
+    // one fixed opt-in limit for every program on this device (a later, smaller program must not lower it)
+    if (P->rows_smem > 160 * 1024 ||
+        cudaFuncSetAttribute(dqn_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess) {
         cudaGetLastError();
         mb_mlp_program_destroy(P);
         return MB_ERR_INVALID;
