@@ -52,6 +52,7 @@ struct mb_tree {
     int coop_blocks;     // co-resident CTAs for the cooperative update kernel
     int gen;             // update-launch generation counter
     int sorted_cluster;  // MB_SORTED_CLUSTER=1: small sorted updates on a cluster of 8 CTAs (opt-in until measured)
+    int sorted_async;    // MB_SORTED_ASYNC=1: barrier-free walk (point-to-point hand-overs), opt-in until measured
     int force_generic;   // MB_FORCE_GENERIC_UPDATE=1: single-CTA PER draw instead of the cluster kernel (A/B timing)
 };
 
@@ -480,24 +481,37 @@ __global__ void __launch_bounds__(kSortedN) tree_update_sorted(TreeDev t, const 
     }
 }
 
-// ---- the same walk spread over a thread-block cluster (opt-in: MB_SORTED_CLUSTER=1) ---------------------
-// tree_update_sorted is bound by ONE SM's load/store unit: ~8.7 k scattered 8-byte loads (stored siblings) and
-// as many scattered stores for 512 entries of a 2^24-leaf tree, ~1 sector request per cycle.  Here the tree is
-// cut at level ls = levels - 3 into 8 subtrees, CTA r of a cluster of 8 owns the entries whose leaf index lies
-// in subtree r (a contiguous run of the sorted batch; entries of different subtrees never meet below level ls),
-// runs the same merge walk for levels 0..ls-1 on its own SM -- prefetch and write-out now use 8 load/store
-// units -- and publishes the value of its subtree root (the stored one if it has no entry) in shared memory;
-// after cluster.sync() the leader reads the 8 roots over DSMEM and computes the 7 nodes above them.  Parents
-// stay fl(left + right) of the current children: bit-identical to the single-CTA kernel.
-constexpr int kClusterBits = 3;
-constexpr int kClusterCtas = 1 << kClusterBits;
+// ---- second-generation small sorted update (opt-in until measured: MB_SORTED_CLUSTER=1, MB_SORTED_ASYNC=1) ----
+// Two independent changes to tree_update_sorted, selected at compile time:
+//
+// CB = 3 (MB_SORTED_CLUSTER): the kernel above is bound by ONE SM's load/store unit: ~8.7 k scattered 8-byte
+//   loads (stored siblings) and as many scattered stores for 512 entries of a 2^24-leaf tree, ~1 sector request
+//   per cycle.  Here the tree is cut at level ls = levels - 3 into 8 subtrees; CTA r of a cluster of 8 owns the
+//   entries whose leaf index lies in subtree r (a contiguous run of the sorted batch; entries of different
+//   subtrees never meet below level ls), runs the walk for levels 0..ls-1 on its own SM -- prefetch and write-out
+//   now use 8 load/store units -- and publishes the value of its subtree root (the stored one if it has no
+//   entry) in shared memory; after cluster.sync() the leader reads the 8 roots over DSMEM and computes the 7
+//   nodes above them.
+//
+// kAsync (MB_SORTED_ASYNC): the walk above spends one CTA-wide barrier per level although an entry only ever
+//   waits for ONE other entry: who hands its value to whom is the Cartesian tree of hb[] (entry j hands the value
+//   of its level-hb[j] node to the nearest entry on its left with a larger hb, which is the leftmost entry of the
+//   sibling subtree).  So every entry walks its levels on its own -- add the prefetched stored sibling, or, when
+//   its right-hand neighbour's hb equals the level, wait for that neighbour's published value and inherit its
+//   neighbour pointer -- and publishes (value, next) with a flag when it reaches level hb.  No barrier in the walk;
+//   the critical path is the ~log-depth chain of hand-overs.  Waiting is cooperative polling (every lane takes
+//   one non-blocking step per round, a warp leaves the loop together), bounded: running out of rounds reports an
+//   error instead of hanging.
+//
+// Parents stay fl(left + right) of the current children in both variants: bit-identical to the kernel above.
+constexpr int kSpinLimit = 1 << 20;   // polling rounds per warp before the walk gives up (a few ms)
 
-template <typename WT>
-__global__ void __launch_bounds__(kSortedN) tree_update_sorted_cluster(TreeDev t, const int64_t *__restrict__ idx,
-                                                                       const WT *__restrict__ w,
-                                                                       const uint8_t *__restrict__ valid, int n,
-                                                                       Normalize nz, int gen) {
-    cg::cluster_group cluster = cg::this_cluster();
+template <typename WT, int CB, bool kAsync>
+__global__ void __launch_bounds__(kSortedN) tree_update_sorted_v2(TreeDev t, const int64_t *__restrict__ idx,
+                                                                  const WT *__restrict__ w,
+                                                                  const uint8_t *__restrict__ valid, int n,
+                                                                  Normalize nz, int gen) {
+    constexpr int kCtas = 1 << CB;
     extern __shared__ __align__(16) unsigned char dyn[];
     double *park = reinterpret_cast<double *>(dyn);
     __shared__ double s_val[kSortedN];
@@ -505,18 +519,23 @@ __global__ void __launch_bounds__(kSortedN) tree_update_sorted_cluster(TreeDev t
     __shared__ double s_w[kSortedN];
     __shared__ short s_hb[kSortedN];
     __shared__ short s_next[kSortedN];
+    __shared__ int s_flag[kSortedN];
     __shared__ int s_warp[kSortedN / 32];
     __shared__ double s_red[kSortedN / 32];
     __shared__ double s_top;                          // value of this CTA's subtree root (level ls)
     __shared__ double s_max;                          // largest new leaf weight among this CTA's entries
+    __shared__ int s_fail;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned rank = cluster.block_rank();
+    unsigned rank = 0;
+    if (CB > 0) rank = cg::this_cluster().block_rank();
     const int levels = t.depth - 1;
-    const int ls = levels - kClusterBits;
+    const int ls = levels - CB;
     const bool in = tid < n;
     const int64_t k = in ? idx[tid] : 0;
     const bool oob = in && (k < 0 || k >= t.size);
     const bool unsorted = in && tid > 0 && idx[tid - 1] > k;
+    if (kAsync) s_flag[tid] = 0;
+    if (tid == 0) s_fail = 0;
     // every CTA looks at the whole batch, so all of them take the same branch (no cluster barrier is skipped)
     const int any_oob = __syncthreads_or(oob ? 1 : 0);
     const int generic = __syncthreads_or((unsorted || valid != nullptr) ? 1 : 0);
@@ -578,47 +597,106 @@ __global__ void __launch_bounds__(kSortedN) tree_update_sorted_cluster(TreeDev t
     const double leaf_val = val;
     unsigned wrote = 0;
     __syncthreads();
-#pragma unroll 1
-    for (int l = 0; l < ls; ++l) {
-        if (alive && hb == l) {
-            s_val[tid] = val;
-            alive = false;
+    if (kAsync) {
+        // Cooperative polling, one warp at a time: in every round each lane that still has work takes ONE
+        // non-blocking step (advance a level, or look at its neighbour's flag and try again next round), and the
+        // warp leaves the loop together when all its lanes are done.  No lane ever spins while another lane of
+        // its warp waits at a reconvergence point, so progress does not depend on how divergent lanes are scheduled.
+        int nx = tid + 1, l = 0;
+        const int lim = !alive ? 0 : (tid == 0 ? ls : hb);          // I compute my ancestors on levels 1..lim
+        bool done = !alive;
+        int rounds = 0;
+        while (__any_sync(0xffffffffu, !done)) {
+            if (!done) {
+                if (l == lim) {                                  // reached the level where I hand over (entry 0: the top)
+                    if (tid != 0) {
+                        reinterpret_cast<volatile double *>(s_val)[tid] = val;
+                        reinterpret_cast<volatile short *>(s_next)[tid] = (short)nx;
+                        __threadfence_block();
+                        reinterpret_cast<volatile int *>(s_flag)[tid] = 1;
+                    }
+                    done = true;
+                } else if (nx < m && s_hb[nx] == l) {            // my right-hand neighbour ends here: take its node value
+                    if (reinterpret_cast<volatile int *>(s_flag)[nx] != 0) {
+                        __threadfence_block();
+                        const double other = reinterpret_cast<volatile double *>(s_val)[nx];
+                        nx = reinterpret_cast<volatile short *>(s_next)[nx];
+                        val = val + other;                       // left + right
+                        park[l * kSortedN + tid] = val;
+                        wrote |= 1u << l;
+                        ++l;
+                    }                                            // else: not published yet, look again next round
+                } else {
+                    val = val + park[l * kSortedN + tid];        // stored sibling (prefetched)
+                    park[l * kSortedN + tid] = val;
+                    wrote |= 1u << l;
+                    ++l;
+                }
+            }
+            if (++rounds > kSpinLimit) {                         // uniform per warp; cannot happen unless the logic is broken
+                if (!done) s_fail = 1;
+                break;
+            }
         }
         __syncthreads();
-        if (alive) {
-            const int j = s_next[tid];
-            double other;
-            if (j < m && s_hb[j] == l) {
-                other = s_val[j];
-                s_next[tid] = s_next[j];
-            } else {
-                other = park[l * kSortedN + tid];
+        if (s_fail) {                                            // uniform: report, write nothing
+            if (tid == 0) {
+                t.st->err = MB_ERR_INVALID;
+                t.st->err_gen = gen;
             }
-            val = val + other;
-            park[l * kSortedN + tid] = val;
-            wrote |= 1u << l;
+            wrote = 0;
+            alive = false;
+        }
+    } else {
+#pragma unroll 1
+        for (int l = 0; l < ls; ++l) {
+            if (alive && hb == l) {
+                s_val[tid] = val;
+                alive = false;
+            }
+            __syncthreads();
+            if (alive) {
+                const int j = s_next[tid];
+                double other;
+                if (j < m && s_hb[j] == l) {
+                    other = s_val[j];
+                    s_next[tid] = s_next[j];
+                } else {
+                    other = park[l * kSortedN + tid];
+                }
+                val = val + other;
+                park[l * kSortedN + tid] = val;
+                wrote |= 1u << l;
+            }
         }
     }
-    if (tid == 0) s_top = m > 0 ? val : __ldcg(t.W + level_off(t, ls) + rank);
-    if (tid < m) {
+    const bool failed = kAsync && s_fail;
+    if (tid == 0) s_top = (m > 0 && !failed) ? val : __ldcg(t.W + level_off(t, ls) + rank);
+    if (tid < m && !failed) {
         t.W[key] = leaf_val;
         for (int l = 0; l < ls; ++l)
             if (wrote & (1u << l)) t.W[level_off(t, l + 1) + (key >> (l + 1))] = park[l * kSortedN + tid];
     }
-    cluster.sync();
+    if (CB > 0) cg::this_cluster().sync();
+    else __syncthreads();
     if (rank == 0 && tid == 0) {
-        double v[kClusterCtas], bm = -INFINITY;
+        double v[kCtas], bm = -INFINITY;
 #pragma unroll
-        for (int r = 0; r < kClusterCtas; ++r) {
-            v[r] = *cluster.map_shared_rank(&s_top, r);
-            bm = fmax(bm, *cluster.map_shared_rank(&s_max, r));
+        for (int r = 0; r < kCtas; ++r) {
+            if (CB > 0) {
+                v[r] = *cg::this_cluster().map_shared_rank(&s_top, r);
+                bm = fmax(bm, *cg::this_cluster().map_shared_rank(&s_max, r));
+            } else {
+                v[r] = s_top;
+                bm = s_max;
+            }
         }
-        int cnt = kClusterCtas;
+        int cnt = kCtas;
 #pragma unroll
-        for (int b = 1; b <= kClusterBits; ++b) {
+        for (int b = 1; b <= CB; ++b) {
             cnt >>= 1;
 #pragma unroll
-            for (int j = 0; j < kClusterCtas / 2; ++j)
+            for (int j = 0; j < (kCtas + 1) / 2; ++j)
                 if (j < cnt) {
                     v[j] = v[2 * j] + v[2 * j + 1];
                     t.W[level_off(t, ls + b) + j] = v[j];
@@ -629,7 +707,7 @@ __global__ void __launch_bounds__(kSortedN) tree_update_sorted_cluster(TreeDev t
             t.st->max_is_f32 = sizeof(WT) == 4 ? 1 : 0;
         }
     }
-    cluster.sync();   // nobody exits (and frees its shared memory) while the leader may still read it
+    if (CB > 0) cg::this_cluster().sync();   // nobody exits (and frees its shared memory) while the leader may still read it
 }
 
 // ---- large batches: the same algorithm as separate launches, sparse at the bottom, dense at the top ----
@@ -867,6 +945,8 @@ int mb_tree_create(int64_t size, int device, mb_tree **out) {
         t->force_generic = (e && e[0] == '1') ? 1 : 0;
         const char *c = getenv("MB_SORTED_CLUSTER");
         t->sorted_cluster = (c && c[0] == '1') ? 1 : 0;
+        const char *y = getenv("MB_SORTED_ASYNC");
+        t->sorted_async = (y && y[0] == '1') ? 1 : 0;
     }
     t->dev.W = nullptr;
     t->dev.owner = nullptr;
@@ -885,8 +965,12 @@ int mb_tree_create(int64_t size, int device, mb_tree **out) {
     tree_state_reset<<<1, 1>>>(t->dev.st, 0.0);
     MB_CUDA(cudaFuncSetAttribute(tree_update_sorted<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     MB_CUDA(cudaFuncSetAttribute(tree_update_sorted<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    MB_CUDA(cudaFuncSetAttribute(tree_update_sorted_cluster<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    MB_CUDA(cudaFuncSetAttribute(tree_update_sorted_cluster<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    MB_CUDA(cudaFuncSetAttribute(tree_update_sorted_v2<float, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    MB_CUDA(cudaFuncSetAttribute(tree_update_sorted_v2<double, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    MB_CUDA(cudaFuncSetAttribute(tree_update_sorted_v2<float, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    MB_CUDA(cudaFuncSetAttribute(tree_update_sorted_v2<double, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    MB_CUDA(cudaFuncSetAttribute(tree_update_sorted_v2<float, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    MB_CUDA(cudaFuncSetAttribute(tree_update_sorted_v2<double, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     int per_sm = 0;
     MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_update_kernel<double, true>, 1024, 0));
     int sms = mb::kNumSMs;
@@ -1013,24 +1097,34 @@ static int launch_update(mb_tree *t, const int64_t *d_index, const void *d_weigh
     if (n <= kSortedN && !t->force_generic) {
         const int threads = (int)(((n + 31) / 32) * 32);
         const size_t dyn = sizeof(double) * (size_t)kSortedN * (size_t)(t->dev.depth - 1);
-        if (t->sorted_cluster && n > 64 && t->dev.depth - 1 >= kClusterBits + 4) {
+        const bool cluster = t->sorted_cluster && n > 64 && t->dev.depth - 1 >= 3 + 4;
+        if (cluster || t->sorted_async) {
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(kClusterCtas);
+            cfg.gridDim = dim3(cluster ? 8 : 1);
             cfg.blockDim = dim3(threads);
             cfg.dynamicSmemBytes = dyn;
             cfg.stream = s;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = kClusterCtas;
+            attr[0].val.clusterDim.x = cluster ? 8 : 1;
             attr[0].val.clusterDim.y = 1;
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
-            cfg.numAttrs = 1;
+            cfg.numAttrs = cluster ? 1 : 0;
             const int ni = (int)n;
-            if (dtype == MB_F32)
-                MB_CUDA(cudaLaunchKernelEx(&cfg, tree_update_sorted_cluster<float>, t->dev, d_index, (const float *)d_weight, d_valid, ni, nz, gen));
+            const float *wf = (const float *)d_weight;
+            const double *wd = (const double *)d_weight;
+            cudaError_t e;
+            if (cluster && t->sorted_async)
+                e = dtype == MB_F32 ? cudaLaunchKernelEx(&cfg, tree_update_sorted_v2<float, 3, true>, t->dev, d_index, wf, d_valid, ni, nz, gen)
+                                    : cudaLaunchKernelEx(&cfg, tree_update_sorted_v2<double, 3, true>, t->dev, d_index, wd, d_valid, ni, nz, gen);
+            else if (cluster)
+                e = dtype == MB_F32 ? cudaLaunchKernelEx(&cfg, tree_update_sorted_v2<float, 3, false>, t->dev, d_index, wf, d_valid, ni, nz, gen)
+                                    : cudaLaunchKernelEx(&cfg, tree_update_sorted_v2<double, 3, false>, t->dev, d_index, wd, d_valid, ni, nz, gen);
             else
-                MB_CUDA(cudaLaunchKernelEx(&cfg, tree_update_sorted_cluster<double>, t->dev, d_index, (const double *)d_weight, d_valid, ni, nz, gen));
+                e = dtype == MB_F32 ? cudaLaunchKernelEx(&cfg, tree_update_sorted_v2<float, 0, true>, t->dev, d_index, wf, d_valid, ni, nz, gen)
+                                    : cudaLaunchKernelEx(&cfg, tree_update_sorted_v2<double, 0, true>, t->dev, d_index, wd, d_valid, ni, nz, gen);
+            MB_CUDA(e);
             mb::count_launch(1);
             return MB_OK;
         }

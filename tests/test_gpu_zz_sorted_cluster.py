@@ -1,5 +1,6 @@
-"""GPU: the opt-in cluster variant of the small sorted tree update (MB_SORTED_CLUSTER=1,
-csrc/sumtree.cu: tree_update_sorted_cluster) against the oracle -- bit-exact, like the single-CTA kernel."""
+"""GPU: the opt-in second-generation small sorted tree update (csrc/sumtree.cu: tree_update_sorted_v2;
+MB_SORTED_CLUSTER=1: 8 subtrees on a cluster of 8 CTAs, MB_SORTED_ASYNC=1: barrier-free walk with point-to-point
+hand-overs, or both) against the oracle -- bit-exact, like the single-CTA kernel."""
 import os
 
 import numpy as np
@@ -12,9 +13,10 @@ from oracle.sumtree import OracleTree
 pytestmark = [pytest.mark.gpu, first_hardware_run_pending]
 
 
-@pytest.fixture()
-def cluster_tree(monkeypatch):
-    monkeypatch.setenv("MB_SORTED_CLUSTER", "1")      # read by mb_tree_create
+@pytest.fixture(params=["cluster", "async", "cluster+async"])
+def cluster_tree(monkeypatch, request):
+    for name, key in (("MB_SORTED_CLUSTER", "cluster"), ("MB_SORTED_ASYNC", "async")):   # read by mb_tree_create
+        monkeypatch.setenv(name, "1" if key in request.param else "0")
     from machin_b200.frame.buffers import WeightTree
     return WeightTree
 

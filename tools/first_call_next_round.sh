@@ -25,15 +25,19 @@ run overlap_update     "MB_X=0"               "--overlap-update"
 run parallel_forwards  "MB_X=0"               "--parallel-forwards"
 run both               "MB_X=0"               "--overlap-update --parallel-forwards"
 run cluster_update     "MB_SORTED_CLUSTER=1"  ""
+run async_update       "MB_SORTED_ASYNC=1"    ""
+run cluster_async      "MB_SORTED_CLUSTER=1 MB_SORTED_ASYNC=1"  ""
 run all                "MB_SORTED_CLUSTER=1"  "--overlap-update --parallel-forwards"
 run fused_autograd     "MB_X=0"               "--net fused"
 run fused_rows         "MB_X=0"               "--net fused-rows"
 run fused_rows_all     "MB_SORTED_CLUSTER=1"  "--net fused-rows --overlap-update"
 timeout 300 python tools/microbench.py > gpurun_out/next_microbench_single.json 2>/dev/null
 MB_SORTED_CLUSTER=1 timeout 300 python tools/microbench.py > gpurun_out/next_microbench_cluster.json 2>/dev/null
+MB_SORTED_ASYNC=1 timeout 300 python tools/microbench.py > gpurun_out/next_microbench_async.json 2>/dev/null
+MB_SORTED_CLUSTER=1 MB_SORTED_ASYNC=1 timeout 300 python tools/microbench.py > gpurun_out/next_microbench_both.json 2>/dev/null
 python - <<'PY'
 import json
-for v in ("single", "cluster"):
+for v in ("single", "cluster", "async", "both"):
     try:
         r = json.load(open(f"gpurun_out/next_microbench_{v}.json"))["results"]
         print(v, {k: round(x["us"], 2) for k, x in r.items() if k.startswith("tree_update_sorted")})

@@ -100,7 +100,8 @@ def main():  # noqa: C901
         byt = (20 + 24 * (D - 1)) * nu
         R[f"tree_update_sorted_{nu}"] = {"us": s * 1e6, "alg_bytes_upper": byt, "GBps": byt / s / 1e9,
                                          "frac": byt / s / 1e9 / PEAK,
-                                         "variant": "cluster" if os.environ.get("MB_SORTED_CLUSTER") == "1" else "single CTA"}
+                                         "variant": ("cluster " if os.environ.get("MB_SORTED_CLUSTER") == "1" else "single CTA ") +
+                                                    ("async walk" if os.environ.get("MB_SORTED_ASYNC") == "1" else "barrier walk")}
     tree.check()
 
     # ---- fused PER draw
