@@ -31,16 +31,6 @@ run all                "MB_SORTED_CLUSTER=1"  "--overlap-update --parallel-forwa
 run fused_autograd     "MB_X=0"               "--net fused"
 run fused_rows         "MB_X=0"               "--net fused-rows"
 run fused_rows_all     "MB_SORTED_CLUSTER=1"  "--net fused-rows --overlap-update"
-timeout 300 python tools/microbench.py > gpurun_out/next_microbench_single.json 2>/dev/null
-MB_SORTED_CLUSTER=1 timeout 300 python tools/microbench.py > gpurun_out/next_microbench_cluster.json 2>/dev/null
-MB_SORTED_ASYNC=1 timeout 300 python tools/microbench.py > gpurun_out/next_microbench_async.json 2>/dev/null
-MB_SORTED_CLUSTER=1 MB_SORTED_ASYNC=1 timeout 300 python tools/microbench.py > gpurun_out/next_microbench_both.json 2>/dev/null
-python - <<'PY'
-import json
-for v in ("single", "cluster", "async", "both"):
-    try:
-        r = json.load(open(f"gpurun_out/next_microbench_{v}.json"))["results"]
-        print(v, {k: round(x["us"], 2) for k, x in r.items() if k.startswith("tree_update_sorted")})
-    except Exception as e:
-        print(v, "FAILED", e)
-PY
+for v in "MB_X=0" "MB_SORTED_CLUSTER=1" "MB_SORTED_ASYNC=1" "MB_SORTED_CLUSTER=1 MB_SORTED_ASYNC=1"; do
+    env $v timeout 120 python tools/ub_sorted_update.py 2>/dev/null | tee -a gpurun_out/next_sorted_update.jsonl
+done
