@@ -128,11 +128,11 @@ class Buffer:
             if t.is_tensor(v):
                 fields.append(Field(attr, attr, None, v.dtype, v.shape[1:], "sub"))
             else:
-                fields.append(Field(attr, attr, None, _scalar_dtype(v), (1,), "sub"))
+                fields.append(Field(attr, attr, None, _scalar_dtype(v), (1,), "sub", scalar=True))
         for attr in tr.custom_attr:
             v = tr[attr]
             if isinstance(v, (bool, int, float, np.number)) and not t.is_tensor(v):
-                fields.append(Field(attr, attr, None, _scalar_dtype(v), (1,), "custom"))
+                fields.append(Field(attr, attr, None, _scalar_dtype(v), (1,), "custom", scalar=True))
         self._major_attr, self._sub_attr, self._custom_attr = list(tr.major_attr), list(tr.sub_attr), list(tr.custom_attr)
         self.storage.set_schema(fields)
 
@@ -269,7 +269,10 @@ class Buffer:
             dense = self.storage.gather(index_tensor, names=list(dict.fromkeys(want)))
         host_idx = None
 
-        def finish(attr, key, tensor):
+        def finish(attr, key, tensor, scalar=False):
+            if not concatenate and scalar:
+                # buffer.py:402-413 returns the sampled Python values as they were stored (reward 10.0, terminal True)
+                return self.post_process_attribute(attr, key, tensor.reshape(-1).tolist())
             tensor = tensor.to(out_device)
             if not concatenate:
                 tensor = list(tensor.split(1, dim=0))
@@ -299,7 +302,7 @@ class Buffer:
                                for f in fields.values() if f.attr == attr and f.kind == "major"})
                 used.append(attr)
             elif attr in self._sub_attr:
-                result.append(finish(attr, None, dense[attr].view(n, -1)))
+                result.append(finish(attr, None, dense[attr].view(n, -1), fields[attr].scalar))
                 used.append(attr)
             elif attr in self._custom_attr:
                 result.append(custom_value(attr))

@@ -21,10 +21,11 @@ from ..._lib import MbField, lib
 
 
 class Field:
-    __slots__ = ("name", "attr", "key", "dtype", "shape", "nbytes", "offset", "kind")
+    __slots__ = ("name", "attr", "key", "dtype", "shape", "nbytes", "offset", "kind", "scalar")
 
-    def __init__(self, name, attr, key, dtype, shape, kind):
+    def __init__(self, name, attr, key, dtype, shape, kind, scalar=False):
         self.name, self.attr, self.key, self.dtype, self.shape, self.kind = name, attr, key, dtype, tuple(shape), kind
+        self.scalar = scalar     # stored from a Python scalar (reward=1.0, terminal=True): unconcatenated samples give those back
         n = 1
         for s in self.shape:
             n *= int(s)
