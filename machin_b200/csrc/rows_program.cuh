@@ -1,0 +1,200 @@
+// Row-tile DQN value math: device code only (no CUDA runtime calls), included by mlp.cu inside its anonymous
+// namespace -- and by tests/cpu_emul/rows_harness.cpp, which compiles THIS SOURCE with g++ against a small shim
+// (threads = OS threads, __syncthreads = a barrier) so that its indexing can be checked where no GPU exists.
+// See the comment block in mlp.cu for the design.
+#pragma once
+#include <stdint.h>
+
+#include "td_device.cuh"
+
+constexpr int RB = 8;            // batch rows per CTA
+constexpr int RT = 256;          // threads: 4 row groups x 64 column groups of 4
+constexpr int RW = 256;          // widest layer output one CTA sweeps
+constexpr int RP = RW + 4;       // activation row pitch in shared memory (floats, multiple of 4)
+constexpr int RL = 8;            // layers
+
+struct RowsArgs {
+    int L, batch;
+    int sizes[RL + 1];
+    const float *W[RL];          // online parameters [out, in] (backward-input reads them as B(k = out, j = in))
+    const float *Wt[RL];         // k-major copies [in, out] of the online / target weights (forward)
+    const float *tWt[RL];
+    const float *b[RL], *tb[RL];
+    const float *state, *next_state;
+    float *h[RL];                // Q(s) pass: output of layer l, [batch, sizes[l + 1]] (post-ReLU; last = q)
+    float *qn, *qtn;             // [batch, A]
+    float *dz[RL];               // gradient w.r.t. the output of layer l (pre-mask of the layer below)
+    TdDqnArgs td;
+};
+
+template <bool kVec>
+__device__ __forceinline__ float4 rows_load_b(const float *__restrict__ row, int j0, int N) {
+    if (kVec) return __ldg(reinterpret_cast<const float4 *>(row + j0));
+    float4 v;
+    v.x = j0 + 0 < N ? __ldg(row + j0 + 0) : 0.0f;
+    v.y = j0 + 1 < N ? __ldg(row + j0 + 1) : 0.0f;
+    v.z = j0 + 2 < N ? __ldg(row + j0 + 2) : 0.0f;
+    v.w = j0 + 3 < N ? __ldg(row + j0 + 3) : 0.0f;
+    return v;
+}
+
+// acc[r][c] = sum_k As[(ty * MR + r) * ap + k] * Bg[k * N + j0 + c]      (rows in shared memory, B k-major in global)
+template <int MR, bool kVec>
+__device__ __forceinline__ void rows_matmul_impl(const float *As, int ap, int K, const float *__restrict__ Bg, int N,
+                                                 float (&acc)[MR][4]) {
+    const int ty = threadIdx.x >> 6, j0 = (threadIdx.x & 63) * 4;
+    const float *a0 = As + (ty * MR) * ap;
+    int k = 0;
+    for (; k + 8 <= K; k += 8) {
+        float4 b[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) b[u] = rows_load_b<kVec>(Bg + (int64_t)(k + u) * N, j0, N);   // 8 loads in flight
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float4 a[MR];
+#pragma unroll
+            for (int r = 0; r < MR; ++r) a[r] = *reinterpret_cast<const float4 *>(a0 + r * ap + k + 4 * h);   // warp-wide broadcast
+#pragma unroll
+            for (int r = 0; r < MR; ++r) {
+                const float av[4] = {a[r].x, a[r].y, a[r].z, a[r].w};
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const float4 bb = b[4 * h + kk];
+                    acc[r][0] = fmaf(av[kk], bb.x, acc[r][0]);
+                    acc[r][1] = fmaf(av[kk], bb.y, acc[r][1]);
+                    acc[r][2] = fmaf(av[kk], bb.z, acc[r][2]);
+                    acc[r][3] = fmaf(av[kk], bb.w, acc[r][3]);
+                }
+            }
+        }
+    }
+    for (; k < K; ++k) {
+        const float4 bb = rows_load_b<kVec>(Bg + (int64_t)k * N, j0, N);
+#pragma unroll
+        for (int r = 0; r < MR; ++r) {
+            const float av = a0[r * ap + k];
+            acc[r][0] = fmaf(av, bb.x, acc[r][0]);
+            acc[r][1] = fmaf(av, bb.y, acc[r][1]);
+            acc[r][2] = fmaf(av, bb.z, acc[r][2]);
+            acc[r][3] = fmaf(av, bb.w, acc[r][3]);
+        }
+    }
+}
+
+template <int MR>
+__device__ __forceinline__ void rows_matmul(const float *As, int ap, int K, const float *__restrict__ Bg, int N,
+                                            float (&acc)[MR][4]) {
+#pragma unroll
+    for (int r = 0; r < MR; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+    if ((int)(threadIdx.x & 63) * 4 >= N) return;
+    // N % 4 == 0: a thread's four columns exist and every row of Bg is 16-byte aligned -> one LDG.128 per k
+    if ((N & 3) == 0) rows_matmul_impl<MR, true>(As, ap, K, Bg, N, acc);
+    else rows_matmul_impl<MR, false>(As, ap, K, Bg, N, acc);
+}
+
+// One forward layer for M = 4 * MR rows held in shared memory.  save0: rows [0, RB) also go to global at batch
+// row b0 + row (activations of the Q(s) pass / q); save1: rows [row1, row1 + RB) go to global (qn or qtn).
+template <int MR>
+__device__ __forceinline__ void rows_forward_layer(const float *in, int ip, float *out, int K, int N,
+                                                   const float *__restrict__ Wt, const float *__restrict__ bias,
+                                                   bool relu, int b0, int batch, float *save0, float *save1, int row1) {
+    float acc[MR][4];
+    rows_matmul<MR>(in, ip, K, Wt, N, acc);
+    const int ty = threadIdx.x >> 6, j0 = (threadIdx.x & 63) * 4;
+    if (j0 < N) {
+#pragma unroll
+        for (int r = 0; r < MR; ++r) {
+            const int row = ty * MR + r;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int j = j0 + c;
+                if (j >= N) continue;
+                float v = __fadd_rn(acc[r][c], __ldg(bias + j));
+                if (relu) v = fmaxf(v, 0.0f);
+                out[row * RP + j] = v;
+                if (save0 && row < RB && b0 + row < batch) save0[(int64_t)(b0 + row) * N + j] = v;
+                if (save1 && row >= row1 && row < row1 + RB && b0 + row - row1 < batch)
+                    save1[(int64_t)(b0 + row - row1) * N + j] = v;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(RT) dqn_rows_kernel(RowsArgs a) {
+    extern __shared__ __align__(16) float rsm[];
+    const int S = a.sizes[0], xp = ((S + 3) & ~3) + 4, L = a.L, A = a.sizes[L];
+    float *X = rsm;                      // [2 * RB][xp]: rows 0..RB-1 = s, RB..2RB-1 = s'
+    float *B0 = X + 2 * RB * xp;         // [2 * RB][RP]
+    float *B1 = B0 + 2 * RB * RP;
+    const int tid = threadIdx.x, b0 = blockIdx.x * RB;
+    for (int e = tid; e < 2 * RB * xp; e += RT) {
+        const int row = e / xp, k = e % xp, b = b0 + (row % RB);
+        const float *src = row < RB ? a.state : a.next_state;
+        X[e] = (k < S && b < a.batch) ? __ldg(src + (int64_t)b * S + k) : 0.0f;
+    }
+    __syncthreads();
+    // ---- online net over [s; s'] (16 rows per weight load)
+    {
+        const float *in = X;
+        int ip = xp;
+        for (int l = 0; l < L; ++l) {
+            float *out = (l & 1) ? B1 : B0;
+            const bool last = l == L - 1;
+            rows_forward_layer<4>(in, ip, out, a.sizes[l], a.sizes[l + 1], a.Wt[l], a.b[l], !last, b0, a.batch, a.h[l],
+                                  last ? a.qn : nullptr, RB);
+            in = out;
+            ip = RP;
+        }
+    }
+    // ---- target net over s'
+    {
+        const float *in = X + RB * xp;
+        int ip = xp;
+        for (int l = 0; l < L; ++l) {
+            float *out = (l & 1) ? B1 : B0;
+            const bool last = l == L - 1;
+            rows_forward_layer<2>(in, ip, out, a.sizes[l], a.sizes[l + 1], a.tWt[l], a.tb[l], !last, b0, a.batch, nullptr,
+                                  last ? a.qtn : nullptr, 0);
+            in = out;
+            ip = RP;
+        }
+    }
+    // ---- TD row math on this CTA's rows (q, qn, qtn were written by this CTA; the barrier above orders them)
+    if (tid < RB && b0 + tid < a.batch) td_dqn_row(a.td, b0 + tid);
+    __syncthreads();
+    // ---- backward-input chain: dz[l-1] = (dz[l] W_l) * (h[l-1] > 0)
+    float *cur = B0, *nxt = B1;
+    for (int e = tid; e < RB * RP; e += RT) {
+        const int row = e / RP, j = e % RP;
+        cur[e] = (j < A && b0 + row < a.batch) ? a.td.grad_q[(int64_t)(b0 + row) * A + j] : 0.0f;
+    }
+    __syncthreads();
+    for (int l = L - 1; l >= 1; --l) {
+        const int K = a.sizes[l + 1], N = a.sizes[l];
+        float acc[2][4];
+        rows_matmul<2>(cur, RP, K, a.W[l], N, acc);
+        const int ty = tid >> 6, j0 = (tid & 63) * 4;
+        if (j0 < N) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int row = ty * 2 + r, b = b0 + row;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int j = j0 + c;
+                    if (j >= N) continue;
+                    float v = 0.0f;
+                    if (b < a.batch) {
+                        v = a.h[l - 1][(int64_t)b * N + j] > 0.0f ? acc[r][c] : 0.0f;
+                        a.dz[l - 1][(int64_t)b * N + j] = v;
+                    }
+                    nxt[row * RP + j] = v;
+                }
+            }
+        }
+        __syncthreads();
+        float *t = cur; cur = nxt; nxt = t;
+    }
+}
