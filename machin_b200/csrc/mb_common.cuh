@@ -29,6 +29,10 @@ void count_launch(int n);  // kernels launched by this library (mb_launch_count)
         MB_LAUNCH_CHECK();   \
     } while (0)
 
+// the CTA's dynamic shared memory as a byte array (a macro so that the host-side emulation used by the tests can
+// substitute its own buffer; under nvcc this is the usual declaration)
+#define MB_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 struct DeviceGuard {
