@@ -1,0 +1,155 @@
+// Replay-row movement and shard-exchange kernels: device code only (no CUDA runtime calls).  Included by rows.cu
+// inside its anonymous namespace and by tests/cpu_emul/wire_harness.cpp, which compiles THIS SOURCE with g++
+// against a shim of the CUDA execution model so that the fixed-shape exchange can be replayed for 4 and 8 shards
+// in the build container (only 2 GPUs were available when it was measured).
+#pragma once
+#include <stdint.h>
+
+#include "machin_b200.h"
+
+struct FieldList {
+    mb_field f[MB_MAX_FIELDS];
+    int n;
+};
+
+__device__ __forceinline__ void warp_copy(char *__restrict__ dst, const char *__restrict__ src, int64_t nbytes,
+                                          int lane) {
+    const uintptr_t mis = (uintptr_t)dst | (uintptr_t)src | (uintptr_t)nbytes;
+    if ((mis & 15) == 0) {
+        const uint4 *s = reinterpret_cast<const uint4 *>(src);
+        uint4 *d = reinterpret_cast<uint4 *>(dst);
+        for (int64_t k = lane; k < (nbytes >> 4); k += 32) d[k] = __ldcs(s + k);
+    } else if ((mis & 7) == 0) {
+        const uint2 *s = reinterpret_cast<const uint2 *>(src);
+        uint2 *d = reinterpret_cast<uint2 *>(dst);
+        for (int64_t k = lane; k < (nbytes >> 3); k += 32) d[k] = s[k];
+    } else if ((mis & 3) == 0) {
+        const uint32_t *s = reinterpret_cast<const uint32_t *>(src);
+        uint32_t *d = reinterpret_cast<uint32_t *>(dst);
+        for (int64_t k = lane; k < (nbytes >> 2); k += 32) d[k] = s[k];
+    } else {
+        for (int64_t k = lane; k < nbytes; k += 32) dst[k] = src[k];
+    }
+}
+
+// kGather: dense[i] <- ring[index[i]]     !kGather: ring[(first + i) % cap] <- dense[i]
+template <bool kGather>
+__global__ void __launch_bounds__(256) rows_move_kernel(char *ring, int64_t pitch, int64_t capacity,
+                                                        const int64_t *__restrict__ index, int64_t first_slot,
+                                                        int64_t n, FieldList fl) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n; i += n_warps) {
+        int64_t slot;
+        if (kGather) {
+            slot = index ? index[i] : i;  // NULL index: identity (unpacking rows received from a peer shard)
+            slot = slot < 0 ? 0 : (slot >= capacity ? capacity - 1 : slot);  // never read outside the ring
+        } else {
+            slot = (first_slot + i) % capacity;
+        }
+        char *row = ring + slot * pitch;
+        for (int f = 0; f < fl.n; ++f) {
+            char *dense = (char *)fl.f[f].d_dense + i * fl.f[f].dense_pitch;
+            if (kGather) warp_copy(dense, row + fl.f[f].row_offset, fl.f[f].nbytes, lane);
+            else warp_copy(row + fl.f[f].row_offset, dense, fl.f[f].nbytes, lane);
+        }
+    }
+}
+
+// Shard-exchange metadata: every wire row carries [index i64 | version i64 | value f64] behind its payload
+// (prioritized_buffer_d.py:293-303 returns index, version and is_weight next to the batch; :184-202 sends
+// index, version and priority back).  One launch packs / unpacks all three columns.
+__global__ void __launch_bounds__(256) rows_pack_meta_kernel(char *__restrict__ wire, int64_t width, int64_t meta_off,
+                                                             int64_t n, const int64_t *__restrict__ index,
+                                                             const int64_t *__restrict__ version,
+                                                             const int64_t *__restrict__ version_table,
+                                                             const double *__restrict__ v64,
+                                                             const float *__restrict__ v32) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    char *m = wire + i * width + meta_off;
+    const int64_t k = index[i];
+    reinterpret_cast<int64_t *>(m)[0] = k;
+    reinterpret_cast<int64_t *>(m)[1] = version ? version[i] : version_table[k];
+    reinterpret_cast<double *>(m)[2] = v64 ? v64[i] : (double)v32[i];
+}
+
+__global__ void __launch_bounds__(256) rows_unpack_meta_kernel(const char *__restrict__ wire, int64_t width,
+                                                               int64_t meta_off, int64_t n, int64_t *__restrict__ index,
+                                                               int64_t *__restrict__ version, double *__restrict__ v64,
+                                                               float *__restrict__ v32) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const char *m = wire + i * width + meta_off;
+    index[i] = reinterpret_cast<const int64_t *>(m)[0];
+    version[i] = reinterpret_cast<const int64_t *>(m)[1];
+    const double v = reinterpret_cast<const double *>(m)[2];
+    if (v64) v64[i] = v;
+    if (v32) v32[i] = (float)v;
+}
+
+// ---- fixed-shape exchange helpers (counts are read on the device: graph-replayable) --------------------
+__global__ void __launch_bounds__(256) wire_compact_kernel(const char *__restrict__ recv, int P, int64_t cap,
+                                                           int64_t width, int64_t meta_off,
+                                                           const int64_t *__restrict__ counts, char *__restrict__ merged,
+                                                           int64_t merged_rows, int64_t *__restrict__ index,
+                                                           int64_t *__restrict__ version, double *__restrict__ isw,
+                                                           const double *__restrict__ scale) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // merged row handled by this warp
+    if (j >= merged_rows) return;
+    int64_t base = 0;
+    int m = 0;
+    while (m < P && j >= base + counts[m]) base += counts[m++];
+    char *dst = merged + j * width;
+    if (m == P) {                                  // padding row: zero payload, weight 0
+        for (int64_t k = lane * 8; k < width; k += 256) *reinterpret_cast<uint2 *>(dst + k) = make_uint2(0, 0);
+        if (lane == 0) { index[j] = 0; version[j] = -1; isw[j] = 0.0; }
+        return;
+    }
+    const char *src = recv + ((int64_t)m * cap + (j - base)) * width;
+    // wire rows are payload (multiple of 16) + 24 bytes of metadata: 8-byte granularity
+    for (int64_t k = lane * 8; k < width; k += 256) *reinterpret_cast<uint2 *>(dst + k) = __ldcs(reinterpret_cast<const uint2 *>(src + k));
+    if (lane == 0) {
+        const char *meta = src + meta_off;
+        index[j] = reinterpret_cast<const int64_t *>(meta)[0];
+        version[j] = reinterpret_cast<const int64_t *>(meta)[1];
+        isw[j] = reinterpret_cast<const double *>(meta)[2] * (scale ? *scale : 1.0);
+    }
+}
+
+__global__ void __launch_bounds__(256) wire_scatter_update_kernel(char *__restrict__ send, int P, int64_t cap,
+                                                                  const int64_t *__restrict__ counts,
+                                                                  const int64_t *__restrict__ index,
+                                                                  const int64_t *__restrict__ version,
+                                                                  const float *__restrict__ priority,
+                                                                  int64_t merged_rows) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= merged_rows) return;
+    int64_t base = 0;
+    int m = 0;
+    while (m < P && j >= base + counts[m]) base += counts[m++];
+    if (m == P) return;
+    char *dst = send + ((int64_t)m * cap + (j - base)) * 24;
+    reinterpret_cast<int64_t *>(dst)[0] = index[j];
+    reinterpret_cast<int64_t *>(dst)[1] = version[j];
+    reinterpret_cast<double *>(dst)[2] = (double)priority[j];
+}
+
+__global__ void __launch_bounds__(256) wire_update_mask_kernel(const char *__restrict__ recv, int P, int64_t cap,
+                                                               const int64_t *__restrict__ counts, int self_block,
+                                                               const int64_t *__restrict__ table, int64_t table_size,
+                                                               int64_t *__restrict__ index, float *__restrict__ priority,
+                                                               uint8_t *__restrict__ valid) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)P * cap) return;
+    const int64_t i = e % cap;
+    const char *src = recv + e * 24;
+    const int64_t k = reinterpret_cast<const int64_t *>(src)[0];
+    const int64_t v = reinterpret_cast<const int64_t *>(src)[1];
+    const bool real = i < counts[self_block] && k >= 0 && k < table_size;
+    index[e] = real ? k : 0;
+    priority[e] = real ? (float)reinterpret_cast<const double *>(src)[2] : 0.0f;
+    valid[e] = (real && table[k] == v) ? 1 : 0;
+}

@@ -1,0 +1,112 @@
+"""CPU: ONE fixed-shape shard exchange (DQNApex static exchange, frame/algorithms/apex.py: draw -> gather into wire
+rows -> pack metadata -> all-to-all -> compaction -> TD -> priority scatter -> all-to-all -> version mask) replayed
+for 1, 2, 4 and 8 shards with the DEVICE SOURCE of the kernels (machin_b200/csrc/rows_device.cuh) compiled with
+g++ against tests/cpu_emul/cuda_shim.h; the all-to-all is a NumPy block transpose.  The exchange was measured on 2
+GPUs only (round 1); this replays the 4- and 8-shard data path in the build container.  Expectations are written
+directly from prioritized_buffer_d.py:204-303 (merged batch in member order, (index, version) per shard, stale
+versions dropped).  Not a CPU path of the library."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+EMUL = os.path.join(ROOT, "tests", "cpu_emul")
+META = 24
+
+
+class MbField(C.Structure):
+    _fields_ = [("row_offset", C.c_int64), ("nbytes", C.c_int64), ("d_dense", C.c_void_p), ("dense_pitch", C.c_int64)]
+
+
+@pytest.fixture(scope="module")
+def wire(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("emul") / "wire_emul.so")
+    cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-Wno-unknown-pragmas", "-pthread", "-shared", "-fPIC",
+           "-I" + os.path.join(ROOT, "machin_b200", "csrc"), "-I" + os.path.join(ROOT, "include"),
+           os.path.join(EMUL, "wire_harness.cpp"), "-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-3000:]
+    return C.CDLL(out)
+
+
+def p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+@pytest.mark.parametrize("P", [1, 2, 4, 8])
+@pytest.mark.parametrize("pitch", [48, 688])
+def test_fixed_shape_exchange_replayed_for_P_shards(wire, P, pitch):
+    rng = np.random.RandomState(P * 1000 + pitch)
+    B = 24                                   # requested batch; every (shard, requester) block holds `cap` = B wire rows
+    cap, capB, W, rows_in_ring = B, B + P, pitch + META, 200
+    # ceil apportioning gives sum(counts) in [B, B + P - 1]; include an empty shard when there are enough of them
+    counts = rng.multinomial(B, np.ones(P) / P).astype(np.int64)
+    if P >= 4:
+        counts[1] += counts[2]
+        counts[2] = 0
+    counts[0] += min(P - 1, 2)
+    assert counts.sum() <= capB - 1 and counts.max() <= cap
+    ring = [rng.randint(0, 256, size=(rows_in_ring, pitch)).astype(np.uint8) for _ in range(P)]
+    table = [rng.randint(0, 5, size=rows_in_ring).astype(np.int64) for _ in range(P)]
+    # ---- every shard m serves every requester r: draw (given), gather into the wire block, pack metadata
+    idx = [[np.sort(rng.randint(0, rows_in_ring, size=cap)).astype(np.int64) for _ in range(P)] for _ in range(P)]
+    isw = [[rng.rand(cap) for _ in range(P)] for _ in range(P)]
+    send = [np.zeros((P * cap, W), dtype=np.uint8) for _ in range(P)]
+    for m in range(P):
+        for r in range(P):
+            block = send[m][r * cap:(r + 1) * cap]
+            f = (MbField * 1)(MbField(0, pitch, block.ctypes.data, W))
+            assert wire.emul_rows_gather(p(ring[m]), C.c_int64(pitch), C.c_int64(rows_in_ring), p(idx[m][r]), C.c_int64(cap), f, 1) == 0
+            assert wire.emul_pack_meta(p(block), C.c_int64(W), C.c_int64(pitch), C.c_int64(cap), p(idx[m][r]), p(table[m]), p(isw[m][r])) == 0
+    version_at_sample = [t.copy() for t in table]
+    # ---- all-to-all: requester r receives block r of every shard, in member order
+    recv = [np.concatenate([send[m][r * cap:(r + 1) * cap] for m in range(P)]) for r in range(P)]
+    n = int(counts.sum())
+    scale = np.array([capB / n])
+    merged, m_idx, m_ver, m_isw = [], [], [], []
+    for r in range(P):
+        mg = np.full((capB, W), 0xAB, dtype=np.uint8)
+        mi, mv, mw = np.full(capB, -7, np.int64), np.full(capB, -7, np.int64), np.full(capB, -7.0)
+        assert wire.emul_wire_compact(p(recv[r]), P, C.c_int64(cap), C.c_int64(W), C.c_int64(pitch), p(counts), p(mg),
+                                      C.c_int64(capB), p(mi), p(mv), p(mw), p(scale)) == 0
+        j = 0
+        for m in range(P):                                  # merged batch: shard 0's rows, then shard 1's, ...
+            for k in range(int(counts[m])):
+                s = int(idx[m][r][k])
+                assert np.array_equal(mg[j, :pitch], ring[m][s]), (r, m, k)
+                assert mi[j] == s and mv[j] == version_at_sample[m][s]
+                assert mw[j] == isw[m][r][k] * scale[0]
+                j += 1
+        assert j == n
+        assert np.all(mg[n:] == 0) and np.all(mi[n:] == 0) and np.all(mv[n:] == -1) and np.all(mw[n:] == 0.0)
+        merged.append(mg), m_idx.append(mi), m_ver.append(mv), m_isw.append(mw)
+    # ---- after TD: every requester sends (index, version, |delta|) back to the shard each row came from
+    pri = [rng.rand(capB).astype(np.float32) for _ in range(P)]
+    send2 = [np.full((P * cap, META), 0xCD, dtype=np.uint8) for _ in range(P)]
+    for r in range(P):
+        assert wire.emul_wire_scatter_update(p(send2[r]), P, C.c_int64(cap), p(counts), p(m_idx[r]), p(m_ver[r]), p(pri[r]),
+                                             C.c_int64(capB)) == 0
+    recv2 = [np.concatenate([send2[r][m * cap:(m + 1) * cap] for r in range(P)]) for m in range(P)]
+    # some slots were overwritten between sampling and write-back: their version moved on (prioritized_buffer_d.py:131)
+    for m in range(P):
+        table[m][rng.rand(rows_in_ring) < 0.2] += 1
+    offset = np.concatenate([[0], np.cumsum(counts)])
+    for m in range(P):
+        u_idx = np.full(P * cap, -7, np.int64)
+        u_pri = np.full(P * cap, -7, np.float32)
+        u_val = np.full(P * cap, 9, np.uint8)
+        assert wire.emul_wire_update_mask(p(recv2[m]), P, C.c_int64(cap), p(counts), m, p(table[m]), C.c_int64(rows_in_ring),
+                                          p(u_idx), p(u_pri), p(u_val)) == 0
+        for r in range(P):
+            for k in range(cap):
+                e = r * cap + k
+                if k < counts[m]:
+                    s = int(idx[m][r][k])
+                    assert u_idx[e] == s and u_pri[e] == pri[r][offset[m] + k]
+                    assert u_val[e] == int(table[m][s] == version_at_sample[m][s])
+                else:
+                    assert u_val[e] == 0 and u_idx[e] == 0
