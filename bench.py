@@ -55,6 +55,9 @@ def parse():
     p.add_argument("--dynamic-exchange", action="store_true",
                    help="N > 1: exactly-sized eager NCCL exchanges between two CUDA graphs instead of the default "
                         "fixed-shape exchange captured with the rest of the update in ONE graph")
+    p.add_argument("--device-apportion", action="store_true",
+                   help="N > 1, fixed-shape exchange, opt-in: shard sums all-gathered and apportioned inside the graph "
+                        "(no host read per update)")
     p.add_argument("--watchdog-s", type=float, default=600.0,
                    help="N > 1: leave with exit code 5 if the run has not finished after this many seconds "
                         "(a stuck collective must not hold the box)")
@@ -360,7 +363,8 @@ def run_b200(a):
         # N = 2: 0.373 ms/update against 0.703 ms for the dynamic path; equivalent to it draw for draw on a group
         # of one, tests/test_gpu_algorithms.py).  --dynamic-exchange: two compute graphs around eager, exactly
         # sized NCCL exchanges (measured at N = 2, 4).
-        learner.enable_cuda_graph(static_exchange=a.static_exchange)
+        learner.enable_cuda_graph(static_exchange=a.static_exchange,
+                                  device_apportion=a.device_apportion and a.static_exchange)
     elif graph:
         learner.enable_cuda_graph()
     K, W, B = a.steps, max(a.warmup, 3), a.batch

@@ -174,6 +174,14 @@ int mb_rows_pack_meta(void *d_wire, int64_t width, int64_t meta_offset, int64_t 
                       const float *d_value_f32, void *stream);
 int mb_rows_unpack_meta(const void *d_wire, int64_t width, int64_t meta_offset, int64_t n, int64_t *d_index,
                         int64_t *d_version, double *d_value_f64, float *d_value_f32, void *stream);
+/* Device-side apportioning of one sharded sample (prioritized_buffer_d.py:229-234): from the all-gathered shard
+ * sums d_sums[n_blocks] computes total = sum + 1e-6, d_counts[m] = ceil(sums[m] * batch / total),
+ * *d_scale = merged_rows / sum(counts), and one mb_per_params block per requester for this shard's draws (beta from
+ * *d_beta, advanced by beta_increment per draw and written back; n_stored from *d_n_stored; n_draw = counts[self]).
+ * Lets a fixed-shape update replay without the host ever reading the shard sums. */
+int mb_wire_apportion(const double *d_sums, int n_blocks, int64_t batch, int self_block, int64_t merged_rows,
+                      const int64_t *d_n_stored, double *d_beta, double beta_increment, int64_t *d_counts,
+                      double *d_scale, mb_per_params *d_params, void *stream);
 /* Fixed-shape shard exchange (every (shard, requester) pair always moves `cap` wire rows; d_counts[m] of the
  * rows of block m are real).  All counts are read on the device, so the calls can be replayed in a CUDA graph.
  *  compact:  recv[P][cap][width] -> merged[sum(counts)][width] in member order, rows beyond the sum zeroed up

@@ -77,6 +77,7 @@ SIGNATURES = {
     "mb_rows_unpack_meta": (i32, [vp, i64, i64, i64, vp, vp, vp, vp, vp]),
     "mb_wire_compact": (i32, [vp, i32, i64, i64, i64, vp, vp, i64, vp, vp, vp, vp, vp]),
     "mb_wire_scatter_update": (i32, [vp, i32, i64, vp, vp, vp, vp, i64, vp]),
+    "mb_wire_apportion": (i32, [vp, i32, i64, i32, i64, vp, vp, f64, vp, vp, vp, vp]),
     "mb_wire_update_mask": (i32, [vp, i32, i64, vp, i32, vp, i64, vp, vp, vp, vp]),
     "mb_td_dqn": (i32, [vp, vp, vp, i64, i32, vp, vp, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]),
     "mb_td_target": (i32, [vp, vp, vp, i64, f32, vp, vp, vp, vp]),

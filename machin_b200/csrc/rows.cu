@@ -105,6 +105,19 @@ int mb_wire_scatter_update(void *d_send, int n_blocks, int64_t cap, const int64_
     return MB_OK;
 }
 
+int mb_wire_apportion(const double *d_sums, int n_blocks, int64_t batch, int self_block, int64_t merged_rows,
+                      const int64_t *d_n_stored, double *d_beta, double beta_increment, int64_t *d_counts,
+                      double *d_scale, mb_per_params *d_params, void *stream) {
+    if (!d_sums || n_blocks < 1 || batch < 1 || self_block < 0 || self_block >= n_blocks || merged_rows < 1 ||
+        !d_n_stored || !d_beta || !d_counts || !d_scale || !d_params)
+        return MB_ERR_INVALID;
+    wire_apportion_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_sums, n_blocks, batch, self_block, merged_rows,
+                                                              d_n_stored, d_beta, beta_increment, d_counts, d_scale,
+                                                              d_params);
+    MB_LAUNCHED(1);
+    return MB_OK;
+}
+
 int mb_wire_update_mask(const void *d_recv, int n_blocks, int64_t cap, const int64_t *d_counts, int self_block,
                         const int64_t *d_version_table, int64_t table_size, int64_t *d_index, float *d_priority,
                         uint8_t *d_valid, void *stream) {

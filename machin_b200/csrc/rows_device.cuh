@@ -153,3 +153,37 @@ __global__ void __launch_bounds__(256) wire_update_mask_kernel(const char *__res
     priority[e] = real ? (float)reinterpret_cast<const double *>(src)[2] : 0.0f;
     valid[e] = (real && table[k] == v) ? 1 : 0;
 }
+
+// Apportioning of one sharded sample on the device (prioritized_buffer_d.py:229-234, :425-427), so that a
+// fixed-shape update needs no host read of the shard sums: total = sum(shard sums) + 1e-6 (left to right, like
+// Python's sum), counts[m] = ceil(sums[m] * batch / total), scale = merged_rows / sum(counts) (padding rows weigh
+// 0, so the mean over merged_rows rows times scale is the mean over the real ones), and one mb_per_params block
+// per requester this shard serves: beta advances by beta_increment per draw (only when this shard draws at all),
+// the final beta goes back to *beta.  One thread: P is the number of GPUs.
+__global__ void wire_apportion_kernel(const double *__restrict__ sums, int P, int64_t batch, int self_block,
+                                      int64_t merged_rows, const int64_t *__restrict__ n_stored, double *beta,
+                                      double beta_increment, int64_t *__restrict__ counts, double *__restrict__ scale,
+                                      mb_per_params *__restrict__ params) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double total = 0.0;
+    for (int m = 0; m < P; ++m) total = __dadd_rn(total, sums[m]);
+    total = __dadd_rn(total, 1e-6);
+    int64_t n = 0;
+    for (int m = 0; m < P; ++m) {
+        const int64_t c = (int64_t)ceil(__ddiv_rn(__dmul_rn(sums[m], (double)batch), total));
+        counts[m] = c;
+        n += c;
+    }
+    *scale = n > 0 ? __ddiv_rn((double)merged_rows, (double)n) : 0.0;
+    const int64_t mine = counts[self_block];
+    double b = *beta;
+    for (int r = 0; r < P; ++r) {
+        params[r].beta = b;
+        params[r].all_weight_sum = total;
+        params[r].n_stored = *n_stored;
+        params[r].step = 0;
+        params[r].n_draw = mine;
+        if (mine > 0) b = fmin(1.0, __dadd_rn(b, beta_increment));
+    }
+    *beta = b;
+}

@@ -106,14 +106,18 @@ class DQNApex(DQNPer):
     # are captured; the row exchange, the gradient all-reduce, the priority write-back and the weight
     # broadcast stay eager NCCL calls between the replays.  The merged batch has a data-dependent size
     # n in [B, B + P - 1] (ceil apportioning), so the graphs run on B + P padded rows whose IS weight is 0.
-    def enable_cuda_graph(self, warmup: int = 3, static_exchange: bool = False):
+    def enable_cuda_graph(self, warmup: int = 3, static_exchange: bool = False, device_apportion: bool = False):
         """``static_exchange``: fixed-shape variant -- every (shard, requester) pair always moves ``batch_size``
         wire rows and the kernels read the apportioned counts from device memory, so draw, both all-to-alls,
         compute, the gradient all-reduce, the optimizer and the tree write-back are ONE graph replay per
         update; the host only reads the shard sums (the reference's own synchronisation point,
-        prioritized_buffer_d.py:221-234), draws the uniforms and refreshes ~100 bytes of parameters."""
+        prioritized_buffer_d.py:221-234), draws the uniforms and refreshes ~100 bytes of parameters.
+        ``device_apportion`` (with ``static_exchange``): the all-gather of the shard sums is captured too and the
+        apportioning (counts, per-draw beta) runs in a one-thread kernel, so the host never waits for the device: per
+        update it draws ``members x batch_size`` uniforms and replays.  Throughput mode: np.random is consumed in
+        fixed-size blocks instead of the reference's apportioned sizes (identical on a group of one)."""
         if static_exchange:
-            return self._enable_static_graph(warmup)
+            return self._enable_static_graph(warmup, device_apportion)
         buf = self.replay_buffer
         dev = buf.buffer_device
         buf._exchange()                                   # collective: agree on the row layout
@@ -189,7 +193,7 @@ class DQNApex(DQNPer):
         t.cuda.synchronize(dev)
 
     # ------------------------------------------------------------------ fixed-shape, single-graph update
-    def _enable_static_graph(self, warmup: int = 3):
+    def _enable_static_graph(self, warmup: int = 3, device_apportion: bool = False):
         import struct
         import torch.distributed as dist
         from ..._lib import lib, ptr, check, stream_ptr
@@ -211,7 +215,13 @@ class DQNApex(DQNPer):
               "send2": z((P * cap, 24), t.uint8), "recv2": z((P * cap, 24), t.uint8),
               "u_idx": z(P * cap, t.int64), "u_pri": z(P * cap, t.float32), "u_valid": z(P * cap, t.uint8),
               "d_idx": [z(cap, t.int64) for _ in range(P)], "d_isw": [z(cap, t.float64) for _ in range(P)],
-              "struct": struct}
+              "struct": struct, "device_apportion": bool(device_apportion),
+              "sums": z(P, t.float64), "beta": z(1, t.float64), "nstored": z(1, t.int64),
+              # device apportioning lets the host run ahead of the device, so what it writes per update goes through a
+              # small ring of pinned buffers guarded by events (copied in FRONT of the replay, not inside the graph)
+              "ring_uni": [t.zeros((P, cap), dtype=t.float64).pin_memory() for _ in range(4)],
+              "ring_ns": [t.zeros(1, dtype=t.int64).pin_memory() for _ in range(4)],
+              "ring_ev": [t.cuda.Event() for _ in range(4)], "ring_i": 0}
         params = list(self.qnet.parameters())
         self._flat_grad = t.zeros(sum(p.numel() for p in params), dtype=t.float32, device=dev)
         o = 0
@@ -226,8 +236,17 @@ class DQNApex(DQNPer):
         tree, table = buf.wt_tree.handle, buf.buffer_version_table
 
         def body():
-            for name in ("counts", "params", "uni", "scale"):
-                st[name].copy_(st[name + "_pin"], non_blocking=True)
+            if st["device_apportion"]:
+                if P > 1:
+                    dist.all_gather_into_tensor(st["sums"], buf.weight_sum_tensor(), group=grp.pg)
+                else:
+                    st["sums"].copy_(buf.weight_sum_tensor())
+                check(lib.mb_wire_apportion(ptr(st["sums"]), P, B, me, capB, ptr(st["nstored"]), ptr(st["beta"]),
+                                            float(buf.beta_increment_per_sampling), ptr(st["counts"]), ptr(st["scale"]),
+                                            ptr(st["params"]), stream_ptr()))
+            else:
+                for name in ("counts", "params", "uni", "scale"):
+                    st[name].copy_(st[name + "_pin"], non_blocking=True)
             for r in range(P):                           # this shard serves every requester, member order
                 wire = st["send"][r * cap:(r + 1) * cap]
                 check(lib.mb_per_sample(tree, ptr(st["uni"][r]), cap, 0, 0.0, 0.0, ptr(st["params"][r]), ptr(st["d_idx"][r]),
@@ -276,6 +295,7 @@ class DQNApex(DQNPer):
         np_state = np.random.get_state()
         self.qnet.train()
         self._static = st
+        st["beta"].fill_(float(beta0))
         self._static_prepare()                           # collective: real counts / uniforms for the warm-up
         cur, side = t.cuda.current_stream(dev), t.cuda.Stream(device=dev)
         side.wait_stream(cur)
@@ -301,6 +321,7 @@ class DQNApex(DQNPer):
                             v.zero_()
         buf.wt_tree.restore(tree_snap)
         buf.curr_beta = beta0
+        st["beta"].fill_(float(beta0))
         np.random.set_state(np_state)
         t.cuda.synchronize(dev)
         if P > 1:
@@ -312,6 +333,19 @@ class DQNApex(DQNPer):
         from ...parallel.exchange import shard_sample_sizes
         st, buf, grp = self._static, self.replay_buffer, self.apex_group
         P, me, cap = st["P"], grp.index, st["cap"]
+        if st["device_apportion"]:
+            # nothing here depends on the device: fixed-size uniform blocks, the stored-row count, and a host mirror
+            # of beta (it advances once per requester served, :425-427; the device holds the authoritative value)
+            i = st["ring_i"] = (st["ring_i"] + 1) % len(st["ring_ev"])
+            st["ring_ev"][i].synchronize()                  # the copy that last used this slot has finished
+            st["ring_uni"][i].numpy()[:] = np.random.uniform(size=(P, cap))
+            st["ring_ns"][i].numpy()[0] = len(buf.storage)
+            st["uni"].copy_(st["ring_uni"][i], non_blocking=True)
+            st["nstored"].copy_(st["ring_ns"][i], non_blocking=True)
+            st["ring_ev"][i].record()
+            for _ in range(P):
+                buf.curr_beta = np.min([1.0, buf.curr_beta + buf.beta_increment_per_sampling])
+            return self.batch_size
         sums = grp.all_gather_f64(buf.weight_sum_tensor()).view(-1).tolist()
         ssize, total = shard_sample_sizes(sums, self.batch_size)
         n, n_mine = int(sum(ssize)), int(ssize[me])

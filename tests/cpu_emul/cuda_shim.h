@@ -34,6 +34,9 @@ inline float __ldcg(const float *p) { return *p; }
 inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }   // volatile: no contraction
 inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 
 // Run `kernel()` for every thread of every CTA of a 1-D grid, CTAs one after the other.
 inline void shim_launch(unsigned grid, unsigned block, const std::function<void()> &kernel) {

@@ -60,4 +60,13 @@ int emul_wire_update_mask(const char *recv, int P, int64_t cap, const int64_t *c
     return 0;
 }
 
+int emul_wire_apportion(const double *sums, int P, int64_t batch, int self_block, int64_t merged_rows,
+                        const int64_t *n_stored, double *beta, double beta_increment, int64_t *counts, double *scale,
+                        mb_per_params *params) {
+    shim_launch(1, 32, [&] {
+        wire_apportion_kernel(sums, P, batch, self_block, merged_rows, n_stored, beta, beta_increment, counts, scale, params);
+    });
+    return 0;
+}
+
 }  // extern "C"

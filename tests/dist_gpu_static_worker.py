@@ -61,6 +61,21 @@ def main():
         np.testing.assert_allclose(b.replay_buffer.wt_tree.weights, a.replay_buffer.wt_tree.weights, rtol=1e-5, atol=1e-9)
         np.testing.assert_allclose(flat(b.qnet), flat(a.qnet), rtol=1e-4, atol=1e-6)
         assert a.replay_buffer.curr_beta == b.replay_buffer.curr_beta
+    # device-side apportioning (host never reads the shard sums): a valid trajectory -- finite losses, consistent
+    # trees, identical weights on every member, beta advanced once per requester served
+    c = make()
+    c.enable_cuda_graph(static_exchange=True, device_apportion=True)
+    beta0 = float(c.replay_buffer.curr_beta)
+    for step in range(6):
+        lc = c.update_device().item()
+        assert np.isfinite(lc) and lc >= 0.0, (step, lc)
+    t.cuda.synchronize()
+    c.replay_buffer.wt_tree.check()
+    assert abs(float(c._static["beta"].item()) - min(1.0, beta0 + 6 * world * 1e-3)) < 1e-12
+    wc = t.from_numpy(flat(c.qnet)).cuda()
+    wcs = [t.empty_like(wc) for _ in range(world)]
+    dist.all_gather(wcs, wc)
+    assert all(t.equal(wcs[0], x) for x in wcs)
     # every member holds the same weights after averaged gradients
     w = t.from_numpy(flat(b.qnet)).cuda()
     ws = [t.empty_like(w) for _ in range(world)]

@@ -110,3 +110,41 @@ def test_fixed_shape_exchange_replayed_for_P_shards(wire, P, pitch):
                     assert u_val[e] == int(table[m][s] == version_at_sample[m][s])
                 else:
                     assert u_val[e] == 0 and u_idx[e] == 0
+
+
+class MbPerParams(C.Structure):
+    _fields_ = [("beta", C.c_double), ("all_weight_sum", C.c_double), ("n_stored", C.c_int64), ("step", C.c_int64),
+                ("n_draw", C.c_int64)]
+
+
+@pytest.mark.parametrize("P", [1, 2, 4, 8])
+def test_device_apportioning_matches_host_apportioning(wire, P):
+    """wire_apportion_kernel against the host formula the dynamic exchange uses (prioritized_buffer_d.py:229-234 via
+    oracle.per.shard_sample_sizes) and the per-draw beta schedule (prioritized_buffer.py:425-427): bit-identical."""
+    from oracle.per import shard_sample_sizes
+    assert C.sizeof(MbPerParams) == 40
+    rng = np.random.RandomState(P)
+    for trial in range(20):
+        B = int(rng.choice([24, 100, 512]))
+        sums = rng.exponential(size=P) * rng.choice([1.0, 1e3, 1e-3], size=P)
+        if P > 2 and trial % 3 == 0:
+            sums[1] = 0.0                                   # an empty shard draws nothing
+        me = int(rng.randint(P))
+        beta0, inc = float(rng.choice([0.4, 0.9995, 1.0])), 1e-3
+        n_stored = np.array([12345], dtype=np.int64)
+        beta = np.array([beta0])
+        counts, scale = np.zeros(P, np.int64), np.zeros(1)
+        params = (MbPerParams * P)()
+        capB = B + P
+        assert wire.emul_wire_apportion(p(sums), P, C.c_int64(B), me, C.c_int64(capB), p(n_stored), p(beta), C.c_double(inc),
+                                        p(counts), p(scale), params) == 0
+        ssize, total = shard_sample_sizes(list(sums), B)
+        assert counts.tolist() == ssize
+        assert scale[0] == capB / sum(ssize)
+        b = beta0
+        for r in range(P):
+            assert (params[r].beta, params[r].all_weight_sum, params[r].n_stored, params[r].step, params[r].n_draw) == \
+                (b, total, 12345, 0, ssize[me])
+            if ssize[me] > 0:
+                b = float(np.min([1.0, b + inc]))
+        assert beta[0] == b
