@@ -42,6 +42,12 @@ def pytest_collection_modifyitems(config, items):
     except Exception:
         has_gpu = False
     if has_gpu:
+        # a kernel that never returns must not hold the GPU box until its own limit: pytest-timeout's thread
+        # method ends the process (a signal cannot interrupt a blocked CUDA call)
+        if config.pluginmanager.hasplugin("timeout"):
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(600, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
