@@ -3,7 +3,7 @@
 #   gpurun --gpus 2 --timeout 900 -- 'bash tools/second_call_next_round.sh'
 # Every torchrun sits under `timeout`; bench.py arms its own watchdog as well.
 mkdir -p gpurun_out
-timeout 420 python -m pytest tests/test_gpu_distributed.py tests/test_gpu_zz_static_exchange.py -m gpu -q -rxXs \
+timeout 420 python -m pytest tests/test_gpu_distributed.py tests/test_gpu_zz_static_exchange.py tests/test_gpu_zz_impala_exchange.py -m gpu -q -rxXs \
     -p no:cacheprovider > gpurun_out/next2_pytest.txt 2>&1
 tail -15 gpurun_out/next2_pytest.txt
 run() {   # name, flags
