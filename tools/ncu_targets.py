@@ -28,7 +28,7 @@ sp = lambda: _lib.stream_ptr()
 for rep in range(4):
     u = t.rand(B, dtype=t.float64, device=dev)
     n, fields, idx, isw = buf.sample_device(B, uniform=u)
-    idx = idx % rows
+    idx = t.sort(idx % rows)[0]          # stays ascending: the write-back must take the sorted kernel, as in the learner
     fields = buf.storage.gather(idx)
     q = [t.randn(B, 6, device=dev) for _ in range(3)]
     out = ops.td_dqn(q[0], q[1], q[2], fields["action/action"], fields["reward"], fields["terminal"], 0.99,
