@@ -217,6 +217,8 @@ def build_learner(a, device, seed, world=1):
                           (PushPullModelServer("qnet", group, 0, lockstep=True),), batch_size=a.batch, learning_rate=1e-3,
                           discount=0.99, update_rate=0.005, replay_size=a.replay_rows, learner_group=group)
         buf = learner.replay_buffer
+        learner.use_fused_program = a.net in ("fused-program", "fused-rows")     # honoured by the fixed-shape exchange
+        learner.fused_kind = "rows" if a.net == "fused-rows" else "program"
     else:
         buf = PrioritizedBuffer(buffer_size=a.replay_rows, buffer_device=device)
         import functools

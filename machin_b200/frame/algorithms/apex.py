@@ -234,6 +234,7 @@ class DQNApex(DQNPer):
         fields = buf.storage.fields
         grp_f = lambda fl, attr: {f.key: fl[f.name] for f in fields.values() if f.attr == attr and f.kind == "major"}
         tree, table = buf.wt_tree.handle, buf.buffer_version_table
+        prog = self._static_program(st, capB) if self.use_fused_program else None
 
         def body():
             if st["device_apportion"]:
@@ -260,16 +261,22 @@ class DQNApex(DQNPer):
                 st["recv"].copy_(st["send"])
             check(lib.mb_wire_compact(ptr(st["recv"]), P, cap, W, pitch, ptr(st["counts"]), ptr(st["merged"]), capB,
                                       ptr(st["idx"]), ptr(st["ver"]), ptr(st["isw"]), ptr(st["scale"]), stream_ptr()))
-            fl = buf.storage.unpack(st["merged"])
-            state, action, next_state = grp_f(fl, "state"), grp_f(fl, "action"), grp_f(fl, "next_state")
-            with t.no_grad():
-                nq = self._criticize(next_state)
-                tq = self._criticize(next_state, True)
-            q = self._criticize(state)
-            td = ops.td_dqn(q.detach(), nq, tq, self.action_get_function(action), fl["reward"], fl["terminal"],
-                            self.discount, is_weight=st["isw"], mode=self.mode, want_grad=True)
-            self._flat_grad.zero_()
-            q.backward(td["grad_q"])
+            if prog is not None:
+                # fused value math (csrc/mlp.cu): forward x3 + TD + backward straight into the flat gradient buffer
+                buf.storage.unpack(st["merged"], names=prog["names"], out=prog["fields"])
+                check(lib.mb_mlp_program_run(prog["handle"], stream_ptr()))
+                td = {"abs_error": prog["abs"], "loss_elem": prog["loss"]}
+            else:
+                fl = buf.storage.unpack(st["merged"])
+                state, action, next_state = grp_f(fl, "state"), grp_f(fl, "action"), grp_f(fl, "next_state")
+                with t.no_grad():
+                    nq = self._criticize(next_state)
+                    tq = self._criticize(next_state, True)
+                q = self._criticize(state)
+                td = ops.td_dqn(q.detach(), nq, tq, self.action_get_function(action), fl["reward"], fl["terminal"],
+                                self.discount, is_weight=st["isw"], mode=self.mode, want_grad=True)
+                self._flat_grad.zero_()
+                q.backward(td["grad_q"])
             if P > 1:
                 dist.all_reduce(self._flat_grad, group=self.learner_group.pg if self.learner_group is not None else grp.pg)
                 self._flat_grad.div_(P)
@@ -326,6 +333,46 @@ class DQNApex(DQNPer):
         t.cuda.synchronize(dev)
         if P > 1:
             grp.barrier()
+
+    def _static_program(self, st, rows):
+        """Opt-in (``use_fused_program``): the fused value-math program of DQNPer over the merged, padded batch of the
+        fixed-shape exchange -- inputs are the unpacked merged rows, the IS weights are the compacted ones (padding
+        rows weigh 0), gradients land in the flat buffer the all-reduce runs on."""
+        import ctypes as C
+        from ...model import FusedMLP
+        from ..._lib import lib, ptr, check
+        from .dqn_per import DQNPer
+        buf = self.replay_buffer
+        fields = buf.storage.fields
+        sk = [f for f in fields.values() if f.attr == "state" and f.kind == "major"]
+        nk = [f for f in fields.values() if f.attr == "next_state" and f.kind == "major"]
+        ak = [f for f in fields.values() if f.attr == "action" and f.kind == "major"]
+        ok = (isinstance(self.qnet, FusedMLP) and isinstance(self.qnet_target, FusedMLP) and self._fused_mse
+              and self.qnet.sizes == self.qnet_target.sizes and len(sk) == len(nk) == len(ak) == 1
+              and sk[0].dtype == t.float32 and sk[0].shape == (self.qnet.sizes[0],) and ak[0].dtype == t.int64
+              and fields["reward"].dtype == t.float32 and fields["terminal"].dtype == t.bool
+              and type(self)._criticize is DQNPer._criticize)
+        if not ok:
+            raise RuntimeError("use_fused_program needs FusedMLP Q-nets, MSELoss and one float32 state / int64 action key")
+        dev, sizes = buf.buffer_device, self.qnet.sizes
+        L = len(sizes) - 1
+        names = [sk[0].name, ak[0].name, "reward", nk[0].name, "terminal"]
+        prog = {"names": names,
+                "fields": {n: t.zeros((rows,) + fields[n].shape, dtype=fields[n].dtype, device=dev) for n in names},
+                "y": t.empty((rows, 1), dtype=t.float32, device=dev), "av": t.empty((rows, 1), dtype=t.float32, device=dev),
+                "abs": t.empty(rows, dtype=t.float32, device=dev), "loss": t.empty((rows, 1), dtype=t.float64, device=dev)}
+        plist = lambda net: [p for layer in net.layers for p in (layer.weight, layer.bias)]
+        arr = lambda xs: (C.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
+        handle = C.c_void_p()
+        with t.cuda.device(dev):
+            create = lib.mb_dqn_mlp_rows_create if self.fused_kind == "rows" else lib.mb_dqn_mlp_program_create
+            check(create(dev.index, L, (C.c_int * (L + 1))(*sizes), rows, arr(plist(self.qnet)), arr(plist(self.qnet_target)),
+                         arr([p.grad for p in plist(self.qnet)]), ptr(prog["fields"][names[0]]), ptr(prog["fields"][names[3]]),
+                         ptr(prog["fields"][names[1]]), ptr(prog["fields"]["reward"]), ptr(prog["fields"]["terminal"]),
+                         ptr(st["isw"]), float(self.discount), 0 if self.mode == "double" else 1, ptr(prog["y"]),
+                         ptr(prog["av"]), ptr(prog["abs"]), ptr(prog["loss"]), C.byref(handle)))
+        prog["handle"] = handle
+        return prog
 
     def _static_prepare(self):
         """Host part of a fixed-shape update: read the shard sums (one sync), apportion, draw this shard's

@@ -104,13 +104,14 @@ class DeviceRing:
                                           arr, len(names), _lib.stream_ptr(stream)))
         return out
 
-    def unpack(self, rows: t.Tensor, names=None, stream=None) -> Dict[str, t.Tensor]:
+    def unpack(self, rows: t.Tensor, names=None, stream=None, out: Dict[str, t.Tensor] = None) -> Dict[str, t.Tensor]:
         """Split ``n`` packed rows (u8[n, >= pitch], e.g. wire rows received from a peer shard, which carry
-        metadata behind the payload) into dense fields."""
+        metadata behind the payload) into dense fields.  ``out``: optional pre-allocated dense tensors."""
         names = list(self.fields) if names is None else [n for n in names if n in self.fields]
         n = int(rows.shape[0])
         assert rows.is_contiguous() and rows.shape[1] >= self.pitch
-        out = {k: t.empty((n,) + self.fields[k].shape, dtype=self.fields[k].dtype, device=rows.device) for k in names}
+        if out is None:
+            out = {k: t.empty((n,) + self.fields[k].shape, dtype=self.fields[k].dtype, device=rows.device) for k in names}
         if n and names:
             arr = self._field_array(names, out)
             _lib.check(lib.mb_rows_gather(_lib.ptr(rows), int(rows.shape[1]), n, None, n, arr, len(names),

@@ -100,3 +100,41 @@ def test_rows_program_rejects_wide_layers():
     dqn.use_fused_program, dqn.fused_kind = True, "rows"
     with pytest.raises(RuntimeError, match="libmachin_b200"):
         dqn.update()
+
+
+@pytest.mark.parametrize("kind", ["rows", "program"])
+def test_fused_program_inside_fixed_shape_exchange_single_member(kind):
+    """DQNApex's fixed-shape update (group of one) with the fused value-math program over the merged, padded batch
+    against the same update through autograd."""
+    from machin_b200.frame.algorithms import DQNApex
+    from machin_b200.model import FusedMLP
+    from machin_b200.parallel import LocalGroup
+    sizes, N, B = [12, 32, 32, 5], 3000, 64
+    S, A = sizes[0], sizes[-1]
+
+    def make(fused):
+        t.manual_seed(0)
+        q, qt = FusedMLP(sizes).cuda(), FusedMLP(sizes).cuda()
+        learner = DQNApex(q, qt, t.optim.SGD, t.nn.MSELoss(reduction="none"), LocalGroup(device="cuda:0"), (), batch_size=B,
+                          learning_rate=0.05, discount=0.9, update_rate=0.1, replay_size=4096)
+        rng = np.random.RandomState(3)
+        learner.replay_buffer.store_episode_tensors(
+            {"state": {"state": t.from_numpy(rng.randn(N, S).astype(np.float32))},
+             "action": {"action": t.from_numpy(rng.randint(0, A, size=(N, 1)))},
+             "next_state": {"state": t.from_numpy(rng.randn(N, S).astype(np.float32))}},
+            {"reward": t.from_numpy(rng.randn(N, 1).astype(np.float32)), "terminal": t.from_numpy(rng.rand(N, 1) < 0.1)},
+            priorities=rng.exponential(size=N))
+        if fused:
+            learner.use_fused_program, learner.fused_kind = True, kind
+        learner.enable_cuda_graph(static_exchange=True)
+        return learner
+
+    a, b = make(False), make(True)
+    for step in range(5):
+        np.random.seed(100 + step)
+        la = a.update_device().item()
+        np.random.seed(100 + step)
+        lb = b.update_device().item()
+        assert abs(la - lb) <= 1e-5 * max(1e-3, abs(la)), (step, la, lb)
+        np.testing.assert_allclose(b.replay_buffer.wt_tree.weights, a.replay_buffer.wt_tree.weights, rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(_flat(b.qnet), _flat(a.qnet), rtol=1e-5, atol=1e-6)

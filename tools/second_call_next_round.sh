@@ -22,3 +22,5 @@ PY
 run static            ""
 run device_apportion  "--device-apportion"
 run dynamic           "--dynamic-exchange"
+run static_fused_rows "--net fused-rows"
+run devapp_fused_rows "--net fused-rows --device-apportion"
