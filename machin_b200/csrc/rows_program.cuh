@@ -39,45 +39,63 @@ __device__ __forceinline__ float4 rows_load_b(const float *__restrict__ row, int
 }
 
 // acc[r][c] = sum_k As[(ty * MR + r) * ap + k] * Bg[k * N + j0 + c]      (rows in shared memory, B k-major in global)
+// The weights come straight from L2 and a CTA of 8 warps has an SM to itself, so nothing else hides the ~700-cycle
+// latency: three register buffers of 8 k-steps rotate -- while one is multiplied (~320 cycles) the loads of the
+// next two are in flight -- and the tail of K is loaded predicated in the same batches instead of one dependent
+// load per step.  k ascends, one fmaf per term: the summation order does not depend on the buffering.
 template <int MR, bool kVec>
 __device__ __forceinline__ void rows_matmul_impl(const float *As, int ap, int K, const float *__restrict__ Bg, int N,
                                                  float (&acc)[MR][4]) {
     const int ty = threadIdx.x >> 6, j0 = (threadIdx.x & 63) * 4;
     const float *a0 = As + (ty * MR) * ap;
-    int k = 0;
-    for (; k + 8 <= K; k += 8) {
-        float4 b[8];
+    auto load8 = [&](float4 (&b)[8], int k) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) b[u] = rows_load_b<kVec>(Bg + (int64_t)(k + u) * N, j0, N);   // 8 loads in flight
+        for (int u = 0; u < 8; ++u) {
+            if (k + u < K) b[u] = rows_load_b<kVec>(Bg + (int64_t)(k + u) * N, j0, N);
+            else b[u] = float4{0.0f, 0.0f, 0.0f, 0.0f};
+        }
+    };
+    auto mul8 = [&](const float4 (&b)[8], int k) {
+        if (k >= K) return;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            float4 a[MR];
-#pragma unroll
-            for (int r = 0; r < MR; ++r) a[r] = *reinterpret_cast<const float4 *>(a0 + r * ap + k + 4 * h);   // warp-wide broadcast
+            const int kh = k + 4 * h;
+            if (kh >= K) break;
+            float av[MR][4];
 #pragma unroll
             for (int r = 0; r < MR; ++r) {
-                const float av[4] = {a[r].x, a[r].y, a[r].z, a[r].w};
+                if (kh + 4 <= K) {                                // rows are 16-byte aligned at multiples of 4
+                    const float4 a = *reinterpret_cast<const float4 *>(a0 + r * ap + kh);   // warp-wide broadcast
+                    av[r][0] = a.x; av[r][1] = a.y; av[r][2] = a.z; av[r][3] = a.w;
+                } else {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const float4 bb = b[4 * h + kk];
-                    acc[r][0] = fmaf(av[kk], bb.x, acc[r][0]);
-                    acc[r][1] = fmaf(av[kk], bb.y, acc[r][1]);
-                    acc[r][2] = fmaf(av[kk], bb.z, acc[r][2]);
-                    acc[r][3] = fmaf(av[kk], bb.w, acc[r][3]);
+                    for (int kk = 0; kk < 4; ++kk) av[r][kk] = kh + kk < K ? a0[r * ap + kh + kk] : 0.0f;
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                if (kh + kk >= K) break;                          // exact term count: no +0 terms
+                const float4 bb = b[4 * h + kk];
+#pragma unroll
+                for (int r = 0; r < MR; ++r) {
+                    acc[r][0] = fmaf(av[r][kk], bb.x, acc[r][0]);
+                    acc[r][1] = fmaf(av[r][kk], bb.y, acc[r][1]);
+                    acc[r][2] = fmaf(av[r][kk], bb.z, acc[r][2]);
+                    acc[r][3] = fmaf(av[r][kk], bb.w, acc[r][3]);
                 }
             }
         }
-    }
-    for (; k < K; ++k) {
-        const float4 bb = rows_load_b<kVec>(Bg + (int64_t)k * N, j0, N);
-#pragma unroll
-        for (int r = 0; r < MR; ++r) {
-            const float av = a0[r * ap + k];
-            acc[r][0] = fmaf(av, bb.x, acc[r][0]);
-            acc[r][1] = fmaf(av, bb.y, acc[r][1]);
-            acc[r][2] = fmaf(av, bb.z, acc[r][2]);
-            acc[r][3] = fmaf(av, bb.w, acc[r][3]);
-        }
+    };
+    float4 b0[8], b1[8], b2[8];
+    load8(b0, 0);
+    load8(b1, 8);
+    for (int k = 0; k < K; k += 24) {
+        load8(b2, k + 16);
+        mul8(b0, k);
+        load8(b0, k + 24);
+        mul8(b1, k + 8);
+        load8(b1, k + 32);
+        mul8(b2, k + 16);
     }
 }
 
