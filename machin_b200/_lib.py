@@ -91,6 +91,7 @@ SIGNATURES = {
     "mb_dqn_mlp_rows_create": (i32, [i32, i32, C.POINTER(i32), i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, vp,
                                      vp, vp, vp, vp, f32, i32, vp, vp, vp, vp, C.POINTER(vp)]),
     "mb_mlp_program_run": (i32, [vp, vp]),
+    "mb_mlp_program_run_part": (i32, [vp, i32, vp]),
     "mb_mlp_program_destroy": (i32, [vp]),
     "mb_adam_step_multi": (i32, [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i32, vp,
                                  f64, f64, f64, f64, f64, vp]),

@@ -268,9 +268,20 @@ class DQNPer(TorchFramework):
         buf = self.replay_buffer
         buf._draw(self.batch_size, uniform=uniform, use_device_params=use_device_params, out=(st["index"], st["isw"]))
         buf.storage.gather(st["index"], names=st["names"], out=st["fields"])
+        forked = None
         with t.cuda.device(buf.buffer_device):
-            check(lib.mb_mlp_program_run(st["handle"], stream_ptr()))
-        buf.update_priority(st["abs"], st["index"])
+            check(lib.mb_mlp_program_run_part(st["handle"], 0, stream_ptr()))        # forward x3, TD, backward-input
+            if self.overlap_priority_update:
+                # |delta| is ready: the write-back runs beside the weight gradients, the optimizer and the target update
+                if self._side_stream is None:
+                    self._side_stream = t.cuda.Stream(device=buf.buffer_device)
+                forked = (t.cuda.current_stream(buf.buffer_device), self._side_stream)
+                forked[1].wait_stream(forked[0])
+                with t.cuda.stream(forked[1]):
+                    buf.update_priority(st["abs"], st["index"])
+            check(lib.mb_mlp_program_run_part(st["handle"], 1, stream_ptr()))        # dW, db
+        if forked is None:
+            buf.update_priority(st["abs"], st["index"])
         if update_value:
             self._sync_grads()
             if np.isfinite(self.grad_max):
@@ -283,6 +294,8 @@ class DQNPer(TorchFramework):
                 self._update_counter += 1
                 if self._update_counter % self.update_steps == 0:
                     hard_update(self.qnet_target, self.qnet)
+        if forked is not None:
+            forked[0].wait_stream(forked[1])     # join before the next draw reads the tree
         return st["loss"].mean()
 
     def _step(self, update_value, update_target, uniform, use_device_params) -> t.Tensor:

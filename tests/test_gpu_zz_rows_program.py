@@ -138,3 +138,41 @@ def test_fused_program_inside_fixed_shape_exchange_single_member(kind):
         assert abs(la - lb) <= 1e-5 * max(1e-3, abs(la)), (step, la, lb)
         np.testing.assert_allclose(b.replay_buffer.wt_tree.weights, a.replay_buffer.wt_tree.weights, rtol=1e-5, atol=1e-9)
         np.testing.assert_allclose(_flat(b.qnet), _flat(a.qnet), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_rows_program_with_overlapped_priority_update(graph):
+    """overlap_priority_update in the fused step: the write-back starts after part 0 (forward, TD, backward-input) on a
+    second stream, beside part 1 (dW), the optimizer and the target update -- same trajectory."""
+    from machin_b200.frame.algorithms import DQNPer
+    from machin_b200.model import FusedAdam, FusedMLP
+    sizes, N, B = [12, 32, 32, 5], 3000, 64
+    S, A = sizes[0], sizes[-1]
+
+    def make(overlap):
+        t.manual_seed(1)
+        q, qt = FusedMLP(sizes).cuda(), FusedMLP(sizes).cuda()
+        learner = DQNPer(q, qt, FusedAdam, t.nn.MSELoss(reduction="none"), batch_size=B, learning_rate=1e-3,
+                         discount=0.9, update_rate=0.1, replay_size=4096)
+        rng = np.random.RandomState(3)
+        learner.replay_buffer.store_episode_tensors(
+            {"state": {"state": t.from_numpy(rng.randn(N, S).astype(np.float32))},
+             "action": {"action": t.from_numpy(rng.randint(0, A, size=(N, 1)))},
+             "next_state": {"state": t.from_numpy(rng.randn(N, S).astype(np.float32))}},
+            {"reward": t.from_numpy(rng.randn(N, 1).astype(np.float32)), "terminal": t.from_numpy(rng.rand(N, 1) < 0.1)},
+            priorities=rng.exponential(size=N))
+        learner.use_fused_program, learner.fused_kind, learner.overlap_priority_update = True, "rows", overlap
+        if graph:
+            learner.enable_cuda_graph()
+        return learner
+
+    a, b = make(False), make(True)
+    for step in range(6):
+        np.random.seed(70 + step)
+        la = a.update_device().item()
+        np.random.seed(70 + step)
+        lb = b.update_device().item()
+        assert la == lb, (step, la, lb)                    # the same kernels on the same inputs
+        assert np.array_equal(a.replay_buffer.wt_tree.weights, b.replay_buffer.wt_tree.weights)
+        assert np.array_equal(_flat(a.qnet), _flat(b.qnet))
+    b.replay_buffer.wt_tree.check()
