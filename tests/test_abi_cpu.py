@@ -137,3 +137,33 @@ def test_distributed_default_priorities_vs_reference():
             tree.update_leaf_batch(oper.normalize_priority(g["wb_pri"]), g["wb_idx"])
             assert np.array_equal(tree.weights, g["tree_after_wb"])
             assert isinstance(tree.get_leaf_max(), np.float32)      # the float32 write-back now owns max_leaf
+
+
+def test_entry_points_reject_bad_arguments_before_touching_the_device():
+    """Argument validation happens before any CUDA call, so it can be exercised without a GPU: NULL handles,
+    negative counts, unsupported dtypes -> MB_ERR_INVALID (mapped to RuntimeError by the shim)."""
+    import ctypes as C
+    from machin_b200 import _lib
+    from machin_b200._lib import lib
+    null = C.c_void_p(0)
+    one = (C.c_int64 * 1)(0)
+    cases = [
+        lib.mb_tree_update_batch(null, one, one, _lib.MB_F64, null, 1, null),
+        lib.mb_tree_update_priority(null, one, one, _lib.MB_F32, null, 1, 1e-2, 0.6, null),
+        lib.mb_tree_find(null, one, 1, one, null),
+        lib.mb_per_sample(null, one, 1, 1, 0.0, 0.4, null, one, one, null),
+        lib.mb_rows_gather(null, 16, 1, one, 1, None, 0, null),
+        lib.mb_wire_compact(null, 1, 1, 40, 16, one, one, 2, one, one, one, null, null),
+        lib.mb_wire_apportion(null, 1, 1, 0, 2, one, one, 1e-3, one, one, one, null),
+        lib.mb_wire_apportion(one, 2, 1, 5, 3, one, one, 1e-3, one, one, one, null),      # self_block out of range
+        lib.mb_mlp_program_run(null, null),
+        lib.mb_mlp_program_run_part(null, 0, null),
+    ]
+    assert all(c == _lib.MB_ERR_INVALID for c in cases), cases
+    with pytest.raises(RuntimeError, match="libmachin_b200"):
+        _lib.check(_lib.MB_ERR_INVALID)
+    for status, message in ((_lib.MB_ERR_INDEX_OOB, "Index has elements out of boundary!"),
+                            (_lib.MB_ERR_DIM_MISMATCH, "Dimension of weights and indexes doesn't match!"),
+                            (_lib.MB_ERR_SIZE_MISMATCH, "Weights size must match tree size!")):
+        with pytest.raises(ValueError, match=message):          # the reference's own messages (SURVEY 8b)
+            _lib.check(status)
