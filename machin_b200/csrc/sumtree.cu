@@ -484,12 +484,16 @@ int mb_tree_create(int64_t size, int device, mb_tree **out) {
     tree_state_reset<<<1, 1>>>(t->dev.st, 0.0);
     MB_CUDA(cudaFuncSetAttribute(tree_update_sorted<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     MB_CUDA(cudaFuncSetAttribute(tree_update_sorted<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    MB_CUDA(cudaFuncSetAttribute(tree_update_sorted_v2<float, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    MB_CUDA(cudaFuncSetAttribute(tree_update_sorted_v2<double, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    MB_CUDA(cudaFuncSetAttribute(tree_update_sorted_v2<float, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    MB_CUDA(cudaFuncSetAttribute(tree_update_sorted_v2<double, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    MB_CUDA(cudaFuncSetAttribute(tree_update_sorted_v2<float, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    MB_CUDA(cudaFuncSetAttribute(tree_update_sorted_v2<double, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    {   // opt-in variants (MB_SORTED_CLUSTER / MB_SORTED_ASYNC): a failure here must not take the default path down
+        const void *v2[] = {(const void *)tree_update_sorted_v2<float, 3, false>, (const void *)tree_update_sorted_v2<double, 3, false>,
+                            (const void *)tree_update_sorted_v2<float, 3, true>, (const void *)tree_update_sorted_v2<double, 3, true>,
+                            (const void *)tree_update_sorted_v2<float, 0, true>, (const void *)tree_update_sorted_v2<double, 0, true>};
+        for (const void *f : v2)
+            if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess) {
+                cudaGetLastError();
+                t->sorted_cluster = t->sorted_async = 0;
+            }
+    }
     int per_sm = 0;
     MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_update_kernel<double, true>, 1024, 0));
     int sms = mb::kNumSMs;
