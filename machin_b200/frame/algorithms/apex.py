@@ -214,7 +214,7 @@ class DQNApex(DQNPer):
               "merged": z((capB, W), t.uint8), "idx": z(capB, t.int64), "ver": z(capB, t.int64), "isw": z(capB, t.float64),
               "send2": z((P * cap, 24), t.uint8), "recv2": z((P * cap, 24), t.uint8),
               "u_idx": z(P * cap, t.int64), "u_pri": z(P * cap, t.float32), "u_valid": z(P * cap, t.uint8),
-              "d_idx": [z(cap, t.int64) for _ in range(P)], "d_isw": [z(cap, t.float64) for _ in range(P)],
+              "d_idx": z((P, cap), t.int64), "d_isw": z((P, cap), t.float64),       # row r: the draw for requester r
               "struct": struct, "device_apportion": bool(device_apportion),
               "sums": z(P, t.float64), "beta": z(1, t.float64), "nstored": z(1, t.int64),
               # device apportioning lets the host run ahead of the device, so what it writes per update goes through a
@@ -249,12 +249,12 @@ class DQNApex(DQNPer):
                 for name in ("counts", "params", "uni", "scale"):
                     st[name].copy_(st[name + "_pin"], non_blocking=True)
             for r in range(P):                           # this shard serves every requester, member order
-                wire = st["send"][r * cap:(r + 1) * cap]
                 check(lib.mb_per_sample(tree, ptr(st["uni"][r]), cap, 0, 0.0, 0.0, ptr(st["params"][r]), ptr(st["d_idx"][r]),
                                         ptr(st["d_isw"][r]), stream_ptr()))
-                buf.storage.gather_into_wire(st["d_idx"][r], wire)
-                check(lib.mb_rows_pack_meta(ptr(wire), W, pitch, cap, ptr(st["d_idx"][r]), None, ptr(table),
-                                            ptr(st["d_isw"][r]), None, stream_ptr()))
+            # the P wire blocks are contiguous in requester order: ONE gather and ONE metadata launch for all of them
+            buf.storage.gather_into_wire(st["d_idx"].view(-1), st["send"])
+            check(lib.mb_rows_pack_meta(ptr(st["send"]), W, pitch, P * cap, ptr(st["d_idx"]), None, ptr(table),
+                                        ptr(st["d_isw"]), None, stream_ptr()))
             if P > 1:
                 dist.all_to_all_single(st["recv"], st["send"], group=grp.pg)
             else:
