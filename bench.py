@@ -55,6 +55,8 @@ def parse():
     p.add_argument("--dynamic-exchange", action="store_true",
                    help="N > 1: exactly-sized eager NCCL exchanges between two CUDA graphs instead of the default "
                         "fixed-shape exchange captured with the rest of the update in ONE graph")
+    p.add_argument("--batched-draw", action="store_true",
+                   help="N > 1, fixed-shape exchange, opt-in: the draws for all requesters in one launch")
     p.add_argument("--device-apportion", action="store_true",
                    help="N > 1, fixed-shape exchange, opt-in: shard sums all-gathered and apportioned inside the graph "
                         "(no host read per update)")
@@ -217,6 +219,7 @@ def build_learner(a, device, seed, world=1):
                           (PushPullModelServer("qnet", group, 0, lockstep=True),), batch_size=a.batch, learning_rate=1e-3,
                           discount=0.99, update_rate=0.005, replay_size=a.replay_rows, learner_group=group)
         buf = learner.replay_buffer
+        learner.batched_draw = a.batched_draw
         learner.use_fused_program = a.net in ("fused-program", "fused-rows")     # honoured by the fixed-shape exchange
         learner.fused_kind = "rows" if a.net == "fused-rows" else "program"
     else:

@@ -129,6 +129,12 @@ int mb_per_sample(mb_tree *tree, const double *d_uniform, int64_t n, int64_t n_s
                   double all_weight_sum, double beta, const mb_per_params *d_params,
                   int64_t *d_index, double *d_is_weight, void *stream);
 
+/* The same draw for n_requesters requesters in one launch (a shard serving every requester of a fixed-shape
+ * update): requester r reads d_uniform[r * n ..], d_params[r] (device-side parameters are mandatory here) and
+ * writes d_index[r * n ..] / d_is_weight[r * n ..].  Each requester's IS weights are normalised by its own max. */
+int mb_per_sample_multi(mb_tree *tree, const double *d_uniform, int64_t n, int n_requesters,
+                        const mb_per_params *d_params, int64_t *d_index, double *d_is_weight, void *stream);
+
 /* Host-buffer variants (same kernels; H2D + launch + D2H + synchronise inside the call). */
 int mb_tree_build_host(mb_tree *tree, const double *h_leaves, int64_t n);
 int mb_tree_find_host(mb_tree *tree, const double *h_query, int64_t n, int64_t *h_index);

@@ -64,6 +64,7 @@ SIGNATURES = {
     "mb_tree_update_priority": (i32, [vp, vp, vp, i32, vp, i64, f64, f64, vp]),
     "mb_tree_update_leaf": (i32, [vp, f64, i64, vp]),
     "mb_per_sample": (i32, [vp, vp, i64, i64, f64, f64, vp, vp, vp, vp]),
+    "mb_per_sample_multi": (i32, [vp, vp, i64, i32, vp, vp, vp, vp]),
     "mb_tree_build_host": (i32, [vp, vp, i64]),
     "mb_tree_find_host": (i32, [vp, vp, i64, vp]),
     "mb_tree_leaf_weight_host": (i32, [vp, vp, i64, vp]),

@@ -248,9 +248,13 @@ class DQNApex(DQNPer):
             else:
                 for name in ("counts", "params", "uni", "scale"):
                     st[name].copy_(st[name + "_pin"], non_blocking=True)
-            for r in range(P):                           # this shard serves every requester, member order
-                check(lib.mb_per_sample(tree, ptr(st["uni"][r]), cap, 0, 0.0, 0.0, ptr(st["params"][r]), ptr(st["d_idx"][r]),
-                                        ptr(st["d_isw"][r]), stream_ptr()))
+            if getattr(self, "batched_draw", False):     # opt-in: every requester's draw in ONE launch (one cluster each)
+                check(lib.mb_per_sample_multi(tree, ptr(st["uni"]), cap, P, ptr(st["params"]), ptr(st["d_idx"]),
+                                              ptr(st["d_isw"]), stream_ptr()))
+            else:
+                for r in range(P):                       # this shard serves every requester, member order
+                    check(lib.mb_per_sample(tree, ptr(st["uni"][r]), cap, 0, 0.0, 0.0, ptr(st["params"][r]),
+                                            ptr(st["d_idx"][r]), ptr(st["d_isw"][r]), stream_ptr()))
             # the P wire blocks are contiguous in requester order: ONE gather and ONE metadata launch for all of them
             buf.storage.gather_into_wire(st["d_idx"].view(-1), st["send"])
             check(lib.mb_rows_pack_meta(ptr(st["send"]), W, pitch, P * cap, ptr(st["d_idx"]), None, ptr(table),

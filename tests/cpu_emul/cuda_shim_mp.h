@@ -2,8 +2,7 @@
 // atomics and thread-block clusters: every CTA of the (single) cluster is a forked PROCESS, every CUDA thread an
 // OS thread of it; "global memory" is a MAP_SHARED region set up before the fork; function-scope __shared__
 // variables are plain statics of the CTA's process; cluster.sync() is a cross-process barrier and
-// cluster.map_shared_rank() fetches the bytes from the owning process, which serves such requests while it waits
-// in the barrier.  Slow and simple: it exists to run a kernel's DEVICE SOURCE in the build container (no GPU) and
+// cluster.map_shared_rank() fetches the bytes from the owning process, where a server thread answers such requests.  Slow and simple: it exists to run a kernel's DEVICE SOURCE in the build container (no GPU) and
 // compare against the oracle.  Nothing under machin_b200/ includes it.
 #pragma once
 #include <sys/mman.h>
@@ -42,6 +41,7 @@ namespace shim {
 
 constexpr int kMaxCtas = 8;
 struct Mailbox {                                // one per CTA, in shared memory
+    std::atomic<int> lock;                      // one requester at a time (any thread of any other CTA)
     std::atomic<int> request;                   // 0 idle, 1 pending, 2 answered
     const void *addr;
     int bytes;
@@ -113,6 +113,11 @@ inline double __shfl_xor_sync(unsigned, double v, int o) {
     shim::warp_barrier[w]->arrive_and_wait();
     return r;
 }
+inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
+using std::max;
+using std::min;
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
 
@@ -144,10 +149,7 @@ struct cluster_group {
         if (threadIdx.x == 0) {
             std::atomic<int> &c = shim::cluster->arrived[shim::sync_gen & 3];
             c.fetch_add(1);
-            while (c.load(std::memory_order_acquire) < shim::n_ctas) {   // serve DSMEM reads of my statics meanwhile
-                shim::serve_mailbox();
-                std::this_thread::yield();
-            }
+            while (c.load(std::memory_order_acquire) < shim::n_ctas) std::this_thread::yield();
             shim::sync_gen++;
         }
         __syncthreads();
@@ -157,12 +159,18 @@ struct cluster_group {
         if ((int)r == shim::rank) return p;
         static thread_local T copy;
         shim::Mailbox &m = shim::cluster->box[r];
+        int expected = 0;
+        while (!m.lock.compare_exchange_weak(expected, 1, std::memory_order_acquire)) {
+            expected = 0;
+            std::this_thread::yield();
+        }
         m.addr = p;                                  // same binary, same address in every CTA's process
         m.bytes = (int)sizeof(T);
         m.request.store(1, std::memory_order_release);
         while (m.request.load(std::memory_order_acquire) != 2) std::this_thread::yield();
         std::memcpy(&copy, m.reply, sizeof(T));
         m.request.store(0, std::memory_order_release);
+        m.lock.store(0, std::memory_order_release);
         return &copy;
     }
 };
@@ -180,7 +188,10 @@ inline double warp_max(double v) {
 namespace shim {
 
 // Launch one cluster of `ctas` CTAs of `block` threads (block % 32 == 0).  Returns 0 if every CTA exited cleanly.
-inline int launch(int ctas, unsigned block, size_t dyn_bytes, const std::function<void()> &kernel) {
+inline int launch(int ctas, unsigned block, size_t dyn_bytes, const std::function<void()> &kernel, int clusters = 1);
+
+inline int launch_one_cluster(int ctas, unsigned block, size_t dyn_bytes, const std::function<void()> &kernel,
+                              int first_block, int grid_blocks) {
     cluster = static_cast<ClusterShared *>(shared_alloc(sizeof(ClusterShared)));
     new (cluster) ClusterShared();
     n_ctas = ctas;
@@ -190,22 +201,31 @@ inline int launch(int ctas, unsigned block, size_t dyn_bytes, const std::functio
         if (pid < 0) { std::perror("fork"); return 4; }
         if (pid == 0) {
             rank = c;
-            blockIdx.x = (unsigned)c;
+            blockIdx.x = (unsigned)(first_block + c);
             blockDim.x = block;
-            gridDim.x = (unsigned)ctas;
+            gridDim.x = (unsigned)grid_blocks;
             dyn_smem = static_cast<unsigned char *>(std::aligned_alloc(16, dyn_bytes ? (dyn_bytes + 15) / 16 * 16 : 16));
             std::barrier<> bar((std::ptrdiff_t)block);
             cta_barrier = &bar;
             const unsigned warps = block / 32;
             warp_scratch = std::vector<WarpScratch>(warps);
             for (unsigned w = 0; w < warps; ++w) warp_barrier.emplace_back(new std::barrier<>(32));
+            // distributed shared memory: a server thread answers reads of this CTA's statics for as long as the CTA
+            // lives (CUDA kernels end with a cluster.sync() so that no CTA exits while a peer may still read it)
+            std::atomic<bool> stop{false};
+            std::thread server([&] {
+                while (!stop.load(std::memory_order_acquire)) {
+                    serve_mailbox();
+                    std::this_thread::yield();
+                }
+            });
             std::vector<std::thread> threads;
             threads.reserve(block);
             for (unsigned t = 0; t < block; ++t)
                 threads.emplace_back([&, t] { threadIdx.x = t; kernel(); });
             for (auto &th : threads) th.join();
-            // a CTA that is done may still be asked for its shared memory by a slower leader: the kernels under
-            // test end with a cluster.sync() for exactly that reason, so nothing more to serve here
+            stop.store(true, std::memory_order_release);
+            server.join();
             std::_Exit(0);
         }
         kids.push_back(pid);
@@ -217,6 +237,15 @@ inline int launch(int ctas, unsigned block, size_t dyn_bytes, const std::functio
         if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) bad = 5;
     }
     return bad;
+}
+
+// `clusters` independent clusters of `ctas` CTAs each (grid = clusters * ctas blocks), one cluster after the other.
+inline int launch(int ctas, unsigned block, size_t dyn_bytes, const std::function<void()> &kernel, int clusters) {
+    for (int cl = 0; cl < clusters; ++cl) {
+        const int rc = launch_one_cluster(ctas, block, dyn_bytes, kernel, cl * ctas, clusters * ctas);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 }  // namespace shim

@@ -50,6 +50,7 @@ def test_device_apportion_matches_host_apportion_single_member():
              "next_state": {"state": t.from_numpy(rng.randn(N, S).astype(np.float32))}},
             {"reward": t.from_numpy(rng.randn(N, 1).astype(np.float32)), "terminal": t.from_numpy(rng.rand(N, 1) < 0.1)},
             priorities=rng.exponential(size=N))
+        learner.batched_draw = device_apportion          # the one-launch draw for all requesters rides along
         learner.enable_cuda_graph(static_exchange=True, device_apportion=device_apportion)
         return learner
 

@@ -20,7 +20,8 @@ except Exception as e:
 PY
 }
 run static            ""
-run device_apportion  "--device-apportion"
+run batched_draw      "--batched-draw"
+run device_apportion  "--device-apportion --batched-draw"
 run dynamic           "--dynamic-exchange"
 run static_fused_rows "--net fused-rows"
 run devapp_fused_rows "--net fused-rows --device-apportion"
