@@ -64,6 +64,7 @@ def main():
     # device-side apportioning (host never reads the shard sums): a valid trajectory -- finite losses, consistent
     # trees, identical weights on every member, beta advanced once per requester served
     c = make()
+    c.batched_draw = True                                 # all requesters' draws in one launch
     c.enable_cuda_graph(static_exchange=True, device_apportion=True)
     beta0 = float(c.replay_buffer.curr_beta)
     for step in range(6):
