@@ -303,6 +303,12 @@ int mb_vtrace(const int64_t *d_offsets, int64_t n_episodes, int64_t n_steps, con
               const float *d_next_value, const float *d_reward, const uint8_t *d_terminal,
               const float *d_log_pi, const float *d_log_mu, float discount, float clip_c,
               float clip_rho, float *d_vs, float *d_vss, float *d_rho, float *d_adv, void *stream);
+/* The same with the length of the longest episode given (0 = unknown): lets the launch put fewer episodes on a
+ * CTA so that long episodes keep the coalesced, shared-memory-staged path instead of the thread-per-episode one. */
+int mb_vtrace_len(const int64_t *d_offsets, int64_t n_episodes, int64_t n_steps, int64_t max_episode_len,
+                  const float *d_value, const float *d_next_value, const float *d_reward,
+                  const uint8_t *d_terminal, const float *d_log_pi, const float *d_log_mu, float discount,
+                  float clip_c, float clip_rho, float *d_vs, float *d_vss, float *d_rho, float *d_adv, void *stream);
 /* A2C/A3C discounted return + GAE (a2c.py:275-313), float64 like the reference's Python floats:
  *   ret[last] = r[last] ; ret[i-1] = ret[i] * discount + r[i-1]
  *   lambda == 1: gae = ret - V(s) ; lambda == 0: gae = r + discount*(1-term)*V(s') - V(s)
@@ -312,6 +318,10 @@ int mb_gae(const int64_t *d_offsets, int64_t n_episodes, int64_t n_steps, const 
            const uint8_t *d_terminal, const float *d_critic_value,
            const float *d_next_critic_value, double discount, double gae_lambda,
            double *d_returns, double *d_gae, void *stream);
+int mb_gae_len(const int64_t *d_offsets, int64_t n_episodes, int64_t n_steps, int64_t max_episode_len,
+               const double *d_reward, const uint8_t *d_terminal, const float *d_critic_value,
+               const float *d_next_critic_value, double discount, double gae_lambda, double *d_returns,
+               double *d_gae, void *stream);
 
 int mb_vtrace_host(int device, const int64_t *h_offsets, int64_t n_episodes, int64_t n_steps,
                    const float *h_value, const float *h_next_value, const float *h_reward,

@@ -97,7 +97,9 @@ SIGNATURES = {
     "mb_adam_step_multi": (i32, [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i32, vp,
                                  f64, f64, f64, f64, f64, vp]),
     "mb_vtrace": (i32, [vp, i64, i64, vp, vp, vp, vp, vp, vp, f32, f32, f32, vp, vp, vp, vp, vp]),
+    "mb_vtrace_len": (i32, [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, f32, f32, f32, vp, vp, vp, vp, vp]),
     "mb_gae": (i32, [vp, i64, i64, vp, vp, vp, vp, f64, f64, vp, vp, vp]),
+    "mb_gae_len": (i32, [vp, i64, i64, i64, vp, vp, vp, vp, f64, f64, vp, vp, vp]),
     "mb_vtrace_host": (i32, [i32, vp, i64, i64, vp, vp, vp, vp, vp, vp, f32, f32, f32, vp, vp, vp, vp]),
     "mb_gae_host": (i32, [i32, vp, i64, i64, vp, vp, vp, vp, f64, f64, vp, vp]),
 }

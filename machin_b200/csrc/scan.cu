@@ -9,6 +9,8 @@
 // recurrence, one thread per episode, entirely out of shared memory; phase C streams vs / vss / adv
 // back out coalesced.  Each float32 operation is rounded separately in the reference's order
 // ((v + delta) + (g*c) * (vs' - v')), so apart from exp() the results are bit-identical to CPU torch.
+#include <algorithm>
+
 #include "mb_common.cuh"
 
 namespace {
@@ -19,18 +21,47 @@ namespace {
 
 extern "C" {
 
-int mb_vtrace(const int64_t *d_offsets, int64_t n_episodes, int64_t n_steps, const float *d_value,
-              const float *d_next_value, const float *d_reward, const uint8_t *d_terminal, const float *d_log_pi,
-              const float *d_log_mu, float discount, float clip_c, float clip_rho, float *d_vs, float *d_vss,
-              float *d_rho, float *d_adv, void *stream) {
+int mb_vtrace_len(const int64_t *d_offsets, int64_t n_episodes, int64_t n_steps, int64_t max_episode_len,
+                  const float *d_value, const float *d_next_value, const float *d_reward, const uint8_t *d_terminal,
+                  const float *d_log_pi, const float *d_log_mu, float discount, float clip_c, float clip_rho, float *d_vs,
+                  float *d_vss, float *d_rho, float *d_adv, void *stream) {
     if (n_episodes < 0 || n_steps < 0) return MB_ERR_INVALID;
     if (n_episodes == 0 || n_steps == 0) return MB_OK;
     if (!d_value || !d_next_value || !d_reward || !d_terminal || !d_log_pi || !d_log_mu) return MB_ERR_INVALID;
     if (!d_offsets && n_steps % n_episodes != 0) return MB_ERR_INVALID;
-    const unsigned blocks = (unsigned)((n_episodes + kEpisodesPerCta - 1) / kEpisodesPerCta);
+    if (!d_offsets) max_episode_len = n_steps / n_episodes;
+    const int epc = episodes_per_cta(max_episode_len, kTile, kEpisodesPerCta);
+    const unsigned blocks = (unsigned)((n_episodes + epc - 1) / epc);
     vtrace_kernel<<<blocks, kEpisodesPerCta, 0, (cudaStream_t)stream>>>(
         d_offsets, n_episodes, n_steps, d_value, d_next_value, d_reward, d_terminal, d_log_pi, d_log_mu, discount,
-        clip_c, clip_rho, d_vs, d_vss, d_rho, d_adv);
+        clip_c, clip_rho, d_vs, d_vss, d_rho, d_adv, epc);
+    MB_LAUNCHED(1);
+    return MB_OK;
+}
+
+int mb_vtrace(const int64_t *d_offsets, int64_t n_episodes, int64_t n_steps, const float *d_value,
+              const float *d_next_value, const float *d_reward, const uint8_t *d_terminal, const float *d_log_pi,
+              const float *d_log_mu, float discount, float clip_c, float clip_rho, float *d_vs, float *d_vss,
+              float *d_rho, float *d_adv, void *stream) {
+    return mb_vtrace_len(d_offsets, n_episodes, n_steps, 0, d_value, d_next_value, d_reward, d_terminal, d_log_pi, d_log_mu,
+                         discount, clip_c, clip_rho, d_vs, d_vss, d_rho, d_adv, stream);
+}
+
+int mb_gae_len(const int64_t *d_offsets, int64_t n_episodes, int64_t n_steps, int64_t max_episode_len,
+               const double *d_reward, const uint8_t *d_terminal, const float *d_critic_value,
+               const float *d_next_critic_value, double discount, double gae_lambda, double *d_returns, double *d_gae,
+               void *stream) {
+    if (n_episodes < 0 || n_steps < 0) return MB_ERR_INVALID;
+    if (n_episodes == 0 || n_steps == 0) return MB_OK;
+    if (!d_reward) return MB_ERR_INVALID;
+    if (d_gae && (!d_terminal || !d_critic_value)) return MB_ERR_INVALID;
+    if (d_gae && gae_lambda == 0.0 && !d_next_critic_value) return MB_ERR_INVALID;
+    if (!d_offsets && n_steps % n_episodes != 0) return MB_ERR_INVALID;
+    if (!d_offsets) max_episode_len = n_steps / n_episodes;
+    const int epc = episodes_per_cta(max_episode_len, kGaeTile, kGaeEpisodes);
+    gae_kernel<<<(unsigned)((n_episodes + epc - 1) / epc), kGaeEpisodes, 0, (cudaStream_t)stream>>>(
+        d_offsets, n_episodes, n_steps, d_reward, d_terminal, d_critic_value, d_next_critic_value, discount,
+        gae_lambda, d_returns, d_gae, epc);
     MB_LAUNCHED(1);
     return MB_OK;
 }
@@ -38,17 +69,8 @@ int mb_vtrace(const int64_t *d_offsets, int64_t n_episodes, int64_t n_steps, con
 int mb_gae(const int64_t *d_offsets, int64_t n_episodes, int64_t n_steps, const double *d_reward,
            const uint8_t *d_terminal, const float *d_critic_value, const float *d_next_critic_value,
            double discount, double gae_lambda, double *d_returns, double *d_gae, void *stream) {
-    if (n_episodes < 0 || n_steps < 0) return MB_ERR_INVALID;
-    if (n_episodes == 0 || n_steps == 0) return MB_OK;
-    if (!d_reward) return MB_ERR_INVALID;
-    if (d_gae && (!d_terminal || !d_critic_value)) return MB_ERR_INVALID;
-    if (d_gae && gae_lambda == 0.0 && !d_next_critic_value) return MB_ERR_INVALID;
-    if (!d_offsets && n_steps % n_episodes != 0) return MB_ERR_INVALID;
-    gae_kernel<<<(unsigned)((n_episodes + kGaeEpisodes - 1) / kGaeEpisodes), kGaeEpisodes, 0, (cudaStream_t)stream>>>(
-        d_offsets, n_episodes, n_steps, d_reward, d_terminal, d_critic_value, d_next_critic_value, discount,
-        gae_lambda, d_returns, d_gae);
-    MB_LAUNCHED(1);
-    return MB_OK;
+    return mb_gae_len(d_offsets, n_episodes, n_steps, 0, d_reward, d_terminal, d_critic_value, d_next_critic_value, discount,
+                      gae_lambda, d_returns, d_gae, stream);
 }
 
 // ------------------------------------------------------------------------------ host variants
@@ -80,7 +102,10 @@ int mb_vtrace_host(int device, const int64_t *h_offsets, int64_t n_episodes, int
     MB_CUDA(cudaMemcpyAsync(st->d, h, in_bytes, cudaMemcpyHostToDevice, st->stream));
     char *d = st->d;
     float *d_vs = (float *)(d + in_bytes), *d_vss = d_vs + S, *d_rho = d_vss + S, *d_adv = d_rho + S;
-    r = mb_vtrace(h_offsets ? (const int64_t *)d : nullptr, n_episodes, n_steps, (const float *)(d + o_v),
+    int64_t longest = 0;   // the host knows the episode lengths: keep the staged path for long episodes too
+    if (h_offsets)
+        for (int64_t e = 0; e < n_episodes; ++e) longest = std::max(longest, h_offsets[e + 1] - h_offsets[e]);
+    r = mb_vtrace_len(h_offsets ? (const int64_t *)d : nullptr, n_episodes, n_steps, longest, (const float *)(d + o_v),
                   (const float *)(d + o_nv), (const float *)(d + o_r), (const uint8_t *)(d + o_t),
                   (const float *)(d + o_lp), (const float *)(d + o_lm), discount, clip_c, clip_rho, d_vs, d_vss,
                   d_rho, d_adv, st->stream);
@@ -120,7 +145,10 @@ int mb_gae_host(int device, const int64_t *h_offsets, int64_t n_episodes, int64_
     MB_CUDA(cudaMemcpyAsync(st->d, h, in_bytes, cudaMemcpyHostToDevice, st->stream));
     char *d = st->d;
     double *d_ret = (double *)(d + in_bytes), *d_adv = d_ret + S;
-    r = mb_gae(h_offsets ? (const int64_t *)d : nullptr, n_episodes, n_steps, (const double *)(d + o_r),
+    int64_t longest = 0;
+    if (h_offsets)
+        for (int64_t e = 0; e < n_episodes; ++e) longest = std::max(longest, h_offsets[e + 1] - h_offsets[e]);
+    r = mb_gae_len(h_offsets ? (const int64_t *)d : nullptr, n_episodes, n_steps, longest, (const double *)(d + o_r),
                (const uint8_t *)(d + o_t), (const float *)(d + o_cv), (const float *)(d + o_ncv), discount,
                gae_lambda, d_ret, d_adv, st->stream);
     if (r != MB_OK) return r;

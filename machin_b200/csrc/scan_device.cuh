@@ -7,6 +7,13 @@
 constexpr int kEpisodesPerCta = 128;
 constexpr int kTile = 2976;  // steps staged per CTA: 4 arrays x (kTile * 33 / 32) floats <= 48 KB
 
+// episodes per CTA for a given longest episode (0 = unknown): as many as fit the staging tile, at most `cap`
+inline int episodes_per_cta(int64_t max_len, int tile, int cap) {
+    if (max_len <= 0) return cap;
+    const int64_t e = tile / max_len;
+    return (int)(e < 1 ? 1 : (e > cap ? cap : e));
+}
+
 __device__ __forceinline__ int sw(int j) { return j + (j >> 5); }  // de-conflict stride-L access
 
 struct StepTerms {
@@ -28,14 +35,16 @@ __global__ void __launch_bounds__(kEpisodesPerCta) vtrace_kernel(
     const float *__restrict__ next_value, const float *__restrict__ reward, const uint8_t *__restrict__ terminal,
     const float *__restrict__ log_pi, const float *__restrict__ log_mu, float g, float clip_c, float clip_rho,
     float *__restrict__ vs_out, float *__restrict__ vss_out, float *__restrict__ rho_out,
-    float *__restrict__ adv_out) {
+    float *__restrict__ adv_out, int epc) {
     __shared__ float sV[kTile + kTile / 32 + 1];
     __shared__ float sD[kTile + kTile / 32 + 1];   // delta, then vs
     __shared__ float sG[kTile + kTile / 32 + 1];   // g*c, then vss
     __shared__ float sR[kTile + kTile / 32 + 1];   // reward, then adv
     const int tid = threadIdx.x;
-    const int64_t e0 = (int64_t)blockIdx.x * kEpisodesPerCta;
-    const int64_t e1 = min(e0 + kEpisodesPerCta, n_ep);
+    // epc (<= blockDim.x) episodes per CTA: the host shrinks it for long episodes so that a CTA's slice still fits
+    // the staging tile (128 episodes of more than 23 steps would not) and the coalesced three-phase path is kept
+    const int64_t e0 = (int64_t)blockIdx.x * epc;
+    const int64_t e1 = min(e0 + epc, n_ep);
     const int64_t fixed_len = offsets ? 0 : n_steps / n_ep;
     const int64_t s0 = offsets ? offsets[e0] : e0 * fixed_len;
     const int64_t s1 = offsets ? offsets[e1] : e1 * fixed_len;
@@ -145,15 +154,15 @@ __global__ void __launch_bounds__(kGaeEpisodes) gae_kernel(const int64_t *__rest
                                                            const uint8_t *__restrict__ terminal,
                                                            const float *__restrict__ cv, const float *__restrict__ ncv,
                                                            double g, double lam, double *__restrict__ ret_out,
-                                                           double *__restrict__ gae_out) {
+                                                           double *__restrict__ gae_out, int epc) {
     __shared__ double sR[kGaeTile + kGaeTile / 32 + 1];   // reward, then return
     __shared__ double sA[kGaeTile + kGaeTile / 32 + 1];   // advantage
     __shared__ float sV[kGaeTile + kGaeTile / 32 + 1];
     __shared__ float sN[kGaeTile + kGaeTile / 32 + 1];
     __shared__ uint8_t sT[kGaeTile + kGaeTile / 32 + 1];
     const int tid = threadIdx.x;
-    const int64_t e0 = (int64_t)blockIdx.x * kGaeEpisodes;
-    const int64_t e1 = min(e0 + kGaeEpisodes, n_ep);
+    const int64_t e0 = (int64_t)blockIdx.x * epc;         // epc <= blockDim.x episodes per CTA, see vtrace_kernel
+    const int64_t e1 = min(e0 + epc, n_ep);
     const int64_t fixed_len = offsets ? 0 : n_steps / n_ep;
     const int64_t s0 = offsets ? offsets[e0] : e0 * fixed_len;
     const int64_t s1 = offsets ? offsets[e1] : e1 * fixed_len;

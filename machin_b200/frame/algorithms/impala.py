@@ -119,7 +119,7 @@ class IMPALA(TorchFramework):
         next_value = self._criticize(next_state).view(sum_length, 1)
         vt = ops.vtrace(value.detach(), next_value.detach(), reward.view(sum_length, 1), terminal.view(sum_length, 1),
                         cur_action_log_prob.detach(), action_log_prob.view(sum_length, 1), self.discount,
-                        self.isw_clip_c, self.isw_clip_rho, offsets=offsets)
+                        self.isw_clip_c, self.isw_clip_rho, offsets=offsets, max_len=int(max(all_length)))
         act_policy_loss = -(vt["rho"] * cur_action_log_prob * vt["adv"])
         if self.entropy_weight is not None:
             act_policy_loss = act_policy_loss + self.entropy_weight * entropy

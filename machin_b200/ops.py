@@ -99,10 +99,11 @@ def soft_update(target_net: t.nn.Module, source_net: t.nn.Module, rate: float):
 
 
 def vtrace(value, next_value, reward, terminal, log_pi, log_mu, discount: float, clip_c: float = 1.0,
-           clip_rho: float = 1.0, offsets: Optional[t.Tensor] = None, n_episodes: Optional[int] = None
-           ) -> Dict[str, t.Tensor]:
+           clip_rho: float = 1.0, offsets: Optional[t.Tensor] = None, n_episodes: Optional[int] = None,
+           max_len: int = 0) -> Dict[str, t.Tensor]:
     """IMPALA V-trace (impala.py:322-362) over flattened episode-major steps.  ``offsets``: int64
-    [n_episodes + 1] CSR episode boundaries on the device, or None for equal-length episodes."""
+    [n_episodes + 1] CSR episode boundaries on the device, or None for equal-length episodes.  ``max_len``: length
+    of the longest episode if the caller knows it (keeps the staged path for long episodes), 0 = unknown."""
     value = _c(value, t.float32)
     shape, dev = value.shape, value.device
     S = value.numel()
@@ -114,7 +115,7 @@ def vtrace(value, next_value, reward, terminal, log_pi, log_mu, discount: float,
         n_episodes = offsets.numel() - 1
     out = {k: t.empty(shape, dtype=t.float32, device=dev) for k in ("vs", "vss", "rho", "adv")}
     with t.cuda.device(dev):
-        _lib.check(lib.mb_vtrace(_lib.ptr(offsets), int(n_episodes), S, _lib.ptr(value), _lib.ptr(args[0]),
+        _lib.check(lib.mb_vtrace_len(_lib.ptr(offsets), int(n_episodes), S, int(max_len), _lib.ptr(value), _lib.ptr(args[0]),
                                  _lib.ptr(args[1]), _lib.ptr(term), _lib.ptr(lp), _lib.ptr(lm), float(discount),
                                  float(clip_c), float(clip_rho), _lib.ptr(out["vs"]), _lib.ptr(out["vss"]),
                                  _lib.ptr(out["rho"]), _lib.ptr(out["adv"]), _lib.stream_ptr()))
@@ -122,8 +123,9 @@ def vtrace(value, next_value, reward, terminal, log_pi, log_mu, discount: float,
 
 
 def gae(reward, terminal, critic_value, next_critic_value, discount: float, gae_lambda: float,
-        offsets: Optional[t.Tensor] = None, n_episodes: Optional[int] = None) -> Dict[str, t.Tensor]:
-    """Discounted returns + GAE (a2c.py:275-313), float64 like the reference's Python floats."""
+        offsets: Optional[t.Tensor] = None, n_episodes: Optional[int] = None, max_len: int = 0) -> Dict[str, t.Tensor]:
+    """Discounted returns + GAE (a2c.py:275-313), float64 like the reference's Python floats.  ``max_len``: see
+    :func:`vtrace`."""
     reward = _c(reward, t.float64)
     dev, S = reward.device, reward.numel()
     term = _u8(terminal)
@@ -133,7 +135,7 @@ def gae(reward, terminal, critic_value, next_critic_value, discount: float, gae_
         n_episodes = offsets.numel() - 1
     out = {k: t.empty(reward.shape, dtype=t.float64, device=dev) for k in ("returns", "gae")}
     with t.cuda.device(dev):
-        _lib.check(lib.mb_gae(_lib.ptr(offsets), int(n_episodes), S, _lib.ptr(reward), _lib.ptr(term), _lib.ptr(cv),
+        _lib.check(lib.mb_gae_len(_lib.ptr(offsets), int(n_episodes), S, int(max_len), _lib.ptr(reward), _lib.ptr(term), _lib.ptr(cv),
                               _lib.ptr(ncv), float(discount), float(gae_lambda), _lib.ptr(out["returns"]),
                               _lib.ptr(out["gae"]), _lib.stream_ptr()))
     return out

@@ -34,11 +34,14 @@ def p(a):
     return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
 
 
+@pytest.mark.parametrize("know_len", [False, True])
 @pytest.mark.parametrize("lengths,seed,use_offsets", [
     ([20] * 64, 0, True), ([20] * 300, 1, False), ([1, 7, 2, 33, 5, 1, 12, 40, 3], 2, True), ([1], 3, True),
     ([3500, 3, 2999], 4, True),                      # slices beyond the staging tile: the straight-from-memory branch
+    ([100] * 200, 6, True), ([100] * 200, 7, False),  # long episodes: fewer episodes per CTA keep the staged path
+    ([2976, 1, 2976, 50], 8, True),
     (list(np.random.RandomState(5).randint(1, 41, 400)), 5, True)])
-def test_vtrace_kernel_source_under_emulation(scan, lengths, seed, use_offsets):
+def test_vtrace_kernel_source_under_emulation(scan, lengths, seed, use_offsets, know_len):
     g = t.Generator().manual_seed(seed)
     n = int(sum(lengths))
     value, next_value, reward = (t.randn(n, 1, generator=g) for _ in range(3))
@@ -55,7 +58,8 @@ def test_vtrace_kernel_source_under_emulation(scan, lengths, seed, use_offsets):
     term_u8 = np.ascontiguousarray(term.numpy().reshape(-1).astype(np.uint8))
     assert scan.emul_vtrace(p(off), C.c_int64(len(lengths)), C.c_int64(n), p(f(value)), p(f(next_value)), p(f(reward)),
                             p(term_u8), p(f(logp)), p(f(logmu)), C.c_float(discount), C.c_float(clip_c), C.c_float(clip_rho),
-                            p(out["vs"]), p(out["vss"]), p(out["rho"]), p(out["adv"])) == 0
+                            p(out["vs"]), p(out["vss"]), p(out["rho"]), p(out["adv"]),
+                            C.c_int64(max(lengths) if know_len else 0)) == 0
     np.testing.assert_allclose(out["rho"], f(rho), rtol=1e-6)
     np.testing.assert_allclose(out["vs"], f(vs), rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(out["vss"], f(vss), rtol=1e-5, atol=1e-6)
@@ -65,8 +69,9 @@ def test_vtrace_kernel_source_under_emulation(scan, lengths, seed, use_offsets):
 
 
 @pytest.mark.parametrize("lam", [1.0, 0.0, 0.95])
-@pytest.mark.parametrize("lengths", [[20] * 70, [1, 9, 2, 31, 4, 1, 17], [1700, 5, 40]])
-def test_gae_kernel_source_under_emulation(scan, lam, lengths):
+@pytest.mark.parametrize("know_len", [False, True])
+@pytest.mark.parametrize("lengths", [[20] * 70, [1, 9, 2, 31, 4, 1, 17], [1700, 5, 40], [90] * 150, [1664, 2, 1664]])
+def test_gae_kernel_source_under_emulation(scan, lam, lengths, know_len):
     rng = np.random.RandomState(int(lam * 100) + len(lengths))
     n = int(sum(lengths))
     reward = rng.randn(n)
@@ -77,7 +82,7 @@ def test_gae_kernel_source_under_emulation(scan, lam, lengths):
     off = np.concatenate(([0], np.cumsum(lengths))).astype(np.int64)
     ret, adv = np.full(n, np.nan), np.full(n, np.nan)
     assert scan.emul_gae(p(off), C.c_int64(len(lengths)), C.c_int64(n), p(reward), p(term), p(cv), p(ncv),
-                         C.c_double(0.97), C.c_double(lam), p(ret), p(adv)) == 0
+                         C.c_double(0.97), C.c_double(lam), p(ret), p(adv), C.c_int64(max(lengths) if know_len else 0)) == 0
     pos = 0
     for L in lengths:
         sl = slice(pos, pos + L)
