@@ -97,8 +97,53 @@ __global__ void __launch_bounds__(kEpisodesPerCta) vtrace_kernel(
             if (vss_out) vss_out[s] = sG[sw(j)];
             if (adv_out) adv_out[s] = sR[sw(j)];
         }
+    } else if (epc == 1) {
+        // ONE episode longer than the staging tile: walk it tile by tile from its end -- coalesced load of the tile,
+        // thread 0 runs the recurrence out of shared memory carrying (vs_next, v_next) across tiles, coalesced store
+        float vs_next = 0.0f, v_next = 0.0f;
+        for (int64_t hi = s1; hi > s0; hi -= kTile) {
+            const int64_t lo = hi - kTile > s0 ? hi - kTile : s0;
+            const int m = (int)(hi - lo);
+            for (int j = tid; j < m; j += kEpisodesPerCta) {
+                const int64_t s = lo + j;
+                const float v = value[s], r = reward[s];
+                const StepTerms t = vtrace_terms(v, next_value[s], r, terminal[s] != 0, log_pi[s], log_mu[s], g,
+                                                 clip_c, clip_rho);
+                sV[sw(j)] = v;
+                sD[sw(j)] = t.delta;
+                sG[sw(j)] = t.gc;
+                sR[sw(j)] = r;
+                if (rho_out) rho_out[s] = t.rho;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                for (int k = m - 1; k >= 0; --k) {
+                    const int j = sw(k);
+                    const float v = sV[j];
+                    float vs = 0.0f, vss = 0.0f;
+                    if (lo + k != s1 - 1) {                                          // last step: vs = vss = 0 (:341-357)
+                        vs = __fadd_rn(__fadd_rn(v, sD[j]), __fmul_rn(sG[j], __fsub_rn(vs_next, v_next)));
+                        vss = vs_next;
+                    }
+                    sD[j] = vs;
+                    sG[j] = vss;
+                    sR[j] = __fsub_rn(__fadd_rn(sR[j], __fmul_rn(g, vss)), v);       // r + g*vss - v   (:367)
+                    vs_next = vs;
+                    v_next = v;
+                }
+            }
+            __syncthreads();
+            for (int j = tid; j < m; j += kEpisodesPerCta) {
+                const int64_t s = lo + j;
+                if (vs_out) vs_out[s] = sD[sw(j)];
+                if (vss_out) vss_out[s] = sG[sw(j)];
+                if (adv_out) adv_out[s] = sR[sw(j)];
+            }
+            __syncthreads();                                                         // the next tile overwrites the staging arrays
+        }
     } else if (len > 0) {
-        // slice does not fit the staging tile (long episodes): same arithmetic straight from HBM
+        // slice does not fit the staging tile and the launch did not know the lengths: same arithmetic, one thread
+        // per episode straight from HBM
         float vs_next = 0.0f, v_next = 0.0f;
         for (int64_t k = len - 1; k >= 0; --k) {
             const int64_t s = b + k;
@@ -201,6 +246,39 @@ __global__ void __launch_bounds__(kGaeEpisodes) gae_kernel(const int64_t *__rest
             const int64_t s = s0 + j;
             if (ret_out) ret_out[s] = sR[sw(j)];
             if (gae_out) gae_out[s] = sA[sw(j)];
+        }
+    } else if (epc == 1) {
+        // ONE episode longer than the staging tile: tile by tile from its end, (ret, last_v, last_a) carried by thread 0
+        double ret = 0.0, last_v = 0.0, last_a = 0.0;
+        for (int64_t hi = s1; hi > s0; hi -= kGaeTile) {
+            const int64_t lo = hi - kGaeTile > s0 ? hi - kGaeTile : s0;
+            const int m = (int)(hi - lo);
+            for (int j = tid; j < m; j += kGaeEpisodes) {
+                const int64_t s = lo + j;
+                sR[sw(j)] = reward[s];
+                if (gae_out) {
+                    sV[sw(j)] = cv[s];
+                    sT[sw(j)] = terminal[s];
+                    if (need_next) sN[sw(j)] = ncv[s];
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                for (int k = m - 1; k >= 0; --k) {
+                    const int j = sw(k);
+                    const GaeStep o = gae_step(sR[j], gae_out ? (double)sV[j] : 0.0, need_next ? (double)sN[j] : 0.0,
+                                               gae_out ? sT[j] != 0 : false, lo + k == s1 - 1, g, lam, ret, last_v, last_a);
+                    sR[j] = o.ret;
+                    sA[j] = o.adv;
+                }
+            }
+            __syncthreads();
+            for (int j = tid; j < m; j += kGaeEpisodes) {
+                const int64_t s = lo + j;
+                if (ret_out) ret_out[s] = sR[sw(j)];
+                if (gae_out) gae_out[s] = sA[sw(j)];
+            }
+            __syncthreads();
         }
     } else if (len > 0) {
         double ret = 0.0, last_v = 0.0, last_a = 0.0;

@@ -39,7 +39,7 @@ def p(a):
     ([20] * 64, 0, True), ([20] * 300, 1, False), ([1, 7, 2, 33, 5, 1, 12, 40, 3], 2, True), ([1], 3, True),
     ([3500, 3, 2999], 4, True),                      # slices beyond the staging tile: the straight-from-memory branch
     ([100] * 200, 6, True), ([100] * 200, 7, False),  # long episodes: fewer episodes per CTA keep the staged path
-    ([2976, 1, 2976, 50], 8, True),
+    ([2976, 1, 2976, 50], 8, True), ([7000], 9, True), ([7000], 10, False), ([2977, 3, 9000, 1], 11, True),
     (list(np.random.RandomState(5).randint(1, 41, 400)), 5, True)])
 def test_vtrace_kernel_source_under_emulation(scan, lengths, seed, use_offsets, know_len):
     g = t.Generator().manual_seed(seed)
@@ -70,7 +70,7 @@ def test_vtrace_kernel_source_under_emulation(scan, lengths, seed, use_offsets, 
 
 @pytest.mark.parametrize("lam", [1.0, 0.0, 0.95])
 @pytest.mark.parametrize("know_len", [False, True])
-@pytest.mark.parametrize("lengths", [[20] * 70, [1, 9, 2, 31, 4, 1, 17], [1700, 5, 40], [90] * 150, [1664, 2, 1664]])
+@pytest.mark.parametrize("lengths", [[20] * 70, [1, 9, 2, 31, 4, 1, 17], [1700, 5, 40], [90] * 150, [1664, 2, 1664], [5000], [1665, 3, 4000, 1]])
 def test_gae_kernel_source_under_emulation(scan, lam, lengths, know_len):
     rng = np.random.RandomState(int(lam * 100) + len(lengths))
     n = int(sum(lengths))
