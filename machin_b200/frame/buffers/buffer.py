@@ -42,6 +42,10 @@ class EpisodeBook:
         self.episode_counter = 0
         self.handles = {}                   # type: Dict[int, np.ndarray]
         self.slot_episode = np.full(self.capacity, -1, dtype=np.int64)
+        # (first slot, length) per episode number: an episode's slots are consecutive modulo the capacity, so whole-
+        # episode sampling can build its slot list with array arithmetic instead of one Python object per episode
+        self._ep_first = np.zeros(1024, dtype=np.int64)
+        self._ep_len = np.zeros(1024, dtype=np.int64)
 
     def assign(self, n: int):
         """Reserve ``n`` consecutive ring slots -> (first_slot, positions)."""
@@ -62,7 +66,33 @@ class EpisodeBook:
             self.slot_episode[slots[self.slot_episode[slots] == ep]] = -1
         self.slot_episode[positions] = episode_number
         self.handles[episode_number] = positions
+        if episode_number >= self._ep_first.shape[0]:
+            grow = max(2 * self._ep_first.shape[0], episode_number + 1)
+            self._ep_first = np.concatenate([self._ep_first, np.zeros(grow - self._ep_first.shape[0], dtype=np.int64)])
+            self._ep_len = np.concatenate([self._ep_len, np.zeros(grow - self._ep_len.shape[0], dtype=np.int64)])
+        self._ep_first[episode_number] = positions[0]
+        self._ep_len[episode_number] = len(positions)
         return episode_number
+
+    def live_episode_range(self):
+        """(lo, hi) if the live episodes are exactly the numbers lo .. hi-1 (the ring evicts oldest first, so this is
+        the normal case), else None."""
+        n = len(self.handles)
+        if n == 0:
+            return None
+        lo = next(iter(self.handles))
+        return (lo, lo + n) if lo + n == self.episode_counter else None
+
+    def episode_slots(self, episodes: np.ndarray):
+        """Slots of the given episode numbers, concatenated in order -> (slots i64[sum len], lengths i64[k])."""
+        episodes = np.asarray(episodes, dtype=np.int64)
+        lens = self._ep_len[episodes]
+        total = int(lens.sum())
+        if total == 0:
+            return np.empty(0, dtype=np.int64), lens
+        begin = np.cumsum(lens) - lens
+        within = np.arange(total, dtype=np.int64) - np.repeat(begin, lens)
+        return (np.repeat(self._ep_first[episodes], lens) + within) % self.capacity, lens
 
     def sampleable(self) -> List[int]:
         return [int(s) for slots in self.handles.values() for s in slots]

@@ -93,6 +93,12 @@ class DistributedBuffer(Buffer):
         g, dev = self.group, self.buffer_device
         P, me = g.size(), g.index
         local_batch_size = _round_up(batch_size / P)                       # :143-144
+        if P == 1:                                                         # nothing to exchange: no collectives, no syncs
+            units, handles, sizes = self._local_sample(local_batch_size, sample_method)
+            if not len(handles):
+                return 0, None, None
+            idx = t.as_tensor(np.asarray(handles, dtype=np.int64)).to(dev)
+            return units, self.storage.gather_packed(idx), [int(x) for x in sizes]
         parts, size_parts, send_rows, send_units = [], [], [0] * P, [0] * P
         for r in self.requesters:                                         # one local draw per requester, member order
             units, handles, sizes = self._local_sample(local_batch_size, sample_method)
@@ -135,6 +141,13 @@ class IMPALABuffer(DistributedBuffer):
 
     def sample_method_episode(self, batch_size: int):
         batch_size = min(len(self.episode_transition_handles), batch_size)
+        live = self.book.live_episode_range()
+        if live is not None:
+            # random.choices(population, k) picks population[floor(random() * n)]: choosing positions consumes the
+            # stream exactly like choosing from list(keys) (impala.py:58), and position i is episode lo + i
+            picks = random.choices(range(live[1] - live[0]), k=batch_size)
+            handles, lens = self.book.episode_slots(live[0] + np.asarray(picks, dtype=np.int64))
+            return batch_size, handles, lens.tolist()
         episodes = random.choices(list(self.episode_transition_handles.keys()), k=batch_size)   # impala.py:58
         parts = [np.asarray(self.episode_transition_handles[episode], dtype=np.int64) for episode in episodes]
         handles = np.concatenate(parts) if parts else np.empty(0, dtype=np.int64)

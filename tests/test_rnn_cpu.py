@@ -121,3 +121,33 @@ def test_host_episode_priorities_match_reference(tag):
         o.beta = np.min([1.0, o.beta + o.beta_inc])
     _replay_prioritized(tag, store, lambda u: o.sample(len(u), uniform=u), o.update_priority, lambda: o.tree.weights,
                         skip_draw)
+
+
+def test_vectorised_episode_sampling_matches_list_sampling():
+    """IMPALABuffer.sample_method_episode builds the slot list of the drawn episodes with array arithmetic (an
+    episode's slots are consecutive modulo the capacity, the live episodes are a contiguous range of numbers): same
+    draws from Python's random stream and the same slots as `random.choices(list(keys))` + per-episode lists
+    (impala.py:52-66), through wrap-around and evictions."""
+    from machin_b200.frame.buffers import EpisodeBook
+    rng = np.random.RandomState(0)
+    book = EpisodeBook(5000)
+    for step in range(1500):
+        n = int(rng.randint(1, 40))
+        _, pos = book.assign(n)
+        book.record(pos)
+        if step % 40:
+            continue
+        handles = book.handles
+        random.seed(step)
+        episodes = random.choices(list(handles.keys()), k=min(len(handles), 64))
+        want = np.concatenate([np.asarray(handles[e], dtype=np.int64) for e in episodes])
+        after = random.random()
+        random.seed(step)
+        live = book.live_episode_range()
+        assert live is not None and live[1] - live[0] == len(handles)
+        picks = random.choices(range(live[1] - live[0]), k=min(len(handles), 64))
+        got, lens = book.episode_slots(live[0] + np.asarray(picks, dtype=np.int64))
+        assert random.random() == after                            # the stream was consumed identically
+        assert np.array_equal(got, want) and lens.tolist() == [len(handles[e]) for e in episodes]
+    book.clear()
+    assert book.live_episode_range() is None
