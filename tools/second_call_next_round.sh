@@ -25,3 +25,7 @@ run device_apportion  "--device-apportion --batched-draw"
 run dynamic           "--dynamic-exchange"
 run static_fused_rows "--net fused-rows"
 run devapp_fused_rows "--net fused-rows --device-apportion"
+# can the process group be torn down once the NCCL-capturing graph is released?  (blocked teardown -> timeout, rc 124)
+timeout 90 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29556 \
+    tools/nccl_graph_repro.py thread_local release > gpurun_out/next2_teardown.txt 2>&1; echo "teardown after release: rc=$?"; tail -3 gpurun_out/next2_teardown.txt
+
