@@ -10,6 +10,7 @@ from conftest import ROOT, run_group
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.timeout(900, method="thread")      # above the 600 s / 300 s limit of the torchrun launch itself
 @pytest.mark.parametrize("world", [2, 4])
 def test_sharded_buffer_over_nccl(world):
     if t.cuda.device_count() < world:

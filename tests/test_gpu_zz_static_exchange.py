@@ -10,6 +10,7 @@ from conftest import ROOT, run_group, first_hardware_run_pending
 pytestmark = [pytest.mark.gpu, first_hardware_run_pending]
 
 
+@pytest.mark.timeout(900, method="thread")      # above the 600 s / 300 s limit of the torchrun launch itself
 @pytest.mark.parametrize("world", [2, 4])
 def test_static_exchange_matches_dynamic_over_nccl(world):
     if t.cuda.device_count() < world:
