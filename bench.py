@@ -257,6 +257,12 @@ KERNELS = {  # C entry point -> (label, algorithmic bytes per launch as f(batch,
     "mb_td_dqn": ("td_dqn (target + |delta| + loss + grad)", lambda B, P, D: (3 * N_ACTIONS * 4 + 8 + 4 + 1 + 8 + 12 + N_ACTIONS * 4) * B),
     "mb_tree_update_priority": ("tree_update (normalise + level-synchronous recompute)", lambda B, P, D: (8 + 4 + 8 + 24 * (D - 1)) * B),
     "mb_soft_update": ("soft_update", lambda B, P, D: 12 * P),
+    # fused value math (--net fused-rows / fused-program): what must cross HBM at least once -- both input batches,
+    # both nets' parameters, the saved activations and output gradients (written by part 0, read by part 1), the
+    # parameter gradients.  The kernels themselves are FFMA / L2-latency bound, not HBM bound.
+    "mb_mlp_program_part0": ("fused forward x3 + TD + backward-input",
+                             lambda B, P, D: 2 * B * STATE_DIM * 4 + 2 * P * 4 + 2 * B * (2 * HIDDEN + N_ACTIONS) * 4 + 40 * B),
+    "mb_mlp_program_part1": ("fused dW / db", lambda B, P, D: B * (STATE_DIM + 4 * HIDDEN + N_ACTIONS) * 4 + P * 4),
 }
 
 
@@ -305,9 +311,15 @@ def time_kernels(learner, table, reps=20, per_graph=16):
     def k_soft(i):
         ops.soft_update(learner.qnet_target, learner.qnet, 0.0)  # rate 0: same traffic, weights unchanged
 
+    timed = [("mb_per_sample", k_sample), ("mb_rows_gather", k_gather), ("mb_td_dqn", k_td),
+             ("mb_tree_update_priority", k_update), ("mb_soft_update", k_soft)]
+    prog = getattr(learner, "_program", None)
+    if prog:                                   # the fused program replaces the stand-alone TD kernel in the step
+        def k_part(part):
+            return lambda i: _lib.check(lib.mb_mlp_program_run_part(prog["handle"], part, sp()))
+        timed = [x for x in timed if x[0] != "mb_td_dqn"] + [("mb_mlp_program_part0", k_part(0)), ("mb_mlp_program_part1", k_part(1))]
     out = {}
-    for name, fn in (("mb_per_sample", k_sample), ("mb_rows_gather", k_gather), ("mb_td_dqn", k_td),
-                     ("mb_tree_update_priority", k_update), ("mb_soft_update", k_soft)):
+    for name, fn in timed:
         side = t.cuda.Stream(device=dev)
         side.wait_stream(t.cuda.current_stream(dev))
         with t.cuda.stream(side):
