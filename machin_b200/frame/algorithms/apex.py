@@ -376,6 +376,8 @@ class DQNApex(DQNPer):
                          ptr(st["isw"]), float(self.discount), 0 if self.mode == "double" else 1, ptr(prog["y"]),
                          ptr(prog["av"]), ptr(prog["abs"]), ptr(prog["loss"]), C.byref(handle)))
         prog["handle"] = handle
+        import weakref
+        weakref.finalize(self, lib.mb_mlp_program_destroy, handle)
         return prog
 
     def _static_prepare(self):

@@ -260,6 +260,8 @@ class DQNPer(TorchFramework):
                 float(self.discount), 0 if self.mode == "double" else 1, ptr(st["y"]), ptr(st["av"]), ptr(st["abs"]),
                 ptr(st["loss"]), C.byref(handle)))
         st["handle"] = handle
+        import weakref
+        weakref.finalize(self, lib.mb_mlp_program_destroy, handle)     # device buffers of the program go with the learner
         self._program = st
         return st
 
