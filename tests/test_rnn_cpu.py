@@ -151,3 +151,16 @@ def test_vectorised_episode_sampling_matches_list_sampling():
         assert np.array_equal(got, want) and lens.tolist() == [len(handles[e]) for e in episodes]
     book.clear()
     assert book.live_episode_range() is None
+
+
+def test_window_index_wraps_around_the_ring():
+    """RNNPrioritizedBuffer._window_index: start slot -> sample_length consecutive slots modulo the capacity (an
+    episode that wrapped around the end of the ring continues at slot 0)."""
+    import types
+    import torch as t
+    from machin_b200.frame.buffers.rnn_buffers import RNNPrioritizedBuffer
+    buf = RNNPrioritizedBuffer.__new__(RNNPrioritizedBuffer)       # no device needed for the index arithmetic
+    buf.sample_length = 4
+    buf.storage = types.SimpleNamespace(max_size=16)
+    got = buf._window_index(t.tensor([0, 5, 13, 15]))
+    assert got.tolist() == [0, 1, 2, 3, 5, 6, 7, 8, 13, 14, 15, 0, 15, 0, 1, 2]
