@@ -70,3 +70,51 @@ def make_cpu_buffer(cls, capacity, **attrs):
     for k, v in attrs.items():
         setattr(buf, k, v)
     return buf
+
+
+class FakeTree:
+    """TEST DOUBLE for machin_b200.frame.buffers.WeightTree over the oracle tree (host memory)."""
+
+    def __init__(self, size):
+        from oracle.sumtree import OracleTree
+        self.ora = OracleTree(size)
+        self.size = size
+
+    @property
+    def weights(self):
+        return self.ora.weights
+
+    @property
+    def max_leaf(self):
+        return self.ora.max_leaf
+
+    def get_leaf_max(self):
+        return self.ora.get_leaf_max()
+
+    def get_weight_sum(self):
+        return self.ora.get_weight_sum()
+
+    def update_leaf_batch(self, weights, indexes, valid=None):
+        assert valid is None
+        self.ora.update_leaf_batch(weights, indexes)
+
+    def clear(self):
+        self.__init__(self.size)
+
+
+def make_cpu_prioritized(cls, capacity, epsilon=1e-2, alpha=0.6, beta=0.4, beta_increment_per_sampling=1e-3, **attrs):
+    """A product prioritized-buffer class over FakeRing + FakeTree; the draw (the CUDA kernel of the product) is the
+    oracle's restatement of prioritized_buffer.py:397-428, everything around it is the product's own Python."""
+    import numpy as np
+    from oracle import per as oper
+
+    class Cpu(cls):
+        def _draw(self, batch_size, all_weight_sum=None, uniform=None, use_device_params=False, out=None):
+            idx, isw = oper.sample_index_and_weight(self.wt_tree.ora, batch_size, len(self.storage), self.curr_beta,
+                                                    all_weight_sum)
+            self.curr_beta = np.min([1.0, self.curr_beta + self.beta_increment_per_sampling])
+            return t.from_numpy(np.asarray(idx, dtype=np.int64)), t.from_numpy(np.asarray(isw))
+
+    buf = make_cpu_buffer(Cpu, capacity, epsilon=epsilon, alpha=alpha, beta=beta, curr_beta=beta,
+                          beta_increment_per_sampling=beta_increment_per_sampling, wt_tree=FakeTree(capacity), **attrs)
+    return buf

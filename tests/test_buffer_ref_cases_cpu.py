@@ -172,3 +172,44 @@ def test_rnn_buffer_end_to_end_vs_reference_fixture(tag):
     random.seed(9)
     bs, (idx_list,) = buf.sample_batch(3, concatenate=False, sample_method="random_unique", sample_attrs=["index"])
     assert [list(w) for w in idx_list] == G[f"u{tag}_batch_index"].reshape(bs, L).tolist()
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_rnn_prioritized_buffer_python_logic_vs_reference_fixture(tag):
+    """RNNPrioritizedBuffer's own Python (store priorities with the unstartable tail zeroed, default priority and its
+    dtype, window gathering and reshaping, beta) over test doubles of ring, tree and draw -- against the fixture of
+    the unmodified reference (rnn_buffers.py:343-413).  The same schedule runs on the device in
+    tests/test_gpu_zz_rnn.py."""
+    from fake_ring import make_cpu_prioritized
+    from machin_b200.frame.buffers import RNNPrioritizedBuffer
+    G = np.load(os.path.join(GOLDEN, "ref_rnn.npz"))
+    cap, L, lens = int(G[f"p{tag}_cap"]), int(G[f"p{tag}_L"]), G[f"p{tag}_lens"]
+    buf = make_cpu_prioritized(RNNPrioritizedBuffer, cap, sample_length=L, sample_dimension=1)
+    pri, states, o = G[f"p{tag}_pri"], G[f"p{tag}_states"], 0
+    kw = dict(sample_attrs=["state", "reward", "index"], additional_concat_custom_attrs=["index"])
+    for k, n in enumerate(lens):
+        n = int(n)
+        ep = [dict(state={"state": t.from_numpy(states[o + i:o + i + 1].copy())}, action={"action": t.tensor([[1]])},
+                   next_state={"state": t.zeros(1, 3)}, reward=0.5, terminal=False, index=o + i) for i in range(n)]
+        p = pri[o:o + n].copy()
+        buf.store_episode(ep, priorities=None if p[0] < 0 else p)
+        o += n
+        assert np.array_equal(buf.wt_tree.weights, G[f"p{tag}_trees"][k]), (tag, k)
+        if k == 3:
+            np.random.seed(21)
+            n_s, _, index, isw = buf.sample_batch(6, sample_attrs=["index"], additional_concat_custom_attrs=["index"])
+            assert np.array_equal(index, G[f"p{tag}_mid_index"])
+            buf.update_priority(G[f"p{tag}_mid_newp"], index)
+            assert np.array_equal(buf.wt_tree.weights, G[f"p{tag}_mid_tree"])
+    np.random.seed(7)
+    for step in range(3):
+        q = f"p{tag}_s{step}_"
+        assert buf.curr_beta == float(G[q + "beta"])
+        n_s, (state, reward, seq), index, isw = buf.sample_batch(len(G[q + "uniform"]), **kw)
+        assert np.array_equal(index, G[q + "index"])
+        np.testing.assert_allclose(isw, G[q + "isw"], rtol=1e-12)
+        assert np.array_equal(state["state"].numpy(), G[q + "state"])
+        assert reward.shape == (n_s, L, 1)
+        assert np.array_equal(seq.numpy(), G[q + "seq"])
+        buf.update_priority(G[q + "newp"], index)
+        assert np.array_equal(buf.wt_tree.weights, G[q + "tree_after"])
