@@ -69,3 +69,58 @@ def _impala_member(rank, world):
 @pytest.mark.parametrize("world", [2, 4])
 def test_impala_episode_exchange_over_gloo(world):
     assert run_multi(_impala_member, world) == ["ok"] * world
+
+
+def _episode5():
+    return [{"state": {"state_1": t.zeros([1, 2])}, "action": {"action_1": t.ones([1, 3])},
+             "next_state": {"next_state_1": t.zeros([1, 2])}, "reward": 1.5, "terminal": True}] * 5
+
+
+def _dist_buffer(group, requesters=None):
+    from fake_ring import make_cpu_buffer
+    from machin_b200.frame.buffers import DistributedBuffer
+    return make_cpu_buffer(DistributedBuffer, 5, buffer_name="buffer", group=group, wr_lock=RLock(), _schema_agreed=False,
+                           requesters=list(range(group.size())) if requesters is None else requesters)
+
+
+def _distributed_buffer_cases(rank, world):
+    """The three cases of the reference's test_buffer_d.py:16-110 (store + sample, size / all_size, clear / all_clear),
+    SPMD: members 0 and 1 hold episodes, member 2 samples; collectives are entered by every member."""
+    from machin_b200.parallel import ShardGroup
+    group = ShardGroup("group")
+    # ---- store_episode and sample_batch
+    buffer = _dist_buffer(group, requesters=[2])
+    if rank in (0, 1):
+        buffer.store_episode(_episode5())
+    random.seed(rank)
+    batch_size, sample = buffer.sample_batch(7)
+    if rank == 2:
+        assert batch_size > 0 and len(sample) == 5
+        assert t.all(sample[0]["state_1"] == 0) and list(sample[0]["state_1"].shape) == [batch_size, 2]
+        assert t.all(sample[1]["action_1"] == 1) and list(sample[1]["action_1"].shape) == [batch_size, 3]
+        assert t.all(sample[3] == 1.5) and list(sample[3].shape) == [batch_size, 1]
+        assert t.all(sample[4]) and list(sample[4].shape) == [batch_size, 1]
+        assert batch_size == 2 * 3                       # ceil(7 / 3) from each of the two members that hold data
+    else:
+        assert batch_size == 0 and sample is None
+    # ---- size and all_size
+    buffer = _dist_buffer(group)
+    if rank == 0:
+        buffer.store_episode(_episode5())
+    assert buffer.size() == (5 if rank == 0 else 0)
+    assert buffer.all_size() == 5
+    # ---- clear and all_clear
+    buffer = _dist_buffer(group)
+    if rank in (0, 1):
+        buffer.store_episode(_episode5())
+    if rank == 0:
+        buffer.clear()
+        assert buffer.size() == 0
+    assert buffer.all_size() == 5
+    buffer.all_clear()
+    assert buffer.all_size() == 0
+    return "ok"
+
+
+def test_distributed_buffer_reference_cases_over_gloo():
+    assert run_multi(_distributed_buffer_cases, 3) == ["ok"] * 3
