@@ -1,0 +1,93 @@
+"""CPU: whole learner updates through the product's own algorithm classes, with host-memory test doubles under
+them -- the ring (tests/fake_ring.py) and, for the CUDA kernels, THE KERNELS' DEVICE SOURCE compiled for the host
+(tests/cpu_emul) -- against fixtures of the unmodified reference (tests/golden/ref_vtrace.npz: IMPALA.update()).
+The same test runs on the device in tests/test_gpu_algorithms.py; this one keeps the Python between the kernels
+(episode sampling with Python's random, loss assembly, optimizer steps) honest where no GPU exists."""
+import ctypes as C
+import os
+import random
+import subprocess
+from threading import RLock
+
+import numpy as np
+import pytest
+import torch as t
+
+from conftest import GOLDEN, ROOT
+from fake_ring import make_cpu_buffer
+
+EMUL = os.path.join(ROOT, "tests", "cpu_emul")
+
+
+@pytest.fixture(scope="module")
+def scan_lib(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("emul") / "scan_emul.so")
+    cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-Wno-unknown-pragmas", "-pthread", "-shared", "-fPIC",
+           "-I" + os.path.join(ROOT, "machin_b200", "csrc"), "-I" + os.path.join(ROOT, "include"),
+           os.path.join(EMUL, "scan_harness.cpp"), "-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-3000:]
+    return C.CDLL(out)
+
+
+def _emulated_vtrace(lib):
+    def vtrace(value, next_value, reward, terminal, log_pi, log_mu, discount, clip_c=1.0, clip_rho=1.0, offsets=None,
+               n_episodes=None, max_len=0):
+        f = lambda x: np.ascontiguousarray(x.detach().numpy().reshape(-1), dtype=np.float32)
+        p = lambda a: C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+        n = value.numel()
+        off = None if offsets is None else np.ascontiguousarray(offsets.numpy(), dtype=np.int64)
+        n_ep = int(n_episodes) if off is None else len(off) - 1
+        term = np.ascontiguousarray(terminal.numpy().reshape(-1).astype(np.uint8))
+        out = {k: np.full(n, np.nan, np.float32) for k in ("vs", "vss", "rho", "adv")}
+        assert lib.emul_vtrace(p(off), C.c_int64(n_ep), C.c_int64(n), p(f(value)), p(f(next_value)), p(f(reward)), p(term),
+                               p(f(log_pi)), p(f(log_mu)), C.c_float(discount), C.c_float(clip_c), C.c_float(clip_rho),
+                               p(out["vs"]), p(out["vss"]), p(out["rho"]), p(out["adv"]), C.c_int64(int(max_len))) == 0
+        return {k: t.from_numpy(v).view(value.shape) for k, v in out.items()}
+    return vtrace
+
+
+@pytest.mark.parametrize("tag", ["fixed", "ragged"])
+def test_impala_update_over_doubles_vs_reference(tag, scan_lib, monkeypatch):
+    import machin_b200.frame.algorithms.impala as impala_mod
+    from machin_b200.frame.buffers import IMPALABuffer
+    from machin_b200.parallel import LocalGroup
+    from test_gpu_algorithms import PolicyNet, ValueNet, _flat, _load_flat
+
+    def buffer_double(buffer_name, group, buffer_size, requesters=None):
+        return make_cpu_buffer(IMPALABuffer, buffer_size, buffer_name=buffer_name, group=group, wr_lock=RLock(),
+                               requesters=[0] if requesters is None else requesters, _schema_agreed=False)
+
+    monkeypatch.setattr(impala_mod, "IMPALABuffer", buffer_double)
+    monkeypatch.setattr(impala_mod.ops, "vtrace", _emulated_vtrace(scan_lib))
+    g = np.load(os.path.join(GOLDEN, "ref_vtrace.npz"))
+    lengths = [int(x) for x in g[f"{tag}_lengths"]]
+    clip_c, clip_rho, discount = (float(x) for x in g[f"{tag}_clip"])
+    S, A = 8, 3
+    actor, critic = PolicyNet(S, A), ValueNet(S)
+    _load_flat(actor, g[f"{tag}_actor0"])
+    _load_flat(critic, g[f"{tag}_critic0"])
+    captured = {}
+
+    def criterion(value, vs):
+        captured["vs"] = vs.detach().clone()
+        return ((value - vs) ** 2).sum()
+
+    imp = impala_mod.IMPALA(actor, critic, t.optim.SGD, criterion, LocalGroup(device="cpu"), (), batch_size=len(lengths),
+                            learning_rate=0.01, isw_clip_c=clip_c, isw_clip_rho=clip_rho, discount=discount,
+                            replay_size=4 * sum(lengths))
+    pos = 0
+    for n in lengths:
+        imp.store_episode([dict(state={"state": t.from_numpy(g[f"{tag}_state"][i:i + 1])},
+                                action={"action": t.tensor([[int(g[f"{tag}_action"][i])]])},
+                                next_state={"state": t.from_numpy(g[f"{tag}_next_state"][i:i + 1])},
+                                reward=float(g[f"{tag}_reward"][i]), action_log_prob=float(g[f"{tag}_logmu"][i]),
+                                terminal=bool(g[f"{tag}_terminal"][i])) for i in range(pos, pos + n)])
+        pos += n
+    t.manual_seed(3); np.random.seed(3); random.seed(3)
+    pol, val = imp.update()
+    ref_pol, ref_val = g[f"{tag}_losses"]
+    np.testing.assert_allclose(captured["vs"].numpy().reshape(-1), g[f"{tag}_vs"], rtol=1e-5, atol=1e-6)
+    assert abs(pol - ref_pol) <= 1e-5 * max(1.0, abs(ref_pol)) and abs(val - ref_val) <= 1e-5 * max(1.0, abs(ref_val))
+    np.testing.assert_allclose(_flat(imp.actor), g[f"{tag}_actor1"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(_flat(imp.critic), g[f"{tag}_critic1"], rtol=1e-5, atol=1e-6)
