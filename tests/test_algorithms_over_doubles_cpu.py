@@ -91,3 +91,50 @@ def test_impala_update_over_doubles_vs_reference(tag, scan_lib, monkeypatch):
     assert abs(pol - ref_pol) <= 1e-5 * max(1.0, abs(ref_pol)) and abs(val - ref_val) <= 1e-5 * max(1.0, abs(ref_val))
     np.testing.assert_allclose(_flat(imp.actor), g[f"{tag}_actor1"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(_flat(imp.critic), g[f"{tag}_critic1"], rtol=1e-5, atol=1e-6)
+
+
+def _emulated_gae(lib):
+    def gae(reward, terminal, critic_value, next_critic_value, discount, gae_lambda, offsets=None, n_episodes=None,
+            max_len=0):
+        p = lambda a: C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+        r = np.ascontiguousarray(reward.detach().numpy().reshape(-1), dtype=np.float64)
+        n = r.shape[0]
+        term = np.ascontiguousarray(terminal.numpy().reshape(-1).astype(np.uint8))
+        cv = np.ascontiguousarray(critic_value.detach().numpy().reshape(-1), dtype=np.float32)
+        ncv = np.ascontiguousarray(next_critic_value.detach().numpy().reshape(-1), dtype=np.float32)
+        off = None if offsets is None else np.ascontiguousarray(offsets.numpy(), dtype=np.int64)
+        n_ep = int(n_episodes) if off is None else len(off) - 1
+        ret, adv = np.full(n, np.nan), np.full(n, np.nan)
+        assert lib.emul_gae(p(off), C.c_int64(n_ep), C.c_int64(n), p(r), p(term), p(cv), p(ncv), C.c_double(discount),
+                            C.c_double(gae_lambda), p(ret), p(adv), C.c_int64(int(max_len))) == 0
+        return {"returns": t.from_numpy(ret).view(reward.shape), "gae": t.from_numpy(adv).view(reward.shape)}
+    return gae
+
+
+@pytest.mark.parametrize("lam", [1.0, 0.0, 0.95])
+def test_a2c_store_episode_and_update_over_doubles_vs_reference(lam, scan_lib, monkeypatch):
+    """A2C.store_episode (batched critic + returns / GAE kernel source under emulation) against the reference's
+    per-step Python loop (tests/golden/ref_gae.npz, a2c.py:269-326), then one update through the buffer double."""
+    import machin_b200.frame.algorithms.a2c as a2c_mod
+    from machin_b200.frame.buffers import Buffer
+    from test_gpu_algorithms import PolicyNet, ValueNet, _load_flat
+    monkeypatch.setattr(a2c_mod.ops, "gae", _emulated_gae(scan_lib))
+    g = np.load(os.path.join(GOLDEN, "ref_gae.npz"))
+    S, A = 8, 3
+    actor, critic = PolicyNet(S, A), ValueNet(S)
+    _load_flat(critic, g["critic0"])
+    a2c = a2c_mod.A2C(actor, critic, t.optim.SGD, t.nn.MSELoss(reduction="sum"), batch_size=8, discount=0.97, gae_lambda=lam,
+                      replay_buffer=make_cpu_buffer(Buffer, 5000))
+    for e in range(4):
+        k = f"lam{lam}_ep{e}_"
+        n = len(g[k + "reward"])
+        ep = [dict(state={"state": t.from_numpy(g[k + "state"][i:i + 1])}, action={"action": t.tensor([[0]])},
+                   next_state={"state": t.from_numpy(g[k + "next_state"][i:i + 1])}, reward=float(g[k + "reward"][i]),
+                   terminal=bool(g[k + "terminal"][i])) for i in range(n)]
+        a2c.store_episode(ep)
+        assert [tr["value"] for tr in ep] == list(g[k + "value"])              # float64 returns: bit-exact
+        np.testing.assert_allclose([tr["gae"] for tr in ep], g[k + "gae"], rtol=1e-5, atol=2e-6)
+    bs, (state, adv) = a2c.replay_buffer.sample_batch(16, sample_attrs=["state", "gae"], additional_concat_custom_attrs=["gae"])
+    assert adv.shape == (bs, 1) and adv.dtype == t.float32
+    pol, val = a2c.update()
+    assert np.isfinite(pol) and np.isfinite(val) and a2c.replay_buffer.size() == 0
