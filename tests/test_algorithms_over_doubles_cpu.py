@@ -138,3 +138,80 @@ def test_a2c_store_episode_and_update_over_doubles_vs_reference(lam, scan_lib, m
     assert adv.shape == (bs, 1) and adv.dtype == t.float32
     pol, val = a2c.update()
     assert np.isfinite(pol) and np.isfinite(val) and a2c.replay_buffer.size() == 0
+
+
+@pytest.fixture(scope="module")
+def td_lib(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("emul") / "td_emul.so")
+    cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-Wno-unknown-pragmas", "-pthread", "-shared", "-fPIC",
+           "-I" + os.path.join(ROOT, "machin_b200", "csrc"), "-I" + os.path.join(ROOT, "include"),
+           os.path.join(EMUL, "td_harness.cpp"), "-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-3000:]
+    return C.CDLL(out)
+
+
+def _emulated_td_dqn(lib):
+    def td_dqn(q, q_next, q_tgt_next, action, reward, terminal, discount, is_weight=None, mode="double", want_grad=False):
+        p = lambda a: C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+        f = lambda x: None if x is None else np.ascontiguousarray(x.detach().numpy(), dtype=np.float32)
+        qa, qn, qt = f(q), f(q_next), f(q_tgt_next)
+        B, A = qt.shape
+        act = np.ascontiguousarray(action.numpy().reshape(-1), dtype=np.int64)
+        rew = np.ascontiguousarray(reward.detach().numpy().reshape(-1), dtype=np.float32)
+        term = np.ascontiguousarray(terminal.numpy().reshape(-1).astype(np.uint8))
+        isw = None if is_weight is None else np.ascontiguousarray(is_weight.numpy().reshape(-1), dtype=np.float64)
+        y, av, ae = (np.full(B, np.nan, np.float32) for _ in range(3))
+        le = np.full(B, np.nan)
+        gq = np.full((B, A), np.nan, np.float32) if want_grad else None
+        assert lib.emul_td_dqn(p(qa), p(qn), p(qt), C.c_int64(B), A, p(act), p(rew), p(term), p(isw), C.c_float(discount),
+                               0 if mode == "double" else 1, p(y), p(av), p(ae), p(le), p(gq)) == 0
+        return {"y": t.from_numpy(y).view(B, 1), "action_value": t.from_numpy(av).view(B, 1), "abs_error": t.from_numpy(ae),
+                "loss_elem": t.from_numpy(le).view(B, 1), "grad_q": None if gq is None else t.from_numpy(gq)}
+    return td_dqn
+
+
+@pytest.mark.parametrize("criterion", ["mse_fused", "mse_generic"])
+def test_dqn_per_update_over_doubles_vs_reference(criterion, td_lib, monkeypatch):
+    """Whole DQNPer.update() -- draw (oracle restatement as the double of the draw kernel), gather, double-DQN target /
+    priority math (the kernel's row function compiled for the host), PER write-back, SGD step, soft target update --
+    against the unmodified reference (tests/golden/ref_td.npz; dqn_per.py:89-161)."""
+    import machin_b200.frame.algorithms.dqn_per as dqn_mod
+    import machin_b200.frame.algorithms.utils as utils_mod
+    from fake_ring import make_cpu_prioritized
+    from machin_b200.frame.buffers import PrioritizedBuffer
+    from oracle import td as otd
+    from test_gpu_algorithms import QNet, _flat, _load_flat
+
+    class CpuPer(PrioritizedBuffer):
+        def update_priority(self, priorities, indexes, valid=None):     # device tensors in the product: host arrays here
+            to_np = lambda x: x.detach().numpy() if t.is_tensor(x) else x
+            return PrioritizedBuffer.update_priority(self, to_np(priorities), to_np(indexes))
+
+    monkeypatch.setattr(dqn_mod.ops, "td_dqn", _emulated_td_dqn(td_lib))
+    soft = lambda tgt, src, rate: otd.soft_update_(list(tgt.parameters()), list(src.parameters()), rate)
+    monkeypatch.setattr(dqn_mod, "soft_update", soft)
+    monkeypatch.setattr(utils_mod, "soft_update", soft)
+    g = np.load(os.path.join(GOLDEN, "ref_td.npz"))
+    S, A, N, B = 6, 4, 200, 32
+    qnet, qtgt = QNet(S, A), QNet(S, A)
+    _load_flat(qtgt, g["dqn_init_qt"])
+    dqn = dqn_mod.DQNPer(qnet, qtgt, t.optim.SGD, t.nn.MSELoss(reduction="sum"), batch_size=B, learning_rate=0.01,
+                         discount=0.97, update_rate=0.05, replay_buffer=make_cpu_prioritized(CpuPer, N))
+    if criterion == "mse_generic":
+        dqn._fused_mse = False
+        dqn.fuse_online_forwards = True
+    assert np.array_equal(_flat(dqn.qnet), g["dqn_init_q"])
+    ep = [dict(state={"state": t.from_numpy(g["dqn_state"][i:i + 1])}, action={"action": t.tensor([[g["dqn_action"][i]]])},
+               next_state={"state": t.from_numpy(g["dqn_next_state"][i:i + 1])}, reward=float(g["dqn_reward"][i]),
+               terminal=bool(g["dqn_terminal"][i])) for i in range(N)]
+    dqn.replay_buffer.store_episode(ep, priorities=list(g["dqn_priority"]))
+    assert np.array_equal(dqn.replay_buffer.wt_tree.weights, g["dqn_tree0"])
+    np.random.seed(11)
+    for step in range(3):
+        loss = dqn.update()
+        ref = float(g[f"dqn_loss{step}"])
+        assert abs(loss - ref) <= 1e-5 * abs(ref), (step, loss, ref)
+        np.testing.assert_allclose(dqn.replay_buffer.wt_tree.weights, g[f"dqn_tree{step + 1}"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(_flat(dqn.qnet), g[f"dqn_q{step + 1}"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(_flat(dqn.qnet_target), g[f"dqn_qt{step + 1}"], rtol=1e-5, atol=1e-6)
