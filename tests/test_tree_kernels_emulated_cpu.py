@@ -91,6 +91,8 @@ def _indexes(rng, size, n, kind):
 @pytest.mark.parametrize("variant", ["sorted", "v2_async", "v2_cluster", "v2_cluster_async"])
 @pytest.mark.parametrize("size,n,kind", CASES)
 def test_sorted_update_kernels_under_emulation(tree_emul, tmp_path, variant, size, n, kind):
+    if n > 256 and "cluster" in variant:
+        pytest.skip("8 CTAs x 512 OS threads: kept out of the CPU suite (the 200-entry case covers several warps per CTA)")
     tree, rng = _tree(size, size % 97 + n)
     idx = _indexes(rng, size, n, kind)
     w = rng.exponential(size=n).astype(np.float32 if n % 2 else np.float64)
