@@ -16,6 +16,8 @@
 // reaches ~1 CTA per SM even though the matrices are small.
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+
 #include <new>
 #include <vector>
 
@@ -384,6 +386,7 @@ struct mb_mlp_program {
     int n_ops, n_phases, grid;
     std::vector<void *> owned;   // device allocations (activations, partials, counters)
     int rows;                    // row-tile variant: transpose refresh + dqn_rows_kernel + single-phase dW program
+    int rows_cpt;                // its thread layout: 4 or 2 output columns per thread (MB_ROWS_CPT, default 4)
     RowsArgs ra;
     TransposeList tl;
     size_t rows_smem;
@@ -599,8 +602,13 @@ int mb_dqn_mlp_rows_create(int device, int n_layers, const int *sizes, int batch
     P->rows_smem = sizeof(float) * (size_t)(2 * RB) * (size_t)(xp + 2 * RP);
     P->rows_grid = (batch + RB - 1) / RB;
     // one fixed opt-in limit for every program on this device (a later, smaller program must not lower it)
+    {
+        const char *e = getenv("MB_ROWS_CPT");
+        P->rows_cpt = (e && e[0] == '2') ? 2 : 4;
+    }
     if (P->rows_smem > 160 * 1024 ||
-        cudaFuncSetAttribute(dqn_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess) {
+        cudaFuncSetAttribute(dqn_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(dqn_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess) {
         cudaGetLastError();
         mb_mlp_program_destroy(P);
         return MB_ERR_INVALID;
@@ -619,7 +627,8 @@ int mb_mlp_program_run_part(mb_mlp_program *P, int part, void *stream) {
         int64_t blocks = (total + 255) / 256;
         if (blocks > (int64_t)mb::kNumSMs * 4) blocks = (int64_t)mb::kNumSMs * 4;
         transpose_multi_kernel<<<(unsigned)blocks, 256, 0, s>>>(P->tl);
-        dqn_rows_kernel<<<(unsigned)P->rows_grid, RT, P->rows_smem, s>>>(P->ra);
+        if (P->rows_cpt == 2) dqn_rows_kernel<2><<<(unsigned)P->rows_grid, RT, P->rows_smem, s>>>(P->ra);
+        else dqn_rows_kernel<4><<<(unsigned)P->rows_grid, RT, P->rows_smem, s>>>(P->ra);
         MB_LAUNCHED(2);
         return MB_OK;
     }

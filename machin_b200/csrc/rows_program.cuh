@@ -27,35 +27,55 @@ struct RowsArgs {
     TdDqnArgs td;
 };
 
-template <bool kVec>
-__device__ __forceinline__ float4 rows_load_b(const float *__restrict__ row, int j0, int N) {
-    if (kVec) return __ldg(reinterpret_cast<const float4 *>(row + j0));
-    float4 v;
-    v.x = j0 + 0 < N ? __ldg(row + j0 + 0) : 0.0f;
-    v.y = j0 + 1 < N ? __ldg(row + j0 + 1) : 0.0f;
-    v.z = j0 + 2 < N ? __ldg(row + j0 + 2) : 0.0f;
-    v.w = j0 + 3 < N ? __ldg(row + j0 + 3) : 0.0f;
-    return v;
+// Thread layout, chosen at compile time: CPT output columns per thread.  RT threads form G = RT * CPT / RW row groups
+// of RW / CPT threads; a thread owns MR = M / G rows x CPT columns of the M x N output.
+//   CPT = 4: 4 row groups x 64 threads, one 16-byte weight load per k (4 LSU wavefronts per warp), MR = 4 (online);
+//   CPT = 2: 2 row groups x 128 threads, one 8-byte weight load per k (2 wavefronts), MR = 8: every weight is
+//            fetched by half as many row groups -- 4 LSU wavefronts per 16 FFMA instead of 5.
+template <int CPT> struct RowsLayout {
+    static constexpr int kThreadsPerGroup = RW / CPT;
+    static constexpr int kGroups = RT / kThreadsPerGroup;
+};
+
+template <int CPT, bool kVec>
+__device__ __forceinline__ void rows_load_b(const float *__restrict__ row, int j0, int N, float (&v)[CPT]) {
+    if (kVec) {
+        if (CPT == 4) {
+            const float4 x = __ldg(reinterpret_cast<const float4 *>(row + j0));
+            v[0] = x.x; v[1] = x.y; v[CPT - 2] = x.z; v[CPT - 1] = x.w;
+        } else {
+            const float2 x = __ldg(reinterpret_cast<const float2 *>(row + j0));
+            v[0] = x.x; v[1] = x.y;
+        }
+        return;
+    }
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) v[c] = j0 + c < N ? __ldg(row + j0 + c) : 0.0f;
 }
 
 // acc[r][c] = sum_k As[(ty * MR + r) * ap + k] * Bg[k * N + j0 + c]      (rows in shared memory, B k-major in global)
 // The weights come straight from L2 and a CTA of 8 warps has an SM to itself, so nothing else hides the ~700-cycle
 // latency: three register buffers of 8 k-steps rotate -- while one is multiplied (~320 cycles) the loads of the
 // next two are in flight -- and the tail of K is loaded predicated in the same batches instead of one dependent
-// load per step.  k ascends, one fmaf per term: the summation order does not depend on the buffering.
-template <int MR, bool kVec>
+// load per step.  k ascends, one fmaf per term: the summation order does not depend on the buffering or the layout.
+template <int MR, int CPT, bool kVec>
 __device__ __forceinline__ void rows_matmul_impl(const float *As, int ap, int K, const float *__restrict__ Bg, int N,
-                                                 float (&acc)[MR][4]) {
-    const int ty = threadIdx.x >> 6, j0 = (threadIdx.x & 63) * 4;
+                                                 float (&acc)[MR][CPT]) {
+    constexpr int NG = RowsLayout<CPT>::kThreadsPerGroup;
+    const int ty = threadIdx.x / NG, j0 = (threadIdx.x % NG) * CPT;
     const float *a0 = As + (ty * MR) * ap;
-    auto load8 = [&](float4 (&b)[8], int k) {
+    auto load8 = [&](float (&b)[8][CPT], int k) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            if (k + u < K) b[u] = rows_load_b<kVec>(Bg + (int64_t)(k + u) * N, j0, N);
-            else b[u] = float4{0.0f, 0.0f, 0.0f, 0.0f};
+            if (k + u < K) {
+                rows_load_b<CPT, kVec>(Bg + (int64_t)(k + u) * N, j0, N, b[u]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) b[u][c] = 0.0f;
+            }
         }
     };
-    auto mul8 = [&](const float4 (&b)[8], int k) {
+    auto mul8 = [&](const float (&b)[8][CPT], int k) {
         if (k >= K) return;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -75,18 +95,14 @@ __device__ __forceinline__ void rows_matmul_impl(const float *As, int ap, int K,
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 if (kh + kk >= K) break;                          // exact term count: no +0 terms
-                const float4 bb = b[4 * h + kk];
 #pragma unroll
-                for (int r = 0; r < MR; ++r) {
-                    acc[r][0] = fmaf(av[r][kk], bb.x, acc[r][0]);
-                    acc[r][1] = fmaf(av[r][kk], bb.y, acc[r][1]);
-                    acc[r][2] = fmaf(av[r][kk], bb.z, acc[r][2]);
-                    acc[r][3] = fmaf(av[r][kk], bb.w, acc[r][3]);
-                }
+                for (int r = 0; r < MR; ++r)
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) acc[r][c] = fmaf(av[r][kk], b[4 * h + kk][c], acc[r][c]);
             }
         }
     };
-    float4 b0[8], b1[8], b2[8];
+    float b0[8][CPT], b1[8][CPT], b2[8][CPT];
     load8(b0, 0);
     load8(b1, 8);
     for (int k = 0; k < K; k += 24) {
@@ -99,34 +115,35 @@ __device__ __forceinline__ void rows_matmul_impl(const float *As, int ap, int K,
     }
 }
 
-template <int MR>
+template <int MR, int CPT>
 __device__ __forceinline__ void rows_matmul(const float *As, int ap, int K, const float *__restrict__ Bg, int N,
-                                            float (&acc)[MR][4]) {
+                                            float (&acc)[MR][CPT]) {
 #pragma unroll
     for (int r = 0; r < MR; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
-    if ((int)(threadIdx.x & 63) * 4 >= N) return;
-    // N % 4 == 0: a thread's four columns exist and every row of Bg is 16-byte aligned -> one LDG.128 per k
-    if ((N & 3) == 0) rows_matmul_impl<MR, true>(As, ap, K, Bg, N, acc);
-    else rows_matmul_impl<MR, false>(As, ap, K, Bg, N, acc);
+        for (int c = 0; c < CPT; ++c) acc[r][c] = 0.0f;
+    if ((int)(threadIdx.x % RowsLayout<CPT>::kThreadsPerGroup) * CPT >= N) return;
+    // N % CPT == 0: a thread's columns all exist and every row of Bg is aligned for one vector load per k
+    if (N % CPT == 0) rows_matmul_impl<MR, CPT, true>(As, ap, K, Bg, N, acc);
+    else rows_matmul_impl<MR, CPT, false>(As, ap, K, Bg, N, acc);
 }
 
-// One forward layer for M = 4 * MR rows held in shared memory.  save0: rows [0, RB) also go to global at batch
+// One forward layer for M = kGroups * MR rows held in shared memory.  save0: rows [0, RB) also go to global at batch
 // row b0 + row (activations of the Q(s) pass / q); save1: rows [row1, row1 + RB) go to global (qn or qtn).
-template <int MR>
+template <int MR, int CPT>
 __device__ __forceinline__ void rows_forward_layer(const float *in, int ip, float *out, int K, int N,
                                                    const float *__restrict__ Wt, const float *__restrict__ bias,
                                                    bool relu, int b0, int batch, float *save0, float *save1, int row1) {
-    float acc[MR][4];
-    rows_matmul<MR>(in, ip, K, Wt, N, acc);
-    const int ty = threadIdx.x >> 6, j0 = (threadIdx.x & 63) * 4;
+    constexpr int NG = RowsLayout<CPT>::kThreadsPerGroup;
+    float acc[MR][CPT];
+    rows_matmul<MR, CPT>(in, ip, K, Wt, N, acc);
+    const int ty = threadIdx.x / NG, j0 = (threadIdx.x % NG) * CPT;
     if (j0 < N) {
 #pragma unroll
         for (int r = 0; r < MR; ++r) {
             const int row = ty * MR + r;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < CPT; ++c) {
                 const int j = j0 + c;
                 if (j >= N) continue;
                 float v = __fadd_rn(acc[r][c], __ldg(bias + j));
@@ -141,7 +158,10 @@ __device__ __forceinline__ void rows_forward_layer(const float *in, int ip, floa
     __syncthreads();
 }
 
+template <int CPT>
 __global__ void __launch_bounds__(RT) dqn_rows_kernel(RowsArgs a) {
+    constexpr int G = RowsLayout<CPT>::kGroups, NG = RowsLayout<CPT>::kThreadsPerGroup;
+    static_assert((2 * RB) % G == 0 && RB % G == 0, "row groups must divide the row counts");
     extern __shared__ __align__(16) float rsm[];
     const int S = a.sizes[0], xp = ((S + 3) & ~3) + 4, L = a.L, A = a.sizes[L];
     float *X = rsm;                      // [2 * RB][xp]: rows 0..RB-1 = s, RB..2RB-1 = s'
@@ -161,8 +181,8 @@ __global__ void __launch_bounds__(RT) dqn_rows_kernel(RowsArgs a) {
         for (int l = 0; l < L; ++l) {
             float *out = (l & 1) ? B1 : B0;
             const bool last = l == L - 1;
-            rows_forward_layer<4>(in, ip, out, a.sizes[l], a.sizes[l + 1], a.Wt[l], a.b[l], !last, b0, a.batch, a.h[l],
-                                  last ? a.qn : nullptr, RB);
+            rows_forward_layer<2 * RB / G, CPT>(in, ip, out, a.sizes[l], a.sizes[l + 1], a.Wt[l], a.b[l], !last, b0, a.batch,
+                                                a.h[l], last ? a.qn : nullptr, RB);
             in = out;
             ip = RP;
         }
@@ -174,8 +194,8 @@ __global__ void __launch_bounds__(RT) dqn_rows_kernel(RowsArgs a) {
         for (int l = 0; l < L; ++l) {
             float *out = (l & 1) ? B1 : B0;
             const bool last = l == L - 1;
-            rows_forward_layer<2>(in, ip, out, a.sizes[l], a.sizes[l + 1], a.tWt[l], a.tb[l], !last, b0, a.batch, nullptr,
-                                  last ? a.qtn : nullptr, 0);
+            rows_forward_layer<RB / G, CPT>(in, ip, out, a.sizes[l], a.sizes[l + 1], a.tWt[l], a.tb[l], !last, b0, a.batch,
+                                            nullptr, last ? a.qtn : nullptr, 0);
             in = out;
             ip = RP;
         }
@@ -192,15 +212,16 @@ __global__ void __launch_bounds__(RT) dqn_rows_kernel(RowsArgs a) {
     __syncthreads();
     for (int l = L - 1; l >= 1; --l) {
         const int K = a.sizes[l + 1], N = a.sizes[l];
-        float acc[2][4];
-        rows_matmul<2>(cur, RP, K, a.W[l], N, acc);
-        const int ty = tid >> 6, j0 = (tid & 63) * 4;
+        constexpr int MRB = RB / G;
+        float acc[MRB][CPT];
+        rows_matmul<MRB, CPT>(cur, RP, K, a.W[l], N, acc);
+        const int ty = tid / NG, j0 = (tid % NG) * CPT;
         if (j0 < N) {
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int row = ty * 2 + r, b = b0 + row;
+            for (int r = 0; r < MRB; ++r) {
+                const int row = ty * MRB + r, b = b0 + row;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < CPT; ++c) {
                     const int j = j0 + c;
                     if (j >= N) continue;
                     float v = 0.0f;

@@ -28,6 +28,8 @@ inline std::barrier<> *shim_cta_barrier = nullptr;
 inline void __syncthreads() { shim_cta_barrier->arrive_and_wait(); }
 
 struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) float2 { float x, y; };
+inline float2 __ldg(const float2 *p) { return *p; }
 inline float __ldg(const float *p) { return *p; }
 inline float4 __ldg(const float4 *p) { return *p; }
 inline float __ldcg(const float *p) { return *p; }

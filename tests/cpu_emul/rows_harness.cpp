@@ -14,7 +14,7 @@ extern "C" int emul_dqn_rows(int L, const int *sizes, int batch, const float *co
                              const float *state, const float *next_state, float *const *h, float *qn, float *qtn,
                              float *const *dz, const int64_t *action, const float *reward, const uint8_t *terminal,
                              const double *isw, float discount, int mode, float *y, float *av, float *abs_err,
-                             double *loss) {
+                             double *loss, int cpt) {
     if (L < 1 || L > RL) return -1;
     RowsArgs a{};
     a.L = L;
@@ -32,6 +32,7 @@ extern "C" int emul_dqn_rows(int L, const int *sizes, int batch, const float *co
                      loss, dz[L - 1]};
     const int xp = ((sizes[0] + 3) & ~3) + 4;
     if ((size_t)(2 * RB) * (size_t)(xp + 2 * RP) > sizeof(rsm) / sizeof(float)) return -2;
-    shim_launch((unsigned)((batch + RB - 1) / RB), RT, [&] { dqn_rows_kernel(a); });
+    if (cpt == 2) shim_launch((unsigned)((batch + RB - 1) / RB), RT, [&] { dqn_rows_kernel<2>(a); });
+    else shim_launch((unsigned)((batch + RB - 1) / RB), RT, [&] { dqn_rows_kernel<4>(a); });
     return 0;
 }

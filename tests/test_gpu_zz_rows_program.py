@@ -27,7 +27,9 @@ def _load_flat(m, flat):
 @pytest.mark.parametrize("sizes,batch", [([6, 16, 16, 4], 32), ([84, 256, 256, 6], 512), ([7, 33, 10, 3], 50),
                                           ([12, 64, 5], 9), ([20, 8, 8, 8, 2], 64)])
 @pytest.mark.parametrize("graph", [False, True])
-def test_rows_program_matches_autograd_path(sizes, batch, graph):
+@pytest.mark.parametrize("cpt", ["4", "2"])
+def test_rows_program_matches_autograd_path(sizes, batch, graph, cpt, monkeypatch):
+    monkeypatch.setenv("MB_ROWS_CPT", cpt)              # thread layout of the row-tile kernel, read at program creation
     from machin_b200.frame.algorithms import DQNPer
     from machin_b200.model import FusedMLP
     S, A, N = sizes[0], sizes[-1], 3000

@@ -43,7 +43,8 @@ def _forward(Ws, bs, x):
 @pytest.mark.parametrize("sizes,batch", [([6, 16, 16, 4], 32), ([84, 256, 256, 6], 20), ([7, 33, 10, 3], 50),
                                           ([12, 64, 5], 9), ([20, 8, 8, 8, 2], 17), ([5, 3], 8)])
 @pytest.mark.parametrize("mode", [0, 1])
-def test_rows_kernel_source_under_emulation(harness, sizes, batch, mode):
+@pytest.mark.parametrize("cpt", [4, 2])
+def test_rows_kernel_source_under_emulation(harness, sizes, batch, mode, cpt):
     rng = np.random.RandomState(len(sizes) * 100 + batch + mode)
     L, S, A = len(sizes) - 1, sizes[0], sizes[-1]
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
@@ -68,7 +69,7 @@ def test_rows_kernel_source_under_emulation(harness, sizes, batch, mode):
         C.c_void_p(state.ctypes.data), C.c_void_p(nstate.ctypes.data), _ptrs(h), C.c_void_p(qn.ctypes.data),
         C.c_void_p(qtn.ctypes.data), _ptrs(dz), C.c_void_p(action.ctypes.data), C.c_void_p(reward.ctypes.data),
         C.c_void_p(terminal.ctypes.data), C.c_void_p(isw.ctypes.data), C.c_float(float(gamma)), mode,
-        C.c_void_p(y.ctypes.data), C.c_void_p(av.ctypes.data), C.c_void_p(ab.ctypes.data), C.c_void_p(loss.ctypes.data))
+        C.c_void_p(y.ctypes.data), C.c_void_p(av.ctypes.data), C.c_void_p(ab.ctypes.data), C.c_void_p(loss.ctypes.data), cpt)
     assert rc == 0
     # ---- restatement (float64 accumulation; the kernel is float32 FMA in k order: tolerance, not bits)
     hs = _forward(W, b, state.astype(np.float64))

@@ -30,6 +30,7 @@ run cluster_async      "MB_SORTED_CLUSTER=1 MB_SORTED_ASYNC=1"  ""
 run all                "MB_SORTED_CLUSTER=1"  "--overlap-update --parallel-forwards"
 run fused_autograd     "MB_X=0"               "--net fused"
 run fused_rows         "MB_X=0"               "--net fused-rows"
+run fused_rows_cpt2    "MB_ROWS_CPT=2"        "--net fused-rows"
 run fused_rows_overlap "MB_X=0"               "--net fused-rows --overlap-update"
 run fused_rows_all     "MB_SORTED_CLUSTER=1 MB_SORTED_ASYNC=1"  "--net fused-rows --overlap-update"
 for v in "MB_X=0" "MB_SORTED_CLUSTER=1" "MB_SORTED_ASYNC=1" "MB_SORTED_CLUSTER=1 MB_SORTED_ASYNC=1"; do
