@@ -317,9 +317,9 @@ def time_kernels(learner, table, reps=20, per_graph=16):
     if prog:                                   # the fused program replaces the stand-alone TD kernel in the step
         def k_part(part):
             return lambda i: _lib.check(lib.mb_mlp_program_run_part(prog["handle"], part, sp()))
-        timed = [x for x in timed if x[0] != "mb_td_dqn"] + [("mb_mlp_program_part0", k_part(0))]
-        if learner.fused_kind == "rows":       # (the cooperative program does everything in part 0)
-            timed.append(("mb_mlp_program_part1", k_part(1)))
+        timed = [x for x in timed if x[0] != "mb_td_dqn"] + [("mb_mlp_program_part0", k_part(1))]
+        if learner.fused_kind == "rows":       # (the cooperative program does everything in part 1 of the C call)
+            timed.append(("mb_mlp_program_part1", k_part(2)))
     out = {}
     for name, fn in timed:
         side = t.cuda.Stream(device=dev)

@@ -277,9 +277,10 @@ int mb_dqn_mlp_rows_create(int device, int n_layers, const int *sizes, int batch
                            float *d_y, float *d_action_value, float *d_abs_error, double *d_loss_elem,
                            mb_mlp_program **out);
 int mb_mlp_program_run(mb_mlp_program *program, void *stream);
-/* The same in two parts, for callers that want to start something else in between on another stream (the priority
- * write-back only needs |delta|): part 0 = forward passes + TD + backward-input (everything for the cooperative
- * program), part 1 = weight / bias gradients (row-tile program only). */
+/* The same in three parts, for callers that overlap other work on a second stream: part 0 = refresh of the k-major
+ * weight copies (row-tile program only; needs nothing but the weights, so it can run beside the draw and the gather),
+ * part 1 = forward passes + TD + backward-input (everything, for the cooperative program), part 2 = weight / bias
+ * gradients (row-tile program only; the priority write-back only needs |delta| and can start before it). */
 int mb_mlp_program_run_part(mb_mlp_program *program, int part, void *stream);
 int mb_mlp_program_destroy(mb_mlp_program *program);
 /* torch.optim.Adam step (amsgrad off) over n_tensors parameter tensors in one launch; d_step_count is a

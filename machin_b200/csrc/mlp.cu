@@ -619,30 +619,37 @@ int mb_dqn_mlp_rows_create(int device, int n_layers, const int *sizes, int batch
 }
 
 int mb_mlp_program_run_part(mb_mlp_program *P, int part, void *stream) {
-    if (!P || part < 0 || part > 1) return MB_ERR_INVALID;
+    if (!P || part < 0 || part > 2) return MB_ERR_INVALID;
     mb::DeviceGuard guard(P->device);
-    if (P->rows && part == 0) {
-        cudaStream_t s = (cudaStream_t)stream;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (part == 0) {                                   // refresh the k-major weight copies (row-tile program only)
+        if (!P->rows) return MB_OK;
         const int64_t total = P->tl.start[P->tl.n];
         int64_t blocks = (total + 255) / 256;
         if (blocks > (int64_t)mb::kNumSMs * 4) blocks = (int64_t)mb::kNumSMs * 4;
         transpose_multi_kernel<<<(unsigned)blocks, 256, 0, s>>>(P->tl);
-        if (P->rows_cpt == 2) dqn_rows_kernel<2><<<(unsigned)P->rows_grid, RT, P->rows_smem, s>>>(P->ra);
-        else dqn_rows_kernel<4><<<(unsigned)P->rows_grid, RT, P->rows_smem, s>>>(P->ra);
-        MB_LAUNCHED(2);
+        MB_LAUNCHED(1);
         return MB_OK;
     }
-    if (!P->rows && part == 1) return MB_OK;     // the cooperative program does everything in part 0
+    if (P->rows && part == 1) {                        // forward x3 + TD + backward-input, one CTA per 8 batch rows
+        if (P->rows_cpt == 2) dqn_rows_kernel<2><<<(unsigned)P->rows_grid, RT, P->rows_smem, s>>>(P->ra);
+        else dqn_rows_kernel<4><<<(unsigned)P->rows_grid, RT, P->rows_smem, s>>>(P->ra);
+        MB_LAUNCHED(1);
+        return MB_OK;
+    }
+    if (!P->rows && part == 2) return MB_OK;           // the cooperative program does everything in part 1
     void *args[] = {&P->d_ops, &P->n_ops, &P->n_phases};
-    MB_CUDA(cudaLaunchCooperativeKernel((const void *)mlp_program_kernel, dim3((unsigned)P->grid), dim3(NT), args, 0,
-                                        (cudaStream_t)stream));
+    MB_CUDA(cudaLaunchCooperativeKernel((const void *)mlp_program_kernel, dim3((unsigned)P->grid), dim3(NT), args, 0, s));
     mb::count_launch(1);
     return MB_OK;
 }
 
 int mb_mlp_program_run(mb_mlp_program *P, void *stream) {
-    const int r = mb_mlp_program_run_part(P, 0, stream);
-    return r != MB_OK ? r : mb_mlp_program_run_part(P, 1, stream);
+    for (int part = 0; part < 3; ++part) {
+        const int r = mb_mlp_program_run_part(P, part, stream);
+        if (r != MB_OK) return r;
+    }
+    return MB_OK;
 }
 
 int mb_mlp_program_destroy(mb_mlp_program *P) {

@@ -268,20 +268,32 @@ class DQNPer(TorchFramework):
     def _step_fused(self, st, update_value, update_target, uniform, use_device_params) -> t.Tensor:
         from ..._lib import lib, check, stream_ptr
         buf = self.replay_buffer
+        dev = buf.buffer_device
+        side = None
+        if self.overlap_priority_update:
+            if self._side_stream is None:
+                self._side_stream = t.cuda.Stream(device=dev)
+            side, cur = self._side_stream, t.cuda.current_stream(dev)
+            side.wait_stream(cur)
+            with t.cuda.stream(side), t.cuda.device(dev):                 # weight copies: beside the draw and the gather
+                check(lib.mb_mlp_program_run_part(st["handle"], 0, stream_ptr()))
+        else:
+            with t.cuda.device(dev):
+                check(lib.mb_mlp_program_run_part(st["handle"], 0, stream_ptr()))
         buf._draw(self.batch_size, uniform=uniform, use_device_params=use_device_params, out=(st["index"], st["isw"]))
         buf.storage.gather(st["index"], names=st["names"], out=st["fields"])
         forked = None
-        with t.cuda.device(buf.buffer_device):
-            check(lib.mb_mlp_program_run_part(st["handle"], 0, stream_ptr()))        # forward x3, TD, backward-input
-            if self.overlap_priority_update:
+        with t.cuda.device(dev):
+            if side is not None:
+                cur.wait_stream(side)
+            check(lib.mb_mlp_program_run_part(st["handle"], 1, stream_ptr()))        # forward x3, TD, backward-input
+            if side is not None:
                 # |delta| is ready: the write-back runs beside the weight gradients, the optimizer and the target update
-                if self._side_stream is None:
-                    self._side_stream = t.cuda.Stream(device=buf.buffer_device)
-                forked = (t.cuda.current_stream(buf.buffer_device), self._side_stream)
-                forked[1].wait_stream(forked[0])
-                with t.cuda.stream(forked[1]):
+                forked = (cur, side)
+                side.wait_stream(cur)
+                with t.cuda.stream(side):
                     buf.update_priority(st["abs"], st["index"])
-            check(lib.mb_mlp_program_run_part(st["handle"], 1, stream_ptr()))        # dW, db
+            check(lib.mb_mlp_program_run_part(st["handle"], 2, stream_ptr()))        # dW, db
         if forked is None:
             buf.update_priority(st["abs"], st["index"])
         if update_value:
