@@ -67,6 +67,8 @@ def parse():
                    "reference (measured: no gain, 0.204 vs 0.205 ms/update)")
     p.add_argument("--parallel-forwards", action="store_true",
                    help="N = 1, opt-in: the two no-grad forwards on side streams (parallel graph branches)")
+    p.add_argument("--fuse-optimizer", action="store_true",
+                   help="N = 1, opt-in: FusedAdam step and soft target update as one launch")
     p.add_argument("--overlap-update", action="store_true",
                    help="N = 1, opt-in: priority write-back on a parallel graph branch beside backward + optimizer")
     p.add_argument("--adam", default="fused", choices=["fused", "torch"], help="FusedAdam (csrc/mlp.cu) or torch.optim.Adam(fused=True)")
@@ -233,6 +235,7 @@ def build_learner(a, device, seed, world=1):
         learner.fuse_online_forwards = a.fuse_forwards
         learner.overlap_priority_update = a.overlap_update and world == 1
         learner.parallel_forwards = a.parallel_forwards and world == 1
+        learner.fuse_optimizer_and_target = a.fuse_optimizer and a.adam == "fused"
     gen = t.Generator(device=device).manual_seed(seed)
     chunk = 1_000_000
     done = 0

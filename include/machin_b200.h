@@ -288,6 +288,12 @@ int mb_mlp_program_destroy(mb_mlp_program *program);
 int mb_adam_step_multi(float *const *d_params, const float *const *d_grads, float *const *d_exp_avg,
                        float *const *d_exp_avg_sq, const int64_t *sizes, int n_tensors, float *d_step_count,
                        double lr, double beta1, double beta2, double eps, double weight_decay, void *stream);
+/* The same step followed, element by element, by the soft target update target = target * (1 - rate) + param * rate
+ * (utils.py:8-27) on the matching target-network tensors: one pass over the parameters, one launch less. */
+int mb_adam_soft_step_multi(float *const *d_params, const float *const *d_grads, float *const *d_exp_avg,
+                            float *const *d_exp_avg_sq, float *const *d_target_params, const int64_t *sizes,
+                            int n_tensors, float *d_step_count, double lr, double beta1, double beta2, double eps,
+                            double weight_decay, double update_rate, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Trajectory reverse scans

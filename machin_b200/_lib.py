@@ -96,6 +96,8 @@ SIGNATURES = {
     "mb_mlp_program_destroy": (i32, [vp]),
     "mb_adam_step_multi": (i32, [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i32, vp,
                                  f64, f64, f64, f64, f64, vp]),
+    "mb_adam_soft_step_multi": (i32, [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
+                                      C.POINTER(i64), i32, vp, f64, f64, f64, f64, f64, f64, vp]),
     "mb_vtrace": (i32, [vp, i64, i64, vp, vp, vp, vp, vp, vp, f32, f32, f32, vp, vp, vp, vp, vp]),
     "mb_vtrace_len": (i32, [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, f32, f32, f32, vp, vp, vp, vp, vp]),
     "mb_gae": (i32, [vp, i64, i64, vp, vp, vp, vp, f64, f64, vp, vp, vp]),

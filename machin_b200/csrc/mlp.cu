@@ -337,6 +337,8 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamList l, float lr, float b
 
 __global__ void adam_step_inc(float *step_count) { *step_count += 1.0f; }
 
+#include "optim_device.cuh"   // adam_soft_kernel: the Adam step and the soft target update in one launch
+
 }  // namespace
 
 extern "C" {
@@ -657,6 +659,39 @@ int mb_mlp_program_destroy(mb_mlp_program *P) {
     mb::DeviceGuard guard(P->device);
     for (void *p : P->owned) cudaFree(p);
     delete P;
+    return MB_OK;
+}
+
+int mb_adam_soft_step_multi(float *const *d_params, const float *const *d_grads, float *const *d_exp_avg,
+                            float *const *d_exp_avg_sq, float *const *d_target_params, const int64_t *sizes,
+                            int n_tensors, float *d_step_count, double lr, double beta1, double beta2, double eps,
+                            double weight_decay, double update_rate, void *stream) {
+    if (n_tensors < 0 || !d_step_count || (n_tensors > 0 && (!d_params || !d_grads || !d_exp_avg || !d_exp_avg_sq ||
+                                                              !d_target_params || !sizes)))
+        return MB_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int base = 0; base < n_tensors; base += MB_MAX_SOFT_TENSORS) {
+        AdamSoftList l;
+        l.n = n_tensors - base < MB_MAX_SOFT_TENSORS ? n_tensors - base : MB_MAX_SOFT_TENSORS;
+        l.start[0] = 0;
+        for (int k = 0; k < l.n; ++k) {
+            l.p[k] = d_params[base + k]; l.g[k] = d_grads[base + k];
+            l.m[k] = d_exp_avg[base + k]; l.v[k] = d_exp_avg_sq[base + k];
+            l.t[k] = d_target_params[base + k];
+            l.start[k + 1] = l.start[k] + sizes[base + k];
+        }
+        const int64_t total = l.start[l.n];
+        if (total == 0) continue;
+        int64_t blocks = (total + 255) / 256;
+        if (blocks > (int64_t)mb::kNumSMs * 8) blocks = (int64_t)mb::kNumSMs * 8;
+        // python: target * (1.0 - update_rate) + param * update_rate ; both scalars become float32 (csrc/td.cu)
+        adam_soft_kernel<<<(unsigned)blocks, 256, 0, s>>>(l, (float)lr, (float)beta1, (float)beta2, (float)eps,
+                                                          (float)weight_decay, d_step_count, (float)(1.0 - update_rate),
+                                                          (float)update_rate);
+        mb::count_launch(1);
+    }
+    adam_step_inc<<<1, 1, 0, s>>>(d_step_count);
+    MB_LAUNCHED(1);
     return MB_OK;
 }
 

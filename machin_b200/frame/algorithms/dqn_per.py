@@ -88,6 +88,8 @@ class DQNPer(TorchFramework):
         # is a chain of sub-10-us kernels; run the two no-grad ones on side streams (parallel graph branches)
         self.parallel_forwards = False
         self._fwd_streams = None
+        # opt-in: FusedAdam's step and the soft target update as ONE launch (one pass over the parameters)
+        self.fuse_optimizer_and_target = False
         super().__init__()
 
     # ------------------------------------------------------------------ properties / acting (dqn.py:213-331)
@@ -298,16 +300,7 @@ class DQNPer(TorchFramework):
             buf.update_priority(st["abs"], st["index"])
         if update_value:
             self._sync_grads()
-            if np.isfinite(self.grad_max):
-                nn.utils.clip_grad_norm_(self.qnet.parameters(), self.grad_max)
-            self.qnet_optim.step()
-        if update_target:
-            if self.update_rate is not None:
-                soft_update(self.qnet_target, self.qnet, self.update_rate)
-            else:
-                self._update_counter += 1
-                if self._update_counter % self.update_steps == 0:
-                    hard_update(self.qnet_target, self.qnet)
+        self._optimizer_and_target(update_value, update_target)
         if forked is not None:
             forked[0].wait_stream(forked[1])     # join before the next draw reads the tree
         return st["loss"].mean()
@@ -369,6 +362,10 @@ class DQNPer(TorchFramework):
             else:
                 self._backward(value_loss)
             self._sync_grads()
+        if self.fuse_optimizer_and_target:
+            self._optimizer_and_target(update_value, update_target)      # FusedAdam + soft update as one launch when possible
+            update_value = update_target = False
+        if update_value:
             if np.isfinite(self.grad_max):   # with max_norm = inf the reference's clip multiplies by exactly 1.0
                 nn.utils.clip_grad_norm_(self.qnet.parameters(), self.grad_max)
             self.qnet_optim.step()
@@ -383,6 +380,26 @@ class DQNPer(TorchFramework):
             forked[0].wait_stream(forked[1])     # join before the next draw reads the tree (td / d_index still alive here)
         self.qnet.eval()
         return value_loss
+
+    def _optimizer_and_target(self, update_value, update_target):
+        """optimizer step + target-network update of one learner update (dqn_per.py:141-160)."""
+        from ...model import FusedAdam
+        if (self.fuse_optimizer_and_target and update_value and update_target and self.update_rate is not None
+                and isinstance(self.qnet_optim, FusedAdam) and not np.isfinite(self.grad_max)):
+            pairs = {id(p): tp for p, tp in zip(self.qnet.parameters(), self.qnet_target.parameters())}
+            self.qnet_optim.step_with_soft_update(pairs, self.update_rate)
+            return
+        if update_value:
+            if np.isfinite(self.grad_max):   # with max_norm = inf the reference's clip multiplies by exactly 1.0
+                nn.utils.clip_grad_norm_(self.qnet.parameters(), self.grad_max)
+            self.qnet_optim.step()
+        if update_target:
+            if self.update_rate is not None:
+                soft_update(self.qnet_target, self.qnet, self.update_rate)
+            else:
+                self._update_counter += 1
+                if self._update_counter % self.update_steps == 0:
+                    hard_update(self.qnet_target, self.qnet)
 
     def _sync_grads(self):
         """Hook: gradient averaging across learner processes (see DQNApex)."""

@@ -104,7 +104,14 @@ class FusedAdam(t.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
 
     @t.no_grad()
-    def step(self, closure=None):
+    def step_with_soft_update(self, target_of, update_rate: float):
+        """One Adam step and, in the same launch, ``target = target * (1 - rate) + param * rate`` on the matching
+        target-network parameters (``target_of``: dict id(param) -> target parameter).  Every parameter with a
+        gradient must have a target; parameters are float32 CUDA tensors."""
+        return self.step(_target_of=target_of, _update_rate=update_rate)
+
+    @t.no_grad()
+    def step(self, closure=None, _target_of=None, _update_rate=0.0):
         for group in self.param_groups:
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
@@ -121,6 +128,14 @@ class FusedAdam(t.optim.Optimizer):
             arr = lambda xs: (C.c_void_p * n)(*[x.data_ptr() for x in xs])
             sizes = (C.c_int64 * n)(*[p.numel() for p in ps])
             b1, b2 = group["betas"]
+            if _target_of is not None:
+                with t.cuda.device(ps[0].device):
+                    _lib.check(lib.mb_adam_soft_step_multi(
+                        arr(ps), arr([p.grad for p in ps]), arr([self.state[p]["exp_avg"] for p in ps]),
+                        arr([self.state[p]["exp_avg_sq"] for p in ps]), arr([_target_of[id(p)] for p in ps]), sizes, n,
+                        _lib.ptr(first["step"]), float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                        float(group["weight_decay"]), float(_update_rate), _lib.stream_ptr()))
+                continue
             with t.cuda.device(ps[0].device):
                 _lib.check(lib.mb_adam_step_multi(arr(ps), arr([p.grad for p in ps]),
                                                   arr([self.state[p]["exp_avg"] for p in ps]),

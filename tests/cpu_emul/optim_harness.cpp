@@ -1,0 +1,25 @@
+// TEST INFRASTRUCTURE ONLY -- compiles machin_b200/csrc/optim_device.cuh (Adam step + soft target update in one
+// launch) for the host through cuda_shim.h.
+#include "cuda_shim.h"
+
+inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+
+#include "optim_device.cuh"
+
+extern "C" int emul_adam_soft(float *const *p, const float *const *g, float *const *m, float *const *v, float *const *tgt,
+                              const int64_t *sizes, int n, float *step, float lr, float b1, float b2, float eps, float wd,
+                              double rate) {
+    AdamSoftList l{};
+    l.n = n;
+    l.start[0] = 0;
+    for (int k = 0; k < n; ++k) {
+        l.p[k] = p[k]; l.g[k] = g[k]; l.m[k] = m[k]; l.v[k] = v[k]; l.t[k] = tgt[k];
+        l.start[k + 1] = l.start[k] + sizes[k];
+    }
+    const int64_t total = l.start[n];
+    shim_launch((unsigned)((total + 255) / 256 > 3 ? 3 : (total + 255) / 256), 256, [&] {      // grid-stride: fewer CTAs than work
+        adam_soft_kernel(l, lr, b1, b2, eps, wd, step, (float)(1.0 - rate), (float)rate);
+    });
+    *step += 1.0f;                                       // adam_step_inc
+    return 0;
+}

@@ -23,8 +23,8 @@ def _flat(m):
     return t.cat([p.detach().reshape(-1) for p in m.parameters()]).cpu().numpy()
 
 
-@pytest.mark.parametrize("flags", [("overlap_priority_update",), ("parallel_forwards",),
-                                   ("overlap_priority_update", "parallel_forwards")])
+@pytest.mark.parametrize("flags", [("overlap_priority_update",), ("parallel_forwards",), ("fuse_optimizer_and_target",),
+                                   ("overlap_priority_update", "parallel_forwards", "fuse_optimizer_and_target")])
 @pytest.mark.parametrize("graph", [False, True])
 def test_stream_parallel_update_same_trajectory(graph, flags):
     from machin_b200.frame.algorithms import DQNPer

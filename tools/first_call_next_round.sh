@@ -31,8 +31,9 @@ run all                "MB_SORTED_CLUSTER=1"  "--overlap-update --parallel-forwa
 run fused_autograd     "MB_X=0"               "--net fused"
 run fused_rows         "MB_X=0"               "--net fused-rows"
 run fused_rows_cpt2    "MB_ROWS_CPT=2"        "--net fused-rows"
+run fuse_optimizer     "MB_X=0"               "--fuse-optimizer"
 run fused_rows_overlap "MB_X=0"               "--net fused-rows --overlap-update"
-run fused_rows_all     "MB_SORTED_CLUSTER=1 MB_SORTED_ASYNC=1"  "--net fused-rows --overlap-update"
+run fused_rows_all     "MB_SORTED_CLUSTER=1 MB_SORTED_ASYNC=1"  "--net fused-rows --overlap-update --fuse-optimizer"
 for v in "MB_X=0" "MB_SORTED_CLUSTER=1" "MB_SORTED_ASYNC=1" "MB_SORTED_CLUSTER=1 MB_SORTED_ASYNC=1"; do
     env $v timeout 120 python tools/ub_sorted_update.py 2>/dev/null | tee -a gpurun_out/next_sorted_update.jsonl
 done
