@@ -289,11 +289,13 @@ int mb_adam_step_multi(float *const *d_params, const float *const *d_grads, floa
                        float *const *d_exp_avg_sq, const int64_t *sizes, int n_tensors, float *d_step_count,
                        double lr, double beta1, double beta2, double eps, double weight_decay, void *stream);
 /* The same step followed, element by element, by the soft target update target = target * (1 - rate) + param * rate
- * (utils.py:8-27) on the matching target-network tensors: one pass over the parameters, one launch less. */
+ * (utils.py:8-27) on the matching target-network tensors: one pass over the parameters, and the step counter is
+ * advanced by the kernel itself (d_ticket: one zero-initialised unsigned of device memory) -- two launches less.
+ * At most MB_MAX_SOFT_TENSORS tensors per call. */
 int mb_adam_soft_step_multi(float *const *d_params, const float *const *d_grads, float *const *d_exp_avg,
                             float *const *d_exp_avg_sq, float *const *d_target_params, const int64_t *sizes,
-                            int n_tensors, float *d_step_count, double lr, double beta1, double beta2, double eps,
-                            double weight_decay, double update_rate, void *stream);
+                            int n_tensors, float *d_step_count, unsigned *d_ticket, double lr, double beta1,
+                            double beta2, double eps, double weight_decay, double update_rate, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Trajectory reverse scans

@@ -28,6 +28,7 @@ MB_ERR_NOMEM = -6
 MB_ERR_NO_DEVICE = -7
 MB_F32, MB_F64 = 0, 1
 MB_MAX_FIELDS = 16
+MB_MAX_SOFT_TENSORS = 24          # include/machin_b200.h
 
 i64, i32, f64, f32, vp = C.c_int64, C.c_int, C.c_double, C.c_float, C.c_void_p
 
@@ -97,7 +98,7 @@ SIGNATURES = {
     "mb_adam_step_multi": (i32, [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i32, vp,
                                  f64, f64, f64, f64, f64, vp]),
     "mb_adam_soft_step_multi": (i32, [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
-                                      C.POINTER(i64), i32, vp, f64, f64, f64, f64, f64, f64, vp]),
+                                      C.POINTER(i64), i32, vp, vp, f64, f64, f64, f64, f64, f64, vp]),
     "mb_vtrace": (i32, [vp, i64, i64, vp, vp, vp, vp, vp, vp, f32, f32, f32, vp, vp, vp, vp, vp]),
     "mb_vtrace_len": (i32, [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, f32, f32, f32, vp, vp, vp, vp, vp]),
     "mb_gae": (i32, [vp, i64, i64, vp, vp, vp, vp, f64, f64, vp, vp, vp]),

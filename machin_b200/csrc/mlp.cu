@@ -664,9 +664,9 @@ int mb_mlp_program_destroy(mb_mlp_program *P) {
 
 int mb_adam_soft_step_multi(float *const *d_params, const float *const *d_grads, float *const *d_exp_avg,
                             float *const *d_exp_avg_sq, float *const *d_target_params, const int64_t *sizes,
-                            int n_tensors, float *d_step_count, double lr, double beta1, double beta2, double eps,
-                            double weight_decay, double update_rate, void *stream) {
-    if (n_tensors < 0 || !d_step_count || (n_tensors > 0 && (!d_params || !d_grads || !d_exp_avg || !d_exp_avg_sq ||
+                            int n_tensors, float *d_step_count, unsigned *d_ticket, double lr, double beta1, double beta2,
+                            double eps, double weight_decay, double update_rate, void *stream) {
+    if (n_tensors < 0 || n_tensors > MB_MAX_SOFT_TENSORS || !d_step_count || !d_ticket || (n_tensors > 0 && (!d_params || !d_grads || !d_exp_avg || !d_exp_avg_sq ||
                                                               !d_target_params || !sizes)))
         return MB_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
@@ -686,12 +686,10 @@ int mb_adam_soft_step_multi(float *const *d_params, const float *const *d_grads,
         if (blocks > (int64_t)mb::kNumSMs * 8) blocks = (int64_t)mb::kNumSMs * 8;
         // python: target * (1.0 - update_rate) + param * update_rate ; both scalars become float32 (csrc/td.cu)
         adam_soft_kernel<<<(unsigned)blocks, 256, 0, s>>>(l, (float)lr, (float)beta1, (float)beta2, (float)eps,
-                                                          (float)weight_decay, d_step_count, (float)(1.0 - update_rate),
-                                                          (float)update_rate);
-        mb::count_launch(1);
+                                                          (float)weight_decay, d_step_count, d_ticket,
+                                                          (float)(1.0 - update_rate), (float)update_rate);
+        MB_LAUNCHED(1);                                   // (one chunk: the kernel advances the step counter itself)
     }
-    adam_step_inc<<<1, 1, 0, s>>>(d_step_count);
-    MB_LAUNCHED(1);
     return MB_OK;
 }
 

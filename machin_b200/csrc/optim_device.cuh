@@ -4,7 +4,9 @@
 // torch.optim.Adam (amsgrad off, maximize off) element by element exactly like adam_kernel in mlp.cu, then -- the
 // updated parameter still in a register -- utils.py:8-27's target = target * (1 - rate) + param * rate with the
 // two scalars rounded to float32 first, like soft_update_multi_kernel in td.cu.  Saves the second pass over the
-// parameters and one launch per learner update.
+// parameters and one launch per learner update.  The step counter is advanced by the kernel itself: every CTA reads
+// it first, and the CTA that finishes LAST (an atomic ticket) writes t + 1 -- no CTA can still need the old value
+// then -- so the separate one-thread increment launch of mb_adam_step_multi is not needed either.
 #pragma once
 #include <stdint.h>
 
@@ -21,7 +23,7 @@ struct AdamSoftList {
 };
 
 __global__ void __launch_bounds__(256) adam_soft_kernel(AdamSoftList l, float lr, float beta1, float beta2, float eps,
-                                                        float weight_decay, const float *step_count, float keep,
+                                                        float weight_decay, float *step_count, unsigned *done, float keep,
                                                         float rate) {
     const int64_t total = l.start[l.n];
     const float t = *step_count + 1.0f;
@@ -42,5 +44,13 @@ __global__ void __launch_bounds__(256) adam_soft_kernel(AdamSoftList l, float lr
         const float p_new = __fsub_rn(p, __fmul_rn(step_size, __fdiv_rn(m, denom)));
         l.p[k][j] = p_new;
         l.t[k][j] = __fadd_rn(__fmul_rn(l.t[k][j], keep), __fmul_rn(p_new, rate));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(done, 1u) == gridDim.x - 1) {     // every CTA has read *step_count by now
+            *done = 0;
+            *step_count = t;
+        }
     }
 }

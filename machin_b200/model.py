@@ -128,13 +128,15 @@ class FusedAdam(t.optim.Optimizer):
             arr = lambda xs: (C.c_void_p * n)(*[x.data_ptr() for x in xs])
             sizes = (C.c_int64 * n)(*[p.numel() for p in ps])
             b1, b2 = group["betas"]
-            if _target_of is not None:
+            if _target_of is not None and n <= _lib.MB_MAX_SOFT_TENSORS:
+                if "ticket" not in first:
+                    first["ticket"] = t.zeros(1, dtype=t.int32, device=ps[0].device)
                 with t.cuda.device(ps[0].device):
                     _lib.check(lib.mb_adam_soft_step_multi(
                         arr(ps), arr([p.grad for p in ps]), arr([self.state[p]["exp_avg"] for p in ps]),
                         arr([self.state[p]["exp_avg_sq"] for p in ps]), arr([_target_of[id(p)] for p in ps]), sizes, n,
-                        _lib.ptr(first["step"]), float(group["lr"]), float(b1), float(b2), float(group["eps"]),
-                        float(group["weight_decay"]), float(_update_rate), _lib.stream_ptr()))
+                        _lib.ptr(first["step"]), _lib.ptr(first["ticket"]), float(group["lr"]), float(b1), float(b2),
+                        float(group["eps"]), float(group["weight_decay"]), float(_update_rate), _lib.stream_ptr()))
                 continue
             with t.cuda.device(ps[0].device):
                 _lib.check(lib.mb_adam_step_multi(arr(ps), arr([p.grad for p in ps]),

@@ -3,6 +3,8 @@
 #include "cuda_shim.h"
 
 inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline unsigned atomicAdd(unsigned *a, unsigned v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
 
 #include "optim_device.cuh"
 
@@ -17,9 +19,9 @@ extern "C" int emul_adam_soft(float *const *p, const float *const *g, float *con
         l.start[k + 1] = l.start[k] + sizes[k];
     }
     const int64_t total = l.start[n];
+    static unsigned ticket = 0;                          // zero between launches: the last CTA resets it
     shim_launch((unsigned)((total + 255) / 256 > 3 ? 3 : (total + 255) / 256), 256, [&] {      // grid-stride: fewer CTAs than work
-        adam_soft_kernel(l, lr, b1, b2, eps, wd, step, (float)(1.0 - rate), (float)rate);
+        adam_soft_kernel(l, lr, b1, b2, eps, wd, step, &ticket, (float)(1.0 - rate), (float)rate);
     });
-    *step += 1.0f;                                       // adam_step_inc
-    return 0;
+    return ticket == 0 ? 0 : 7;                          // (the kernel advanced *step itself)
 }

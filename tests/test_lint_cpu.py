@@ -11,3 +11,24 @@ def test_no_undefined_names():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "lint_names.py")], cwd=ROOT,
                          capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_every_referenced_library_symbol_exists():
+    """Every entry point called on `lib` and every attribute read from the `_lib` module anywhere in the Python sources
+    must exist in the ctypes shim: the code paths that use them only run on a GPU box, an AttributeError there
+    costs a paid-for run."""
+    import glob
+    import re
+    from machin_b200 import _lib
+    files = [f for pat in ("machin_b200/**/*.py", "tools/*.py", "tests/*.py", "bench.py", "__graft_entry__.py")
+             for f in glob.glob(os.path.join(ROOT, pat), recursive=True)]
+    missing = []
+    for f in files:
+        src = open(f).read()
+        for name in set(re.findall(r"\blib\.(mb_[a-z0-9_]+)", src)):
+            if name not in _lib.SIGNATURES:
+                missing.append((os.path.relpath(f, ROOT), "lib." + name))
+        for name in set(re.findall(r"\b_lib\.([A-Za-z_][A-Za-z0-9_]*)", src)):
+            if not hasattr(_lib, name):
+                missing.append((os.path.relpath(f, ROOT), "_lib." + name))
+    assert not missing, missing
