@@ -1,11 +1,14 @@
 #!/bin/bash
-# First GPU call of the next round (one GPU, ~12 minutes): everything written after round 1's GPU budget ran
+# First GPU call of the next round (one GPU, ~25 minutes): everything written after round 1's GPU budget ran
 # out -- run the pending tests, then A/B the opt-in variants against the default on the bench workload.
-#   gpurun --timeout 1200 -- 'bash tools/first_call_next_round.sh'
+#   gpurun --timeout 2400 -- 'bash tools/first_call_next_round.sh'
 # Results land in gpurun_out/next_*.  Nothing here changes clocks or kills by pattern.
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -rxXs -p no:cacheprovider > gpurun_out/next_pytest.txt 2>&1
+timeout 1200 python -m pytest tests -m gpu -q -rxXs -p no:cacheprovider > gpurun_out/next_pytest.txt 2>&1
 tail -25 gpurun_out/next_pytest.txt
+for v in "MB_X=0" "MB_SORTED_CLUSTER=1" "MB_SORTED_ASYNC=1" "MB_SORTED_CLUSTER=1 MB_SORTED_ASYNC=1"; do
+    env $v timeout 120 python tools/ub_sorted_update.py 2>/dev/null | tee -a gpurun_out/next_sorted_update.jsonl
+done
 run() {   # name, env, flags
     env $2 timeout 240 python bench.py --steps 3000 --warmup 50 --no-cpu-baseline $3 \
         > gpurun_out/next_bench_$1.json 2> gpurun_out/next_bench_$1.err
@@ -34,6 +37,3 @@ run fused_rows_cpt2    "MB_ROWS_CPT=2"        "--net fused-rows"
 run fuse_optimizer     "MB_X=0"               "--fuse-optimizer"
 run fused_rows_overlap "MB_X=0"               "--net fused-rows --overlap-update"
 run fused_rows_all     "MB_SORTED_CLUSTER=1 MB_SORTED_ASYNC=1"  "--net fused-rows --overlap-update --fuse-optimizer"
-for v in "MB_X=0" "MB_SORTED_CLUSTER=1" "MB_SORTED_ASYNC=1" "MB_SORTED_CLUSTER=1 MB_SORTED_ASYNC=1"; do
-    env $v timeout 120 python tools/ub_sorted_update.py 2>/dev/null | tee -a gpurun_out/next_sorted_update.jsonl
-done
