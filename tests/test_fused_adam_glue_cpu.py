@@ -55,3 +55,45 @@ def test_fused_adam_calls(monkeypatch):
     ps[1].grad = None
     opt.step()
     assert rec.calls[-1][1][5] == 1
+
+
+def test_fused_program_creation_arguments(monkeypatch):
+    """DQNPer._fused_program(): the argument order handed to mb_dqn_mlp_rows_create / mb_dqn_mlp_program_create must be
+    the C prototype's (include/machin_b200.h): device, n_layers, sizes, batch, params, target params, grads, state,
+    next_state, action, reward, terminal, is_weight, discount, mode, y, action_value, abs_error, loss_elem, out."""
+    import contextlib
+    import numpy as np
+    import machin_b200._lib as lib_mod
+    from fake_ring import FakeTree, make_cpu_buffer
+    from machin_b200.frame.algorithms import DQNPer
+    from machin_b200.frame.buffers import PrioritizedBuffer
+    rec = _Recorder()
+    monkeypatch.setattr(lib_mod, "lib", rec)
+    monkeypatch.setattr(t.cuda, "device", lambda d: contextlib.nullcontext())
+    sizes, B = [6, 16, 16, 4], 32
+    q, qt = model_mod.FusedMLP(sizes), model_mod.FusedMLP(sizes)
+    buf = make_cpu_buffer(PrioritizedBuffer, 200, epsilon=1e-2, alpha=0.6, beta=0.4, curr_beta=0.4,
+                          beta_increment_per_sampling=1e-3, wt_tree=FakeTree(200))
+    dqn = DQNPer(q, qt, t.optim.SGD, t.nn.MSELoss(reduction="none"), batch_size=B, discount=0.9, update_rate=0.1,
+                 replay_buffer=buf)
+    buf.store_episode([dict(state={"state": t.zeros(1, 6)}, action={"action": t.tensor([[1]])},
+                            next_state={"state": t.zeros(1, 6)}, reward=0.5, terminal=False) for _ in range(5)],
+                      priorities=list(np.ones(5)))
+    for kind, entry in (("rows", "mb_dqn_mlp_rows_create"), ("program", "mb_dqn_mlp_program_create")):
+        dqn.use_fused_program, dqn.fused_kind, dqn._program = True, kind, None
+        st = dqn._fused_program()
+        assert st, "the program was not built"
+        name, a = [c for c in rec.calls if c[0].startswith("mb_dqn_mlp")][-1]
+        assert name == entry and len(a) == 20
+        assert a[1] == 3 and list(a[2]) == sizes and a[3] == B
+        plist = lambda net: [p for layer in net.layers for p in (layer.weight, layer.bias)]
+        assert _vals(a[4], 6) == [p.data_ptr() for p in plist(dqn.qnet)]
+        assert _vals(a[5], 6) == [p.data_ptr() for p in plist(dqn.qnet_target)]
+        assert _vals(a[6], 6) == [p.grad.data_ptr() for p in plist(dqn.qnet)]
+        f = st["fields"]
+        want = [f["state/state"], f["next_state/state"], f["action/action"], f["reward"], f["terminal"], st["isw"]]
+        assert [x.value for x in a[7:13]] == [w.data_ptr() for w in want]
+        assert (f["state/state"].shape, f["action/action"].dtype, f["terminal"].dtype) == ((B, 6), t.int64, t.bool)
+        assert abs(a[13] - 0.9) < 1e-12 and a[14] == 0                      # discount, mode 0 = double DQN
+        assert [x.value for x in a[15:19]] == [st[k].data_ptr() for k in ("y", "av", "abs", "loss")]
+        assert (st["y"].dtype, st["abs"].shape, st["loss"].dtype) == (t.float32, (B,), t.float64)
