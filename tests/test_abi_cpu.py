@@ -167,3 +167,47 @@ def test_entry_points_reject_bad_arguments_before_touching_the_device():
                             (_lib.MB_ERR_SIZE_MISMATCH, "Weights size must match tree size!")):
         with pytest.raises(ValueError, match=message):          # the reference's own messages
             _lib.check(status)
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Argument count and argument classes (pointer / int / int64 / float / double) of every ctypes signature in
+    machin_b200/_lib.py against the prototype in include/machin_b200.h: ctypes converts silently, a swapped or missing
+    argument would only show up as garbage on the device."""
+    import ctypes as C
+    import re
+    from machin_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "machin_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = dict(re.findall(r"\b(?:int|long long|const char \*|const double \*|double \*|void \*|int64_t)\s*(mb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;",
+                             header, flags=re.S))
+
+    def c_class(arg):
+        arg = " ".join(arg.split())
+        if arg in ("void", ""):
+            return None
+        if "*" in arg:
+            return "ptr"
+        if re.search(r"\bint64_t\b", arg):
+            return "i64"
+        if re.search(r"\bdouble\b", arg):
+            return "f64"
+        if re.search(r"\bfloat\b", arg):
+            return "f32"
+        if re.search(r"\b(int|unsigned|mb_dtype)\b", arg):
+            return "i32"
+        raise AssertionError(f"unclassified C argument: {arg!r}")
+
+    def py_class(tp):
+        if tp in (C.c_void_p, C.c_char_p) or (isinstance(tp, type) and issubclass(tp, C._Pointer)):
+            return "ptr"
+        return {C.c_int64: "i64", C.c_double: "f64", C.c_float: "f32", C.c_int: "i32", C.c_int32: "i32"}[tp]
+
+    assert len(protos) >= 40
+    bad = []
+    for name, (_res, args) in _lib.SIGNATURES.items():
+        assert name in protos, name
+        want = [c for c in (c_class(a) for a in protos[name].split(",")) if c is not None]
+        got = [py_class(a) for a in args]
+        if want != got:
+            bad.append((name, want, got))
+    assert not bad, bad
