@@ -9,11 +9,21 @@ import machin_b200.model as model_mod
 
 
 class _Recorder:
+    """Stands in for the ctypes library object: records every call and converts the arguments the way ctypes would
+    (``argtype.from_param``), so a None where an int is declared, a float for an int64, a wrong argument count ...
+    raise here exactly like they would in front of the real library."""
+
     def __init__(self):
         self.calls = []
 
     def __getattr__(self, name):
+        from machin_b200._lib import SIGNATURES
+        _res, argtypes = SIGNATURES[name]
+
         def call(*args):
+            assert len(args) == len(argtypes), (name, len(args), len(argtypes))
+            for a, tp in zip(args, argtypes):
+                tp.from_param(a)
             self.calls.append((name, args))
             return 0
         return call
@@ -74,6 +84,7 @@ def test_fused_program_creation_arguments(monkeypatch):
     q, qt = model_mod.FusedMLP(sizes), model_mod.FusedMLP(sizes)
     buf = make_cpu_buffer(PrioritizedBuffer, 200, epsilon=1e-2, alpha=0.6, beta=0.4, curr_beta=0.4,
                           beta_increment_per_sampling=1e-3, wt_tree=FakeTree(200))
+    buf.buffer_device = t.device("cpu", 0)               # (a device WITH an index, like "cuda:0")
     dqn = DQNPer(q, qt, t.optim.SGD, t.nn.MSELoss(reduction="none"), batch_size=B, discount=0.9, update_rate=0.1,
                  replay_buffer=buf)
     buf.store_episode([dict(state={"state": t.zeros(1, 6)}, action={"action": t.tensor([[1]])},
@@ -97,3 +108,33 @@ def test_fused_program_creation_arguments(monkeypatch):
         assert abs(a[13] - 0.9) < 1e-12 and a[14] == 0                      # discount, mode 0 = double DQN
         assert [x.value for x in a[15:19]] == [st[k].data_ptr() for k in ("y", "av", "abs", "loss")]
         assert (st["y"].dtype, st["abs"].shape, st["loss"].dtype) == (t.float32, (B,), t.float64)
+
+
+def test_ops_call_sites_convert_like_ctypes(monkeypatch):
+    """machin_b200.ops wrappers: argument count / types of the calls into the library (typed recorder), incl. the
+    entry points that take the longest episode length."""
+    import contextlib
+    import machin_b200.ops as ops
+    rec = _Recorder()
+    monkeypatch.setattr(ops, "lib", rec)
+    monkeypatch.setattr(t.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(ops._lib, "stream_ptr", lambda stream=None: C.c_void_p(0))
+    monkeypatch.setattr(ops, "_c", lambda x, dtype=None: None if x is None else (x if dtype is None else x.to(dtype)).contiguous())
+    n = 12
+    f = lambda: t.randn(n, 1)
+    term = t.zeros(n, 1, dtype=t.bool)
+    off = t.tensor([0, 5, 12])
+    out = ops.vtrace(f(), f(), f(), term, -t.rand(n, 1), -t.rand(n, 1), 0.99, 1.0, 1.0, offsets=off, max_len=7)
+    name, a = rec.calls[-1]
+    assert name == "mb_vtrace_len" and a[1:4] == (2, n, 7) and set(out) == {"vs", "vss", "rho", "adv"}
+    ops.vtrace(f(), f(), f(), term, f(), f(), 0.99, n_episodes=3)
+    assert rec.calls[-1][1][0].value in (None, 0) and rec.calls[-1][1][1:4] == (3, n, 0)
+    out = ops.gae(t.randn(n, dtype=t.float64), term.view(-1), t.randn(n), t.randn(n), 0.97, 0.95, n_episodes=1)
+    name, a = rec.calls[-1]
+    assert name == "mb_gae_len" and a[1:4] == (1, n, 0) and a[8:10] == (0.97, 0.95) and set(out) == {"returns", "gae"}
+    td = ops.td_dqn(t.randn(n, 4), t.randn(n, 4), t.randn(n, 4), t.zeros(n, 1, dtype=t.int64), f(), term, 0.9,
+                    is_weight=t.rand(n, dtype=t.float64), want_grad=True)
+    name, a = rec.calls[-1]
+    assert name == "mb_td_dqn" and a[3:5] == (n, 4) and td["grad_q"].shape == (n, 4)
+    ops.td_target(f(), f(), term, 0.9, value=f())
+    assert rec.calls[-1][0] == "mb_td_target"
