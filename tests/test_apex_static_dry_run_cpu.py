@@ -1,0 +1,131 @@
+"""CPU: a DRY RUN of DQNApex's fixed-shape update (frame/algorithms/apex.py: _enable_static_graph, its body(), the
+host preparation and update_device) -- every Python line executes, CUDA streams / graphs / pinned memory are no-op
+stand-ins, the ring and tree are host-memory doubles, and the library is a recorder that converts every argument
+the way ctypes would and checks it against the declared signature.  No numbers are checked (the kernels do not
+run): this catches what a GPU box would otherwise be the first to see -- a wrong argument count or type, a
+missing attribute, a shape error -- in the default N > 1 path and its opt-in variants (device apportioning, one-launch
+draw, fused value-math program)."""
+import contextlib
+import ctypes as C
+from threading import RLock
+
+import numpy as np
+import pytest
+import torch as t
+
+from fake_ring import FakeRing, FakeTree, make_cpu_buffer
+from test_library_call_sites_cpu import _Recorder
+
+
+class _Stream:
+    def wait_stream(self, other):
+        pass
+
+
+class _Event:
+    def synchronize(self):
+        pass
+
+    def record(self):
+        pass
+
+
+class _Graph:
+    def replay(self):
+        pass
+
+
+class _Tree(FakeTree):
+    handle = C.c_void_p(1)
+
+    def snapshot(self):
+        return self.ora.weights.copy(), self.ora.max_leaf
+
+    def restore(self, snap):
+        self.ora.weights[:] = snap[0]
+        self.ora.max_leaf = snap[1]
+
+
+class _Ring(FakeRing):
+    def gather_into_wire(self, index, wire, stream=None):
+        wire[:, :self.pitch] = self.data[index.clamp(0, self.max_size - 1)]
+
+
+@pytest.mark.parametrize("variant", ["default", "device_apportion+batched_draw", "fused_rows", "fused_program"])
+def test_fixed_shape_update_dry_run(variant, monkeypatch):
+    import machin_b200._lib as lib_mod
+    import machin_b200.frame.algorithms.apex as apex_mod
+    import machin_b200.frame.algorithms.dqn_per as dqn_mod
+    import machin_b200.frame.buffers.prioritized_buffer as per_mod
+    import machin_b200.model as model_mod
+    import machin_b200.ops as ops
+    from machin_b200.frame.buffers import DistributedPrioritizedBuffer
+    from machin_b200.parallel import LocalGroup
+    rec = _Recorder()
+    for mod in (lib_mod, ops, per_mod, model_mod):
+        monkeypatch.setattr(mod, "lib", rec)
+    monkeypatch.setattr(lib_mod, "stream_ptr", lambda stream=None: C.c_void_p(0))
+    monkeypatch.setattr(ops, "_c", lambda x, dtype=None: None if x is None else (x if dtype is None else x.to(dtype)).contiguous())
+    monkeypatch.setattr(t.Tensor, "pin_memory", lambda self: self)
+    monkeypatch.setattr(t.Tensor, "is_cuda", property(lambda self: True))          # "device" tensors of the dry run
+    monkeypatch.setattr(t.cuda, "Event", _Event)
+    monkeypatch.setattr(t.cuda, "Stream", lambda device=None: _Stream())
+    monkeypatch.setattr(t.cuda, "current_stream", lambda device=None: _Stream())
+    monkeypatch.setattr(t.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(t.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(t.cuda, "synchronize", lambda device=None: None)
+    monkeypatch.setattr(t.cuda, "CUDAGraph", _Graph)
+    monkeypatch.setattr(t.cuda, "graph", lambda g, **kw: contextlib.nullcontext())
+    dev = t.device("cpu", 0)
+
+    def buffer_double(buffer_name, group, buffer_size, requesters=None, **kw):
+        buf = make_cpu_buffer(DistributedPrioritizedBuffer, buffer_size, epsilon=1e-2, alpha=0.6, beta=0.4, curr_beta=0.4,
+                              beta_increment_per_sampling=1e-3, wt_tree=_Tree(buffer_size), buffer_name=buffer_name, group=group,
+                              wr_lock=RLock(), _requesters=requesters, _sampler=None,
+                              buffer_version_table=t.zeros(buffer_size, dtype=t.int64))
+        buf.storage = _Ring(buffer_size)
+        buf.buffer_device = dev
+        buf.weight_sum_tensor = lambda: t.tensor([buf.wt_tree.get_weight_sum()], dtype=t.float64)
+        return buf
+
+    monkeypatch.setattr(apex_mod, "DistributedPrioritizedBuffer", buffer_double)
+    S, A, B, N = 6, 4, 16, 200
+    fused = variant.startswith("fused")
+    Net = (lambda: model_mod.FusedMLP([S, 16, 16, A])) if fused else (lambda: t.nn.Sequential(t.nn.Linear(S, 16), t.nn.ReLU(), t.nn.Linear(16, A)))
+
+    class Q(t.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.net = Net()
+
+        def forward(self, state):
+            return self.net(state)
+
+    q, qt = (Net(), Net()) if fused else (Q(), Q())
+    if fused:                                   # FusedMLP.forward launches kernels: the dry run computes it with torch
+        monkeypatch.setattr(model_mod.FusedMLP, "forward", lambda self, state, action=None: t.nn.functional.linear(
+            t.relu(t.nn.functional.linear(t.relu(t.nn.functional.linear(state, self.layers[0].weight, self.layers[0].bias)),
+                                          self.layers[1].weight, self.layers[1].bias)), self.layers[2].weight, self.layers[2].bias))
+    group = LocalGroup(device="cpu")
+    group.device = dev
+    learner = apex_mod.DQNApex(q, qt, model_mod.FusedAdam if fused else t.optim.SGD, t.nn.MSELoss(reduction="none"), group, (),
+                               batch_size=B, learning_rate=0.01, discount=0.9, update_rate=0.1, replay_size=N)
+    learner.replay_buffer.store_episode(
+        [dict(state={"state": t.randn(1, S)}, action={"action": t.tensor([[i % A]])}, next_state={"state": t.randn(1, S)},
+              reward=float(i), terminal=False) for i in range(50)], priorities=list(np.random.RandomState(0).exponential(size=50)))
+    if variant == "device_apportion+batched_draw":
+        learner.batched_draw = True
+    if fused:
+        learner.use_fused_program, learner.fused_kind = True, ("rows" if variant == "fused_rows" else "program")
+    learner.enable_cuda_graph(static_exchange=True, device_apportion=variant.startswith("device_apportion"))
+    for _ in range(3):
+        loss = learner.update_device()
+        assert loss.shape == ()
+    called = {name for name, _ in rec.calls}
+    want = {"mb_rows_pack_meta", "mb_wire_compact", "mb_wire_scatter_update", "mb_wire_update_mask",
+            "mb_tree_update_priority"}
+    want |= {"mb_per_sample_multi", "mb_wire_apportion"} if variant.startswith("device") else {"mb_per_sample"}
+    want |= {"mb_dqn_mlp_rows_create" if variant == "fused_rows" else "mb_dqn_mlp_program_create", "mb_mlp_program_run",
+             "mb_adam_step_multi"} if fused else {"mb_td_dqn"}
+    assert want <= called, sorted(want - called)
+    assert learner.graph_launches >= 0
