@@ -129,3 +129,65 @@ def test_fixed_shape_update_dry_run(variant, monkeypatch):
              "mb_adam_step_multi"} if fused else {"mb_td_dqn"}
     assert want <= called, sorted(want - called)
     assert learner.graph_launches >= 0
+
+
+@pytest.mark.parametrize("flags", [(), ("overlap_priority_update",), ("parallel_forwards",), ("fuse_optimizer_and_target",),
+                                   ("fused_rows",), ("fused_rows", "overlap_priority_update", "fuse_optimizer_and_target"),
+                                   ("fused_program",)])
+@pytest.mark.parametrize("graph", [False, True])
+def test_single_learner_update_dry_run(flags, graph, monkeypatch):
+    """The same for DQNPer's captured single-GPU update and its stream-level / fusion options."""
+    import machin_b200._lib as lib_mod
+    import machin_b200.frame.algorithms.dqn_per as dqn_mod
+    import machin_b200.frame.buffers.prioritized_buffer as per_mod
+    import machin_b200.model as model_mod
+    import machin_b200.ops as ops
+    from machin_b200.frame.buffers import PrioritizedBuffer
+    rec = _Recorder()
+    for mod in (lib_mod, ops, per_mod, model_mod):
+        monkeypatch.setattr(mod, "lib", rec)
+    monkeypatch.setattr(lib_mod, "stream_ptr", lambda stream=None: C.c_void_p(0))
+    monkeypatch.setattr(ops, "_c", lambda x, dtype=None: None if x is None else (x if dtype is None else x.to(dtype)).contiguous())
+    monkeypatch.setattr(t.Tensor, "pin_memory", lambda self: self)
+    monkeypatch.setattr(t.Tensor, "is_cuda", property(lambda self: True))
+    monkeypatch.setattr(t.cuda, "Event", _Event)
+    monkeypatch.setattr(t.cuda, "Stream", lambda device=None: _Stream())
+    monkeypatch.setattr(t.cuda, "current_stream", lambda device=None: _Stream())
+    monkeypatch.setattr(t.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(t.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(t.cuda, "synchronize", lambda device=None: None)
+    monkeypatch.setattr(t.cuda, "CUDAGraph", _Graph)
+    monkeypatch.setattr(t.cuda, "graph", lambda g, **kw: contextlib.nullcontext())
+    S, A, B, N = 6, 4, 16, 200
+    fused = any(f.startswith("fused_") for f in flags)
+    Net = lambda: model_mod.FusedMLP([S, 16, 16, A])
+    monkeypatch.setattr(model_mod.FusedMLP, "forward", lambda self, state, action=None: t.nn.functional.linear(
+        t.relu(t.nn.functional.linear(t.relu(t.nn.functional.linear(state, self.layers[0].weight, self.layers[0].bias)),
+                                      self.layers[1].weight, self.layers[1].bias)), self.layers[2].weight, self.layers[2].bias))
+    buf = make_cpu_buffer(PrioritizedBuffer, N, epsilon=1e-2, alpha=0.6, beta=0.4, curr_beta=0.4, beta_increment_per_sampling=1e-3,
+                          wt_tree=_Tree(N))
+    buf.storage = _Ring(N)
+    buf.buffer_device = t.device("cpu", 0)
+    learner = dqn_mod.DQNPer(Net(), Net(), model_mod.FusedAdam, t.nn.MSELoss(reduction="none"), batch_size=B, learning_rate=0.01,
+                             discount=0.9, update_rate=0.1, replay_buffer=buf)
+    buf.store_episode([dict(state={"state": t.randn(1, S)}, action={"action": t.tensor([[i % A]])},
+                            next_state={"state": t.randn(1, S)}, reward=float(i), terminal=False) for i in range(50)],
+                      priorities=list(np.random.RandomState(0).exponential(size=50)))
+    for f in flags:
+        if f == "fused_rows":
+            learner.use_fused_program, learner.fused_kind = True, "rows"
+        elif f == "fused_program":
+            learner.use_fused_program, learner.fused_kind = True, "program"
+        else:
+            assert hasattr(learner, f)
+            setattr(learner, f, True)
+    if graph:
+        learner.enable_cuda_graph()
+    for _ in range(3):
+        loss = learner.update_device()
+        assert loss.shape == ()
+    called = {name for name, _ in rec.calls}
+    want = {"mb_per_sample", "mb_tree_update_priority"}
+    want |= {"mb_mlp_program_run_part"} if fused else {"mb_td_dqn"}
+    want |= {"mb_adam_soft_step_multi"} if "fuse_optimizer_and_target" in flags else {"mb_adam_step_multi", "mb_soft_update_multi"}
+    assert want <= called, sorted(want - called)
