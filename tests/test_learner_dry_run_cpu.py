@@ -17,6 +17,22 @@ from fake_ring import FakeRing, FakeTree, make_cpu_buffer
 from test_library_call_sites_cpu import _Recorder
 
 
+def _patch_library(monkeypatch, rec):
+    """Every module of the package that holds a reference to the ctypes library gets the recorder instead."""
+    import importlib
+    import pkgutil
+    import sys
+    import machin_b200
+    import machin_b200._lib as lib_mod
+    real = lib_mod.lib
+    for info in pkgutil.walk_packages(machin_b200.__path__, "machin_b200."):
+        if not info.name.endswith("libmachin_b200"):              # (the shared library sits in the package directory)
+            importlib.import_module(info.name)
+    for name, mod in list(sys.modules.items()):
+        if name.startswith("machin_b200") and getattr(mod, "lib", None) is real:
+            monkeypatch.setattr(mod, "lib", rec)
+
+
 class _Stream:
     def wait_stream(self, other):
         pass
@@ -51,7 +67,7 @@ class _Ring(FakeRing):
         wire[:, :self.pitch] = self.data[index.clamp(0, self.max_size - 1)]
 
 
-@pytest.mark.parametrize("variant", ["default", "device_apportion+batched_draw", "fused_rows", "fused_program"])
+@pytest.mark.parametrize("variant", ["default", "device_apportion+batched_draw", "fused_rows", "fused_program", "dynamic"])
 def test_fixed_shape_update_dry_run(variant, monkeypatch):
     import machin_b200._lib as lib_mod
     import machin_b200.frame.algorithms.apex as apex_mod
@@ -62,11 +78,11 @@ def test_fixed_shape_update_dry_run(variant, monkeypatch):
     from machin_b200.frame.buffers import DistributedPrioritizedBuffer
     from machin_b200.parallel import LocalGroup
     rec = _Recorder()
-    for mod in (lib_mod, ops, per_mod, model_mod):
-        monkeypatch.setattr(mod, "lib", rec)
+    _patch_library(monkeypatch, rec)
     monkeypatch.setattr(lib_mod, "stream_ptr", lambda stream=None: C.c_void_p(0))
     monkeypatch.setattr(ops, "_c", lambda x, dtype=None: None if x is None else (x if dtype is None else x.to(dtype)).contiguous())
     monkeypatch.setattr(t.Tensor, "pin_memory", lambda self: self)
+    monkeypatch.setattr(t, "empty", t.zeros)              # what a kernel would have filled in reads as zeros, not garbage
     monkeypatch.setattr(t.Tensor, "is_cuda", property(lambda self: True))          # "device" tensors of the dry run
     monkeypatch.setattr(t.cuda, "Event", _Event)
     monkeypatch.setattr(t.cuda, "Stream", lambda device=None: _Stream())
@@ -117,13 +133,19 @@ def test_fixed_shape_update_dry_run(variant, monkeypatch):
         learner.batched_draw = True
     if fused:
         learner.use_fused_program, learner.fused_kind = True, ("rows" if variant == "fused_rows" else "program")
-    learner.enable_cuda_graph(static_exchange=True, device_apportion=variant.startswith("device_apportion"))
+    if variant == "dynamic":                    # exactly-sized eager exchanges between two captured graphs
+        learner.enable_cuda_graph()
+    else:
+        learner.enable_cuda_graph(static_exchange=True, device_apportion=variant.startswith("device_apportion"))
     for _ in range(3):
         loss = learner.update_device()
         assert loss.shape == ()
     called = {name for name, _ in rec.calls}
-    want = {"mb_rows_pack_meta", "mb_wire_compact", "mb_wire_scatter_update", "mb_wire_update_mask",
-            "mb_tree_update_priority"}
+    want = {"mb_rows_pack_meta", "mb_tree_update_priority"}
+    if variant == "dynamic":
+        assert {"mb_rows_unpack_meta", "mb_per_sample", "mb_td_dqn"} | want <= called
+        return
+    want |= {"mb_wire_compact", "mb_wire_scatter_update", "mb_wire_update_mask"}
     want |= {"mb_per_sample_multi", "mb_wire_apportion"} if variant.startswith("device") else {"mb_per_sample"}
     want |= {"mb_dqn_mlp_rows_create" if variant == "fused_rows" else "mb_dqn_mlp_program_create", "mb_mlp_program_run",
              "mb_adam_step_multi"} if fused else {"mb_td_dqn"}
@@ -144,11 +166,11 @@ def test_single_learner_update_dry_run(flags, graph, monkeypatch):
     import machin_b200.ops as ops
     from machin_b200.frame.buffers import PrioritizedBuffer
     rec = _Recorder()
-    for mod in (lib_mod, ops, per_mod, model_mod):
-        monkeypatch.setattr(mod, "lib", rec)
+    _patch_library(monkeypatch, rec)
     monkeypatch.setattr(lib_mod, "stream_ptr", lambda stream=None: C.c_void_p(0))
     monkeypatch.setattr(ops, "_c", lambda x, dtype=None: None if x is None else (x if dtype is None else x.to(dtype)).contiguous())
     monkeypatch.setattr(t.Tensor, "pin_memory", lambda self: self)
+    monkeypatch.setattr(t, "empty", t.zeros)
     monkeypatch.setattr(t.Tensor, "is_cuda", property(lambda self: True))
     monkeypatch.setattr(t.cuda, "Event", _Event)
     monkeypatch.setattr(t.cuda, "Stream", lambda device=None: _Stream())
