@@ -7,7 +7,7 @@ import torch.nn as nn
 
 from ... import ops
 
-_SPEC_CACHE: Dict[int, tuple] = {}
+_SPEC_CACHE: Dict[tuple, tuple] = {}
 
 
 def _unwrap(model):
@@ -32,7 +32,7 @@ def safe_call(model, *named_args, method="__call__"):
     always returns a tuple (utils.py:52-161)."""
     inner = _unwrap(model)
     fn = inner.forward if method == "__call__" else getattr(inner, method)
-    key = (id(type(inner)), method)
+    key = (type(inner), method)          # the class itself, not its id: ids are reused after a class is collected
     spec = _SPEC_CACHE.get(key)
     if spec is None:
         s = inspect.getfullargspec(fn)

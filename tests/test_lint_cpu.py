@@ -28,7 +28,7 @@ def test_every_referenced_library_symbol_exists():
         for name in set(re.findall(r"\blib\.(mb_[a-z0-9_]+)", src)):
             if name not in _lib.SIGNATURES:
                 missing.append((os.path.relpath(f, ROOT), "lib." + name))
-        for name in set(re.findall(r"\b_lib\.([A-Za-z_][A-Za-z0-9_]*)", src)):
+        for name in set(re.findall(r"\b_lib\.([A-Za-z_][A-Za-z0-9_]*)", src)) - {"py"}:        # ("_lib.py" in prose)
             if not hasattr(_lib, name):
                 missing.append((os.path.relpath(f, ROOT), "_lib." + name))
     assert not missing, missing
