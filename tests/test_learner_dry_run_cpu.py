@@ -213,3 +213,67 @@ def test_single_learner_update_dry_run(flags, graph, monkeypatch):
     want |= {"mb_mlp_program_run_part"} if fused else {"mb_td_dqn"}
     want |= {"mb_adam_soft_step_multi"} if "fuse_optimizer_and_target" in flags else {"mb_adam_step_multi", "mb_soft_update_multi"}
     assert want <= called, sorted(want - called)
+
+
+def _dry_run_patches(monkeypatch):
+    import machin_b200._lib as lib_mod
+    import machin_b200.ops as ops
+    rec = _Recorder()
+    _patch_library(monkeypatch, rec)
+    monkeypatch.setattr(lib_mod, "stream_ptr", lambda stream=None: C.c_void_p(0))
+    monkeypatch.setattr(ops, "_c", lambda x, dtype=None: None if x is None else (x if dtype is None else x.to(dtype)).contiguous())
+    monkeypatch.setattr(t.Tensor, "pin_memory", lambda self: self)
+    monkeypatch.setattr(t, "empty", t.zeros)
+    monkeypatch.setattr(t.Tensor, "is_cuda", property(lambda self: True))
+    monkeypatch.setattr(t.cuda, "Event", _Event)
+    monkeypatch.setattr(t.cuda, "Stream", lambda device=None: _Stream())
+    monkeypatch.setattr(t.cuda, "current_stream", lambda device=None: _Stream())
+    monkeypatch.setattr(t.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(t.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(t.cuda, "synchronize", lambda device=None: None)
+    monkeypatch.setattr(t.cuda, "CUDAGraph", _Graph)
+    monkeypatch.setattr(t.cuda, "graph", lambda g, **kw: contextlib.nullcontext())
+    return rec
+
+
+def _per_double(N):
+    from machin_b200.frame.buffers import PrioritizedBuffer
+    buf = make_cpu_buffer(PrioritizedBuffer, N, epsilon=1e-2, alpha=0.6, beta=0.4, curr_beta=0.4, beta_increment_per_sampling=1e-3,
+                          wt_tree=_Tree(N))
+    buf.storage = _Ring(N)
+    buf.buffer_device = t.device("cpu", 0)
+    return buf
+
+
+def test_ddpg_per_update_dry_run(monkeypatch):
+    """DDPGPer.update (ddpg_per.py:92-185 mirror): actor / critic / two targets over the prioritized buffer double."""
+    import machin_b200.frame.algorithms.ddpg_per as ddpg_mod
+    rec = _dry_run_patches(monkeypatch)
+    S, A, B, N = 5, 2, 8, 100
+
+    class Actor(t.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = t.nn.Linear(S, A)
+
+        def forward(self, state):
+            return t.tanh(self.fc(state))
+
+    class Critic(t.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = t.nn.Linear(S + A, 1)
+
+        def forward(self, state, action):
+            return self.fc(t.cat([state, action], dim=1))
+
+    learner = ddpg_mod.DDPGPer(Actor(), Actor(), Critic(), Critic(), t.optim.SGD, t.nn.MSELoss(reduction="none"), batch_size=B,
+                               replay_buffer=_per_double(N))
+    learner.replay_buffer.store_episode(
+        [dict(state={"state": t.randn(1, S)}, action={"action": t.randn(1, A)}, next_state={"state": t.randn(1, S)},
+              reward=float(i), terminal=(i == 29)) for i in range(30)], priorities=list(np.ones(30)))
+    for _ in range(2):
+        out = learner.update()
+        assert len(out) == 2 and all(np.isfinite(x) for x in out)
+    called = {name for name, _ in rec.calls}
+    assert {"mb_per_sample", "mb_td_target", "mb_tree_update_priority", "mb_soft_update_multi"} <= called, sorted(called)
