@@ -50,6 +50,19 @@ for _ in range(3):
                                      _lib.ptr(scale), _lib.ptr(params), _lib.stream_ptr()))
     _lib.check(lib.mb_per_sample_multi(tree, _lib.ptr(uni), B, P, _lib.ptr(params), _lib.ptr(idx), _lib.ptr(isw),
                                        _lib.stream_ptr()))
+# kernels that had no capture in round 1: returns / GAE, DDPG target, the scatter direction of the row mover
+from machin_b200 import ops  # noqa: E402
+T = 1024 * 20
+te = t.zeros(T, dtype=t.bool, device=dev)
+te[19::20] = True
+for _ in range(2):
+    ops.gae(t.randn(T, dtype=t.float64, device=dev), te, t.randn(T, device=dev), t.randn(T, device=dev), 0.99, 0.95, n_episodes=1024)
+    ops.td_target(t.randn(B, 1, device=dev), t.randn(B, 1, device=dev), te[:B].view(B, 1), 0.99, value=t.randn(B, 1, device=dev))
+    buf.store_episode_tensors(
+        {"state": {"state": t.randn(4096, S, device=dev)}, "action": {"action": t.randint(0, A, (4096, 1), device=dev)},
+         "next_state": {"state": t.randn(4096, S, device=dev)}},
+        {"reward": t.randn(4096, 1, device=dev), "terminal": t.rand(4096, 1, device=dev) < 0.01},
+        priorities=t.rand(4096, device=dev, dtype=t.float64))
 t.cuda.synchronize()
 buf.wt_tree.check()
 print("done", counts.tolist())
