@@ -60,7 +60,7 @@ def parse():
     p.add_argument("--device-apportion", action="store_true",
                    help="N > 1, fixed-shape exchange, opt-in: shard sums all-gathered and apportioned inside the graph "
                         "(no host read per update)")
-    p.add_argument("--watchdog-s", type=float, default=600.0,
+    p.add_argument("--watchdog-s", type=float, default=420.0,
                    help="N > 1: leave with exit code 5 if the run has not finished after this many seconds "
                         "(a stuck collective must not hold the box)")
     p.add_argument("--fuse-forwards", action="store_true", help="one online forward over [s; s'] instead of two passes like the "
