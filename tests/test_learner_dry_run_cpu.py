@@ -277,3 +277,56 @@ def test_ddpg_per_update_dry_run(monkeypatch):
         assert len(out) == 2 and all(np.isfinite(x) for x in out)
     called = {name for name, _ in rec.calls}
     assert {"mb_per_sample", "mb_td_target", "mb_tree_update_priority", "mb_soft_update_multi"} <= called, sorted(called)
+
+
+def test_ddpg_apex_update_dry_run(monkeypatch):
+    """DDPGApex.update over the sharded-buffer double on a group of one (the path tools/ddpg_apex_bench.py times)."""
+    import machin_b200.frame.algorithms.apex as apex_mod
+    import machin_b200.model as model_mod
+    from machin_b200.frame.buffers import DistributedPrioritizedBuffer
+    from machin_b200.parallel import LocalGroup
+    rec = _dry_run_patches(monkeypatch)
+    dev = t.device("cpu", 0)
+
+    def buffer_double(buffer_name, group, buffer_size, requesters=None, **kw):
+        buf = make_cpu_buffer(DistributedPrioritizedBuffer, buffer_size, epsilon=1e-2, alpha=0.6, beta=0.4, curr_beta=0.4,
+                              beta_increment_per_sampling=1e-3, wt_tree=_Tree(buffer_size), buffer_name=buffer_name, group=group,
+                              wr_lock=RLock(), _requesters=requesters, _sampler=None,
+                              buffer_version_table=t.zeros(buffer_size, dtype=t.int64))
+        buf.storage = _Ring(buffer_size)
+        buf.buffer_device = dev
+        buf.weight_sum_tensor = lambda: t.tensor([max(buf.wt_tree.get_weight_sum(), 1.0)], dtype=t.float64)
+        return buf
+
+    monkeypatch.setattr(apex_mod, "DistributedPrioritizedBuffer", buffer_double)
+    S, A, B, N = 5, 2, 8, 100
+
+    class Actor(t.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = t.nn.Linear(S, A)
+
+        def forward(self, state):
+            return t.tanh(self.fc(state))
+
+    class Critic(t.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = t.nn.Linear(S + A, 1)
+
+        def forward(self, state, action):
+            return self.fc(t.cat([state, action], dim=1))
+
+    group = LocalGroup(device="cpu")
+    group.device = dev
+    learner = apex_mod.DDPGApex(Actor(), Actor(), Critic(), Critic(), model_mod.FusedAdam, t.nn.MSELoss(reduction="none"), group, (),
+                                batch_size=B, replay_size=N)
+    learner.replay_buffer.store_episode(
+        [dict(state={"state": t.randn(1, S)}, action={"action": t.randn(1, A)}, next_state={"state": t.randn(1, S)},
+              reward=float(i), terminal=(i == 29)) for i in range(30)], priorities=list(np.ones(30)))
+    for _ in range(2):
+        out = learner.update()
+        assert len(out) == 2
+    called = {name for name, _ in rec.calls}
+    assert {"mb_per_sample", "mb_rows_pack_meta", "mb_rows_unpack_meta", "mb_td_target", "mb_tree_update_priority",
+            "mb_adam_step_multi", "mb_soft_update_multi"} <= called, sorted(called)
