@@ -397,7 +397,7 @@ class DQNApex(DQNPer):
             st["nstored"].copy_(st["ring_ns"][i], non_blocking=True)
             st["ring_ev"][i].record()
             for _ in range(P):
-                buf.curr_beta = np.min([1.0, buf.curr_beta + buf.beta_increment_per_sampling])
+                buf.curr_beta = np.float64(min(1.0, buf.curr_beta + buf.beta_increment_per_sampling))
             return self.batch_size
         sums = grp.all_gather_f64(buf.weight_sum_tensor()).view(-1).tolist()
         ssize, total = shard_sample_sizes(sums, self.batch_size)
@@ -410,7 +410,7 @@ class DQNApex(DQNPer):
                                    dtype=np.uint8)
             if n_mine > 0:
                 st["uni_pin"].numpy()[r, :n_mine] = np.random.uniform(size=n_mine)
-                buf.curr_beta = np.min([1.0, buf.curr_beta + buf.beta_increment_per_sampling])
+                buf.curr_beta = np.float64(min(1.0, buf.curr_beta + buf.beta_increment_per_sampling))
         return n
 
     def update_device(self, update_value=True, update_target=True, uniform=None):

@@ -164,6 +164,7 @@ class DQNPer(TorchFramework):
         buf.enable_graph_params()
         self._u_static = t.rand(self.batch_size, dtype=t.float64, device=dev)
         self._u_pinned = t.empty(self.batch_size, dtype=t.float64).pin_memory()
+        self._u_pinned_np = self._u_pinned.numpy()       # (a view: taking it per update costs microseconds)
         self._h2d_done = t.cuda.Event()
         cur = t.cuda.current_stream(dev)
         side = t.cuda.Stream(device=dev)
@@ -206,13 +207,13 @@ class DQNPer(TorchFramework):
             buf = self.replay_buffer
             if uniform is None:
                 self._h2d_done.synchronize()
-                self._u_pinned.numpy()[:] = np.random.uniform(size=self.batch_size)   # same stream as :411
+                self._u_pinned_np[:] = np.random.uniform(size=self.batch_size)       # same stream as :411
                 self._u_static.copy_(self._u_pinned, non_blocking=True)
                 self._h2d_done.record()
             else:
                 self._u_static.copy_(uniform)
             self._graph.replay()
-            buf.curr_beta = np.min([1.0, buf.curr_beta + buf.beta_increment_per_sampling])
+            buf.curr_beta = np.float64(min(1.0, buf.curr_beta + buf.beta_increment_per_sampling))
             return self._static_loss
         return self._step(update_value, update_target, uniform, False)
 

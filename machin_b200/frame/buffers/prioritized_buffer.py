@@ -161,7 +161,7 @@ class PrioritizedBuffer(Buffer):
         _lib.check(lib.mb_per_sample(self.wt_tree.handle, _lib.ptr(uniform), batch_size, len(self.storage),
                                      float(all_weight_sum or 0.0), float(self.curr_beta), None,
                                      _lib.ptr(d_index), _lib.ptr(d_isw), _lib.stream_ptr()))
-        self.curr_beta = np.min([1.0, self.curr_beta + self.beta_increment_per_sampling])
+        self.curr_beta = np.float64(min(1.0, self.curr_beta + self.beta_increment_per_sampling))   # == np.min([1.0, ...]) (:425-427), 25x cheaper
         return d_index, d_isw
 
     def sample_device(self, batch_size: int, uniform: t.Tensor = None, names=None, use_device_params=False
