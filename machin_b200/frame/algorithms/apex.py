@@ -402,15 +402,24 @@ class DQNApex(DQNPer):
         sums = grp.all_gather_f64(buf.weight_sum_tensor()).view(-1).tolist()
         ssize, total = shard_sample_sizes(sums, self.batch_size)
         n, n_mine = int(sum(ssize)), int(ssize[me])
-        st["counts_pin"].numpy()[:] = ssize
-        st["scale_pin"].numpy()[0] = st["capB"] / n
-        raw = st["params_pin"].numpy()
-        for r in range(P):                                # one draw per requester; beta advances per draw (:425-427)
-            raw[r] = np.frombuffer(st["struct"].pack("<ddqqq", float(buf.curr_beta), float(total), len(buf.storage), 0, n_mine),
-                                   dtype=np.uint8)
+        views = st.get("np")
+        if views is None:                                 # NumPy views of the pinned blocks, taken once
+            rec = np.dtype([("beta", "<f8"), ("total", "<f8"), ("n_stored", "<i8"), ("step", "<i8"), ("n_draw", "<i8")])
+            views = st["np"] = {"counts": st["counts_pin"].numpy(), "scale": st["scale_pin"].numpy(),
+                                "params": st["params_pin"].numpy().view(rec).reshape(P), "uni": st["uni_pin"].numpy()}
+        views["counts"][:] = ssize
+        views["scale"][0] = st["capB"] / n
+        beta, betas = buf.curr_beta, []
+        for _ in range(P):                                # one draw per requester; beta advances per draw (:425-427)
+            betas.append(beta)
             if n_mine > 0:
-                st["uni_pin"].numpy()[r, :n_mine] = np.random.uniform(size=n_mine)
-                buf.curr_beta = np.float64(min(1.0, buf.curr_beta + buf.beta_increment_per_sampling))
+                beta = np.float64(min(1.0, beta + buf.beta_increment_per_sampling))
+        prm = views["params"]
+        prm["beta"], prm["total"], prm["n_stored"], prm["step"], prm["n_draw"] = betas, total, len(buf.storage), 0, n_mine
+        if n_mine > 0:
+            # P consecutive draws of n_mine uniforms are one draw of P * n_mine from the same MT19937 stream (:411)
+            views["uni"][:, :n_mine] = np.random.uniform(size=P * n_mine).reshape(P, n_mine)
+        buf.curr_beta = beta
         return n
 
     def update_device(self, update_value=True, update_target=True, uniform=None):
