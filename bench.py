@@ -385,8 +385,20 @@ def run_b200(a):
         # N = 2: 0.373 ms/update against 0.703 ms for the dynamic path; equivalent to it draw for draw on a group
         # of one, tests/test_gpu_algorithms.py).  --dynamic-exchange: two compute graphs around eager, exactly
         # sized NCCL exchanges (measured at N = 2, 4).
-        learner.enable_cuda_graph(static_exchange=a.static_exchange,
-                                  device_apportion=a.device_apportion and a.static_exchange)
+        try:
+            learner.enable_cuda_graph(static_exchange=a.static_exchange,
+                                      device_apportion=a.device_apportion and a.static_exchange)
+        except Exception as exc:   # noqa: BLE001 -- a capture problem is deterministic: every rank lands here together
+            if not a.static_exchange:
+                raise
+            sys.stderr.write(f"bench.py: rank {rank}: fixed-shape exchange could not be captured ({exc!r}); "
+                             "falling back to the dynamic exchange\n")
+            t.cuda.synchronize(device)
+            a.static_exchange = False
+            del learner
+            t.cuda.empty_cache()
+            learner = build_learner(a, device, seed=rank, world=world)
+            learner.enable_cuda_graph()
     elif graph:
         learner.enable_cuda_graph()
     K, W, B = a.steps, max(a.warmup, 3), a.batch
