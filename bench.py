@@ -395,6 +395,7 @@ def run_b200(a):
                              "falling back to the dynamic exchange\n")
             t.cuda.synchronize(device)
             a.static_exchange = False
+            a.skip_teardown = True      # a half-captured NCCL graph may linger: leave like the fixed-shape run does
             del learner
             t.cuda.empty_cache()
             learner = build_learner(a, device, seed=rank, world=world)
@@ -460,7 +461,7 @@ def run_b200(a):
     ms_total, e2e_ms = float(tt[0]), float(tt[1])
     def leave():
         if world > 1:
-            if graph and a.static_exchange:
+            if graph and (a.static_exchange or getattr(a, "skip_teardown", False)):
                 # NCCL collectives captured in a CUDA graph: destroy_process_group() hangs while the graph is
                 # alive (tools/nccl_graph_repro.py) -- flush and leave without the teardown
                 sys.stdout.flush()
