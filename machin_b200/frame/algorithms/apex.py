@@ -194,7 +194,6 @@ class DQNApex(DQNPer):
 
     # ------------------------------------------------------------------ fixed-shape, single-graph update
     def _enable_static_graph(self, warmup: int = 3, device_apportion: bool = False):
-        import struct
         import torch.distributed as dist
         from ..._lib import lib, ptr, check, stream_ptr
         from ..buffers import PrioritizedBuffer
@@ -215,7 +214,7 @@ class DQNApex(DQNPer):
               "send2": z((P * cap, 24), t.uint8), "recv2": z((P * cap, 24), t.uint8),
               "u_idx": z(P * cap, t.int64), "u_pri": z(P * cap, t.float32), "u_valid": z(P * cap, t.uint8),
               "d_idx": z((P, cap), t.int64), "d_isw": z((P, cap), t.float64),       # row r: the draw for requester r
-              "struct": struct, "device_apportion": bool(device_apportion),
+              "device_apportion": bool(device_apportion),
               "sums": z(P, t.float64), "beta": z(1, t.float64), "nstored": z(1, t.int64),
               # device apportioning lets the host run ahead of the device, so what it writes per update goes through a
               # small ring of pinned buffers guarded by events (copied in FRONT of the replay, not inside the graph)

@@ -29,7 +29,7 @@ def _learner(P, me, B, sums, device_apportion):
     cap = B
     z = lambda shape, dt: t.zeros(shape, dtype=dt)
     learner._static = {
-        "P": P, "cap": cap, "capB": B + P, "struct": struct, "device_apportion": device_apportion,
+        "P": P, "cap": cap, "capB": B + P, "device_apportion": device_apportion,
         "counts_pin": z(P, t.int64), "params_pin": z((P, 40), t.uint8), "uni_pin": z((P, cap), t.float64),
         "scale_pin": z(1, t.float64), "uni": z((P, cap), t.float64), "nstored": z(1, t.int64),
         "ring_uni": [z((P, cap), t.float64) for _ in range(4)], "ring_ns": [z(1, t.int64) for _ in range(4)],
