@@ -363,20 +363,7 @@ class DQNPer(TorchFramework):
             else:
                 self._backward(value_loss)
             self._sync_grads()
-        if self.fuse_optimizer_and_target:
-            self._optimizer_and_target(update_value, update_target)      # FusedAdam + soft update as one launch when possible
-            update_value = update_target = False
-        if update_value:
-            if np.isfinite(self.grad_max):   # with max_norm = inf the reference's clip multiplies by exactly 1.0
-                nn.utils.clip_grad_norm_(self.qnet.parameters(), self.grad_max)
-            self.qnet_optim.step()
-        if update_target:
-            if self.update_rate is not None:
-                soft_update(self.qnet_target, self.qnet, self.update_rate)
-            else:
-                self._update_counter += 1
-                if self._update_counter % self.update_steps == 0:
-                    hard_update(self.qnet_target, self.qnet)
+        self._optimizer_and_target(update_value, update_target)   # (FusedAdam + soft update as one launch when opted in)
         if forked is not None:
             forked[0].wait_stream(forked[1])     # join before the next draw reads the tree (td / d_index still alive here)
         self.qnet.eval()
