@@ -9,11 +9,9 @@ Rows are written by ``mb_rows_scatter`` and sampled by ``mb_rows_gather`` (csrc/
 Slot assignment follows storage.py:97-114: append until full, then overwrite at the ring
 cursor; an episode longer than the ring raises ``ValueError("Failed to store episode.")``.
 """
-import ctypes as C
 from collections import OrderedDict
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional
 
-import numpy as np
 import torch as t
 
 from ... import _lib

@@ -17,7 +17,7 @@ import numpy as np
 import torch as t
 
 from ..transition import TransitionBase
-from .buffer import Buffer, EpisodeBook
+from .buffer import Buffer
 from .prioritized_buffer import PrioritizedBuffer
 
 

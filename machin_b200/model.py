@@ -8,7 +8,7 @@ target updates, model servers and checkpoints see a normal module.  ``FusedAdam`
 Any other ``nn.Module`` / optimizer keeps working through the generic autograd path.
 """
 import ctypes as C
-from typing import List, Sequence
+from typing import Sequence
 
 import torch as t
 import torch.nn as nn

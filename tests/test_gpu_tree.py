@@ -8,7 +8,6 @@ import pytest
 import torch as t
 
 from conftest import GOLDEN
-from oracle import per as oper
 from oracle.sumtree import OracleTree
 
 pytestmark = pytest.mark.gpu

@@ -1,8 +1,6 @@
 """GPU: the opt-in second-generation small sorted tree update (csrc/sumtree.cu: tree_update_sorted_v2;
 MB_SORTED_CLUSTER=1: 8 subtrees on a cluster of 8 CTAs, MB_SORTED_ASYNC=1: barrier-free walk with point-to-point
 hand-overs, or both) against the oracle -- bit-exact, like the single-CTA kernel."""
-import os
-
 import numpy as np
 import pytest
 import torch as t

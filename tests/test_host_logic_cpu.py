@@ -1,7 +1,6 @@
 """CPU: host-side logic of the path -- Transition validation (mirrors the cases of the reference's
 test/frame/test_transition.py), row layout properties, shard apportioning (prioritized_buffer_d.py:229-234),
 safe_call argument routing (algorithms/utils.py:52-161)."""
-import numpy as np
 import pytest
 import torch as t
 from hypothesis import given, settings

@@ -72,7 +72,6 @@ def test_fixed_shape_update_dry_run(variant, monkeypatch):
     import machin_b200._lib as lib_mod
     import machin_b200.frame.algorithms.apex as apex_mod
     import machin_b200.frame.algorithms.dqn_per as dqn_mod
-    import machin_b200.frame.buffers.prioritized_buffer as per_mod
     import machin_b200.model as model_mod
     import machin_b200.ops as ops
     from machin_b200.frame.buffers import DistributedPrioritizedBuffer

@@ -7,7 +7,6 @@ order with per-shard IS weights over the global sum, and after the write-back ev
 tree updated requester by requester with stale versions dropped."""
 import ctypes as C
 import os
-import struct
 import subprocess
 
 import numpy as np

@@ -1,6 +1,6 @@
 """torchrun helper: host-side time per phase of the sharded APEX learner step (rank 0)."""
 import argparse, os, sys, time
-import numpy as np, torch as t, torch.distributed as dist
+import torch as t, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])

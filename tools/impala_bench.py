@@ -6,7 +6,6 @@ import os
 import sys
 import time
 
-import numpy as np
 import torch as t
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

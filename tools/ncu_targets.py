@@ -4,7 +4,6 @@ that `ncu -k regex:<kernel>` can capture it.  Used only under the profiler; prin
 import os
 import sys
 
-import numpy as np
 import torch as t
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
