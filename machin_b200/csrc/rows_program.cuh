@@ -47,10 +47,10 @@ __device__ __forceinline__ void rows_load_b(const float *__restrict__ row, int j
             const float2 x = __ldg(reinterpret_cast<const float2 *>(row + j0));
             v[0] = x.x; v[1] = x.y;
         }
-        return;
-    }
+    } else {
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) v[c] = j0 + c < N ? __ldg(row + j0 + c) : 0.0f;
+        for (int c = 0; c < CPT; ++c) v[c] = j0 + c < N ? __ldg(row + j0 + c) : 0.0f;
+    }
 }
 
 // acc[r][c] = sum_k As[(ty * MR + r) * ap + k] * Bg[k * N + j0 + c]      (rows in shared memory, B k-major in global)
