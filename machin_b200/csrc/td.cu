@@ -6,6 +6,7 @@
 // gathered action value and abs_error are bit-identical to CPU torch given the same Q values.
 #include "mb_common.cuh"
 #include "td_device.cuh"
+#include "dist_device.cuh"
 
 namespace {
 
@@ -67,6 +68,25 @@ int mb_td_dqn(const float *d_q, const float *d_q_next, const float *d_q_tgt_next
     TdDqnArgs a{d_q, d_q_next, d_q_tgt_next, batch, n_actions, d_action, d_reward, d_terminal, d_is_weight,
                 discount, mode, d_y, d_action_value, d_abs_error, d_loss_elem, d_grad_q};
     td_dqn_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    MB_LAUNCHED(1);
+    return MB_OK;
+}
+
+int mb_td_rainbow(const float *d_q_dist, const float *d_next_q_dist, const float *d_target_next_q_dist, int64_t batch,
+                  int n_actions, int n_atoms, const float *d_support, const int64_t *d_action, const float *d_value,
+                  const uint8_t *d_terminal, const double *d_is_weight, double v_min, double v_max, double discount_n,
+                  float *d_target_dist, float *d_loss_row, float *d_abs_error, double *d_loss_elem, float *d_grad_q,
+                  void *stream) {
+    if (batch < 0 || n_actions < 1 || n_atoms < 2 || n_atoms > kDistMaxAtoms) return MB_ERR_INVALID;
+    if (!d_q_dist || !d_next_q_dist || !d_target_next_q_dist || !d_support || !d_action || !d_value || !d_terminal)
+        return MB_ERR_INVALID;
+    if (batch == 0) return MB_OK;
+    // the reference's Python doubles become float32 scalars where they meet a float32 tensor (rainbow.py:247-255)
+    DistArgs a{d_q_dist, d_next_q_dist, d_target_next_q_dist, d_support, batch, n_actions, n_atoms, d_action, d_value,
+               d_terminal, d_is_weight, (float)(v_min + 1e-6), (float)(v_max - 1e-6), (float)v_min,
+               (float)((v_max - v_min) / ((double)n_atoms - 1.0)), (float)discount_n, d_target_dist, d_loss_row,
+               d_abs_error, d_loss_elem, d_grad_q};
+    td_dist_kernel<<<(unsigned)batch, kDistThreads, 0, (cudaStream_t)stream>>>(a);
     MB_LAUNCHED(1);
     return MB_OK;
 }

@@ -581,10 +581,110 @@ def gen_rnn():
     np.savez_compressed(os.path.join(OUT, "ref_rnn.npz"), **out)
 
 
+# --------------------------------------------------------------------------- RAINBOW (distributional target)
+class _DistQNet(t.nn.Module):
+    """The shape contract of rainbow.py:44-48: [batch, action_num, atom_num], last dimension soft-maxed."""
+
+    def __init__(self, s, a, atoms, h=16):
+        super().__init__()
+        self.fc1 = t.nn.Linear(s, h)
+        self.fc2 = t.nn.Linear(h, a * atoms)
+        self.a, self.atoms = a, atoms
+
+    def forward(self, state):
+        return t.softmax(self.fc2(t.relu(self.fc1(state))).view(-1, self.a, self.atoms), dim=-1)
+
+
+def gen_rainbow():
+    from machin.frame.algorithms import RAINBOW
+    from machin.model.nets.base import static_module_wrapper as smw
+
+    out = {}
+    seed_all(0)
+    S, A, ATOMS, B, NSTEP = 5, 3, 11, 32, 3
+    VMIN, VMAX, DISC = -2.0, 3.0, 0.9          # delta_z = 0.5: rewards on the grid land on atoms exactly
+    qnet, qtgt = _DistQNet(S, A, ATOMS), _DistQNet(S, A, ATOMS)
+    rb = RAINBOW(smw(qnet, "cpu", "cpu"), smw(qtgt, "cpu", "cpu"), t.optim.SGD, VMIN, VMAX, batch_size=B,
+                 learning_rate=0.05, discount=DISC, update_rate=0.1, reward_future_steps=NSTEP, replay_size=400)
+    out["init_q"], out["init_qt"] = _flat_params(rb.qnet), _flat_params(rb.qnet_target)
+    out["config"] = np.array([S, A, ATOMS, B, NSTEP, VMIN, VMAX, DISC, 0.05, 0.1])
+    rng = np.random.RandomState(21)
+    # episodes of several lengths (shorter than, equal to, longer than the n-step horizon); rewards: half of them
+    # on the 0.5 grid (so that terminal targets hit atoms exactly: both neighbour weights are 0 there,
+    # rainbow.py:257-262), some far outside [v_min, v_max] (clamped)
+    lens = [1, 2, 3, 4, 1, 2, 7, 1, 3, 12, 2, 1, 30, 2, 1, 3, 41, 1, 2, 2]
+    ep_state, ep_next, ep_act, ep_rew, ep_term, ep_value = [], [], [], [], [], []
+    for ei, n in enumerate(lens):
+        st, nst = rng.randn(n, S).astype(np.float32), rng.randn(n, S).astype(np.float32)
+        act = rng.randint(0, A, size=n).astype(np.int64)
+        grid = rng.choice([-1.0, -0.5, 0.0, 0.5, 1.0, 6.0, -7.0], size=n)
+        rew = np.where(rng.rand(n) < 0.5, grid, rng.randn(n)).astype(np.float64)
+        if n <= 2:
+            rew[-1] = (-1.0, -0.5, 0.0, 0.5, 1.0)[ei % 5]      # terminal target exactly on an atom
+        term = np.zeros(n, dtype=bool)
+        term[-1] = ei % 5 != 3                 # some episodes end without a terminal flag
+        ep = [dict(state={"state": t.from_numpy(st[i:i + 1])}, action={"action": t.tensor([[act[i]]])},
+                   next_state={"state": t.from_numpy(nst[i:i + 1])}, reward=float(rew[i]), terminal=bool(term[i]))
+              for i in range(n)]
+        rb.store_episode(ep)
+        ep_state.append(st), ep_next.append(nst), ep_act.append(act), ep_rew.append(rew), ep_term.append(term)
+        ep_value.append(np.array([tr["value"] for tr in ep], dtype=np.float64))     # rainbow.py:186-196
+    out.update(lens=np.array(lens), state=np.concatenate(ep_state), next_state=np.concatenate(ep_next),
+               action=np.concatenate(ep_act), reward=np.concatenate(ep_rew), terminal=np.concatenate(ep_term),
+               value=np.concatenate(ep_value), tree0=rb.replay_buffer.wt_tree.weights.copy())
+    # record what one update saw and produced, without touching its code: wrap the buffer calls around it and
+    # Tensor.index_add_ (its second call leaves the projected target distribution in `self`)
+    buf = rb.replay_buffer
+    real_sample, real_update, real_index_add = buf.sample_batch, buf.update_priority, t.Tensor.index_add_
+    seen = {}
+
+    def sample_batch(*a, **k):
+        r = real_sample(*a, **k)
+        seen["batch"], seen["index"], seen["isw"] = r[1], r[2], r[3]
+        return r
+
+    def update_priority(priorities, indexes):
+        seen["abs_error"] = np.array(priorities)
+        return real_update(priorities, indexes)
+
+    def index_add_(self, *a, **k):
+        r = real_index_add(self, *a, **k)
+        seen["target_dist"] = self
+        return r
+
+    buf.sample_batch, buf.update_priority = sample_batch, update_priority
+    seed_all(13)
+    for step in range(3):
+        s0 = np.random.get_state()
+        out[f"u{step}"] = np.random.uniform(size=B)
+        np.random.set_state(s0)
+        t.Tensor.index_add_ = index_add_
+        try:
+            loss = rb.update()
+        finally:
+            t.Tensor.index_add_ = real_index_add
+        state, action, value, next_state, terminal, _ = seen["batch"]
+        out[f"index{step}"], out[f"isw{step}"] = np.array(seen["index"]), np.array(seen["isw"])
+        out[f"b_state{step}"], out[f"b_next{step}"] = state["state"].numpy(), next_state["state"].numpy()
+        out[f"b_action{step}"], out[f"b_value{step}"] = action["action"].numpy(), value.numpy()
+        out[f"b_terminal{step}"] = terminal.numpy()
+        out[f"target_dist{step}"] = seen["target_dist"].view(B, ATOMS).numpy().copy()
+        out[f"abs_error{step}"] = seen["abs_error"]
+        out[f"loss{step}"] = np.float64(loss)
+        out[f"tree{step + 1}"] = buf.wt_tree.weights.copy()
+        out[f"q{step + 1}"], out[f"qt{step + 1}"] = _flat_params(rb.qnet), _flat_params(rb.qnet_target)
+    # acting (rainbow.py:110-133): expectation over the support, argmax
+    probe = rng.randn(9, S).astype(np.float32)
+    out["act_state"] = probe
+    out["act_online"] = rb.act_discrete({"state": t.from_numpy(probe)}).numpy()
+    out["act_target"] = rb.act_discrete({"state": t.from_numpy(probe)}, use_target=True).numpy()
+    np.savez_compressed(os.path.join(OUT, "ref_rainbow.npz"), **out)
+
+
 if __name__ == "__main__":
     ref_shim.load()
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["tree", "per", "td", "vtrace", "gae", "buffer", "per_d", "rnn"]
+    which = sys.argv[1:] or ["tree", "per", "td", "vtrace", "gae", "buffer", "per_d", "rnn", "rainbow"]
     for name in which:
         globals()["gen_" + name]()
         print("wrote", name)
