@@ -3,5 +3,6 @@ from .apex import DDPGApex, DQNApex
 from .ddpg_per import DDPGPer
 from .dqn_per import DQNPer
 from .impala import IMPALA
+from .rainbow import RAINBOW
 
-__all__ = ["DQNPer", "DQNApex", "DDPGPer", "DDPGApex", "IMPALA", "A2C", "A3C"]
+__all__ = ["DQNPer", "DQNApex", "DDPGPer", "DDPGApex", "IMPALA", "A2C", "A3C", "RAINBOW"]

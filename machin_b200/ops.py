@@ -52,6 +52,48 @@ def td_dqn(q, q_next, q_tgt_next, action, reward, terminal, discount: float, is_
     return {"y": y, "action_value": av, "abs_error": ae, "loss_elem": le, "grad_q": gq}
 
 
+_SUPPORT_CACHE: Dict[tuple, t.Tensor] = {}
+
+
+def value_support(v_min: float, v_max: float, atoms: int, device) -> t.Tensor:
+    """t.linspace(v_min, v_max, atoms) as the reference evaluates it -- float32 on the CPU (rainbow.py:119,227) --
+    uploaded once per (range, size, device)."""
+    key = (float(v_min), float(v_max), int(atoms), str(device))
+    sup = _SUPPORT_CACHE.get(key)
+    if sup is None:
+        sup = _SUPPORT_CACHE[key] = t.linspace(v_min, v_max, atoms).to(device)
+    return sup
+
+
+def td_rainbow(q_dist, next_q_dist, target_next_q_dist, action, value, terminal, v_min: float, v_max: float,
+               discount_n: float, is_weight=None, want_grad: bool = False) -> Dict[str, t.Tensor]:
+    """Categorical TD target, row loss and priority of RAINBOW (rainbow.py:212-306) in one launch.
+
+    q_dist / next_q_dist / target_next_q_dist: f32[B, A, N] soft-maxed distributions of the online net on s, the
+    online net on s' and the target net on s'; action int[B,1]; value f32[B,1] (stored n-step value); terminal
+    bool[B,1]; discount_n = discount ** reward_future_steps; is_weight f64[B].  Returns target_dist f32[B, N],
+    loss_row f32[B], abs_error f32[B] (= |loss_row| + 1e-6), loss_elem f64[B] (its mean is the reference's scalar loss)
+    and, if ``want_grad``, grad_q = d loss / d q_dist."""
+    q_dist, next_q_dist, target_next_q_dist = (_c(x, t.float32) for x in (q_dist, next_q_dist, target_next_q_dist))
+    B, A, N = q_dist.shape
+    if next_q_dist.shape != q_dist.shape or target_next_q_dist.shape != q_dist.shape:
+        raise ValueError("the three value distributions must have the same [batch, action_num, atom_num] shape")
+    dev = q_dist.device
+    action, value, term = _c(action, t.int64), _c(value, t.float32), _u8(terminal)
+    isw = _c(is_weight, t.float64)
+    sup = value_support(v_min, v_max, N, dev)
+    out = {"target_dist": t.empty((B, N), dtype=t.float32, device=dev), "loss_row": t.empty(B, dtype=t.float32, device=dev),
+           "abs_error": t.empty(B, dtype=t.float32, device=dev), "loss_elem": t.empty(B, dtype=t.float64, device=dev),
+           "grad_q": t.empty((B, A, N), dtype=t.float32, device=dev) if want_grad else None}
+    with t.cuda.device(dev):
+        _lib.check(lib.mb_td_rainbow(_lib.ptr(q_dist), _lib.ptr(next_q_dist), _lib.ptr(target_next_q_dist), B, A, N,
+                                     _lib.ptr(sup), _lib.ptr(action), _lib.ptr(value), _lib.ptr(term), _lib.ptr(isw),
+                                     float(v_min), float(v_max), float(discount_n), _lib.ptr(out["target_dist"]),
+                                     _lib.ptr(out["loss_row"]), _lib.ptr(out["abs_error"]), _lib.ptr(out["loss_elem"]),
+                                     _lib.ptr(out["grad_q"]), _lib.stream_ptr()))
+    return out
+
+
 def td_target(next_value, reward, terminal, discount: float, value=None) -> Dict[str, t.Tensor]:
     """y = reward + discount * ~terminal * next_value (ddpg.py:506-510); abs_error = |value - y|."""
     next_value, reward = _c(next_value, t.float32), _c(reward, t.float32)

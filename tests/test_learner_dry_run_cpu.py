@@ -329,3 +329,36 @@ def test_ddpg_apex_update_dry_run(monkeypatch):
     called = {name for name, _ in rec.calls}
     assert {"mb_per_sample", "mb_rows_pack_meta", "mb_rows_unpack_meta", "mb_td_target", "mb_tree_update_priority",
             "mb_adam_step_multi", "mb_soft_update_multi"} <= called, sorted(called)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_rainbow_update_dry_run(graph, monkeypatch):
+    """RAINBOW (rainbow.py mirror): n-step store, the captured / eager update with the categorical value block, acting."""
+    import machin_b200.frame.algorithms.rainbow as rb_mod
+    import machin_b200.model as model_mod
+    rec = _dry_run_patches(monkeypatch)
+    S, A, ATOMS, B, N = 5, 3, 11, 8, 100
+
+    class DistQ(t.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = t.nn.Linear(S, A * ATOMS)
+
+        def forward(self, state):
+            return t.softmax(self.fc(state).view(-1, A, ATOMS), dim=-1)
+
+    learner = rb_mod.RAINBOW(DistQ(), DistQ(), model_mod.FusedAdam, -2.0, 3.0, batch_size=B, reward_future_steps=3,
+                             replay_buffer=_per_double(N))
+    for n in (1, 2, 7, 30):
+        learner.store_episode([dict(state={"state": t.randn(1, S)}, action={"action": t.tensor([[i % A]])},
+                                    next_state={"state": t.randn(1, S)}, reward=float(i % 3), terminal=(i == n - 1))
+                               for i in range(n)])
+    assert "value" in learner.replay_buffer.storage.fields
+    if graph:
+        learner.enable_cuda_graph()
+    for _ in range(3):
+        assert learner.update_device().shape == ()
+    assert learner.act_discrete({"state": t.randn(4, S)}).shape == (4, 1)
+    called = {name for name, _ in rec.calls}
+    assert {"mb_per_sample", "mb_td_rainbow", "mb_tree_update_priority", "mb_adam_step_multi", "mb_soft_update_multi"} <= called
+    assert "mb_td_dqn" not in called

@@ -185,3 +185,72 @@ def test_emulated_kernel_matches_oracle(emul, B, A, N, v_min, v_max):
     # without IS weights: all ones
     out1 = run_kernel(emul, qd, nq, tq, action, value, terminal, None, v_min, v_max, disc_n)
     np.testing.assert_allclose(out1["loss_elem"].mean(), orb.weighted_loss(rows, np.ones(B)), rtol=1e-6)
+
+
+# ------------------------------------------------------------------ the learner class over host-memory doubles
+def _emulated_td_rainbow(lib):
+    def td_rainbow(q_dist, next_q_dist, target_next_q_dist, action, value, terminal, v_min, v_max, discount_n,
+                   is_weight=None, want_grad=False):
+        out = run_kernel(lib, q_dist.detach().numpy(), next_q_dist.numpy(), target_next_q_dist.numpy(), action.numpy(),
+                         value.numpy(), terminal.numpy(), None if is_weight is None else is_weight.numpy(), v_min, v_max,
+                         discount_n)
+        return {k: t.from_numpy(v) for k, v in out.items()}
+    return td_rainbow
+
+
+def test_rainbow_learner_over_doubles_vs_reference(emul, ref, monkeypatch):
+    """Whole RAINBOW.store_episode / update() / act_discrete through the product's class -- ring and tree as host-memory
+    doubles, the value block as the kernel's device source compiled for the host -- against the unmodified reference:
+    n-step values, sampled slots, projected targets (bit for bit), losses, tree after the write-back, weights after
+    the SGD step and the soft target update, greedy actions."""
+    import machin_b200.frame.algorithms.dqn_per as dqn_mod
+    import machin_b200.frame.algorithms.rainbow as rb_mod
+    import machin_b200.frame.algorithms.utils as utils_mod
+    from fake_ring import make_cpu_prioritized
+    from machin_b200.frame.buffers import PrioritizedBuffer
+    from oracle import td as otd
+
+    class CpuPer(PrioritizedBuffer):
+        def update_priority(self, priorities, indexes, valid=None):     # device tensors in the product: host arrays here
+            to_np = lambda x: x.detach().numpy() if t.is_tensor(x) else x
+            return PrioritizedBuffer.update_priority(self, to_np(priorities), to_np(indexes))
+
+    z, cfg = ref
+    monkeypatch.setattr(rb_mod.ops, "td_rainbow", _emulated_td_rainbow(emul))
+    soft = lambda tgt, src, rate: otd.soft_update_(list(tgt.parameters()), list(src.parameters()), rate)
+    monkeypatch.setattr(dqn_mod, "soft_update", soft)
+    monkeypatch.setattr(utils_mod, "soft_update", soft)
+    S, A, N, B = cfg["S"], cfg["A"], cfg["N"], cfg["B"]
+    qnet, qtgt = DistQNet(S, A, N), DistQNet(S, A, N)
+    load_flat(qtgt, z["init_qt"])
+    rb = rb_mod.RAINBOW(qnet, qtgt, t.optim.SGD, cfg["VMIN"], cfg["VMAX"], batch_size=B, learning_rate=cfg["LR"],
+                        discount=cfg["DISC"], update_rate=cfg["TAU"], reward_future_steps=cfg["NSTEP"],
+                        replay_buffer=make_cpu_prioritized(CpuPer, 400))
+    assert np.array_equal(np.concatenate([p.detach().numpy().reshape(-1) for p in rb.qnet.parameters()]), z["init_q"])
+    o = 0
+    for n in z["lens"]:
+        ep = [dict(state={"state": t.from_numpy(z["state"][i:i + 1])}, action={"action": t.tensor([[int(z["action"][i])]])},
+                   next_state={"state": t.from_numpy(z["next_state"][i:i + 1])}, reward=float(z["reward"][i]),
+                   terminal=bool(z["terminal"][i])) for i in range(o, o + n)]
+        rb.store_episode(ep)
+        assert [tr["value"] for tr in ep] == list(z["value"][o:o + n])          # Python floats: bit-exact
+        o += n
+    assert np.array_equal(rb.replay_buffer.wt_tree.weights, z["tree0"])
+    flat = lambda net: np.concatenate([p.detach().numpy().reshape(-1) for p in net.parameters()])
+    np.random.seed(13)
+    for step in range(3):
+        loss = rb.update()
+        assert np.array_equal(rb.last_target_dist.numpy(), z[f"target_dist{step}"]), step
+        want = float(z[f"loss{step}"])
+        assert abs(loss - want) <= 1e-5 * abs(want), (step, loss, want)
+        np.testing.assert_allclose(rb.replay_buffer.wt_tree.weights, z[f"tree{step + 1}"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(flat(rb.qnet), z[f"q{step + 1}"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(flat(rb.qnet_target), z[f"qt{step + 1}"], rtol=1e-5, atol=1e-6)
+    probe = {"state": t.from_numpy(z["act_state"])}
+    assert np.array_equal(rb.act_discrete(probe).numpy(), z["act_online"])
+    assert np.array_equal(rb.act_discrete(probe, use_target=True).numpy(), z["act_target"])
+    # a tensor reward gives the same stored value (f32 arithmetic, as the reference would do with it)
+    ep = [dict(state={"state": t.zeros(1, S)}, action={"action": t.tensor([[0]])}, next_state={"state": t.zeros(1, S)},
+               reward=t.tensor([[0.5]]), terminal=i == 2) for i in range(3)]
+    rb.store_episode(ep)
+    assert isinstance(ep[0]["value"], float) and abs(ep[0]["value"] - (0.5 + 0.9 * (0.5 + 0.9 * 0.5))) < 1e-6
