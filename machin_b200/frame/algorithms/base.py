@@ -1,37 +1,31 @@
-"""Minimal TorchFramework base (machin/frame/algorithms/base.py:11-184): model registry + save/load."""
+"""Minimal TorchFramework base (surface of machin/frame/algorithms/base.py:11-184): the model registry the
+algorithms declare through ``_is_top`` / ``_is_restorable``, a replaceable backward function, and save / load of the
+restorable models as ``<name>_<version>.pt`` files.  Visualisation is a no-op here."""
 import os
+import re
 from typing import Callable, Dict
 
 import torch as t
 
 
+def _abstract(what):
+    def getter(self):
+        raise NotImplementedError(f"{type(self).__name__} must define {what}")
+    return property(getter)
+
+
 class TorchFramework:
-    _is_top = []
-    _is_restorable = []
+    _is_top = []          # attribute names of the models a user passes in
+    _is_restorable = []   # attribute names of the models save() / load() cover
+
+    optimizers = _abstract("optimizers")
+    lr_schedulers = _abstract("lr_schedulers")
+    top_models = property(lambda self: [getattr(self, name) for name in self._is_top])
+    restorable_models = property(lambda self: [getattr(self, name) for name in self._is_restorable])
+    backward_function = property(lambda self: self._backward)
 
     def __init__(self):
-        self._backward = t.autograd.backward
-        self._visualized = set()
-
-    @property
-    def optimizers(self):
-        raise NotImplementedError
-
-    @property
-    def lr_schedulers(self):
-        raise NotImplementedError
-
-    @property
-    def top_models(self):
-        return [getattr(self, m) for m in self._is_top]
-
-    @property
-    def restorable_models(self):
-        return [getattr(self, m) for m in self._is_restorable]
-
-    @property
-    def backward_function(self):
-        return self._backward
+        self._backward, self._visualized = t.autograd.backward, set()
 
     @classmethod
     def get_top_model_names(cls):
@@ -46,29 +40,33 @@ class TorchFramework:
         return False
 
     def set_backward_function(self, backward_func: Callable):
-        assert callable(backward_func), "Backward function must be callable."
+        if not callable(backward_func):
+            raise AssertionError("Backward function must be callable.")
         self._backward = backward_func
 
+    @staticmethod
+    def _file_name(name, version):
+        return f"{name}_{version}.pt"
+
     def save(self, model_dir: str, network_map: Dict[str, str] = None, version: int = 0):
-        network_map = network_map or {}
         os.makedirs(model_dir, exist_ok=True)
-        for r in self._is_restorable:
-            t.save(getattr(self, r), os.path.join(model_dir, f"{network_map.get(r, r)}_{version}.pt"))
+        for attr in self._is_restorable:
+            name = (network_map or {}).get(attr, attr)
+            t.save(getattr(self, attr), os.path.join(model_dir, self._file_name(name, version)))
 
     def load(self, model_dir: str, network_map: Dict[str, str] = None, version: int = -1):
-        network_map = network_map or {}
-        for r in self._is_restorable:
-            name = network_map.get(r, r)
-            if version < 0:
-                found = [int(f[len(name) + 1:-3]) for f in os.listdir(model_dir)
-                         if f.startswith(name + "_") and f.endswith(".pt")]
-                if not found:
+        """``version`` < 0: the newest checkpoint of every model found in ``model_dir``."""
+        for attr in self._is_restorable:
+            name = (network_map or {}).get(attr, attr)
+            chosen = version
+            if chosen < 0:
+                pattern = re.compile(re.escape(name) + r"_(\d+)\.pt$")
+                versions = [int(m.group(1)) for m in map(pattern.match, os.listdir(model_dir)) if m]
+                if not versions:
                     raise RuntimeError(f"no checkpoint for {name} in {model_dir}")
-                v = max(found)
-            else:
-                v = version
-            loaded = t.load(os.path.join(model_dir, f"{name}_{v}.pt"), map_location="cpu", weights_only=False)
-            getattr(self, r).load_state_dict(loaded.state_dict() if hasattr(loaded, "state_dict") else loaded)
+                chosen = max(versions)
+            loaded = t.load(os.path.join(model_dir, self._file_name(name, chosen)), map_location="cpu", weights_only=False)
+            getattr(self, attr).load_state_dict(loaded.state_dict() if hasattr(loaded, "state_dict") else loaded)
 
     def visualize_model(self, *_, **__):
         pass

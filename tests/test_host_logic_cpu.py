@@ -96,3 +96,43 @@ def test_safe_call_routes_named_arguments():
     assert isinstance(out, tuple) and out[0].shape == (4, 1)
     with pytest.raises(RuntimeError, match="missing required arguments"):
         safe_call(net, {"state": t.zeros(4, 3)})
+
+
+def test_framework_base_registry_save_and_load(tmp_path):
+    """TorchFramework surface (machin/frame/algorithms/base.py:11-184): model registry, replaceable backward function,
+    save as <name>_<version>.pt, load a given version or the newest one, network_map renames."""
+    from machin_b200.frame.algorithms.base import TorchFramework
+
+    class Algo(TorchFramework):
+        _is_top = ["net", "net_target"]
+        _is_restorable = ["net_target"]
+
+        def __init__(self):
+            self.net, self.net_target = t.nn.Linear(3, 2), t.nn.Linear(3, 2)
+            super().__init__()
+
+    a = Algo()
+    assert Algo.get_top_model_names() == ["net", "net_target"] and Algo.get_restorable_model_names() == ["net_target"]
+    assert a.top_models == [a.net, a.net_target] and a.restorable_models == [a.net_target]
+    assert not Algo.is_distributed() and a.backward_function is t.autograd.backward
+    with pytest.raises(NotImplementedError):
+        a.optimizers
+    with pytest.raises(AssertionError, match="Backward function must be callable."):
+        a.set_backward_function(3)
+    marker = lambda *args, **kw: None
+    a.set_backward_function(marker)
+    assert a.backward_function is marker
+    a.save(str(tmp_path), version=2)
+    first = a.net_target.weight.detach().clone()
+    with t.no_grad():
+        a.net_target.weight.add_(1.0)
+    a.save(str(tmp_path), version=10)
+    a.save(str(tmp_path), network_map={"net_target": "renamed"}, version=1)
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["net_target_10.pt", "net_target_2.pt", "renamed_1.pt"]
+    b = Algo()
+    b.load(str(tmp_path), version=2)
+    assert t.equal(b.net_target.weight, first)
+    b.load(str(tmp_path))                                        # newest: 10, not the lexicographically larger "2"
+    assert t.equal(b.net_target.weight, first + 1.0)
+    with pytest.raises(RuntimeError, match="no checkpoint"):
+        b.load(str(tmp_path), network_map={"net_target": "missing"})
