@@ -87,49 +87,50 @@ class A2C(TorchFramework):
             episode, required_attrs=("state", "action", "next_state", "reward", "value", "gae", "terminal"))
 
     # ------------------------------------------------------------------ update (a2c.py:328-422)
+    def _draw(self, attrs, concatenate):
+        """One mini-batch of unique stored steps with the given attributes; the last one is the custom column."""
+        return self.replay_buffer.sample_batch(self.batch_size, sample_method="random_unique", concatenate=concatenate,
+                                               sample_attrs=attrs, additional_concat_custom_attrs=attrs[-1:])
+
+    def _descend(self, net, optim, loss):
+        net.zero_grad()
+        self._backward(loss)
+        nn.utils.clip_grad_norm_(net.parameters(), self.gradient_max)
+        optim.step()
+
+    def _policy_round(self, concatenate, apply):
+        n, (state, action, adv) = self._draw(["state", "action", "gae"], concatenate)
+        if self.normalize_advantage:
+            adv = (adv - adv.mean()) / (adv.std() + 1e-6)
+        evaluated = self._eval_act(state, action)
+        log_prob = evaluated[1].view(n, 1)
+        loss = -(log_prob * adv.type_as(log_prob))
+        if self.entropy_weight is not None and evaluated[2] is not None:
+            loss += self.entropy_weight * evaluated[2].mean()
+        loss = loss.mean()
+        if apply:
+            self._descend(self.actor, self.actor_optim, loss)
+        return loss.item()
+
+    def _value_round(self, concatenate, apply):
+        _, (state, target) = self._draw(["state", "value"], concatenate)
+        predicted = self._criticize(state)
+        loss = self.criterion(target.type_as(predicted), predicted) * self.value_weight
+        if apply:
+            self._descend(self.critic, self.critic_optim, loss)
+        return loss.item()
+
     def update(self, update_value=True, update_policy=True, concatenate_samples=True, **__):
-        sum_act_loss = 0
-        sum_value_loss = 0
-        self.actor.train()
-        self.critic.train()
-        for _ in range(self.actor_update_times):
-            batch_size, (state, action, advantage) = self.replay_buffer.sample_batch(
-                self.batch_size, sample_method="random_unique", concatenate=concatenate_samples,
-                sample_attrs=["state", "action", "gae"], additional_concat_custom_attrs=["gae"])
-            if self.normalize_advantage:
-                advantage = (advantage - advantage.mean()) / (advantage.std() + 1e-6)
-            if self.entropy_weight is not None:
-                __, action_log_prob, new_action_entropy, *_ = self._eval_act(state, action)
-            else:
-                __, action_log_prob, *_ = self._eval_act(state, action)
-                new_action_entropy = None
-            action_log_prob = action_log_prob.view(batch_size, 1)
-            act_policy_loss = -(action_log_prob * advantage.type_as(action_log_prob))
-            if new_action_entropy is not None:
-                act_policy_loss += self.entropy_weight * new_action_entropy.mean()
-            act_policy_loss = act_policy_loss.mean()
-            sum_act_loss += act_policy_loss.item()
-            if update_policy:
-                self.actor.zero_grad()
-                self._backward(act_policy_loss)
-                nn.utils.clip_grad_norm_(self.actor.parameters(), self.gradient_max)
-                self.actor_optim.step()
-        for _ in range(self.critic_update_times):
-            batch_size, (state, target_value) = self.replay_buffer.sample_batch(
-                self.batch_size, sample_method="random_unique", concatenate=concatenate_samples,
-                sample_attrs=["state", "value"], additional_concat_custom_attrs=["value"])
-            value = self._criticize(state)
-            value_loss = self.criterion(target_value.type_as(value), value) * self.value_weight
-            sum_value_loss += value_loss.item()
-            if update_value:
-                self.critic.zero_grad()
-                self._backward(value_loss)
-                nn.utils.clip_grad_norm_(self.critic.parameters(), self.gradient_max)
-                self.critic_optim.step()
+        """``actor_update_times`` policy rounds, then ``critic_update_times`` value rounds, each on its own mini-batch;
+        the buffer is cleared afterwards (on-policy).  Returns (mean policy objective, mean value loss)."""
+        for net in (self.actor, self.critic):
+            net.train()
+        policy = sum(self._policy_round(concatenate_samples, update_policy) for _ in range(self.actor_update_times))
+        value = sum(self._value_round(concatenate_samples, update_value) for _ in range(self.critic_update_times))
         self.replay_buffer.clear()
-        self.actor.eval()
-        self.critic.eval()
-        return -sum_act_loss / self.actor_update_times, sum_value_loss / self.critic_update_times
+        for net in (self.actor, self.critic):
+            net.eval()
+        return -policy / self.actor_update_times, value / self.critic_update_times
 
     def update_lr_scheduler(self):
         if hasattr(self, "actor_lr_sch"):
