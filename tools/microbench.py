@@ -174,6 +174,18 @@ def main():  # noqa: C901
         s = graphed([fn] * 8) if nb < 1e5 else timed(fn, reps=5)
         byt = 137 * nb
         R[f"td_dqn_{nb}"] = {"us": s * 1e6, "alg_bytes": byt, "GBps": byt / s / 1e9, "frac": byt / s / 1e9 / PEAK}
+    # ---- RAINBOW value block (written after round 1's GPU budget: first numbers come from the next round)
+    for nb in (512, 1 << 18):
+        A, N = 6, 51
+        qd = [t.softmax(t.randn(nb, A, N, device=dev), dim=-1) for _ in range(3)]
+        a = t.randint(0, A, (nb, 1), device=dev)
+        val = t.randn(nb, 1, device=dev) * 5
+        te = t.rand(nb, 1, device=dev) < 0.1
+        w = t.rand(nb, dtype=t.float64, device=dev)
+        fn = lambda: ops.td_rainbow(qd[0], qd[1], qd[2], a, val, te, -10.0, 10.0, 0.99 ** 3, is_weight=w, want_grad=True)
+        s = graphed([fn] * 8) if nb < 1e5 else timed(fn, reps=5)
+        byt = (4 * A * N * 4 + N * 4 + 30) * nb
+        R[f"td_rainbow_{nb}"] = {"us": s * 1e6, "alg_bytes": byt, "GBps": byt / s / 1e9, "frac": byt / s / 1e9 / PEAK}
     out["env"] = {"force_generic": os.environ.get("MB_FORCE_GENERIC_UPDATE", "0"), "gpu": t.cuda.get_device_name(0)}
     print(json.dumps(out, indent=1))
 
