@@ -290,7 +290,7 @@ def time_kernels(learner, table, reps=20, per_graph=16):
     sp = lambda: _lib.stream_ptr()
 
     def k_sample(i):
-        _lib.check(lib.mb_per_sample(tree, _lib.ptr(table[i]), B, n_stored, 0.0, 0.4, None, _lib.ptr(idx[i]),
+        _lib.check(lib.mb_per_sample(tree, _lib.ptr(table[i % table.shape[0]]), B, n_stored, 0.0, 0.4, None, _lib.ptr(idx[i]),
                                      _lib.ptr(isw[i]), sp()))
 
     for i in range(per_graph):
@@ -348,6 +348,11 @@ def time_kernels(learner, table, reps=20, per_graph=16):
     return out
 
 
+def cuda_device(index):
+    import torch as t
+    return t.device("cuda", index)
+
+
 def run_b200(a):
     import torch as t
     import torch.distributed as dist
@@ -364,7 +369,7 @@ def run_b200(a):
     if not t.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     t.cuda.set_device(local)
-    device = t.device("cuda", local)
+    device = cuda_device(local)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: one JSON line only

@@ -1,0 +1,106 @@
+"""CPU: a DRY RUN of bench.py's B200 arm at N = 1 -- argument parsing, learner construction, the ring fill, graph
+capture, the device-timed loop, the end-to-end loop, the per-kernel timing harness and the JSON line -- with CUDA
+streams / events / graphs as no-op stand-ins, the ring and the tree as host-memory doubles and the library as the
+signature-checking recorder (tests/test_learner_dry_run_cpu.py).  No number means anything; what is checked is that
+every Python line of the arm executes and that the line carries the contract's keys, for the default flags and for
+the opt-in variants the next GPU session will time."""
+import contextlib
+import importlib.util
+import json
+import os
+import sys
+
+import pytest
+import torch as t
+
+from conftest import ROOT
+from fake_ring import make_cpu_buffer
+from test_learner_dry_run_cpu import _Ring, _Tree, _dry_run_patches
+
+
+class _BenchTree(_Tree):
+    depth = property(lambda self: self.ora.depth)
+
+    def check(self):
+        pass
+
+
+class _BenchRing(_Ring):
+    """(bench.py's per-kernel timing harness builds the gather descriptor itself)"""
+    from machin_b200.frame.buffers.device_ring import DeviceRing
+    _field_array = DeviceRing._field_array
+    del DeviceRing
+
+
+class _TimedEvent:
+    def __init__(self, enable_timing=False):
+        pass
+
+    def record(self, stream=None):
+        pass
+
+    def synchronize(self):
+        pass
+
+    def elapsed_time(self, other):
+        return 1.0
+
+
+def _load_bench():
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("flags", [[], ["--no-graph"], ["--net", "fused"], ["--net", "fused-rows", "--overlap-update", "--fuse-optimizer"],
+                                   ["--parallel-forwards", "--overlap-update"], ["--adam", "torch"]])
+def test_b200_arm_dry_run(flags, monkeypatch):
+    import machin_b200.frame.buffers as buffers_mod
+    bench = _load_bench()
+    rec = _dry_run_patches(monkeypatch)
+    monkeypatch.setattr(bench, "cuda_device", lambda index: t.device("cpu", index))
+    monkeypatch.setattr(t.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(t.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(t.cuda, "Event", _TimedEvent)
+    monkeypatch.setattr(t.cuda, "empty_cache", lambda: None)
+    monkeypatch.setattr(t.cuda, "is_current_stream_capturing", lambda: False)
+    monkeypatch.setattr(t.nn.Module, "cuda", lambda self, device=None: self)
+    real_per = buffers_mod.PrioritizedBuffer
+
+    def per_double(buffer_size, buffer_device):
+        buf = make_cpu_buffer(real_per, buffer_size, epsilon=1e-2, alpha=0.6, beta=0.4, curr_beta=0.4,
+                              beta_increment_per_sampling=1e-3, wt_tree=_BenchTree(buffer_size))
+        buf.storage = _BenchRing(buffer_size)
+        buf.buffer_device = buffer_device
+        return buf
+
+    monkeypatch.setattr(buffers_mod, "PrioritizedBuffer", per_double)
+    written = []
+
+    class OsProxy:                                       # bench.py keeps a private handle to fd 1 and points fd 1 at stderr:
+        dup = staticmethod(lambda fd: 99)                # not under pytest's own capture
+        dup2 = staticmethod(lambda a, b: None)
+        write = staticmethod(lambda fd, data: written.append(data) if fd == 99 else os.write(fd, data))
+
+        def __getattr__(self, name):
+            return getattr(os, name)
+
+    monkeypatch.setattr(bench, "os", OsProxy())
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "3", "--warmup", "1", "--replay-rows", "3000", "--batch", "16",
+                                      "--no-cpu-baseline", *flags])
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    bench.run_b200(bench.parse())
+    assert len(written) == 1
+    line = json.loads(written[0].decode())
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 3 and line["warmup"] == 3 and line["vs_baseline"] is None
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert line["e2e"]["h2d_bytes_per_step"] == 8 * 16 and "workload" in line["config"]
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    called = {name for name, _ in rec.calls}
+    assert "mb_per_sample" in called and "mb_tree_update_priority" in called
