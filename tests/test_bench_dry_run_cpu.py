@@ -104,3 +104,109 @@ def test_b200_arm_dry_run(flags, monkeypatch):
     assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     called = {name for name, _ in rec.calls}
     assert "mb_per_sample" in called and "mb_tree_update_priority" in called
+
+
+class _Left(Exception):
+    """bench.py left through os._exit (what the fixed-shape run does instead of the NCCL teardown)."""
+
+
+@pytest.mark.parametrize("case", ["static", "dynamic", "static_capture_fails"])
+def test_b200_arm_dry_run_two_ranks(case, monkeypatch):
+    """The N > 1 arm as rank 0 of a 2-process job: process-group calls are no-ops and the shard group is a group of
+    one, so the exchange moves nothing -- but bench.py's own N > 1 code (learner construction, the fixed-shape default,
+    the fall-back to the dynamic exchange when the capture raises, push_weights in the loop, the max-over-ranks
+    reduction, leaving without the teardown) executes line by line."""
+    import torch.distributed as dist
+    import machin_b200.frame.algorithms.apex as apex_mod
+    import machin_b200.parallel as parallel_mod
+    from machin_b200.frame.buffers import DistributedPrioritizedBuffer
+    from threading import RLock
+    bench = _load_bench()
+    rec = _dry_run_patches(monkeypatch)
+    dev = t.device("cpu", 0)
+    monkeypatch.setattr(bench, "cuda_device", lambda index: dev)
+    monkeypatch.setattr(t.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(t.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(t.cuda, "Event", _TimedEvent)
+    monkeypatch.setattr(t.cuda, "empty_cache", lambda: None)
+    monkeypatch.setattr(t.cuda, "is_current_stream_capturing", lambda: False)
+    monkeypatch.setattr(t.nn.Module, "cuda", lambda self, device=None: self)
+    for name in ("init_process_group", "barrier", "destroy_process_group", "all_reduce"):
+        monkeypatch.setattr(dist, name, lambda *a, **k: None)
+
+    def group_of_one(name, device=None):
+        g = parallel_mod.LocalGroup(name, device="cpu")
+        g.device = dev
+        return g
+
+    monkeypatch.setattr(parallel_mod, "ShardGroup", group_of_one)
+
+    def buffer_double(buffer_name, group, buffer_size, requesters=None, **kw):
+        buf = make_cpu_buffer(DistributedPrioritizedBuffer, buffer_size, epsilon=1e-2, alpha=0.6, beta=0.4, curr_beta=0.4,
+                              beta_increment_per_sampling=1e-3, wt_tree=_BenchTree(buffer_size), buffer_name=buffer_name,
+                              group=group, wr_lock=RLock(), _requesters=requesters, _sampler=None,
+                              buffer_version_table=t.zeros(buffer_size, dtype=t.int64))
+        buf.storage = _BenchRing(buffer_size)
+        buf.buffer_device = dev
+        buf.weight_sum_tensor = lambda: t.tensor([max(buf.wt_tree.get_weight_sum(), 1.0)], dtype=t.float64)
+        return buf
+
+    monkeypatch.setattr(apex_mod, "DistributedPrioritizedBuffer", buffer_double)
+    if case == "static_capture_fails":
+        real_enable, calls = apex_mod.DQNApex.enable_cuda_graph, []
+
+        def enable(self, warmup=3, static_exchange=False, device_apportion=False):
+            calls.append(static_exchange)
+            if static_exchange:
+                raise RuntimeError("capture refused (injected)")
+            return real_enable(self, warmup)
+
+        monkeypatch.setattr(apex_mod.DQNApex, "enable_cuda_graph", enable)
+    written, left = [], []
+
+    class OsProxy:
+        dup = staticmethod(lambda fd: 99)
+        dup2 = staticmethod(lambda a, b: None)
+        write = staticmethod(lambda fd, data: written.append(data) if fd == 99 else os.write(fd, data))
+
+        @staticmethod
+        def _exit(code):
+            left.append(code)
+            raise _Left()
+
+        def __getattr__(self, name):
+            return getattr(os, name)
+
+    monkeypatch.setattr(bench, "os", OsProxy())
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", "2", "--steps", "3", "--warmup", "1", "--replay-rows", "3000",
+                                      "--batch", "16", "--watchdog-s", "600",
+                                      *(["--dynamic-exchange"] if case == "dynamic" else [])])
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("LOCAL_RANK", "0")
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    import threading
+    timers = []
+    real_timer = threading.Timer
+    monkeypatch.setattr(threading, "Timer", lambda *a, **k: timers.append(real_timer(*a, **k)) or timers[-1])
+    try:
+        if case == "dynamic":
+            bench.run_b200(bench.parse())                       # leaves through destroy_process_group (a no-op here)
+        else:
+            with pytest.raises(_Left):
+                bench.run_b200(bench.parse())
+            assert left == [0]
+    finally:
+        for tm in timers:
+            tm.cancel()                                         # the watchdog must not outlive the test
+    assert len(written) == 1
+    line = json.loads(written[0].decode())
+    assert line["n_gpus"] == 2 and line["cpu_baseline"] is None
+    launch = line["config"]["launch"]
+    if case == "static":
+        assert launch == "one CUDA graph per update"
+    else:
+        assert launch.startswith("two CUDA graphs")
+    if case == "static_capture_fails":
+        assert calls == [True, False]
+    called = {name for name, _ in rec.calls}
+    assert ("mb_wire_compact" in called) == (case == "static")
