@@ -32,3 +32,28 @@ def test_every_referenced_library_symbol_exists():
             if not hasattr(_lib, name):
                 missing.append((os.path.relpath(f, ROOT), "_lib." + name))
     assert not missing, missing
+
+
+def test_every_library_call_has_the_declared_number_of_arguments():
+    """Static arity check of every `lib.mb_*(...)` / `create(...)`-style direct call in the Python sources against the
+    ctypes signatures (calls with *args are skipped): tools/ and the GPU-only branches get this without running."""
+    import ast
+    import glob
+    from machin_b200 import _lib
+    files = [f for pat in ("machin_b200/**/*.py", "tools/*.py", "tests/*.py", "bench.py", "__graft_entry__.py")
+             for f in glob.glob(os.path.join(ROOT, pat), recursive=True)]
+    wrong, seen = [], 0
+    for f in files:
+        for node in ast.walk(ast.parse(open(f).read())):
+            if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute)):
+                continue
+            name = node.func.attr
+            if not name.startswith("mb_") or name not in _lib.SIGNATURES or node.keywords:
+                continue
+            if any(isinstance(a, ast.Starred) for a in node.args):
+                continue
+            seen += 1
+            want = len(_lib.SIGNATURES[name][1])
+            if len(node.args) != want:
+                wrong.append((os.path.relpath(f, ROOT), node.lineno, name, len(node.args), want))
+    assert seen > 100 and not wrong, (seen, wrong)
