@@ -227,12 +227,14 @@ int mb_td_dqn(const float *d_q, const float *d_q_next, const float *d_q_tgt_next
  * b = (T_z - v_min) / delta_z; target_dist = the two index_add_ passes of :279-280 in element order (a target
  * exactly on an atom loses its mass, as in the reference); loss_row = -sum_k target_dist * log(q[b,action,k] + 1e-6);
  * abs_error = |loss_row| + 1e-6; loss_elem (float64): mean over the batch = the reference's scalar loss, i.e. the
- * mean of the [B, B] product of :303; d_grad_q = d loss / d q_dist.  n_atoms <= 256.  Outputs may be NULL. */
+ * mean of the [B, B] product of :303; d_grad_q = d loss / d q_dist.  d_weight_scale: NULL, or one device double
+ * = sum(is_weight) / batch^2 supplied by the caller (large batches; otherwise every row's CTA sums d_is_weight).
+ * n_atoms <= 256.  Outputs may be NULL. */
 int mb_td_rainbow(const float *d_q_dist, const float *d_next_q_dist, const float *d_target_next_q_dist, int64_t batch,
                   int n_actions, int n_atoms, const float *d_support, const int64_t *d_action, const float *d_value,
-                  const uint8_t *d_terminal, const double *d_is_weight, double v_min, double v_max, double discount_n,
-                  float *d_target_dist, float *d_loss_row, float *d_abs_error, double *d_loss_elem, float *d_grad_q,
-                  void *stream);
+                  const uint8_t *d_terminal, const double *d_is_weight, const double *d_weight_scale, double v_min,
+                  double v_max, double discount_n, float *d_target_dist, float *d_loss_row, float *d_abs_error,
+                  double *d_loss_elem, float *d_grad_q, void *stream);
 /* DDPGPer target + priority (ddpg_per.py:117-160, ddpg.py:506-510):
  *   y = reward + (discount * !terminal) * next_value ; abs_error = |value - y| (value nullable) */
 int mb_td_target(const float *d_next_value, const float *d_reward, const uint8_t *d_terminal,

@@ -83,7 +83,7 @@ SIGNATURES = {
     "mb_wire_update_mask": (i32, [vp, i32, i64, vp, i32, vp, i64, vp, vp, vp, vp]),
     "mb_td_dqn": (i32, [vp, vp, vp, i64, i32, vp, vp, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]),
     "mb_td_target": (i32, [vp, vp, vp, i64, f32, vp, vp, vp, vp]),
-    "mb_td_rainbow": (i32, [vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, f64, f64, f64, vp, vp, vp, vp, vp, vp]),
+    "mb_td_rainbow": (i32, [vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, f64, f64, f64, vp, vp, vp, vp, vp, vp]),
     "mb_soft_update": (i32, [vp, vp, i64, f64, vp]),
     "mb_soft_update_multi": (i32, [C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i32, f64, vp]),
     "mb_mlp_linear_forward": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, i64, vp, i32, vp]),

@@ -21,6 +21,8 @@ struct DistArgs {
     const float *value;          // [B] n-step value stored with the transition (:186-196)
     const uint8_t *terminal;     // [B]
     const double *isw;           // [B] or null (all ones)
+    const double *scale;         // null, or 1 value = sum_i is_weight_i / B^2 computed by the caller (large batches:
+                                 // otherwise EVERY row's CTA walks the whole is_weight vector)
     float lo, hi;                // clamp bounds: (float)(v_min + 1e-6), (float)(v_max - 1e-6)
     float vmin, delta_z;         // (float)v_min, (float)((v_max - v_min) / (N - 1.0))
     float gamma_n;               // (float)(discount ** reward_future_steps)
@@ -56,7 +58,13 @@ __global__ void __launch_bounds__(kDistThreads) td_dist_kernel(DistArgs t) {
     // sum_i is_weight_i / B^2: what the mean over the [B, B] product (:303) sends back to every row
     const double inv = 1.0 / ((double)t.batch * (double)t.batch);
     double part = 0.0;
-    for (int64_t i = tid; i < t.batch; i += kDistThreads) part += (t.isw ? t.isw[i] : 1.0) * inv;
+    if (t.scale) {
+        if (tid == 0) part = *t.scale;
+    } else if (!t.isw) {
+        if (tid == 0) part = (double)t.batch * inv;
+    } else {
+        for (int64_t i = tid; i < t.batch; i += kDistThreads) part += t.isw[i] * inv;
+    }
     s_part[tid] = part;
     __syncthreads();
     if (tid == 0) {

@@ -74,16 +74,16 @@ int mb_td_dqn(const float *d_q, const float *d_q_next, const float *d_q_tgt_next
 
 int mb_td_rainbow(const float *d_q_dist, const float *d_next_q_dist, const float *d_target_next_q_dist, int64_t batch,
                   int n_actions, int n_atoms, const float *d_support, const int64_t *d_action, const float *d_value,
-                  const uint8_t *d_terminal, const double *d_is_weight, double v_min, double v_max, double discount_n,
-                  float *d_target_dist, float *d_loss_row, float *d_abs_error, double *d_loss_elem, float *d_grad_q,
-                  void *stream) {
+                  const uint8_t *d_terminal, const double *d_is_weight, const double *d_weight_scale, double v_min,
+                  double v_max, double discount_n, float *d_target_dist, float *d_loss_row, float *d_abs_error,
+                  double *d_loss_elem, float *d_grad_q, void *stream) {
     if (batch < 0 || n_actions < 1 || n_atoms < 2 || n_atoms > kDistMaxAtoms) return MB_ERR_INVALID;
     if (!d_q_dist || !d_next_q_dist || !d_target_next_q_dist || !d_support || !d_action || !d_value || !d_terminal)
         return MB_ERR_INVALID;
     if (batch == 0) return MB_OK;
     // the reference's Python doubles become float32 scalars where they meet a float32 tensor (rainbow.py:247-255)
     DistArgs a{d_q_dist, d_next_q_dist, d_target_next_q_dist, d_support, batch, n_actions, n_atoms, d_action, d_value,
-               d_terminal, d_is_weight, (float)(v_min + 1e-6), (float)(v_max - 1e-6), (float)v_min,
+               d_terminal, d_is_weight, d_weight_scale, (float)(v_min + 1e-6), (float)(v_max - 1e-6), (float)v_min,
                (float)((v_max - v_min) / ((double)n_atoms - 1.0)), (float)discount_n, d_target_dist, d_loss_row,
                d_abs_error, d_loss_elem, d_grad_q};
     td_dist_kernel<<<(unsigned)batch, kDistThreads, 0, (cudaStream_t)stream>>>(a);

@@ -82,13 +82,15 @@ def td_rainbow(q_dist, next_q_dist, target_next_q_dist, action, value, terminal,
     action, value, term = _c(action, t.int64), _c(value, t.float32), _u8(terminal)
     isw = _c(is_weight, t.float64)
     sup = value_support(v_min, v_max, N, dev)
+    # every row's CTA would walk the whole is_weight vector: beyond a few thousand rows, reduce it once up front
+    scale = (isw.sum() * (1.0 / (B * B))).view(1) if (isw is not None and B > 4096) else None
     out = {"target_dist": t.empty((B, N), dtype=t.float32, device=dev), "loss_row": t.empty(B, dtype=t.float32, device=dev),
            "abs_error": t.empty(B, dtype=t.float32, device=dev), "loss_elem": t.empty(B, dtype=t.float64, device=dev),
            "grad_q": t.empty((B, A, N), dtype=t.float32, device=dev) if want_grad else None}
     with t.cuda.device(dev):
         _lib.check(lib.mb_td_rainbow(_lib.ptr(q_dist), _lib.ptr(next_q_dist), _lib.ptr(target_next_q_dist), B, A, N,
                                      _lib.ptr(sup), _lib.ptr(action), _lib.ptr(value), _lib.ptr(term), _lib.ptr(isw),
-                                     float(v_min), float(v_max), float(discount_n), _lib.ptr(out["target_dist"]),
+                                     _lib.ptr(scale), float(v_min), float(v_max), float(discount_n), _lib.ptr(out["target_dist"]),
                                      _lib.ptr(out["loss_row"]), _lib.ptr(out["abs_error"]), _lib.ptr(out["loss_elem"]),
                                      _lib.ptr(out["grad_q"]), _lib.stream_ptr()))
     return out

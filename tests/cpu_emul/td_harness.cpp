@@ -22,10 +22,10 @@ inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 
 extern "C" int emul_td_rainbow(const float *q, const float *qn, const float *qtn, int64_t batch, int A, int N,
                                const float *support, const int64_t *action, const float *value, const uint8_t *terminal,
-                               const double *isw, double v_min, double v_max, double discount_n, float *target_dist,
+                               const double *isw, const double *scale, double v_min, double v_max, double discount_n, float *target_dist,
                                float *loss_row, float *abs_err, double *loss_elem, float *grad_q) {
     if (N < 2 || N > kDistMaxAtoms) return -1;
-    DistArgs a{q, qn, qtn, support, batch, A, N, action, value, terminal, isw, (float)(v_min + 1e-6), (float)(v_max - 1e-6),
+    DistArgs a{q, qn, qtn, support, batch, A, N, action, value, terminal, isw, scale, (float)(v_min + 1e-6), (float)(v_max - 1e-6),
                (float)v_min, (float)((v_max - v_min) / ((double)N - 1.0)), (float)discount_n, target_dist, loss_row, abs_err,
                loss_elem, grad_q};
     shim_launch((unsigned)batch, kDistThreads, [&] { td_dist_kernel(a); });

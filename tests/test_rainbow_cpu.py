@@ -122,7 +122,7 @@ def emul(tmp_path_factory):
     return C.CDLL(out)
 
 
-def run_kernel(lib, qd, nq, tq, action, value, terminal, isw, v_min, v_max, disc_n):
+def run_kernel(lib, qd, nq, tq, action, value, terminal, isw, v_min, v_max, disc_n, scale=None):
     B, A, N = qd.shape
     c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
     qd, nq, tq = c(qd, np.float32), c(nq, np.float32), c(tq, np.float32)
@@ -134,7 +134,7 @@ def run_kernel(lib, qd, nq, tq, action, value, terminal, isw, v_min, v_max, disc
                loss_elem=np.zeros(B, np.float64), grad_q=np.full((B, A, N), -7, np.float32))
     p = lambda a: C.c_void_p(0) if a is None else C.c_void_p(a.ctypes.data)
     rc = lib.emul_td_rainbow(p(qd), p(nq), p(tq), C.c_int64(B), A, N, p(sup), p(action), p(value), p(terminal), p(isw),
-                             C.c_double(v_min), C.c_double(v_max), C.c_double(disc_n), p(out["target_dist"]),
+                             p(None if scale is None else np.array([scale], dtype=np.float64)), C.c_double(v_min), C.c_double(v_max), C.c_double(disc_n), p(out["target_dist"]),
                              p(out["loss_row"]), p(out["abs_error"]), p(out["loss_elem"]), p(out["grad_q"]))
     assert rc == 0
     return out
@@ -182,6 +182,11 @@ def test_emulated_kernel_matches_oracle(emul, B, A, N, v_min, v_max):
     want = np.zeros((B, A, N), dtype=np.float32)
     want[np.arange(B), action] = orb.grad_q_sel(td, qd[np.arange(B), action], isw)
     np.testing.assert_allclose(out["grad_q"], want, rtol=2e-6, atol=1e-12)
+    # the caller may supply sum(is_weight) / B^2 (large batches): same outputs
+    out2 = run_kernel(emul, qd, nq, tq, action, value, terminal, isw, v_min, v_max, disc_n, scale=float(np.sum(isw) / (B * B)))
+    np.testing.assert_allclose(out2["loss_elem"], out["loss_elem"], rtol=1e-12)
+    np.testing.assert_allclose(out2["grad_q"], out["grad_q"], rtol=1e-6, atol=1e-12)
+    assert np.array_equal(out2["target_dist"], out["target_dist"])
     # without IS weights: all ones
     out1 = run_kernel(emul, qd, nq, tq, action, value, terminal, None, v_min, v_max, disc_n)
     np.testing.assert_allclose(out1["loss_elem"].mean(), orb.weighted_loss(rows, np.ones(B)), rtol=1e-6)
