@@ -39,7 +39,8 @@ def test_value_block_vs_reference_fixture(ref, step):  # noqa: F811
 
 
 @pytest.mark.parametrize("B,A,N,v_min,v_max", [(1, 1, 2, 0.0, 1.0), (7, 2, 51, -10.0, 10.0), (33, 18, 51, -10.0, 10.0),
-                                               (5, 200, 10, 0.0, 40.0), (3, 4, 256, -3.0, 5.0), (512, 6, 51, -10.0, 10.0)])
+                                               (5, 200, 10, 0.0, 40.0), (3, 4, 256, -3.0, 5.0), (512, 6, 51, -10.0, 10.0),
+                                               (4100, 2, 10, 0.0, 40.0)])   # > 4096 rows: sum(is_weight) reduced once up front
 def test_value_block_vs_oracle(B, A, N, v_min, v_max):
     rng = np.random.RandomState(B * 1000 + N)
     soft = lambda x: np.exp(x) / np.exp(x).sum(-1, keepdims=True)
