@@ -20,6 +20,7 @@ from .utils import model_device, safe_call
 
 
 class A2C(TorchFramework):
+    _config_frame, _config_kind = "A2C", "local"
     _is_top = ["actor", "critic"]
     _is_restorable = ["actor", "critic"]
 
@@ -152,6 +153,8 @@ class _NoStepOptimizer:
 
 
 class A3C(A2C):
+    _config_frame, _config_kind = "A3C", "a3c"
+
     def __init__(self, actor: nn.Module, critic: nn.Module, criterion: Callable, grad_server: Tuple, *_,
                  batch_size: int = 100, actor_update_times: int = 5, critic_update_times: int = 10,
                  entropy_weight: float = None, value_weight: float = 0.5, gradient_max: float = np.inf,

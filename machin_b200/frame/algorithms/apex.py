@@ -44,6 +44,8 @@ def _flat_grad_all_reduce(params, group, flat=None):
 
 
 class DQNApex(DQNPer):
+    _config_frame, _config_kind = "DQNApex", "apex"
+
     def __init__(self, qnet: nn.Module, qnet_target: nn.Module, optimizer: Callable, criterion: Callable,
                  apex_group, model_server: Tuple, *_, lr_scheduler: Callable = None, lr_scheduler_args=(),
                  lr_scheduler_kwargs=(), batch_size: int = 100, epsilon_decay: float = 0.9999,
@@ -470,6 +472,7 @@ from .ddpg_per import DDPGPer  # noqa: E402
 
 class DDPGApex(DDPGPer):
     """apex.py:256-532: DDPGPer over the sharded buffer; pushes the ACTOR after every update."""
+    _config_frame, _config_kind = "DDPGApex", "apex"
 
     def __init__(self, actor: nn.Module, actor_target: nn.Module, critic: nn.Module, critic_target: nn.Module,
                  optimizer: Callable, criterion: Callable, apex_group, model_server: Tuple, *_,

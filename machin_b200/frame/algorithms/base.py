@@ -24,8 +24,28 @@ class TorchFramework:
     restorable_models = property(lambda self: [getattr(self, name) for name in self._is_restorable])
     backward_function = property(lambda self: self._backward)
 
+    _config_frame = None  # key of config.DEFAULTS, and how init_from_config builds: "local", "apex", "impala", "a3c"
+    _config_kind = None
+
     def __init__(self):
         self._backward, self._visualized = t.autograd.backward, set()
+
+    @classmethod
+    def generate_config(cls, config):
+        """A copy of ``config`` with this framework's name and default ``frame_config`` (see config.py)."""
+        from .config import generate_config
+        return generate_config(cls._config_frame, config)
+
+    @classmethod
+    def init_from_config(cls, config, model_device="cuda"):
+        """Build the framework from a config: models / optimizer / criterion / lr_scheduler given as classes or names.
+        Collective for the distributed frameworks (every rank calls it)."""
+        from . import config as builders
+        if cls._config_kind == "local":
+            return builders.init_local(cls, config, model_device)
+        if cls._config_kind == "a3c":
+            return builders.init_a3c(cls, config, model_device)
+        return builders.init_sharded(cls, config, model_device, cls._config_kind)
 
     @classmethod
     def get_top_model_names(cls):

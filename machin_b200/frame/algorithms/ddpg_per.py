@@ -25,6 +25,7 @@ from .utils import hard_update, model_device, safe_call, soft_update
 
 
 class DDPGPer(TorchFramework):
+    _config_frame, _config_kind = "DDPGPer", "local"
     _is_top = ["actor", "critic", "actor_target", "critic_target"]
     _is_restorable = ["actor_target", "critic_target"]
 

@@ -23,6 +23,7 @@ from .utils import hard_update, model_device, safe_call, soft_update
 
 
 class DQNPer(TorchFramework):
+    _config_frame, _config_kind = "DQNPer", "local"
     _is_top = ["qnet", "qnet_target"]
     _is_restorable = ["qnet_target"]
 

@@ -21,6 +21,7 @@ from .utils import safe_call
 
 
 class IMPALA(TorchFramework):
+    _config_frame, _config_kind = "IMPALA", "impala"
     _is_top = ["actor", "critic"]
     _is_restorable = ["actor", "critic"]
 

@@ -31,6 +31,8 @@ class _NoCriterion:
 
 
 class RAINBOW(DQNPer):
+    _config_frame, _config_kind = "RAINBOW", "local"
+
     def __init__(self, qnet, qnet_target, optimizer: Callable, value_min, value_max, *_,
                  lr_scheduler: Callable = None, lr_scheduler_args: Tuple[Tuple] = None,
                  lr_scheduler_kwargs: Tuple[Dict] = None, batch_size: int = 100, epsilon_decay: float = 0.9999,

@@ -23,7 +23,7 @@ class ShardGroup:
         self.ranks = list(range(world)) if ranks is None else list(ranks)
         self.pg = None if ranks is None else dist.new_group(self.ranks)
         self.rank = dist.get_rank()
-        backend = dist.get_backend(self.pg)
+        backend = dist.get_backend()           # (of the default group: a rank outside ``ranks`` holds no handle to ask)
         self.device = device if device is not None else (
             t.device("cuda", t.cuda.current_device()) if backend == "nccl" else t.device("cpu"))
 

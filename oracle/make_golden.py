@@ -681,10 +681,24 @@ def gen_rainbow():
     np.savez_compressed(os.path.join(OUT, "ref_rainbow.npz"), **out)
 
 
+# --------------------------------------------------------------------------- default configs (generate_config)
+def gen_configs():
+    """What <Framework>.generate_config produces in the unmodified reference: from an empty config, and from one whose
+    frame_config already holds values (the defaults win, dqn.py:530-535)."""
+    import json
+    from machin.frame.algorithms import A2C, A3C, DDPGApex, DDPGPer, DQNApex, DQNPer, IMPALA, RAINBOW
+    out = {}
+    for cls in (DQNPer, DDPGPer, DQNApex, DDPGApex, IMPALA, A2C, A3C, RAINBOW):
+        out[cls.__name__] = {"empty": cls.generate_config({}),
+                             "prefilled": cls.generate_config({"frame_config": {"batch_size": 7, "my_own_key": 1}, "other": 2})}
+    with open(os.path.join(OUT, "ref_configs.json"), "w") as fh:
+        json.dump(out, fh, indent=1, sort_keys=True)            # (Infinity for gradient_max: json's own extension)
+
+
 if __name__ == "__main__":
     ref_shim.load()
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["tree", "per", "td", "vtrace", "gae", "buffer", "per_d", "rnn", "rainbow"]
+    which = sys.argv[1:] or ["tree", "per", "td", "vtrace", "gae", "buffer", "per_d", "rnn", "rainbow", "configs"]
     for name in which:
         globals()["gen_" + name]()
         print("wrote", name)
