@@ -63,6 +63,12 @@ for _ in range(2):
          "next_state": {"state": t.randn(4096, S, device=dev)}},
         {"reward": t.randn(4096, 1, device=dev), "terminal": t.rand(4096, 1, device=dev) < 0.01},
         priorities=t.rand(4096, device=dev, dtype=t.float64))
+# the RAINBOW value block at the learner batch (6 actions x 51 atoms)
+AT = 51
+dist = [t.softmax(t.randn(B, A, AT, device=dev), dim=-1) for _ in range(3)]
+for _ in range(2):
+    ops.td_rainbow(dist[0], dist[1], dist[2], t.randint(0, A, (B, 1), device=dev), t.randn(B, 1, device=dev) * 5, te[:B].view(B, 1),
+                   -10.0, 10.0, 0.99 ** 3, is_weight=t.rand(B, dtype=t.float64, device=dev), want_grad=True)
 t.cuda.synchronize()
 buf.wt_tree.check()
 print("done", counts.tolist())
