@@ -423,6 +423,18 @@ class DQNApex(DQNPer):
         buf.curr_beta = beta
         return n
 
+    def release_graphs(self):
+        """Collective-safe teardown helper: drop every captured graph of this learner (the fixed-shape one holds NCCL
+        collectives; torch.distributed's teardown was seen to block while it is alive, tools/nccl_graph_repro.py).
+        Later updates run the eager exchange.  Synchronise the device and pass a barrier first."""
+        for holder, keys in ((getattr(self, "_static", None), ("graph",)), (getattr(self, "_apex_graph", None), ("g1", "g2"))):
+            for key in keys if holder else ():
+                graph = holder.pop(key, None)
+                if graph is not None:
+                    graph.reset()
+        self._apex_graph = None
+        super().release_graphs()
+
     def update_device(self, update_value=True, update_target=True, uniform=None):
         if getattr(self, "_static", None) is not None and "graph" in self._static and update_value and update_target:
             self._static_prepare()

@@ -202,6 +202,12 @@ class DQNPer(TorchFramework):
         buf.sync_graph_params()
         t.cuda.synchronize(dev)
 
+    def release_graphs(self):
+        """Drop the captured update; later updates launch eagerly again.  The device must be idle (synchronise first)."""
+        graph, self._graph = self._graph, None
+        if graph is not None:
+            graph.reset()
+
     def update_device(self, update_value=True, update_target=True, uniform: t.Tensor = None) -> t.Tensor:
         """One learner update without any host synchronisation; returns the loss as a CUDA scalar."""
         if self._graph is not None and update_value and update_target:

@@ -47,8 +47,13 @@ class _Event:
 
 
 class _Graph:
+    released = 0
+
     def replay(self):
         pass
+
+    def reset(self):
+        type(self).released += 1
 
 
 class _Tree(FakeTree):
@@ -139,6 +144,10 @@ def test_fixed_shape_update_dry_run(variant, monkeypatch):
     for _ in range(3):
         loss = learner.update_device()
         assert loss.shape == ()
+    before, n_calls = _Graph.released, len(rec.calls)
+    learner.release_graphs()                    # afterwards: the eager exchange, launch by launch
+    assert _Graph.released - before == (2 if variant == "dynamic" else 1)
+    assert learner.update_device().shape == () and len(rec.calls) > n_calls
     called = {name for name, _ in rec.calls}
     want = {"mb_rows_pack_meta", "mb_tree_update_priority"}
     if variant == "dynamic":
@@ -207,6 +216,11 @@ def test_single_learner_update_dry_run(flags, graph, monkeypatch):
     for _ in range(3):
         loss = learner.update_device()
         assert loss.shape == ()
+    if graph:
+        before, n_calls = _Graph.released, len(rec.calls)
+        learner.release_graphs()
+        assert _Graph.released - before == 1 and learner._graph is None
+        assert learner.update_device().shape == () and len(rec.calls) > n_calls       # eager launches again
     called = {name for name, _ in rec.calls}
     want = {"mb_per_sample", "mb_tree_update_priority"}
     want |= {"mb_mlp_program_run_part"} if fused else {"mb_td_dqn"}
