@@ -110,8 +110,10 @@ class DDPGPer(TorchFramework):
         return {"action": raw_output_action}
 
     # ------------------------------------------------------------------ learner step (ddpg_per.py:92-185)
-    def _sample(self):
-        n, fields, d_index, d_isw = self.replay_buffer.sample_device(self.batch_size)
+    def _sample(self, uniform=None, use_device_params=False):
+        # (a sharded buffer's collective sample_device takes no uniforms: they are drawn per shard)
+        extra = {"uniform": uniform, "use_device_params": use_device_params} if (uniform is not None or use_device_params) else {}
+        n, fields, d_index, d_isw = self.replay_buffer.sample_device(self.batch_size, **extra)
         group = lambda attr: {f.key: fields[f.name] for f in self.replay_buffer.storage.fields.values()
                               if f.attr == attr and f.kind == "major"}
         return n, group("state"), group("action"), fields["reward"], group("next_state"), fields["terminal"], d_index, d_isw
@@ -119,10 +121,14 @@ class DDPGPer(TorchFramework):
     def _sync_grads(self, params):
         """Hook: gradient averaging across learner processes (see DDPGApex)."""
 
-    def update_device(self, update_value=True, update_policy=True, update_target=True):
+    def _clip(self, net):
+        if np.isfinite(self.gradient_max):     # with max_norm = inf the reference's clip multiplies by exactly 1.0
+            nn.utils.clip_grad_norm_(net.parameters(), self.gradient_max)
+
+    def _step(self, update_value, update_policy, update_target, uniform=None, use_device_params=False):
         self.actor.train()
         self.critic.train()
-        batch_size, state, action, reward, next_state, terminal, d_index, d_isw = self._sample()
+        batch_size, state, action, reward, next_state, terminal, d_index, d_isw = self._sample(uniform, use_device_params)
         others = {}
         with t.no_grad():
             next_action = self.action_transform_function(self._act(next_state, True), next_state, others)
@@ -135,7 +141,7 @@ class DDPGPer(TorchFramework):
             self.critic.zero_grad()
             self._backward(value_loss)
             self._sync_grads(list(self.critic.parameters()))
-            nn.utils.clip_grad_norm_(self.critic.parameters(), self.gradient_max)
+            self._clip(self.critic)
             self.critic_optim.step()
         cur_action = self.action_transform_function(self._act(state), state, others)
         act_value = self._criticize(state, cur_action)
@@ -146,7 +152,7 @@ class DDPGPer(TorchFramework):
             self.actor.zero_grad()
             self._backward(act_policy_loss)
             self._sync_grads(list(self.actor.parameters()))
-            nn.utils.clip_grad_norm_(self.actor.parameters(), self.gradient_max)
+            self._clip(self.actor)
             self.actor_optim.step()
         if update_target:
             if self.update_rate is not None:
@@ -160,6 +166,91 @@ class DDPGPer(TorchFramework):
         self.actor.eval()
         self.critic.eval()
         return -act_policy_loss, value_loss
+
+    # ---- CUDA graph: the whole update (draw, gather, 6 forwards, both backward passes, both optimizers, priority
+    # write-back, both soft updates) captured once and replayed; only the uniforms change.  Same protocol as DQNPer's.
+    def enable_cuda_graph(self, warmup: int = 3):
+        """Single-process prioritized buffer, soft target updates and capturable optimizers (SGD, or Adam / AdamW --
+        ``capturable`` is switched on here).  torch's capture protocol needs ``warmup`` real updates first: networks,
+        optimizer state, tree and beta are snapshotted before and restored in place after."""
+        if type(self.replay_buffer) is not PrioritizedBuffer or self.update_rate is None:
+            raise RuntimeError("DDPGPer.enable_cuda_graph needs a single-process PrioritizedBuffer and soft target updates")
+        buf = self.replay_buffer
+        dev = buf.buffer_device
+        nets = (self.actor, self.actor_target, self.critic, self.critic_target)
+        optims = (self.actor_optim, self.critic_optim)
+        tensors_of = lambda m: list(m.parameters()) + list(m.buffers())
+        saved_nets = [[x.detach().clone() for x in tensors_of(m)] for m in nets]
+        fresh = [len(o.state) == 0 for o in optims]
+        saved_optim = [{id(p): {k: (v.clone() if t.is_tensor(v) else v) for k, v in st.items()} for p, st in o.state.items()}
+                       for o in optims]
+        saved_tree, saved_beta = buf.wt_tree.snapshot(), buf.curr_beta
+        for o in optims:
+            for group in o.param_groups:
+                if "capturable" in group:
+                    group["capturable"] = True
+            for st in o.state.values():
+                if "step" in st and t.is_tensor(st["step"]) and not st["step"].is_cuda:
+                    st["step"] = st["step"].to(dev)
+        buf.enable_graph_params()
+        self._u_static = t.rand(self.batch_size, dtype=t.float64, device=dev)
+        self._u_pinned = t.empty(self.batch_size, dtype=t.float64).pin_memory()
+        self._u_pinned_np = self._u_pinned.numpy()
+        self._h2d_done = t.cuda.Event()
+        cur, side = t.cuda.current_stream(dev), t.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with t.cuda.stream(side):
+            for _ in range(warmup):
+                self._step(True, True, True, self._u_static, True)
+                self._u_static.uniform_()
+        cur.wait_stream(side)
+        t.cuda.synchronize(dev)
+        for o in optims:
+            o.zero_grad(set_to_none=True)
+        from ..._lib import lib
+        graph = t.cuda.CUDAGraph()
+        launched = lib.mb_launch_count()
+        with t.cuda.graph(graph):
+            self._static_losses = self._step(True, True, True, self._u_static, True)
+        self._graph = graph
+        self.graph_launches = lib.mb_launch_count() - launched   # libmachin_b200 kernels per replay
+        with t.no_grad():
+            for m, saved in zip(nets, saved_nets):
+                for x, v in zip(tensors_of(m), saved):
+                    x.copy_(v)
+            for o, was_fresh, saved in zip(optims, fresh, saved_optim):
+                for p, st in o.state.items():
+                    for k, v in st.items():
+                        if t.is_tensor(v):
+                            if was_fresh:
+                                v.zero_()
+                            elif id(p) in saved:
+                                v.copy_(saved[id(p)][k])
+        buf.wt_tree.restore(saved_tree)
+        buf.curr_beta = saved_beta
+        buf.sync_graph_params()
+        t.cuda.synchronize(dev)
+
+    def release_graphs(self):
+        graph, self._graph = getattr(self, "_graph", None), None
+        if graph is not None:
+            graph.reset()
+
+    def update_device(self, update_value=True, update_policy=True, update_target=True, uniform: t.Tensor = None):
+        """One learner update without host synchronisation -> (policy value, value loss) as CUDA scalars."""
+        if getattr(self, "_graph", None) is not None and update_value and update_policy and update_target:
+            buf = self.replay_buffer
+            if uniform is None:
+                self._h2d_done.synchronize()
+                self._u_pinned_np[:] = np.random.uniform(size=self.batch_size)       # same stream as :411
+                self._u_static.copy_(self._u_pinned, non_blocking=True)
+                self._h2d_done.record()
+            else:
+                self._u_static.copy_(uniform)
+            self._graph.replay()
+            buf.curr_beta = np.float64(min(1.0, buf.curr_beta + buf.beta_increment_per_sampling))
+            return self._static_losses
+        return self._step(update_value, update_policy, update_target, uniform)
 
     def update(self, update_value=True, update_policy=True, update_target=True, concatenate_samples=True, **__):
         pol, val = self.update_device(update_value, update_policy, update_target)

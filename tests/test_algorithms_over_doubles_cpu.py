@@ -215,3 +215,52 @@ def test_dqn_per_update_over_doubles_vs_reference(criterion, td_lib, monkeypatch
         np.testing.assert_allclose(dqn.replay_buffer.wt_tree.weights, g[f"dqn_tree{step + 1}"], rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(_flat(dqn.qnet), g[f"dqn_q{step + 1}"], rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(_flat(dqn.qnet_target), g[f"dqn_qt{step + 1}"], rtol=1e-5, atol=1e-6)
+
+
+def test_ddpg_per_update_over_doubles_vs_reference(monkeypatch):
+    """Whole DDPGPer.update() over the ring / tree doubles against the unmodified reference (ref_td.npz;
+    ddpg_per.py:92-185): critic step on the IS-weighted loss, actor step through the updated critic, priorities from
+    Q(s, mu(s)) of the updated critic, both soft updates.  The target / |error| kernel (validated on the device) is
+    stood in for by its oracle restatement."""
+    import machin_b200.frame.algorithms.ddpg_per as ddpg_mod
+    import machin_b200.frame.algorithms.utils as utils_mod
+    from fake_ring import make_cpu_prioritized
+    from machin_b200.frame.buffers import PrioritizedBuffer
+    from oracle import td as otd
+    from test_gpu_algorithms import Actor, Critic, _flat, _load_flat
+
+    class CpuPer(PrioritizedBuffer):
+        def update_priority(self, priorities, indexes, valid=None):
+            to_np = lambda x: x.detach().numpy() if t.is_tensor(x) else x
+            return PrioritizedBuffer.update_priority(self, to_np(priorities), to_np(indexes))
+
+    def td_target(next_value, reward, terminal, discount, value=None):
+        y = otd.ddpg_target(next_value, reward, terminal, discount)
+        return {"y": y, "abs_error": None if value is None else otd.abs_error(value, y)}
+
+    monkeypatch.setattr(ddpg_mod.ops, "td_target", td_target)
+    soft = lambda tgt, src, rate: otd.soft_update_(list(tgt.parameters()), list(src.parameters()), rate)
+    monkeypatch.setattr(ddpg_mod, "soft_update", soft)
+    monkeypatch.setattr(utils_mod, "soft_update", soft)
+    g = np.load(os.path.join(GOLDEN, "ref_td.npz"))
+    S, A, N, B = 5, 2, 150, 16
+    actor, actor_t, critic, critic_t = Actor(S, A), Actor(S, A), Critic(S, A), Critic(S, A)
+    _load_flat(actor_t, g["ddpg_init_actor_t"])
+    _load_flat(critic_t, g["ddpg_init_critic_t"])
+    ddpg = ddpg_mod.DDPGPer(actor, actor_t, critic, critic_t, t.optim.SGD, t.nn.MSELoss(reduction="sum"), batch_size=B,
+                            actor_learning_rate=0.005, critic_learning_rate=0.01, discount=0.95, update_rate=0.1,
+                            replay_buffer=make_cpu_prioritized(CpuPer, N))
+    assert np.array_equal(_flat(ddpg.actor), g["ddpg_init_actor"]) and np.array_equal(_flat(ddpg.critic), g["ddpg_init_critic"])
+    ep = [dict(state={"state": t.from_numpy(g["ddpg_state"][i:i + 1])}, action={"action": t.from_numpy(g["ddpg_action"][i:i + 1])},
+               next_state={"state": t.from_numpy(g["ddpg_next_state"][i:i + 1])}, reward=float(g["ddpg_reward"][i]),
+               terminal=bool(g["ddpg_terminal"][i])) for i in range(N)]
+    ddpg.replay_buffer.store_episode(ep, priorities=list(g["ddpg_priority"]))
+    np.random.seed(12)
+    for step in range(3):
+        pol, val = ddpg.update()
+        ref_pol, ref_val = g[f"ddpg_loss{step}"]
+        assert abs(pol - ref_pol) <= 1e-5 * max(1.0, abs(ref_pol)) and abs(val - ref_val) <= 1e-5 * max(1.0, abs(ref_val))
+        np.testing.assert_allclose(ddpg.replay_buffer.wt_tree.weights, g[f"ddpg_tree{step + 1}"], rtol=1e-5, atol=1e-7)
+        for name, net in (("actor", ddpg.actor), ("critic", ddpg.critic), ("actor_t", ddpg.actor_target),
+                          ("critic_t", ddpg.critic_target)):
+            np.testing.assert_allclose(_flat(net), g[f"ddpg_{name}{step + 1}"], rtol=1e-5, atol=1e-6)

@@ -1,0 +1,46 @@
+"""GPU: DDPGPer's whole update captured as one CUDA graph reproduces the reference trajectory (ref_td.npz), like the
+eager update in tests/test_gpu_algorithms.py; enabling the graph leaves networks, tree and beta untouched; after
+release_graphs() the eager path continues the same trajectory."""
+import os
+
+import numpy as np
+import pytest
+import torch as t
+
+from conftest import GOLDEN, first_hardware_run_pending
+from test_gpu_algorithms import Actor, Critic, _flat, _load_flat
+
+pytestmark = [pytest.mark.gpu, first_hardware_run_pending]
+
+
+@pytest.mark.parametrize("release_after", [None, 1])
+def test_ddpg_per_captured_update_vs_reference(release_after):
+    from machin_b200.frame.algorithms import DDPGPer
+    g = np.load(os.path.join(GOLDEN, "ref_td.npz"))
+    S, A, N, B = 5, 2, 150, 16
+    actor, actor_t, critic, critic_t = Actor(S, A).cuda(), Actor(S, A).cuda(), Critic(S, A).cuda(), Critic(S, A).cuda()
+    _load_flat(actor_t, g["ddpg_init_actor_t"])
+    _load_flat(critic_t, g["ddpg_init_critic_t"])
+    ddpg = DDPGPer(actor, actor_t, critic, critic_t, t.optim.SGD, t.nn.MSELoss(reduction="sum"), batch_size=B,
+                   actor_learning_rate=0.005, critic_learning_rate=0.01, discount=0.95, update_rate=0.1, replay_size=N)
+    ep = [dict(state={"state": t.from_numpy(g["ddpg_state"][i:i + 1])}, action={"action": t.from_numpy(g["ddpg_action"][i:i + 1])},
+               next_state={"state": t.from_numpy(g["ddpg_next_state"][i:i + 1])}, reward=float(g["ddpg_reward"][i]),
+               terminal=bool(g["ddpg_terminal"][i])) for i in range(N)]
+    ddpg.replay_buffer.store_episode(ep, priorities=list(g["ddpg_priority"]))
+    tree0 = ddpg.replay_buffer.wt_tree.weights.copy()
+    ddpg.enable_cuda_graph()
+    assert np.array_equal(ddpg.replay_buffer.wt_tree.weights, tree0) and ddpg.replay_buffer.curr_beta == 0.4
+    assert np.array_equal(_flat(ddpg.actor), g["ddpg_init_actor"]) and np.array_equal(_flat(ddpg.critic), g["ddpg_init_critic"])
+    assert ddpg.graph_launches >= 6           # draw, gather, 2 x target, write-back, 2 x soft update
+    np.random.seed(12)
+    for step in range(3):
+        if release_after == step:
+            t.cuda.synchronize()
+            ddpg.release_graphs()
+        pol, val = ddpg.update()
+        ref_pol, ref_val = g[f"ddpg_loss{step}"]
+        assert abs(pol - ref_pol) <= 1e-5 * max(1.0, abs(ref_pol)) and abs(val - ref_val) <= 1e-5 * max(1.0, abs(ref_val))
+        np.testing.assert_allclose(ddpg.replay_buffer.wt_tree.weights, g[f"ddpg_tree{step + 1}"], rtol=1e-5, atol=1e-7)
+        for name, net in (("actor", ddpg.actor), ("critic", ddpg.critic), ("actor_t", ddpg.actor_target),
+                          ("critic_t", ddpg.critic_target)):
+            np.testing.assert_allclose(_flat(net), g[f"ddpg_{name}{step + 1}"], rtol=1e-5, atol=1e-6)

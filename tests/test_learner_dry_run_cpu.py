@@ -258,9 +258,12 @@ def _per_double(N):
     return buf
 
 
-def test_ddpg_per_update_dry_run(monkeypatch):
-    """DDPGPer.update (ddpg_per.py:92-185 mirror): actor / critic / two targets over the prioritized buffer double."""
+@pytest.mark.parametrize("mode", ["eager", "graph_sgd", "graph_fused_adam"])
+def test_ddpg_per_update_dry_run(mode, monkeypatch):
+    """DDPGPer.update (ddpg_per.py:92-185 mirror): actor / critic / two targets over the prioritized buffer double,
+    eager and with the whole update captured (then released again)."""
     import machin_b200.frame.algorithms.ddpg_per as ddpg_mod
+    import machin_b200.model as model_mod
     rec = _dry_run_patches(monkeypatch)
     S, A, B, N = 5, 2, 8, 100
 
@@ -280,14 +283,28 @@ def test_ddpg_per_update_dry_run(monkeypatch):
         def forward(self, state, action):
             return self.fc(t.cat([state, action], dim=1))
 
-    learner = ddpg_mod.DDPGPer(Actor(), Actor(), Critic(), Critic(), t.optim.SGD, t.nn.MSELoss(reduction="none"), batch_size=B,
+    optimizer = model_mod.FusedAdam if mode == "graph_fused_adam" else t.optim.SGD
+    learner = ddpg_mod.DDPGPer(Actor(), Actor(), Critic(), Critic(), optimizer, t.nn.MSELoss(reduction="none"), batch_size=B,
                                replay_buffer=_per_double(N))
     learner.replay_buffer.store_episode(
         [dict(state={"state": t.randn(1, S)}, action={"action": t.randn(1, A)}, next_state={"state": t.randn(1, S)},
               reward=float(i), terminal=(i == 29)) for i in range(30)], priorities=list(np.ones(30)))
+    if mode != "eager":
+        before = [p.detach().clone() for p in learner.actor.parameters()]
+        learner.enable_cuda_graph()
+        assert all(t.equal(a, b) for a, b in zip(before, learner.actor.parameters()))      # warm-up undone in place
+        assert learner.replay_buffer.curr_beta == 0.4
     for _ in range(2):
         out = learner.update()
         assert len(out) == 2 and all(np.isfinite(x) for x in out)
+    if mode != "eager":
+        assert learner.replay_buffer.curr_beta == pytest.approx(0.402)
+        learner.release_graphs()
+        assert learner._graph is None and len(learner.update()) == 2
+        with pytest.raises(RuntimeError, match="soft target updates"):
+            hard = ddpg_mod.DDPGPer(Actor(), Actor(), Critic(), Critic(), t.optim.SGD, t.nn.MSELoss(reduction="none"),
+                                    batch_size=B, update_rate=None, update_steps=5, replay_buffer=_per_double(N))
+            hard.enable_cuda_graph()
     called = {name for name, _ in rec.calls}
     assert {"mb_per_sample", "mb_td_target", "mb_tree_update_priority", "mb_soft_update_multi"} <= called, sorted(called)
 
