@@ -44,6 +44,8 @@ def main():
     p.add_argument("--batch", type=int, default=512)
     p.add_argument("--steps", type=int, default=200)
     p.add_argument("--warmup", type=int, default=10)
+    p.add_argument("--graph", action="store_true", help="one GPU only: DDPGPer over a single-process prioritized buffer with "
+                   "the whole update captured as one CUDA graph (DDPGPer.enable_cuda_graph)")
     a = p.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     t.cuda.set_device(local)
@@ -59,8 +61,14 @@ def main():
         group = LocalGroup(device=dev)
     t.manual_seed(0)                                    # identical initial weights on every learner
     nets = [Actor().to(dev), Actor().to(dev), Critic().to(dev), Critic().to(dev)]
-    learner = DDPGApex(*nets, FusedAdam, t.nn.MSELoss(reduction="none"), group, (), batch_size=a.batch, replay_size=a.rows,
-                       learner_group=group if world > 1 else None)
+    if a.graph:
+        if world != 1:
+            raise SystemExit("--graph is the single-GPU variant")
+        from machin_b200.frame.algorithms import DDPGPer
+        learner = DDPGPer(*nets, FusedAdam, t.nn.MSELoss(reduction="none"), batch_size=a.batch, replay_size=a.rows)
+    else:
+        learner = DDPGApex(*nets, FusedAdam, t.nn.MSELoss(reduction="none"), group, (), batch_size=a.batch, replay_size=a.rows,
+                           learner_group=group if world > 1 else None)
     gen = t.Generator(device=dev).manual_seed(rank)
     done = 0
     while done < a.rows:
@@ -80,6 +88,8 @@ def main():
             dist.barrier()
         t.cuda.synchronize(dev)
 
+    if a.graph:
+        learner.enable_cuda_graph()
     for _ in range(max(a.warmup, 3)):
         learner.update()
     barrier()
@@ -98,7 +108,8 @@ def main():
         print(json.dumps({"workload": f"C4 APEX-DDPG learner: PER {a.rows} rows per shard x (state {S}, act {A}), batch {a.batch}",
                           "n_gpus": world, "ms_per_update": ms_step, "updates_per_sec": 1e3 / ms_step,
                           "transitions_sampled_per_sec": world * a.batch * 1e3 / ms_step, "last": [float(x) for x in out],
-                          "launch": "eager (host-synchronous update(): loss read back every step)", "steps": a.steps}))
+                          "launch": ("one CUDA graph per update" if a.graph else "eager") + " (host-synchronous update(): loss read back every step)",
+                          "steps": a.steps}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -37,3 +37,8 @@ run fused_rows_cpt2    "MB_ROWS_CPT=2"        "--net fused-rows"
 run fuse_optimizer     "MB_X=0"               "--fuse-optimizer"
 run fused_rows_overlap "MB_X=0"               "--net fused-rows --overlap-update"
 run fused_rows_all     "MB_SORTED_CLUSTER=1 MB_SORTED_ASYNC=1"  "--net fused-rows --overlap-update --fuse-optimizer"
+# C4 (APEX-DDPG shapes) on one GPU: eager sharded learner on a group of one against DDPGPer with the update captured
+for v in "" "--graph"; do
+    timeout 200 python tools/ddpg_apex_bench.py --rows 2000000 --steps 300 $v 2> gpurun_out/next_ddpg.err | tee -a gpurun_out/next_ddpg.jsonl
+done
+timeout 300 python tools/microbench.py > gpurun_out/next_microbench.json 2> gpurun_out/next_microbench.err; tail -c 600 gpurun_out/next_microbench.json
