@@ -52,6 +52,7 @@ _A2C = {**_models("Actor", "Critic"), **_COMMON, "batch_size": 100, "actor_updat
         **_LOCAL_REPLAY, **_VISUAL}
 
 DEFAULTS: Dict[str, Dict[str, Any]] = {
+    "DQN": {**_DQN, **_LOCAL_REPLAY, "mode": "double", **_VISUAL},
     "DQNPer": {**_DQN, **_LOCAL_REPLAY, "mode": "double", **_VISUAL},
     "RAINBOW": {**_DQN, **_LOCAL_REPLAY, "mode": "double", **_VISUAL, "value_min": -1.0, "value_max": 1.0,
                 "reward_future_steps": 3},

@@ -686,19 +686,52 @@ def gen_configs():
     """What <Framework>.generate_config produces in the unmodified reference: from an empty config, and from one whose
     frame_config already holds values (the defaults win, dqn.py:530-535)."""
     import json
-    from machin.frame.algorithms import A2C, A3C, DDPGApex, DDPGPer, DQNApex, DQNPer, IMPALA, RAINBOW
+    from machin.frame.algorithms import A2C, A3C, DDPGApex, DDPGPer, DQN, DQNApex, DQNPer, IMPALA, RAINBOW
     out = {}
-    for cls in (DQNPer, DDPGPer, DQNApex, DDPGApex, IMPALA, A2C, A3C, RAINBOW):
+    for cls in (DQN, DQNPer, DDPGPer, DQNApex, DDPGApex, IMPALA, A2C, A3C, RAINBOW):
         out[cls.__name__] = {"empty": cls.generate_config({}),
                              "prefilled": cls.generate_config({"frame_config": {"batch_size": 7, "my_own_key": 1}, "other": 2})}
     with open(os.path.join(OUT, "ref_configs.json"), "w") as fh:
         json.dump(out, fh, indent=1, sort_keys=True)            # (Infinity for gradient_max: json's own extension)
 
 
+# --------------------------------------------------------------------------- DQN with uniform replay (BASELINE config C1)
+def gen_dqn():
+    """C1's shapes (CartPole: state 4, 2 actions, ring 10 000, batch 32) with synthetic transitions: five updates per
+    mode; uniform sampling consumes Python's random stream (buffer.py:234)."""
+    from machin.frame.algorithms import DQN
+    from machin.model.nets.base import static_module_wrapper as smw
+
+    out = {}
+    S, A, N, B = 4, 2, 300, 32
+    rng = np.random.RandomState(31)
+    st, nst = rng.randn(N, S).astype(np.float32), rng.randn(N, S).astype(np.float32)
+    act = rng.randint(0, A, size=N).astype(np.int64)
+    rew = rng.choice([0.0, 1.0], size=N)
+    term = rng.rand(N) < 0.05
+    out.update(state=st, next_state=nst, action=act, reward=rew, terminal=term)
+    for mode in ("vanilla", "fixed_target", "double"):
+        seed_all(0)
+        qnet, qtgt = _QNet(S, A), _QNet(S, A)
+        dqn = DQN(smw(qnet, "cpu", "cpu"), smw(qtgt, "cpu", "cpu"), t.optim.SGD, t.nn.MSELoss(), batch_size=B,
+                  learning_rate=0.2, discount=0.97, update_rate=0.1, replay_size=10000, mode=mode)
+        out[f"{mode}_init_q"], out[f"{mode}_init_qt"] = _flat_params(dqn.qnet), _flat_params(dqn.qnet_target)
+        ep = [dict(state={"state": t.from_numpy(st[i:i + 1])}, action={"action": t.tensor([[act[i]]])},
+                   next_state={"state": t.from_numpy(nst[i:i + 1])}, reward=float(rew[i]), terminal=bool(term[i]))
+              for i in range(N)]
+        for lo in range(0, N, 50):                      # six episodes of 50 steps
+            dqn.store_episode(ep[lo:lo + 50])
+        seed_all(17)
+        for step in range(5):
+            out[f"{mode}_loss{step}"] = np.float64(dqn.update())
+            out[f"{mode}_q{step + 1}"], out[f"{mode}_qt{step + 1}"] = _flat_params(dqn.qnet), _flat_params(dqn.qnet_target)
+    np.savez_compressed(os.path.join(OUT, "ref_dqn.npz"), **out)
+
+
 if __name__ == "__main__":
     ref_shim.load()
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["tree", "per", "td", "vtrace", "gae", "buffer", "per_d", "rnn", "rainbow", "configs"]
+    which = sys.argv[1:] or ["tree", "per", "td", "vtrace", "gae", "buffer", "per_d", "rnn", "rainbow", "configs", "dqn"]
     for name in which:
         globals()["gen_" + name]()
         print("wrote", name)

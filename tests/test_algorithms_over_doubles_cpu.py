@@ -157,7 +157,7 @@ def _emulated_td_dqn(lib):
         f = lambda x: None if x is None else np.ascontiguousarray(x.detach().numpy(), dtype=np.float32)
         qa, qn, qt = f(q), f(q_next), f(q_tgt_next)
         B, A = qt.shape
-        act = np.ascontiguousarray(action.numpy().reshape(-1), dtype=np.int64)
+        act = None if action is None else np.ascontiguousarray(action.numpy().reshape(-1), dtype=np.int64)
         rew = np.ascontiguousarray(reward.detach().numpy().reshape(-1), dtype=np.float32)
         term = np.ascontiguousarray(terminal.numpy().reshape(-1).astype(np.uint8))
         isw = None if is_weight is None else np.ascontiguousarray(is_weight.numpy().reshape(-1), dtype=np.float64)
@@ -264,3 +264,45 @@ def test_ddpg_per_update_over_doubles_vs_reference(monkeypatch):
         for name, net in (("actor", ddpg.actor), ("critic", ddpg.critic), ("actor_t", ddpg.actor_target),
                           ("critic_t", ddpg.critic_target)):
             np.testing.assert_allclose(_flat(net), g[f"ddpg_{name}{step + 1}"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["vanilla", "fixed_target", "double"])
+def test_dqn_uniform_replay_over_doubles_vs_reference(mode, td_lib, monkeypatch):
+    """BASELINE config C1's shapes: DQN with the uniform Buffer (slots from Python's random stream, buffer.py:234), all
+    three modes, five updates each against the unmodified reference (tests/golden/ref_dqn.npz; dqn.py:333-463)."""
+    import machin_b200.frame.algorithms.dqn as dqn_mod
+    import machin_b200.frame.algorithms.dqn_per as per_mod
+    import machin_b200.frame.algorithms.utils as utils_mod
+    from machin_b200.frame.buffers import Buffer
+    from oracle import td as otd
+    from test_gpu_algorithms import QNet, _flat, _load_flat
+    monkeypatch.setattr(dqn_mod.ops, "td_dqn", _emulated_td_dqn(td_lib))
+    soft = lambda tgt, src, rate: otd.soft_update_(list(tgt.parameters()), list(src.parameters()), rate)
+    for mod in (dqn_mod, per_mod, utils_mod):
+        monkeypatch.setattr(mod, "soft_update", soft)
+    g = np.load(os.path.join(GOLDEN, "ref_dqn.npz"))
+    S, A, N, B = 4, 2, 300, 32
+    qnet, qtgt = QNet(S, A), QNet(S, A)
+    _load_flat(qtgt, g[f"{mode}_init_qt"])
+    if mode == "vanilla":
+        _load_flat(qnet, g[f"{mode}_init_q"])           # no target net in this mode: the online net is its own target
+    dqn = dqn_mod.DQN(qnet, qtgt, t.optim.SGD, t.nn.MSELoss(), batch_size=B, learning_rate=0.2, discount=0.97, update_rate=0.1,
+                      replay_buffer=make_cpu_buffer(Buffer, 10000), mode=mode)
+    assert np.array_equal(_flat(dqn.qnet), g[f"{mode}_init_q"]) and (dqn.qnet_target is dqn.qnet) == (mode == "vanilla")
+    assert dqn.criterion.reduction == "mean"                              # the user's criterion is left alone
+    ep = [dict(state={"state": t.from_numpy(g["state"][i:i + 1])}, action={"action": t.tensor([[int(g["action"][i])]])},
+               next_state={"state": t.from_numpy(g["next_state"][i:i + 1])}, reward=float(g["reward"][i]),
+               terminal=bool(g["terminal"][i])) for i in range(N)]
+    for lo in range(0, N, 50):
+        dqn.store_episode(ep[lo:lo + 50])
+    t.manual_seed(17); np.random.seed(17); random.seed(17)
+    for step in range(5):
+        loss = dqn.update()
+        want = float(g[f"{mode}_loss{step}"])
+        assert abs(loss - want) <= 1e-5 * abs(want), (mode, step, loss, want)
+        np.testing.assert_allclose(_flat(dqn.qnet), g[f"{mode}_q{step + 1}"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(_flat(dqn.qnet_target), g[f"{mode}_qt{step + 1}"], rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError, match="Unknown DQN mode"):
+        dqn_mod.DQN(qnet, qtgt, t.optim.SGD, t.nn.MSELoss(), mode="triple", replay_buffer=make_cpu_buffer(Buffer, 10))
+    with pytest.raises(RuntimeError, match="nothing to capture"):
+        dqn.enable_cuda_graph()

@@ -11,7 +11,7 @@ import torch as t
 
 from conftest import GOLDEN
 
-NAMES = ["DQNPer", "DDPGPer", "DQNApex", "DDPGApex", "IMPALA", "A2C", "A3C", "RAINBOW"]
+NAMES = ["DQN", "DQNPer", "DDPGPer", "DQNApex", "DDPGApex", "IMPALA", "A2C", "A3C", "RAINBOW"]
 
 
 def _plain(x):
