@@ -159,18 +159,15 @@ def init_local(cls, config, model_device):
 
 def _members_group(name, members, device):
     """ShardGroup over the given ranks ("all": every rank), or a group of one outside torch.distributed."""
-    import torch.distributed as dist
-    from ...parallel import LocalGroup, ShardGroup
-    if not (dist.is_available() and dist.is_initialized()):
-        return LocalGroup(name, device=device)
-    return ShardGroup(name, ranks=None if members == "all" else [int(m) for m in members], device=device)
+    from ..helpers.servers import _group
+    return _group(name, members, device)
 
 
 def init_sharded(cls, config, model_device, group_key):
     """DQNApex / DDPGApex / IMPALA (apex.py:188-254, impala.py:446-509).  Collective: every rank calls it."""
     import torch.distributed as dist
     from ...parallel import ShardGroup
-    from ...parallel.server import PushPullModelServer
+    from ..helpers.servers import model_server_helper
     f = deepcopy(config["frame_config"])
     device = t.device(model_device)
     group = _members_group(f[group_key + "_group_name"], f[group_key + "_members"], device)
@@ -183,8 +180,7 @@ def init_sharded(cls, config, model_device, group_key):
     optimizer, criterion, lr_scheduler = _resolve_training_objects(f)
     if group_key == "apex":
         criterion.reduction = "none"                # apex.py:225
-    servers = (PushPullModelServer("model_server_0", _members_group(f["model_server_group_name"],
-                                                                    f["model_server_members"], device), 0),)
+    servers = model_server_helper(1, f["model_server_group_name"], f["model_server_members"], device)
     for key in ("optimizer", "criterion", "lr_scheduler"):
         del f[key]
     if spmd and n_learners < group.size():
@@ -201,21 +197,15 @@ def init_a3c(cls, config, model_device):
     """a3c.py:207-248.  Collective.  The member with index 0 of the gradient-server group owns the managed copies of
     actor and critic and their optimizers.  (The reference builds its managed copies from late-binding lambdas that all
     create the LAST model class, a3c.py:221-224; here each server manages a copy of its own model.)"""
-    from ...parallel.server import PushPullGradServer
+    from ..helpers.servers import grad_server_helper
     f = deepcopy(config["frame_config"])
     device = t.device(model_device)
     classes, models = _build_models(f, device)
     optimizer, criterion, lr_scheduler = _resolve_training_objects(f)
-    group = _members_group(f["grad_server_group_name"], f["grad_server_members"], device)
-    rates = (f["actor_learning_rate"], f["critic_learning_rate"])
-    sch_args, sch_kwargs = f["lr_scheduler_args"] or ((), ()), f["lr_scheduler_kwargs"] or ({}, {})
-    servers = []
-    for i, (c, a, k) in enumerate(zip(classes, f["model_args"], f["model_kwargs"])):
-        server = PushPullGradServer(f"grad_server_{i}", group, 0)
-        if group.index == 0:
-            managed = c(*a, **k).to(device)
-            opt = optimizer(managed.parameters(), lr=rates[i])
-            server.manage_model(managed, opt, lr_scheduler and lr_scheduler(opt, *sch_args[i], **sch_kwargs[i]))
-        servers.append(server)
+    creators = [(lambda c=c, a=a, k=k: c(*a, **k)) for c, a, k in zip(classes, f["model_args"], f["model_kwargs"])]
+    servers = grad_server_helper(creators, group_name=f["grad_server_group_name"], members=f["grad_server_members"],
+                                 optimizer=optimizer, learning_rate=[f["actor_learning_rate"], f["critic_learning_rate"]],
+                                 lr_scheduler=lr_scheduler, lr_scheduler_args=f["lr_scheduler_args"] or ((), ()),
+                                 lr_scheduler_kwargs=f["lr_scheduler_kwargs"] or ({}, {}), device=device)
     del f["criterion"]
     return cls(*models, criterion, tuple(servers), **f)

@@ -236,3 +236,24 @@ def test_init_sharded_roles_over_gloo():
     assert [r["learners"] for r in res] == [(2, True), (2, True), (2, False)]
     assert all(r["requesters"] == [0, 1] and r["reduction"] == "none" and r["optimizer"] == "Adam" for r in res)
     assert res[0]["sum"] == res[1]["sum"] == 3.0 and "sum" not in res[2]
+
+
+def test_server_helpers_on_a_group_of_one(doubles):
+    """machin.frame.helpers.servers surface: names, one server per model, the primary manages model + optimizer +
+    scheduler, per-model learning rates and optimizer keyword arguments."""
+    from machin_b200.frame.helpers import grad_server_helper, model_server_helper
+    dev = t.device("cpu", 0)
+    servers = model_server_helper(3, group_name="weights", device=dev)
+    assert [s.model_name for s in servers] == ["model_server_0", "model_server_1", "model_server_2"]
+    assert len({id(s.group) for s in servers}) == 1 and servers[0].group.get_group_name() == "weights"
+    made = []
+    creators = [lambda: made.append("a") or GlobalNet(3), lambda: made.append("b") or GlobalNet(5)]
+    grads = grad_server_helper(creators, group_name="grads", optimizer=t.optim.SGD, learning_rate=[0.1, 0.2],
+                               optimizer_kwargs=[{"momentum": 0.5}, {}], lr_scheduler=t.optim.lr_scheduler.StepLR,
+                               lr_scheduler_args=[(3,), (4,)], device=dev)
+    assert made == ["a", "b"] and [g.server_name for g in grads] == ["grad_server_0", "grad_server_1"]
+    assert grads[0].model.fc.in_features == 3 and grads[1].model.fc.in_features == 5
+    assert grads[0].optimizer.param_groups[0]["lr"] == 0.1 and grads[0].optimizer.param_groups[0]["momentum"] == 0.5
+    assert grads[1].optimizer.param_groups[0]["lr"] == 0.2 and grads[1].lr_scheduler.step_size == 4
+    same = grad_server_helper([lambda: GlobalNet()], learning_rate=0.01, device=dev)
+    assert isinstance(same[0].optimizer, t.optim.Adam) and same[0].optimizer.param_groups[0]["lr"] == 0.01
