@@ -1,6 +1,6 @@
 #!/bin/bash
-# Second GPU call of the next round (2 GPUs, charged 2x; ~6 minutes): the multi-GPU paths that have never run.
-#   gpurun --gpus 2 --timeout 900 -- 'bash tools/second_call_next_round.sh'
+# Second GPU call of the next round (2 GPUs, charged 2x; ~10 minutes): the multi-GPU paths that have never run.
+#   gpurun --gpus 2 --timeout 1200 -- 'bash tools/second_call_next_round.sh'
 # Every torchrun sits under `timeout`; bench.py arms its own watchdog as well.
 mkdir -p gpurun_out
 timeout 420 python -m pytest tests/test_gpu_distributed.py tests/test_gpu_zz_static_exchange.py tests/test_gpu_zz_impala_exchange.py -m gpu -q -rxXs \
@@ -29,3 +29,9 @@ run devapp_fused_rows "--net fused-rows --device-apportion"
 timeout 90 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29556 \
     tools/nccl_graph_repro.py thread_local release > gpurun_out/next2_teardown.txt 2>&1; echo "teardown after release: rc=$?"; tail -3 gpurun_out/next2_teardown.txt
 
+# C5's shape at the size of this call: 1 actor GPU -> 1 learner GPU (trajectory push + weight broadcast over NCCL)
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29557 \
+    tools/impala_dist_bench.py --steps 30 > gpurun_out/next2_impala.json 2> gpurun_out/next2_impala.err; tail -2 gpurun_out/next2_impala.json
+# C4's shape at 2 shards (eager exchange)
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29558 \
+    tools/ddpg_apex_bench.py --rows 2000000 --steps 200 > gpurun_out/next2_ddpg.json 2> gpurun_out/next2_ddpg.err; tail -2 gpurun_out/next2_ddpg.json
