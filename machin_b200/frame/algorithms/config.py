@@ -157,6 +157,13 @@ def init_local(cls, config, model_device):
     return cls(*models, **f)
 
 
+def _device(spec):
+    """torch.device of ``spec``; a CUDA device without an index becomes the current one (groups and servers allocate
+    on it and the library wants an ordinal)."""
+    dev = t.device(spec)
+    return t.device("cuda", t.cuda.current_device()) if dev.type == "cuda" and dev.index is None else dev
+
+
 def _members_group(name, members, device):
     """ShardGroup over the given ranks ("all": every rank), or a group of one outside torch.distributed."""
     from ..helpers.servers import _group
@@ -169,7 +176,7 @@ def init_sharded(cls, config, model_device, group_key):
     from ...parallel import ShardGroup
     from ..helpers.servers import model_server_helper
     f = deepcopy(config["frame_config"])
-    device = t.device(model_device)
+    device = _device(model_device)
     group = _members_group(f[group_key + "_group_name"], f[group_key + "_members"], device)
     _, models = _build_models(f, device)
     n_learners = int(f["learner_process_number"])
@@ -199,7 +206,7 @@ def init_a3c(cls, config, model_device):
     create the LAST model class, a3c.py:221-224; here each server manages a copy of its own model.)"""
     from ..helpers.servers import grad_server_helper
     f = deepcopy(config["frame_config"])
-    device = t.device(model_device)
+    device = _device(model_device)
     classes, models = _build_models(f, device)
     optimizer, criterion, lr_scheduler = _resolve_training_objects(f)
     creators = [(lambda c=c, a=a, k=k: c(*a, **k)) for c, a, k in zip(classes, f["model_args"], f["model_kwargs"])]
