@@ -507,6 +507,17 @@ def run_b200(a):
                "sample": (f"{done} full learner updates of oracle/learner.py (NumPy float64 tree at full size, "
                           f"Python-object storage capped at {a.cpu_storage_rows} rows, CPU torch MLP); best of thread "
                           f"counts 1..32 -> {threads} threads, {os.cpu_count()} cores present")}
+    # host <-> device bytes per update and rank, counted from the tensors that are copied: the uniforms (and, for the
+    # fixed-shape exchange, the apportioned counts, the per-requester parameter blocks and the loss scale) go in; the
+    # loss comes out -- and at N > 1 the all-gathered shard sums the host apportions with (prioritized_buffer_d.py:221-234)
+    st = getattr(learner, "_static", None) if (world > 1 and a.static_exchange) else None
+    if st is not None and not st["device_apportion"]:
+        h2d_bytes = sum(st[k].numel() * st[k].element_size() for k in ("uni", "counts", "params", "scale"))
+    elif st is not None:
+        h2d_bytes = st["uni"].numel() * 8 + 8
+    else:
+        h2d_bytes = 8 * B
+    d2h_bytes = 8 + (8 * world if (world > 1 and not (st is not None and st["device_apportion"])) else 0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -521,7 +532,7 @@ def run_b200(a):
                    "exchange": None if world == 1 else "per update: all-gather of shard sums, all-to-all of sampled rows, "
                                "all-to-all of priority write-backs, all-reduce of gradients, broadcast of weights (NCCL)",
                    "l2": "inputs larger than L2: 268 MB tree + 6.9 GB ring, randomly addressed every step"},
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 8,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": e2e_ms / K, "last_loss": last},
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / K,
         "kernels": {KERNELS[k][0]: v for k, v in kern.items()},
