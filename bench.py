@@ -458,7 +458,14 @@ def run_b200(a):
     barrier()
     e2e_ms = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3)
     # ---- per-kernel event timing inside the step
-    kern = time_kernels(learner, table) if (rank == 0 and world == 1) else {}
+    kern = {}
+    if rank == 0:
+        try:                                   # (local kernels of this rank's shard; no collective inside)
+            kern = time_kernels(learner, table)
+        except Exception as exc:               # noqa: BLE001 -- at N > 1 the other ranks wait for this one: never raise here
+            if world == 1:
+                raise
+            sys.stderr.write(f"bench.py: per-kernel timing skipped at N = {world}: {exc!r}\n")
     clocks = sampler.stop()
     tt = t.tensor([ms_total, e2e_ms], device=device, dtype=t.float64)
     if world > 1:

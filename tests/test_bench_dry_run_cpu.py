@@ -201,6 +201,8 @@ def test_b200_arm_dry_run_two_ranks(case, monkeypatch):
     assert len(written) == 1
     line = json.loads(written[0].decode())
     assert line["n_gpus"] == 2 and line["cpu_baseline"] is None
+    assert line["roofline"] is not None and line["kernels"]          # rank 0 times its shard's kernels at N > 1 too
+    assert line["e2e"]["d2h_bytes_per_step"] == 8 + 8 * 2
     launch = line["config"]["launch"]
     if case == "static":
         assert launch == "one CUDA graph per update"
