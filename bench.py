@@ -269,7 +269,7 @@ KERNELS = {  # C entry point -> (label, algorithmic bytes per launch as f(batch,
 }
 
 
-def time_kernels(learner, table, reps=20, per_graph=16):
+def time_kernels(learner, table, reps=20, per_graph=16, capture_mode=None):
     """Average device time per launch of each libmachin_b200 kernel of the step.
 
     Eager launches are CPU-launch-bound (the kernels take microseconds), so each kernel is captured
@@ -332,7 +332,7 @@ def time_kernels(learner, table, reps=20, per_graph=16):
         t.cuda.current_stream(dev).wait_stream(side)
         t.cuda.synchronize(dev)
         g = t.cuda.CUDAGraph()
-        with t.cuda.graph(g):
+        with (t.cuda.graph(g, capture_error_mode=capture_mode) if capture_mode else t.cuda.graph(g)):
             for i in range(per_graph):
                 fn(i)
         g.replay()
@@ -461,7 +461,8 @@ def run_b200(a):
     kern = {}
     if rank == 0:
         try:                                   # (local kernels of this rank's shard; no collective inside)
-            kern = time_kernels(learner, table)
+            # (with a process group alive, NCCL's watchdog thread may touch CUDA while this thread captures)
+            kern = time_kernels(learner, table, capture_mode="thread_local" if world > 1 else None)
         except Exception as exc:               # noqa: BLE001 -- at N > 1 the other ranks wait for this one: never raise here
             if world == 1:
                 raise
