@@ -59,6 +59,11 @@ class TorchFramework:
     def is_distributed(cls):
         return False
 
+    def enable_multiprocessing(self):
+        """base.py:86-92: put every top model into shared memory (a no-op for CUDA parameters)."""
+        for model in self.top_models:
+            model.share_memory()
+
     def set_backward_function(self, backward_func: Callable):
         if not callable(backward_func):
             raise AssertionError("Backward function must be callable.")

@@ -95,6 +95,26 @@ class DDPGPer(TorchFramework):
         action, *others = safe_call(self.actor_target if use_target else self.actor, state)
         return (t.argmax(action, dim=1).view(action.shape[0], 1), action, *others)
 
+    def act_discrete_with_noise(self, state: Dict[str, Any], use_target: bool = False, choose_max_prob: float = 0.95, **__):
+        """ddpg.py:287-331: the actor outputs a probability row per state; near-one-hot rows are softened so that the
+        largest component is chosen with ``choose_max_prob``, then one action is sampled per row."""
+        probs, *others = safe_call(self.actor_target if use_target else self.actor, state)
+        if not (probs.dim() == 2 and bool(t.all((probs.sum(dim=1) - 1.0).abs() < 1e-5)) and bool(t.all(probs >= 0))):
+            raise ValueError("Input tensor is not a probability tensor, it must have 2 dimensions (0 and 1), a sum of 1.0 "
+                             "for each row in dimension 1, and a positive value for each element.")
+        batch_size, action_dim = probs.shape
+        if action_dim > 1 and choose_max_prob < 1.0:
+            probs = t.softmax(probs * np.log((action_dim - 1) / (1 - choose_max_prob) * choose_max_prob), dim=1)
+        # (the reference draws a [batch, 1] block of samples PER ROW and reshapes it to [batch, 1], ddpg.py:327: that only
+        #  fits for one state at a time -- which is how acting calls it; kept, so that the random stream is consumed alike)
+        result = t.distributions.Categorical(probs).sample([batch_size, 1]).view(batch_size, 1)
+        return (result, probs, *others)
+
+    @staticmethod
+    def reward_function(reward, discount, next_value, terminal, _):
+        """ddpg.py:506-510, as torch ops; the learner step evaluates the same expression inside csrc/td.cu."""
+        return reward + discount * ~terminal.to(reward.device) * next_value.to(reward.device)
+
     def _act(self, state: Dict[str, Any], use_target: bool = False, **__):
         return safe_call(self.actor_target if use_target else self.actor, state)[0]
 

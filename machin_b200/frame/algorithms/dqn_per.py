@@ -132,6 +132,12 @@ class DQNPer(TorchFramework):
     def action_get_function(sampled_actions):
         return sampled_actions["action"]
 
+    @staticmethod
+    def reward_function(reward, discount, next_value, terminal, _):
+        """dqn.py:497-501, as torch ops.  The learner steps do not call it: csrc/td.cu evaluates exactly this expression
+        (same operation order) inside the target kernel -- a subclass that changes it must override ``_step`` as well."""
+        return reward + discount * ~terminal.to(reward.device) * next_value.to(reward.device)
+
     # ------------------------------------------------------------------ learner step (dqn_per.py:89-161)
     def _sample(self, uniform=None, use_device_params=False):
         n, fields, d_index, d_isw = self.replay_buffer.sample_device(self.batch_size, uniform=uniform,

@@ -728,10 +728,50 @@ def gen_dqn():
     np.savez_compressed(os.path.join(OUT, "ref_dqn.npz"), **out)
 
 
+# --------------------------------------------------------------------------- public surface of the mirrored classes
+def gen_surface():
+    """Public attributes (methods, properties, class attributes) of every reference class this repository mirrors,
+    and the parameter names of their constructors / public methods -- the drop-in boundary of SURVEY 8b as data."""
+    import inspect
+    import json
+    from machin.frame import algorithms as A
+    from machin.frame import buffers as B
+    from machin.frame.buffers import rnn_buffers as R
+    from machin.frame.buffers.prioritized_buffer import WeightTree
+    from machin.parallel.server import PushPullGradServer, PushPullModelServer
+    classes = {"WeightTree": WeightTree, "Buffer": B.Buffer, "PrioritizedBuffer": B.PrioritizedBuffer,
+               "DistributedBuffer": B.DistributedBuffer, "DistributedPrioritizedBuffer": B.DistributedPrioritizedBuffer,
+               "RNNBuffer": R.RNNBuffer, "RNNPrioritizedBuffer": R.RNNPrioritizedBuffer,
+               "DQN": A.DQN, "DQNPer": A.DQNPer, "DDPGPer": A.DDPGPer, "DQNApex": A.DQNApex, "DDPGApex": A.DDPGApex,
+               "IMPALA": A.IMPALA, "A2C": A.A2C, "A3C": A.A3C, "RAINBOW": A.RAINBOW,
+               "PushPullModelServer": PushPullModelServer, "PushPullGradServer": PushPullGradServer}
+    out = {}
+    for name, cls in classes.items():
+        members = {}
+        for attr in dir(cls):
+            if attr.startswith("_") and attr != "__init__":
+                continue
+            raw = inspect.getattr_static(cls, attr)
+            obj = getattr(cls, attr)
+            if isinstance(raw, property):
+                members[attr] = "property"
+            elif callable(obj):
+                try:
+                    params = [p for p in inspect.signature(obj).parameters if p not in ("self", "cls")]
+                except (TypeError, ValueError):
+                    params = None
+                members[attr] = params
+            else:
+                members[attr] = "attribute"
+        out[name] = members
+    with open(os.path.join(OUT, "ref_surface.json"), "w") as fh:
+        json.dump(out, fh, indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     ref_shim.load()
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["tree", "per", "td", "vtrace", "gae", "buffer", "per_d", "rnn", "rainbow", "configs", "dqn"]
+    which = sys.argv[1:] or ["tree", "per", "td", "vtrace", "gae", "buffer", "per_d", "rnn", "rainbow", "configs", "dqn", "surface"]
     for name in which:
         globals()["gen_" + name]()
         print("wrote", name)
