@@ -125,7 +125,9 @@ def doubles(monkeypatch):
 
     for mod in (dqn_mod, ddpg_mod):
         monkeypatch.setattr(mod, "PrioritizedBuffer", per)
-    monkeypatch.setattr(a2c_mod, "Buffer", lambda buffer_size=1000, buffer_device=None, **kw: make_cpu_buffer(real_buf, buffer_size))
+    import machin_b200.frame.algorithms.dqn as uniform_mod
+    for mod in (a2c_mod, uniform_mod):
+        monkeypatch.setattr(mod, "Buffer", lambda buffer_size=1000, buffer_device=None, **kw: make_cpu_buffer(real_buf, buffer_size))
     monkeypatch.setattr(apex_mod, "DistributedPrioritizedBuffer", dper)
     monkeypatch.setattr(impala_mod, "IMPALABuffer", lambda buffer_name, group, buffer_size, requesters=None: make_cpu_buffer(
         real_imp, buffer_size, buffer_name=buffer_name, group=group, wr_lock=RLock(), requesters=requesters or [0],
