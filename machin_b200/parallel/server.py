@@ -128,6 +128,12 @@ class PushPullGradServer:
             if self.lr_scheduler is not None:
                 self.lr_scheduler.step()
             self._model_server.push(self.model)
+            if model is not None and model is not self.model:
+                # the primary's own worker model is a different object from the managed copy (grad_server_helper builds
+                # the managed one from a creator): it receives the published parameters like every other worker's
+                with t.no_grad():
+                    t._foreach_copy_(_state_tensors(model), [x.detach() for x in _state_tensors(self.model)])
+                model.pp_version = self.model.pp_version
         else:
             self._model_server.pull(ref)
         self._acc.zero_()

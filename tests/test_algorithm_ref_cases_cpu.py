@@ -144,3 +144,60 @@ def test_a2c_reference_cases(doubles, monkeypatch):  # noqa: F811
             a2c.store_episode(_steps(3, t.zeros([1, 1], dtype=t.int)))
             pol, val = a2c.update(update_value=flags[0], update_policy=flags[1], concatenate_samples=True)
             assert np.isfinite(pol) and np.isfinite(val) and a2c.replay_buffer.size() == 0
+
+
+class _Policy(t.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.fc = t.nn.Linear(S, A)
+
+    def forward(self, state, action=None):
+        dist = t.distributions.Categorical(logits=self.fc(state))
+        act = action if action is not None else dist.sample().view(-1, 1)
+        return act, dist.log_prob(act.flatten()).view(-1, 1), dist.entropy().view(-1, 1)
+
+
+def test_impala_and_a3c_reference_cases_on_a_group_of_one(doubles):  # noqa: F811
+    """test_impala.py / test_a3c.py case lists (act, store, update with every flag combination, set_sync / manual_sync),
+    with the group of one that exists outside torch.distributed: model and gradient servers are real, collectives are
+    identities."""
+    from machin_b200.frame.algorithms import A3C, IMPALA
+    from machin_b200.frame.helpers import grad_server_helper, model_server_helper
+    from machin_b200.parallel import LocalGroup
+    dev = t.device("cpu", 0)
+    group = LocalGroup("impala", device="cpu")
+    group.device = dev
+    imp = IMPALA(_Policy(), Critic(S), t.optim.Adam, t.nn.MSELoss(reduction="sum"), group,
+                 model_server_helper(1, device=dev), batch_size=2, replay_size=100)
+    act, logp, *_ = imp.act({"state": t.zeros([1, S])})
+    assert act.shape == (1, 1) and imp.is_distributed()
+    with pytest.raises(ValueError, match="Episode must be non-empty"):
+        imp.store_episode([])
+    for n in (3, 5):
+        ep = _steps(n, t.zeros([1, 1], dtype=t.int))
+        for tr in ep:
+            tr["action_log_prob"] = 0.1
+        imp.store_episode(ep)
+        assert ep[0]["episode_length"] == n and all(tr["episode_length"] == 0 for tr in ep[1:])
+    for flags in itertools.product((True, False), repeat=2):
+        pol, val = imp.update(update_value=flags[0], update_policy=flags[1])
+        assert np.isfinite(pol) and np.isfinite(val)
+    imp.set_sync(False)
+    imp.manual_sync()
+    assert imp.actor.pp_version >= 1                     # pushed after every update (impala.py:393-396)
+
+    servers = grad_server_helper([_Policy, lambda: Critic(S)], learning_rate=[1e-3, 1e-3], device=dev)
+    a3c = A3C(_Policy(), Critic(S), t.nn.MSELoss(reduction="sum"), servers, batch_size=2, replay_size=100,
+              actor_update_times=1, critic_update_times=1)
+    assert a3c.is_distributed() and a3c.optimizers == [] and a3c.lr_schedulers == []
+    before = [p.detach().clone() for p in servers[1].model.parameters()]
+    for flags in itertools.product((True, False), repeat=2):
+        a3c.store_episode(_steps(3, t.zeros([1, 1], dtype=t.int)))
+        pol, val = a3c.update(update_value=flags[0], update_policy=flags[1])
+        assert np.isfinite(pol) and np.isfinite(val)
+    a3c.set_sync(False)
+    a3c.manual_sync()
+    # (advantages are zero in a dry run, so only the critic sees gradients) the server's copy stepped and was pulled
+    assert any(not t.equal(a, b) for a, b in zip(before, servers[1].model.parameters()))
+    assert all(t.equal(a, b) for a, b in zip(a3c.critic.parameters(), servers[1].model.parameters()))
+    assert all(t.equal(a, b) for a, b in zip(a3c.actor.parameters(), servers[0].model.parameters()))
