@@ -393,3 +393,45 @@ def test_rainbow_update_dry_run(graph, monkeypatch):
     called = {name for name, _ in rec.calls}
     assert {"mb_per_sample", "mb_td_rainbow", "mb_tree_update_priority", "mb_adam_step_multi", "mb_soft_update_multi"} <= called
     assert "mb_td_dqn" not in called
+
+
+def test_real_device_ring_dry_run(monkeypatch):
+    """The REAL DeviceRing (not the host-memory double) under the recorder: schema layout, field descriptor arrays and
+    every gather / scatter / unpack entry point are driven through Buffer's store and sample paths.  Nothing moves (the
+    recorder launches nothing), but descriptor construction and argument types are the product's."""
+    from machin_b200.frame.buffers import Buffer
+    from machin_b200.frame.buffers.device_ring import DeviceRing
+    from machin_b200._lib import MbField
+    rec = _dry_run_patches(monkeypatch)
+    dev = t.device("cpu", 0)
+    buf = make_cpu_buffer(Buffer, 64)
+    buf.storage, buf.buffer_device = DeviceRing(64, dev), dev
+    ep = [dict(state={"state": t.randn(1, 5), "aux": t.randn(1, 2, 3)}, action={"action": t.tensor([[i % 3]], dtype=t.int)},
+               next_state={"state": t.randn(1, 5), "aux": t.randn(1, 2, 3)}, reward=float(i), terminal=i == 6, note="text",
+               score=i) for i in range(7)]
+    buf.store_episode(ep)
+    ring = buf.storage
+    assert ring.pitch % 16 == 0 and ring.data.shape == (64, ring.pitch) and len(ring) == 7
+    offsets = sorted((f.offset, f.nbytes) for f in ring.fields.values())
+    assert all(a + n <= b for (a, n), (b, _) in zip(offsets, offsets[1:])) and offsets[-1][0] + offsets[-1][1] <= ring.pitch
+    assert ring.fields["reward"].scalar and ring.fields["action/action"].dtype == t.int32 and "note" not in ring.fields
+    n, (state, action, reward, others) = buf.sample_batch(4, sample_attrs=["state", "action", "reward", "*"],
+                                                          additional_concat_custom_attrs=["score"])
+    assert n == 4 and state["aux"].shape == (4, 2, 3) and action["action"].dtype == t.int32 and reward.shape == (4, 1)
+    assert others["score"].shape == (4, 1) and len(others["note"]) == 4
+    n, (state, reward) = buf.sample_batch(3, concatenate=False, sample_attrs=["state", "reward"])
+    assert n == 3 and len(state["state"]) == 3 and isinstance(reward[0], float)
+    buf.store_episode_tensors = Buffer.store_episode_tensors.__get__(buf)
+    idx = t.tensor([0, 3, 5])
+    packed = ring.gather_packed(idx)
+    assert packed.shape == (3, ring.pitch)
+    out = {k: t.zeros((3,) + f.shape, dtype=f.dtype) for k, f in ring.fields.items()}
+    assert ring.unpack(packed, out=out) is out and set(ring.unpack(packed, names=["reward", "nope"])) == {"reward"}
+    wire = t.zeros((3, ring.pitch + 24), dtype=t.uint8)
+    ring.gather_into_wire(idx, wire)
+    with pytest.raises(RuntimeError, match="schema already fixed"):
+        ring.set_schema([])
+    calls = [name for name, _ in rec.calls]
+    assert {"mb_rows_scatter", "mb_rows_gather", "mb_rows_gather_packed"} <= set(calls)
+    gathers = [args for name, args in rec.calls if name == "mb_rows_gather"]
+    assert all(isinstance(a[5], C.Array) and a[5]._type_ is MbField for a in gathers)
