@@ -201,3 +201,46 @@ def test_impala_and_a3c_reference_cases_on_a_group_of_one(doubles):  # noqa: F81
     assert any(not t.equal(a, b) for a, b in zip(before, servers[1].model.parameters()))
     assert all(t.equal(a, b) for a, b in zip(a3c.critic.parameters(), servers[1].model.parameters()))
     assert all(t.equal(a, b) for a, b in zip(a3c.actor.parameters(), servers[0].model.parameters()))
+
+
+def test_apex_reference_cases_on_a_group_of_one(doubles):  # noqa: F811
+    """test_apex.py case list for DQNApex / DDPGApex (act with and without syncing, store, update -> weights pushed,
+    manual_sync, the sampler-side serve_update) with real model servers on a group of one."""
+    from machin_b200.frame.algorithms import DDPGApex, DQNApex
+    from machin_b200.frame.helpers import model_server_helper
+    from machin_b200.parallel import LocalGroup
+    dev = t.device("cpu", 0)
+
+    def group(name):
+        g = LocalGroup(name, device="cpu")
+        g.device = dev
+        return g
+
+    apex = DQNApex(QNet(S, A), QNet(S, A), t.optim.Adam, t.nn.MSELoss(reduction="sum"), group("dqn_apex"),
+                   model_server_helper(1, device=dev), batch_size=2, replay_size=100)
+    state = {"state": t.zeros([1, S])}
+    apex.store_episode(_steps(3, t.zeros([1, 1], dtype=t.int)))
+    for flags in itertools.product((True, False), repeat=2):
+        assert np.isfinite(apex.update(update_value=flags[0], update_target=flags[1]))
+    version = apex.qnet.pp_version
+    assert version >= 4                                          # published after every update (apex.py:141-150)
+    assert apex.act_discrete(state).shape == (1, 1) and apex.act_discrete(state, True).shape == (1, 1)
+    assert apex.act_discrete_with_noise(state).shape == (1, 1)
+    apex.set_sync(False)
+    assert apex.act_discrete(state).shape == (1, 1) and not apex.is_syncing
+    apex.manual_sync()
+    apex.serve_update()                                          # what a member that only holds a shard calls instead
+    assert DQNApex.is_distributed()
+
+    ddpg = DDPGApex(Actor(S, 2), Actor(S, 2), Critic(S, 2), Critic(S, 2), t.optim.Adam, t.nn.MSELoss(reduction="sum"),
+                    group("ddpg_apex"), model_server_helper(1, device=dev), batch_size=2, replay_size=100)
+    ddpg.store_episode(_steps(3, t.zeros([1, 2])))
+    for flags in itertools.product((True, False), repeat=3):
+        pol, val = ddpg.update(update_value=flags[0], update_policy=flags[1], update_target=flags[2])
+        assert np.isfinite(pol) and np.isfinite(val)
+    assert ddpg.actor.pp_version >= 8                            # the ACTOR is what gets published (apex.py:372-381)
+    assert ddpg.act(state).shape == (1, 2) and ddpg.act(state, use_target=True).shape == (1, 2)
+    ddpg.set_sync(False)
+    ddpg.manual_sync()
+    ddpg.serve_update()
+    assert ddpg.act_with_noise(state, noise_param=(0.0, 0.1)).shape == (1, 2)

@@ -121,6 +121,7 @@ def doubles(monkeypatch):
                               wr_lock=RLock(), _requesters=requesters, _sampler=None,
                               buffer_version_table=t.zeros(buffer_size, dtype=t.int64))
         buf.storage, buf.buffer_device = _Ring(buffer_size), t.device("cpu", 0)
+        buf.weight_sum_tensor = lambda: t.tensor([max(buf.wt_tree.get_weight_sum(), 1.0)], dtype=t.float64)
         return buf
 
     for mod in (dqn_mod, ddpg_mod):
