@@ -435,3 +435,41 @@ def test_real_device_ring_dry_run(monkeypatch):
     assert {"mb_rows_scatter", "mb_rows_gather", "mb_rows_gather_packed"} <= set(calls)
     gathers = [args for name, args in rec.calls if name == "mb_rows_gather"]
     assert all(isinstance(a[5], C.Array) and a[5]._type_ is MbField for a in gathers)
+
+
+def test_buffer_constructors_dry_run(monkeypatch):
+    """The real constructors (they need a device: tests/fake_ring.py bypasses them everywhere else): argument routing
+    through the RNN / prioritized class hierarchy, device normalisation, the loud refusals."""
+    import machin_b200._lib as lib_mod
+    import machin_b200.frame.buffers.prioritized_buffer as per_mod
+    from machin_b200.frame.buffers import (Buffer, DistributedBuffer, DistributedPrioritizedBuffer, PrioritizedBuffer,
+                                           RNNBuffer, RNNPrioritizedBuffer)
+    from machin_b200.parallel import LocalGroup
+    _dry_run_patches(monkeypatch)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Buffer(10, "cuda")                                       # the recorder reports no device: refused loudly
+    monkeypatch.setattr(lib_mod, "require_device", lambda index=0: None)
+    monkeypatch.setattr(per_mod, "WeightTree", lambda size, device: _Tree(size))
+    with pytest.raises(ValueError, match="must be a CUDA device"):
+        Buffer(10, "cpu")
+    with pytest.raises(ValueError, match="custom storage is not supported"):
+        Buffer(10, "cuda", storage=object())
+    b = Buffer(10)
+    assert b.buffer_device == t.device("cuda", 0) and b.storage.max_size == 10 and b.size() == 0
+    p = PrioritizedBuffer(16, "cuda:0", epsilon=0.1, alpha=0.5, beta=0.3, beta_increment_per_sampling=0.01)
+    assert (p.epsilon, p.alpha, p.beta, p.curr_beta, p.beta_increment_per_sampling) == (0.1, 0.5, 0.3, 0.3, 0.01)
+    assert p.wt_tree.size == 16
+    r = RNNBuffer(sample_length=4, buffer_size=20)
+    assert (r.sample_length, r.sample_dimension, r.storage.max_size) == (4, 1, 20)
+    with pytest.raises(ValueError, match="custom storage is not supported"):
+        RNNBuffer(sample_length=4, storage=object())
+    rp = RNNPrioritizedBuffer(sample_length=3, sample_dimension=0, buffer_size=32, alpha=0.7)      # the reference cannot
+    assert (rp.sample_length, rp.sample_dimension, rp.alpha, rp.wt_tree.size) == (3, 0, 0.7, 32)   # construct this one
+    group = LocalGroup("g", device="cpu")
+    group.device = t.device("cuda", 0)
+    d = DistributedBuffer("buffer", group, buffer_size=12)
+    assert d.buffer_name == "buffer" and d.requesters == [0] and d.buffer_device == t.device("cuda", 0)
+    real_zeros = t.zeros                                # (the version table is allocated on the device right away)
+    monkeypatch.setattr(t, "zeros", lambda *a, device=None, **k: real_zeros(*a, **k))
+    dp = DistributedPrioritizedBuffer("buffer", group, buffer_size=12, beta=0.5)
+    assert dp.curr_beta == 0.5 and dp.buffer_version_table.shape == (12,) and dp.buffer_version_table.dtype == t.int64
