@@ -193,7 +193,8 @@ class DDPGPer(TorchFramework):
         """Single-process prioritized buffer, soft target updates and capturable optimizers (SGD, or Adam / AdamW --
         ``capturable`` is switched on here).  torch's capture protocol needs ``warmup`` real updates first: networks,
         optimizer state, tree and beta are snapshotted before and restored in place after."""
-        if type(self.replay_buffer) is not PrioritizedBuffer or self.update_rate is None:
+        from ..buffers.prioritized_buffer import PrioritizedBuffer as single_process_per
+        if type(self.replay_buffer) is not single_process_per or self.update_rate is None:
             raise RuntimeError("DDPGPer.enable_cuda_graph needs a single-process PrioritizedBuffer and soft target updates")
         buf = self.replay_buffer
         dev = buf.buffer_device

@@ -72,7 +72,7 @@ def main():
     te = t.zeros(steps, 1, dtype=t.bool)
     te[T - 1::T] = True
     c, rho, delta = ovt.vtrace_prepare(lp, lm, v, nv, r, te, 0.99, 1.0, 1.0)
-    sub = 64                                   # bounded sample: 64 episodes of the loop, scaled up
+    sub = min(64, EP)                          # bounded sample: 64 episodes of the loop, scaled up
     t0 = time.perf_counter()
     ovt.vtrace_loop(v[:sub * T], delta[:sub * T], c[:sub * T], [T] * sub, 0.99)
     loop_ms = (time.perf_counter() - t0) * 1e3 * EP / sub
