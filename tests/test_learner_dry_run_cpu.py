@@ -473,3 +473,73 @@ def test_buffer_constructors_dry_run(monkeypatch):
     monkeypatch.setattr(t, "zeros", lambda *a, device=None, **k: real_zeros(*a, **k))
     dp = DistributedPrioritizedBuffer("buffer", group, buffer_size=12, beta=0.5)
     assert dp.curr_beta == 0.5 and dp.buffer_version_table.shape == (12,) and dp.buffer_version_table.dtype == t.int64
+
+
+@pytest.mark.parametrize("variant", ["default", "device_apportion+batched_draw"])
+def test_fixed_shape_update_dry_run_as_member_of_two(variant, monkeypatch):
+    """The P > 1 branches of the fixed-shape update (captured all-to-alls, gradient all-reduce, per-requester draws into
+    [P, cap] blocks, one gather and one metadata launch over P * cap rows) executed in ONE process: a group double of
+    size 2 whose collectives copy this member's own contribution into every slot."""
+    import torch.distributed as dist
+    import machin_b200.frame.algorithms.apex as apex_mod
+    from machin_b200.frame.buffers import DistributedPrioritizedBuffer
+    from machin_b200.parallel import LocalGroup
+    rec = _dry_run_patches(monkeypatch)
+    dev = t.device("cpu", 0)
+
+    class GroupOfTwo(LocalGroup):
+        index, pg = 0, None
+
+        def size(self):
+            return 2
+
+        def all_gather_f64(self, value):
+            return t.stack([value, value])
+
+    monkeypatch.setattr(dist, "all_to_all_single", lambda out, inp, group=None: out.copy_(inp))
+    monkeypatch.setattr(dist, "all_reduce", lambda x, group=None, op=None: None)
+    monkeypatch.setattr(dist, "all_gather_into_tensor", lambda out, inp, group=None: out.copy_(inp.repeat(out.numel() // inp.numel())))
+
+    def buffer_double(buffer_name, group, buffer_size, requesters=None, **kw):
+        buf = make_cpu_buffer(DistributedPrioritizedBuffer, buffer_size, epsilon=1e-2, alpha=0.6, beta=0.4, curr_beta=0.4,
+                              beta_increment_per_sampling=1e-3, wt_tree=_Tree(buffer_size), buffer_name=buffer_name, group=group,
+                              wr_lock=RLock(), _requesters=requesters, _sampler=None,
+                              buffer_version_table=t.zeros(buffer_size, dtype=t.int64))
+        buf.storage, buf.buffer_device = _Ring(buffer_size), dev
+        buf.weight_sum_tensor = lambda: t.tensor([buf.wt_tree.get_weight_sum()], dtype=t.float64)
+        buf._agree_on_schema = lambda: None                     # (a collective over Python objects; both members stored)
+        return buf
+
+    monkeypatch.setattr(apex_mod, "DistributedPrioritizedBuffer", buffer_double)
+    S, A, B, N = 6, 4, 16, 200
+    net = lambda: t.nn.Sequential(t.nn.Linear(S, 16), t.nn.ReLU(), t.nn.Linear(16, A))
+
+    class Q(t.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.net = net()
+
+        def forward(self, state):
+            return self.net(state)
+
+    group = GroupOfTwo(device="cpu")
+    group.device = dev
+    learner = apex_mod.DQNApex(Q(), Q(), t.optim.SGD, t.nn.MSELoss(reduction="none"), group, (), batch_size=B, learning_rate=0.01,
+                               discount=0.9, update_rate=0.1, replay_size=N, learner_group=group)
+    learner.replay_buffer.store_episode(
+        [dict(state={"state": t.randn(1, S)}, action={"action": t.tensor([[i % A]])}, next_state={"state": t.randn(1, S)},
+              reward=float(i), terminal=False) for i in range(50)], priorities=list(np.random.RandomState(0).exponential(size=50)))
+    learner.batched_draw = "batched_draw" in variant
+    learner.enable_cuda_graph(static_exchange=True, device_apportion=variant.startswith("device_apportion"))
+    st = learner._static
+    assert st["P"] == 2 and st["d_idx"].shape == (2, B) and st["send"].shape == (2 * B, st["W"]) and st["capB"] == B + 2
+    for _ in range(3):
+        assert learner.update_device().shape == ()
+    if not variant.startswith("device"):
+        assert int(st["counts_pin"].sum()) in (B, B + 1)        # ceil apportioning over two equal shards
+    names = [name for name, _ in rec.calls]
+    gathers = [args for name, args in rec.calls if name == "mb_rows_pack_meta"]
+    assert gathers and all(a[3] == 2 * B for a in gathers)      # ONE metadata launch over both requester blocks
+    assert ("mb_per_sample_multi" in names) == ("batched_draw" in variant)
+    assert {"mb_wire_compact", "mb_wire_scatter_update", "mb_wire_update_mask", "mb_tree_update_priority"} <= set(names)
+    learner.push_weights()                                      # every member learns: nothing to broadcast
