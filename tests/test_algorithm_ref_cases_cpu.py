@@ -13,6 +13,8 @@ import torch as t
 from test_config_cpu import Actor, Critic, QNet, doubles  # noqa: F401  (doubles: fixture)
 
 S, A = 4, 2
+# (the reference's lr-scheduler case steps the scheduler before any optimizer step, test_dqn.py:test_lr_scheduler)
+pytestmark = pytest.mark.filterwarnings("ignore:Detected call of `lr_scheduler.step")
 
 
 def _steps(n, action):
