@@ -543,3 +543,79 @@ def test_fixed_shape_update_dry_run_as_member_of_two(variant, monkeypatch):
     assert ("mb_per_sample_multi" in names) == ("batched_draw" in variant)
     assert {"mb_wire_compact", "mb_wire_scatter_update", "mb_wire_update_mask", "mb_tree_update_priority"} <= set(names)
     learner.push_weights()                                      # every member learns: nothing to broadcast
+
+
+def test_impala_fixed_shape_graph_dry_run(monkeypatch):
+    """IMPALA.enable_cuda_graph for trajectories of one length (BASELINE C3): staging of the host-picked episode slots,
+    replay, the eager fall-back for a batch of another shape (Python's random consumed once either way), release."""
+    import random
+    from threading import RLock
+    import machin_b200.frame.algorithms.impala as impala_mod
+    from machin_b200.frame.buffers import IMPALABuffer
+    from machin_b200.parallel import LocalGroup
+    rec = _dry_run_patches(monkeypatch)
+    dev = t.device("cpu", 0)
+    S, A, T, B = 5, 3, 4, 6
+
+    def buffer_double(buffer_name, group, buffer_size, requesters=None):
+        buf = make_cpu_buffer(IMPALABuffer, buffer_size, buffer_name=buffer_name, group=group, wr_lock=RLock(),
+                              requesters=requesters or [0], _schema_agreed=False)
+        buf.buffer_device = dev
+        return buf
+
+    monkeypatch.setattr(impala_mod, "IMPALABuffer", buffer_double)
+
+    class Policy(t.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = t.nn.Linear(S, A)
+
+        def forward(self, state, action=None):
+            dist = t.distributions.Categorical(logits=self.fc(state))
+            act = action if action is not None else dist.sample().view(-1, 1)
+            return act, dist.log_prob(act.flatten()).view(-1, 1), dist.entropy().view(-1, 1)
+
+    class Value(t.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = t.nn.Linear(S, 1)
+
+        def forward(self, state):
+            return self.fc(state)
+
+    group = LocalGroup("impala", device="cpu")
+    group.device = dev
+    imp = impala_mod.IMPALA(Policy(), Value(), t.optim.SGD, t.nn.MSELoss(reduction="sum"), group, (), batch_size=B, replay_size=400)
+
+    def episode(n):
+        return [dict(state={"state": t.randn(1, S)}, action={"action": t.tensor([[i % A]])}, next_state={"state": t.randn(1, S)},
+                     reward=float(i), action_log_prob=-0.5, terminal=i == n - 1) for i in range(n)]
+
+    for _ in range(9):
+        imp.store_episode(episode(T))
+    before = [p.detach().clone() for p in imp.actor.parameters()]
+    random.seed(5)
+    state = random.getstate()
+    imp.enable_cuda_graph(episode_length=T)
+    assert random.getstate() == state                            # the warm-up's episode picks are put back
+    assert all(t.equal(a, b) for a, b in zip(before, imp.actor.parameters()))
+    st = imp._graph_state
+    assert st["idx"].shape == (B * T,) and st["offsets"].tolist() == list(range(0, B * T + 1, T))
+    n_calls = len(rec.calls)
+    pol, val = imp.update_device()
+    assert pol.shape == () and len(rec.calls) == n_calls         # a replay launches nothing through the entry points
+    assert random.getstate() != state and sorted(set(st["idx_pin"].tolist())) == sorted(set(st["idx"].tolist()))
+    assert len(imp.update()) == 2
+    imp.store_episode(episode(T + 3))                            # a longer episode may now be drawn: eager fall-back
+    random.seed(0)
+    for _ in range(6):
+        out = imp.update_device()
+        assert out is not None and out[0].shape == ()
+    assert len(rec.calls) > n_calls                              # at least one of those batches ran eagerly
+    with pytest.raises(RuntimeError, match="sampled episodes of exactly"):
+        other = impala_mod.IMPALA(Policy(), Value(), t.optim.SGD, t.nn.MSELoss(reduction="sum"), group, (), batch_size=B,
+                                  replay_size=400)
+        other.store_episode(episode(T + 1))
+        other.enable_cuda_graph(episode_length=T)
+    imp.release_graphs()
+    assert imp._graph is None and imp.update_device()[0].shape == ()

@@ -103,11 +103,24 @@ def test_ddpg_bench_tool_dry_run(flags, device_doubles, monkeypatch, capsys):
     assert {"mb_per_sample", "mb_td_target", "mb_tree_update_priority"} <= {name for name, _ in device_doubles.calls}
 
 
-def test_impala_bench_tool_dry_run(device_doubles, monkeypatch, capsys):
+@pytest.mark.parametrize("flags", [[], ["--graph"]])
+def test_impala_bench_tool_dry_run(flags, device_doubles, monkeypatch, capsys):
+    import machin_b200.frame.algorithms.impala as impala_mod
     tool = _load("impala_bench")
     for name, value in (("S", 6), ("A", 3), ("T", 4), ("EP", 8)):
         monkeypatch.setattr(tool, name, value)
+    monkeypatch.setattr(sys, "argv", ["impala_bench.py", *flags])
+    monkeypatch.setattr(tool.t.optim, "Adam", t.optim.SGD)       # (torch's capturable Adam refuses host tensors)
+    real_double = impala_mod.IMPALABuffer
+
+    def with_device(*a, **k):
+        buf = real_double(*a, **k)
+        buf.buffer_device = t.device("cpu", 0)
+        return buf
+
+    monkeypatch.setattr(impala_mod, "IMPALABuffer", with_device)
     tool.main()
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     assert "C3 IMPALA" in line["config"] and line["gpu_update_ms"] > 0 and line["cpu_us_per_step"] > 0
+    assert line["launch"] == ("one CUDA graph per update" if flags else "eager")
     assert "mb_vtrace_len" in {name for name, _ in device_doubles.calls}

@@ -43,4 +43,6 @@ for v in "" "--graph"; do
 done
 timeout 300 python tools/microbench.py > gpurun_out/next_microbench.json 2> gpurun_out/next_microbench.err; tail -c 600 gpurun_out/next_microbench.json
 # C3 (IMPALA, 1024 episodes x T = 20) on one GPU: the whole update, next to the reference's V-trace loop on the host
-timeout 240 python tools/impala_bench.py 2> gpurun_out/next_impala.err | tee gpurun_out/next_impala.json
+for v in "" "--graph"; do
+    timeout 240 python tools/impala_bench.py $v 2>> gpurun_out/next_impala.err | tee -a gpurun_out/next_impala.jsonl
+done

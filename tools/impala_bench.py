@@ -55,6 +55,9 @@ def main():
              "next_state": {"state": t.randn(T, S, device=dev)}},
             {"reward": t.randn(T, 1, device=dev), "terminal": term},
             {"action_log_prob": -t.rand(T, 1, device=dev), "episode_length": el})
+    graph = "--graph" in sys.argv[1:]          # the whole update of the fixed-length batch as one CUDA graph replay
+    if graph:
+        imp.enable_cuda_graph(episode_length=T)
     for _ in range(3):
         imp.update()
     t.cuda.synchronize()
@@ -76,7 +79,8 @@ def main():
     t0 = time.perf_counter()
     ovt.vtrace_loop(v[:sub * T], delta[:sub * T], c[:sub * T], [T] * sub, 0.99)
     loop_ms = (time.perf_counter() - t0) * 1e3 * EP / sub
-    print(json.dumps({"config": f"C3 IMPALA {EP} episodes x T={T}, state {S}", "gpu_update_ms": gpu_ms,
+    print(json.dumps({"config": f"C3 IMPALA {EP} episodes x T={T}, state {S}", "launch": "one CUDA graph per update" if graph else "eager",
+                      "gpu_update_ms": gpu_ms,
                       "gpu_steps_per_s": steps / gpu_ms * 1e3,
                       "cpu_vtrace_loop_ms_scaled": loop_ms, "cpu_us_per_step": loop_ms * 1e3 / steps,
                       "note": "gpu: whole IMPALA.update() (episode sampling, gather, actor/critic forward+backward, "
