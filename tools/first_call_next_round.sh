@@ -1,7 +1,7 @@
 #!/bin/bash
-# First GPU call of the next round (one GPU, ~25 minutes): everything written after round 1's GPU budget ran
+# First GPU call of the next round (one GPU, ~30 minutes): everything written after round 1's GPU budget ran
 # out -- run the pending tests, then A/B the opt-in variants against the default on the bench workload.
-#   gpurun --timeout 2400 -- 'bash tools/first_call_next_round.sh'
+#   gpurun --timeout 2700 -- 'bash tools/first_call_next_round.sh'
 # Results land in gpurun_out/next_*.  Nothing here changes clocks or kills by pattern.
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q -rxXs -p no:cacheprovider > gpurun_out/next_pytest.txt 2>&1
