@@ -6,8 +6,11 @@ fixed cases of the CPU suite.  Takes minutes; not collected by pytest.
     python tools/fuzz_emulated.py tree [n]       # the sorted-update variants vs the generic update body
     python tools/fuzz_emulated.py rows [n]       # dqn_rows_kernel vs its NumPy restatement, random network shapes
     python tools/fuzz_emulated.py scan [n]       # V-trace / GAE, episode-length mixes around the staging-tile boundaries
+    python tools/fuzz_emulated.py exchange [n]   # the fixed-shape shard exchange for random shard counts / pitches / counts
 
-DESIGN.md 8b quotes the runs made in the build container (300 + 400, 240, 160, 284 launches: no mismatch)."""
+DESIGN.md 8b quotes the first runs made in the build container (300 + 400, 240, 160, 284 launches); later runs of this
+tool: rainbow 1500, tree 150 (x 4 variants), rows 100 (x 4 mode / layout combinations), scan 150, exchange 300 -- no
+mismatch in any of them."""
 import ctypes as C
 import os
 import subprocess
@@ -147,9 +150,34 @@ def fuzz_scan(n):
     return bad
 
 
+def fuzz_exchange(n):
+    """The fixed-shape shard exchange (gather into wire rows -> metadata -> all-to-all -> compaction -> priority scatter ->
+    all-to-all -> version mask) replayed for random shard counts, row pitches and apportioned counts: the test function of
+    the suite with its random stream shifted."""
+    import test_exchange_emulated_cpu as T
+    lib, bad = build("wire"), 0
+    exchange = plain(T.test_fixed_shape_exchange_replayed_for_P_shards)
+    apportion = plain(T.test_device_apportioning_matches_host_apportioning)
+    real = np.random.RandomState
+    for seed in range(n):
+        rng = real(12000 + seed)
+        P, pitch = int(rng.choice([1, 2, 3, 4, 5, 6, 7, 8])), 16 * int(rng.randint(1, 60))
+        T.np.random.RandomState = lambda s, _k=seed: real(s + 7919 * (_k + 1))
+        try:
+            exchange(lib, P, pitch)
+            apportion(lib, P)
+        except AssertionError as e:
+            bad += 1
+            print("MISMATCH exchange seed", seed, P, pitch, str(e)[:160])
+        finally:
+            T.np.random.RandomState = real
+    return bad
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "rainbow"
-    count = int(sys.argv[2]) if len(sys.argv) > 2 else {"rainbow": 300, "tree": 60, "rows": 40, "scan": 60}[which]
-    mismatches = {"rainbow": fuzz_rainbow, "tree": fuzz_tree, "rows": fuzz_rows, "scan": fuzz_scan}[which](count)
+    count = int(sys.argv[2]) if len(sys.argv) > 2 else {"rainbow": 300, "tree": 60, "rows": 40, "scan": 60, "exchange": 100}[which]
+    mismatches = {"rainbow": fuzz_rainbow, "tree": fuzz_tree, "rows": fuzz_rows, "scan": fuzz_scan,
+                  "exchange": fuzz_exchange}[which](count)
     print(f"{which}: {count} random configurations, {mismatches} mismatches")
     sys.exit(1 if mismatches else 0)
