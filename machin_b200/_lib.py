@@ -41,6 +41,9 @@ class MbPerParams(C.Structure):
     _fields_ = [("beta", f64), ("all_weight_sum", f64), ("n_stored", i64), ("step", i64), ("n_draw", i64)]
 
 
+PER_PARAMS_BYTES = C.sizeof(MbPerParams)      # 40: the device-side block every graph-mode draw reads
+
+
 # name -> (restype, argtypes); every symbol declared in include/machin_b200.h
 SIGNATURES = {
     "mb_abi_version": (i32, []),

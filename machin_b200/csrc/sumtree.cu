@@ -35,6 +35,7 @@ struct mb_tree {
     int gen;             // update-launch generation counter
     int sorted_cluster;  // MB_SORTED_CLUSTER=1: small sorted updates on a cluster of 8 CTAs (opt-in until measured)
     int sorted_async;    // MB_SORTED_ASYNC=1: barrier-free walk (point-to-point hand-overs), opt-in until measured
+    int legacy_update;   // MB_UPDATE_LEGACY=1: the single-CTA / cluster sorted kernels instead of tree_update_part (A/B timing)
     int force_generic;   // MB_FORCE_GENERIC_UPDATE=1: single-CTA PER draw instead of the cluster kernel (A/B timing)
 };
 
@@ -275,6 +276,8 @@ int mb_tree_create(int64_t size, int device, mb_tree **out) {
     {
         const char *e = getenv("MB_FORCE_GENERIC_UPDATE");
         t->force_generic = (e && e[0] == '1') ? 1 : 0;
+        const char *lg = getenv("MB_UPDATE_LEGACY");
+        t->legacy_update = (lg && lg[0] == '1') ? 1 : 0;
         const char *c = getenv("MB_SORTED_CLUSTER");
         t->sorted_cluster = (c && c[0] == '1') ? 1 : 0;
         const char *y = getenv("MB_SORTED_ASYNC");
@@ -297,6 +300,8 @@ int mb_tree_create(int64_t size, int device, mb_tree **out) {
     tree_state_reset<<<1, 1>>>(t->dev.st, 0.0);
     MB_CUDA(cudaFuncSetAttribute(tree_update_sorted<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     MB_CUDA(cudaFuncSetAttribute(tree_update_sorted<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    MB_CUDA(cudaFuncSetAttribute(tree_update_part<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    MB_CUDA(cudaFuncSetAttribute(tree_update_part<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     {   // opt-in variants (MB_SORTED_CLUSTER / MB_SORTED_ASYNC): a failure here must not take the default path down
         const void *v2[] = {(const void *)tree_update_sorted_v2<float, 3, false>, (const void *)tree_update_sorted_v2<double, 3, false>,
                             (const void *)tree_update_sorted_v2<float, 3, true>, (const void *)tree_update_sorted_v2<double, 3, true>,
@@ -430,6 +435,18 @@ static int launch_update(mb_tree *t, const int64_t *d_index, const void *d_weigh
     if (n > 0x7fffffff) return MB_ERR_INVALID;
     mb::DeviceGuard g(t->device);
     const int gen = ++t->gen;
+    if (n <= kPartMaxN && !t->force_generic && !t->legacy_update) {
+        // one launch, one CTA per subtree (128 at 10 M leaves), any order / mask / duplicates
+        const int levels = t->dev.depth - 1;
+        const unsigned grid = 1u << part_cut(levels);
+        const size_t dyn = part_dyn_smem(levels);
+        if (dtype == MB_F32)
+            tree_update_part<float><<<grid, kPartThreads, dyn, s>>>(t->dev, d_index, (const float *)d_weight, d_valid, (int)n, nz, gen);
+        else
+            tree_update_part<double><<<grid, kPartThreads, dyn, s>>>(t->dev, d_index, (const double *)d_weight, d_valid, (int)n, nz, gen);
+        MB_LAUNCHED(1);
+        return MB_OK;
+    }
     if (n <= kSortedN && !t->force_generic) {
         const int threads = (int)(((n + 31) / 32) * 32);
         const size_t dyn = sizeof(double) * (size_t)kSortedN * (size_t)(t->dev.depth - 1);

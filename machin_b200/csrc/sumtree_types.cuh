@@ -10,7 +10,7 @@ struct TreeState {
     int err_gen;       // launch generation that raised it (so later launches are not skipped)
     int max_is_f32;    // max_leaf came from a float32 batch (the reference keeps it as np.float32 then,
                        // which changes the dtype of normalize(max_leaf) for default-priority stores)
-    int pad;
+    int ticket;        // tree_update_part: CTAs that have finished their subtree (the last one lifts the top; 0 between launches)
 };
 
 struct TreeDev {

@@ -470,3 +470,260 @@ __global__ void __launch_bounds__(kSortedN) tree_update_sorted_v2(TreeDev t, con
     }
     if (CB > 0) cg::this_cluster().sync();   // nobody exits (and frees its shared memory) while the leader may still read it
 }
+
+
+// ---- third generation: the update spread over the whole GPU in ONE launch, no grid barrier ---------------------
+// The single-CTA kernels above are bound by one SM's load/store unit (~8.7 k scattered sibling loads and as many
+// scattered stores for 512 entries of a 2^24-leaf tree) and by 24 CTA-wide barriers.  Here the tree is cut at level
+// ls = levels - cut into G = 2^cut subtrees, ONE CTA PER SUBTREE (G = 128 at 10 M leaves: the prefetch and the
+// write-out run on 128 load/store units and every CTA's sibling loads are in flight at the same time):
+//   A  every CTA scans the whole batch (n <= 4096 indexes: 32 KB out of L2) and keeps the entries of its own
+//      subtree -- ordered compaction, so a sorted batch stays sorted; validation sees the whole batch in every CTA,
+//      so all CTAs take the same decision without talking to each other
+//   B  entries of different subtrees never meet below level ls: the CTA sorts its entries if they are not
+//      ascending (bitonic, shared memory), keeps the LAST of equal keys (highest batch position: last write wins),
+//      and runs the static merge-tree walk of tree_update_sorted for levels 0..ls-1 (a warp-only walk with
+//      __syncwarp when it has <= 32 entries, which is the normal case: 512 draws / 128 subtrees)
+//   C  __threadfence + a ticket: the CTA that draws the last ticket re-derives the G - 1 nodes above level ls from
+//      the G subtree roots (untouched roots are re-added to the value they already hold, by the tree invariant),
+//      folds the batch maximum into max_leaf and resets the ticket for the next launch.
+// A CTA with more than kPartCap distinct entries (only possible for n > 512 on a heavily skewed batch) walks its
+// levels through global memory like the generic body -- slower, still correct, still independent of the others.
+// Parents are fl(left + right) of the current children everywhere: bit-identical to the reference update.
+constexpr int kPartThreads = 512;
+constexpr int kPartCap = 512;       // distinct entries a CTA walks out of shared memory
+constexpr int kPartMaxN = 4096;     // largest batch served by this kernel
+constexpr int kPartMaxCut = 7;      // at most 128 subtrees
+constexpr int kPartPosBits = 12;    // batch position inside the 64-bit sort key (kPartMaxN = 2^12)
+
+__host__ __device__ __forceinline__ int part_cut(int levels) {
+    const int c = levels - 6;
+    return c < 0 ? 0 : (c > kPartMaxCut ? kPartMaxCut : c);
+}
+__host__ __device__ __forceinline__ size_t part_dyn_smem(int levels) {
+    return sizeof(unsigned long long) * kPartMaxN + sizeof(double) * (size_t)kPartCap * (size_t)(levels - part_cut(levels) + 1);
+}
+
+// The merge-tree walk of one subtree.  kWarp: the caller is warp 0 alone and the subtree has <= 32 entries.
+template <bool kWarp>
+__device__ __forceinline__ void part_walk(const TreeDev &t, double *park, double *s_val, const unsigned *s_key,
+                                          const double *s_w, short *s_hb, short *s_next, int m, int ls, int tid) {
+    bool alive = tid < m;
+    unsigned key = 0;
+    double val = 0.0;
+    int hb = -1;
+    if (alive) {
+        key = s_key[tid];
+        val = s_w[tid];
+        hb = tid == 0 ? ls : 31 - __clz(s_key[tid - 1] ^ key);      // < ls for tid > 0: same subtree
+        s_hb[tid] = (short)hb;
+        s_next[tid] = (short)(tid + 1);
+        const int lim = hb < ls ? hb : ls - 1;
+        double pre[kSortedLevels];
+#pragma unroll
+        for (int l = 0; l < kSortedLevels; ++l)
+            if (l <= lim) pre[l] = __ldcg(t.W + level_off(t, l) + ((key >> l) ^ 1u));
+#pragma unroll
+        for (int l = 0; l < kSortedLevels; ++l)
+            if (l <= lim) park[l * kPartCap + tid] = pre[l];
+    }
+    const double leaf_val = val;
+    unsigned wrote = 0;
+    if (kWarp) __syncwarp();
+    else __syncthreads();
+#pragma unroll 1
+    for (int l = 0; l < ls; ++l) {
+        if (alive && hb == l) {          // right child whose left sibling is touched too: hand over, retire
+            s_val[tid] = val;
+            alive = false;
+        }
+        if (kWarp) __syncwarp();
+        else __syncthreads();
+        if (alive) {
+            const int j = s_next[tid];
+            double other;
+            if (j < m && s_hb[j] == l) {
+                other = s_val[j];
+                s_next[tid] = s_next[j];
+            } else {
+                other = park[l * kPartCap + tid];
+            }
+            val = val + other;           // left + right (IEEE addition is commutative)
+            park[l * kPartCap + tid] = val;
+            wrote |= 1u << l;
+        }
+    }
+    if (tid < m) {
+        t.W[key] = leaf_val;
+        for (int l = 0; l < ls; ++l)
+            if (wrote & (1u << l)) t.W[level_off(t, l + 1) + (key >> (l + 1))] = park[l * kPartCap + tid];
+    }
+}
+
+template <typename WT>
+__global__ void __launch_bounds__(kPartThreads) tree_update_part(TreeDev t, const int64_t *__restrict__ idx,
+                                                                 const WT *__restrict__ w,
+                                                                 const uint8_t *__restrict__ valid, int n,
+                                                                 Normalize nz, int gen) {
+    MB_DYNAMIC_SMEM(dyn);
+    unsigned long long *s_ent = reinterpret_cast<unsigned long long *>(dyn);      // [kPartMaxN] (leaf << 12) | position
+    double *park = reinterpret_cast<double *>(dyn + sizeof(unsigned long long) * kPartMaxN);   // [ls][kPartCap]
+    __shared__ double s_val[kPartCap];
+    __shared__ unsigned s_key[kPartCap];
+    __shared__ double s_w[kPartCap];
+    __shared__ short s_hb[kPartCap];
+    __shared__ short s_next[kPartCap];
+    __shared__ int s_warp[kPartThreads / 32];
+    __shared__ double s_red[kPartThreads / 32];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int kWarps = kPartThreads / 32;
+    const int levels = t.depth - 1;
+    const int cut = part_cut(levels);
+    const int ls = levels - cut;
+    const unsigned rank = blockIdx.x;
+    // ---- A: scan the whole batch, keep my subtree's entries in batch order
+    int m = 0;
+    bool oob = false;
+    double mx = -INFINITY;
+    for (int base = 0; base < n; base += kPartThreads) {
+        const int i = base + tid;
+        bool mine = false;
+        int64_t k = 0;
+        if (i < n && (!valid || valid[i])) {
+            k = idx[i];
+            if (k < 0 || k >= t.size) oob = true;
+            else mine = (unsigned)(k >> ls) == rank;
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, mine);
+        if (lane == 0) s_warp[wid] = __popc(ballot);
+        __syncthreads();
+        int before = 0, tot = 0;
+#pragma unroll
+        for (int j = 0; j < kWarps; ++j) {
+            if (j < wid) before += s_warp[j];
+            tot += s_warp[j];
+        }
+        if (mine) {
+            s_ent[m + before + __popc(ballot & ((1u << lane) - 1u))] =
+                ((unsigned long long)k << kPartPosBits) | (unsigned long long)i;
+            mx = fmax(mx, normalized_weight(w[i], nz));      // max over ALL written weights, duplicates included (:175)
+        }
+        m += tot;
+        __syncthreads();
+    }
+    if (__syncthreads_or(oob ? 1 : 0)) {   // every CTA sees the same batch: all of them leave, nothing is written
+        if (rank == 0 && tid == 0) {
+            t.st->err = MB_ERR_INDEX_OOB;
+            t.st->err_gen = gen;
+        }
+        return;
+    }
+    if (m > 0) {   // (uniform per CTA)
+        mx = mb::warp_max(mx);
+        if (lane == 0) s_red[wid] = mx;
+        // ---- B1: ascending?  (a batch that came out of the stratified draw is; merged shard blocks are not)
+        bool unsorted = false;
+        for (int i = tid + 1; i < m; i += kPartThreads) unsorted |= s_ent[i - 1] > s_ent[i];
+        if (__syncthreads_or(unsorted ? 1 : 0)) {
+            int p2 = 1;
+            while (p2 < m) p2 <<= 1;
+            for (int i = m + tid; i < p2; i += kPartThreads) s_ent[i] = ~0ull;
+            __syncthreads();
+            for (int k2 = 2; k2 <= p2; k2 <<= 1)
+                for (int j = k2 >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < p2; i += kPartThreads) {
+                        const int q = i ^ j;
+                        if (q > i) {
+                            const unsigned long long a = s_ent[i], b = s_ent[q];
+                            if ((a > b) == ((i & k2) == 0)) {
+                                s_ent[i] = b;
+                                s_ent[q] = a;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+        }
+        if (tid == 0) {
+            double bm = s_red[0];
+            for (int j = 1; j < kWarps; ++j) bm = fmax(bm, s_red[j]);
+            if (bm > -INFINITY) atomic_max_f64(&t.st->batch_max, bm);
+        }
+        // ---- B2: distinct leaves (the last of equal keys carries the highest batch position)
+        int distinct = 0;
+        for (int base = 0; base < m; base += kPartThreads) {
+            const int i = base + tid;
+            const bool win = i < m && (i == m - 1 || (s_ent[i + 1] >> kPartPosBits) != (s_ent[i] >> kPartPosBits));
+            const unsigned ballot = __ballot_sync(0xffffffffu, win);
+            if (lane == 0) s_warp[wid] = __popc(ballot);
+            __syncthreads();
+            int before = 0, tot = 0;
+#pragma unroll
+            for (int j = 0; j < kWarps; ++j) {
+                if (j < wid) before += s_warp[j];
+                tot += s_warp[j];
+            }
+            const int pos = distinct + before + __popc(ballot & ((1u << lane) - 1u));
+            if (win && pos < kPartCap) {
+                const unsigned long long e = s_ent[i];
+                s_key[pos] = (unsigned)(e >> kPartPosBits);
+                s_w[pos] = normalized_weight(w[(int)(e & ((1u << kPartPosBits) - 1u))], nz);
+            }
+            distinct += tot;
+            __syncthreads();
+        }
+        if (distinct <= 32) {
+            if (wid == 0) part_walk<true>(t, park, s_val, s_key, s_w, s_hb, s_next, distinct, ls, tid);
+        } else if (distinct <= kPartCap) {
+            part_walk<false>(t, park, s_val, s_key, s_w, s_hb, s_next, distinct, ls, tid);
+        } else {
+            // skewed large batch: level-synchronous recompute through global memory, my entries only
+            for (int i = tid; i < m; i += kPartThreads) {
+                const unsigned long long e = s_ent[i];
+                if (i == m - 1 || (s_ent[i + 1] >> kPartPosBits) != (e >> kPartPosBits))
+                    t.W[e >> kPartPosBits] = normalized_weight(w[(int)(e & ((1u << kPartPosBits) - 1u))], nz);
+            }
+            for (int l = 1; l <= ls; ++l) {
+                __syncthreads();
+                const double *below = t.W + level_off(t, l - 1);
+                double *here = t.W + level_off(t, l);
+                for (int i = tid; i < m; i += kPartThreads) {
+                    const int64_t node = (int64_t)(s_ent[i] >> kPartPosBits) >> l;
+                    const double2 c = __ldcg(reinterpret_cast<const double2 *>(below + 2 * node));
+                    here[node] = c.x + c.y;
+                }
+            }
+        }
+    }
+    // ---- C: ticket; the last CTA lifts the levels above the cut
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&t.st->ticket, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int G = 1 << cut;
+    if (tid < G) s_val[tid] = __ldcg(t.W + level_off(t, ls) + tid);
+    for (int b = 1; b <= cut; ++b) {
+        __syncthreads();
+        double v = 0.0;
+        const bool on = tid < (G >> b);
+        if (on) v = s_val[2 * tid] + s_val[2 * tid + 1];
+        __syncthreads();
+        if (on) {
+            s_val[tid] = v;
+            t.W[level_off(t, ls + b) + tid] = v;
+        }
+    }
+    if (tid == 0) {
+        // max_leaf = max(np.max(weights), max_leaf): the new value (and its dtype) wins ties (:175)
+        const double bm = __ldcg(&t.st->batch_max);
+        if (bm > -INFINITY && !(t.st->max_leaf > bm)) {
+            t.st->max_leaf = bm;
+            t.st->max_is_f32 = sizeof(WT) == 4 ? 1 : 0;
+        }
+        t.st->batch_max = -INFINITY;
+        t.st->ticket = 0;
+    }
+}

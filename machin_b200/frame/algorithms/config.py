@@ -215,4 +215,6 @@ def init_a3c(cls, config, model_device):
                                  lr_scheduler=lr_scheduler, lr_scheduler_args=f["lr_scheduler_args"] or ((), ()),
                                  lr_scheduler_kwargs=f["lr_scheduler_kwargs"] or ({}, {}), device=device)
     del f["criterion"]
+    if f.get("replay_device") in (None, "cpu"):
+        f["replay_device"] = None                   # HBM of the model's device (there is no host replay memory)
     return cls(*models, criterion, tuple(servers), **f)

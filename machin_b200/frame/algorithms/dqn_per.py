@@ -19,7 +19,7 @@ from ... import ops
 from ..buffers import PrioritizedBuffer
 from ..transition import Transition
 from .base import TorchFramework
-from .utils import hard_update, model_device, safe_call, soft_update
+from .utils import capture_safe, hard_update, model_device, safe_call, soft_update
 
 
 class DQNPer(TorchFramework):
@@ -187,7 +187,7 @@ class DQNPer(TorchFramework):
             self.qnet_optim.zero_grad(set_to_none=True)
         from ..._lib import lib
         launched = lib.mb_launch_count()
-        with t.cuda.graph(graph):
+        with capture_safe(), t.cuda.graph(graph):
             self._static_loss = self._step(True, True, self._u_static, True)
         self._graph = graph
         self.graph_launches = lib.mb_launch_count() - launched   # libmachin_b200 kernels per replay

@@ -68,3 +68,21 @@ def soft_update(target_net: nn.Module, source_net: nn.Module, update_rate) -> No
     """target = target * (1 - rate) + source * rate, one kernel per parameter block (csrc/td.cu)."""
     with t.no_grad():
         ops.soft_update(target_net, source_net, update_rate)
+
+
+class capture_safe:
+    """Context for CUDA-graph capture of a user model: ``torch.distributions`` validates its arguments with a
+    host-synchronising ``_is_all_true`` (illegal while a stream is capturing, and a failed capture leaves torch's
+    CUDA generator unusable for the rest of the process), so validation is off inside and restored after.
+    The warm-up iterations run outside, with validation on."""
+
+    def __enter__(self):
+        import torch.distributions as D
+        self._was = D.Distribution._validate_args
+        D.Distribution.set_default_validate_args(False)
+        return self
+
+    def __exit__(self, *exc):
+        import torch.distributions as D
+        D.Distribution.set_default_validate_args(self._was)
+        return False

@@ -15,7 +15,7 @@ import numpy as np
 import torch as t
 
 from ... import _lib
-from ..._lib import lib
+from ..._lib import lib, PER_PARAMS_BYTES
 from ..transition import TransitionBase
 from .buffer import Buffer
 from .weight_tree import WeightTree
@@ -108,14 +108,15 @@ class PrioritizedBuffer(Buffer):
         draw can be replayed inside a CUDA graph while they change.  ``curr_beta`` is advanced on the
         device by the captured step (:meth:`advance_beta_device`) and mirrored on the host."""
         if getattr(self, "_params_raw", None) is None:
-            self._params_raw = t.zeros(32, dtype=t.uint8, device=self.buffer_device)
+            self._params_raw = t.zeros(PER_PARAMS_BYTES, dtype=t.uint8, device=self.buffer_device)
             self._params_f64 = self._params_raw.view(t.float64)
             self._params_i64 = self._params_raw.view(t.int64)
         self.sync_graph_params()
 
     def sync_graph_params(self):
+        # every field of mb_per_params: beta, all_weight_sum (0 = read the root), n_stored, step, n_draw
         host = t.tensor([float(self.curr_beta), 0.0], dtype=t.float64).view(t.uint8)
-        ints = t.tensor([len(self.storage), 0], dtype=t.int64).view(t.uint8)
+        ints = t.tensor([len(self.storage), 0, 0], dtype=t.int64).view(t.uint8)
         self._params_raw.copy_(t.cat([host, ints]))
 
     def advance_beta_device(self):

@@ -5,10 +5,9 @@ Replaces, on the data path, machin/parallel/server/param_server.py:21-493 and or
 Here the parameters travel as ONE flat byte buffer ``[all tensors of state_dict | version i64]`` in a
 single broadcast from the pushing member; the ordered server's version chain
 (ordered_server.py:112-128: a push is accepted iff the stored newest version equals ``prev_version``)
-becomes a monotonically increasing ``pp_version`` that rides in the same message.
+is kept: the stored newest version is replicated on every member and decided from a 16-byte all-gather.
 
-SPMD convention: in a synchronisation round the pushing member calls :meth:`push` and every other
-member calls :meth:`pull`; both enter the same broadcast.
+SPMD convention: in a synchronisation round every member calls :meth:`push` or :meth:`pull`.
 """
 from typing import List
 
@@ -20,12 +19,26 @@ def _state_tensors(model: t.nn.Module) -> List[t.Tensor]:
 
 
 class PushPullModelServer:
+    """Versioned weight exchange (param_server.py:21-91 over ordered_server.py:100-142).
+
+    The reference's server process keeps ``{version: state_dict}`` and accepts a push iff the newest stored
+    version equals the pusher's ``prev_version`` (``ordered_server.py:112-128``); a rejected pusher pulls the
+    newest parameters instead (``param_server.py:49-71``).  Here that storage is a flat device buffer
+    ``[version i64 | pad | tensors...]`` replicated on every member: a synchronisation round is ONE all-gather
+    of 16 bytes per member ``(pushing?, prev_version)`` -- the order in which the reference's lock would see
+    the requests is member order -- and, if a push is accepted, ONE broadcast of the flat buffer from the
+    accepted pusher.  Rejected pushers and pullers load from their local replica.
+
+    SPMD convention: in a round every member calls :meth:`push` or :meth:`pull`."""
+
     def __init__(self, model_name: str, group, src_index: int = 0, lockstep: bool = False):
-        """``lockstep``: every round has exactly one push and every other member pulls it, so the version
-        is known without reading it back from the device (no host synchronisation in :meth:`pull`)."""
+        """``lockstep``: every round has exactly one push, by member ``src_index`` whose chain is intact, and
+        every other member pulls it -- the outcome is known without the all-gather and without reading anything
+        back from the device (no host synchronisation; capturable in a CUDA graph)."""
         self.model_name, self.group, self.src_index = model_name, group, int(src_index)
         self.lockstep = bool(lockstep)
         self._flat = None
+        self._newest = None           # version of the stored parameters; None = key not created yet
 
     @staticmethod
     def _layout(tensors):
@@ -41,36 +54,59 @@ class PushPullModelServer:
             self._flat = t.zeros(nbytes, dtype=t.uint8, device=self.group.device)
         return self._flat
 
+    def _views(self, flat, tensors, offs):
+        return [flat[o:o + x.numel() * x.element_size()].view(x.dtype).view(x.shape) for x, o in zip(tensors, offs)]
+
+    def _load(self, model, flat, tensors, offs):
+        with t.no_grad():
+            t._foreach_copy_(tensors, self._views(flat, tensors, offs))   # one multi-tensor launch
+
+    def _round(self, model: t.nn.Module, pushing: bool):
+        """One synchronisation round.  Returns (accepted member or None, flat, tensors, offs)."""
+        tensors = _state_tensors(model)
+        offs, total = self._layout(tensors)
+        flat = self._buffer(total)
+        me = self.group.index
+        prev = int(getattr(model, "pp_version", 0))
+        if self.lockstep:
+            winner, version = self.src_index, (self._newest or 0) + 1
+        else:
+            meta = t.tensor([1 if pushing else 0, prev], dtype=t.int64, device=self.group.device)
+            seen = self.group.all_gather_f64(meta).tolist()          # (dtype-agnostic gather) [P, 2]
+            winner = next((m for m, (is_push, pv) in enumerate(seen)
+                           if is_push and (self._newest is None or pv == self._newest)), None)   # :116-126
+            version = None if winner is None else seen[winner][1] + 1
+        if winner is not None:
+            if winner == me:
+                t._foreach_copy_(self._views(flat, tensors, offs), [x.detach() for x in tensors])
+                flat[0:8].view(t.int64).fill_(version)
+            self.group.broadcast(flat, winner)
+            self._newest = version
+        return winner, flat, tensors, offs
+
     def push(self, model: t.nn.Module, pull_on_fail=True) -> bool:
-        """param_server.py:36-71.  Always succeeds here: there is one pusher per round."""
+        """param_server.py:36-71: True iff the server accepted ``pp_version + 1`` on top of ``pp_version``;
+        otherwise (someone else extended the chain first) the newest parameters are loaded into ``model``."""
         if not hasattr(model, "pp_version"):
             model.pp_version = 0
-        tensors = _state_tensors(model)
-        offs, total = self._layout(tensors)
-        flat = self._buffer(total)
-        views = [flat[o:o + x.numel() * x.element_size()].view(x.dtype).view(x.shape) for x, o in zip(tensors, offs)]
-        t._foreach_copy_(views, [x.detach() for x in tensors])     # one multi-tensor launch
-        model.pp_version += 1
-        flat[0:8].view(t.int64).fill_(model.pp_version)
-        self.group.broadcast(flat, self.src_index)
-        return True
+        winner, flat, tensors, offs = self._round(model, True)
+        if winner == self.group.index:
+            model.pp_version += 1
+            return True
+        if pull_on_fail:
+            self._load(model, flat, tensors, offs)
+            model.pp_version = self._newest
+        return False
 
     def pull(self, model: t.nn.Module) -> bool:
-        """param_server.py:73-91: load the newest parameters iff they are newer than ``pp_version``."""
-        tensors = _state_tensors(model)
-        offs, total = self._layout(tensors)
-        flat = self._buffer(total)
-        self.group.broadcast(flat, self.src_index)
-        if self.lockstep:
-            version = getattr(model, "pp_version", 0) + 1
-        else:
-            version = int(flat[0:8].view(t.int64).item())
-            if hasattr(model, "pp_version") and version <= model.pp_version:
-                return False
-        with t.no_grad():
-            views = [flat[o:o + x.numel() * x.element_size()].view(x.dtype).view(x.shape) for x, o in zip(tensors, offs)]
-            t._foreach_copy_(tensors, views)
-        model.pp_version = version
+        """param_server.py:73-91: load the newest parameters iff they are newer than ``pp_version``.
+        False only while nothing has ever been pushed."""
+        _, flat, tensors, offs = self._round(model, False)
+        if self._newest is None:
+            return False
+        if self.lockstep or not hasattr(model, "pp_version") or model.pp_version < self._newest:
+            self._load(model, flat, tensors, offs)
+            model.pp_version = self._newest
         return True
 
 

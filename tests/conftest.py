@@ -9,13 +9,6 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-# Tests written after round 1's GPU budget was spent have never run on hardware: they are reported as
-# xpass / xfail (non-strict) until their first run on a B200 is looked at, so that a mistake in a NEW test
-# cannot mask the validated suite behind `-x`.  Remove the mark once the test has been seen to pass.
-first_hardware_run_pending = pytest.mark.xfail(
-    reason="new in round 1 after the GPU budget was spent: first hardware run pending", strict=False)
-
-
 def run_group(cmd, timeout):
     """subprocess.run for torchrun launches: the launcher and every worker live in ONE new process group that
     is killed as a whole on timeout (a worker stuck in a collective must not outlive the test)."""

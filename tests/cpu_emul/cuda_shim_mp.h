@@ -103,6 +103,7 @@ inline unsigned __ballot_sync(unsigned, int pred) {
     shim::warp_barrier[w]->arrive_and_wait();
     return r;
 }
+inline void __syncwarp() { shim::warp_barrier[threadIdx.x >> 5]->arrive_and_wait(); }   // all 32 lanes of the warp call it
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 inline double __shfl_xor_sync(unsigned, double v, int o) {
     const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -132,6 +133,7 @@ inline int atomicMax(int *a, int v) {
     while (old < v && !__atomic_compare_exchange_n(a, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
     return old;
 }
+inline int atomicAdd(int *a, int v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicCAS(unsigned long long *a, unsigned long long cmp, unsigned long long val) {
     __atomic_compare_exchange_n(a, &cmp, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
     return cmp;

@@ -4,7 +4,8 @@
 //        f64 max_leaf, f64 W[2^depth - 1], i64 idx[n], (f32|f64) w[n], u8 valid[n] (if has_valid)
 //   out: f64 W[2^depth - 1], f64 max_leaf, i64 max_is_f32, i64 err
 // variant: 0 tree_update_sorted (GPU-validated; checks the shim), 1 v2<CB=0, async>, 2 v2<CB=3, barrier>,
-//          3 v2<CB=3, async>, 4 tree_update_kernel<.., false> (generic single-CTA body)
+//          3 v2<CB=3, async>, 4 tree_update_kernel<.., false> (generic single-CTA body),
+//          5 tree_update_part (one CTA per subtree, CTAs run one after the other: the kernel has no cross-CTA wait)
 #include "cuda_shim_mp.h"
 
 #include "machin_b200.h"
@@ -26,6 +27,11 @@ static int run(int variant, TreeDev t, const int64_t *idx, const WT *w, const ui
     case 2: return shim::launch(8, threads, dyn, [=] { tree_update_sorted_v2<WT, 3, false>(t, idx, w, valid, n, nz, 1); });
     case 3: return shim::launch(8, threads, dyn, [=] { tree_update_sorted_v2<WT, 3, true>(t, idx, w, valid, n, nz, 1); });
     case 4: return shim::launch(1, threads, 0, [=] { tree_update_kernel<WT, false>(t, idx, w, valid, (int64_t)n, nz, 1); });
+    case 5: {
+        const int levels = t.depth - 1;
+        return shim::launch(1, kPartThreads, part_dyn_smem(levels),
+                            [=] { tree_update_part<WT>(t, idx, w, valid, n, nz, 1); }, 1 << part_cut(levels));
+    }
     }
     return 9;
 }

@@ -19,7 +19,6 @@ def main():
     dist.init_process_group("nccl", device_id=t.device("cuda", local))
     from machin_b200.frame.buffers import DistributedPrioritizedBuffer
     from machin_b200.parallel import ShardGroup
-    from machin_b200.parallel.server import PushPullModelServer
     from oracle import per as oper
     from oracle.sumtree import OracleTree
 
@@ -43,6 +42,8 @@ def main():
         assert n == 0
         buf.update_priority(None, None)
     assert buf.all_size() == 5 * (world - 1)
+    if rank == 0:
+        print(f"reference distributed golden ok (world {world})", flush=True)
     # ---- 2. every member a learner: parity of each shard's draws / write-backs against the oracle
     np.random.seed(10 + rank)
     cap, S = 4096, 84
@@ -100,15 +101,20 @@ def main():
     got, want = buf.wt_tree.weights, ora.weights
     assert np.allclose(got, want, rtol=1e-6, atol=0), np.abs(got - want).max()
     assert got[victim] == leaf0[victim]
-    # ---- 3. weight broadcast with version
-    server = PushPullModelServer("m", group, 0)
-    net = t.nn.Linear(8, 4).cuda()
     if rank == 0:
-        with t.no_grad():
-            net.weight.fill_(3.0)
-        server.push(net)
-    else:
-        assert server.pull(net) and float(net.weight.sum()) == 96.0 and net.pp_version == 1
+        print(f"sharded draw / gather / version-filtered write-back ok (world {world}): tainted slot {victim} kept", flush=True)
+    # ---- 3. weight server over NCCL: the reference's goldens 11/12/13, a pull that is not newer, a rejected push on
+    #         a stale chain, two pushers in one round (param_server.py:36-91, ordered_server.py:112-128)
+    from server_cases import grad_expect, grad_server_case, model_server_case
+    dev = t.device("cuda", local)
+    assert model_server_case(rank, world, device=dev)
+    if rank == 0:
+        print(f"model server ok (world {world}): goldens 11/12/13, stale pull, rejected push, racing pushers", flush=True)
+    # ---- 4. A3C gradient server over NCCL (param_server.py:411-493; test_param_server.py:108-173)
+    for method in ("mean", "sum"):
+        assert grad_server_case(rank, world, method, device=dev)
+        if rank == 0:
+            print(f"grad server ok (world {world}): {method} -> {grad_expect(method, world)}", flush=True)
     dist.barrier()
     if rank == 0:
         print("dist ok")

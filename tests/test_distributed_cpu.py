@@ -173,46 +173,9 @@ def test_sharded_all_learners_and_version_filter():
     assert all(run_multi(_all_learners, 2))
 
 
-class _Lin(t.nn.Module):
-    def __init__(self):
-        super().__init__()
-        self.fc1 = t.nn.Linear(1, 1, bias=False)
-        self.fc2 = t.nn.Linear(1, 1, bias=False)
-        self.fc3 = t.nn.Linear(1, 1, bias=False)
-        with t.no_grad():
-            self.fc1.weight.fill_(1)
-            self.fc2.weight.fill_(2)
-            self.fc3.weight.fill_(3)
-
-    def forward(self, x):
-        return self.fc3(self.fc2(self.fc1(x)))
-
-
 def _model_server(rank, world):
-    from machin_b200.parallel.group import ShardGroup
-    from machin_b200.parallel.server import PushPullModelServer
-    group = ShardGroup("group")
-    server = PushPullModelServer("model", group, src_index=0)
-    model = _Lin()
-    for i in range(10):                       # test_param_server.py:92-101: weights +1 per push -> 11,12,13
-        if rank == 0:
-            with t.no_grad():
-                for p in model.parameters():
-                    p += 1
-            assert server.push(model)
-        else:
-            assert server.pull(model)
-    assert [model.fc1.weight.item(), model.fc2.weight.item(), model.fc3.weight.item()] == [11, 12, 13]
-    assert model.pp_version == 10
-    # stale pull: receiver already holds a newer version -> not loaded
-    if rank == 0:
-        model.pp_version = 3
-        server.push(model)
-        return True
-    with t.no_grad():
-        model.fc1.weight.fill_(-7)
-    assert server.pull(model) is False and model.fc1.weight.item() == -7
-    return True
+    from server_cases import model_server_case
+    return model_server_case(rank, world)
 
 
 def test_model_server_push_pull_golden():
@@ -220,23 +183,9 @@ def test_model_server_push_pull_golden():
 
 
 def _grad_server(rank, world, method, expect):
-    from machin_b200.parallel.group import ShardGroup
-    from machin_b200.parallel.server import PushPullGradServer
-    group = ShardGroup("group")
-    server = PushPullGradServer("server", group, primary_index=0, reduce_method=method, pushes_per_reduce=2)
-    model = _Lin()
-    if rank == 0:
-        server.manage_model(model, t.optim.SGD(model.parameters(), lr=1.0))
-    for i in range(2):                        # test_param_server.py:108-173: 2 workers x 2 pushes
-        if rank == 0:
-            server.push(None)                 # the server process itself has no gradients
-        else:
-            model.zero_grad()
-            model(t.ones([1, 1])).backward()  # grads 6, 3, 2
-            server.push(model)
-    got = [model.fc1.weight.item(), model.fc2.weight.item(), model.fc3.weight.item()]
-    assert got == list(expect), got
-    return True
+    from server_cases import grad_server_case, grad_expect
+    assert grad_expect(method, world) == tuple(expect)
+    return grad_server_case(rank, world, method)
 
 
 @pytest.mark.parametrize("method,expect", [("mean", (-5, -1, 1)), ("sum", (-23, -10, -5))])

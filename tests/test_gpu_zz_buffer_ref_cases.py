@@ -6,9 +6,9 @@ scalar attributes, lists for custom attributes, "*" collecting the remaining cus
 import pytest
 import torch as t
 
-from conftest import first_hardware_run_pending
 
-pytestmark = [pytest.mark.gpu, first_hardware_run_pending]
+
+pytestmark = [pytest.mark.gpu]
 
 BUFFER_SIZE, SAMPLE_BUFFER_SIZE = 5, 10
 REQUIRED = ("state", "action", "next_state", "reward", "terminal")

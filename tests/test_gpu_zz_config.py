@@ -5,10 +5,10 @@ import numpy as np
 import pytest
 import torch as t
 
-from conftest import first_hardware_run_pending
+
 from test_config_cpu import Actor, Critic, QNet  # noqa: F401  (resolved by name from this module's globals)
 
-pytestmark = [pytest.mark.gpu, first_hardware_run_pending]
+pytestmark = [pytest.mark.gpu]
 S, A = 4, 3
 
 

@@ -7,10 +7,10 @@ import numpy as np
 import pytest
 import torch as t
 
-from conftest import GOLDEN, first_hardware_run_pending
+from conftest import GOLDEN
 from test_gpu_algorithms import Actor, Critic, _flat, _load_flat
 
-pytestmark = [pytest.mark.gpu, first_hardware_run_pending]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("release_after", [None, 1])

@@ -8,10 +8,10 @@ import numpy as np
 import pytest
 import torch as t
 
-from conftest import GOLDEN, first_hardware_run_pending
+from conftest import GOLDEN
 from test_gpu_algorithms import QNet, _flat, _load_flat
 
-pytestmark = [pytest.mark.gpu, first_hardware_run_pending]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("mode", ["vanilla", "fixed_target", "double"])

@@ -5,9 +5,9 @@ import sys
 import pytest
 import torch as t
 
-from conftest import ROOT, run_group, first_hardware_run_pending
+from conftest import ROOT, run_group
 
-pytestmark = [pytest.mark.gpu, first_hardware_run_pending]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.timeout(900, method="thread")      # above the 600 s / 300 s limit of the torchrun launch itself

@@ -5,9 +5,9 @@ import numpy as np
 import pytest
 import torch as t
 
-from conftest import first_hardware_run_pending
 
-pytestmark = [pytest.mark.gpu, first_hardware_run_pending]
+
+pytestmark = [pytest.mark.gpu]
 
 
 class QNet(t.nn.Module):

@@ -6,11 +6,11 @@ import numpy as np
 import pytest
 import torch as t
 
-from conftest import first_hardware_run_pending
+
 from oracle import rainbow as orb
 from test_rainbow_cpu import DistQNet, load_flat, net_outputs, ref  # noqa: F401  (ref: fixture)
 
-pytestmark = [pytest.mark.gpu, first_hardware_run_pending]
+pytestmark = [pytest.mark.gpu]
 
 
 def run_device(qd, nq, tq, action, value, terminal, isw, v_min, v_max, disc_n):

@@ -3,10 +3,10 @@ scheduler; int32 actions and integer rewards) through the product's classes on t
 CPU dry runs in tests/test_algorithm_ref_cases_cpu.py, here with real buffers and kernels."""
 import pytest
 
-from conftest import first_hardware_run_pending
+
 from test_algorithm_ref_cases_cpu import ddpg_cases, value_based_cases
 
-pytestmark = [pytest.mark.gpu, first_hardware_run_pending]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("kind", ["DQNPer", "DQN", "RAINBOW"])

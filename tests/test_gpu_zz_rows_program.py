@@ -6,9 +6,9 @@ import numpy as np
 import pytest
 import torch as t
 
-from conftest import GOLDEN, first_hardware_run_pending
+from conftest import GOLDEN
 
-pytestmark = [pytest.mark.gpu, first_hardware_run_pending]
+pytestmark = [pytest.mark.gpu]
 
 
 def _flat(m):

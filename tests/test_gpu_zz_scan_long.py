@@ -4,12 +4,12 @@ import numpy as np
 import pytest
 import torch as t
 
-from conftest import first_hardware_run_pending
+
 from oracle import gae as ogae
 from oracle import vtrace as ovt
 from test_gpu_rows_td_scan import _vtrace_case
 
-pytestmark = [pytest.mark.gpu, first_hardware_run_pending]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("lengths,use_offsets", [([100] * 300, True), ([100] * 300, False), ([7000], True), ([7000], False),

@@ -5,10 +5,10 @@ import numpy as np
 import pytest
 import torch as t
 
-from conftest import first_hardware_run_pending
+
 from oracle.sumtree import OracleTree
 
-pytestmark = [pytest.mark.gpu, first_hardware_run_pending]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(params=["cluster", "async", "cluster+async"])

@@ -17,7 +17,7 @@ from conftest import ROOT
 from oracle.sumtree import OracleTree
 
 EMUL = os.path.join(ROOT, "tests", "cpu_emul")
-VARIANTS = {"sorted": 0, "v2_async": 1, "v2_cluster": 2, "v2_cluster_async": 3, "generic": 4}
+VARIANTS = {"sorted": 0, "v2_async": 1, "v2_cluster": 2, "v2_cluster_async": 3, "generic": 4, "part": 5}
 
 
 @pytest.fixture(scope="module")
@@ -88,7 +88,7 @@ def _indexes(rng, size, n, kind):
     return idx
 
 
-@pytest.mark.parametrize("variant", ["sorted", "v2_async", "v2_cluster", "v2_cluster_async"])
+@pytest.mark.parametrize("variant", ["sorted", "v2_async", "v2_cluster", "v2_cluster_async", "part"])
 @pytest.mark.parametrize("size,n,kind", CASES)
 def test_sorted_update_kernels_under_emulation(tree_emul, tmp_path, variant, size, n, kind):
     if n > 256 and "cluster" in variant:
@@ -103,7 +103,7 @@ def test_sorted_update_kernels_under_emulation(tree_emul, tmp_path, variant, siz
     assert max_leaf == tree.max_leaf
 
 
-@pytest.mark.parametrize("variant", ["sorted", "v2_async", "v2_cluster", "v2_cluster_async", "generic"])
+@pytest.mark.parametrize("variant", ["sorted", "v2_async", "v2_cluster", "v2_cluster_async", "generic", "part"])
 def test_unsorted_masked_and_out_of_range_under_emulation(tree_emul, tmp_path, variant):
     size, n = 3000, 64
     tree, rng = _tree(size, 5)
@@ -146,3 +146,49 @@ def test_priority_normalisation_float32_under_emulation(tree_emul, tmp_path):
     tree.update_leaf_batch(leaf, idx)
     assert err == 0 and is_f32 in (0, 1)
     assert np.array_equal(got, tree.weights)
+
+
+@pytest.mark.parametrize("size,n,kind", [
+    (1 << 15, 1500, "merged_blocks"),      # P ascending blocks concatenated (the sharded write-back), masked, duplicates across blocks
+    (1 << 15, 4096, "skewed"),             # > 512 distinct entries in ONE subtree: the global-memory walk of that CTA
+    (1 << 17, 700, "skewed_sorted"),       # ... 700 distinct ascending entries in one subtree of 1024 leaves
+    (50, 9, "tiny"),                       # depth 7: a single CTA, no cut
+    (1, 1, "one_leaf"),                    # depth 1: the leaf is the root
+])
+def test_partitioned_update_kernel_under_emulation(tree_emul, tmp_path, size, n, kind):
+    """tree_update_part: one CTA per subtree, batches up to 4096 in any order, with a mask and duplicates."""
+    tree, rng = _tree(size, 11 + n)
+    valid = None
+    if kind == "merged_blocks":
+        idx = np.concatenate([np.sort(rng.randint(0, size, size=n // 4)) for _ in range(4)])
+        idx = np.concatenate([idx, idx[:n - len(idx)]]).astype(np.int64)
+        idx[5] = idx[n // 2 + 3]
+        valid = rng.rand(n) < 0.8
+        idx[np.flatnonzero(~valid)[:3]] = size + 100           # masked-out entries may be out of range
+    elif kind == "skewed":
+        span = size >> part_cut_py(size)
+        idx = np.concatenate([rng.randint(3 * span, 4 * span, size=n - 200), rng.randint(0, size, size=200)]).astype(np.int64)
+    elif kind == "skewed_sorted":
+        span = size >> part_cut_py(size)
+        idx = np.sort(rng.choice(np.arange(2 * span, 3 * span), size=n, replace=False)).astype(np.int64)
+    else:
+        idx = rng.randint(0, size, size=n).astype(np.int64)
+    w = rng.exponential(size=n).astype(np.float32 if n % 2 else np.float64)
+    got, max_leaf, is_f32, err = run_kernel(tree_emul, str(tmp_path), "part", tree, idx, w, valid=valid)
+    if valid is not None:
+        tree.update_leaf_batch(w[valid], idx[valid])
+    else:
+        tree.update_leaf_batch(w, idx)
+    assert err == 0
+    assert np.array_equal(got, tree.weights)
+    assert max_leaf == tree.max_leaf
+    # a second launch on the result: the ticket was reset by the last CTA of the first
+    tree.weights[:] = got
+    got2, *_ , err2 = run_kernel(tree_emul, str(tmp_path), "part", tree, idx[:1], w[:1],
+                                 valid=None if valid is None else np.ones(1, dtype=bool))
+    tree.update_leaf_batch(w[:1], idx[:1]) if idx[0] < size else None
+
+
+def part_cut_py(size):
+    depth = int(np.ceil(np.log2(size))) + 1 if size > 1 else 1
+    return max(0, min(7, depth - 1 - 6))
