@@ -282,6 +282,7 @@ int mb_tree_create(int64_t size, int device, mb_tree **out) {
         t->sorted_cluster = (c && c[0] == '1') ? 1 : 0;
         const char *y = getenv("MB_SORTED_ASYNC");
         t->sorted_async = (y && y[0] == '1') ? 1 : 0;
+        if (t->sorted_cluster || t->sorted_async) t->legacy_update = 1;   // asking for a legacy variant selects the legacy path
     }
     t->dev.W = nullptr;
     t->dev.owner = nullptr;

@@ -54,6 +54,8 @@ def test_impala_captured_update_vs_reference():
     # an episode of another length: batches that contain it run eagerly, the others keep replaying
     imp.store_episode([dict(state={"state": t.zeros(1, S)}, action={"action": t.tensor([[0]])}, next_state={"state": t.zeros(1, S)},
                             reward=0.0, action_log_prob=-1.0, terminal=i == 6) for i in range(7)])
-    for _ in range(8):
+    # (four updates only: plain SGD at lr 0.01 on a summed squared error diverges on this toy problem -- the same
+    # schedule over host doubles reaches 1e9 at the sixth update and inf at the eighth)
+    for _ in range(4):
         pol, val = imp.update()
         assert np.isfinite(pol) and np.isfinite(val)
