@@ -43,6 +43,10 @@ def parse():
     p.add_argument("--steps", type=int, default=2000)
     p.add_argument("--warmup", type=int, default=50)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+                   help="BASELINE.json configuration: c2 APEX-DQN PER 10 M (default: the metric's configuration), c3 IMPALA "
+                        "1024 x T=20 on one GPU, c4 APEX-DDPG sharded learner (12.5 M rows per shard), c5 IMPALA actors -> "
+                        "learner over NCCL (bench_workloads.py)")
     p.add_argument("--replay-rows", type=int, default=10_000_000)
     p.add_argument("--batch", type=int, default=512)
     p.add_argument("--cpu-storage-rows", type=int, default=50_000)
@@ -552,7 +556,13 @@ def run_b200(a):
 
 if __name__ == "__main__":
     args = parse()
-    if args.impl == "reference":
+    if args.workload != "c2":
+        import bench_workloads as bw
+        if args.impl == "reference":
+            bw.run_reference(args)
+        else:
+            {"c3": bw.run_c3, "c4": bw.run_c4, "c5": bw.run_c5}[args.workload](args, ClockSampler)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "machin_b200.h"
 
 namespace mb {
@@ -75,7 +77,10 @@ __device__ __forceinline__ double warp_max(double v) {
 }
 
 // Pinned + device staging shared by the *_host entry points of one device.
+// `mu` is held for the whole of a *_host call (ensure -> memcpy -> launch -> synchronise -> copy-out): the library is
+// loaded with ctypes.CDLL (GIL released), so two Python threads may enter host entry points of one GPU at once.
 struct Staging {
+    std::mutex mu;
     int device = -1;
     cudaStream_t stream = nullptr;
     char *h = nullptr;

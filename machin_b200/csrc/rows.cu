@@ -5,11 +5,60 @@
 // insert (storage.py:85-114).  The device ring is an array of packed rows (`pitch` bytes, multiple of
 // 16); one warp moves one row with 16-byte accesses wherever offsets and pitches allow it, so a
 // sampled transition costs one contiguous HBM segment instead of one Python object per attribute.
+#include <stdlib.h>
+
 #include "mb_common.cuh"
 
 namespace {
 
 #include "rows_device.cuh"
+
+#include "rows_tma.cuh"   // rows_gather_bulk_kernel (cp.async.bulk / mbarrier)
+
+// MB_ROWS_LEGACY=1: the one-warp-per-row gather everywhere (A/B timing and the parity test of the two kernels)
+bool rows_legacy() {
+    const char *e = getenv("MB_ROWS_LEGACY");
+    return e && e[0] == '1';
+}
+
+// Bulk-copy gather if the wide fields qualify: every field whose offset / size / destination / pitch are multiples
+// of 16 leaves shared memory with one cp.async.bulk; it pays when those fields carry most of the bytes.
+bool launch_gather_bulk(const char *ring, int64_t pitch, int64_t capacity, const int64_t *index, int64_t n,
+                        const FieldList &fl, cudaStream_t s) {
+    if (rows_legacy() || (pitch & 15) || ((uintptr_t)ring & 15) || pitch > 48 * 1024) return false;
+    unsigned mask = 0;
+    int64_t wide = 0, all = 0;
+    for (int f = 0; f < fl.n; ++f) {
+        const mb_field &x = fl.f[f];
+        all += x.nbytes;
+        if (x.nbytes >= 16 && ((x.row_offset | x.nbytes | x.dense_pitch | (int64_t)(uintptr_t)x.d_dense) & 15) == 0) {
+            mask |= 1u << f;
+            wide += x.nbytes;
+        }
+    }
+    if (2 * wide < all) return false;
+    // rows per tile: enough tiles to cover every SM twice at small n, at most 16 rows and 12 KB per stage
+    int64_t R = n / (2 * mb::kNumSMs);
+    R = R < 1 ? 1 : (R > 16 ? 16 : R);
+    while (R > 1 && R * pitch > 12 * 1024) --R;
+    const int64_t stage = (R * pitch + 127) & ~(int64_t)127;
+    const size_t dyn = (size_t)(stage * kBulkStages);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(rows_gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        attr_set = true;
+    }
+    const int64_t n_tiles = (n + R - 1) / R;
+    int64_t per_sm = (int64_t)(200 * 1024) / (int64_t)(dyn + 1024);
+    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+    int64_t blocks = (int64_t)mb::kNumSMs * per_sm;
+    if (blocks > n_tiles) blocks = n_tiles;
+    rows_gather_bulk_kernel<<<(unsigned)blocks, kBulkThreads, dyn, s>>>(ring, pitch, capacity, index, n, fl, (int)R, mask);
+    return true;
+}
 
 int launch_rows(bool gather, void *ring, int64_t pitch, int64_t capacity, const int64_t *index,
                 int64_t first_slot, int64_t n, const mb_field *fields, int n_fields, cudaStream_t s) {
@@ -23,6 +72,10 @@ int launch_rows(bool gather, void *ring, int64_t pitch, int64_t capacity, const 
         fl.f[i] = fields[i];
         if (fields[i].row_offset < 0 || fields[i].nbytes < 0 || fields[i].row_offset + fields[i].nbytes > pitch)
             return MB_ERR_INVALID;
+    }
+    if (gather && launch_gather_bulk((const char *)ring, pitch, capacity, index, n, fl, s)) {
+        MB_LAUNCHED(1);
+        return MB_OK;
     }
     int64_t blocks = (n + 7) / 8;  // 8 warps (rows) per CTA
     const int64_t cap = (int64_t)mb::kNumSMs * 16;

@@ -83,6 +83,7 @@ int mb_vtrace_host(int device, const int64_t *h_offsets, int64_t n_episodes, int
     mb::DeviceGuard g(device);
     mb::Staging *st = mb::staging_for(device);
     if (!st) return MB_ERR_CUDA;
+    std::lock_guard<std::mutex> staging_lock(st->mu);
     const size_t S = (size_t)n_steps, fb = 4 * S;
     const size_t off_bytes = h_offsets ? 8 * (size_t)(n_episodes + 1) : 0;
     const size_t in_bytes = off_bytes + 5 * fb + ((S + 15) / 16) * 16;
@@ -128,6 +129,7 @@ int mb_gae_host(int device, const int64_t *h_offsets, int64_t n_episodes, int64_
     mb::DeviceGuard g(device);
     mb::Staging *st = mb::staging_for(device);
     if (!st) return MB_ERR_CUDA;
+    std::lock_guard<std::mutex> staging_lock(st->mu);
     const size_t S = (size_t)n_steps;
     const size_t off_bytes = h_offsets ? 8 * (size_t)(n_episodes + 1) : 0;
     const size_t o_r = off_bytes, o_cv = o_r + 8 * S, o_ncv = o_cv + 4 * S, o_t = o_ncv + 4 * S;

@@ -626,6 +626,7 @@ int mb_per_sample_multi(mb_tree *t, const double *d_uniform, int64_t n, int n_re
     mb::DeviceGuard g((t)->device);                           \
     mb::Staging *st = mb::staging_for((t)->device);           \
     if (!st) return MB_ERR_CUDA;                              \
+    std::lock_guard<std::mutex> _staging_lock(st->mu);        \
     {                                                         \
         int _r = st->ensure((hb), (db));                      \
         if (_r != MB_OK) return _r;                           \

@@ -153,7 +153,17 @@ class DQNPer(TorchFramework):
         (SGD, or Adam/AdamW with ``capturable=True``, which is switched on here) and a Q-net without
         data-dependent Python control flow.  torch's capture protocol needs ``warmup`` real updates
         first; networks, optimizer state, tree and beta are snapshotted before and restored in place
-        after, so enabling the graph does not change the training trajectory."""
+        after, so enabling the graph does not change the training trajectory.
+
+        Soft target updates only: a hard update every ``update_steps`` is a host-side decision that a replayed graph
+        would freeze at whatever it was during capture.  The same holds for a float learning rate changed by an
+        ``lr_scheduler``: use a tensor ``lr`` (updated in place) or keep such learners eager."""
+        if self.update_rate is None:
+            raise RuntimeError(f"{type(self).__name__}.enable_cuda_graph needs soft target updates (update_rate): the hard "
+                               "update every update_steps is decided on the host and cannot be replayed")
+        if hasattr(self, "qnet_lr_sch") and not all(t.is_tensor(g["lr"]) for g in self.qnet_optim.param_groups):
+            raise RuntimeError(f"{type(self).__name__}.enable_cuda_graph: an lr_scheduler changes a float learning rate that "
+                               "the captured optimizer step has baked in; give the optimizer a tensor lr or stay eager")
         buf = self.replay_buffer
         dev = buf.buffer_device
         fresh_optim = len(self.qnet_optim.state) == 0

@@ -93,3 +93,45 @@ def test_vtrace_and_gae_host_entry_points():
                             [float(x) for x in nv[sl]], eret, 0.97, lam)
             assert np.array_equal(ret[sl], np.array(eret)) and np.array_equal(gae[sl], np.array(egae))
             pos += n
+
+
+def test_host_entry_points_from_concurrent_threads():
+    """ctypes releases the GIL inside the library: two Python threads (an actor storing, a learner sampling) may be in
+    *_host entry points of the same GPU at once.  The per-device staging area is locked for the whole call, so each
+    thread's results equal the oracle's for its own tree."""
+    import threading
+    from machin_b200._lib import lib
+    errors = []
+
+    def worker(seed, size, rounds):
+        try:
+            rng = np.random.RandomState(seed)
+            h = C.c_void_p()
+            assert lib.mb_tree_create(size, 0, C.byref(h)) == 0
+            ora = OracleTree(size)
+            leaves = rng.exponential(size=size)
+            assert lib.mb_tree_build_host(h, _p(leaves), size) == 0
+            ora.update_all_leaves(leaves)
+            for r in range(rounds):
+                n = int(rng.randint(1, 3000))
+                idx = rng.randint(0, size, size=n).astype(np.int64)
+                w = rng.exponential(size=n)
+                assert lib.mb_tree_update_batch_host(h, _p(idx), _p(w), 1, n) == 0
+                ora.update_leaf_batch(w, idx)
+                q = rng.uniform(0, ora.get_weight_sum(), size=n)
+                got = np.empty(n, dtype=np.int64)
+                assert lib.mb_tree_find_host(h, _p(q), n, _p(got)) == 0
+                assert np.array_equal(got, ora.find_leaf_index(q)), (seed, r)
+                lw = np.empty(n)
+                assert lib.mb_tree_leaf_weight_host(h, _p(got), n, _p(lw)) == 0
+                assert np.array_equal(lw, ora.get_leaf_weight(got)), (seed, r)
+            assert lib.mb_tree_destroy(h) == 0
+        except BaseException as e:   # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(s, 20_000 + 977 * s, 40)) for s in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors

@@ -56,6 +56,9 @@ def graphed(fns, reps=20):
 
 
 def main():  # noqa: C901
+    from bench import ClockSampler          # nvidia-smi clocks / throttle reasons sampled during the whole run
+    sampler = ClockSampler(0)
+    sampler.start()
     out = {"peak_hbm_gbs": PEAK, "results": {}}
     R = out["results"]
     N = 10_000_000
@@ -100,8 +103,8 @@ def main():  # noqa: C901
         byt = (20 + 24 * (D - 1)) * nu
         R[f"tree_update_sorted_{nu}"] = {"us": s * 1e6, "alg_bytes_upper": byt, "GBps": byt / s / 1e9,
                                          "frac": byt / s / 1e9 / PEAK,
-                                         "variant": ("cluster " if os.environ.get("MB_SORTED_CLUSTER") == "1" else "single CTA ") +
-                                                    ("async walk" if os.environ.get("MB_SORTED_ASYNC") == "1" else "barrier walk")}
+                                         "variant": "tree_update_part (one CTA per subtree)" if os.environ.get("MB_UPDATE_LEGACY") != "1"
+                                         else "legacy single-CTA sorted walk"}
     tree.check()
 
     # ---- fused PER draw
@@ -186,7 +189,9 @@ def main():  # noqa: C901
         s = graphed([fn] * 8) if nb < 1e5 else timed(fn, reps=5)
         byt = (4 * A * N * 4 + N * 4 + 30) * nb
         R[f"td_rainbow_{nb}"] = {"us": s * 1e6, "alg_bytes": byt, "GBps": byt / s / 1e9, "frac": byt / s / 1e9 / PEAK}
-    out["env"] = {"force_generic": os.environ.get("MB_FORCE_GENERIC_UPDATE", "0"), "gpu": t.cuda.get_device_name(0)}
+    out["clocks"] = sampler.stop()
+    out["env"] = {"force_generic": os.environ.get("MB_FORCE_GENERIC_UPDATE", "0"), "gpu": t.cuda.get_device_name(0),
+                  "rows_legacy": os.environ.get("MB_ROWS_LEGACY", "0"), "update_legacy": os.environ.get("MB_UPDATE_LEGACY", "0")}
     print(json.dumps(out, indent=1))
 
 
