@@ -76,8 +76,14 @@ def parse():
     p.add_argument("--overlap-update", action="store_true",
                    help="N = 1, opt-in: priority write-back on a parallel graph branch beside backward + optimizer")
     p.add_argument("--adam", default="fused", choices=["fused", "torch"], help="FusedAdam (csrc/mlp.cu) or torch.optim.Adam(fused=True)")
+    p.add_argument("--serial", action="store_true",
+                   help="switch the three stream-level options off (round 1's launch order: one chain of kernels)")
     a = p.parse_args()
     a.static_exchange = not a.dynamic_exchange
+    if not a.serial and a.net == "torch":
+        # default since round 2 (measured at N = 1: 198 -> 138 us/update, profiles/r2_ab_variants.md): the two no-grad
+        # forwards and the priority write-back are parallel branches of the captured graph, Adam + soft update one launch
+        a.parallel_forwards = a.overlap_update = a.fuse_optimizer = True
     return a
 
 
@@ -226,6 +232,9 @@ def build_learner(a, device, seed, world=1):
                           discount=0.99, update_rate=0.005, replay_size=a.replay_rows, learner_group=group)
         buf = learner.replay_buffer
         learner.batched_draw = a.batched_draw
+        learner.parallel_forwards = a.parallel_forwards
+        learner.overlap_priority_update = a.overlap_update
+        learner.fuse_optimizer_and_target = a.fuse_optimizer and a.adam == "fused"
         learner.use_fused_program = a.net in ("fused-program", "fused-rows")     # honoured by the fixed-shape exchange
         learner.fused_kind = "rows" if a.net == "fused-rows" else "program"
     else:
@@ -262,7 +271,7 @@ KERNELS = {  # C entry point -> (label, algorithmic bytes per launch as f(batch,
     "mb_per_sample": ("per_sample (stratify + descent + IS weight)", lambda B, P, D: (8 * (D - 1) + 32) * B),
     "mb_rows_gather": ("rows_gather (batch assembly)", lambda B, P, D: 2 * ROW_BYTES * B),
     "mb_td_dqn": ("td_dqn (target + |delta| + loss + grad)", lambda B, P, D: (3 * N_ACTIONS * 4 + 8 + 4 + 1 + 8 + 12 + N_ACTIONS * 4) * B),
-    "mb_tree_update_priority": ("tree_update (normalise + level-synchronous recompute)", lambda B, P, D: (8 + 4 + 8 + 24 * (D - 1)) * B),
+    "mb_tree_update_priority": ("tree_update_part (normalise + one CTA per subtree, one launch)", lambda B, P, D: (8 + 4 + 8 + 24 * (D - 1)) * B),
     "mb_soft_update": ("soft_update", lambda B, P, D: 12 * P),
     # fused value math (--net fused-rows / fused-program): what must cross HBM at least once -- both input batches,
     # both nets' parameters, the saved activations and output gradients (written by part 0, read by part 1), the
@@ -539,10 +548,12 @@ def run_b200(a):
                    "parallelism": f"{world} learner(s), one replay shard each",
                    "launch": ("one CUDA graph per update" if (world == 1 or a.static_exchange) else
                               "two CUDA graphs per update around eager NCCL exchanges") if graph else "eager",
-                   "net": a.net, "adam": a.adam, "priority_update": "parallel graph branch" if (a.overlap_update and world == 1) else "in line",
-                   "online_forwards": "one pass over [s; s']" if a.fuse_forwards else ("split, no-grad ones on parallel branches" if (a.parallel_forwards and world == 1) else "split (as the reference)"),
+                   "net": a.net, "adam": a.adam,
+                   "optimizer_and_target": "one launch (FusedAdam step + soft update)" if (a.fuse_optimizer and a.adam == "fused") else "two launches", "priority_update": "parallel graph branch" if (a.overlap_update and (world == 1 or a.static_exchange)) else "in line",
+                   "online_forwards": "one pass over [s; s']" if a.fuse_forwards else ("split, no-grad ones on parallel branches" if (a.parallel_forwards and (world == 1 or a.static_exchange)) else "split (as the reference)"),
                    "exchange": None if world == 1 else "per update: all-gather of shard sums, all-to-all of sampled rows, "
-                               "all-to-all of priority write-backs, all-reduce of gradients, broadcast of weights (NCCL)",
+                               "all-to-all of priority write-backs, all-reduce of gradients (NCCL); no weight broadcast: every "
+                               "member learns and applies the same averaged gradients (actor-only members: --workload c5)",
                    "l2": "inputs larger than L2: 268 MB tree + 6.9 GB ring, randomly addressed every step"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": e2e_ms / K, "last_loss": last},

@@ -43,6 +43,24 @@ def _flat_grad_all_reduce(params, group, flat=None):
         o += g.numel()
 
 
+def _snapshot_optimizer(optim):
+    """Tensor state of an optimizer, cloned: what the warm-up updates of a graph capture will change."""
+    return {id(p): {k: (v.clone() if t.is_tensor(v) else v) for k, v in st.items()} for p, st in optim.state.items()}
+
+
+def _restore_optimizer(optim, saved, was_fresh):
+    """Undo the warm-up in place (the graph holds these addresses): a fresh optimizer goes back to zeros, a used one
+    to the snapshot -- enabling a graph must not change the trajectory."""
+    with t.no_grad():
+        for p, st in optim.state.items():
+            for k, v in st.items():
+                if t.is_tensor(v):
+                    if was_fresh:
+                        v.zero_()
+                    elif id(p) in saved and k in saved[id(p)]:
+                        v.copy_(saved[id(p)][k])
+
+
 class DQNApex(DQNPer):
     _config_frame, _config_kind = "DQNApex", "apex"
 
@@ -162,6 +180,7 @@ class DQNApex(DQNPer):
             raise RuntimeError("DQNApex.enable_cuda_graph needs an MSELoss criterion and soft target updates")
         saved = [[x.detach().clone() for x in list(m.parameters()) + list(m.buffers())] for m in (self.qnet, self.qnet_target)]
         fresh = len(self.qnet_optim.state) == 0
+        saved_optim = _snapshot_optimizer(self.qnet_optim)
         self.qnet.train()
         cur, side = t.cuda.current_stream(dev), t.cuda.Stream(device=dev)
         side.wait_stream(cur)
@@ -185,11 +204,7 @@ class DQNApex(DQNPer):
             for m, sv in zip((self.qnet, self.qnet_target), saved):
                 for x, v in zip(list(m.parameters()) + list(m.buffers()), sv):
                     x.copy_(v)
-            if fresh:
-                for pst in self.qnet_optim.state.values():
-                    for v in pst.values():
-                        if t.is_tensor(v):
-                            v.zero_()
+        _restore_optimizer(self.qnet_optim, saved_optim, fresh)
         st["g1"], st["g2"] = g1, g2
         self._apex_graph = st
         t.cuda.synchronize(dev)
@@ -274,35 +289,68 @@ class DQNApex(DQNPer):
             else:
                 fl = buf.storage.unpack(st["merged"])
                 state, action, next_state = grp_f(fl, "state"), grp_f(fl, "action"), grp_f(fl, "next_state")
-                with t.no_grad():
-                    nq = self._criticize(next_state)
-                    tq = self._criticize(next_state, True)
-                q = self._criticize(state)
+                if self.parallel_forwards:
+                    # the two no-grad forwards on side streams: parallel branches of the captured graph (as DQNPer does)
+                    if self._fwd_streams is None:
+                        self._fwd_streams = (t.cuda.Stream(device=dev), t.cuda.Stream(device=dev))
+                    cur = t.cuda.current_stream(dev)
+                    outs = []
+                    for side, use_target in zip(self._fwd_streams, (False, True)):
+                        side.wait_stream(cur)
+                        with t.cuda.stream(side), t.no_grad():
+                            outs.append(self._criticize(next_state, use_target))
+                    q = self._criticize(state)
+                    for side in self._fwd_streams:
+                        cur.wait_stream(side)
+                    nq, tq = outs
+                else:
+                    with t.no_grad():
+                        nq = self._criticize(next_state)
+                        tq = self._criticize(next_state, True)
+                    q = self._criticize(state)
                 td = ops.td_dqn(q.detach(), nq, tq, self.action_get_function(action), fl["reward"], fl["terminal"],
                                 self.discount, is_weight=st["isw"], mode=self.mode, want_grad=True)
+
+            def write_back():
+                check(lib.mb_wire_scatter_update(ptr(st["send2"]), P, cap, ptr(st["counts"]), ptr(st["idx"]), ptr(st["ver"]),
+                                                 ptr(td["abs_error"]), capB, stream_ptr()))
+                if P > 1:
+                    dist.all_to_all_single(st["recv2"], st["send2"], group=grp.pg)
+                else:
+                    st["recv2"].copy_(st["send2"])
+                check(lib.mb_wire_update_mask(ptr(st["recv2"]), P, cap, ptr(st["counts"]), me, ptr(table), table.numel(),
+                                              ptr(st["u_idx"]), ptr(st["u_pri"]), ptr(st["u_valid"]), stream_ptr()))
+                PrioritizedBuffer.update_priority(buf, st["u_pri"], st["u_idx"], valid=st["u_valid"])
+
+            forked = None
+            if self.overlap_priority_update:
+                # |delta| is ready: its exchange and the masked tree update only feed the NEXT draw, so they run on a side
+                # stream beside backward, the gradient all-reduce and the optimizer.  Every rank issues its collectives in
+                # the same program order (rows, priorities, gradients), which is the order they take on NCCL's stream.
+                if self._side_stream is None:
+                    self._side_stream = t.cuda.Stream(device=dev)
+                forked = (t.cuda.current_stream(dev), self._side_stream)
+                forked[1].wait_stream(forked[0])
+                with t.cuda.stream(forked[1]):
+                    write_back()
+            if prog is None:
                 self._flat_grad.zero_()
                 q.backward(td["grad_q"])
             if P > 1:
-                dist.all_reduce(self._flat_grad, group=self.learner_group.pg if self.learner_group is not None else grp.pg)
-                self._flat_grad.div_(P)
-            if np.isfinite(self.grad_max):
-                nn.utils.clip_grad_norm_(self.qnet.parameters(), self.grad_max)
-            self.qnet_optim.step()
-            soft_update(self.qnet_target, self.qnet, self.update_rate)
-            check(lib.mb_wire_scatter_update(ptr(st["send2"]), P, cap, ptr(st["counts"]), ptr(st["idx"]), ptr(st["ver"]),
-                                             ptr(td["abs_error"]), capB, stream_ptr()))
-            if P > 1:
-                dist.all_to_all_single(st["recv2"], st["send2"], group=grp.pg)
+                red = self.learner_group if self.learner_group is not None else grp
+                dist.all_reduce(self._flat_grad, group=red.pg)
+                self._flat_grad.div_(red.size())
+            self._optimizer_and_target(True, True)        # clip (if finite), optimizer step, soft target update
+            if forked is None:
+                write_back()
             else:
-                st["recv2"].copy_(st["send2"])
-            check(lib.mb_wire_update_mask(ptr(st["recv2"]), P, cap, ptr(st["counts"]), me, ptr(table), table.numel(),
-                                          ptr(st["u_idx"]), ptr(st["u_pri"]), ptr(st["u_valid"]), stream_ptr()))
-            PrioritizedBuffer.update_priority(buf, st["u_pri"], st["u_idx"], valid=st["u_valid"])
+                forked[0].wait_stream(forked[1])            # join before the next draw reads the tree
             return td["loss_elem"].mean()
 
         # snapshot everything the warm-up replays will touch
         saved = [[x.detach().clone() for x in list(m.parameters()) + list(m.buffers())] for m in (self.qnet, self.qnet_target)]
         fresh = len(self.qnet_optim.state) == 0
+        saved_optim = _snapshot_optimizer(self.qnet_optim)
         tree_snap, beta0 = buf.wt_tree.snapshot(), buf.curr_beta
         np_state = np.random.get_state()
         self.qnet.train()
@@ -326,11 +374,7 @@ class DQNApex(DQNPer):
             for m, sv in zip((self.qnet, self.qnet_target), saved):
                 for x, v in zip(list(m.parameters()) + list(m.buffers()), sv):
                     x.copy_(v)
-            if fresh:
-                for pst in self.qnet_optim.state.values():
-                    for v in pst.values():
-                        if t.is_tensor(v):
-                            v.zero_()
+        _restore_optimizer(self.qnet_optim, saved_optim, fresh)
         buf.wt_tree.restore(tree_snap)
         buf.curr_beta = beta0
         st["beta"].fill_(float(beta0))

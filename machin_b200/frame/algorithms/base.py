@@ -80,17 +80,24 @@ class TorchFramework:
             t.save(getattr(self, attr), os.path.join(model_dir, self._file_name(name, version)))
 
     def load(self, model_dir: str, network_map: Dict[str, str] = None, version: int = -1):
-        """``version`` < 0: the newest checkpoint of every model found in ``model_dir``."""
-        for attr in self._is_restorable:
-            name = (network_map or {}).get(attr, attr)
-            chosen = version
-            if chosen < 0:
-                pattern = re.compile(re.escape(name) + r"_(\d+)\.pt$")
-                versions = [int(m.group(1)) for m in map(pattern.match, os.listdir(model_dir)) if m]
-                if not versions:
-                    raise RuntimeError(f"no checkpoint for {name} in {model_dir}")
-                chosen = max(versions)
-            loaded = t.load(os.path.join(model_dir, self._file_name(name, chosen)), map_location="cpu", weights_only=False)
+        """base.py:94-129 over utils/prepare.py:52-117 (prep_load_model): the requested ``version`` if EVERY restorable
+        model has it, otherwise (and for ``version`` < 0) the newest version that all of them share -- never a mixed
+        set of checkpoints.  ``RuntimeError`` if the directory is missing or no common version exists."""
+        if not os.path.isdir(model_dir):
+            raise RuntimeError("Model directory doesn't exist!")
+        names = {attr: (network_map or {}).get(attr, attr) for attr in self._is_restorable}
+        have = {name: set() for name in names.values()}
+        for entry in os.listdir(model_dir):
+            m = re.fullmatch(r"([a-zA-Z0-9_-]+)_([0-9]+)\.pt", entry)
+            if m is not None and m.group(1) in have:
+                have[m.group(1)].add(int(m.group(2)))
+        if version is None or version < 0 or not all(version in v for v in have.values()):
+            common = set.intersection(*have.values()) if have else set()
+            if not common:
+                raise RuntimeError("Cannot find a valid version for all models!")
+            version = max(common)
+        for attr, name in names.items():
+            loaded = t.load(os.path.join(model_dir, self._file_name(name, version)), map_location="cpu", weights_only=False)
             getattr(self, attr).load_state_dict(loaded.state_dict() if hasattr(loaded, "state_dict") else loaded)
 
     def visualize_model(self, *_, **__):

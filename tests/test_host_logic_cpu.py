@@ -134,5 +134,43 @@ def test_framework_base_registry_save_and_load(tmp_path):
     assert t.equal(b.net_target.weight, first)
     b.load(str(tmp_path))                                        # newest: 10, not the lexicographically larger "2"
     assert t.equal(b.net_target.weight, first + 1.0)
-    with pytest.raises(RuntimeError, match="no checkpoint"):
+    with pytest.raises(RuntimeError, match="Cannot find a valid version"):   # the reference's message (utils/prepare.py:109)
         b.load(str(tmp_path), network_map={"net_target": "missing"})
+
+
+def test_load_picks_newest_version_common_to_all_models(tmp_path):
+    """utils/prepare.py:52-117: after a partial save (actor_5 present, critic_5 missing) the newest COMMON version is
+    loaded -- never a mixed pair -- and a missing directory / no common version raise RuntimeError."""
+    import torch as t
+    from machin_b200.frame.algorithms.base import TorchFramework
+
+    class Two(TorchFramework):
+        _is_top = ["actor", "critic"]
+        _is_restorable = ["actor", "critic"]
+
+        def __init__(self):
+            self.actor, self.critic = t.nn.Linear(1, 1, bias=False), t.nn.Linear(1, 1, bias=False)
+            super().__init__()
+
+    def fill(algo, a, c):
+        with t.no_grad():
+            algo.actor.weight.fill_(a)
+            algo.critic.weight.fill_(c)
+
+    algo = Two()
+    fill(algo, 3.0, 30.0)
+    algo.save(str(tmp_path), version=3)
+    fill(algo, 5.0, 50.0)
+    algo.save(str(tmp_path), version=5)
+    (tmp_path / "critic_5.pt").unlink()                      # partial save
+    fill(algo, 0.0, 0.0)
+    algo.load(str(tmp_path))                                 # newest common = 3
+    assert algo.actor.weight.item() == 3.0 and algo.critic.weight.item() == 30.0
+    fill(algo, 0.0, 0.0)
+    algo.load(str(tmp_path), version=5)                      # not available for every model: falls back to the common one
+    assert algo.actor.weight.item() == 3.0 and algo.critic.weight.item() == 30.0
+    (tmp_path / "critic_3.pt").unlink()
+    with pytest.raises(RuntimeError, match="valid version"):
+        algo.load(str(tmp_path))
+    with pytest.raises(RuntimeError, match="doesn't exist"):
+        algo.load(str(tmp_path / "nope"))
