@@ -80,7 +80,7 @@ def parse():
                    help="switch the three stream-level options off (round 1's launch order: one chain of kernels)")
     a = p.parse_args()
     a.static_exchange = not a.dynamic_exchange
-    if not a.serial and a.net == "torch":
+    if not a.serial and a.net in ("torch", "fused"):
         # default since round 2 (measured at N = 1: 198 -> 138 us/update, profiles/r2_ab_variants.md): the two no-grad
         # forwards and the priority write-back are parallel branches of the captured graph, Adam + soft update one launch
         a.parallel_forwards = a.overlap_update = a.fuse_optimizer = True

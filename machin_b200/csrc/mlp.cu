@@ -200,6 +200,149 @@ __global__ void __launch_bounds__(NT) gemm_kernel(GemmArgs g) {
     gemm_item<kAKfast, kBKfast>(g, sm, blockIdx.x, blockIdx.y, gridDim.x, blockIdx.z, gridDim.z);
 }
 
+// ---- small-problem GEMM: the learner's layers are 512 x 256 x 256 and smaller -----------------------------------
+// With 64 x 64 tiles such a layer is 32 tiles (64 with a grid-level K-split and its reduction pass): most of the 148
+// SMs idle and each CTA walks the whole K serially -- measured 11 us per layer.  Here the tile is 32 x 32 (128 CTAs for
+// 512 x 256), and the K range of a tile is cut over KG groups of 64 threads INSIDE the CTA: each group multiplies its
+// K-slice out of its own shared-memory stage (same register-staged software pipeline as above, 4 x 4 outputs per
+// thread), the groups' partial tiles are added in group order through shared memory (a fixed summation order: the
+// result does not depend on scheduling), and group 0 runs the fused epilogue.  No workspace, no second pass.
+constexpr int ST = 32, SG = 64, STK = 32;     // tile edge, threads per K-group, K-step
+
+template <int KG>
+struct SmallSmem {
+    float As[KG][STK][ST + 4];
+    float Bs[KG][STK][ST + 4];
+};
+
+template <int KG, bool kAKfast, bool kBKfast>
+__global__ void __launch_bounds__(SG * KG) gemm_small_kernel(GemmArgs g) {
+    __shared__ SmallSmem<KG> sm;
+    const int tid = threadIdx.x, grp = tid / SG, lt = tid % SG;
+    const int i0 = blockIdx.y * ST, j0 = blockIdx.x * ST;
+    const int k_begin = grp * g.k_per_split;
+    const int k_end = min(g.K, k_begin + g.k_per_split);
+    const int ty = lt >> 3, tx = lt & 7;      // 8 x 8 threads, 4 x 4 outputs each
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+    constexpr int U = ST * STK / SG;          // 16 elements of A and of B per thread and K-step
+    float ra[U], rb[U];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = lt + u * SG;
+            int i, k;
+            if (kAKfast) { i = e / STK; k = e % STK; } else { k = e / ST; i = e % ST; }
+            const int gi = i0 + i, gk = k0 + k;
+            ra[u] = (gi < g.M && gk < k_end) ? __ldcg(g.A + (int64_t)gi * g.a_i + (int64_t)gk * g.a_k) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = lt + u * SG;
+            int j, k;
+            if (kBKfast) { j = e / STK; k = e % STK; } else { k = e / ST; j = e % ST; }
+            const int gj = j0 + j, gk = k0 + k;
+            float v = 0.0f;
+            if (gj < g.N && gk < k_end)
+                v = (gj == g.ones_col) ? 1.0f : __ldcg(g.B + (int64_t)gj * g.b_j + (int64_t)gk * g.b_k);
+            rb[u] = v;
+        }
+    };
+    auto park = [&]() {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = lt + u * SG;
+            if (kAKfast) sm.As[grp][e % STK][e / STK] = ra[u]; else sm.As[grp][e / ST][e % ST] = ra[u];
+            if (kBKfast) sm.Bs[grp][e % STK][e / STK] = rb[u]; else sm.Bs[grp][e / ST][e % ST] = rb[u];
+        }
+    };
+    // every group runs the same number of steps (g.k_per_split is a multiple of STK; an empty slice multiplies zeros),
+    // so the CTA-wide barriers line up
+    const int steps = g.k_per_split / STK;
+    if (k_begin < k_end) fetch(k_begin);
+    else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) ra[u] = rb[u] = 0.0f;
+    }
+    for (int s = 0; s < steps; ++s) {
+        const int k0 = k_begin + s * STK;
+        park();
+        __syncthreads();
+        if (s + 1 < steps) {
+            if (k0 + STK < k_end) fetch(k0 + STK);
+            else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) ra[u] = rb[u] = 0.0f;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < STK; ++k) {
+            const float4 a = *reinterpret_cast<const float4 *>(&sm.As[grp][k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&sm.Bs[grp][k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(av[x], bv[y], acc[x][y]);
+        }
+        __syncthreads();
+    }
+    // partial tiles of groups 1.. -> their own (now idle) A stage, as [32][32+4]; group 0 adds them in group order
+    if (KG > 1) {
+        if (grp > 0) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+                *reinterpret_cast<float4 *>(&sm.As[grp][ty * 4 + x][tx * 4]) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+        }
+        __syncthreads();
+        if (grp == 0) {
+#pragma unroll
+            for (int q = 1; q < KG; ++q)
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const float4 p = *reinterpret_cast<const float4 *>(&sm.As[q][ty * 4 + x][tx * 4]);
+                    acc[x][0] = __fadd_rn(acc[x][0], p.x);
+                    acc[x][1] = __fadd_rn(acc[x][1], p.y);
+                    acc[x][2] = __fadd_rn(acc[x][2], p.z);
+                    acc[x][3] = __fadd_rn(acc[x][3], p.w);
+                }
+        }
+    }
+    if (grp == 0) {
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) epilogue_store(g, i0 + ty * 4 + x, j0 + tx * 4 + y, acc[x][y]);
+    }
+}
+
+bool small_gemm_enabled() {          // MB_GEMM_LEGACY=1: the 64 x 64 kernel everywhere (A/B timing)
+    const char *e = getenv("MB_GEMM_LEGACY");
+    return !(e && e[0] == '1');
+}
+
+template <bool kA, bool kB>
+bool launch_small(GemmArgs g, cudaStream_t s) {
+    const int tiles64 = ((g.N + TN - 1) / TN) * ((g.M + TM - 1) / TM);
+    if (!small_gemm_enabled() || tiles64 >= 2 * mb::kNumSMs) return false;
+    const dim3 grid((g.N + ST - 1) / ST, (g.M + ST - 1) / ST, 1);
+    const int ksteps = (g.K + STK - 1) / STK;
+    if (ksteps >= 4) {
+        g.k_per_split = (ksteps + 3) / 4 * STK;
+        gemm_small_kernel<4, kA, kB><<<grid, SG * 4, 0, s>>>(g);
+    } else if (ksteps >= 2) {
+        g.k_per_split = (ksteps + 1) / 2 * STK;
+        gemm_small_kernel<2, kA, kB><<<grid, SG * 2, 0, s>>>(g);
+    } else {
+        g.k_per_split = STK;
+        gemm_small_kernel<1, kA, kB><<<grid, SG, 0, s>>>(g);
+    }
+    return true;
+}
+
 int pick_splits(int tiles, int K) {
     int s = 1;
     while (tiles * s * 2 <= mb::kNumSMs + mb::kNumSMs / 4 && (K / (s * 2)) >= 2 * TK && s < 32) s *= 2;
@@ -208,6 +351,10 @@ int pick_splits(int tiles, int K) {
 
 template <bool kA, bool kB>
 int launch(GemmArgs g, float *workspace, int64_t workspace_floats, int *counters, int n_counters, cudaStream_t s) {
+    if (launch_small<kA, kB>(g, s)) {
+        MB_LAUNCHED(1);
+        return MB_OK;
+    }
     const int tx = (g.N + TN - 1) / TN, ty = (g.M + TM - 1) / TM;
     int splits = pick_splits(tx * ty, g.K);
     if (splits > 1 && (!workspace || !counters || (int64_t)splits * g.M * g.N > workspace_floats || tx * ty > n_counters))

@@ -86,9 +86,15 @@ class FusedMLP(nn.Module):
         self._ws = None
 
     def _workspace(self, device):
-        if self._ws is None or self._ws.buf.device != device:
-            self._ws = _Workspace(device)
-        return self._ws
+        """One split-K scratch per (device, stream): two forwards of the same network may run on different streams at
+        the same time (DQNPer.parallel_forwards), and launches are only ordered within a stream."""
+        key = (device, getattr(t.cuda.current_stream(device), "cuda_stream", 0))
+        if self._ws is None:
+            self._ws = {}
+        ws = self._ws.get(key)
+        if ws is None:
+            ws = self._ws[key] = _Workspace(device)
+        return ws
 
     def forward(self, state, action=None):
         x = state if action is None else t.cat([state, action.to(state.dtype)], dim=1)
