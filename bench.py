@@ -59,11 +59,9 @@ def parse():
     p.add_argument("--dynamic-exchange", action="store_true",
                    help="N > 1: exactly-sized eager NCCL exchanges between two CUDA graphs instead of the default "
                         "fixed-shape exchange captured with the rest of the update in ONE graph")
-    p.add_argument("--batched-draw", action="store_true",
-                   help="N > 1, fixed-shape exchange, opt-in: the draws for all requesters in one launch")
-    p.add_argument("--device-apportion", action="store_true",
-                   help="N > 1, fixed-shape exchange, opt-in: shard sums all-gathered and apportioned inside the graph "
-                        "(no host read per update)")
+    p.add_argument("--host-apportion", action="store_true",
+                   help="N > 1, fixed-shape exchange: round 1's variant -- the host reads the all-gathered shard sums every "
+                        "update and apportions; one draw launch per requester (measured at N = 2: 278 vs 220 us/update)")
     p.add_argument("--watchdog-s", type=float, default=420.0,
                    help="N > 1: leave with exit code 5 if the run has not finished after this many seconds "
                         "(a stuck collective must not hold the box)")
@@ -80,6 +78,9 @@ def parse():
                    help="switch the three stream-level options off (round 1's launch order: one chain of kernels)")
     a = p.parse_args()
     a.static_exchange = not a.dynamic_exchange
+    # default since round 2 (profiles/r2_n2_variants.md): shard sums all-gathered and apportioned inside the graph (no host
+    # read per update), the draws for all requesters in one launch
+    a.device_apportion = a.batched_draw = not a.host_apportion
     if not a.serial and a.net in ("torch", "fused"):
         # default since round 2 (measured at N = 1: 198 -> 138 us/update, profiles/r2_ab_variants.md): the two no-grad
         # forwards and the priority write-back are parallel branches of the captured graph, Adam + soft update one launch
@@ -487,9 +488,14 @@ def run_b200(a):
     ms_total, e2e_ms = float(tt[0]), float(tt[1])
     def leave():
         if world > 1:
-            if graph and (a.static_exchange or getattr(a, "skip_teardown", False)):
-                # NCCL collectives captured in a CUDA graph: destroy_process_group() hangs while the graph is
-                # alive (tools/nccl_graph_repro.py) -- flush and leave without the teardown
+            # NCCL collectives captured in a CUDA graph: destroy_process_group() blocks while such a graph is alive, and
+            # returns once it has been released (tools/nccl_graph_repro.py ... release; profiles/r2_nccl_graph_release.log)
+            t.cuda.synchronize(device)
+            dist.barrier()
+            if hasattr(learner, "release_graphs"):
+                learner.release_graphs()
+            t.cuda.synchronize(device)
+            if getattr(a, "skip_teardown", False):      # a capture that failed half-way may still hold NCCL work
                 sys.stdout.flush()
                 sys.stderr.flush()
                 dist.barrier()

@@ -189,10 +189,11 @@ def test_b200_arm_dry_run_two_ranks(case, monkeypatch):
     real_timer = threading.Timer
     monkeypatch.setattr(threading, "Timer", lambda *a, **k: timers.append(real_timer(*a, **k)) or timers[-1])
     try:
-        if case == "dynamic":
-            bench.run_b200(bench.parse())                       # leaves through destroy_process_group (a no-op here)
+        if case != "static_capture_fails":
+            bench.run_b200(bench.parse())                       # releases its graphs, then destroy_process_group (a no-op here)
+            assert left == []
         else:
-            with pytest.raises(_Left):
+            with pytest.raises(_Left):                          # a half-captured NCCL graph may linger: no teardown
                 bench.run_b200(bench.parse())
             assert left == [0]
     finally:
@@ -202,7 +203,9 @@ def test_b200_arm_dry_run_two_ranks(case, monkeypatch):
     line = json.loads(written[0].decode())
     assert line["n_gpus"] == 2 and line["cpu_baseline"] is None
     assert line["roofline"] is not None and line["kernels"]          # rank 0 times its shard's kernels at N > 1 too
-    assert line["e2e"]["d2h_bytes_per_step"] == 8 + 8 * 2
+    # the default fixed-shape update apportions on the device: only the loss comes back; the dynamic exchange (and the
+    # fall-back to it) reads the P shard sums on the host
+    assert line["e2e"]["d2h_bytes_per_step"] == (8 if case == "static" else 8 + 8 * 2)
     launch = line["config"]["launch"]
     if case == "static":
         assert launch == "one CUDA graph per update"
