@@ -59,6 +59,10 @@ def parse():
     p.add_argument("--dynamic-exchange", action="store_true",
                    help="N > 1: exactly-sized eager NCCL exchanges between two CUDA graphs instead of the default "
                         "fixed-shape exchange captured with the rest of the update in ONE graph")
+    p.add_argument("--peer-exchange", action="store_true",
+                   help="N > 1, fixed-shape exchange: no NCCL inside the update -- rows, priorities, shard sums and gradients "
+                        "are stored into the other GPUs' buffers over NVLink by csrc/peer.cu (falls back to NCCL if the buffers "
+                        "cannot be peer-mapped)")
     p.add_argument("--host-apportion", action="store_true",
                    help="N > 1, fixed-shape exchange: round 1's variant -- the host reads the all-gathered shard sums every "
                         "update and apportions; one draw launch per requester (measured at N = 2: 278 vs 220 us/update)")
@@ -406,7 +410,8 @@ def run_b200(a):
         # sized NCCL exchanges (measured at N = 2, 4).
         try:
             learner.enable_cuda_graph(static_exchange=a.static_exchange,
-                                      device_apportion=a.device_apportion and a.static_exchange)
+                                      device_apportion=a.device_apportion and a.static_exchange,
+                                      peer_exchange=a.peer_exchange and a.static_exchange)
         except Exception as exc:   # noqa: BLE001 -- a capture problem is deterministic: every rank lands here together
             if not a.static_exchange:
                 raise
@@ -557,6 +562,11 @@ def run_b200(a):
                    "net": a.net, "adam": a.adam,
                    "optimizer_and_target": "one launch (FusedAdam step + soft update)" if (a.fuse_optimizer and a.adam == "fused") else "two launches", "priority_update": "parallel graph branch" if (a.overlap_update and (world == 1 or a.static_exchange)) else "in line",
                    "online_forwards": "one pass over [s; s']" if a.fuse_forwards else ("split, no-grad ones on parallel branches" if (a.parallel_forwards and (world == 1 or a.static_exchange)) else "split (as the reference)"),
+                   "transport": None if world == 1 else (
+                       "peer memory over NVLink: this library's kernels store into the other GPUs' buffers, one barrier kernel "
+                       "per exchange (csrc/peer.cu)" if (getattr(learner, "_static", None) or {}).get("peer") is not None
+                       else "NCCL (torch.distributed), collectives captured in the update's CUDA graph" if a.static_exchange
+                       else "NCCL (torch.distributed), eager"),
                    "exchange": None if world == 1 else "per update: all-gather of shard sums, all-to-all of sampled rows, "
                                "all-to-all of priority write-backs, all-reduce of gradients (NCCL); no weight broadcast: every "
                                "member learns and applies the same averaged gradients (actor-only members: --workload c5)",

@@ -206,6 +206,40 @@ int mb_wire_update_mask(const void *d_recv, int n_blocks, int64_t cap, const int
                         uint8_t *d_valid, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Shard exchange over peer memory (NVLink / NVSwitch): the collectives of the fixed-shape update as direct
+ * stores from this library's kernels into the other GPUs' buffers, instead of NCCL calls.
+ * Replaces, on the data path, the per-member RPCs of prioritized_buffer_d.py:221-245 (sample), :184-202 (priority
+ * write-back) and the gradient / weight movement of apex.py:141-150.  The buffers are symmetric allocations (same
+ * size on every member, peer-mapped once by the host side -- torch.distributed._symmetric_memory in
+ * machin_b200/parallel/peer.py); `peers[m]` is member m's buffer as mapped into THIS process (peers[self] = the
+ * local one).  Every call takes host arrays of n_blocks device pointers (baked into the launch: capturable).
+ *  push_rows:    the cap rows drawn for requester r (block r of d_index / d_is_weight) -> peers[r], block `self`:
+ *                [packed row | index | version_table[index] | is_weight] at `width` bytes per row (gather + metadata
+ *                + all-to-all in one kernel: the row never exists in a local send buffer)
+ *  push_update:  write-back of merged row j (served by shard m at position i) -> peers[m], block `self`, as
+ *                (index, version, priority) -- the scatter + all-to-all of the NCCL path
+ *  push:         nbytes of d_src -> peers[r] + self * slot_stride for every r (all-gather of shard sums: 8 bytes;
+ *                gradient all-reduce, first half: the flat gradient buffer into slot `self` of every member)
+ *  sum:          d_out[i] = (slots[0][i] + slots[1][i] + ...) / divisor, member order -- every member adds the
+ *                same numbers in the same order, so all members hold bit-identical averaged gradients
+ *  barrier:      every member stores epoch+1 into flag `self` of every member (release, system scope) and waits
+ *                until its own n_blocks flags reached it (acquire): what was pushed before the barrier by any
+ *                member is visible after it.  d_state[0] = epoch (kept on the device: graph replays advance it),
+ *                d_state[1] != 0 after a wait longer than timeout_ns (a member died): checked by the host side. */
+#define MB_MAX_PEERS 16
+int mb_wire_push_rows(const void *d_ring, int64_t pitch, int64_t capacity, const int64_t *d_index,
+                      const double *d_is_weight, const int64_t *d_version_table, int n_blocks, int64_t cap,
+                      int self_block, int64_t width, void *const *peers, void *stream);
+int mb_wire_push_update(int n_blocks, int64_t cap, int self_block, const int64_t *d_counts, const int64_t *d_index,
+                        const int64_t *d_version, const float *d_priority, int64_t merged_rows, void *const *peers,
+                        void *stream);
+int mb_peer_push(const void *d_src, int64_t nbytes, int n_blocks, int self_block, int64_t slot_stride,
+                 void *const *peers, void *stream);
+int mb_peer_sum(const float *d_slots, int n_blocks, int64_t n, float divisor, float *d_out, void *stream);
+int mb_peer_barrier(void *const *peer_flags, int n_blocks, int self_block, uint64_t *d_state,
+                    int64_t timeout_ns, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * TD target / priority math
  * ------------------------------------------------------------------------------------------ */
 /* DQNPer.update value block (dqn_per.py:105-139, dqn.py:497-501), float32:

@@ -29,6 +29,7 @@ MB_ERR_NO_DEVICE = -7
 MB_F32, MB_F64 = 0, 1
 MB_MAX_FIELDS = 16
 MB_MAX_SOFT_TENSORS = 24          # include/machin_b200.h
+MB_MAX_PEERS = 16
 
 i64, i32, f64, f32, vp = C.c_int64, C.c_int, C.c_double, C.c_float, C.c_void_p
 
@@ -84,6 +85,11 @@ SIGNATURES = {
     "mb_wire_scatter_update": (i32, [vp, i32, i64, vp, vp, vp, vp, i64, vp]),
     "mb_wire_apportion": (i32, [vp, i32, i64, i32, i64, vp, vp, f64, vp, vp, vp, vp]),
     "mb_wire_update_mask": (i32, [vp, i32, i64, vp, i32, vp, i64, vp, vp, vp, vp]),
+    "mb_wire_push_rows": (i32, [vp, i64, i64, vp, vp, vp, i32, i64, i32, i64, C.POINTER(vp), vp]),
+    "mb_wire_push_update": (i32, [i32, i64, i32, vp, vp, vp, vp, i64, C.POINTER(vp), vp]),
+    "mb_peer_push": (i32, [vp, i64, i32, i32, i64, C.POINTER(vp), vp]),
+    "mb_peer_sum": (i32, [vp, i32, i64, f32, vp, vp]),
+    "mb_peer_barrier": (i32, [C.POINTER(vp), i32, i32, vp, i64, vp]),
     "mb_td_dqn": (i32, [vp, vp, vp, i64, i32, vp, vp, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]),
     "mb_td_target": (i32, [vp, vp, vp, i64, f32, vp, vp, vp, vp]),
     "mb_td_rainbow": (i32, [vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, f64, f64, f64, vp, vp, vp, vp, vp, vp]),

@@ -187,3 +187,79 @@ __global__ void wire_apportion_kernel(const double *__restrict__ sums, int P, in
     }
     *beta = b;
 }
+
+
+// ---- shard exchange over peer memory (NVLink): the same data movement as gather + pack_meta + all-to-all, and as
+// scatter_update + all-to-all, with the destination in ANOTHER GPU's buffer (peer-mapped pointers).  Plain stores:
+// the ordering against the consumer is the peer barrier that follows (csrc/peer.cu).
+struct PeerPtrs {
+    char *p[MB_MAX_PEERS];
+};
+
+__global__ void __launch_bounds__(256) wire_push_rows_kernel(const char *__restrict__ ring, int64_t pitch,
+                                                             int64_t capacity, const int64_t *__restrict__ index,
+                                                             const double *__restrict__ isw,
+                                                             const int64_t *__restrict__ version_table, int P,
+                                                             int64_t cap, int self_block, int64_t width, PeerPtrs recv) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t j = warp; j < (int64_t)P * cap; j += n_warps) {
+        const int r = (int)(j / cap);                      // requester this row was drawn for
+        const int64_t i = j - (int64_t)r * cap;
+        int64_t slot = index[j];
+        slot = slot < 0 ? 0 : (slot >= capacity ? capacity - 1 : slot);
+        char *dst = recv.p[r] + ((int64_t)self_block * cap + i) * width;
+        warp_copy(dst, ring + slot * pitch, pitch, lane);
+        if (lane == 0) {
+            char *m = dst + pitch;
+            reinterpret_cast<int64_t *>(m)[0] = index[j];
+            reinterpret_cast<int64_t *>(m)[1] = version_table[slot];
+            reinterpret_cast<double *>(m)[2] = isw[j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) wire_push_update_kernel(int P, int64_t cap, int self_block,
+                                                               const int64_t *__restrict__ counts,
+                                                               const int64_t *__restrict__ index,
+                                                               const int64_t *__restrict__ version,
+                                                               const float *__restrict__ priority, int64_t merged_rows,
+                                                               PeerPtrs recv) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= merged_rows) return;
+    int64_t base = 0;
+    int m = 0;
+    while (m < P && j >= base + counts[m]) base += counts[m++];
+    if (m == P) return;                                    // padding row of the merged batch
+    char *dst = recv.p[m] + ((int64_t)self_block * cap + (j - base)) * 24;
+    reinterpret_cast<int64_t *>(dst)[0] = index[j];
+    reinterpret_cast<int64_t *>(dst)[1] = version[j];
+    reinterpret_cast<double *>(dst)[2] = (double)priority[j];
+}
+
+// nbytes of src -> slot `self_block` of every member (blockIdx.y = destination member)
+__global__ void __launch_bounds__(256) peer_push_kernel(const char *__restrict__ src, int64_t nbytes, int self_block,
+                                                        int64_t slot_stride, PeerPtrs dst) {
+    char *out = dst.p[blockIdx.y] + (int64_t)self_block * slot_stride;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    if ((((uintptr_t)src | (uintptr_t)out | (uintptr_t)nbytes) & 15) == 0) {
+        for (int64_t k = tid; k < (nbytes >> 4); k += stride)
+            reinterpret_cast<uint4 *>(out)[k] = reinterpret_cast<const uint4 *>(src)[k];
+    } else if ((((uintptr_t)src | (uintptr_t)out | (uintptr_t)nbytes) & 7) == 0) {
+        for (int64_t k = tid; k < (nbytes >> 3); k += stride)
+            reinterpret_cast<uint2 *>(out)[k] = reinterpret_cast<const uint2 *>(src)[k];
+    } else {
+        for (int64_t k = tid; k < nbytes; k += stride) out[k] = src[k];
+    }
+}
+
+// out[i] = (slots[0][i] + slots[1][i] + ... + slots[P-1][i]) / divisor, member order (separately rounded adds)
+__global__ void __launch_bounds__(256) peer_sum_kernel(const float *__restrict__ slots, int P, int64_t n, float divisor,
+                                                       float *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float acc = slots[i];
+        for (int m = 1; m < P; ++m) acc = __fadd_rn(acc, slots[(int64_t)m * n + i]);
+        out[i] = __fdiv_rn(acc, divisor);
+    }
+}

@@ -126,7 +126,8 @@ class DQNApex(DQNPer):
     # are captured; the row exchange, the gradient all-reduce, the priority write-back and the weight
     # broadcast stay eager NCCL calls between the replays.  The merged batch has a data-dependent size
     # n in [B, B + P - 1] (ceil apportioning), so the graphs run on B + P padded rows whose IS weight is 0.
-    def enable_cuda_graph(self, warmup: int = 3, static_exchange: bool = False, device_apportion: bool = False):
+    def enable_cuda_graph(self, warmup: int = 3, static_exchange: bool = False, device_apportion: bool = False,
+                          peer_exchange: bool = False):
         """``static_exchange``: fixed-shape variant -- every (shard, requester) pair always moves ``batch_size``
         wire rows and the kernels read the apportioned counts from device memory, so draw, both all-to-alls,
         compute, the gradient all-reduce, the optimizer and the tree write-back are ONE graph replay per
@@ -135,9 +136,13 @@ class DQNApex(DQNPer):
         ``device_apportion`` (with ``static_exchange``): the all-gather of the shard sums is captured too and the
         apportioning (counts, per-draw beta) runs in a one-thread kernel, so the host never waits for the device: per
         update it draws ``members x batch_size`` uniforms and replays.  Throughput mode: np.random is consumed in
-        fixed-size blocks instead of the reference's apportioned sizes (identical on a group of one)."""
+        fixed-size blocks instead of the reference's apportioned sizes (identical on a group of one).
+        ``peer_exchange`` (with ``static_exchange``): no NCCL inside the update -- sampled rows, priority write-backs,
+        shard sums and gradients are stored straight into the other GPUs' buffers over NVLink by this library's
+        kernels (csrc/peer.cu), ordered by one small barrier kernel per exchange; falls back to NCCL (with a warning)
+        if the buffers cannot be peer-mapped."""
         if static_exchange:
-            return self._enable_static_graph(warmup, device_apportion)
+            return self._enable_static_graph(warmup, device_apportion, peer_exchange)
         buf = self.replay_buffer
         dev = buf.buffer_device
         buf._exchange()                                   # collective: agree on the row layout
@@ -210,7 +215,7 @@ class DQNApex(DQNPer):
         t.cuda.synchronize(dev)
 
     # ------------------------------------------------------------------ fixed-shape, single-graph update
-    def _enable_static_graph(self, warmup: int = 3, device_apportion: bool = False):
+    def _enable_static_graph(self, warmup: int = 3, device_apportion: bool = False, peer_exchange: bool = False):
         import torch.distributed as dist
         from ..._lib import lib, ptr, check, stream_ptr
         from ..buffers import PrioritizedBuffer
@@ -219,7 +224,17 @@ class DQNApex(DQNPer):
         if not self._fused_mse or self.update_rate is None or B > 1024 or list(buf._exchange().requesters) != list(range(P)):
             raise RuntimeError("static exchange needs MSELoss, soft target updates, batch <= 1024 and every member learning")
         pitch = buf.storage.pitch
-        W, cap, capB = pitch + 24, B, B + P
+        peer = None
+        if peer_exchange and P > 1:
+            try:
+                from ...parallel.peer import PeerMemory
+                peer = PeerMemory.create(grp)
+            except Exception as exc:      # noqa: BLE001 -- every member fails alike (same torch, same topology)
+                import warnings
+                warnings.warn(f"peer exchange unavailable ({exc!r}); the fixed-shape update keeps its NCCL collectives")
+                peer = None
+        # wire row = packed row + (index, version, is_weight); padded to 16 bytes for the peer stores
+        W, cap, capB = pitch + (32 if peer is not None else 24), B, B + P
         z = lambda shape, dt: t.zeros(shape, dtype=dt, device=dev)
         st = {"P": P, "cap": cap, "capB": capB, "W": W,
               "counts": z(P, t.int64), "counts_pin": t.zeros(P, dtype=t.int64).pin_memory(),
@@ -251,10 +266,21 @@ class DQNApex(DQNPer):
         grp_f = lambda fl, attr: {f.key: fl[f.name] for f in fields.values() if f.attr == attr and f.kind == "major"}
         tree, table = buf.wt_tree.handle, buf.buffer_version_table
         prog = self._static_program(st, capB) if self.use_fused_program else None
+        st["peer"] = peer
+        if peer is not None:
+            n_grad = int(self._flat_grad.numel())
+            pb = {"recv": peer.alloc((P * cap, W), t.uint8), "recv2": peer.alloc((P * cap, 24), t.uint8),
+                  "sums": peer.alloc((P,), t.float64), "grads": peer.alloc((P, n_grad), t.float32)}
+            st["peer_buffers"] = pb
+            st["recv"], st["recv2"], st["sums"] = pb["recv"].local, pb["recv2"].local, pb["sums"].local
+            SITE_SUMS, SITE_ROWS, SITE_PRIORITIES, SITE_GRADS = 0, 1, 2, 3
 
         def body():
             if st["device_apportion"]:
-                if P > 1:
+                if peer is not None:
+                    check(lib.mb_peer_push(ptr(buf.weight_sum_tensor()), 8, P, me, 8, pb["sums"].ptrs, stream_ptr()))
+                    peer.barrier(SITE_SUMS)
+                elif P > 1:
                     dist.all_gather_into_tensor(st["sums"], buf.weight_sum_tensor(), group=grp.pg)
                 else:
                     st["sums"].copy_(buf.weight_sum_tensor())
@@ -271,14 +297,20 @@ class DQNApex(DQNPer):
                 for r in range(P):                       # this shard serves every requester, member order
                     check(lib.mb_per_sample(tree, ptr(st["uni"][r]), cap, 0, 0.0, 0.0, ptr(st["params"][r]),
                                             ptr(st["d_idx"][r]), ptr(st["d_isw"][r]), stream_ptr()))
-            # the P wire blocks are contiguous in requester order: ONE gather and ONE metadata launch for all of them
-            buf.storage.gather_into_wire(st["d_idx"].view(-1), st["send"])
-            check(lib.mb_rows_pack_meta(ptr(st["send"]), W, pitch, P * cap, ptr(st["d_idx"]), None, ptr(table),
-                                        ptr(st["d_isw"]), None, stream_ptr()))
-            if P > 1:
-                dist.all_to_all_single(st["recv"], st["send"], group=grp.pg)
+            if peer is not None:
+                # gather + metadata + all-to-all as ONE kernel: every row goes straight into its requester's buffer
+                check(lib.mb_wire_push_rows(ptr(buf.storage.data), pitch, buf.storage.max_size, ptr(st["d_idx"]),
+                                            ptr(st["d_isw"]), ptr(table), P, cap, me, W, pb["recv"].ptrs, stream_ptr()))
+                peer.barrier(SITE_ROWS)
             else:
-                st["recv"].copy_(st["send"])
+                # the P wire blocks are contiguous in requester order: ONE gather and ONE metadata launch for all of them
+                buf.storage.gather_into_wire(st["d_idx"].view(-1), st["send"])
+                check(lib.mb_rows_pack_meta(ptr(st["send"]), W, pitch, P * cap, ptr(st["d_idx"]), None, ptr(table),
+                                            ptr(st["d_isw"]), None, stream_ptr()))
+                if P > 1:
+                    dist.all_to_all_single(st["recv"], st["send"], group=grp.pg)
+                else:
+                    st["recv"].copy_(st["send"])
             check(lib.mb_wire_compact(ptr(st["recv"]), P, cap, W, pitch, ptr(st["counts"]), ptr(st["merged"]), capB,
                                       ptr(st["idx"]), ptr(st["ver"]), ptr(st["isw"]), ptr(st["scale"]), stream_ptr()))
             if prog is not None:
@@ -312,12 +344,17 @@ class DQNApex(DQNPer):
                                 self.discount, is_weight=st["isw"], mode=self.mode, want_grad=True)
 
             def write_back():
-                check(lib.mb_wire_scatter_update(ptr(st["send2"]), P, cap, ptr(st["counts"]), ptr(st["idx"]), ptr(st["ver"]),
-                                                 ptr(td["abs_error"]), capB, stream_ptr()))
-                if P > 1:
-                    dist.all_to_all_single(st["recv2"], st["send2"], group=grp.pg)
+                if peer is not None:
+                    check(lib.mb_wire_push_update(P, cap, me, ptr(st["counts"]), ptr(st["idx"]), ptr(st["ver"]),
+                                                  ptr(td["abs_error"]), capB, pb["recv2"].ptrs, stream_ptr()))
+                    peer.barrier(SITE_PRIORITIES)
                 else:
-                    st["recv2"].copy_(st["send2"])
+                    check(lib.mb_wire_scatter_update(ptr(st["send2"]), P, cap, ptr(st["counts"]), ptr(st["idx"]), ptr(st["ver"]),
+                                                     ptr(td["abs_error"]), capB, stream_ptr()))
+                    if P > 1:
+                        dist.all_to_all_single(st["recv2"], st["send2"], group=grp.pg)
+                    else:
+                        st["recv2"].copy_(st["send2"])
                 check(lib.mb_wire_update_mask(ptr(st["recv2"]), P, cap, ptr(st["counts"]), me, ptr(table), table.numel(),
                                               ptr(st["u_idx"]), ptr(st["u_pri"]), ptr(st["u_valid"]), stream_ptr()))
                 PrioritizedBuffer.update_priority(buf, st["u_pri"], st["u_idx"], valid=st["u_valid"])
@@ -336,7 +373,14 @@ class DQNApex(DQNPer):
             if prog is None:
                 self._flat_grad.zero_()
                 q.backward(td["grad_q"])
-            if P > 1:
+            if peer is not None:
+                # gradient all-reduce: my flat buffer into slot `me` of every member, barrier, then every member adds
+                # the P slots in member order -- bit-identical averaged gradients everywhere
+                n_grad = int(self._flat_grad.numel())
+                check(lib.mb_peer_push(ptr(self._flat_grad), 4 * n_grad, P, me, 4 * n_grad, pb["grads"].ptrs, stream_ptr()))
+                peer.barrier(SITE_GRADS)
+                check(lib.mb_peer_sum(ptr(pb["grads"].local), P, n_grad, float(P), ptr(self._flat_grad), stream_ptr()))
+            elif P > 1:
                 red = self.learner_group if self.learner_group is not None else grp
                 dist.all_reduce(self._flat_grad, group=red.pg)
                 self._flat_grad.div_(red.size())

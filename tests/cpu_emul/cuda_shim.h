@@ -36,6 +36,7 @@ inline float __ldcg(const float *p) { return *p; }
 inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }   // volatile: no contraction
 inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }

@@ -69,4 +69,42 @@ int emul_wire_apportion(const double *sums, int P, int64_t batch, int self_block
     return 0;
 }
 
+// peer-memory exchange: "peers" are plain host buffers here (one per emulated shard)
+int emul_wire_push_rows(const char *ring, int64_t pitch, int64_t capacity, const int64_t *index, const double *isw,
+                        const int64_t *version_table, int P, int64_t cap, int self_block, int64_t width, char **peers) {
+    PeerPtrs pp{};
+    for (int m = 0; m < P; ++m) pp.p[m] = peers[m];
+    int64_t blocks = ((int64_t)P * cap * 32 + 255) / 256;
+    if (blocks > 64) blocks = 64;
+    shim_launch((unsigned)blocks, 256, [&] {
+        wire_push_rows_kernel(ring, pitch, capacity, index, isw, version_table, P, cap, self_block, width, pp);
+    });
+    return 0;
+}
+
+int emul_wire_push_update(int P, int64_t cap, int self_block, const int64_t *counts, const int64_t *index,
+                          const int64_t *version, const float *priority, int64_t merged_rows, char **peers) {
+    PeerPtrs pp{};
+    for (int m = 0; m < P; ++m) pp.p[m] = peers[m];
+    shim_launch((unsigned)((merged_rows + 255) / 256), 256, [&] {
+        wire_push_update_kernel(P, cap, self_block, counts, index, version, priority, merged_rows, pp);
+    });
+    return 0;
+}
+
+int emul_peer_push(const char *src, int64_t nbytes, int P, int self_block, int64_t slot_stride, char **peers) {
+    PeerPtrs pp{};
+    for (int m = 0; m < P; ++m) pp.p[m] = peers[m];
+    for (int dst = 0; dst < P; ++dst) {                 // blockIdx.y = destination member
+        blockIdx.y = (unsigned)dst;
+        shim_launch(2, 256, [&] { blockIdx.y = (unsigned)dst; peer_push_kernel(src, nbytes, self_block, slot_stride, pp); });
+    }
+    return 0;
+}
+
+int emul_peer_sum(const float *slots, int P, int64_t n, float divisor, float *out) {
+    shim_launch(2, 256, [&] { peer_sum_kernel(slots, P, n, divisor, out); });
+    return 0;
+}
+
 }  // extern "C"

@@ -77,6 +77,39 @@ def main():
     wcs = [t.empty_like(wc) for _ in range(world)]
     dist.all_gather(wcs, wc)
     assert all(t.equal(wcs[0], x) for x in wcs)
+    # ---- peer exchange (no NCCL inside the update: rows, priorities, shard sums and gradients are stored into the
+    #      other GPUs' buffers over NVLink by csrc/peer.cu): the same trajectory as the NCCL fixed-shape update, with
+    #      host apportioning (draw for draw against `b2`) and with device apportioning + the stream-level options
+    b2, d = make(), make()
+    b2.enable_cuda_graph(static_exchange=True)
+    d.enable_cuda_graph(static_exchange=True, peer_exchange=True)
+    peer_on = d._static["peer"] is not None
+    for step in range(6):
+        np.random.seed(500 * rank + step)
+        lb2 = b2.update_device().item()
+        np.random.seed(500 * rank + step)
+        ld = d.update_device().item()
+        assert abs(ld - lb2) <= 1e-5 * max(1.0, abs(lb2)), (step, ld, lb2)
+        np.testing.assert_allclose(d.replay_buffer.wt_tree.weights, b2.replay_buffer.wt_tree.weights, rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(flat(d.qnet), flat(b2.qnet), rtol=1e-4, atol=1e-6)
+    if peer_on:
+        d._static["peer"].check()
+    e = make()
+    e.batched_draw = e.parallel_forwards = e.overlap_priority_update = True
+    e.enable_cuda_graph(static_exchange=True, device_apportion=True, peer_exchange=True)
+    for step in range(8):
+        le = e.update_device().item()
+        assert np.isfinite(le) and le >= 0.0, (step, le)
+    t.cuda.synchronize()
+    e.replay_buffer.wt_tree.check()
+    if e._static["peer"] is not None:
+        e._static["peer"].check()
+    we = t.from_numpy(flat(e.qnet)).cuda()
+    wes = [t.empty_like(we) for _ in range(world)]
+    dist.all_gather(wes, we)
+    assert all(t.equal(wes[0], x) for x in wes)           # bit-identical weights on every member (ordered peer sum)
+    if rank == 0:
+        print(f"peer exchange {'ok' if peer_on else 'UNAVAILABLE (NCCL fallback ran)'} (world {world})", flush=True)
     # every member holds the same weights after averaged gradients
     w = t.from_numpy(flat(b.qnet)).cuda()
     ws = [t.empty_like(w) for _ in range(world)]

@@ -65,6 +65,16 @@ def test_fixed_shape_exchange_replayed_for_P_shards(wire, P, pitch):
     version_at_sample = [t.copy() for t in table]
     # ---- all-to-all: requester r receives block r of every shard, in member order
     recv = [np.concatenate([send[m][r * cap:(r + 1) * cap] for m in range(P)]) for r in range(P)]
+    # ---- the peer-memory variant (csrc/peer.cu: mb_wire_push_rows): ONE kernel per shard gathers, adds the metadata
+    #      and stores every row straight into its requester's receive buffer -- must equal gather + pack + all-to-all
+    pushed = [np.zeros((P * cap, W), dtype=np.uint8) for _ in range(P)]
+    peers = (C.c_void_p * P)(*[b.ctypes.data for b in pushed])
+    for m in range(P):
+        all_idx, all_isw = np.concatenate(idx[m]), np.concatenate(isw[m])
+        assert wire.emul_wire_push_rows(p(ring[m]), C.c_int64(pitch), C.c_int64(rows_in_ring), p(all_idx), p(all_isw),
+                                        p(table[m]), P, C.c_int64(cap), m, C.c_int64(W), peers) == 0
+    for r in range(P):
+        assert np.array_equal(pushed[r], recv[r]), r
     n = int(counts.sum())
     scale = np.array([capB / n])
     merged, m_idx, m_ver, m_isw = [], [], [], []
@@ -91,6 +101,15 @@ def test_fixed_shape_exchange_replayed_for_P_shards(wire, P, pitch):
         assert wire.emul_wire_scatter_update(p(send2[r]), P, C.c_int64(cap), p(counts), p(m_idx[r]), p(m_ver[r]), p(pri[r]),
                                              C.c_int64(capB)) == 0
     recv2 = [np.concatenate([send2[r][m * cap:(m + 1) * cap] for r in range(P)]) for m in range(P)]
+    # peer-memory variant (mb_wire_push_update): the same (index, version, priority) triples land in the serving
+    # shard's buffer directly; entries beyond counts[m] are never written (and never read: the mask checks counts)
+    pushed2 = [np.full((P * cap, META), 0xCD, dtype=np.uint8) for _ in range(P)]
+    peers2 = (C.c_void_p * P)(*[b.ctypes.data for b in pushed2])
+    for r in range(P):
+        assert wire.emul_wire_push_update(P, C.c_int64(cap), r, p(counts), p(m_idx[r]), p(m_ver[r]), p(pri[r]),
+                                          C.c_int64(capB), peers2) == 0
+    for m in range(P):
+        assert np.array_equal(pushed2[m], recv2[m]), m
     # some slots were overwritten between sampling and write-back: their version moved on (prioritized_buffer_d.py:131)
     for m in range(P):
         table[m][rng.rand(rows_in_ring) < 0.2] += 1
@@ -148,3 +167,25 @@ def test_device_apportioning_matches_host_apportioning(wire, P):
             if ssize[me] > 0:
                 b = float(np.min([1.0, b + inc]))
         assert beta[0] == b
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 8])
+def test_peer_push_and_ordered_sum(wire, P):
+    """mb_peer_push + mb_peer_sum: every member's buffer lands in slot `self` of every member, and the sum is taken in
+    member order with separately rounded float32 adds and one division -- all members get bit-identical averages."""
+    rng = np.random.RandomState(P)
+    n = 1000 + P                                             # not a multiple of 4: the byte-wise tail of the copy
+    grads = [(rng.randn(n) * 10 ** rng.uniform(-3, 3, size=n)).astype(np.float32) for _ in range(P)]
+    slots = [np.full((P, n), np.nan, dtype=np.float32) for _ in range(P)]
+    peers = (C.c_void_p * P)(*[b.ctypes.data for b in slots])
+    for m in range(P):
+        assert wire.emul_peer_push(p(grads[m]), C.c_int64(4 * n), P, m, C.c_int64(4 * n), peers) == 0
+    want = grads[0].copy()
+    for m in range(1, P):
+        want = (want + grads[m]).astype(np.float32)
+    want = (want / np.float32(P)).astype(np.float32)
+    for m in range(P):
+        assert np.array_equal(slots[m], np.stack(grads))
+        out = np.zeros(n, dtype=np.float32)
+        assert wire.emul_peer_sum(p(slots[m]), P, C.c_int64(n), C.c_float(P), p(out)) == 0
+        assert np.array_equal(out, want)
