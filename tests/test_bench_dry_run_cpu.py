@@ -155,7 +155,7 @@ def test_b200_arm_dry_run_two_ranks(case, monkeypatch):
     if case == "static_capture_fails":
         real_enable, calls = apex_mod.DQNApex.enable_cuda_graph, []
 
-        def enable(self, warmup=3, static_exchange=False, device_apportion=False):
+        def enable(self, warmup=3, static_exchange=False, device_apportion=False, peer_exchange=False):
             calls.append(static_exchange)
             if static_exchange:
                 raise RuntimeError("capture refused (injected)")
