@@ -327,7 +327,8 @@ bool small_gemm_enabled() {          // MB_GEMM_LEGACY=1: the 64 x 64 kernel eve
 template <bool kA, bool kB>
 bool launch_small(GemmArgs g, cudaStream_t s) {
     const int tiles64 = ((g.N + TN - 1) / TN) * ((g.M + TM - 1) / TM);
-    if (!small_gemm_enabled() || tiles64 >= 2 * mb::kNumSMs) return false;
+    // (reductions longer than 1024 keep the grid-level split-K of the 64 x 64 kernel: more, shorter partial sums)
+    if (!small_gemm_enabled() || tiles64 >= 2 * mb::kNumSMs || g.K > 1024) return false;
     const dim3 grid((g.N + ST - 1) / ST, (g.M + ST - 1) / ST, 1);
     const int ksteps = (g.K + STK - 1) / STK;
     if (ksteps >= 4) {
