@@ -226,8 +226,11 @@ def test_fused_mlp_matches_torch(sizes, batch, legacy, monkeypatch):
     y.backward(gy)
     y2.backward(gy)
     np.testing.assert_allclose(x.grad.cpu().numpy(), x2.grad.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    # weight gradients are float32 sums over the batch in a blocking that differs from cuBLAS': the absolute rounding
+    # noise of such a sum grows with its length (entries near zero next to entries of magnitude ~80 at batch 8192)
+    atol = 1e-5 if batch <= 2048 else 5e-5
     for a, b in zip(net.parameters(), ref.parameters()):
-        np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.cpu().numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.cpu().numpy(), rtol=1e-4, atol=atol)
     with t.no_grad():
         assert net(x).shape == (batch, sizes[-1])
 
