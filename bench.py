@@ -53,16 +53,18 @@ def parse():
     p.add_argument("--cpu-steps", type=int, default=1500)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per update")
-    p.add_argument("--net", default="torch", choices=["torch", "fused", "fused-program", "fused-rows"],
-                   help="Q-net implementation: nn.Module over cuBLAS (default, fastest measured), FusedMLP autograd "
-                        "(csrc/mlp.cu), or FusedMLP + the persistent fused forward/TD/backward program")
+    p.add_argument("--net", default="fused", choices=["torch", "fused", "fused-program", "fused-rows"],
+                   help="Q-net implementation: FusedMLP (default since round 2: one csrc/mlp.cu kernel per layer and direction, "
+                        "127 vs 135 us/update at N = 1), a plain nn.Module over cuBLAS + eager torch kernels, or FusedMLP + one "
+                        "of the fused forward/TD/backward programs (slower, opt-in)")
     p.add_argument("--dynamic-exchange", action="store_true",
                    help="N > 1: exactly-sized eager NCCL exchanges between two CUDA graphs instead of the default "
                         "fixed-shape exchange captured with the rest of the update in ONE graph")
-    p.add_argument("--peer-exchange", action="store_true",
-                   help="N > 1, fixed-shape exchange: no NCCL inside the update -- rows, priorities, shard sums and gradients "
-                        "are stored into the other GPUs' buffers over NVLink by csrc/peer.cu (falls back to NCCL if the buffers "
-                        "cannot be peer-mapped)")
+    p.add_argument("--nccl-exchange", action="store_true",
+                   help="N > 1, fixed-shape exchange: NCCL collectives captured in the graph instead of the default since round "
+                        "2 -- rows, priorities, shard sums and gradients stored into the other GPUs' buffers over NVLink by "
+                        "csrc/peer.cu, one barrier kernel per exchange (measured at N = 2: 200 vs 220 us/update; falls back to "
+                        "NCCL by itself if the buffers cannot be peer-mapped)")
     p.add_argument("--host-apportion", action="store_true",
                    help="N > 1, fixed-shape exchange: round 1's variant -- the host reads the all-gathered shard sums every "
                         "update and apportions; one draw launch per requester (measured at N = 2: 278 vs 220 us/update)")
@@ -85,6 +87,7 @@ def parse():
     # default since round 2 (profiles/r2_n2_variants.md): shard sums all-gathered and apportioned inside the graph (no host
     # read per update), the draws for all requesters in one launch
     a.device_apportion = a.batched_draw = not a.host_apportion
+    a.peer_exchange = not a.nccl_exchange
     if not a.serial and a.net in ("torch", "fused"):
         # default since round 2 (measured at N = 1: 198 -> 138 us/update, profiles/r2_ab_variants.md): the two no-grad
         # forwards and the priority write-back are parallel branches of the captured graph, Adam + soft update one launch

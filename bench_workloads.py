@@ -391,11 +391,12 @@ def run_c4(a, ClockSampler):
 
     t.manual_seed(0)                                    # identical initial weights on every learner
     nets = [Actor().to(dev), Actor().to(dev), Critic().to(dev), Critic().to(dev)]
-    graph = world == 1 and not a.no_graph
+    graph = not a.no_graph
     if world > 1:
         group = ShardGroup("apex", device=dev)
         learner = DDPGApex(*nets, FusedAdam, t.nn.MSELoss(reduction="none"), group, (), batch_size=B, replay_size=rows,
                            learner_group=group)
+        learner.batched_draw = learner.overlap_priority_update = not a.serial
     else:
         learner = DDPGPer(*nets, FusedAdam, t.nn.MSELoss(reduction="none"), batch_size=B, replay_size=rows)
     buf = learner.replay_buffer
@@ -411,7 +412,9 @@ def run_c4(a, ClockSampler):
             priorities=t.empty(n, device=dev, dtype=t.float64).exponential_(1.0, generator=gen))
         done += n
     buf.wt_tree.check()
-    if graph:
+    if graph and world > 1:
+        learner.enable_cuda_graph(device_apportion=not a.host_apportion, peer_exchange=not a.nccl_exchange)
+    elif graph:
         learner.enable_cuda_graph()
     K, W = a.steps, max(a.warmup, 3)
     np.random.seed(1234 + rank)
@@ -426,6 +429,9 @@ def run_c4(a, ClockSampler):
     f_dev, f_wall, last = _timed(run, K, lambda s: learner.update())
     # at N > 1 the exchange reads the shard sums on the host every update: wall time is the honest clock there
     ms_total, e2e_ms = run.max_over_ranks([ms_dev if graph else max(ms_dev, ms_wall), max(f_dev, f_wall)])
+    if hasattr(learner, "release_graphs"):
+        t.cuda.synchronize(dev)
+        learner.release_graphs()
     # this library's kernels on this rank's shard
     kern = {}
     if rank == 0:
@@ -474,8 +480,11 @@ def run_c4(a, ClockSampler):
                        "shard_bytes": int(buf.storage.pitch) * rows, "optimizer": "Adam (FusedAdam)",
                        "parallelism": f"{world} learner(s), one replay shard each",
                        "launch": "one CUDA graph per update" if graph else "eager kernels around eager NCCL exchanges",
-                       "exchange": None if world == 1 else "per update: all-gather of shard sums (host read), all-to-all of sampled "
-                                   "rows, all-to-all of priority write-backs, 2 all-reduces of gradients (critic, actor)",
+                       "transport": None if world == 1 else (
+                           "peer memory over NVLink (csrc/peer.cu): push kernels + one barrier kernel per exchange"
+                           if (getattr(learner, "_static", None) or {}).get("peer") is not None else "NCCL (torch.distributed)"),
+                       "exchange": None if world == 1 else "per update: shard sums, sampled rows, priority write-backs, "
+                                   "2 gradient averages (critic, actor)",
                        "l2": "inputs larger than L2: 268 MB tree + 38.8 GB ring per shard, randomly addressed every step"},
             "e2e": {"value": world * B * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 16 + (8 * world if world > 1 else 0), "ms_per_step": e2e_ms / K,

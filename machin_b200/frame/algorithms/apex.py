@@ -19,7 +19,7 @@ import torch.nn as nn
 from ... import ops
 from ..buffers import DistributedPrioritizedBuffer
 from .dqn_per import DQNPer
-from .utils import soft_update
+from .utils import capture_safe, soft_update
 
 
 def _flat_grad_all_reduce(params, group, flat=None):
@@ -61,7 +61,265 @@ def _restore_optimizer(optim, saved, was_fresh):
                         v.copy_(saved[id(p)][k])
 
 
-class DQNApex(DQNPer):
+class _FixedShapeExchange:
+    """The fixed-shape shard exchange shared by DQNApex and DDPGApex (mixed into both): every (shard, requester) pair
+    always moves ``batch_size`` wire rows and every kernel reads the apportioned counts from device memory, so the whole
+    sharded update -- shard sums, apportioning, draws, row exchange, the learner's math, gradient averaging, priority
+    exchange, masked tree update -- is ONE CUDA graph replay.  Transport: peer memory over NVLink (csrc/peer.cu: the
+    producing kernel stores into the consumer's buffer, one barrier kernel per exchange) or NCCL collectives captured in
+    the graph.  Follows prioritized_buffer_d.py:184-303; state lives in ``self._static``."""
+
+    SITE_SUMS, SITE_ROWS, SITE_PRIORITIES, SITE_GRADS, SITE_GRADS_2 = 0, 1, 2, 3, 4
+
+    def _static_setup(self, device_apportion: bool, peer_exchange: bool, grad_floats: int):
+        """Collective.  Allocates every buffer of the exchange (peer-mapped ones if ``peer_exchange`` works here) and
+        stores the state dict in ``self._static``.  ``grad_floats``: size of the largest flat gradient buffer that will be
+        averaged through :meth:`_static_all_reduce`."""
+        buf, grp = self.replay_buffer, self.apex_group
+        dev, P, B = buf.buffer_device, grp.size(), self.batch_size
+        if B > 1024 or list(buf._exchange().requesters) != list(range(P)):
+            raise RuntimeError("static exchange needs batch <= 1024 and every member learning")
+        pitch = buf.storage.pitch
+        peer = None
+        if peer_exchange and P > 1:
+            try:
+                from ...parallel.peer import PeerMemory
+                peer = PeerMemory.create(grp)
+            except Exception as exc:      # noqa: BLE001 -- every member fails alike (same torch, same topology)
+                import warnings
+                warnings.warn(f"peer exchange unavailable ({exc!r}); the fixed-shape update keeps its NCCL collectives")
+                peer = None
+        # wire row = packed row + (index, version, is_weight); padded to 16 bytes for the peer stores
+        W, cap, capB = pitch + (32 if peer is not None else 24), B, B + P
+        z = lambda shape, dt: t.zeros(shape, dtype=dt, device=dev)
+        st = {"P": P, "cap": cap, "capB": capB, "W": W, "peer": peer,
+              "counts": z(P, t.int64), "counts_pin": t.zeros(P, dtype=t.int64).pin_memory(),
+              "params": z((P, 40), t.uint8), "params_pin": t.zeros((P, 40), dtype=t.uint8).pin_memory(),
+              "uni": z((P, cap), t.float64), "uni_pin": t.zeros((P, cap), dtype=t.float64).pin_memory(),
+              "scale": z(1, t.float64), "scale_pin": t.zeros(1, dtype=t.float64).pin_memory(),
+              "send": z((P * cap, W), t.uint8), "recv": z((P * cap, W), t.uint8),
+              "merged": z((capB, W), t.uint8), "idx": z(capB, t.int64), "ver": z(capB, t.int64), "isw": z(capB, t.float64),
+              "send2": z((P * cap, 24), t.uint8), "recv2": z((P * cap, 24), t.uint8),
+              "u_idx": z(P * cap, t.int64), "u_pri": z(P * cap, t.float32), "u_valid": z(P * cap, t.uint8),
+              "d_idx": z((P, cap), t.int64), "d_isw": z((P, cap), t.float64),       # row r: the draw for requester r
+              "device_apportion": bool(device_apportion),
+              "sums": z(P, t.float64), "beta": z(1, t.float64), "nstored": z(1, t.int64),
+              # device apportioning lets the host run ahead of the device, so what it writes per update goes through a
+              # small ring of pinned buffers guarded by events (copied in FRONT of the replay, not inside the graph)
+              "ring_uni": [t.zeros((P, cap), dtype=t.float64).pin_memory() for _ in range(4)],
+              "ring_ns": [t.zeros(1, dtype=t.int64).pin_memory() for _ in range(4)],
+              "ring_ev": [t.cuda.Event() for _ in range(4)], "ring_i": 0}
+        if peer is not None:
+            pb = {"recv": peer.alloc((P * cap, W), t.uint8), "recv2": peer.alloc((P * cap, 24), t.uint8),
+                  "sums": peer.alloc((P,), t.float64), "grads": peer.alloc((P, int(grad_floats)), t.float32)}
+            st["peer_buffers"] = pb
+            st["recv"], st["recv2"], st["sums"] = pb["recv"].local, pb["recv2"].local, pb["sums"].local
+        self._static = st
+        return st
+
+    def _static_sample(self):
+        """Capturable: shard sums -> apportioning -> this shard's draws for every requester -> row exchange ->
+        compaction.  Leaves the merged, padded batch in ``st["merged"]`` (wire rows), ``st["idx"]`` / ``st["ver"]`` /
+        ``st["isw"]`` (IS weights already scaled so that a mean over the padded rows is the mean over the real ones)."""
+        import torch.distributed as dist
+        from ..._lib import lib, ptr, check, stream_ptr
+        st, buf, grp = self._static, self.replay_buffer, self.apex_group
+        P, me, B, cap, capB, W, peer = st["P"], grp.index, self.batch_size, st["cap"], st["capB"], st["W"], st["peer"]
+        pitch, tree, table = buf.storage.pitch, buf.wt_tree.handle, buf.buffer_version_table
+        pb = st.get("peer_buffers")
+        if st["device_apportion"]:
+            if peer is not None:
+                check(lib.mb_peer_push(ptr(buf.weight_sum_tensor()), 8, P, me, 8, pb["sums"].ptrs, stream_ptr()))
+                peer.barrier(self.SITE_SUMS)
+            elif P > 1:
+                dist.all_gather_into_tensor(st["sums"], buf.weight_sum_tensor(), group=grp.pg)
+            else:
+                st["sums"].copy_(buf.weight_sum_tensor())
+            check(lib.mb_wire_apportion(ptr(st["sums"]), P, B, me, capB, ptr(st["nstored"]), ptr(st["beta"]),
+                                        float(buf.beta_increment_per_sampling), ptr(st["counts"]), ptr(st["scale"]),
+                                        ptr(st["params"]), stream_ptr()))
+        else:
+            for name in ("counts", "params", "uni", "scale"):
+                st[name].copy_(st[name + "_pin"], non_blocking=True)
+        if getattr(self, "batched_draw", False):     # opt-in: every requester's draw in ONE launch (one cluster each)
+            check(lib.mb_per_sample_multi(tree, ptr(st["uni"]), cap, P, ptr(st["params"]), ptr(st["d_idx"]),
+                                          ptr(st["d_isw"]), stream_ptr()))
+        else:
+            for r in range(P):                       # this shard serves every requester, member order
+                check(lib.mb_per_sample(tree, ptr(st["uni"][r]), cap, 0, 0.0, 0.0, ptr(st["params"][r]),
+                                        ptr(st["d_idx"][r]), ptr(st["d_isw"][r]), stream_ptr()))
+        if peer is not None:
+            # gather + metadata + all-to-all as ONE kernel: every row goes straight into its requester's buffer
+            check(lib.mb_wire_push_rows(ptr(buf.storage.data), pitch, buf.storage.max_size, ptr(st["d_idx"]),
+                                        ptr(st["d_isw"]), ptr(table), P, cap, me, W, pb["recv"].ptrs, stream_ptr()))
+            peer.barrier(self.SITE_ROWS)
+        else:
+            # the P wire blocks are contiguous in requester order: ONE gather and ONE metadata launch for all of them
+            buf.storage.gather_into_wire(st["d_idx"].view(-1), st["send"])
+            check(lib.mb_rows_pack_meta(ptr(st["send"]), W, pitch, P * cap, ptr(st["d_idx"]), None, ptr(table),
+                                        ptr(st["d_isw"]), None, stream_ptr()))
+            if P > 1:
+                dist.all_to_all_single(st["recv"], st["send"], group=grp.pg)
+            else:
+                st["recv"].copy_(st["send"])
+        check(lib.mb_wire_compact(ptr(st["recv"]), P, cap, W, pitch, ptr(st["counts"]), ptr(st["merged"]), capB,
+                                  ptr(st["idx"]), ptr(st["ver"]), ptr(st["isw"]), ptr(st["scale"]), stream_ptr()))
+
+    def _static_write_back(self, abs_error: t.Tensor):
+        """Capturable: route (index, version, |delta|) of every merged row back to the shard that served it, filter by
+        version, update this shard's tree (prioritized_buffer_d.py:184-202, :282-291)."""
+        import torch.distributed as dist
+        from ..._lib import lib, ptr, check, stream_ptr
+        from ..buffers import PrioritizedBuffer
+        st, buf, grp = self._static, self.replay_buffer, self.apex_group
+        P, me, cap, capB, peer, table = st["P"], grp.index, st["cap"], st["capB"], st["peer"], self.replay_buffer.buffer_version_table
+        if peer is not None:
+            check(lib.mb_wire_push_update(P, cap, me, ptr(st["counts"]), ptr(st["idx"]), ptr(st["ver"]), ptr(abs_error), capB,
+                                          st["peer_buffers"]["recv2"].ptrs, stream_ptr()))
+            peer.barrier(self.SITE_PRIORITIES)
+        else:
+            check(lib.mb_wire_scatter_update(ptr(st["send2"]), P, cap, ptr(st["counts"]), ptr(st["idx"]), ptr(st["ver"]),
+                                             ptr(abs_error), capB, stream_ptr()))
+            if P > 1:
+                dist.all_to_all_single(st["recv2"], st["send2"], group=grp.pg)
+            else:
+                st["recv2"].copy_(st["send2"])
+        check(lib.mb_wire_update_mask(ptr(st["recv2"]), P, cap, ptr(st["counts"]), me, ptr(table), table.numel(),
+                                      ptr(st["u_idx"]), ptr(st["u_pri"]), ptr(st["u_valid"]), stream_ptr()))
+        PrioritizedBuffer.update_priority(buf, st["u_pri"], st["u_idx"], valid=st["u_valid"])
+
+    def _static_write_back_maybe_forked(self, abs_error: t.Tensor):
+        """The write-back only feeds the NEXT draw: with ``overlap_priority_update`` it runs on a side stream (a parallel
+        branch of the captured graph) beside backward, gradient averaging and the optimizers.  Every member issues its
+        exchanges in the same program order.  Returns the (main, side) stream pair to join, or None."""
+        if not getattr(self, "overlap_priority_update", False):
+            return None
+        dev = self.replay_buffer.buffer_device
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = t.cuda.Stream(device=dev)
+        forked = (t.cuda.current_stream(dev), self._side_stream)
+        forked[1].wait_stream(forked[0])
+        with t.cuda.stream(forked[1]):
+            self._static_write_back(abs_error)
+        return forked
+
+    def _static_all_reduce(self, flat: t.Tensor, site: int = 3):
+        """Capturable: average a flat float32 gradient buffer over the members, in place.  Peer transport: my buffer
+        into slot ``me`` of every member, barrier, then every member adds the P slots in member order -- bit-identical
+        averaged gradients everywhere."""
+        import torch.distributed as dist
+        from ..._lib import lib, ptr, check, stream_ptr
+        st, grp = self._static, self.apex_group
+        P, me, peer = st["P"], grp.index, st["peer"]
+        n = int(flat.numel())
+        if peer is not None:
+            slots = st["peer_buffers"]["grads"]
+            stride = int(slots.local.shape[1]) * 4
+            check(lib.mb_peer_push(ptr(flat), 4 * n, P, me, stride, slots.ptrs, stream_ptr()))
+            peer.barrier(site)
+            if n == slots.local.shape[1]:
+                check(lib.mb_peer_sum(ptr(slots.local), P, n, float(P), ptr(flat), stream_ptr()))
+            else:                                       # a smaller buffer in the same slots: strided view, same order
+                acc = slots.local[0, :n].clone()
+                for m in range(1, P):
+                    acc += slots.local[m, :n]
+                flat.copy_(acc / P)
+        elif P > 1:
+            red = self.learner_group if getattr(self, "learner_group", None) is not None else grp
+            dist.all_reduce(flat, group=red.pg)
+            flat.div_(red.size())
+
+    def _static_capture(self, body, warmup, nets, optims):
+        """torch's capture protocol around ``body`` (warm-up on a side stream, capture, undo everything the warm-up
+        touched in place) -> (graph, what body returned during capture)."""
+        from ..._lib import lib
+        st, buf, grp = self._static, self.replay_buffer, self.apex_group
+        dev = buf.buffer_device
+        tensors_of = lambda m: list(m.parameters()) + list(m.buffers())
+        saved = [[x.detach().clone() for x in tensors_of(m)] for m in nets]
+        fresh = [len(o.state) == 0 for o in optims]
+        saved_optim = [_snapshot_optimizer(o) for o in optims]
+        tree_snap, beta0 = buf.wt_tree.snapshot(), buf.curr_beta
+        np_state = np.random.get_state()
+        for m in nets:
+            m.train()
+        st["beta"].fill_(float(beta0))
+        self._static_prepare()                           # collective: real counts / uniforms for the warm-up
+        cur, side = t.cuda.current_stream(dev), t.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with t.cuda.stream(side):
+            for _ in range(warmup):
+                body()
+        cur.wait_stream(side)
+        t.cuda.synchronize(dev)
+        graph = t.cuda.CUDAGraph()
+        launched = lib.mb_launch_count()
+        with capture_safe(), t.cuda.graph(graph, capture_error_mode="thread_local"):
+            out = body()
+        st["graph"] = graph
+        self.graph_launches = lib.mb_launch_count() - launched     # libmachin_b200 kernels per replayed update
+        with t.no_grad():
+            for m, sv in zip(nets, saved):
+                for x, v in zip(tensors_of(m), sv):
+                    x.copy_(v)
+        for o, sv, fr in zip(optims, saved_optim, fresh):
+            _restore_optimizer(o, sv, fr)
+        buf.wt_tree.restore(tree_snap)
+        buf.curr_beta = beta0
+        st["beta"].fill_(float(beta0))
+        np.random.set_state(np_state)
+        t.cuda.synchronize(dev)
+        if st["P"] > 1:
+            grp.barrier()
+        if st["peer"] is not None:
+            st["peer"].check()
+        return graph, out
+
+    def _static_prepare(self):
+        """Host part of a fixed-shape update: read the shard sums (one sync), apportion, draw this shard's
+        uniforms from np.random in the reference's order, refresh the pinned parameter blocks."""
+        from ...parallel.exchange import shard_sample_sizes
+        st, buf, grp = self._static, self.replay_buffer, self.apex_group
+        P, me, cap = st["P"], grp.index, st["cap"]
+        if st["device_apportion"]:
+            # nothing here depends on the device: fixed-size uniform blocks, the stored-row count, and a host mirror
+            # of beta (it advances once per requester served, :425-427; the device holds the authoritative value)
+            i = st["ring_i"] = (st["ring_i"] + 1) % len(st["ring_ev"])
+            st["ring_ev"][i].synchronize()                  # the copy that last used this slot has finished
+            st["ring_uni"][i].numpy()[:] = np.random.uniform(size=(P, cap))
+            st["ring_ns"][i].numpy()[0] = len(buf.storage)
+            st["uni"].copy_(st["ring_uni"][i], non_blocking=True)
+            st["nstored"].copy_(st["ring_ns"][i], non_blocking=True)
+            st["ring_ev"][i].record()
+            for _ in range(P):
+                buf.curr_beta = np.float64(min(1.0, buf.curr_beta + buf.beta_increment_per_sampling))
+            return self.batch_size
+        sums = grp.all_gather_f64(buf.weight_sum_tensor()).view(-1).tolist()
+        ssize, total = shard_sample_sizes(sums, self.batch_size)
+        n, n_mine = int(sum(ssize)), int(ssize[me])
+        views = st.get("np")
+        if views is None:                                 # NumPy views of the pinned blocks, taken once
+            rec = np.dtype([("beta", "<f8"), ("total", "<f8"), ("n_stored", "<i8"), ("step", "<i8"), ("n_draw", "<i8")])
+            views = st["np"] = {"counts": st["counts_pin"].numpy(), "scale": st["scale_pin"].numpy(),
+                                "params": st["params_pin"].numpy().view(rec).reshape(P), "uni": st["uni_pin"].numpy()}
+        views["counts"][:] = ssize
+        views["scale"][0] = st["capB"] / n
+        beta, betas = buf.curr_beta, []
+        for _ in range(P):                                # one draw per requester; beta advances per draw (:425-427)
+            betas.append(beta)
+            if n_mine > 0:
+                beta = np.float64(min(1.0, beta + buf.beta_increment_per_sampling))
+        prm = views["params"]
+        prm["beta"], prm["total"], prm["n_stored"], prm["step"], prm["n_draw"] = betas, total, len(buf.storage), 0, n_mine
+        if n_mine > 0:
+            # P consecutive draws of n_mine uniforms are one draw of P * n_mine from the same MT19937 stream (:411)
+            views["uni"][:, :n_mine] = np.random.uniform(size=P * n_mine).reshape(P, n_mine)
+        buf.curr_beta = beta
+        return n
+
+
+
+class DQNApex(_FixedShapeExchange, DQNPer):
     _config_frame, _config_kind = "DQNApex", "apex"
 
     def __init__(self, qnet: nn.Module, qnet_target: nn.Module, optimizer: Callable, criterion: Callable,
@@ -216,43 +474,11 @@ class DQNApex(DQNPer):
 
     # ------------------------------------------------------------------ fixed-shape, single-graph update
     def _enable_static_graph(self, warmup: int = 3, device_apportion: bool = False, peer_exchange: bool = False):
-        import torch.distributed as dist
         from ..._lib import lib, ptr, check, stream_ptr
-        from ..buffers import PrioritizedBuffer
         buf, grp = self.replay_buffer, self.apex_group
-        dev, P, me, B = buf.buffer_device, grp.size(), grp.index, self.batch_size
-        if not self._fused_mse or self.update_rate is None or B > 1024 or list(buf._exchange().requesters) != list(range(P)):
-            raise RuntimeError("static exchange needs MSELoss, soft target updates, batch <= 1024 and every member learning")
-        pitch = buf.storage.pitch
-        peer = None
-        if peer_exchange and P > 1:
-            try:
-                from ...parallel.peer import PeerMemory
-                peer = PeerMemory.create(grp)
-            except Exception as exc:      # noqa: BLE001 -- every member fails alike (same torch, same topology)
-                import warnings
-                warnings.warn(f"peer exchange unavailable ({exc!r}); the fixed-shape update keeps its NCCL collectives")
-                peer = None
-        # wire row = packed row + (index, version, is_weight); padded to 16 bytes for the peer stores
-        W, cap, capB = pitch + (32 if peer is not None else 24), B, B + P
-        z = lambda shape, dt: t.zeros(shape, dtype=dt, device=dev)
-        st = {"P": P, "cap": cap, "capB": capB, "W": W,
-              "counts": z(P, t.int64), "counts_pin": t.zeros(P, dtype=t.int64).pin_memory(),
-              "params": z((P, 40), t.uint8), "params_pin": t.zeros((P, 40), dtype=t.uint8).pin_memory(),
-              "uni": z((P, cap), t.float64), "uni_pin": t.zeros((P, cap), dtype=t.float64).pin_memory(),
-              "scale": z(1, t.float64), "scale_pin": t.zeros(1, dtype=t.float64).pin_memory(),
-              "send": z((P * cap, W), t.uint8), "recv": z((P * cap, W), t.uint8),
-              "merged": z((capB, W), t.uint8), "idx": z(capB, t.int64), "ver": z(capB, t.int64), "isw": z(capB, t.float64),
-              "send2": z((P * cap, 24), t.uint8), "recv2": z((P * cap, 24), t.uint8),
-              "u_idx": z(P * cap, t.int64), "u_pri": z(P * cap, t.float32), "u_valid": z(P * cap, t.uint8),
-              "d_idx": z((P, cap), t.int64), "d_isw": z((P, cap), t.float64),       # row r: the draw for requester r
-              "device_apportion": bool(device_apportion),
-              "sums": z(P, t.float64), "beta": z(1, t.float64), "nstored": z(1, t.int64),
-              # device apportioning lets the host run ahead of the device, so what it writes per update goes through a
-              # small ring of pinned buffers guarded by events (copied in FRONT of the replay, not inside the graph)
-              "ring_uni": [t.zeros((P, cap), dtype=t.float64).pin_memory() for _ in range(4)],
-              "ring_ns": [t.zeros(1, dtype=t.int64).pin_memory() for _ in range(4)],
-              "ring_ev": [t.cuda.Event() for _ in range(4)], "ring_i": 0}
+        dev, P = buf.buffer_device, grp.size()
+        if not self._fused_mse or self.update_rate is None:
+            raise RuntimeError("static exchange needs MSELoss and soft target updates")
         params = list(self.qnet.parameters())
         self._flat_grad = t.zeros(sum(p.numel() for p in params), dtype=t.float32, device=dev)
         o = 0
@@ -262,57 +488,14 @@ class DQNApex(DQNPer):
         for group in self.qnet_optim.param_groups:
             if "capturable" in group:
                 group["capturable"] = True
+        st = self._static_setup(device_apportion, peer_exchange, self._flat_grad.numel())
+        capB = st["capB"]
         fields = buf.storage.fields
         grp_f = lambda fl, attr: {f.key: fl[f.name] for f in fields.values() if f.attr == attr and f.kind == "major"}
-        tree, table = buf.wt_tree.handle, buf.buffer_version_table
         prog = self._static_program(st, capB) if self.use_fused_program else None
-        st["peer"] = peer
-        if peer is not None:
-            n_grad = int(self._flat_grad.numel())
-            pb = {"recv": peer.alloc((P * cap, W), t.uint8), "recv2": peer.alloc((P * cap, 24), t.uint8),
-                  "sums": peer.alloc((P,), t.float64), "grads": peer.alloc((P, n_grad), t.float32)}
-            st["peer_buffers"] = pb
-            st["recv"], st["recv2"], st["sums"] = pb["recv"].local, pb["recv2"].local, pb["sums"].local
-            SITE_SUMS, SITE_ROWS, SITE_PRIORITIES, SITE_GRADS = 0, 1, 2, 3
 
         def body():
-            if st["device_apportion"]:
-                if peer is not None:
-                    check(lib.mb_peer_push(ptr(buf.weight_sum_tensor()), 8, P, me, 8, pb["sums"].ptrs, stream_ptr()))
-                    peer.barrier(SITE_SUMS)
-                elif P > 1:
-                    dist.all_gather_into_tensor(st["sums"], buf.weight_sum_tensor(), group=grp.pg)
-                else:
-                    st["sums"].copy_(buf.weight_sum_tensor())
-                check(lib.mb_wire_apportion(ptr(st["sums"]), P, B, me, capB, ptr(st["nstored"]), ptr(st["beta"]),
-                                            float(buf.beta_increment_per_sampling), ptr(st["counts"]), ptr(st["scale"]),
-                                            ptr(st["params"]), stream_ptr()))
-            else:
-                for name in ("counts", "params", "uni", "scale"):
-                    st[name].copy_(st[name + "_pin"], non_blocking=True)
-            if getattr(self, "batched_draw", False):     # opt-in: every requester's draw in ONE launch (one cluster each)
-                check(lib.mb_per_sample_multi(tree, ptr(st["uni"]), cap, P, ptr(st["params"]), ptr(st["d_idx"]),
-                                              ptr(st["d_isw"]), stream_ptr()))
-            else:
-                for r in range(P):                       # this shard serves every requester, member order
-                    check(lib.mb_per_sample(tree, ptr(st["uni"][r]), cap, 0, 0.0, 0.0, ptr(st["params"][r]),
-                                            ptr(st["d_idx"][r]), ptr(st["d_isw"][r]), stream_ptr()))
-            if peer is not None:
-                # gather + metadata + all-to-all as ONE kernel: every row goes straight into its requester's buffer
-                check(lib.mb_wire_push_rows(ptr(buf.storage.data), pitch, buf.storage.max_size, ptr(st["d_idx"]),
-                                            ptr(st["d_isw"]), ptr(table), P, cap, me, W, pb["recv"].ptrs, stream_ptr()))
-                peer.barrier(SITE_ROWS)
-            else:
-                # the P wire blocks are contiguous in requester order: ONE gather and ONE metadata launch for all of them
-                buf.storage.gather_into_wire(st["d_idx"].view(-1), st["send"])
-                check(lib.mb_rows_pack_meta(ptr(st["send"]), W, pitch, P * cap, ptr(st["d_idx"]), None, ptr(table),
-                                            ptr(st["d_isw"]), None, stream_ptr()))
-                if P > 1:
-                    dist.all_to_all_single(st["recv"], st["send"], group=grp.pg)
-                else:
-                    st["recv"].copy_(st["send"])
-            check(lib.mb_wire_compact(ptr(st["recv"]), P, cap, W, pitch, ptr(st["counts"]), ptr(st["merged"]), capB,
-                                      ptr(st["idx"]), ptr(st["ver"]), ptr(st["isw"]), ptr(st["scale"]), stream_ptr()))
+            self._static_sample()
             if prog is not None:
                 # fused value math (csrc/mlp.cu): forward x3 + TD + backward straight into the flat gradient buffer
                 buf.storage.unpack(st["merged"], names=prog["names"], out=prog["fields"])
@@ -342,90 +525,19 @@ class DQNApex(DQNPer):
                     q = self._criticize(state)
                 td = ops.td_dqn(q.detach(), nq, tq, self.action_get_function(action), fl["reward"], fl["terminal"],
                                 self.discount, is_weight=st["isw"], mode=self.mode, want_grad=True)
-
-            def write_back():
-                if peer is not None:
-                    check(lib.mb_wire_push_update(P, cap, me, ptr(st["counts"]), ptr(st["idx"]), ptr(st["ver"]),
-                                                  ptr(td["abs_error"]), capB, pb["recv2"].ptrs, stream_ptr()))
-                    peer.barrier(SITE_PRIORITIES)
-                else:
-                    check(lib.mb_wire_scatter_update(ptr(st["send2"]), P, cap, ptr(st["counts"]), ptr(st["idx"]), ptr(st["ver"]),
-                                                     ptr(td["abs_error"]), capB, stream_ptr()))
-                    if P > 1:
-                        dist.all_to_all_single(st["recv2"], st["send2"], group=grp.pg)
-                    else:
-                        st["recv2"].copy_(st["send2"])
-                check(lib.mb_wire_update_mask(ptr(st["recv2"]), P, cap, ptr(st["counts"]), me, ptr(table), table.numel(),
-                                              ptr(st["u_idx"]), ptr(st["u_pri"]), ptr(st["u_valid"]), stream_ptr()))
-                PrioritizedBuffer.update_priority(buf, st["u_pri"], st["u_idx"], valid=st["u_valid"])
-
-            forked = None
-            if self.overlap_priority_update:
-                # |delta| is ready: its exchange and the masked tree update only feed the NEXT draw, so they run on a side
-                # stream beside backward, the gradient all-reduce and the optimizer.  Every rank issues its collectives in
-                # the same program order (rows, priorities, gradients), which is the order they take on NCCL's stream.
-                if self._side_stream is None:
-                    self._side_stream = t.cuda.Stream(device=dev)
-                forked = (t.cuda.current_stream(dev), self._side_stream)
-                forked[1].wait_stream(forked[0])
-                with t.cuda.stream(forked[1]):
-                    write_back()
+            forked = self._static_write_back_maybe_forked(td["abs_error"])
             if prog is None:
                 self._flat_grad.zero_()
                 q.backward(td["grad_q"])
-            if peer is not None:
-                # gradient all-reduce: my flat buffer into slot `me` of every member, barrier, then every member adds
-                # the P slots in member order -- bit-identical averaged gradients everywhere
-                n_grad = int(self._flat_grad.numel())
-                check(lib.mb_peer_push(ptr(self._flat_grad), 4 * n_grad, P, me, 4 * n_grad, pb["grads"].ptrs, stream_ptr()))
-                peer.barrier(SITE_GRADS)
-                check(lib.mb_peer_sum(ptr(pb["grads"].local), P, n_grad, float(P), ptr(self._flat_grad), stream_ptr()))
-            elif P > 1:
-                red = self.learner_group if self.learner_group is not None else grp
-                dist.all_reduce(self._flat_grad, group=red.pg)
-                self._flat_grad.div_(red.size())
+            self._static_all_reduce(self._flat_grad, self.SITE_GRADS)
             self._optimizer_and_target(True, True)        # clip (if finite), optimizer step, soft target update
             if forked is None:
-                write_back()
+                self._static_write_back(td["abs_error"])
             else:
                 forked[0].wait_stream(forked[1])            # join before the next draw reads the tree
             return td["loss_elem"].mean()
 
-        # snapshot everything the warm-up replays will touch
-        saved = [[x.detach().clone() for x in list(m.parameters()) + list(m.buffers())] for m in (self.qnet, self.qnet_target)]
-        fresh = len(self.qnet_optim.state) == 0
-        saved_optim = _snapshot_optimizer(self.qnet_optim)
-        tree_snap, beta0 = buf.wt_tree.snapshot(), buf.curr_beta
-        np_state = np.random.get_state()
-        self.qnet.train()
-        self._static = st
-        st["beta"].fill_(float(beta0))
-        self._static_prepare()                           # collective: real counts / uniforms for the warm-up
-        cur, side = t.cuda.current_stream(dev), t.cuda.Stream(device=dev)
-        side.wait_stream(cur)
-        with t.cuda.stream(side):
-            for _ in range(warmup):
-                body()
-        cur.wait_stream(side)
-        t.cuda.synchronize(dev)
-        graph = t.cuda.CUDAGraph()
-        launched = lib.mb_launch_count()
-        with t.cuda.graph(graph, capture_error_mode="thread_local"):
-            st["loss"] = body()
-        st["graph"] = graph
-        self.graph_launches = lib.mb_launch_count() - launched     # libmachin_b200 kernels per replayed update
-        with t.no_grad():
-            for m, sv in zip((self.qnet, self.qnet_target), saved):
-                for x, v in zip(list(m.parameters()) + list(m.buffers()), sv):
-                    x.copy_(v)
-        _restore_optimizer(self.qnet_optim, saved_optim, fresh)
-        buf.wt_tree.restore(tree_snap)
-        buf.curr_beta = beta0
-        st["beta"].fill_(float(beta0))
-        np.random.set_state(np_state)
-        t.cuda.synchronize(dev)
-        if P > 1:
-            grp.barrier()
+        _, st["loss"] = self._static_capture(body, warmup, (self.qnet, self.qnet_target), (self.qnet_optim,))
 
     def _static_program(self, st, rows):
         """Opt-in (``use_fused_program``): the fused value-math program of DQNPer over the merged, padded batch of the
@@ -468,48 +580,6 @@ class DQNApex(DQNPer):
         import weakref
         weakref.finalize(self, lib.mb_mlp_program_destroy, handle)
         return prog
-
-    def _static_prepare(self):
-        """Host part of a fixed-shape update: read the shard sums (one sync), apportion, draw this shard's
-        uniforms from np.random in the reference's order, refresh the pinned parameter blocks."""
-        from ...parallel.exchange import shard_sample_sizes
-        st, buf, grp = self._static, self.replay_buffer, self.apex_group
-        P, me, cap = st["P"], grp.index, st["cap"]
-        if st["device_apportion"]:
-            # nothing here depends on the device: fixed-size uniform blocks, the stored-row count, and a host mirror
-            # of beta (it advances once per requester served, :425-427; the device holds the authoritative value)
-            i = st["ring_i"] = (st["ring_i"] + 1) % len(st["ring_ev"])
-            st["ring_ev"][i].synchronize()                  # the copy that last used this slot has finished
-            st["ring_uni"][i].numpy()[:] = np.random.uniform(size=(P, cap))
-            st["ring_ns"][i].numpy()[0] = len(buf.storage)
-            st["uni"].copy_(st["ring_uni"][i], non_blocking=True)
-            st["nstored"].copy_(st["ring_ns"][i], non_blocking=True)
-            st["ring_ev"][i].record()
-            for _ in range(P):
-                buf.curr_beta = np.float64(min(1.0, buf.curr_beta + buf.beta_increment_per_sampling))
-            return self.batch_size
-        sums = grp.all_gather_f64(buf.weight_sum_tensor()).view(-1).tolist()
-        ssize, total = shard_sample_sizes(sums, self.batch_size)
-        n, n_mine = int(sum(ssize)), int(ssize[me])
-        views = st.get("np")
-        if views is None:                                 # NumPy views of the pinned blocks, taken once
-            rec = np.dtype([("beta", "<f8"), ("total", "<f8"), ("n_stored", "<i8"), ("step", "<i8"), ("n_draw", "<i8")])
-            views = st["np"] = {"counts": st["counts_pin"].numpy(), "scale": st["scale_pin"].numpy(),
-                                "params": st["params_pin"].numpy().view(rec).reshape(P), "uni": st["uni_pin"].numpy()}
-        views["counts"][:] = ssize
-        views["scale"][0] = st["capB"] / n
-        beta, betas = buf.curr_beta, []
-        for _ in range(P):                                # one draw per requester; beta advances per draw (:425-427)
-            betas.append(beta)
-            if n_mine > 0:
-                beta = np.float64(min(1.0, beta + buf.beta_increment_per_sampling))
-        prm = views["params"]
-        prm["beta"], prm["total"], prm["n_stored"], prm["step"], prm["n_draw"] = betas, total, len(buf.storage), 0, n_mine
-        if n_mine > 0:
-            # P consecutive draws of n_mine uniforms are one draw of P * n_mine from the same MT19937 stream (:411)
-            views["uni"][:, :n_mine] = np.random.uniform(size=P * n_mine).reshape(P, n_mine)
-        buf.curr_beta = beta
-        return n
 
     def release_graphs(self):
         """Collective-safe teardown helper: drop every captured graph of this learner (the fixed-shape one holds NCCL
@@ -570,7 +640,7 @@ class DQNApex(DQNPer):
 from .ddpg_per import DDPGPer  # noqa: E402
 
 
-class DDPGApex(DDPGPer):
+class DDPGApex(_FixedShapeExchange, DDPGPer):
     """apex.py:256-532: DDPGPer over the sharded buffer; pushes the ACTOR after every update."""
     _config_frame, _config_kind = "DDPGApex", "apex"
 
@@ -616,6 +686,90 @@ class DDPGApex(DDPGPer):
         self.replay_buffer.update_priority(None, None)
         if self.actor_model_server is not None:
             self.actor_model_server.pull(self.actor)
+
+    # ---- the sharded DDPG update as ONE CUDA graph (BASELINE C4): the fixed-shape exchange of _FixedShapeExchange around
+    # ddpg_per.py:92-185 -- every member a learner with its own replay shard, critic and actor gradients averaged
+    # through two flat buffers.  The merged batch has B + P rows of which sum(counts) are real: the critic loss is
+    # weighted by the (scaled) IS weights, which are 0 on padding rows; the policy loss is a mean over the real rows.
+    def enable_cuda_graph(self, warmup: int = 3, device_apportion: bool = True, peer_exchange: bool = True):
+        buf = self.replay_buffer
+        dev = buf.buffer_device
+        if self.update_rate is None:
+            raise RuntimeError("DDPGApex.enable_cuda_graph needs soft target updates (update_rate)")
+        flats = []
+        for net, optim in ((self.critic, self.critic_optim), (self.actor, self.actor_optim)):
+            params = list(net.parameters())
+            flat = t.zeros(sum(p.numel() for p in params), dtype=t.float32, device=dev)
+            o = 0
+            for p in params:
+                p.grad = flat[o:o + p.numel()].view_as(p)
+                o += p.numel()
+            for group in optim.param_groups:
+                if "capturable" in group:
+                    group["capturable"] = True
+            flats.append(flat)
+        self._flat_critic, self._flat_actor = flats
+        st = self._static_setup(device_apportion, peer_exchange, max(f.numel() for f in flats))
+        capB = st["capB"]
+        fields = buf.storage.fields
+        grp_f = lambda fl, attr: {f.key: fl[f.name] for f in fields.values() if f.attr == attr and f.kind == "major"}
+
+        def body():
+            self._static_sample()
+            fl = buf.storage.unpack(st["merged"])
+            state, action, next_state = grp_f(fl, "state"), grp_f(fl, "action"), grp_f(fl, "next_state")
+            reward, terminal, isw = fl["reward"], fl["terminal"], st["isw"]
+            real = (st["ver"] >= 0).to(t.float32)                 # compaction marks padding rows with version -1
+            others = {}
+            with t.no_grad():
+                next_action = self.action_transform_function(self._act(next_state, True), next_state, others)
+                next_value = self._criticize(next_state, next_action, True).view(capB, -1)
+                y_i = ops.td_target(next_value, reward, terminal, self.discount)["y"]
+            cur_value = self._criticize(state, action)
+            value_loss = self.criterion(cur_value, y_i.type_as(cur_value))
+            value_loss = (value_loss * isw.view(capB, 1).type_as(value_loss)).mean()
+            self._flat_critic.zero_()
+            self._backward(value_loss)
+            self._static_all_reduce(self._flat_critic, self.SITE_GRADS)
+            self._clip(self.critic)
+            self.critic_optim.step()
+            cur_action = self.action_transform_function(self._act(state), state, others)
+            act_value = self._criticize(state, cur_action)
+            act_policy_loss = -(act_value.view(-1) * real).sum() / real.sum()
+            abs_error = ops.td_target(next_value, reward, terminal, self.discount, value=act_value.detach())["abs_error"]
+            forked = self._static_write_back_maybe_forked(abs_error)
+            self._flat_actor.zero_()
+            self._backward(act_policy_loss)
+            self._static_all_reduce(self._flat_actor, self.SITE_GRADS_2)
+            self._clip(self.actor)
+            self.actor_optim.step()
+            soft_update(self.actor_target, self.actor, self.update_rate)
+            soft_update(self.critic_target, self.critic, self.update_rate)
+            if forked is None:
+                self._static_write_back(abs_error)
+            else:
+                forked[0].wait_stream(forked[1])            # join before the next draw reads the tree
+            return -act_policy_loss, value_loss
+
+        nets = (self.actor, self.actor_target, self.critic, self.critic_target)
+        _, st["losses"] = self._static_capture(body, warmup, nets, (self.actor_optim, self.critic_optim))
+        self.actor.eval()
+        self.critic.eval()
+
+    def release_graphs(self):
+        st = getattr(self, "_static", None)
+        graph = st.pop("graph", None) if st else None
+        if graph is not None:
+            graph.reset()
+        super().release_graphs()
+
+    def update_device(self, update_value=True, update_policy=True, update_target=True, uniform=None):
+        st = getattr(self, "_static", None)
+        if st is not None and "graph" in st and update_value and update_policy and update_target:
+            self._static_prepare()
+            st["graph"].replay()
+            return st["losses"]
+        return super().update_device(update_value, update_policy, update_target, uniform)
 
     def update(self, update_value=True, update_policy=True, update_target=True, concatenate_samples=True, **__):
         result = super().update(update_value, update_policy, update_target, concatenate_samples)

@@ -110,6 +110,60 @@ def main():
     assert all(t.equal(wes[0], x) for x in wes)           # bit-identical weights on every member (ordered peer sum)
     if rank == 0:
         print(f"peer exchange {'ok' if peer_on else 'UNAVAILABLE (NCCL fallback ran)'} (world {world})", flush=True)
+    # ---- the sharded DDPG update (BASELINE C4) as one graph over the same exchange: against the dynamic, eager exchange
+    #      draw for draw (host apportioning), NCCL transport and peer transport
+    from machin_b200.frame.algorithms import DDPGApex
+    AD = 3
+
+    class Actor(t.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc1, self.fc2 = t.nn.Linear(S, 16), t.nn.Linear(16, AD)
+
+        def forward(self, state):
+            return t.tanh(self.fc2(t.relu(self.fc1(state))))
+
+    class Critic(t.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc1, self.fc2 = t.nn.Linear(S + AD, 16), t.nn.Linear(16, 1)
+
+        def forward(self, state, action):
+            return self.fc2(t.relu(self.fc1(t.cat([state, action], dim=1))))
+
+    def make_ddpg():
+        t.manual_seed(7)
+        nets = [Actor().cuda(), Actor().cuda(), Critic().cuda(), Critic().cuda()]
+        learner = DDPGApex(*nets, t.optim.SGD, t.nn.MSELoss(reduction="none"), group, (), batch_size=B, actor_learning_rate=0.01,
+                           critic_learning_rate=0.02, discount=0.9, update_rate=0.1, replay_size=4096, learner_group=group)
+        rng = np.random.RandomState(11 + rank)
+        learner.replay_buffer.store_episode_tensors(
+            {"state": {"state": t.from_numpy(rng.randn(N, S).astype(np.float32))},
+             "action": {"action": t.from_numpy(rng.rand(N, AD).astype(np.float32) * 2 - 1)},
+             "next_state": {"state": t.from_numpy(rng.randn(N, S).astype(np.float32))}},
+            {"reward": t.from_numpy(rng.randn(N, 1).astype(np.float32)), "terminal": t.from_numpy(rng.rand(N, 1) < 0.1)},
+            priorities=rng.exponential(size=N))
+        return learner
+
+    da, dn, dp = make_ddpg(), make_ddpg(), make_ddpg()
+    dn.enable_cuda_graph(device_apportion=False, peer_exchange=False)
+    dp.enable_cuda_graph(device_apportion=False, peer_exchange=True)
+    for step in range(5):
+        outs = []
+        for learner in (da, dn, dp):
+            np.random.seed(900 * rank + step)
+            outs.append([x.item() for x in learner.update_device()])
+        for other in outs[1:]:
+            for x, y in zip(outs[0], other):
+                assert abs(x - y) <= 1e-5 * max(1.0, abs(x)), (step, outs)
+        for learner in (dn, dp):
+            np.testing.assert_allclose(learner.replay_buffer.wt_tree.weights, da.replay_buffer.wt_tree.weights, rtol=1e-5, atol=1e-9)
+            np.testing.assert_allclose(flat(learner.actor), flat(da.actor), rtol=1e-4, atol=1e-6)
+            np.testing.assert_allclose(flat(learner.critic), flat(da.critic), rtol=1e-4, atol=1e-6)
+    if dp._static["peer"] is not None:
+        dp._static["peer"].check()
+    if rank == 0:
+        print(f"sharded DDPG fixed-shape update ok (world {world})", flush=True)
     # every member holds the same weights after averaged gradients
     w = t.from_numpy(flat(b.qnet)).cuda()
     ws = [t.empty_like(w) for _ in range(world)]

@@ -44,3 +44,47 @@ def test_ddpg_per_captured_update_vs_reference(release_after):
         for name, net in (("actor", ddpg.actor), ("critic", ddpg.critic), ("actor_t", ddpg.actor_target),
                           ("critic_t", ddpg.critic_target)):
             np.testing.assert_allclose(_flat(net), g[f"ddpg_{name}{step + 1}"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("device_apportion", [False, True])
+def test_ddpg_apex_fixed_shape_update_matches_dynamic_single_member(device_apportion):
+    """DDPGApex.enable_cuda_graph (the sharded DDPG update as ONE graph over the fixed-shape exchange) on a group of
+    one against the dynamic, eager exchange: same draws, same losses, same networks, same tree.  (The merged batch of
+    the fixed-shape update carries one padding row per member: the critic loss weighs it 0, the policy loss masks it.)"""
+    from machin_b200.frame.algorithms import DDPGApex
+    from machin_b200.parallel import LocalGroup
+    S, A, N, B = 7, 3, 2000, 48
+
+    def make(static):
+        t.manual_seed(1)
+        nets = [Actor(S, A).cuda(), Actor(S, A).cuda(), Critic(S, A).cuda(), Critic(S, A).cuda()]
+        learner = DDPGApex(*nets, t.optim.SGD, t.nn.MSELoss(reduction="none"), LocalGroup(device="cuda:0"), (), batch_size=B,
+                           actor_learning_rate=0.01, critic_learning_rate=0.02, discount=0.9, update_rate=0.1, replay_size=4096)
+        rng = np.random.RandomState(5)
+        learner.replay_buffer.store_episode_tensors(
+            {"state": {"state": t.from_numpy(rng.randn(N, S).astype(np.float32))},
+             "action": {"action": t.from_numpy(rng.rand(N, A).astype(np.float32) * 2 - 1)},
+             "next_state": {"state": t.from_numpy(rng.randn(N, S).astype(np.float32))}},
+            {"reward": t.from_numpy(rng.randn(N, 1).astype(np.float32)), "terminal": t.from_numpy(rng.rand(N, 1) < 0.1)},
+            priorities=rng.exponential(size=N))
+        if static:
+            learner.enable_cuda_graph(device_apportion=device_apportion, peer_exchange=False)
+        return learner
+
+    a, b = make(False), make(True)
+    assert np.array_equal(a.replay_buffer.wt_tree.weights, b.replay_buffer.wt_tree.weights)
+    for net_a, net_b in zip((a.actor, a.critic), (b.actor, b.critic)):
+        assert np.array_equal(_flat(net_a), _flat(net_b))
+    for step in range(6):
+        np.random.seed(40 + step)
+        pa, va = (x.item() for x in a.update_device())
+        np.random.seed(40 + step)
+        pb, vb = (x.item() for x in b.update_device())
+        assert abs(pa - pb) <= 1e-5 * max(1.0, abs(pa)) and abs(va - vb) <= 1e-5 * max(1.0, abs(va)), (step, pa, pb, va, vb)
+        np.testing.assert_allclose(b.replay_buffer.wt_tree.weights, a.replay_buffer.wt_tree.weights, rtol=1e-5, atol=1e-9)
+        for net_a, net_b in ((a.actor, b.actor), (a.critic, b.critic), (a.actor_target, b.actor_target),
+                             (a.critic_target, b.critic_target)):
+            np.testing.assert_allclose(_flat(net_b), _flat(net_a), rtol=1e-4, atol=1e-6)
+    b.replay_buffer.wt_tree.check()
+    t.cuda.synchronize()
+    b.release_graphs()

@@ -20,6 +20,9 @@ def test_static_exchange_matches_dynamic_over_nccl(world):
            os.path.join(ROOT, "tests", "dist_gpu_static_worker.py")]
     out = run_group(cmd, timeout=300)
     assert out.returncode == 0 and "static ok" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    # the peer-memory exchange must really have run (a box whose GPUs cannot be peer-mapped reports UNAVAILABLE)
+    assert f"peer exchange ok (world {world})" in out.stdout, out.stdout[-3000:]
+    assert f"sharded DDPG fixed-shape update ok (world {world})" in out.stdout, out.stdout[-3000:]
 
 
 def test_device_apportion_matches_host_apportion_single_member():

@@ -360,6 +360,21 @@ def test_ddpg_apex_update_dry_run(monkeypatch):
     called = {name for name, _ in rec.calls}
     assert {"mb_per_sample", "mb_rows_pack_meta", "mb_rows_unpack_meta", "mb_td_target", "mb_tree_update_priority",
             "mb_adam_step_multi", "mb_soft_update_multi"} <= called, sorted(called)
+    # the same learner with the sharded update as one graph over the fixed-shape exchange (BASELINE C4's path)
+    monkeypatch.setattr(t.cuda, "CUDAGraph", _Graph)
+    monkeypatch.setattr(t.cuda, "graph", lambda g, **kw: contextlib.nullcontext())
+    for overlap in (False, True):
+        n0 = len(rec.calls)
+        learner.overlap_priority_update = overlap
+        learner.batched_draw = overlap
+        learner.enable_cuda_graph(device_apportion=overlap, peer_exchange=True)     # (no peer mapping here: NCCL path, P = 1)
+        for _ in range(2):
+            out = learner.update()
+            assert len(out) == 2
+        new = {name for name, _ in rec.calls[n0:]}
+        assert {"mb_wire_compact", "mb_wire_scatter_update", "mb_wire_update_mask", "mb_td_target", "mb_tree_update_priority",
+                "mb_adam_step_multi"} <= new, sorted(new)
+        learner.release_graphs()
 
 
 @pytest.mark.parametrize("graph", [False, True])
