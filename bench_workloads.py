@@ -389,6 +389,18 @@ def run_c4(a, ClockSampler):
         def forward(self, state, action):
             return self.fc3(t.relu(self.fc2(t.relu(self.fc1(t.cat([state, action], dim=1))))))
 
+    if a.net == "fused":                                # the same layers as one csrc/mlp.cu kernel per layer and direction
+        from machin_b200.model import FusedMLP
+
+        class Actor(t.nn.Module):                       # noqa: F811
+            def __init__(self):
+                super().__init__()
+                self.net = FusedMLP([S, H, H, A])
+
+            def forward(self, state):
+                return t.tanh(self.net(state))
+
+        Critic = lambda: FusedMLP([S + A, H, H, 1])     # noqa: E731  forward(state, action) concatenates
     t.manual_seed(0)                                    # identical initial weights on every learner
     nets = [Actor().to(dev), Actor().to(dev), Critic().to(dev), Critic().to(dev)]
     graph = not a.no_graph
@@ -477,7 +489,7 @@ def run_c4(a, ClockSampler):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 tree/IS-weights + f32 TD", "data": "synthetic", "learner_updates_per_sec": K / (ms_total * 1e-3),
             "config": {"workload": _c4_name(rows, world), "batch": B, "rows_per_shard": rows, "row_pitch_bytes": int(buf.storage.pitch),
-                       "shard_bytes": int(buf.storage.pitch) * rows, "optimizer": "Adam (FusedAdam)",
+                       "shard_bytes": int(buf.storage.pitch) * rows, "optimizer": "Adam (FusedAdam)", "net": a.net,
                        "parallelism": f"{world} learner(s), one replay shard each",
                        "launch": "one CUDA graph per update" if graph else "eager kernels around eager NCCL exchanges",
                        "transport": None if world == 1 else (
