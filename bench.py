@@ -52,6 +52,7 @@ def parse():
     p.add_argument("--cpu-storage-rows", type=int, default=50_000)
     p.add_argument("--cpu-steps", type=int, default=1500)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-port", action="store_true", help="CPU arm: the oracle's restatement even if the vendored reference is there")
     p.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per update")
     p.add_argument("--net", default="fused", choices=["torch", "fused", "fused-program", "fused-rows"],
                    help="Q-net implementation: FusedMLP (default since round 2: one csrc/mlp.cu kernel per layer and direction, "
@@ -108,10 +109,8 @@ def cpu_learner_rate(a, steps, warmup, budget_s=25.0):
     the GPU box): the thread count is calibrated over {1,2,4,8,16,32,all} and the best one is timed.
     The run stops after ``steps`` updates or ``budget_s`` seconds, whichever comes first."""
     import torch as t
-    from oracle.learner import CpuDqnPerLearner
-
     np.random.seed(0)
-    learner = CpuDqnPerLearner(a.replay_rows, a.cpu_storage_rows, STATE_DIM, N_ACTIONS, a.batch, hidden=HIDDEN)
+    learner, kind = make_cpu_learner(a)
     ncpu = os.cpu_count() or 1
     best, best_dt = 1, float("inf")
     for th in [c for c in (1, 2, 4, 8, 16, 32) if c <= ncpu] + ([ncpu] if ncpu <= 64 else []):
@@ -132,17 +131,39 @@ def cpu_learner_rate(a, steps, warmup, budget_s=25.0):
         learner.step()
         done += 1
     dt = time.perf_counter() - t0
-    return a.batch * done / dt, dt / done * 1e3, best, done
+    return a.batch * done / dt, dt / done * 1e3, best, done, kind
+
+
+def make_cpu_learner(a):
+    """The CPU arm: the UNMODIFIED reference (machin's own DQNPer over its own PrioritizedBuffer, vendored by
+    oracle/vendor_ref.py into oracle/_ref, or mounted at /root/reference) when it is there -- kind "reference" -- else the
+    oracle's restatement of the same update (oracle/learner.py) -- kind "port"."""
+    from oracle import ref_shim
+    if not a.cpu_port and ref_shim.available():
+        try:
+            from oracle.ref_learner import ReferenceDqnPerLearner
+            return ReferenceDqnPerLearner(a.replay_rows, a.cpu_storage_rows, STATE_DIM, N_ACTIONS, a.batch, hidden=HIDDEN), "reference"
+        except Exception as exc:   # noqa: BLE001 -- e.g. an import the shim does not cover on this box: say so, use the port
+            sys.stderr.write(f"bench.py: the vendored reference could not be set up ({exc!r}); timing the oracle port instead\n")
+    from oracle.learner import CpuDqnPerLearner
+    return CpuDqnPerLearner(a.replay_rows, a.cpu_storage_rows, STATE_DIM, N_ACTIONS, a.batch, hidden=HIDDEN), "port"
+
+
+def cpu_sample_text(kind, done, threads, a):
+    what = ("machin's own DQNPer.update() over its own PrioritizedBuffer (unmodified reference, oracle/_ref): NumPy float64 "
+            "sum tree at full size" if kind == "reference" else
+            "oracle/learner.py (restatement of DQNPer.update(): NumPy float64 tree at full size")
+    return (f"{done} full learner updates of {what} ({a.replay_rows} leaves), Python-object storage capped at "
+            f"{a.cpu_storage_rows} transitions, CPU torch MLP; best of thread counts 1..32 -> {threads} threads, "
+            f"{os.cpu_count()} cores present")
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, ms, threads, done = cpu_learner_rate(a, a.steps, max(a.warmup, 3), budget_s=120.0)
-    sample = (f"{done} updates of the full algorithm, best of thread counts 1..32 -> {threads} threads "
-              f"({os.cpu_count()} cores present); float64 sum tree at full size ({a.replay_rows} leaves), "
-              f"Python-object storage capped at {a.cpu_storage_rows} rows (slots folded with index % rows)")
+    value, ms, threads, done, kind = cpu_learner_rate(a, a.steps, max(a.warmup, 3), budget_s=120.0)
+    sample = cpu_sample_text(kind, done, threads, a)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": done,
         "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -150,7 +171,7 @@ def run_reference(a):
         "learner_updates_per_sec": value / a.batch,
         "config": {"workload": workload_name(a), "batch": a.batch, "replay_rows": a.replay_rows,
                    "optimizer": "Adam", "device": "host CPU"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -537,11 +558,9 @@ def run_b200(a):
                             "(DESIGN.md section 5 reports the saturated-throughput figures per kernel)"}
     cpu = None
     if not a.no_cpu_baseline and world == 1:
-        v, ms, threads, done = cpu_learner_rate(a, a.cpu_steps, 5)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": ms,
-               "sample": (f"{done} full learner updates of oracle/learner.py (NumPy float64 tree at full size, "
-                          f"Python-object storage capped at {a.cpu_storage_rows} rows, CPU torch MLP); best of thread "
-                          f"counts 1..32 -> {threads} threads, {os.cpu_count()} cores present")}
+        v, ms, threads, done, kind = cpu_learner_rate(a, a.cpu_steps, 5)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "ms_per_step": ms,
+               "sample": cpu_sample_text(kind, done, threads, a)}
     # host <-> device bytes per update and rank, counted from the tensors that are copied: the uniforms (and, for the
     # fixed-shape exchange, the apportioned counts, the per-requester parameter blocks and the loss scale) go in; the
     # loss comes out -- and at N > 1 the all-gathered shard sums the host apportions with (prioritized_buffer_d.py:221-234)

@@ -13,7 +13,10 @@ import os
 import sys
 from unittest.mock import MagicMock
 
-REFERENCE_ROOT = os.environ.get("MACHIN_REFERENCE", "/root/reference")
+# the mounted reference in the build container; on the GPU box the copy oracle/vendor_ref.py made (oracle/_ref)
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = os.environ.get("MACHIN_REFERENCE") or (
+    "/root/reference" if os.path.isdir("/root/reference/machin") else _VENDORED)
 
 _OPTIONAL = [
     "gym", "gym.spaces", "gym.wrappers", "gym.wrappers.time_limit", "GPUtil",
