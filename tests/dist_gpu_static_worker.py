@@ -32,7 +32,7 @@ def main():
     from machin_b200.frame.algorithms import DQNApex
     from machin_b200.parallel import ShardGroup
     S, A, B = 12, 5, 64
-    N = 3000 + 400 * rank
+    N = min(3000 + 250 * rank, 4000)                      # (a shard never holds more than its ring of 4096)
     group = ShardGroup("group")
 
     def make():

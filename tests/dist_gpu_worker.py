@@ -49,7 +49,7 @@ def main():
     cap, S = 4096, 84
     buf = DistributedPrioritizedBuffer("buffer2", group, cap)
     rng = np.random.RandomState(rank)
-    n_rows = 3000 + 500 * rank
+    n_rows = min(3000 + 250 * rank, 4000)                 # (a shard never holds more than its ring of 4096)
     state = rng.randn(n_rows, S).astype(np.float32)
     pri = rng.exponential(size=n_rows)
     buf.store_episode_tensors({"state": {"state": t.from_numpy(state)}, "action": {"action": t.zeros(n_rows, 1, dtype=t.int64) + rank},
