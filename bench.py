@@ -311,6 +311,9 @@ KERNELS = {  # C entry point -> (label, algorithmic bytes per launch as f(batch,
 }
 
 
+PER_STEP = {}    # launches per update of a timed kernel where it is not 1 (filled by time_kernels)
+
+
 def time_kernels(learner, table, reps=20, per_graph=16, capture_mode=None):
     """Average device time per launch of each libmachin_b200 kernel of the step.
 
@@ -358,6 +361,37 @@ def time_kernels(learner, table, reps=20, per_graph=16, capture_mode=None):
 
     timed = [("mb_per_sample", k_sample), ("mb_rows_gather", k_gather), ("mb_td_dqn", k_td),
              ("mb_tree_update_priority", k_update), ("mb_soft_update", k_soft)]
+    from machin_b200.model import FusedMLP
+    if isinstance(learner.qnet, FusedMLP) and not getattr(learner, "_program", None):
+        # FusedMLP Q-net: every layer of every pass is one csrc/mlp.cu GEMM launch of this library.  Per update: three
+        # forwards (online s, online s', target s'), the backward of the online one (weight gradient per layer, input
+        # gradient for all but the first layer).
+        sizes = learner.qnet.sizes
+        ws = learner.qnet._workspace(dev)
+        for l in range(len(sizes) - 1):
+            K, N = sizes[l], sizes[l + 1]
+            x, w, b = t.randn(B, K, device=dev), t.randn(N, K, device=dev), t.randn(N, device=dev)
+            y, dy, dx = t.empty(B, N, device=dev), t.randn(B, N, device=dev), t.empty(B, K, device=dev)
+            dw, db = t.empty(N, K, device=dev), t.empty(N, device=dev)
+            relu = int(l < len(sizes) - 2)
+
+            def k_fwd(i, x=x, w=w, b=b, y=y, N=N, K=K, relu=relu):
+                _lib.check(lib.mb_mlp_linear_forward(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), B, N, K, relu, *ws.args(), sp()))
+
+            def k_dw(i, x=x, dy=dy, dw=dw, db=db, N=N, K=K):
+                _lib.check(lib.mb_mlp_linear_backward_weight(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(dw), _lib.ptr(db), B, N, K, *ws.args(), sp()))
+
+            def k_dx(i, x=x, w=w, dy=dy, dx=dx, N=N, K=K):
+                _lib.check(lib.mb_mlp_linear_backward_input(_lib.ptr(dy), _lib.ptr(w), _lib.ptr(x), _lib.ptr(dx), B, N, K, *ws.args(), sp()))
+
+            KERNELS[f"gemm_fwd_{l}"] = (f"gemm_small forward {B}x{N}x{K} (+bias{', ReLU' if relu else ''})", lambda B_, P_, D_, N=N, K=K: 4 * (B_ * K + N * K + N + B_ * N))
+            KERNELS[f"gemm_dw_{l}"] = (f"gemm weight+bias gradient {N}x{K + 1}x{B}", lambda B_, P_, D_, N=N, K=K: 4 * (B_ * N + B_ * K + N * K + N))
+            timed += [(f"gemm_fwd_{l}", k_fwd), (f"gemm_dw_{l}", k_dw)]
+            PER_STEP[f"gemm_fwd_{l}"], PER_STEP[f"gemm_dw_{l}"] = 3.0, 1.0
+            if l > 0:
+                KERNELS[f"gemm_dx_{l}"] = (f"gemm_small input gradient {B}x{K}x{N} (ReLU mask)", lambda B_, P_, D_, N=N, K=K: 4 * (B_ * N + N * K + 2 * B_ * K))
+                timed.append((f"gemm_dx_{l}", k_dx))
+                PER_STEP[f"gemm_dx_{l}"] = 1.0
     prog = getattr(learner, "_program", None)
     if prog:                                   # the fused program replaces the stand-alone TD kernel in the step
         def k_part(part):
@@ -386,7 +420,7 @@ def time_kernels(learner, table, reps=20, per_graph=16, capture_mode=None):
         e1.record()
         t.cuda.synchronize(dev)
         out[name] = {"avg_us": e0.elapsed_time(e1) * 1e3 / (reps * per_graph), "launches_timed": reps * per_graph,
-                     "per_step": 1.0}
+                     "per_step": PER_STEP.get(name, 1.0)}
     return out
 
 
@@ -551,9 +585,17 @@ def run_b200(a):
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(dom)
+        # `dom` = the kernel with the largest share of the update's device time (launches per update x time per launch);
+        # the single slowest launch is named beside it
+        slow = max(kern, key=lambda k: kern[k]["avg_us"])
         roofline = {"bound": "hbm", "kernel": label, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_us": kern[dom]["avg_us"],
+                    "launches_per_step": kern[dom]["per_step"],
+                    "slowest_single_launch": {"kernel": KERNELS[slow][0], "avg_launch_us": kern[slow]["avg_us"],
+                                              "algorithmic_bytes_per_launch": KERNELS[slow][1](B, n_params, depth),
+                                              "frac": KERNELS[slow][1](B, n_params, depth) / (kern[slow]["avg_us"] * 1e-6) / 1e9 / peak,
+                                              "traffic": (json.load(open(tp)).get(slow) if os.path.exists(tp) else None)},
                     "note": "B=512 touches <1 MB per launch: the step is launch/latency-bound, not bandwidth-bound "
                             "(DESIGN.md section 5 reports the saturated-throughput figures per kernel)"}
     cpu = None
