@@ -10,9 +10,8 @@ import torch as t
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 
-a = argparse.Namespace(gpus=1, steps=3, warmup=3, impl="b200", replay_rows=int(os.environ.get("ROWS", "2000000")),
-                       batch=512, cpu_storage_rows=1000, cpu_steps=1, no_cpu_baseline=True, no_graph=False,
-                       net="torch", adam="fused", fuse_forwards=False)
+sys.argv = [sys.argv[0], "--replay-rows", os.environ.get("ROWS", "2000000"), "--no-cpu-baseline", *sys.argv[1:]]
+a = bench.parse()                      # bench.py's defaults (fused net, stream-level options); extra flags pass through
 dev = t.device("cuda", 0)
 learner = bench.build_learner(a, dev, seed=0)
 learner.enable_cuda_graph()
