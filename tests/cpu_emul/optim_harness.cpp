@@ -2,7 +2,6 @@
 // launch) for the host through cuda_shim.h.
 #include "cuda_shim.h"
 
-inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline unsigned atomicAdd(unsigned *a, unsigned v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
 

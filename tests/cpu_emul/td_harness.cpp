@@ -17,7 +17,6 @@ extern "C" int emul_td_dqn(const float *q, const float *qn, const float *qtn, in
 
 // ---- categorical TD target of RAINBOW (csrc/dist_device.cuh), launched with the geometry and the scalar
 // conversions of mb_td_rainbow (csrc/td.cu)
-inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 #include "dist_device.cuh"
 
 extern "C" int emul_td_rainbow(const float *q, const float *qn, const float *qtn, int64_t batch, int A, int N,

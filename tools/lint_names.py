@@ -114,11 +114,12 @@ def check(tree, filename):
 
 
 def main():
-    paths = sys.argv[1:] or ["machin_b200", "oracle", "tests", "tools", "bench.py", "__graft_entry__.py"]
+    paths = sys.argv[1:] or ["machin_b200", "oracle", "tests", "tools", "bench.py", "bench_workloads.py", "__graft_entry__.py"]
     files = []
     for p in paths:
         if os.path.isdir(p):
-            for root, _, names in os.walk(p):
+            for root, dirs, names in os.walk(p):
+                dirs[:] = [d for d in dirs if d != "_ref"]       # oracle/_ref: the vendored, unmodified reference (not ours)
                 files += [os.path.join(root, n) for n in names if n.endswith(".py")]
         else:
             files.append(p)
