@@ -384,12 +384,12 @@ def time_kernels(learner, table, reps=20, per_graph=16, capture_mode=None):
             def k_dx(i, x=x, w=w, dy=dy, dx=dx, N=N, K=K):
                 _lib.check(lib.mb_mlp_linear_backward_input(_lib.ptr(dy), _lib.ptr(w), _lib.ptr(x), _lib.ptr(dx), B, N, K, *ws.args(), sp()))
 
-            KERNELS[f"gemm_fwd_{l}"] = (f"gemm_small forward {B}x{N}x{K} (+bias{', ReLU' if relu else ''})", lambda B_, P_, D_, N=N, K=K: 4 * (B_ * K + N * K + N + B_ * N))
+            KERNELS[f"gemm_fwd_{l}"] = (f"gemm forward {B}x{N}x{K} (+bias{', ReLU' if relu else ''})", lambda B_, P_, D_, N=N, K=K: 4 * (B_ * K + N * K + N + B_ * N))
             KERNELS[f"gemm_dw_{l}"] = (f"gemm weight+bias gradient {N}x{K + 1}x{B}", lambda B_, P_, D_, N=N, K=K: 4 * (B_ * N + B_ * K + N * K + N))
             timed += [(f"gemm_fwd_{l}", k_fwd), (f"gemm_dw_{l}", k_dw)]
             PER_STEP[f"gemm_fwd_{l}"], PER_STEP[f"gemm_dw_{l}"] = 3.0, 1.0
             if l > 0:
-                KERNELS[f"gemm_dx_{l}"] = (f"gemm_small input gradient {B}x{K}x{N} (ReLU mask)", lambda B_, P_, D_, N=N, K=K: 4 * (B_ * N + N * K + 2 * B_ * K))
+                KERNELS[f"gemm_dx_{l}"] = (f"gemm input gradient {B}x{K}x{N} (ReLU mask)", lambda B_, P_, D_, N=N, K=K: 4 * (B_ * N + N * K + 2 * B_ * K))
                 timed.append((f"gemm_dx_{l}", k_dx))
                 PER_STEP[f"gemm_dx_{l}"] = 1.0
     prog = getattr(learner, "_program", None)

@@ -319,10 +319,181 @@ __global__ void __launch_bounds__(SG * KG) gemm_small_kernel(GemmArgs g) {
     }
 }
 
-bool small_gemm_enabled() {          // MB_GEMM_LEGACY=1: the 64 x 64 kernel everywhere (A/B timing)
-    const char *e = getenv("MB_GEMM_LEGACY");
-    return !(e && e[0] == '1');
+// ---- whole-K GEMM: the learner's layers have K <= 512, so a 32 x 32 output tile's ENTIRE operand panels fit in shared
+// memory (2 x 32 x K floats: 64 KB at K = 256).  The kernel above still walks K in steps of 32 (fetch -> park -> barrier ->
+// multiply -> barrier per step): measured 8-9 us per layer, every warp spending most of its issue slots on address
+// arithmetic, staging stores and barrier waits.  Here the panels are copied ONCE with cp.async (16-byte copies straight
+// from L2 into shared memory, no registers, all in flight together), one barrier, then the four K-groups of 64 threads
+// multiply their quarter of K out of shared memory with no further synchronisation (per 4 k: 8 LDS.128 + 64 FFMA per
+// thread), and the partial tiles are added in group order like above.  One global round trip instead of K / 32.
+// Operand layouts (C[i, j] = sum_k A(i, k) B(j, k)):  k-fast -> panel [32][Kp] (Kp = K padded to 4, + 4 floats of row
+// padding against bank conflicts);  k-slow -> panel [Kp][36].  Anything a 16-byte copy cannot express (row starts that
+// are not 16-byte aligned, ragged edges, the virtual column of ones) is filled by plain loads.
+constexpr int WK_MAX_K = 512;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Fill one operand panel.  kKfast: panel[r][k] (row stride ld = Kp + 4), else panel[k][r] (row stride 36).
+// rows = tile rows that exist (< 32 at the edge), r0 = first row, stride_r / stride_k = element strides in global memory.
+template <bool kKfast>
+__device__ __forceinline__ void wk_fill(float *panel, const float *__restrict__ src, int64_t stride_r, int64_t stride_k,
+                                        int r0, int n_rows, int K, int Kp, int ones_row, int tid, int nthreads) {
+    const int ld = kKfast ? Kp + 4 : 36;
+    if (kKfast) {
+        // chunks of 4 consecutive k of one row
+        const int chunks_per_row = Kp >> 2;
+        const bool fast = stride_k == 1 && (stride_r & 3) == 0 && ((uintptr_t)src & 15) == 0;
+        for (int c = tid; c < 32 * chunks_per_row; c += nthreads) {
+            const int r = c / chunks_per_row, k = (c - r * chunks_per_row) << 2;
+            float *dst = panel + r * ld + k;
+            const int gr = r0 + r;
+            if (gr == ones_row) {
+                dst[0] = dst[1] = dst[2] = dst[3] = 1.0f;      // (k beyond K multiplies zeros of the other panel)
+            } else if (gr < n_rows && fast && k + 4 <= K) {
+                cp_async16(dst, src + (int64_t)gr * stride_r + k);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    dst[q] = (gr < n_rows && k + q < K) ? __ldcg(src + (int64_t)gr * stride_r + (int64_t)(k + q) * stride_k) : 0.0f;
+            }
+        }
+    } else {
+        // chunks of 4 consecutive rows at one k
+        const bool fast = stride_r == 1 && (stride_k & 3) == 0 && ((uintptr_t)src & 15) == 0 && (r0 & 3) == 0;
+        for (int c = tid; c < Kp * 8; c += nthreads) {
+            const int k = c >> 3, r = (c & 7) << 2;
+            float *dst = panel + k * ld + r;
+            const int gr = r0 + r;
+            if (k < K && fast && gr + 4 <= n_rows && !(ones_row >= gr && ones_row < gr + 4)) {
+                cp_async16(dst, src + (int64_t)k * stride_k + gr);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float v = 0.0f;
+                    if (gr + q == ones_row) v = 1.0f;
+                    else if (k < K && gr + q < n_rows) v = __ldcg(src + (int64_t)(gr + q) * stride_r + (int64_t)k * stride_k);
+                    dst[q] = v;
+                }
+            }
+        }
+    }
+}
+
+template <bool kAKfast, bool kBKfast>
+__global__ void __launch_bounds__(256) gemm_wk_kernel(GemmArgs g, int Kp) {
+    MB_DYNAMIC_SMEM(dyn);
+    const int lda = kAKfast ? Kp + 4 : 36, ldb = kBKfast ? Kp + 4 : 36;
+    float *As = reinterpret_cast<float *>(dyn);
+    const int a_floats = kAKfast ? 32 * lda : Kp * lda;
+    float *Bs = As + (a_floats < 3 * 32 * 36 ? 3 * 32 * 36 : a_floats);   // (the A region also hosts the reduction scratch)
+    const int tid = threadIdx.x, grp = tid >> 6, lt = tid & 63;
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    wk_fill<kAKfast>(As, g.A, g.a_i, g.a_k, i0, g.M, g.K, Kp, -1, tid, 256);
+    // B's row index is the output column j; the virtual column of ones (db) is row `ones_col` of B
+    wk_fill<kBKfast>(Bs, g.B, g.b_j, g.b_k, j0, g.ones_col >= 0 ? g.N - 1 : g.N, g.K, Kp, g.ones_col, tid, 256);
+    cp_async_wait_all();
+    __syncthreads();
+    const int ty = lt >> 3, tx = lt & 7;          // 8 x 8 threads per K-group, 4 x 4 outputs each
+    const int kq = ((Kp >> 2) + 3) / 4 * 4;        // k's per group (multiple of 4)
+    const int k_begin = grp * kq, k_end = min(Kp, k_begin + kq);
+    float acc[4][4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = 0.0f;
+    for (int k = k_begin; k < k_end; k += 4) {
+        float a[4][4], b[4][4];                     // [row / col][kk]
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (kAKfast) {
+                const float4 v = *reinterpret_cast<const float4 *>(As + (ty * 4 + q) * lda + k);
+                a[q][0] = v.x; a[q][1] = v.y; a[q][2] = v.z; a[q][3] = v.w;
+            } else {
+                const float4 v = *reinterpret_cast<const float4 *>(As + (k + q) * lda + ty * 4);
+                a[0][q] = v.x; a[1][q] = v.y; a[2][q] = v.z; a[3][q] = v.w;
+            }
+            if (kBKfast) {
+                const float4 v = *reinterpret_cast<const float4 *>(Bs + (tx * 4 + q) * ldb + k);
+                b[q][0] = v.x; b[q][1] = v.y; b[q][2] = v.z; b[q][3] = v.w;
+            } else {
+                const float4 v = *reinterpret_cast<const float4 *>(Bs + (k + q) * ldb + tx * 4);
+                b[0][q] = v.x; b[1][q] = v.y; b[2][q] = v.z; b[3][q] = v.w;
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x][kk], b[y][kk], acc[x][y]);
+    }
+    // partial tiles of groups 1..3 -> the (now idle) A panel as [32][36]; group 0 adds them in group order
+    __syncthreads();
+    float *red = As;                                // 3 x 32 x 36 floats <= the A panel (K >= 4 -> Kp >= 4; checked on the host)
+    if (grp > 0) {
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+            *reinterpret_cast<float4 *>(red + ((grp - 1) * 32 + ty * 4 + x) * 36 + tx * 4) =
+                make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+    }
+    __syncthreads();
+    if (grp == 0) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const float4 p = *reinterpret_cast<const float4 *>(red + (q * 32 + ty * 4 + x) * 36 + tx * 4);
+                acc[x][0] = __fadd_rn(acc[x][0], p.x);
+                acc[x][1] = __fadd_rn(acc[x][1], p.y);
+                acc[x][2] = __fadd_rn(acc[x][2], p.z);
+                acc[x][3] = __fadd_rn(acc[x][3], p.w);
+            }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) epilogue_store(g, i0 + ty * 4 + x, j0 + tx * 4 + y, acc[x][y]);
+    }
+}
+
+// MB_GEMM=wk (default) | small (32 x 32 tiles, K in steps of 32) | legacy (64 x 64 tiles, grid split-K): A/B timing
+int gemm_mode() {
+    const char *e = getenv("MB_GEMM");
+    if (e && e[0] == 's') return 1;
+    if (e && e[0] == 'l') return 2;
+    const char *l = getenv("MB_GEMM_LEGACY");
+    return (l && l[0] == '1') ? 2 : 0;
+}
+
+template <bool kA, bool kB>
+bool launch_wk(GemmArgs g, cudaStream_t s) {
+    const int tiles64 = ((g.N + TN - 1) / TN) * ((g.M + TM - 1) / TM);
+    if (gemm_mode() != 0 || tiles64 >= 2 * mb::kNumSMs || g.K > WK_MAX_K || g.K < 1) return false;
+    const int Kp = (g.K + 3) / 4 * 4;
+    const size_t a_floats = kA ? (size_t)32 * (Kp + 4) : (size_t)Kp * 36;
+    const size_t b_floats = kB ? (size_t)32 * (Kp + 4) : (size_t)Kp * 36;
+    // the reduction scratch (3 x 32 x 36 floats) lives in the A panel
+    const size_t a_need = a_floats < (size_t)3 * 32 * 36 ? (size_t)3 * 32 * 36 : a_floats;
+    const size_t dyn = sizeof(float) * (a_need + b_floats);
+    static bool attr_done[2][2] = {{false, false}, {false, false}};
+    if (!attr_done[kA][kB]) {
+        if (cudaFuncSetAttribute(gemm_wk_kernel<kA, kB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        attr_done[kA][kB] = true;
+    }
+    if (dyn > 200 * 1024) return false;
+    const dim3 grid((g.N + 31) / 32, (g.M + 31) / 32, 1);
+    // (the B panel starts right after a_need floats: pass Kp so that the kernel derives the same layout)
+    gemm_wk_kernel<kA, kB><<<grid, 256, dyn, s>>>(g, Kp);
+    return true;
+}
+
+bool small_gemm_enabled() { return gemm_mode() != 2; }
 
 template <bool kA, bool kB>
 bool launch_small(GemmArgs g, cudaStream_t s) {
@@ -352,7 +523,7 @@ int pick_splits(int tiles, int K) {
 
 template <bool kA, bool kB>
 int launch(GemmArgs g, float *workspace, int64_t workspace_floats, int *counters, int n_counters, cudaStream_t s) {
-    if (launch_small<kA, kB>(g, s)) {
+    if (launch_wk<kA, kB>(g, s) || launch_small<kA, kB>(g, s)) {
         MB_LAUNCHED(1);
         return MB_OK;
     }

@@ -203,12 +203,13 @@ def test_a2c_store_episode_vs_reference(lam):
 
 
 # ----------------------------------------------------------------------------- fused MLP / Adam
-@pytest.mark.parametrize("legacy", ["0", "1"])     # 32 x 32 tiles with the in-CTA K-split (default) / 64 x 64 tiles + grid split-K
+# whole-K panels + cp.async (default) / 32 x 32 tiles, K in steps of 32 / 64 x 64 tiles + grid split-K
+@pytest.mark.parametrize("legacy", ["wk", "small", "legacy"])
 @pytest.mark.parametrize("sizes,batch", [([84, 256, 256, 6], 512), ([6, 16, 16, 4], 32), ([393, 300, 1], 100), ([5, 7], 3),
                                          ([84, 256, 256, 6], 1536), ([33, 65, 31], 8192), ([256, 256], 33)])
 def test_fused_mlp_matches_torch(sizes, batch, legacy, monkeypatch):
     from machin_b200.model import FusedMLP
-    monkeypatch.setenv("MB_GEMM_LEGACY", legacy)
+    monkeypatch.setenv("MB_GEMM", legacy)
     t.manual_seed(0)
     net = FusedMLP(sizes).cuda()
     ref = t.nn.Sequential()
