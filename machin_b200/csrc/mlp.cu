@@ -405,39 +405,53 @@ __global__ void __launch_bounds__(256) gemm_wk_kernel(GemmArgs g, int Kp) {
     for (int x = 0; x < 4; ++x)
 #pragma unroll
         for (int y = 0; y < 4; ++y) acc[x][y] = 0.0f;
-    for (int k = k_begin; k < k_end; k += 4) {
-        float a[4][4], b[4][4];                     // [row / col][kk]
+    // software-pipelined: the 8 LDS.128 of the next 4 k are in flight while the 64 FFMA of the current ones issue
+    // (two warps per scheduler cannot hide the shared-memory latency by themselves)
+    float a[2][4][4], b[2][4][4];                   // [buffer][row / col][kk]
+    auto load = [&](int buf, int k) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            if (kAKfast) {
-                const float4 v = *reinterpret_cast<const float4 *>(As + (ty * 4 + q) * lda + k);
-                a[q][0] = v.x; a[q][1] = v.y; a[q][2] = v.z; a[q][3] = v.w;
+            if (kAKfast) {   // rows ty + 8q: consecutive rows across lanes, row stride Kp + 4 floats -> conflict-free LDS.128
+                const float4 v = *reinterpret_cast<const float4 *>(As + (ty + 8 * q) * lda + k);
+                a[buf][q][0] = v.x; a[buf][q][1] = v.y; a[buf][q][2] = v.z; a[buf][q][3] = v.w;
             } else {
                 const float4 v = *reinterpret_cast<const float4 *>(As + (k + q) * lda + ty * 4);
-                a[0][q] = v.x; a[1][q] = v.y; a[2][q] = v.z; a[3][q] = v.w;
+                a[buf][0][q] = v.x; a[buf][1][q] = v.y; a[buf][2][q] = v.z; a[buf][3][q] = v.w;
             }
-            if (kBKfast) {
-                const float4 v = *reinterpret_cast<const float4 *>(Bs + (tx * 4 + q) * ldb + k);
-                b[q][0] = v.x; b[q][1] = v.y; b[q][2] = v.z; b[q][3] = v.w;
+            if (kBKfast) {   // columns tx + 8q (same reason)
+                const float4 v = *reinterpret_cast<const float4 *>(Bs + (tx + 8 * q) * ldb + k);
+                b[buf][q][0] = v.x; b[buf][q][1] = v.y; b[buf][q][2] = v.z; b[buf][q][3] = v.w;
             } else {
                 const float4 v = *reinterpret_cast<const float4 *>(Bs + (k + q) * ldb + tx * 4);
-                b[0][q] = v.x; b[1][q] = v.y; b[2][q] = v.z; b[3][q] = v.w;
+                b[buf][0][q] = v.x; b[buf][1][q] = v.y; b[buf][2][q] = v.z; b[buf][3][q] = v.w;
             }
         }
+    };
+    auto mult = [&](int buf) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
             for (int x = 0; x < 4; ++x)
 #pragma unroll
-                for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x][kk], b[y][kk], acc[x][y]);
+                for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[buf][x][kk], b[buf][y][kk], acc[x][y]);
+    };
+    if (k_begin < k_end) load(0, k_begin);
+    for (int k = k_begin; k < k_end; k += 8) {
+        if (k + 4 < k_end) load(1, k + 4);
+        mult(0);
+        if (k + 4 < k_end) {
+            if (k + 8 < k_end) load(0, k + 8);
+            mult(1);
+        }
     }
     // partial tiles of groups 1..3 -> the (now idle) A panel as [32][36]; group 0 adds them in group order
     __syncthreads();
-    float *red = As;                                // 3 x 32 x 36 floats <= the A panel (K >= 4 -> Kp >= 4; checked on the host)
+    float *red = As;                                // 3 groups x 64 threads x 16 floats (<= the 3 x 32 x 36 floats reserved)
+    // (the scratch is indexed by thread, not by output position: slot [lt][x] holds that thread's 4 values of row x)
     if (grp > 0) {
 #pragma unroll
         for (int x = 0; x < 4; ++x)
-            *reinterpret_cast<float4 *>(red + ((grp - 1) * 32 + ty * 4 + x) * 36 + tx * 4) =
+            *reinterpret_cast<float4 *>(red + ((grp - 1) * 64 + lt) * 16 + x * 4) =
                 make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
     }
     __syncthreads();
@@ -446,7 +460,7 @@ __global__ void __launch_bounds__(256) gemm_wk_kernel(GemmArgs g, int Kp) {
         for (int q = 0; q < 3; ++q)
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
-                const float4 p = *reinterpret_cast<const float4 *>(red + (q * 32 + ty * 4 + x) * 36 + tx * 4);
+                const float4 p = *reinterpret_cast<const float4 *>(red + (q * 64 + lt) * 16 + x * 4);
                 acc[x][0] = __fadd_rn(acc[x][0], p.x);
                 acc[x][1] = __fadd_rn(acc[x][1], p.y);
                 acc[x][2] = __fadd_rn(acc[x][2], p.z);
@@ -455,7 +469,8 @@ __global__ void __launch_bounds__(256) gemm_wk_kernel(GemmArgs g, int Kp) {
 #pragma unroll
         for (int x = 0; x < 4; ++x)
 #pragma unroll
-            for (int y = 0; y < 4; ++y) epilogue_store(g, i0 + ty * 4 + x, j0 + tx * 4 + y, acc[x][y]);
+            for (int y = 0; y < 4; ++y)
+                epilogue_store(g, i0 + (kAKfast ? ty + 8 * x : ty * 4 + x), j0 + (kBKfast ? tx + 8 * y : tx * 4 + y), acc[x][y]);
     }
 }
 
