@@ -39,42 +39,72 @@ def _linear_fwd(x, w, b, relu, ws):
 
 class _MLPFunction(t.autograd.Function):
     @staticmethod
-    def forward(ctx, x, ws, *params):
+    def forward(ctx, x, ws, side_ws, *params):
         x = x.contiguous().float()
         n_layers = len(params) // 2
         acts = [x]
         for l in range(n_layers):
             acts.append(_linear_fwd(acts[-1], params[2 * l], params[2 * l + 1], l < n_layers - 1, ws))
-        ctx.ws = ws
+        ctx.ws, ctx.side_ws = ws, side_ws
         ctx.n_layers = n_layers
         ctx.save_for_backward(*acts[:-1], *params[0::2])
         return acts[-1]
 
     @staticmethod
     def backward(ctx, dy):
+        """Input gradients form a dependent chain (layer l needs layer l+1's); weight / bias gradients only feed the
+        optimizer.  So the weight-gradient GEMM of every layer runs on a side stream -- a parallel branch of a captured
+        update -- beside the chain, and the main stream joins once at the end (`PARALLEL_WEIGHT_GRADS`)."""
         n, ws = ctx.n_layers, ctx.ws
         saved = ctx.saved_tensors
         inputs, weights = saved[:n], saved[n:]
         dy = dy.contiguous().float()
+        dev = dy.device
         grads = [None] * (2 * n)
         dx = None
+        side = _side_stream(dev) if (PARALLEL_WEIGHT_GRADS and n > 1) else None
+        cur = t.cuda.current_stream(dev) if side is not None else None
+        side_ws = ctx.side_ws if side is not None else None
+        keep = []
         for l in range(n - 1, -1, -1):
             x, w = inputs[l], weights[l]
             M, K = x.shape
             N = w.shape[0]
             dw = t.empty_like(w)
             db = t.empty(N, dtype=t.float32, device=w.device)
-            _lib.check(lib.mb_mlp_linear_backward_weight(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(dw), _lib.ptr(db), M, N, K,
-                                                         *ws.args(), _lib.stream_ptr()))
+            if side is not None:
+                side.wait_stream(cur)                      # dy of this layer is ready
+                with t.cuda.stream(side):
+                    _lib.check(lib.mb_mlp_linear_backward_weight(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(dw), _lib.ptr(db), M, N, K,
+                                                                 *side_ws.args(), _lib.stream_ptr()))
+            else:
+                _lib.check(lib.mb_mlp_linear_backward_weight(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(dw), _lib.ptr(db), M, N, K,
+                                                             *ws.args(), _lib.stream_ptr()))
             grads[2 * l], grads[2 * l + 1] = dw, db
             if l > 0 or ctx.needs_input_grad[0]:
                 dxl = t.empty((M, K), dtype=t.float32, device=w.device)
                 _lib.check(lib.mb_mlp_linear_backward_input(_lib.ptr(dy), _lib.ptr(w), _lib.ptr(x) if l > 0 else None,
                                                             _lib.ptr(dxl), M, N, K, *ws.args(), _lib.stream_ptr()))
+                keep.append(dy)                            # the side stream may still be reading it: alive until the join
                 dy = dxl
                 if l == 0:
                     dx = dxl
-        return (dx, None, *grads)
+        if side is not None:
+            cur.wait_stream(side)                          # every dw / db is complete before autograd hands them on
+        del keep
+        return (dx, None, None, *grads)
+
+
+PARALLEL_WEIGHT_GRADS = True       # FusedMLP.backward: weight-gradient GEMMs on a side stream (see _MLPFunction.backward)
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    s = _SIDE_STREAMS.get(key)
+    if s is None:
+        s = _SIDE_STREAMS[key] = t.cuda.Stream(device=device)
+    return s
 
 
 class FusedMLP(nn.Module):
@@ -85,10 +115,11 @@ class FusedMLP(nn.Module):
         self.layers = nn.ModuleList([nn.Linear(a, b) for a, b in zip(sizes[:-1], sizes[1:])])
         self._ws = None
 
-    def _workspace(self, device):
+    def _workspace(self, device, side=False):
         """One split-K scratch per (device, stream): two forwards of the same network may run on different streams at
-        the same time (DQNPer.parallel_forwards), and launches are only ordered within a stream."""
-        key = (device, getattr(t.cuda.current_stream(device), "cuda_stream", 0))
+        the same time (DQNPer.parallel_forwards), and launches are only ordered within a stream.  ``side``: the scratch
+        of the weight-gradient branch of this stream's backward."""
+        key = (device, getattr(t.cuda.current_stream(device), "cuda_stream", 0), side)
         if self._ws is None:
             self._ws = {}
         ws = self._ws.get(key)
@@ -102,7 +133,7 @@ class FusedMLP(nn.Module):
             raise RuntimeError("FusedMLP runs on CUDA tensors only (no CPU fallback)")
         params = [p for layer in self.layers for p in (layer.weight, layer.bias)]
         with t.cuda.device(x.device):
-            return _MLPFunction.apply(x, self._workspace(x.device), *params)
+            return _MLPFunction.apply(x, self._workspace(x.device), self._workspace(x.device, side=True), *params)
 
 
 class FusedAdam(t.optim.Optimizer):
