@@ -466,11 +466,47 @@ __global__ void __launch_bounds__(256) gemm_wk_kernel(GemmArgs g, int Kp) {
                 acc[x][2] = __fadd_rn(acc[x][2], p.z);
                 acc[x][3] = __fadd_rn(acc[x][3], p.w);
             }
+        // Epilogue.  epilogue_store() per element would issue up to 32 dependent-looking global loads (bias / mask)
+        // interleaved with the stores -- the compiler cannot hoist them across stores it must assume alias -- i.e. a
+        // chain of L2 round trips longer than the multiply itself.  All loads first, then the arithmetic, then the stores.
+        int rows[4], cols[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) rows[x] = i0 + (kAKfast ? ty + 8 * x : ty * 4 + x);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) cols[y] = j0 + (kBKfast ? tx + 8 * y : tx * 4 + y);
+        float bias_v[4], mask_v[4][4];
+#pragma unroll
+        for (int y = 0; y < 4; ++y) bias_v[y] = (g.bias && cols[y] < g.N) ? __ldg(g.bias + cols[y]) : 0.0f;
 #pragma unroll
         for (int x = 0; x < 4; ++x)
 #pragma unroll
             for (int y = 0; y < 4; ++y)
-                epilogue_store(g, i0 + (kAKfast ? ty + 8 * x : ty * 4 + x), j0 + (kBKfast ? tx + 8 * y : tx * 4 + y), acc[x][y]);
+                mask_v[x][y] = (g.mask && rows[x] < g.M && cols[y] < g.N) ? __ldg(g.mask + (int64_t)rows[x] * g.c_i + cols[y]) : 1.0f;
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                float v = acc[x][y];
+                if (g.bias) v = __fadd_rn(v, bias_v[y]);
+                if (g.relu) v = fmaxf(v, 0.0f);
+                if (g.mask) v = mask_v[x][y] > 0.0f ? v : 0.0f;
+                acc[x][y] = v;
+            }
+        const bool vec = !kBKfast && g.ones_col < 0 && (g.c_i & 3) == 0 && (((uintptr_t)g.C) & 15) == 0 && cols[3] < g.N;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            if (rows[x] >= g.M) continue;
+            if (vec) {
+                *reinterpret_cast<float4 *>(g.C + (int64_t)rows[x] * g.c_i + cols[0]) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+            } else {
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    if (cols[y] >= g.N) continue;
+                    if (g.ones_col >= 0 && cols[y] == g.ones_col) g.extra[rows[x]] = acc[x][y];
+                    else g.C[(int64_t)rows[x] * g.c_i + cols[y]] = acc[x][y];
+                }
+            }
+        }
     }
 }
 
