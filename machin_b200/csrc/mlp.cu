@@ -383,22 +383,23 @@ __device__ __forceinline__ void wk_fill(float *panel, const float *__restrict__ 
     }
 }
 
-template <bool kAKfast, bool kBKfast>
-__global__ void __launch_bounds__(256) gemm_wk_kernel(GemmArgs g, int Kp) {
+template <int KG, bool kAKfast, bool kBKfast>     // KG K-groups of 64 threads: 4 (K < 128) or 8
+__global__ void __launch_bounds__(64 * KG) gemm_wk_kernel(GemmArgs g, int Kp) {
     MB_DYNAMIC_SMEM(dyn);
     const int lda = kAKfast ? Kp + 4 : 36, ldb = kBKfast ? Kp + 4 : 36;
     float *As = reinterpret_cast<float *>(dyn);
     const int a_floats = kAKfast ? 32 * lda : Kp * lda;
-    float *Bs = As + (a_floats < 3 * 32 * 36 ? 3 * 32 * 36 : a_floats);   // (the A region also hosts the reduction scratch)
+    constexpr int kRed = (KG - 1) * 64 * 16;                               // reduction scratch: (KG - 1) groups x 64 threads x 16
+    float *Bs = As + (a_floats < kRed ? kRed : a_floats);                  // (the A region also hosts it)
     const int tid = threadIdx.x, grp = tid >> 6, lt = tid & 63;
     const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
-    wk_fill<kAKfast>(As, g.A, g.a_i, g.a_k, i0, g.M, g.K, Kp, -1, tid, 256);
+    wk_fill<kAKfast>(As, g.A, g.a_i, g.a_k, i0, g.M, g.K, Kp, -1, tid, 64 * KG);
     // B's row index is the output column j; the virtual column of ones (db) is row `ones_col` of B
-    wk_fill<kBKfast>(Bs, g.B, g.b_j, g.b_k, j0, g.ones_col >= 0 ? g.N - 1 : g.N, g.K, Kp, g.ones_col, tid, 256);
+    wk_fill<kBKfast>(Bs, g.B, g.b_j, g.b_k, j0, g.ones_col >= 0 ? g.N - 1 : g.N, g.K, Kp, g.ones_col, tid, 64 * KG);
     cp_async_wait_all();
     __syncthreads();
     const int ty = lt >> 3, tx = lt & 7;          // 8 x 8 threads per K-group, 4 x 4 outputs each
-    const int kq = ((Kp >> 2) + 3) / 4 * 4;        // k's per group (multiple of 4)
+    const int kq = ((Kp >> 2) + KG - 1) / KG * 4;  // k's per group (multiple of 4)
     const int k_begin = grp * kq, k_end = min(Kp, k_begin + kq);
     float acc[4][4];
 #pragma unroll
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(256) gemm_wk_kernel(GemmArgs g, int Kp) {
     }
     // partial tiles of groups 1..3 -> the (now idle) A panel as [32][36]; group 0 adds them in group order
     __syncthreads();
-    float *red = As;                                // 3 groups x 64 threads x 16 floats (<= the 3 x 32 x 36 floats reserved)
+    float *red = As;                                // (KG - 1) groups x 64 threads x 16 floats
     // (the scratch is indexed by thread, not by output position: slot [lt][x] holds that thread's 4 values of row x)
     if (grp > 0) {
 #pragma unroll
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(256) gemm_wk_kernel(GemmArgs g, int Kp) {
     __syncthreads();
     if (grp == 0) {
 #pragma unroll
-        for (int q = 0; q < 3; ++q)
+        for (int q = 0; q < KG - 1; ++q)
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
                 const float4 p = *reinterpret_cast<const float4 *>(red + (q * 64 + lt) * 16 + x * 4);
@@ -519,29 +520,33 @@ int gemm_mode() {
     return (l && l[0] == '1') ? 2 : 0;
 }
 
+template <int KG, bool kA, bool kB>
+bool launch_wk_groups(GemmArgs g, cudaStream_t s, int Kp) {
+    const size_t a_floats = kA ? (size_t)32 * (Kp + 4) : (size_t)Kp * 36;
+    const size_t b_floats = kB ? (size_t)32 * (Kp + 4) : (size_t)Kp * 36;
+    const size_t red = (size_t)(KG - 1) * 64 * 16;           // the reduction scratch lives in the A panel
+    const size_t dyn = sizeof(float) * ((a_floats < red ? red : a_floats) + b_floats);
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(gemm_wk_kernel<KG, kA, kB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        attr_done = true;
+    }
+    if (dyn > 200 * 1024) return false;
+    const dim3 grid((g.N + 31) / 32, (g.M + 31) / 32, 1);
+    gemm_wk_kernel<KG, kA, kB><<<grid, 64 * KG, dyn, s>>>(g, Kp);
+    return true;
+}
+
 template <bool kA, bool kB>
 bool launch_wk(GemmArgs g, cudaStream_t s) {
     const int tiles64 = ((g.N + TN - 1) / TN) * ((g.M + TM - 1) / TM);
     if (gemm_mode() != 0 || tiles64 >= 2 * mb::kNumSMs || g.K > WK_MAX_K || g.K < 1) return false;
     const int Kp = (g.K + 3) / 4 * 4;
-    const size_t a_floats = kA ? (size_t)32 * (Kp + 4) : (size_t)Kp * 36;
-    const size_t b_floats = kB ? (size_t)32 * (Kp + 4) : (size_t)Kp * 36;
-    // the reduction scratch (3 x 32 x 36 floats) lives in the A panel
-    const size_t a_need = a_floats < (size_t)3 * 32 * 36 ? (size_t)3 * 32 * 36 : a_floats;
-    const size_t dyn = sizeof(float) * (a_need + b_floats);
-    static bool attr_done[2][2] = {{false, false}, {false, false}};
-    if (!attr_done[kA][kB]) {
-        if (cudaFuncSetAttribute(gemm_wk_kernel<kA, kB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
-            cudaGetLastError();
-            return false;
-        }
-        attr_done[kA][kB] = true;
-    }
-    if (dyn > 200 * 1024) return false;
-    const dim3 grid((g.N + 31) / 32, (g.M + 31) / 32, 1);
-    // (the B panel starts right after a_need floats: pass Kp so that the kernel derives the same layout)
-    gemm_wk_kernel<kA, kB><<<grid, 256, dyn, s>>>(g, Kp);
-    return true;
+    // more K-groups = more warps per scheduler to hide the shared-memory latency of the multiply (each group walks K / KG)
+    return Kp >= 128 ? launch_wk_groups<8, kA, kB>(g, s, Kp) : launch_wk_groups<4, kA, kB>(g, s, Kp);
 }
 
 bool small_gemm_enabled() { return gemm_mode() != 2; }

@@ -334,7 +334,14 @@ class DQNPer(TorchFramework):
         if st is not None:
             return self._step_fused(st, update_value, update_target, uniform, use_device_params)
         self.qnet.train()
-        batch_size, state, action, reward, next_state, terminal, d_index, d_isw = self._sample(uniform, use_device_params)
+        fork = self.overlap_priority_update and type(self.replay_buffer) is PrioritizedBuffer
+        # with a side branch, everything that only feeds the NEXT update (beta advance, priority write-back) or the host
+        # (the scalar loss) runs there; the main stream carries draw -> gather -> forward -> TD -> backward -> optimizer
+        self.replay_buffer.defer_beta_advance = bool(fork and use_device_params)
+        try:
+            batch_size, state, action, reward, next_state, terminal, d_index, d_isw = self._sample(uniform, use_device_params)
+        finally:
+            self.replay_buffer.defer_beta_advance = False
         if self.fuse_online_forwards and state.keys() == next_state.keys():
             both = self._criticize({k: t.cat([state[k], next_state[k]], dim=0) for k in state})
             q_value, next_q_value = both[:batch_size], both[batch_size:].detach()
@@ -363,13 +370,12 @@ class DQNPer(TorchFramework):
         td = ops.td_dqn(q_value.detach().contiguous(), next_q_value.contiguous(), target_next_q_value, act, reward, terminal, self.discount,
                         is_weight=d_isw, mode=self.mode, want_grad=self._fused_mse)
         batch_size = int(reward.shape[0])  # a sharded buffer may return more than batch_size rows
-        if self._fused_mse:
-            value_loss = td["loss_elem"].mean()
-        else:
+        value_loss = None
+        if not self._fused_mse:
             action_value = q_value.gather(dim=1, index=act.to(dtype=t.long))
             value_loss = (self.criterion(action_value, td["y"]) * d_isw.view(batch_size, 1)).mean()
         forked = None
-        if self.overlap_priority_update and type(self.replay_buffer) is PrioritizedBuffer:
+        if fork:
             dev = self.replay_buffer.buffer_device
             if self._side_stream is None:
                 self._side_stream = t.cuda.Stream(device=dev)
@@ -377,8 +383,14 @@ class DQNPer(TorchFramework):
             forked[1].wait_stream(forked[0])
             with t.cuda.stream(forked[1]):
                 self.replay_buffer.update_priority(td["abs_error"], d_index)
+                if use_device_params:
+                    self.replay_buffer.advance_beta_device()
+                if value_loss is None:
+                    value_loss = td["loss_elem"].mean()
         else:
             self.replay_buffer.update_priority(td["abs_error"], d_index)
+            if value_loss is None:
+                value_loss = td["loss_elem"].mean()
         if update_value:
             self.qnet_optim.zero_grad(set_to_none=True)
             if self._fused_mse:

@@ -150,8 +150,9 @@ class PrioritizedBuffer(Buffer):
             _lib.check(lib.mb_per_sample(self.wt_tree.handle, _lib.ptr(uniform), batch_size, 0, 0.0, 0.0,
                                          _lib.ptr(self._params_raw), _lib.ptr(d_index), _lib.ptr(d_isw),
                                          _lib.stream_ptr()))
-            self.advance_beta_device()
-            return d_index, d_isw
+            if not getattr(self, "defer_beta_advance", False):
+                self.advance_beta_device()             # (a learner that forks a side branch advances beta there: it only
+            return d_index, d_isw                       #  feeds the NEXT draw -- two small launches off the critical path)
         if uniform is None:
             # same call and same stream as the reference (:411): B doubles from np.random, staged through a
             # small ring of pinned buffers so that the copy is a true asynchronous H2D

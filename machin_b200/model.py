@@ -53,8 +53,9 @@ class _MLPFunction(t.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         """Input gradients form a dependent chain (layer l needs layer l+1's); weight / bias gradients only feed the
-        optimizer.  So the weight-gradient GEMM of every layer runs on a side stream -- a parallel branch of a captured
-        update -- beside the chain, and the main stream joins once at the end (`PARALLEL_WEIGHT_GRADS`)."""
+        optimizer and are independent of each other.  So the weight-gradient GEMM of every layer runs on its own side
+        stream -- parallel branches of a captured update -- beside the chain, and the main stream joins them at the end
+        (`PARALLEL_WEIGHT_GRADS`)."""
         n, ws = ctx.n_layers, ctx.ws
         saved = ctx.saved_tensors
         inputs, weights = saved[:n], saved[n:]
@@ -62,9 +63,9 @@ class _MLPFunction(t.autograd.Function):
         dev = dy.device
         grads = [None] * (2 * n)
         dx = None
-        side = _side_stream(dev) if (PARALLEL_WEIGHT_GRADS and n > 1) else None
-        cur = t.cuda.current_stream(dev) if side is not None else None
-        side_ws = ctx.side_ws if side is not None else None
+        sides = [_side_stream(dev, l) for l in range(n)] if (PARALLEL_WEIGHT_GRADS and n > 1) else None
+        cur = t.cuda.current_stream(dev) if sides is not None else None
+        side_ws = ctx.side_ws if sides is not None else None
         keep = []
         for l in range(n - 1, -1, -1):
             x, w = inputs[l], weights[l]
@@ -72,11 +73,12 @@ class _MLPFunction(t.autograd.Function):
             N = w.shape[0]
             dw = t.empty_like(w)
             db = t.empty(N, dtype=t.float32, device=w.device)
-            if side is not None:
+            if sides is not None:
+                side = sides[l]                            # one branch per layer: the weight gradients are independent of each other
                 side.wait_stream(cur)                      # dy of this layer is ready
                 with t.cuda.stream(side):
                     _lib.check(lib.mb_mlp_linear_backward_weight(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(dw), _lib.ptr(db), M, N, K,
-                                                                 *side_ws.args(), _lib.stream_ptr()))
+                                                                 *side_ws[l].args(), _lib.stream_ptr()))
             else:
                 _lib.check(lib.mb_mlp_linear_backward_weight(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(dw), _lib.ptr(db), M, N, K,
                                                              *ws.args(), _lib.stream_ptr()))
@@ -89,8 +91,9 @@ class _MLPFunction(t.autograd.Function):
                 dy = dxl
                 if l == 0:
                     dx = dxl
-        if side is not None:
-            cur.wait_stream(side)                          # every dw / db is complete before autograd hands them on
+        if sides is not None:
+            for side in sides:
+                cur.wait_stream(side)                      # every dw / db is complete before autograd hands them on
         del keep
         return (dx, None, None, *grads)
 
@@ -99,8 +102,8 @@ PARALLEL_WEIGHT_GRADS = True       # FusedMLP.backward: weight-gradient GEMMs on
 _SIDE_STREAMS = {}
 
 
-def _side_stream(device):
-    key = (device.type, device.index)
+def _side_stream(device, slot=0):
+    key = (device.type, device.index, slot)
     s = _SIDE_STREAMS.get(key)
     if s is None:
         s = _SIDE_STREAMS[key] = t.cuda.Stream(device=device)
@@ -115,7 +118,7 @@ class FusedMLP(nn.Module):
         self.layers = nn.ModuleList([nn.Linear(a, b) for a, b in zip(sizes[:-1], sizes[1:])])
         self._ws = None
 
-    def _workspace(self, device, side=False):
+    def _workspace(self, device, side=0):
         """One split-K scratch per (device, stream): two forwards of the same network may run on different streams at
         the same time (DQNPer.parallel_forwards), and launches are only ordered within a stream.  ``side``: the scratch
         of the weight-gradient branch of this stream's backward."""
@@ -124,7 +127,7 @@ class FusedMLP(nn.Module):
             self._ws = {}
         ws = self._ws.get(key)
         if ws is None:
-            ws = self._ws[key] = _Workspace(device)
+            ws = self._ws[key] = _Workspace(device) if not side else _Workspace(device, floats=1 << 19)
         return ws
 
     def forward(self, state, action=None):
@@ -133,7 +136,8 @@ class FusedMLP(nn.Module):
             raise RuntimeError("FusedMLP runs on CUDA tensors only (no CPU fallback)")
         params = [p for layer in self.layers for p in (layer.weight, layer.bias)]
         with t.cuda.device(x.device):
-            return _MLPFunction.apply(x, self._workspace(x.device), self._workspace(x.device, side=True), *params)
+            sides = tuple(self._workspace(x.device, side=l + 1) for l in range(len(self.layers)))   # one per weight-gradient branch
+            return _MLPFunction.apply(x, self._workspace(x.device), sides, *params)
 
 
 class FusedAdam(t.optim.Optimizer):

@@ -16,4 +16,4 @@ except Exception as e:
     print(m, "FAILED", e); print(open(f"gpurun_out/r2_gemm_{m}.err").read()[-1200:])
 PY
 done
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:gemm_wk -s 6 -c 3 -o gpurun_out/r2_gemm_wk python tools/ncu_targets_r2.py > gpurun_out/r2_ncu_gemm_wk.log 2>&1; tail -2 gpurun_out/r2_ncu_gemm_wk.log
+
