@@ -493,6 +493,11 @@ class DQNApex(_FixedShapeExchange, DQNPer):
         fields = buf.storage.fields
         grp_f = lambda fl, attr: {f.key: fl[f.name] for f in fields.values() if f.attr == attr and f.kind == "major"}
         prog = self._static_program(st, capB) if self.use_fused_program else None
+        from ...model import FusedMLP
+        # FusedMLP: the backward kernels write dW / db straight into the flat buffer (no zero-fill, no accumulate launches)
+        sinks = isinstance(self.qnet, FusedMLP) and prog is None
+        if sinks:
+            self.qnet.set_grad_sinks([p.grad for p in params])
 
         def body():
             self._static_sample()
@@ -526,16 +531,22 @@ class DQNApex(_FixedShapeExchange, DQNPer):
                 td = ops.td_dqn(q.detach(), nq, tq, self.action_get_function(action), fl["reward"], fl["terminal"],
                                 self.discount, is_weight=st["isw"], mode=self.mode, want_grad=True)
             forked = self._static_write_back_maybe_forked(td["abs_error"])
+            loss = None
+            if forked is not None:
+                with t.cuda.stream(forked[1]):              # the scalar loss only goes to the host: off the critical path too
+                    loss = td["loss_elem"].mean()
             if prog is None:
-                self._flat_grad.zero_()
+                if not sinks:
+                    self._flat_grad.zero_()
                 q.backward(td["grad_q"])
             self._static_all_reduce(self._flat_grad, self.SITE_GRADS)
             self._optimizer_and_target(True, True)        # clip (if finite), optimizer step, soft target update
             if forked is None:
                 self._static_write_back(td["abs_error"])
+                loss = td["loss_elem"].mean()
             else:
                 forked[0].wait_stream(forked[1])            # join before the next draw reads the tree
-            return td["loss_elem"].mean()
+            return loss
 
         _, st["loss"] = self._static_capture(body, warmup, (self.qnet, self.qnet_target), (self.qnet_optim,))
 
@@ -591,6 +602,8 @@ class DQNApex(_FixedShapeExchange, DQNPer):
                 if graph is not None:
                     graph.reset()
         self._apex_graph = None
+        if hasattr(self.qnet, "set_grad_sinks"):
+            self.qnet.set_grad_sinks(None)             # back to ordinary autograd accumulation for the eager path
         super().release_graphs()
 
     def update_device(self, update_value=True, update_target=True, uniform=None):

@@ -39,13 +39,13 @@ def _linear_fwd(x, w, b, relu, ws):
 
 class _MLPFunction(t.autograd.Function):
     @staticmethod
-    def forward(ctx, x, ws, side_ws, *params):
+    def forward(ctx, x, ws, side_ws, sinks, *params):
         x = x.contiguous().float()
         n_layers = len(params) // 2
         acts = [x]
         for l in range(n_layers):
             acts.append(_linear_fwd(acts[-1], params[2 * l], params[2 * l + 1], l < n_layers - 1, ws))
-        ctx.ws, ctx.side_ws = ws, side_ws
+        ctx.ws, ctx.side_ws, ctx.sinks = ws, side_ws, sinks
         ctx.n_layers = n_layers
         ctx.save_for_backward(*acts[:-1], *params[0::2])
         return acts[-1]
@@ -71,8 +71,11 @@ class _MLPFunction(t.autograd.Function):
             x, w = inputs[l], weights[l]
             M, K = x.shape
             N = w.shape[0]
-            dw = t.empty_like(w)
-            db = t.empty(N, dtype=t.float32, device=w.device)
+            # gradient sinks (FusedMLP.set_grad_sinks): the kernel writes dW / db straight into the caller's buffers (e.g.
+            # views of one flat all-reduce buffer) and autograd gets None -- no zero-fill, no per-parameter accumulate launches
+            sink = ctx.sinks is not None
+            dw = ctx.sinks[2 * l] if sink else t.empty_like(w)
+            db = ctx.sinks[2 * l + 1] if sink else t.empty(N, dtype=t.float32, device=w.device)
             if sides is not None:
                 side = sides[l]                            # one branch per layer: the weight gradients are independent of each other
                 side.wait_stream(cur)                      # dy of this layer is ready
@@ -82,7 +85,8 @@ class _MLPFunction(t.autograd.Function):
             else:
                 _lib.check(lib.mb_mlp_linear_backward_weight(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(dw), _lib.ptr(db), M, N, K,
                                                              *ws.args(), _lib.stream_ptr()))
-            grads[2 * l], grads[2 * l + 1] = dw, db
+            if not sink:
+                grads[2 * l], grads[2 * l + 1] = dw, db
             if l > 0 or ctx.needs_input_grad[0]:
                 dxl = t.empty((M, K), dtype=t.float32, device=w.device)
                 _lib.check(lib.mb_mlp_linear_backward_input(_lib.ptr(dy), _lib.ptr(w), _lib.ptr(x) if l > 0 else None,
@@ -95,7 +99,7 @@ class _MLPFunction(t.autograd.Function):
             for side in sides:
                 cur.wait_stream(side)                      # every dw / db is complete before autograd hands them on
         del keep
-        return (dx, None, None, *grads)
+        return (dx, None, None, None, *grads)
 
 
 PARALLEL_WEIGHT_GRADS = True       # FusedMLP.backward: weight-gradient GEMMs on a side stream (see _MLPFunction.backward)
@@ -117,6 +121,20 @@ class FusedMLP(nn.Module):
         self.sizes = list(sizes)
         self.layers = nn.ModuleList([nn.Linear(a, b) for a, b in zip(sizes[:-1], sizes[1:])])
         self._ws = None
+        self._grad_sinks = None
+
+    def set_grad_sinks(self, sinks):
+        """``sinks``: one contiguous float32 CUDA tensor per parameter (weight, bias per layer, parameter order) that the
+        backward kernels write the gradients INTO -- typically views of one flat buffer that is all-reduced as a whole;
+        autograd then receives no gradient for the parameters (``p.grad`` should be set to the same views by the caller).
+        ``None`` restores ordinary autograd accumulation."""
+        if sinks is not None:
+            sinks = tuple(sinks)
+            params = [p for layer in self.layers for p in (layer.weight, layer.bias)]
+            if len(sinks) != len(params) or any(s.shape != p.shape or s.dtype != t.float32 or not s.is_contiguous()
+                                                for s, p in zip(sinks, params)):
+                raise ValueError("grad sinks must match the parameters: contiguous float32 tensors of the same shapes")
+        self._grad_sinks = sinks
 
     def _workspace(self, device, side=0):
         """One split-K scratch per (device, stream): two forwards of the same network may run on different streams at
@@ -137,7 +155,7 @@ class FusedMLP(nn.Module):
         params = [p for layer in self.layers for p in (layer.weight, layer.bias)]
         with t.cuda.device(x.device):
             sides = tuple(self._workspace(x.device, side=l + 1) for l in range(len(self.layers)))   # one per weight-gradient branch
-            return _MLPFunction.apply(x, self._workspace(x.device), sides, *params)
+            return _MLPFunction.apply(x, self._workspace(x.device), sides, self._grad_sinks, *params)
 
 
 class FusedAdam(t.optim.Optimizer):
