@@ -220,7 +220,8 @@ int mb_wire_update_mask(const void *d_recv, int n_blocks, int64_t cap, const int
  *                (index, version, priority) -- the scatter + all-to-all of the NCCL path
  *  push:         nbytes of d_src -> peers[r] + self * slot_stride for every r (all-gather of shard sums: 8 bytes;
  *                gradient all-reduce, first half: the flat gradient buffer into slot `self` of every member)
- *  sum:          d_out[i] = (slots[0][i] + slots[1][i] + ...) / divisor, member order -- every member adds the
+ *  sum:          d_out[i] = (slots[0][i] + slots[1][i] + ...) / divisor for i < n, slot m at d_slots + m * slot_floats,
+ *                member order -- every member adds the
  *                same numbers in the same order, so all members hold bit-identical averaged gradients
  *  barrier:      every member stores epoch+1 into flag `self` of every member (release, system scope) and waits
  *                until its own n_blocks flags reached it (acquire): what was pushed before the barrier by any
@@ -229,13 +230,28 @@ int mb_wire_update_mask(const void *d_recv, int n_blocks, int64_t cap, const int
 #define MB_MAX_PEERS 16
 int mb_wire_push_rows(const void *d_ring, int64_t pitch, int64_t capacity, const int64_t *d_index,
                       const double *d_is_weight, const int64_t *d_version_table, int n_blocks, int64_t cap,
-                      int self_block, int64_t width, void *const *peers, void *stream);
+                      int self_block, int64_t width, void *const *peers, void *const *peer_flags, unsigned int *d_ticket,
+                      uint64_t *d_state, void *stream);
 int mb_wire_push_update(int n_blocks, int64_t cap, int self_block, const int64_t *d_counts, const int64_t *d_index,
                         const int64_t *d_version, const float *d_priority, int64_t merged_rows, void *const *peers,
                         void *stream);
 int mb_peer_push(const void *d_src, int64_t nbytes, int n_blocks, int self_block, int64_t slot_stride,
-                 void *const *peers, void *stream);
-int mb_peer_sum(const float *d_slots, int n_blocks, int64_t n, float divisor, float *d_out, void *stream);
+                 void *const *peers, void *const *peer_flags, unsigned int *d_ticket, uint64_t *d_state, void *stream);
+int mb_peer_sum(const float *d_slots, int n_blocks, int64_t n, int64_t slot_floats, float divisor, float *d_out,
+                void *const *peer_flags, int self_block, uint64_t *d_state, void *stream);
+/* The barrier folded into its neighbours (peer_flags != NULL): a producer (push_rows, push) publishes the site's next
+ * epoch from the LAST CTA of its grid (d_ticket: one zeroed unsigned per site) after fencing its peer stores; a consumer
+ * (compact_wait, sum) waits at its top until this member's n_blocks flags reached the epoch in d_state[0].  Saves the
+ * separate barrier launch between them.  sums_apportion: all-gather of the shard sums + barrier + mb_wire_apportion in
+ * one warp (the first exchange of an update). */
+int mb_wire_compact_wait(const void *d_recv, int n_blocks, int64_t cap, int64_t width, int64_t meta_offset,
+                         const int64_t *d_counts, void *d_merged, int64_t merged_rows, int64_t *d_index, int64_t *d_version,
+                         double *d_is_weight, const double *d_scale, void *const *peer_flags, int self_block,
+                         uint64_t *d_state, void *stream);
+int mb_peer_sums_apportion(void *const *peer_flags, void *const *peer_sums, const double *d_my_sum, int n_blocks,
+                           int self_block, uint64_t *d_state, int64_t timeout_ns, int64_t batch, int64_t merged_rows,
+                           const int64_t *d_n_stored, double *d_beta, double beta_increment, int64_t *d_counts,
+                           double *d_scale, mb_per_params *d_params, void *stream);
 int mb_peer_barrier(void *const *peer_flags, int n_blocks, int self_block, uint64_t *d_state,
                     int64_t timeout_ns, void *stream);
 

@@ -142,7 +142,7 @@ int mb_wire_compact(const void *d_recv, int n_blocks, int64_t cap, int64_t width
     if (merged_rows == 0) return MB_OK;
     wire_compact_kernel<<<(unsigned)((merged_rows * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const char *)d_recv, n_blocks, cap, width, meta_offset, d_counts, (char *)d_merged, merged_rows, d_index,
-        d_version, d_is_weight, d_scale);
+        d_version, d_is_weight, d_scale, PeerSignal{});
     MB_LAUNCHED(1);
     return MB_OK;
 }

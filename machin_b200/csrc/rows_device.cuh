@@ -7,6 +7,61 @@
 
 #include "machin_b200.h"
 
+// ---- peer-memory exchange: pointer tables and the signal / wait halves of the barrier (used by the push kernels at the
+// end of this file and by wire_compact_kernel)
+struct PeerPtrs {
+    char *p[MB_MAX_PEERS];
+};
+
+// Barrier folded into its neighbours (instead of a separate barrier launch between producer and consumer):
+//   producer  every CTA fences its peer stores at system scope and takes a ticket; the LAST CTA of the grid publishes
+//             epoch = state[0] + 1 into flag `self` of every member and stores it back into state[0]
+//   consumer  every CTA waits until the P flags of THIS member reached state[0] (the local producer ran earlier on the
+//             same stream, so state[0] already holds the current epoch), then reads what the members pushed.
+// flags == nullptr switches both off (the NCCL transport, the emulation of the plain kernels).
+struct PeerSignal {
+    PeerPtrs flags;                 // member m's flag row of this site, as mapped here
+    unsigned long long *state;      // [0] epoch, [1] timed-out
+    unsigned int *ticket;           // zero between launches
+    int P, self_block, on;
+};
+
+__device__ __forceinline__ void peer_signal_tail(const PeerSignal &sg, unsigned total_ctas) {
+    if (!sg.on) return;
+    __threadfence_system();                         // my CTA's peer stores are visible system-wide ...
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(sg.ticket, 1u);
+        if (t == total_ctas - 1) {                  // ... and so are everybody else's: they fenced before their ticket
+            *sg.ticket = 0;
+            __threadfence_system();
+            const unsigned long long epoch = sg.state[0] + 1;
+            for (int r = 0; r < sg.P; ++r)
+                *(reinterpret_cast<volatile unsigned long long *>(sg.flags.p[r]) + sg.self_block) = epoch;
+            sg.state[0] = epoch;
+        }
+    }
+}
+
+__device__ __forceinline__ void peer_wait_head(const PeerSignal &sg) {
+    if (!sg.on) return;
+    if ((int)threadIdx.x < sg.P) {
+        const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long *>(sg.state);
+        const volatile unsigned long long *mine =
+            reinterpret_cast<volatile unsigned long long *>(sg.flags.p[sg.self_block]) + threadIdx.x;
+        long long spins = 0;
+        while (*mine < epoch) {
+            if (++spins > (1ll << 25)) {            // a member never arrived (~10 s of L2 polls): report, do not hang the GPU
+                sg.state[1] = 1;
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+}
+
+
 struct FieldList {
     mb_field f[MB_MAX_FIELDS];
     int n;
@@ -95,7 +150,8 @@ __global__ void __launch_bounds__(256) wire_compact_kernel(const char *__restric
                                                            const int64_t *__restrict__ counts, char *__restrict__ merged,
                                                            int64_t merged_rows, int64_t *__restrict__ index,
                                                            int64_t *__restrict__ version, double *__restrict__ isw,
-                                                           const double *__restrict__ scale) {
+                                                           const double *__restrict__ scale, PeerSignal wait) {
+    peer_wait_head(wait);            // (peer transport: every member's rows have landed; no-op otherwise)
     const int lane = threadIdx.x & 31;
     const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // merged row handled by this warp
     if (j >= merged_rows) return;
@@ -160,11 +216,10 @@ __global__ void __launch_bounds__(256) wire_update_mask_kernel(const char *__res
 // 0, so the mean over merged_rows rows times scale is the mean over the real ones), and one mb_per_params block
 // per requester this shard serves: beta advances by beta_increment per draw (only when this shard draws at all),
 // the final beta goes back to *beta.  One thread: P is the number of GPUs.
-__global__ void wire_apportion_kernel(const double *__restrict__ sums, int P, int64_t batch, int self_block,
-                                      int64_t merged_rows, const int64_t *__restrict__ n_stored, double *beta,
-                                      double beta_increment, int64_t *__restrict__ counts, double *__restrict__ scale,
-                                      mb_per_params *__restrict__ params) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ void wire_apportion_body(const double *__restrict__ sums, int P, int64_t batch, int self_block,
+                                                    int64_t merged_rows, const int64_t *__restrict__ n_stored, double *beta,
+                                                    double beta_increment, int64_t *__restrict__ counts,
+                                                    double *__restrict__ scale, mb_per_params *__restrict__ params) {
     double total = 0.0;
     for (int m = 0; m < P; ++m) total = __dadd_rn(total, sums[m]);
     total = __dadd_rn(total, 1e-6);
@@ -188,19 +243,24 @@ __global__ void wire_apportion_kernel(const double *__restrict__ sums, int P, in
     *beta = b;
 }
 
+__global__ void wire_apportion_kernel(const double *__restrict__ sums, int P, int64_t batch, int self_block,
+                                      int64_t merged_rows, const int64_t *__restrict__ n_stored, double *beta,
+                                      double beta_increment, int64_t *__restrict__ counts, double *__restrict__ scale,
+                                      mb_per_params *__restrict__ params) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    wire_apportion_body(sums, P, batch, self_block, merged_rows, n_stored, beta, beta_increment, counts, scale, params);
+}
+
 
 // ---- shard exchange over peer memory (NVLink): the same data movement as gather + pack_meta + all-to-all, and as
 // scatter_update + all-to-all, with the destination in ANOTHER GPU's buffer (peer-mapped pointers).  Plain stores:
 // the ordering against the consumer is the peer barrier that follows (csrc/peer.cu).
-struct PeerPtrs {
-    char *p[MB_MAX_PEERS];
-};
-
 __global__ void __launch_bounds__(256) wire_push_rows_kernel(const char *__restrict__ ring, int64_t pitch,
                                                              int64_t capacity, const int64_t *__restrict__ index,
                                                              const double *__restrict__ isw,
                                                              const int64_t *__restrict__ version_table, int P,
-                                                             int64_t cap, int self_block, int64_t width, PeerPtrs recv) {
+                                                             int64_t cap, int self_block, int64_t width, PeerPtrs recv,
+                                                             PeerSignal sg) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -218,6 +278,7 @@ __global__ void __launch_bounds__(256) wire_push_rows_kernel(const char *__restr
             reinterpret_cast<double *>(m)[2] = isw[j];
         }
     }
+    peer_signal_tail(sg, gridDim.x);
 }
 
 __global__ void __launch_bounds__(256) wire_push_update_kernel(int P, int64_t cap, int self_block,
@@ -240,7 +301,7 @@ __global__ void __launch_bounds__(256) wire_push_update_kernel(int P, int64_t ca
 
 // nbytes of src -> slot `self_block` of every member (blockIdx.y = destination member)
 __global__ void __launch_bounds__(256) peer_push_kernel(const char *__restrict__ src, int64_t nbytes, int self_block,
-                                                        int64_t slot_stride, PeerPtrs dst) {
+                                                        int64_t slot_stride, PeerPtrs dst, PeerSignal sg) {
     char *out = dst.p[blockIdx.y] + (int64_t)self_block * slot_stride;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     if ((((uintptr_t)src | (uintptr_t)out | (uintptr_t)nbytes) & 15) == 0) {
@@ -252,14 +313,16 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const char *__restrict__
     } else {
         for (int64_t k = tid; k < nbytes; k += stride) out[k] = src[k];
     }
+    peer_signal_tail(sg, gridDim.x * gridDim.y);
 }
 
 // out[i] = (slots[0][i] + slots[1][i] + ... + slots[P-1][i]) / divisor, member order (separately rounded adds)
-__global__ void __launch_bounds__(256) peer_sum_kernel(const float *__restrict__ slots, int P, int64_t n, float divisor,
-                                                       float *__restrict__ out) {
+__global__ void __launch_bounds__(256) peer_sum_kernel(const float *__restrict__ slots, int P, int64_t n, int64_t slot_floats,
+                                                       float divisor, float *__restrict__ out, PeerSignal wait) {
+    peer_wait_head(wait);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float acc = slots[i];
-        for (int m = 1; m < P; ++m) acc = __fadd_rn(acc, slots[(int64_t)m * n + i]);
+        for (int m = 1; m < P; ++m) acc = __fadd_rn(acc, slots[(int64_t)m * slot_floats + i]);
         out[i] = __fdiv_rn(acc, divisor);
     }
 }

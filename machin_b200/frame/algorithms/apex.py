@@ -129,15 +129,21 @@ class _FixedShapeExchange:
         pb = st.get("peer_buffers")
         if st["device_apportion"]:
             if peer is not None:
-                check(lib.mb_peer_push(ptr(buf.weight_sum_tensor()), 8, P, me, 8, pb["sums"].ptrs, stream_ptr()))
-                peer.barrier(self.SITE_SUMS)
-            elif P > 1:
-                dist.all_gather_into_tensor(st["sums"], buf.weight_sum_tensor(), group=grp.pg)
+                # all-gather of the shard sums + barrier + apportioning: ONE one-warp kernel
+                from ...parallel.peer import BARRIER_TIMEOUT_NS
+                flags, _, state = peer.site(self.SITE_SUMS)
+                check(lib.mb_peer_sums_apportion(flags, pb["sums"].ptrs, ptr(buf.weight_sum_tensor()), P, me, state,
+                                                 BARRIER_TIMEOUT_NS, B, capB, ptr(st["nstored"]), ptr(st["beta"]),
+                                                 float(buf.beta_increment_per_sampling), ptr(st["counts"]), ptr(st["scale"]),
+                                                 ptr(st["params"]), stream_ptr()))
             else:
-                st["sums"].copy_(buf.weight_sum_tensor())
-            check(lib.mb_wire_apportion(ptr(st["sums"]), P, B, me, capB, ptr(st["nstored"]), ptr(st["beta"]),
-                                        float(buf.beta_increment_per_sampling), ptr(st["counts"]), ptr(st["scale"]),
-                                        ptr(st["params"]), stream_ptr()))
+                if P > 1:
+                    dist.all_gather_into_tensor(st["sums"], buf.weight_sum_tensor(), group=grp.pg)
+                else:
+                    st["sums"].copy_(buf.weight_sum_tensor())
+                check(lib.mb_wire_apportion(ptr(st["sums"]), P, B, me, capB, ptr(st["nstored"]), ptr(st["beta"]),
+                                            float(buf.beta_increment_per_sampling), ptr(st["counts"]), ptr(st["scale"]),
+                                            ptr(st["params"]), stream_ptr()))
         else:
             for name in ("counts", "params", "uni", "scale"):
                 st[name].copy_(st[name + "_pin"], non_blocking=True)
@@ -149,19 +155,24 @@ class _FixedShapeExchange:
                 check(lib.mb_per_sample(tree, ptr(st["uni"][r]), cap, 0, 0.0, 0.0, ptr(st["params"][r]),
                                         ptr(st["d_idx"][r]), ptr(st["d_isw"][r]), stream_ptr()))
         if peer is not None:
-            # gather + metadata + all-to-all as ONE kernel: every row goes straight into its requester's buffer
+            # gather + metadata + all-to-all as ONE kernel: every row goes straight into its requester's buffer; its last
+            # CTA signals the site, and the compaction waits at its top for every member's signal (no barrier launch)
+            flags, ticket, state = peer.site(self.SITE_ROWS)
             check(lib.mb_wire_push_rows(ptr(buf.storage.data), pitch, buf.storage.max_size, ptr(st["d_idx"]),
-                                        ptr(st["d_isw"]), ptr(table), P, cap, me, W, pb["recv"].ptrs, stream_ptr()))
-            peer.barrier(self.SITE_ROWS)
+                                        ptr(st["d_isw"]), ptr(table), P, cap, me, W, pb["recv"].ptrs, flags, ticket, state,
+                                        stream_ptr()))
+            check(lib.mb_wire_compact_wait(ptr(st["recv"]), P, cap, W, pitch, ptr(st["counts"]), ptr(st["merged"]), capB,
+                                           ptr(st["idx"]), ptr(st["ver"]), ptr(st["isw"]), ptr(st["scale"]), flags, me, state,
+                                           stream_ptr()))
+            return
+        # the P wire blocks are contiguous in requester order: ONE gather and ONE metadata launch for all of them
+        buf.storage.gather_into_wire(st["d_idx"].view(-1), st["send"])
+        check(lib.mb_rows_pack_meta(ptr(st["send"]), W, pitch, P * cap, ptr(st["d_idx"]), None, ptr(table),
+                                    ptr(st["d_isw"]), None, stream_ptr()))
+        if P > 1:
+            dist.all_to_all_single(st["recv"], st["send"], group=grp.pg)
         else:
-            # the P wire blocks are contiguous in requester order: ONE gather and ONE metadata launch for all of them
-            buf.storage.gather_into_wire(st["d_idx"].view(-1), st["send"])
-            check(lib.mb_rows_pack_meta(ptr(st["send"]), W, pitch, P * cap, ptr(st["d_idx"]), None, ptr(table),
-                                        ptr(st["d_isw"]), None, stream_ptr()))
-            if P > 1:
-                dist.all_to_all_single(st["recv"], st["send"], group=grp.pg)
-            else:
-                st["recv"].copy_(st["send"])
+            st["recv"].copy_(st["send"])
         check(lib.mb_wire_compact(ptr(st["recv"]), P, cap, W, pitch, ptr(st["counts"]), ptr(st["merged"]), capB,
                                   ptr(st["idx"]), ptr(st["ver"]), ptr(st["isw"]), ptr(st["scale"]), stream_ptr()))
 
@@ -215,15 +226,11 @@ class _FixedShapeExchange:
         if peer is not None:
             slots = st["peer_buffers"]["grads"]
             stride = int(slots.local.shape[1]) * 4
-            check(lib.mb_peer_push(ptr(flat), 4 * n, P, me, stride, slots.ptrs, stream_ptr()))
-            peer.barrier(site)
-            if n == slots.local.shape[1]:
-                check(lib.mb_peer_sum(ptr(slots.local), P, n, float(P), ptr(flat), stream_ptr()))
-            else:                                       # a smaller buffer in the same slots: strided view, same order
-                acc = slots.local[0, :n].clone()
-                for m in range(1, P):
-                    acc += slots.local[m, :n]
-                flat.copy_(acc / P)
+            flags, ticket, state = peer.site(site)
+            # my buffer into slot `me` of every member (the last CTA signals), then the ordered sum waits at its top
+            check(lib.mb_peer_push(ptr(flat), 4 * n, P, me, stride, slots.ptrs, flags, ticket, state, stream_ptr()))
+            check(lib.mb_peer_sum(ptr(slots.local), P, n, int(slots.local.shape[1]), float(P), ptr(flat), flags, me, state,
+                                  stream_ptr()))
         elif P > 1:
             red = self.learner_group if getattr(self, "learner_group", None) is not None else grp
             dist.all_reduce(flat, group=red.pg)

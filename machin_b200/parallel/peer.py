@@ -44,6 +44,7 @@ class PeerMemory:
         self._site_flags = [(C.c_void_p * self.P)(*[int(a) + site * _lib.MB_MAX_PEERS * 8 for a in self.flags.ptrs])
                             for site in range(MAX_SITES)]
         self.state = t.zeros((MAX_SITES, 2), dtype=t.int64, device=self.device)  # per site: [epoch, timed-out]
+        self.tickets = t.zeros(MAX_SITES, dtype=t.int32, device=self.device)     # per site: CTAs of the producer that are done
         t.cuda.synchronize(self.device)
         group.barrier()                                             # every member's flags are zero before anyone signals
 
@@ -83,6 +84,11 @@ class PeerMemory:
         calls the barriers of one ``site`` in the same order."""
         _lib.check(lib.mb_peer_barrier(self._site_flags[site], self.P, self.me, _lib.ptr(self.state[site]),
                                        BARRIER_TIMEOUT_NS, _lib.stream_ptr()))
+
+    def site(self, site: int):
+        """(flag pointer table, ticket, state) of one site: the arguments of the entry points that fold the barrier into
+        the producing kernel (signal from its last CTA) and the consuming kernel (wait at its top)."""
+        return self._site_flags[site], _lib.ptr(self.tickets[site:site + 1]), _lib.ptr(self.state[site])
 
     def check(self):
         """Host-side (synchronises): raise if a barrier gave up waiting for a member."""

@@ -26,6 +26,8 @@ inline shim_dim3 blockDim, gridDim;
 inline std::barrier<> *shim_cta_barrier = nullptr;
 
 inline void __syncthreads() { shim_cta_barrier->arrive_and_wait(); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline unsigned atomicAdd(unsigned *a, unsigned v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
 
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(8) float2 { float x, y; };

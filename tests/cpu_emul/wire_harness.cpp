@@ -39,7 +39,7 @@ int emul_wire_compact(const char *recv, int P, int64_t cap, int64_t width, int64
                       char *merged, int64_t merged_rows, int64_t *index, int64_t *version, double *isw,
                       const double *scale) {
     shim_launch((unsigned)((merged_rows * 32 + 255) / 256), 256, [&] {
-        wire_compact_kernel(recv, P, cap, width, meta_off, counts, merged, merged_rows, index, version, isw, scale);
+        wire_compact_kernel(recv, P, cap, width, meta_off, counts, merged, merged_rows, index, version, isw, scale, PeerSignal{});
     });
     return 0;
 }
@@ -77,7 +77,7 @@ int emul_wire_push_rows(const char *ring, int64_t pitch, int64_t capacity, const
     int64_t blocks = ((int64_t)P * cap * 32 + 255) / 256;
     if (blocks > 64) blocks = 64;
     shim_launch((unsigned)blocks, 256, [&] {
-        wire_push_rows_kernel(ring, pitch, capacity, index, isw, version_table, P, cap, self_block, width, pp);
+        wire_push_rows_kernel(ring, pitch, capacity, index, isw, version_table, P, cap, self_block, width, pp, PeerSignal{});
     });
     return 0;
 }
@@ -97,13 +97,13 @@ int emul_peer_push(const char *src, int64_t nbytes, int P, int self_block, int64
     for (int m = 0; m < P; ++m) pp.p[m] = peers[m];
     for (int dst = 0; dst < P; ++dst) {                 // blockIdx.y = destination member
         blockIdx.y = (unsigned)dst;
-        shim_launch(2, 256, [&] { blockIdx.y = (unsigned)dst; peer_push_kernel(src, nbytes, self_block, slot_stride, pp); });
+        shim_launch(2, 256, [&] { blockIdx.y = (unsigned)dst; peer_push_kernel(src, nbytes, self_block, slot_stride, pp, PeerSignal{}); });
     }
     return 0;
 }
 
 int emul_peer_sum(const float *slots, int P, int64_t n, float divisor, float *out) {
-    shim_launch(2, 256, [&] { peer_sum_kernel(slots, P, n, divisor, out); });
+    shim_launch(2, 256, [&] { peer_sum_kernel(slots, P, n, n, divisor, out, PeerSignal{}); });
     return 0;
 }
 
