@@ -248,6 +248,12 @@ int mb_wire_compact_wait(const void *d_recv, int n_blocks, int64_t cap, int64_t 
                          const int64_t *d_counts, void *d_merged, int64_t merged_rows, int64_t *d_index, int64_t *d_version,
                          double *d_is_weight, const double *d_scale, void *const *peer_flags, int self_block,
                          uint64_t *d_state, void *stream);
+/* compact + unpack in one launch: merged row j goes straight into the dense field tensors (`fields` as in mb_rows_gather;
+ * row offsets relative to the wire row), padding rows zero-filled, metadata as in mb_wire_compact */
+int mb_wire_compact_fields(const void *d_recv, int n_blocks, int64_t cap, int64_t width, int64_t meta_offset,
+                           const int64_t *d_counts, const mb_field *fields, int n_fields, int64_t merged_rows,
+                           int64_t *d_index, int64_t *d_version, double *d_is_weight, const double *d_scale,
+                           void *const *peer_flags, int self_block, uint64_t *d_state, void *stream);
 int mb_peer_sums_apportion(void *const *peer_flags, void *const *peer_sums, const double *d_my_sum, int n_blocks,
                            int self_block, uint64_t *d_state, int64_t timeout_ns, int64_t batch, int64_t merged_rows,
                            const int64_t *d_n_stored, double *d_beta, double beta_increment, int64_t *d_counts,

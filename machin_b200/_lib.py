@@ -90,6 +90,7 @@ SIGNATURES = {
     "mb_peer_push": (i32, [vp, i64, i32, i32, i64, C.POINTER(vp), C.POINTER(vp), vp, vp, vp]),
     "mb_peer_sum": (i32, [vp, i32, i64, i64, f32, vp, C.POINTER(vp), i32, vp, vp]),
     "mb_wire_compact_wait": (i32, [vp, i32, i64, i64, i64, vp, vp, i64, vp, vp, vp, vp, C.POINTER(vp), i32, vp, vp]),
+    "mb_wire_compact_fields": (i32, [vp, i32, i64, i64, i64, vp, C.POINTER(MbField), i32, i64, vp, vp, vp, vp, C.POINTER(vp), i32, vp, vp]),
     "mb_peer_sums_apportion": (i32, [C.POINTER(vp), C.POINTER(vp), vp, i32, i32, vp, i64, i64, i64, vp, vp, f64, vp, vp, vp, vp]),
     "mb_peer_barrier": (i32, [C.POINTER(vp), i32, i32, vp, i64, vp]),
     "mb_td_dqn": (i32, [vp, vp, vp, i64, i32, vp, vp, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]),

@@ -211,6 +211,31 @@ int mb_wire_compact_wait(const void *d_recv, int n_blocks, int64_t cap, int64_t 
     return MB_OK;
 }
 
+int mb_wire_compact_fields(const void *d_recv, int n_blocks, int64_t cap, int64_t width, int64_t meta_offset,
+                           const int64_t *d_counts, const mb_field *fields, int n_fields, int64_t merged_rows,
+                           int64_t *d_index, int64_t *d_version, double *d_is_weight, const double *d_scale,
+                           void *const *peer_flags, int self_block, uint64_t *d_state, void *stream) {
+    if (!d_recv || !d_counts || !fields || n_fields < 1 || n_fields > MB_MAX_FIELDS || !d_index || !d_version || !d_is_weight ||
+        n_blocks < 1 || cap < 1 || width % 8 || meta_offset % 8 || meta_offset + 24 > width || merged_rows < 0)
+        return MB_ERR_INVALID;
+    if (merged_rows == 0) return MB_OK;
+    FieldList fl;
+    fl.n = n_fields;
+    for (int i = 0; i < n_fields; ++i) {
+        fl.f[i] = fields[i];
+        if (fields[i].row_offset < 0 || fields[i].nbytes < 0 || fields[i].row_offset + fields[i].nbytes > meta_offset || !fields[i].d_dense)
+            return MB_ERR_INVALID;
+    }
+    PeerSignal wait;
+    const int r = fill_signal(wait, peer_flags, n_blocks, self_block, d_state, nullptr);
+    if (r != MB_OK) return r;
+    wire_compact_fields_kernel<<<(unsigned)((merged_rows * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const char *)d_recv, n_blocks, cap, width, meta_offset, d_counts, fl, merged_rows, d_index, d_version, d_is_weight,
+        d_scale, wait);
+    MB_LAUNCHED(1);
+    return MB_OK;
+}
+
 int mb_peer_sums_apportion(void *const *peer_flags, void *const *peer_sums, const double *d_my_sum, int n_blocks,
                            int self_block, uint64_t *d_state, int64_t timeout_ns, int64_t batch, int64_t merged_rows,
                            const int64_t *d_n_stored, double *d_beta, double beta_increment, int64_t *d_counts,

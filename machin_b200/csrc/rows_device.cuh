@@ -175,6 +175,40 @@ __global__ void __launch_bounds__(256) wire_compact_kernel(const char *__restric
     }
 }
 
+// Compaction straight into the dense field tensors (compact + unpack in one launch): merged row j is split into its fields
+// like rows_move_kernel<true> does, padding rows are zero-filled, metadata goes out as in wire_compact_kernel.
+__global__ void __launch_bounds__(256) wire_compact_fields_kernel(const char *__restrict__ recv, int P, int64_t cap,
+                                                                  int64_t width, int64_t meta_off,
+                                                                  const int64_t *__restrict__ counts, FieldList fl,
+                                                                  int64_t merged_rows, int64_t *__restrict__ index,
+                                                                  int64_t *__restrict__ version, double *__restrict__ isw,
+                                                                  const double *__restrict__ scale, PeerSignal wait) {
+    peer_wait_head(wait);
+    const int lane = threadIdx.x & 31;
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // merged row handled by this warp
+    if (j >= merged_rows) return;
+    int64_t base = 0;
+    int m = 0;
+    while (m < P && j >= base + counts[m]) base += counts[m++];
+    if (m == P) {                                  // padding row: zero fields, weight 0
+        for (int f = 0; f < fl.n; ++f) {
+            char *dense = (char *)fl.f[f].d_dense + j * fl.f[f].dense_pitch;
+            for (int64_t k = lane; k < fl.f[f].nbytes; k += 32) dense[k] = 0;
+        }
+        if (lane == 0) { index[j] = 0; version[j] = -1; isw[j] = 0.0; }
+        return;
+    }
+    const char *src = recv + ((int64_t)m * cap + (j - base)) * width;
+    for (int f = 0; f < fl.n; ++f)
+        warp_copy((char *)fl.f[f].d_dense + j * fl.f[f].dense_pitch, src + fl.f[f].row_offset, fl.f[f].nbytes, lane);
+    if (lane == 0) {
+        const char *meta = src + meta_off;
+        index[j] = reinterpret_cast<const int64_t *>(meta)[0];
+        version[j] = reinterpret_cast<const int64_t *>(meta)[1];
+        isw[j] = reinterpret_cast<const double *>(meta)[2] * (scale ? *scale : 1.0);
+    }
+}
+
 __global__ void __launch_bounds__(256) wire_scatter_update_kernel(char *__restrict__ send, int P, int64_t cap,
                                                                   const int64_t *__restrict__ counts,
                                                                   const int64_t *__restrict__ index,

@@ -70,6 +70,11 @@ class _FixedShapeExchange:
     the graph.  Follows prioritized_buffer_d.py:184-303; state lives in ``self._static``."""
 
     SITE_SUMS, SITE_ROWS, SITE_PRIORITIES, SITE_GRADS, SITE_GRADS_2 = 0, 1, 2, 3, 4
+    # Folding the barrier into the producing / consuming kernels (signal from the producer's last CTA after a system-scope
+    # fence in EVERY CTA, wait at the top of every consumer CTA) removes a launch per exchange but measured SLOWER than
+    # the separate one-warp barrier kernel (N = 2: 170.9 vs 152.6 us / update): a kernel boundary publishes the peer stores
+    # for free, `__threadfence_system()` in hundreds of CTAs does not.  Kept as an option for the experiment log.
+    fold_barriers = False
 
     def _static_setup(self, device_apportion: bool, peer_exchange: bool, grad_floats: int):
         """Collective.  Allocates every buffer of the exchange (peer-mapped ones if ``peer_exchange`` works here) and
@@ -117,10 +122,12 @@ class _FixedShapeExchange:
         self._static = st
         return st
 
-    def _static_sample(self):
+    def _static_sample(self, dense: bool = True):
         """Capturable: shard sums -> apportioning -> this shard's draws for every requester -> row exchange ->
-        compaction.  Leaves the merged, padded batch in ``st["merged"]`` (wire rows), ``st["idx"]`` / ``st["ver"]`` /
-        ``st["isw"]`` (IS weights already scaled so that a mean over the padded rows is the mean over the real ones)."""
+        compaction.  Leaves ``st["idx"]`` / ``st["ver"]`` / ``st["isw"]`` (IS weights already scaled so that a mean over
+        the padded rows is the mean over the real ones) and returns the merged, padded batch as dense field tensors
+        (``dense``; over the peer transport compaction and unpacking are ONE launch) -- or, ``dense=False``, leaves it as
+        wire rows in ``st["merged"]`` and returns None."""
         import torch.distributed as dist
         from ..._lib import lib, ptr, check, stream_ptr
         st, buf, grp = self._static, self.replay_buffer, self.apex_group
@@ -157,14 +164,26 @@ class _FixedShapeExchange:
         if peer is not None:
             # gather + metadata + all-to-all as ONE kernel: every row goes straight into its requester's buffer; its last
             # CTA signals the site, and the compaction waits at its top for every member's signal (no barrier launch)
-            flags, ticket, state = peer.site(self.SITE_ROWS)
+            flags, ticket, state = peer.site(self.SITE_ROWS) if self.fold_barriers else (None, None, None)
             check(lib.mb_wire_push_rows(ptr(buf.storage.data), pitch, buf.storage.max_size, ptr(st["d_idx"]),
                                         ptr(st["d_isw"]), ptr(table), P, cap, me, W, pb["recv"].ptrs, flags, ticket, state,
                                         stream_ptr()))
+            if not self.fold_barriers:
+                peer.barrier(self.SITE_ROWS)
+            if dense:
+                fl = st.get("dense")
+                if fl is None:
+                    fields = buf.storage.fields
+                    fl = st["dense"] = {k: t.zeros((capB,) + f.shape, dtype=f.dtype, device=buf.buffer_device) for k, f in fields.items()}
+                    st["dense_arr"] = buf.storage._field_array(list(fields), fl)
+                check(lib.mb_wire_compact_fields(ptr(st["recv"]), P, cap, W, pitch, ptr(st["counts"]), st["dense_arr"], len(fl),
+                                                 capB, ptr(st["idx"]), ptr(st["ver"]), ptr(st["isw"]), ptr(st["scale"]), flags, me,
+                                                 state, stream_ptr()))
+                return fl
             check(lib.mb_wire_compact_wait(ptr(st["recv"]), P, cap, W, pitch, ptr(st["counts"]), ptr(st["merged"]), capB,
                                            ptr(st["idx"]), ptr(st["ver"]), ptr(st["isw"]), ptr(st["scale"]), flags, me, state,
                                            stream_ptr()))
-            return
+            return None
         # the P wire blocks are contiguous in requester order: ONE gather and ONE metadata launch for all of them
         buf.storage.gather_into_wire(st["d_idx"].view(-1), st["send"])
         check(lib.mb_rows_pack_meta(ptr(st["send"]), W, pitch, P * cap, ptr(st["d_idx"]), None, ptr(table),
@@ -175,6 +194,7 @@ class _FixedShapeExchange:
             st["recv"].copy_(st["send"])
         check(lib.mb_wire_compact(ptr(st["recv"]), P, cap, W, pitch, ptr(st["counts"]), ptr(st["merged"]), capB,
                                   ptr(st["idx"]), ptr(st["ver"]), ptr(st["isw"]), ptr(st["scale"]), stream_ptr()))
+        return buf.storage.unpack(st["merged"]) if dense else None
 
     def _static_write_back(self, abs_error: t.Tensor):
         """Capturable: route (index, version, |delta|) of every merged row back to the shard that served it, filter by
@@ -226,9 +246,11 @@ class _FixedShapeExchange:
         if peer is not None:
             slots = st["peer_buffers"]["grads"]
             stride = int(slots.local.shape[1]) * 4
-            flags, ticket, state = peer.site(site)
-            # my buffer into slot `me` of every member (the last CTA signals), then the ordered sum waits at its top
+            flags, ticket, state = peer.site(site) if self.fold_barriers else (None, None, None)
+            # my buffer into slot `me` of every member, barrier, then the ordered sum
             check(lib.mb_peer_push(ptr(flat), 4 * n, P, me, stride, slots.ptrs, flags, ticket, state, stream_ptr()))
+            if not self.fold_barriers:
+                peer.barrier(site)
             check(lib.mb_peer_sum(ptr(slots.local), P, n, int(slots.local.shape[1]), float(P), ptr(flat), flags, me, state,
                                   stream_ptr()))
         elif P > 1:
@@ -507,14 +529,13 @@ class DQNApex(_FixedShapeExchange, DQNPer):
             self.qnet.set_grad_sinks([p.grad for p in params])
 
         def body():
-            self._static_sample()
+            fl = self._static_sample(dense=prog is None)
             if prog is not None:
                 # fused value math (csrc/mlp.cu): forward x3 + TD + backward straight into the flat gradient buffer
                 buf.storage.unpack(st["merged"], names=prog["names"], out=prog["fields"])
                 check(lib.mb_mlp_program_run(prog["handle"], stream_ptr()))
                 td = {"abs_error": prog["abs"], "loss_elem": prog["loss"]}
             else:
-                fl = buf.storage.unpack(st["merged"])
                 state, action, next_state = grp_f(fl, "state"), grp_f(fl, "action"), grp_f(fl, "next_state")
                 if self.parallel_forwards:
                     # the two no-grad forwards on side streams: parallel branches of the captured graph (as DQNPer does)
@@ -735,8 +756,7 @@ class DDPGApex(_FixedShapeExchange, DDPGPer):
         grp_f = lambda fl, attr: {f.key: fl[f.name] for f in fields.values() if f.attr == attr and f.kind == "major"}
 
         def body():
-            self._static_sample()
-            fl = buf.storage.unpack(st["merged"])
+            fl = self._static_sample()
             state, action, next_state = grp_f(fl, "state"), grp_f(fl, "action"), grp_f(fl, "next_state")
             reward, terminal, isw = fl["reward"], fl["terminal"], st["isw"]
             real = (st["ver"] >= 0).to(t.float32)                 # compaction marks padding rows with version -1

@@ -69,6 +69,18 @@ int emul_wire_apportion(const double *sums, int P, int64_t batch, int self_block
     return 0;
 }
 
+int emul_wire_compact_fields(const char *recv, int P, int64_t cap, int64_t width, int64_t meta_off, const int64_t *counts,
+                             const mb_field *fields, int n_fields, int64_t merged_rows, int64_t *index, int64_t *version,
+                             double *isw, const double *scale) {
+    FieldList fl{};
+    fl.n = n_fields;
+    for (int i = 0; i < n_fields; ++i) fl.f[i] = fields[i];
+    shim_launch((unsigned)((merged_rows * 32 + 255) / 256), 256, [&] {
+        wire_compact_fields_kernel(recv, P, cap, width, meta_off, counts, fl, merged_rows, index, version, isw, scale, PeerSignal{});
+    });
+    return 0;
+}
+
 // peer-memory exchange: "peers" are plain host buffers here (one per emulated shard)
 int emul_wire_push_rows(const char *ring, int64_t pitch, int64_t capacity, const int64_t *index, const double *isw,
                         const int64_t *version_table, int P, int64_t cap, int self_block, int64_t width, char **peers) {

@@ -93,6 +93,16 @@ def test_fixed_shape_exchange_replayed_for_P_shards(wire, P, pitch):
                 j += 1
         assert j == n
         assert np.all(mg[n:] == 0) and np.all(mi[n:] == 0) and np.all(mv[n:] == -1) and np.all(mw[n:] == 0.0)
+        # compact + unpack in one launch (mb_wire_compact_fields): two fields cut out of every merged row land in dense
+        # tensors, byte for byte what splitting `mg` gives; same metadata
+        half = (pitch // 2) // 8 * 8
+        fa, fb = np.full((capB, half), 0x55, np.uint8), np.full((capB, pitch - half), 0x55, np.uint8)
+        fl = (MbField * 2)(MbField(0, half, fa.ctypes.data, half), MbField(half, pitch - half, fb.ctypes.data, pitch - half))
+        mi2, mv2, mw2 = np.full(capB, -7, np.int64), np.full(capB, -7, np.int64), np.full(capB, -7.0)
+        assert wire.emul_wire_compact_fields(p(recv[r]), P, C.c_int64(cap), C.c_int64(W), C.c_int64(pitch), p(counts), fl, 2,
+                                             C.c_int64(capB), p(mi2), p(mv2), p(mw2), p(scale)) == 0
+        assert np.array_equal(fa, mg[:, :half]) and np.array_equal(fb, mg[:, half:pitch])
+        assert np.array_equal(mi2, mi) and np.array_equal(mv2, mv) and np.array_equal(mw2, mw)
         merged.append(mg), m_idx.append(mi), m_ver.append(mv), m_isw.append(mw)
     # ---- after TD: every requester sends (index, version, |delta|) back to the shard each row came from
     pri = [rng.rand(capB).astype(np.float32) for _ in range(P)]
