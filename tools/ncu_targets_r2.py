@@ -98,6 +98,34 @@ for _ in range(2):
     _lib.check(lib.mb_rows_unpack_meta(_lib.ptr(recv), W, pitch, P * B, _lib.ptr(v_idx), _lib.ptr(v_ver), _lib.ptr(v_isw), None, sp()))
 t.cuda.synchronize()
 buf.wt_tree.check()
+# ---- the peer-memory exchange kernels on ONE GPU: every "peer" is this GPU's own buffer (the stores go to local HBM instead of
+#      over NVLink; same code, same shapes as N = 8), the barrier with a group of one
+import ctypes as C  # noqa: E402
+W2 = pitch + 32
+peer_recv = t.zeros((P * B, W2), dtype=t.uint8, device=dev)
+peer_recv2 = t.zeros((P * B, 24), dtype=t.uint8, device=dev)
+n_grad = sum(p.numel() for p in q.parameters())
+flat = t.randn(n_grad, device=dev)
+slots = t.zeros((P, n_grad), dtype=t.float32, device=dev)
+flags, state = t.zeros(16, dtype=t.int64, device=dev), t.zeros(2, dtype=t.int64, device=dev)
+same = lambda x: (C.c_void_p * P)(*[x.data_ptr()] * P)
+one = lambda x: (C.c_void_p * 1)(x.data_ptr())
+dense = {k: t.zeros((B + P,) + f.shape, dtype=f.dtype, device=dev) for k, f in buf.storage.fields.items()}
+dense_arr = buf.storage._field_array(list(buf.storage.fields), dense)
+recv_w2 = t.zeros((P * B, W2), dtype=t.uint8, device=dev)
+for _ in range(2):
+    _lib.check(lib.mb_wire_push_rows(_lib.ptr(buf.storage.data), pitch, buf.storage.max_size, _lib.ptr(idx), _lib.ptr(isw), _lib.ptr(table),
+                                     P, B, 0, W2, same(peer_recv), None, None, None, sp()))
+    _lib.check(lib.mb_peer_barrier(one(flags), 1, 0, _lib.ptr(state), 10 ** 9, sp()))
+    _lib.check(lib.mb_wire_compact_fields(_lib.ptr(peer_recv), P, B, W2, pitch, _lib.ptr(counts), dense_arr, len(dense), B + P,
+                                          _lib.ptr(m_idx), _lib.ptr(m_ver), _lib.ptr(m_isw), _lib.ptr(scale), None, 0, None, sp()))
+    _lib.check(lib.mb_wire_push_update(P, B, 0, _lib.ptr(counts), _lib.ptr(m_idx), _lib.ptr(m_ver), _lib.ptr(pri), B + P, same(peer_recv2), sp()))
+    _lib.check(lib.mb_peer_push(_lib.ptr(flat), 4 * n_grad, P, 0, 4 * n_grad, same(slots), None, None, None, sp()))
+    _lib.check(lib.mb_peer_sum(_lib.ptr(slots), P, n_grad, n_grad, float(P), _lib.ptr(flat), None, 0, None, sp()))
+    sums1, flags1, state1 = t.zeros(1, dtype=t.float64, device=dev), t.zeros(16, dtype=t.int64, device=dev), t.zeros(2, dtype=t.int64, device=dev)
+    _lib.check(lib.mb_peer_sums_apportion(one(flags1), one(sums1), lib.mb_tree_root_ptr(tree), 1, 0, _lib.ptr(state1), 10 ** 9, B, B + 1,
+                                          _lib.ptr(nst), _lib.ptr(beta), 1e-3, _lib.ptr(counts[:1]), _lib.ptr(scale), _lib.ptr(params[:1]), sp()))
+t.cuda.synchronize()
 # ---- scans and the other target kernels
 for n_ep in (1024, 4096):
     T = n_ep * 20

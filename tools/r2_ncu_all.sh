@@ -26,6 +26,6 @@ with open(path, "w", newline="") as f:          # keep the columns the summaries
 PY
     cat gpurun_out/r2_ncu_$1_summary.md
 }
-pass step   'per_sample_cluster$|rows_gather_bulk|gemm_small|td_dqn|tree_update_part|adam|soft_update' 48
-pass wire   'per_sample_cluster_multi|rows_move_kernel|rows_pack|rows_unpack|wire_' 28
+pass step   'per_sample_cluster$|rows_gather_bulk|gemm_wk|gemm_kernel|td_dqn|tree_update_part|adam|soft_update' 56
+pass wire   'per_sample_cluster_multi|rows_move_kernel|rows_pack|rows_unpack|wire_|peer_' 44
 pass scans  'vtrace|gae_kernel|td_target|td_dist|tree_find|tree_leaf|tree_build' 40
