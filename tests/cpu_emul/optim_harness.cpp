@@ -3,7 +3,6 @@
 #include "cuda_shim.h"
 
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-inline unsigned atomicAdd(unsigned *a, unsigned v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
 
 #include "optim_device.cuh"
 
