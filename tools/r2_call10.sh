@@ -13,7 +13,6 @@ for k, v in j["results"].items():
     print(f"{k:28s} {v.get('us', v.get('ms', 0) * 1e3):10.2f} us  frac {v.get('frac', 0):.3f}")
 print(j["clocks"])
 PY
-MB_ROWS_LEGACY=1 timeout 400 python tools/microbench.py > gpurun_out/r2_microbench_rows_legacy.json 2> gpurun_out/r2_microbench_rows_legacy.err
 for mode in "" "--serial --net torch"; do
   name=default; [ -n "$mode" ] && name=round1_order_torch_net
   timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches_$name.csv python tools/step_launches.py $mode > gpurun_out/r2_launches_$name.log 2>&1
