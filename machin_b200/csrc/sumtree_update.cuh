@@ -490,8 +490,11 @@ __global__ void __launch_bounds__(kSortedN) tree_update_sorted_v2(TreeDev t, con
 // A CTA with more than kPartCap distinct entries (only possible for n > 512 on a heavily skewed batch) walks its
 // levels through global memory like the generic body -- slower, still correct, still independent of the others.
 // Parents are fl(left + right) of the current children everywhere: bit-identical to the reference update.
-constexpr int kPartThreads = 512;
-constexpr int kPartCap = 512;       // distinct entries a CTA walks out of shared memory
+#ifndef MB_PART_THREADS
+#define MB_PART_THREADS 512         // (the CPU emulation harness compiles the same source with 128: 4x fewer OS threads)
+#endif
+constexpr int kPartThreads = MB_PART_THREADS;
+constexpr int kPartCap = kPartThreads;   // distinct entries a CTA walks out of shared memory (one thread per entry)
 constexpr int kPartMaxN = 4096;     // largest batch served by this kernel
 constexpr int kPartMaxCut = 7;      // at most 128 subtrees
 constexpr int kPartPosBits = 12;    // batch position inside the 64-bit sort key (kPartMaxN = 2^12)
