@@ -176,7 +176,7 @@ def run_reference(a):
         dtype = "f32"
     else:
         rows = a.replay_rows if a.replay_rows != 10_000_000 else C4["ROWS"]
-        value, ms, threads, done, sample = cpu_ddpg_rate(C4, rows, budget_s=90.0, max_updates=a.steps)
+        value, ms, threads, done, sample = cpu_ddpg_rate(C4, rows, budget_s=90.0, max_updates=a.steps, storage_rows=a.cpu_storage_rows)
         name, dtype = _c4_name(rows, 1), "f64 tree/IS-weights + f32 TD"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": done,
             "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -482,7 +482,7 @@ def run_c4(a, ClockSampler):
                     "note": "B=512: every launch moves < 4 MB -- latency-bound; saturated figures in DESIGN.md section 2"}
     cpu = None
     if not a.no_cpu_baseline and rank == 0 and world == 1:
-        v, ms, threads, done_u, sample = cpu_ddpg_rate(cfg, rows, budget_s=25.0, max_updates=a.cpu_steps)
+        v, ms, threads, done_u, sample = cpu_ddpg_rate(cfg, rows, budget_s=25.0, max_updates=a.cpu_steps, storage_rows=a.cpu_storage_rows)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": ms, "sample": sample}
     h2d = 8 * B * (world if world > 1 else 1)
     line = {"metric": METRIC, "value": world * B * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

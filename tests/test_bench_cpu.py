@@ -17,7 +17,7 @@ def run_bench(*flags, env=None):
 
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
-    res = run_bench("--impl", "reference", "--steps", "2", "--warmup", "1", "--replay-rows", "50000")
+    res = run_bench("--impl", "reference", "--steps", "2", "--warmup", "1", "--replay-rows", "50000", "--cpu-storage-rows", "2000")
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, res.stdout
@@ -30,6 +30,18 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     cb = j["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == j["value"]
     assert cb["unit"] == j["unit"]
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_of_the_sharded_ddpg_workload():
+    """bench.py --workload c4 --impl reference: the oracle port of the reference's DDPG-PER update, same contract."""
+    res = run_bench("--impl", "reference", "--workload", "c4", "--steps", "2", "--replay-rows", "20000", "--cpu-storage-rows", "1000")
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, res.stdout
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "transitions_sampled_per_sec" and j["value"] > 0
+    assert j["cpu_baseline"]["kind"] == "port" and "C4" in j["config"]["workload"]
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
