@@ -577,6 +577,10 @@ class DQNApex(_FixedShapeExchange, DQNPer):
             return loss
 
         _, st["loss"] = self._static_capture(body, warmup, (self.qnet, self.qnet_target), (self.qnet_optim,))
+        if sinks:
+            # the captured kernels keep writing into the flat buffer; eager updates (update_value=False, a released graph)
+            # go through ordinary autograd accumulation again
+            self.qnet.set_grad_sinks(None)
 
     def _static_program(self, st, rows):
         """Opt-in (``use_fused_program``): the fused value-math program of DQNPer over the merged, padded batch of the
