@@ -511,6 +511,65 @@ __global__ void __launch_bounds__(64 * KG) gemm_wk_kernel(GemmArgs g, int Kp) {
     }
 }
 
+// ---- narrow outputs (N <= 8: the last layer of a Q-net or critic): one WARP per row -------------------------------------
+// A 32 x 32 tile wastes 26 of its 32 columns on a 6-wide output and the launch is 16 CTAs walking K = 256 each (measured
+// 7.7 us, as long as the 256-wide layer).  Here the N weight rows live in shared memory, every warp takes one input row:
+// lane l multiplies elements 4l.. of the row (float4 loads, stride 128) against all N weight rows, the N partial sums are
+// reduced with shuffles in a fixed order, lanes 0..N-1 add the bias and store.  64 CTAs for 512 rows, one L2 round trip.
+constexpr int NARROW_MAX_N = 8;
+
+__global__ void __launch_bounds__(256) gemm_narrow_kernel(GemmArgs g) {
+    MB_DYNAMIC_SMEM(dyn);
+    float *ws = reinterpret_cast<float *>(dyn);                 // [N][K]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int K = g.K, N = g.N;
+    for (int c = tid; c < (N * K) >> 2; c += 256) {
+        const int j = (c << 2) / K, k = (c << 2) - j * K;
+        *reinterpret_cast<float4 *>(ws + j * K + k) = __ldg(reinterpret_cast<const float4 *>(g.B + (int64_t)j * g.b_j + k));
+    }
+    __syncthreads();
+    for (int row = blockIdx.x * 8 + wid; row < g.M; row += gridDim.x * 8) {
+        float acc[NARROW_MAX_N];
+#pragma unroll
+        for (int j = 0; j < NARROW_MAX_N; ++j) acc[j] = 0.0f;
+        const float *x = g.A + (int64_t)row * g.a_i;
+        for (int k = lane * 4; k < K; k += 128) {
+            const float4 xv = __ldcg(reinterpret_cast<const float4 *>(x + k));
+#pragma unroll
+            for (int j = 0; j < NARROW_MAX_N; ++j)
+                if (j < N) {
+                    const float4 wv = *reinterpret_cast<const float4 *>(ws + j * K + k);
+                    acc[j] = fmaf(xv.w, wv.w, fmaf(xv.z, wv.z, fmaf(xv.y, wv.y, fmaf(xv.x, wv.x, acc[j]))));
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < NARROW_MAX_N; ++j)
+            if (j < N) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[j] = __fadd_rn(acc[j], __shfl_xor_sync(0xffffffffu, acc[j], o));
+            }
+        float out = 0.0f;                                        // lane j keeps column j
+#pragma unroll
+        for (int j = 0; j < NARROW_MAX_N; ++j)
+            if (lane == j) out = acc[j];
+        if (lane < N) {
+            if (g.bias) out = __fadd_rn(out, __ldg(g.bias + lane));
+            if (g.relu) out = fmaxf(out, 0.0f);
+            g.C[(int64_t)row * g.c_i + lane] = out;
+        }
+    }
+}
+
+bool launch_narrow(const GemmArgs &g, cudaStream_t s) {
+    if (g.N > NARROW_MAX_N || g.N < 1 || g.K < 4 || (g.K & 3) || g.K > 2048 || g.a_k != 1 || g.b_k != 1 || (g.a_i & 3) || (g.b_j & 3) ||
+        g.mask || g.ones_col >= 0 || (((uintptr_t)g.A | (uintptr_t)g.B) & 15) || (size_t)g.N * g.K * sizeof(float) > 48 * 1024)
+        return false;
+    int blocks = (g.M + 7) / 8;
+    if (blocks > 4 * mb::kNumSMs) blocks = 4 * mb::kNumSMs;
+    gemm_narrow_kernel<<<blocks, 256, sizeof(float) * (size_t)g.N * g.K, s>>>(g);
+    return true;
+}
+
 // MB_GEMM=wk (default) | small (32 x 32 tiles, K in steps of 32) | legacy (64 x 64 tiles, grid split-K): A/B timing
 int gemm_mode() {
     const char *e = getenv("MB_GEMM");
@@ -579,7 +638,7 @@ int pick_splits(int tiles, int K) {
 
 template <bool kA, bool kB>
 int launch(GemmArgs g, float *workspace, int64_t workspace_floats, int *counters, int n_counters, cudaStream_t s) {
-    if (launch_wk<kA, kB>(g, s) || launch_small<kA, kB>(g, s)) {
+    if ((kA && kB && gemm_mode() == 0 && launch_narrow(g, s)) || launch_wk<kA, kB>(g, s) || launch_small<kA, kB>(g, s)) {
         MB_LAUNCHED(1);
         return MB_OK;
     }
