@@ -23,6 +23,7 @@ class A2C(TorchFramework):
     _config_frame, _config_kind = "A2C", "local"
     _is_top = ["actor", "critic"]
     _is_restorable = ["actor", "critic"]
+    on_policy = True      # update() consumes the buffer (a2c.py:419): machin_b200.auto runs one update per stored episode
 
     def __init__(self, actor: nn.Module, critic: nn.Module, optimizer: Callable, criterion: Callable, *_,
                  lr_scheduler: Callable = None, lr_scheduler_args=(), lr_scheduler_kwargs=(), batch_size: int = 100,

@@ -768,6 +768,33 @@ def gen_surface():
         json.dump(out, fh, indent=1, sort_keys=True)
 
 
+def gen_auto_surface():
+    """Public functions / classes / methods of the reference's automation layer (machin/auto) with their parameter names.
+    Read from the SOURCE with ``ast``: the package imports pytorch-lightning and gym, which this image does not have."""
+    import ast
+    import json
+    root = os.path.join(ref_shim.REFERENCE_ROOT, "machin", "auto")
+    out = {}
+    for module in ("config", "dataset", "launcher", os.path.join("envs", "openai_gym")):
+        tree = ast.parse(open(os.path.join(root, module + ".py")).read())
+
+        def params(fn):
+            args = fn.args
+            names = [a.arg for a in args.posonlyargs + args.args + args.kwonlyargs]
+            return [n for n in names if n not in ("self", "cls")]
+
+        members = {}
+        for node in tree.body:
+            if isinstance(node, ast.FunctionDef) and not node.name.startswith("_"):
+                members[node.name] = params(node)
+            elif isinstance(node, ast.ClassDef) and not node.name.startswith("_"):
+                members[node.name] = {m.name: params(m) for m in node.body if isinstance(m, ast.FunctionDef)
+                                      and (not m.name.startswith("_") or m.name in ("__init__", "__next__", "__len__", "__iter__"))}
+        out[module.replace(os.sep, ".")] = members
+    with open(os.path.join(OUT, "ref_auto_surface.json"), "w") as fh:
+        json.dump(out, fh, indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     ref_shim.load()
     os.makedirs(OUT, exist_ok=True)
