@@ -76,6 +76,18 @@ class _FixedShapeExchange:
     # for free, `__threadfence_system()` in hundreds of CTAs does not.  Kept as an option for the experiment log.
     fold_barriers = False
 
+    PEER_CHECK_EVERY = 1024
+
+    def _check_peers_now_and_then(self):
+        """A peer barrier that gave up on a member (parallel/peer.py: 20 s) lets the update run on with stale rows; the
+        flag it leaves is read here every PEER_CHECK_EVERY host-side updates (one small device-to-host read)."""
+        st = getattr(self, "_static", None)
+        if st is None or st.get("peer") is None:
+            return
+        self._peer_checks = getattr(self, "_peer_checks", 0) + 1
+        if self._peer_checks % self.PEER_CHECK_EVERY == 0:
+            st["peer"].check()
+
     def _static_setup(self, device_apportion: bool, peer_exchange: bool, grad_floats: int):
         """Collective.  Allocates every buffer of the exchange (peer-mapped ones if ``peer_exchange`` works here) and
         stores the state dict in ``self._static``.  ``grad_floats``: size of the largest flat gradient buffer that will be
@@ -662,6 +674,7 @@ class DQNApex(_FixedShapeExchange, DQNPer):
 
     def update(self, update_value=True, update_target=True, concatenate_samples=True, **__):
         result = super().update(update_value, update_target, concatenate_samples)
+        self._check_peers_now_and_then()
         self.push_weights()
         return result
 
@@ -817,6 +830,7 @@ class DDPGApex(_FixedShapeExchange, DDPGPer):
 
     def update(self, update_value=True, update_policy=True, update_target=True, concatenate_samples=True, **__):
         result = super().update(update_value, update_policy, update_target, concatenate_samples)
+        self._check_peers_now_and_then()
         srv = self.actor_model_server
         if srv is not None:
             net = self.actor.module if self._is_using_DP_or_DDP else self.actor

@@ -75,3 +75,29 @@ def test_device_apportion_mode_never_needs_the_sums():
         assert np.array_equal(st["uni"].numpy(), np.random.uniform(size=(P, B)))
         assert st["nstored"].item() == 777
     assert abs(buf.curr_beta - (0.4 + 6 * P * 1e-3)) < 1e-12
+
+
+def test_peer_timeout_flag_is_read_every_so_often():
+    """A peer barrier that gave up leaves a flag on the device; the host-side update reads it once per PEER_CHECK_EVERY calls."""
+    from machin_b200.frame.algorithms.apex import _FixedShapeExchange
+
+    class Peer:
+        checks = 0
+
+        def check(self):
+            Peer.checks += 1
+            if Peer.checks == 2:
+                raise RuntimeError("peer exchange: a member did not reach a barrier")
+
+    learner = _FixedShapeExchange.__new__(_FixedShapeExchange)
+    learner._check_peers_now_and_then()                       # no fixed-shape state: nothing to read
+    learner._static = {"peer": None}
+    learner._check_peers_now_and_then()                       # NCCL transport: nothing to read
+    learner._static = {"peer": Peer()}
+    learner.PEER_CHECK_EVERY = 4
+    for _ in range(7):
+        learner._check_peers_now_and_then()
+    assert Peer.checks == 1
+    import pytest
+    with pytest.raises(RuntimeError, match="did not reach a barrier"):
+        learner._check_peers_now_and_then()
