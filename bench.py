@@ -625,6 +625,7 @@ def run_b200(a):
                               "two CUDA graphs per update around eager NCCL exchanges") if graph else "eager",
                    "net": a.net, "adam": a.adam,
                    "optimizer_and_target": "one launch (FusedAdam step + soft update)" if (a.fuse_optimizer and a.adam == "fused") else "two launches", "priority_update": "parallel graph branch" if (a.overlap_update and (world == 1 or a.static_exchange)) else "in line",
+                   "step_options_off": os.environ.get("MB_STEP_OFF", "") or None,
                    "online_forwards": "one pass over [s; s']" if a.fuse_forwards else ("split, no-grad ones on parallel branches" if (a.parallel_forwards and (world == 1 or a.static_exchange)) else "split (as the reference)"),
                    "transport": None if world == 1 else (
                        "peer memory over NVLink: this library's kernels store into the other GPUs' buffers, one barrier kernel "

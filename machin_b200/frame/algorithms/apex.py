@@ -19,7 +19,7 @@ import torch.nn as nn
 from ... import ops
 from ..buffers import DistributedPrioritizedBuffer
 from .dqn_per import DQNPer
-from .utils import capture_safe, soft_update
+from .utils import capture_graph, capture_safe, soft_update
 
 
 def _flat_grad_all_reduce(params, group, flat=None):
@@ -295,7 +295,7 @@ class _FixedShapeExchange:
         t.cuda.synchronize(dev)
         graph = t.cuda.CUDAGraph()
         launched = lib.mb_launch_count()
-        with capture_safe(), t.cuda.graph(graph, capture_error_mode="thread_local"):
+        with capture_safe(), capture_graph(graph, side, capture_error_mode="thread_local"):
             out = body()
         st["graph"] = graph
         self.graph_launches = lib.mb_launch_count() - launched     # libmachin_b200 kernels per replayed update
@@ -497,9 +497,9 @@ class DQNApex(_FixedShapeExchange, DQNPer):
         from ..._lib import lib
         g1, g2 = t.cuda.CUDAGraph(), t.cuda.CUDAGraph()
         launched = lib.mb_launch_count()
-        with t.cuda.graph(g1):
+        with capture_graph(g1, side):
             st["abs"], st["loss"] = compute()
-        with t.cuda.graph(g2):
+        with capture_graph(g2, side):
             apply()
         # libmachin_b200 kernels per update that run from the two graphs (replays bypass the C entry points,
         # which count the eager launches of the exchange themselves)

@@ -21,7 +21,7 @@ from ... import ops
 from ..buffers import PrioritizedBuffer
 from ..transition import Transition
 from .base import TorchFramework
-from .utils import capture_safe, hard_update, model_device, safe_call, soft_update
+from .utils import capture_graph, capture_safe, hard_update, model_device, safe_call, soft_update
 
 
 class DDPGPer(TorchFramework):
@@ -231,7 +231,7 @@ class DDPGPer(TorchFramework):
         from ..._lib import lib
         graph = t.cuda.CUDAGraph()
         launched = lib.mb_launch_count()
-        with capture_safe(), t.cuda.graph(graph):
+        with capture_safe(), capture_graph(graph, side):
             self._static_losses = self._step(True, True, True, self._u_static, True)
         self._graph = graph
         self.graph_launches = lib.mb_launch_count() - launched   # libmachin_b200 kernels per replay

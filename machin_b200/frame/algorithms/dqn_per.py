@@ -19,7 +19,7 @@ from ... import ops
 from ..buffers import PrioritizedBuffer
 from ..transition import Transition
 from .base import TorchFramework
-from .utils import capture_safe, hard_update, model_device, safe_call, soft_update
+from .utils import capture_graph, capture_safe, hard_update, model_device, safe_call, soft_update, step_option
 
 
 class DQNPer(TorchFramework):
@@ -197,7 +197,7 @@ class DQNPer(TorchFramework):
             self.qnet_optim.zero_grad(set_to_none=True)
         from ..._lib import lib
         launched = lib.mb_launch_count()
-        with capture_safe(), t.cuda.graph(graph):
+        with capture_safe(), capture_graph(graph, side):
             self._static_loss = self._step(True, True, self._u_static, True)
         self._graph = graph
         self.graph_launches = lib.mb_launch_count() - launched   # libmachin_b200 kernels per replay
@@ -380,13 +380,23 @@ class DQNPer(TorchFramework):
             if self._side_stream is None:
                 self._side_stream = t.cuda.Stream(device=dev)
             forked = (t.cuda.current_stream(dev), self._side_stream)
+            # the beta advance and the scalar loss (three small torch kernels) do not depend on the tree update: behind it
+            # they make the side branch as long as backward + optimizer on the main stream, so they get a branch of their
+            # own -- the first forward stream, idle since its join in front of the TD kernel
+            third = self._fwd_streams[0] if (step_option("third_branch") and self.parallel_forwards
+                                             and self._fwd_streams is not None) else None
             forked[1].wait_stream(forked[0])
             with t.cuda.stream(forked[1]):
                 self.replay_buffer.update_priority(td["abs_error"], d_index)
+            if third is not None:
+                third.wait_stream(forked[0])
+            with t.cuda.stream(third if third is not None else forked[1]):
                 if use_device_params:
                     self.replay_buffer.advance_beta_device()
                 if value_loss is None:
                     value_loss = td["loss_elem"].mean()
+            if third is not None:
+                forked = (*forked, third)
         else:
             self.replay_buffer.update_priority(td["abs_error"], d_index)
             if value_loss is None:
@@ -400,7 +410,8 @@ class DQNPer(TorchFramework):
             self._sync_grads()
         self._optimizer_and_target(update_value, update_target)   # (FusedAdam + soft update as one launch when opted in)
         if forked is not None:
-            forked[0].wait_stream(forked[1])     # join before the next draw reads the tree (td / d_index still alive here)
+            for branch in forked[1:]:
+                forked[0].wait_stream(branch)    # join before the next draw reads the tree (td / d_index still alive here)
         self.qnet.eval()
         return value_loss
 

@@ -17,7 +17,7 @@ from ... import ops
 from ..buffers import IMPALABuffer
 from ..transition import Transition
 from .base import TorchFramework
-from .utils import capture_safe, safe_call
+from .utils import capture_graph, capture_safe, safe_call
 
 
 class IMPALA(TorchFramework):
@@ -206,7 +206,7 @@ class IMPALA(TorchFramework):
             o.zero_grad(set_to_none=True)
         graph = t.cuda.CUDAGraph()
         launched = lib.mb_launch_count()
-        with capture_safe(), t.cuda.graph(graph):
+        with capture_safe(), capture_graph(graph, side):
             st["losses"] = body()
         self.graph_launches = lib.mb_launch_count() - launched
         with t.no_grad():

@@ -70,6 +70,24 @@ def soft_update(target_net: nn.Module, source_net: nn.Module, update_rate) -> No
         ops.soft_update(target_net, source_net, update_rate)
 
 
+def step_option(name: str) -> bool:
+    """Stream-level options of the captured update.  All on by default; ``MB_STEP_OFF=capture_stream,last_grad_main,
+    third_branch`` switches the named ones off (A/B timing: bench.py)."""
+    import os
+    return name not in os.environ.get("MB_STEP_OFF", "").split(",")
+
+
+def capture_graph(graph, warmup_stream, **kwargs):
+    """``torch.cuda.graph(graph, ...)`` capturing ON the stream the warm-up iterations ran on.  torch's default is an
+    internal capture stream of its own -- a different handle, so everything keyed by the current stream (FusedMLP's
+    workspaces: model.py) would be created again inside the capture, and the zero-fill of its counters would be replayed
+    in front of the online forward by every update (4 launches of ~2 us on the critical path, profiles/
+    r2_launches_default_step.csv IDs 8-11)."""
+    if step_option("capture_stream"):
+        kwargs["stream"] = warmup_stream
+    return t.cuda.graph(graph, **kwargs)
+
+
 class capture_safe:
     """Context for CUDA-graph capture of a user model: ``torch.distributions`` validates its arguments with a
     host-synchronising ``_is_all_true`` (illegal while a stream is capturing, and a failed capture leaves torch's

@@ -8,6 +8,7 @@ target updates, model servers and checkpoints see a normal module.  ``FusedAdam`
 Any other ``nn.Module`` / optimizer keeps working through the generic autograd path.
 """
 import ctypes as C
+import os
 from typing import Sequence
 
 import torch as t
@@ -66,7 +67,7 @@ class _MLPFunction(t.autograd.Function):
         sides = [_side_stream(dev, l) for l in range(n)] if (PARALLEL_WEIGHT_GRADS and n > 1) else None
         cur = t.cuda.current_stream(dev) if sides is not None else None
         side_ws = ctx.side_ws if sides is not None else None
-        keep = []
+        keep, used = [], []
         for l in range(n - 1, -1, -1):
             x, w = inputs[l], weights[l]
             M, K = x.shape
@@ -76,8 +77,12 @@ class _MLPFunction(t.autograd.Function):
             sink = ctx.sinks is not None
             dw = ctx.sinks[2 * l] if sink else t.empty_like(w)
             db = ctx.sinks[2 * l + 1] if sink else t.empty(N, dtype=t.float32, device=w.device)
-            if sides is not None:
+            # the first layer's weight gradient is the LAST kernel of the backward (nothing is left on the main stream to run
+            # beside it): on a branch it would only add a fork and a join to the critical path
+            on_branch = sides is not None and not (LAST_WEIGHT_GRAD_ON_MAIN and l == 0 and not ctx.needs_input_grad[0])
+            if on_branch:
                 side = sides[l]                            # one branch per layer: the weight gradients are independent of each other
+                used.append(side)
                 side.wait_stream(cur)                      # dy of this layer is ready
                 with t.cuda.stream(side):
                     _lib.check(lib.mb_mlp_linear_backward_weight(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(dw), _lib.ptr(db), M, N, K,
@@ -95,14 +100,15 @@ class _MLPFunction(t.autograd.Function):
                 dy = dxl
                 if l == 0:
                     dx = dxl
-        if sides is not None:
-            for side in sides:
-                cur.wait_stream(side)                      # every dw / db is complete before autograd hands them on
+        for side in used:                                  # (only branches that were forked: a stream outside a capture
+            cur.wait_stream(side)                          #  must not be joined into it) every dw / db is complete before
+                                                           #  autograd hands them on
         del keep
         return (dx, None, None, None, *grads)
 
 
 PARALLEL_WEIGHT_GRADS = True       # FusedMLP.backward: weight-gradient GEMMs on a side stream (see _MLPFunction.backward)
+LAST_WEIGHT_GRAD_ON_MAIN = "last_grad_main" not in os.environ.get("MB_STEP_OFF", "").split(",")
 _SIDE_STREAMS = {}
 
 
