@@ -13,6 +13,17 @@ namespace mb {
 
 void set_cuda_error(cudaError_t e, const char *file, int line);
 void count_launch(int n);  // kernels launched by this library (mb_launch_count)
+// MB_CARVEOUT=max (experiment): every kernel of the learner update asks for the largest shared-memory
+// carve-out, so that consecutive kernels of one update never make an SM switch its L1 / shared-memory split.  A
+// preference only: results do not depend on it.
+bool carveout_max();
+#define MB_PREFER_MAX_SMEM(...)                                                                              \
+    do {                                                                                                     \
+        static const bool mb_once_ = mb::carveout_max() &&                                                   \
+            cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributePreferredSharedMemoryCarveout,                \
+                                 (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess;                        \
+        (void)mb_once_;                                                                                      \
+    } while (0)
 
 #define MB_CUDA(expr)                                        \
     do {                                                     \

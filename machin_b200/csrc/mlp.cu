@@ -566,6 +566,7 @@ bool launch_narrow(const GemmArgs &g, cudaStream_t s) {
         return false;
     int blocks = (g.M + 7) / 8;
     if (blocks > 4 * mb::kNumSMs) blocks = 4 * mb::kNumSMs;
+    MB_PREFER_MAX_SMEM(gemm_narrow_kernel);
     gemm_narrow_kernel<<<blocks, 256, sizeof(float) * (size_t)g.N * g.K, s>>>(g);
     return true;
 }
@@ -595,6 +596,7 @@ bool launch_wk_groups(GemmArgs g, cudaStream_t s, int Kp) {
     }
     if (dyn > 200 * 1024) return false;
     const dim3 grid((g.N + 31) / 32, (g.M + 31) / 32, 1);
+    MB_PREFER_MAX_SMEM(gemm_wk_kernel<KG, kA, kB>);
     gemm_wk_kernel<KG, kA, kB><<<grid, 64 * KG, dyn, s>>>(g, Kp);
     return true;
 }
@@ -1119,6 +1121,7 @@ int mb_adam_soft_step_multi(float *const *d_params, const float *const *d_grads,
         int64_t blocks = (total + 255) / 256;
         if (blocks > (int64_t)mb::kNumSMs * 8) blocks = (int64_t)mb::kNumSMs * 8;
         // python: target * (1.0 - update_rate) + param * update_rate ; both scalars become float32 (csrc/td.cu)
+        MB_PREFER_MAX_SMEM(adam_soft_kernel);
         adam_soft_kernel<<<(unsigned)blocks, 256, 0, s>>>(l, (float)lr, (float)beta1, (float)beta2, (float)eps,
                                                           (float)weight_decay, d_step_count, d_ticket,
                                                           (float)(1.0 - update_rate), (float)update_rate);

@@ -56,6 +56,7 @@ bool launch_gather_bulk(const char *ring, int64_t pitch, int64_t capacity, const
     per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
     int64_t blocks = (int64_t)mb::kNumSMs * per_sm;
     if (blocks > n_tiles) blocks = n_tiles;
+    MB_PREFER_MAX_SMEM(rows_gather_bulk_kernel);
     rows_gather_bulk_kernel<<<(unsigned)blocks, kBulkThreads, dyn, s>>>(ring, pitch, capacity, index, n, fl, (int)R, mask);
     return true;
 }

@@ -16,6 +16,13 @@ void set_cuda_error(cudaError_t e, const char *file, int line) {
 
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool carveout_max() {
+    static const bool on = [] {
+        const char *e = getenv("MB_CARVEOUT");
+        return e && !strcmp(e, "max");
+    }();
+    return on;
+}
 long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 static std::mutex g_staging_mu;

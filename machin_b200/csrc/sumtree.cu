@@ -441,10 +441,13 @@ static int launch_update(mb_tree *t, const int64_t *d_index, const void *d_weigh
         const int levels = t->dev.depth - 1;
         const unsigned grid = 1u << part_cut(levels);
         const size_t dyn = part_dyn_smem(levels);
-        if (dtype == MB_F32)
+        if (dtype == MB_F32) {
+            MB_PREFER_MAX_SMEM(tree_update_part<float>);
             tree_update_part<float><<<grid, kPartThreads, dyn, s>>>(t->dev, d_index, (const float *)d_weight, d_valid, (int)n, nz, gen);
-        else
+        } else {
+            MB_PREFER_MAX_SMEM(tree_update_part<double>);
             tree_update_part<double><<<grid, kPartThreads, dyn, s>>>(t->dev, d_index, (const double *)d_weight, d_valid, (int)n, nz, gen);
+        }
         MB_LAUNCHED(1);
         return MB_OK;
     }
@@ -577,6 +580,7 @@ int mb_per_sample(mb_tree *t, const double *d_uniform, int64_t n, int64_t n_stor
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
+        MB_PREFER_MAX_SMEM(per_sample_cluster);
         MB_CUDA(cudaLaunchKernelEx(&cfg, per_sample_cluster, t->dev, d_uniform, n, a, d_index, d_is_weight));
     } else if (n <= 1024) {
         per_sample_small<<<1, (unsigned)(((n + 31) / 32) * 32), 0, s>>>(t->dev, d_uniform, n, a, d_index, d_is_weight);
@@ -616,6 +620,7 @@ int mb_per_sample_multi(mb_tree *t, const double *d_uniform, int64_t n, int n_re
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    MB_PREFER_MAX_SMEM(per_sample_cluster_multi);
     MB_CUDA(cudaLaunchKernelEx(&cfg, per_sample_cluster_multi, t->dev, d_uniform, n, d_params, d_index, d_is_weight));
     MB_LAUNCHED(1);
     return MB_OK;

@@ -67,6 +67,7 @@ int mb_td_dqn(const float *d_q, const float *d_q_next, const float *d_q_tgt_next
     if (batch == 0) return MB_OK;
     TdDqnArgs a{d_q, d_q_next, d_q_tgt_next, batch, n_actions, d_action, d_reward, d_terminal, d_is_weight,
                 discount, mode, d_y, d_action_value, d_abs_error, d_loss_elem, d_grad_q};
+    MB_PREFER_MAX_SMEM(td_dqn_kernel);
     td_dqn_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
     MB_LAUNCHED(1);
     return MB_OK;

@@ -76,17 +76,24 @@ class _FixedShapeExchange:
     # for free, `__threadfence_system()` in hundreds of CTAs does not.  Kept as an option for the experiment log.
     fold_barriers = False
 
-    PEER_CHECK_EVERY = 1024
+    PEER_CHECK_EVERY, PEER_CHECK_SECONDS = 1024, 30.0
 
     def _check_peers_now_and_then(self):
         """A peer barrier that gave up on a member (parallel/peer.py: 20 s) lets the update run on with stale rows; the
-        flag it leaves is read here every PEER_CHECK_EVERY host-side updates (one small device-to-host read)."""
+        flag it leaves is read here every PEER_CHECK_EVERY host-side updates, or PEER_CHECK_SECONDS after the last read (one
+        small device-to-host read)."""
         st = getattr(self, "_static", None)
         if st is None or st.get("peer") is None:
             return
+        import time
+        now = time.monotonic()
         self._peer_checks = getattr(self, "_peer_checks", 0) + 1
-        if self._peer_checks % self.PEER_CHECK_EVERY == 0:
+        # (also whenever updates have become slow: with a member gone every barrier of every update waits out its timeout)
+        if self._peer_checks % self.PEER_CHECK_EVERY == 0 or now - getattr(self, "_peer_checked_at", now) > self.PEER_CHECK_SECONDS:
             st["peer"].check()
+            self._peer_checked_at = now
+        elif not hasattr(self, "_peer_checked_at"):
+            self._peer_checked_at = now
 
     def _static_setup(self, device_apportion: bool, peer_exchange: bool, grad_floats: int):
         """Collective.  Allocates every buffer of the exchange (peer-mapped ones if ``peer_exchange`` works here) and

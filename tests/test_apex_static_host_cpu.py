@@ -101,3 +101,28 @@ def test_peer_timeout_flag_is_read_every_so_often():
     import pytest
     with pytest.raises(RuntimeError, match="did not reach a barrier"):
         learner._check_peers_now_and_then()
+
+
+def test_peer_timeout_flag_is_read_when_updates_turn_slow(monkeypatch):
+    import time
+    from machin_b200.frame.algorithms.apex import _FixedShapeExchange
+
+    class Peer:
+        checks = 0
+
+        def check(self):
+            Peer.checks += 1
+
+    clock = [100.0]
+    monkeypatch.setattr(time, "monotonic", lambda: clock[0])
+    learner = _FixedShapeExchange.__new__(_FixedShapeExchange)
+    learner._static = {"peer": Peer()}
+    for _ in range(5):                                        # fast updates: no read
+        clock[0] += 0.001
+        learner._check_peers_now_and_then()
+    assert Peer.checks == 0
+    clock[0] += 80.0                                          # an update that sat out four 20 s barrier timeouts
+    learner._check_peers_now_and_then()
+    assert Peer.checks == 1
+    learner._check_peers_now_and_then()
+    assert Peer.checks == 1
