@@ -254,6 +254,8 @@ class Trainer:
                  limit_test_batches: int = 1, callbacks: List[Any] = None):
         if max_steps is None and max_epochs is None:
             raise ValueError("Trainer needs max_steps or max_epochs: the episode datasets never end")
+        if max_steps is None and limit_train_batches is None:
+            raise ValueError("Trainer needs limit_train_batches with max_epochs: an epoch of an endless dataset never ends")
         self.max_steps, self.max_epochs = max_steps, max_epochs
         self.limit_train_batches, self.limit_test_batches = limit_train_batches, limit_test_batches
         self.callbacks = list(callbacks or [])

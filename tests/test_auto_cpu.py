@@ -152,6 +152,8 @@ def test_trainer_fit_limits_and_callbacks(doubles, tmp_path):
     assert (trainer.global_step, trainer.current_epoch) == (1, 1) and launcher.frame.replay_buffer.size() == 3
     with pytest.raises(ValueError, match="max_steps or max_epochs"):
         Trainer()
+    with pytest.raises(ValueError, match="limit_train_batches with max_epochs"):
+        Trainer(max_epochs=2)
     # early stopping on the monitored key: best at epoch 1, three epochs without improvement end the run at epoch 4
     rewards = [1.0, 5.0, 4.0, 5.0, 3.0, 9.0, 9.0]
     launcher = Launcher(dqn_config(), lambda frame, env_config: OneTransition(rewards), model_device="cpu")
