@@ -174,3 +174,20 @@ def test_load_picks_newest_version_common_to_all_models(tmp_path):
         algo.load(str(tmp_path))
     with pytest.raises(RuntimeError, match="doesn't exist"):
         algo.load(str(tmp_path / "nope"))
+
+
+def test_step_options_and_capture_stream(monkeypatch):
+    """MB_STEP_OFF switches the stream-level options of the captured update off by name; capture_graph hands the warm-up
+    stream to torch.cuda.graph unless `capture_stream` is off."""
+    import torch as t
+    from machin_b200.frame.algorithms import utils
+    seen = []
+    monkeypatch.setattr(t.cuda, "graph", lambda graph, **kw: seen.append((graph, kw)) or "ctx")
+    monkeypatch.delenv("MB_STEP_OFF", raising=False)
+    assert all(utils.step_option(n) for n in ("capture_stream", "last_grad_main", "third_branch"))
+    assert utils.capture_graph("g", "warmup-stream", capture_error_mode="thread_local") == "ctx"
+    assert seen[-1] == ("g", {"stream": "warmup-stream", "capture_error_mode": "thread_local"})
+    monkeypatch.setenv("MB_STEP_OFF", "capture_stream,third_branch")
+    assert not utils.step_option("capture_stream") and not utils.step_option("third_branch") and utils.step_option("last_grad_main")
+    utils.capture_graph("g", "warmup-stream")
+    assert seen[-1] == ("g", {})
