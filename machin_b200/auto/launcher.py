@@ -75,12 +75,14 @@ class _EpisodeModule:
         return t.device("cuda", t.cuda.current_device()) if dist.get_backend() == "nccl" else t.device("cpu")
 
     def _log(self, logs: List[Dict[str, Any]], sync_keys=()):
+        in_job = dist.is_available() and dist.is_initialized()
         for entry in logs:
             for key, value in entry.items():
                 if isinstance(value, tuple) and len(value) == 2 and callable(value[1]):
                     value[1](self, key, value[0])
                 else:
-                    self.log(key, value, prog_bar=True, sync_dist=key in sync_keys and bool(key))
+                    # only the monitored key is reduced: other keys may be missing on other ranks (launcher.py:227-239)
+                    self.log(key, value, prog_bar=True, sync_dist=bool(key) and key in sync_keys and in_job)
 
     def _updates_for(self, sample) -> int:
         """One update per stored transition (launcher.py:63-64).  An on-policy framework empties its buffer inside

@@ -795,6 +795,112 @@ def gen_auto_surface():
         json.dump(out, fh, indent=1, sort_keys=True)
 
 
+def gen_auto_trace():
+    """What the UNMODIFIED launchers of machin/auto/launcher.py do with a batch: the order of ``store_episode`` / ``update``
+    calls on the framework, the log entries that reach ``self.log`` and the handler tuples, for the local launcher and for
+    the distributed one on the first batch of epoch 0 / a later batch / a later epoch.  pytorch-lightning is not in the
+    image: ``LightningModule`` is replaced by a recording ``nn.Module`` stub, and only launcher.py / dataset.py / config.py
+    are imported (the package's own __init__ pulls in gym and the lightning plugins)."""
+    import importlib.abc
+    import importlib.machinery
+    import json
+    import types
+    from unittest.mock import MagicMock
+    import torch.nn as nn
+
+    class MockFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+        roots = ("pytorch_lightning", "gym", "matplotlib", "PIL", "moviepy")
+
+        def find_spec(self, name, path, target=None):
+            if name.split(".")[0] in self.roots and name != "pytorch_lightning":
+                return importlib.machinery.ModuleSpec(name, self, is_package=True)
+            return None
+
+        def create_module(self, spec):
+            m = MagicMock()
+            m.__name__, m.__path__, m.__spec__, m.__loader__ = spec.name, [], spec, self
+            return m
+
+        def exec_module(self, module):
+            pass
+
+    class LightningModule(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.logged, self.current_epoch, self.device = [], 0, "cpu"
+
+        def log(self, key, value, **kw):
+            self.logged.append([key, value, dict(sorted(kw.items()))])
+
+    for name in [k for k in sys.modules if k.split(".")[0] in MockFinder.roots]:
+        del sys.modules[name]
+    stub = types.ModuleType("pytorch_lightning")
+    stub.__path__, stub.LightningModule, stub.Trainer, stub.trainer = [], LightningModule, MagicMock(), MagicMock()
+    sys.modules["pytorch_lightning"] = stub
+    sys.meta_path.insert(0, MockFinder())
+    package = types.ModuleType("machin.auto")
+    package.__path__ = [os.path.join(ref_shim.REFERENCE_ROOT, "machin", "auto")]
+    sys.modules["machin.auto"] = package
+    sys.modules["machin.auto.envs"] = types.ModuleType("machin.auto.envs")
+    from machin.auto import dataset, launcher
+
+    class Frame:
+        def __init__(self):
+            self.events = []
+
+        def store_episode(self, episode):
+            self.events.append(["store", len(episode)])
+
+        def update(self):
+            self.events.append(["update"])
+
+    class Group:
+        def __init__(self, frame):
+            self.frame = frame
+
+        def barrier(self):
+            self.frame.events.append(["barrier"])
+
+    def handler(module, key, value):
+        module.frame.events.append(["handler", key, value])
+
+    def batch():
+        first, second = dataset.DatasetResult(), dataset.DatasetResult()
+        for i in range(3):
+            first.add_observation({"i": i})
+        first.add_log({"a": 1.5})
+        first.add_log({"v": (7, handler)})
+        for i in range(2):
+            second.add_observation({"i": i})
+        second.add_log({"total_reward": 9.0})
+        return [first, second]
+
+    def fresh(cls):
+        module = cls.__new__(cls)
+        LightningModule.__init__(module)
+        module.frame = Frame()
+        return module
+
+    out = {}
+    local = fresh(launcher.Launcher)
+    local.training_step(batch(), 0)
+    out["launcher_training_step"] = {"events": local.frame.events, "logged": local.logged}
+    local = fresh(launcher.Launcher)
+    local.test_step(batch(), 0)
+    out["launcher_test_step"] = {"events": local.frame.events, "logged": local.logged}
+    for name, epoch, batch_idx in (("first_batch", 0, 0), ("later_batch", 0, 1), ("later_epoch", 1, 0)):
+        d = fresh(launcher.DistributedLauncher)
+        d.group, d._train_esm, d._test_esm, d.current_epoch = Group(d.frame), "total_reward", None, epoch
+        d.training_step(list(reversed(batch())), batch_idx)       # (the monitored key sits in the FIRST sample)
+        out["distributed_training_step_" + name] = {"events": d.frame.events, "logged": d.logged}
+    d = fresh(launcher.DistributedLauncher)
+    d.group, d._train_esm, d._test_esm = Group(d.frame), "total_reward", None
+    d.test_step(batch(), 0)
+    out["distributed_test_step"] = {"events": d.frame.events, "logged": d.logged}
+    with open(os.path.join(OUT, "ref_auto_trace.json"), "w") as fh:
+        json.dump(out, fh, indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     ref_shim.load()
     os.makedirs(OUT, exist_ok=True)

@@ -423,3 +423,76 @@ def test_auto_surface_matches_reference():
             else:
                 check(f"{module_name}.{name}", getattr(module, name), spec)
     assert not problems, problems
+
+
+# ------------------------------------------------------------------------------------------------ the loop against the reference's
+def test_launcher_steps_match_reference_trace():
+    """tests/golden/ref_auto_trace.json: what the UNMODIFIED launchers (machin/auto/launcher.py, run in the build container
+    over a recording LightningModule stub: oracle/make_golden.py::gen_auto_trace) do with the same batches.  The local
+    launcher must make the same calls in the same order.  The distributed one must make the same calls per step -- stores,
+    one update per stored transition except on the first batch of epoch 0, logs of the first sample only -- in its own
+    order (all stores, then the agreed number of updates: DESIGN.md 6) and without a barrier in a world of one."""
+    from collections import Counter
+    from conftest import GOLDEN
+    from machin_b200.auto.launcher import _EpisodeModule
+    ref = json.load(open(os.path.join(GOLDEN, "ref_auto_trace.json")))
+
+    class Frame:
+        role = "learner"
+
+        def __init__(self):
+            self.events = []
+
+        def store_episode(self, episode):
+            self.events.append(["store", len(episode)])
+
+        def update(self):
+            self.events.append(["update"])
+
+    def handler(module, key, value):
+        module.frame.events.append(["handler", key, value])
+
+    def batch():
+        first, second = DatasetResult(), DatasetResult()
+        for i in range(3):
+            first.add_observation({"i": i})
+        first.add_log({"a": 1.5})
+        first.add_log({"v": (7, handler)})
+        for i in range(2):
+            second.add_observation({"i": i})
+        second.add_log({"total_reward": 9.0})
+        return [first, second]
+
+    def fresh(cls):
+        module = cls.__new__(cls)
+        _EpisodeModule.__init__(module, {}, None)
+        module.frame, module._graph_pending, module.calls = Frame(), False, []
+        plain = module.log
+        module.log = lambda key, value, prog_bar=False, sync_dist=False: (
+            module.calls.append([key, value, {"prog_bar": prog_bar, "sync_dist": sync_dist}]), plain(key, value, prog_bar, sync_dist))
+        return module
+
+    def same_logs(mine, theirs):
+        return [[k, v, {"sync_dist": False, **kw}] for k, v, kw in theirs] == mine
+
+    local = fresh(Launcher)
+    local.training_step(batch(), 0)
+    assert local.frame.events == ref["launcher_training_step"]["events"]
+    assert same_logs(local.calls, ref["launcher_training_step"]["logged"])
+    local = fresh(Launcher)
+    local.test_step(batch(), 0)
+    assert local.frame.events == ref["launcher_test_step"]["events"] and same_logs(local.calls, ref["launcher_test_step"]["logged"])
+    for name, epoch, batch_idx in (("first_batch", 0, 0), ("later_batch", 0, 1), ("later_epoch", 1, 0)):
+        theirs = ref["distributed_training_step_" + name]
+        d = fresh(DistributedLauncher)
+        d._train_esm, d._test_esm, d.current_epoch = "total_reward", None, epoch
+        d.training_step(list(reversed(batch())), batch_idx)
+        count = lambda events: Counter(tuple(e) for e in events if e != ["barrier"])
+        assert count(d.frame.events) == count(theirs["events"]), name
+        stores = [e for e in d.frame.events if e[0] == "store"]
+        assert d.frame.events[:len(stores)] == stores == [e for e in theirs["events"] if e[0] == "store"]
+        assert same_logs(d.calls, theirs["logged"]), name
+    d = fresh(DistributedLauncher)
+    d._train_esm, d._test_esm = "total_reward", None
+    d.test_step(batch(), 0)
+    assert d.frame.events == ref["distributed_test_step"]["events"] and same_logs(d.calls, ref["distributed_test_step"]["logged"])
