@@ -901,6 +901,107 @@ def gen_auto_trace():
         json.dump(out, fh, indent=1, sort_keys=True)
 
 
+class AutoQNet(t.nn.Module):
+    """Q-net of the dataset fixture (tests/test_auto_cpu.py defines the same class: same layers in the same order)."""
+
+    def __init__(self, state_dim, action_num):
+        super().__init__()
+        self.fc1, self.fc2 = t.nn.Linear(state_dim, 16), t.nn.Linear(16, action_num)
+
+    def forward(self, state):
+        return self.fc2(t.relu(self.fc1(state)))
+
+
+def gen_auto_dataset():
+    """Two episodes collected by the UNMODIFIED ``RLGymDiscActDataset`` (machin/auto/envs/openai_gym.py:32-140) with the
+    reference's DQN acting (epsilon 0.5, so that both the greedy and the random branch occur) on the cart-pole of
+    machin_b200/auto/envs/classic_control.py behind a stub ``gym`` (spaces + a render method).  The fixture holds every
+    transition; machin_b200's dataset must collect the same ones from the same seeds."""
+    import importlib.abc
+    import importlib.machinery
+    import types
+    from unittest.mock import MagicMock
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from machin_b200.auto.envs import classic_control
+
+    class Space:
+        def __init__(self, *a, **k):
+            pass
+
+    gym = types.ModuleType("gym")
+    gym.__path__ = []
+    spaces = types.ModuleType("gym.spaces")
+    for name in ("Box", "Discrete", "MultiBinary", "MultiDiscrete"):
+        setattr(spaces, name, type(name, (Space,), {}))
+    rendering = types.ModuleType("gym.envs.classic_control.rendering")
+    rendering.Viewer = type("Viewer", (), {"__init__": lambda self, *a, **k: None})
+    gym.spaces = spaces
+    for name in [k for k in sys.modules if k.split(".")[0] in ("gym", "pytorch_lightning", "matplotlib", "PIL", "moviepy")]:
+        del sys.modules[name]
+    sys.modules.update({"gym": gym, "gym.spaces": spaces, "gym.envs": types.ModuleType("gym.envs"),
+                        "gym.envs.classic_control": types.ModuleType("gym.envs.classic_control"),
+                        "gym.envs.classic_control.rendering": rendering})
+    sys.modules["gym.envs.classic_control"].rendering = rendering
+
+    class MockFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+        roots = ("pytorch_lightning", "matplotlib", "PIL", "moviepy", "gym")
+
+        def find_spec(self, name, path, target=None):
+            if name.split(".")[0] in self.roots and name not in sys.modules and name != "pytorch_lightning":
+                return importlib.machinery.ModuleSpec(name, self, is_package=True)
+            return None
+
+        def create_module(self, spec):
+            m = MagicMock()
+            m.__name__, m.__path__, m.__spec__, m.__loader__ = spec.name, [], spec, self
+            return m
+
+        def exec_module(self, module):
+            pass
+
+    class LightningModule(t.nn.Module):
+        pass
+
+    stub = types.ModuleType("pytorch_lightning")
+    stub.__path__, stub.LightningModule, stub.Trainer, stub.trainer = [], LightningModule, MagicMock(), MagicMock()
+    sys.modules["pytorch_lightning"] = stub
+    sys.meta_path.insert(0, MockFinder())
+    for name in [k for k in sys.modules if k.startswith("machin.auto")]:
+        del sys.modules[name]
+    from machin.auto.config import generate_algorithm_config, init_algorithm_from_config
+    from machin.auto.envs.openai_gym import RLGymDiscActDataset
+
+    class Env(classic_control.CartPole):
+        def __init__(self, seed):
+            super().__init__(seed=seed)
+            self.action_space, self.observation_space = spaces.Discrete(), spaces.Box()
+
+        def render(self, mode="rgb_array"):
+            return np.zeros((2, 2, 3), dtype=np.uint8)
+
+    globals()["QNet"] = AutoQNet                      # the reference resolves model names in the globals of the call stack
+    config = generate_algorithm_config("DQN", {})
+    config["frame_config"]["models"] = ["QNet", "QNet"]
+    config["frame_config"]["model_kwargs"] = [{"state_dim": 4, "action_num": 2}] * 2
+    t.manual_seed(11)
+    dqn = init_algorithm_from_config(config)
+    dqn.epsilon = 0.5
+    dataset = RLGymDiscActDataset(dqn, Env(seed=5), render_every_episode=10 ** 9)
+    out = {}
+    t.manual_seed(12)
+    for e in range(2):
+        result = next(dataset)
+        obs = result.observations
+        out[f"ep{e}_state"] = np.concatenate([o["state"]["state"].numpy() for o in obs])
+        out[f"ep{e}_next_state"] = np.concatenate([o["next_state"]["state"].numpy() for o in obs])
+        out[f"ep{e}_action"] = np.concatenate([o["action"]["action"].numpy() for o in obs])
+        out[f"ep{e}_reward"] = np.array([o["reward"] for o in obs], dtype=np.float64)
+        out[f"ep{e}_terminal"] = np.array([o["terminal"] for o in obs], dtype=np.bool_)
+        out[f"ep{e}_total_reward"] = np.float64([log["total_reward"] for log in result.logs if "total_reward" in log][-1])
+    out["epsilon_after"] = np.float64(dqn.epsilon)
+    np.savez_compressed(os.path.join(OUT, "ref_auto_dataset.npz"), **out)
+
+
 if __name__ == "__main__":
     ref_shim.load()
     os.makedirs(OUT, exist_ok=True)

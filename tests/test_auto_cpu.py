@@ -496,3 +496,42 @@ def test_launcher_steps_match_reference_trace():
     d._train_esm, d._test_esm = "total_reward", None
     d.test_step(batch(), 0)
     assert d.frame.events == ref["distributed_test_step"]["events"] and same_logs(d.calls, ref["distributed_test_step"]["logged"])
+
+
+class AutoQNet(t.nn.Module):
+    """The Q-net of tests/golden/ref_auto_dataset.npz (oracle/make_golden.py::AutoQNet: same layers in the same order)."""
+
+    def __init__(self, state_dim, action_num):
+        super().__init__()
+        self.fc1, self.fc2 = t.nn.Linear(state_dim, 16), t.nn.Linear(16, action_num)
+
+    def forward(self, state):
+        return self.fc2(t.relu(self.fc1(state)))
+
+
+def test_discrete_dataset_collects_the_reference_episodes(doubles):
+    """tests/golden/ref_auto_dataset.npz: two episodes collected by the UNMODIFIED RLGymDiscActDataset with the reference's
+    DQN acting (oracle/make_golden.py::gen_auto_dataset).  Same seeds, same net, same task: the dataset here must hand the
+    launcher the very same transitions -- states bit for bit, the epsilon-greedy actions (same random stream), rewards,
+    terminal flags, total reward -- and leave epsilon where the reference leaves it."""
+    from conftest import GOLDEN
+    from machin_b200.frame.algorithms import DQN
+    ref = np.load(os.path.join(GOLDEN, "ref_auto_dataset.npz"))
+    cfg = DQN.generate_config({})
+    cfg["frame_config"].update(models=["AutoQNet", "AutoQNet"], model_kwargs=[{"state_dim": 4, "action_num": 2}] * 2)
+    t.manual_seed(11)
+    dqn = auto_config.init_algorithm_from_config(cfg, model_device="cpu")
+    dqn.epsilon = 0.5
+    dataset = openai_gym.RLGymDiscActDataset(dqn, classic_control.CartPole(seed=5), render_every_episode=10 ** 9)
+    t.manual_seed(12)
+    for e in range(2):
+        result = next(dataset)
+        obs = result.observations
+        assert len(obs) == len(ref[f"ep{e}_reward"])
+        assert np.array_equal(np.concatenate([o["state"]["state"].numpy() for o in obs]), ref[f"ep{e}_state"])
+        assert np.array_equal(np.concatenate([o["next_state"]["state"].numpy() for o in obs]), ref[f"ep{e}_next_state"])
+        assert np.array_equal(np.concatenate([o["action"]["action"].numpy() for o in obs]), ref[f"ep{e}_action"])
+        assert [o["reward"] for o in obs] == list(ref[f"ep{e}_reward"]) and all(isinstance(o["reward"], float) for o in obs)
+        assert [o["terminal"] for o in obs] == list(ref[f"ep{e}_terminal"]) and all(isinstance(o["terminal"], bool) for o in obs)
+        assert result.logs[-1] == {"total_reward": float(ref[f"ep{e}_total_reward"])}
+    assert dqn.epsilon == float(ref["epsilon_after"])
