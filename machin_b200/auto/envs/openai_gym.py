@@ -11,7 +11,7 @@ per episode and not per step (``manual_sync`` / ``set_sync``, :92-94, :139).
 Pinned: ``tests/golden/ref_auto_dataset.npz`` -- two cart-pole episodes collected by the unmodified discrete dataset with
 the reference's DQN acting; the dataset here collects the same transitions bit for bit (tests/test_auto_cpu.py).
 Different: the reference's continuous dataset indexes ``[0]`` into the tensor ``act_with_noise`` returns for a plain actor
-(openai_gym.py:217-219) and stores an action WITHOUT its batch dimension; here the stored action is ``[1, action_dim]``
+(openai_gym.py:215-217) and stores an action WITHOUT its batch dimension; here the stored action is ``[1, action_dim]``
 like every other attribute.
 Added: an IMPALA transition carries ``action_log_prob`` (its ``store_episode`` requires it, impala.py:224-237; the
 reference's dataset omits it and cannot feed IMPALA).  Rendering to video (:97-98, :134-135) belongs to the media
