@@ -2,7 +2,7 @@
 
 A dataset is an endless iterator of :class:`DatasetResult`: one episode's transitions (the dictionaries
 ``store_episode`` takes) plus the log entries that episode produced.  A log value is a scalar, or a pair
-``(value, handler)`` whose handler is called as ``handler(launcher, key, value)`` (dataset.py:82, launcher.py:96-102).
+``(value, handler)`` whose handler is called as ``handler(launcher, key, value)`` (dataset.py:79, launcher.py:96-102).
 Image / video handlers (dataset.py:38-73) belong to the media utilities, which are outside the learner path."""
 from typing import Any, Callable, Dict, Iterator, List, Tuple, Union
 

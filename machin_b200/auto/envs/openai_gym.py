@@ -7,7 +7,7 @@ without it the names in ``classic_control.REGISTRY`` resolve to the built-in tas
 Kept from the reference: the environment must have a simple (array) observation and a finite horizon; Q networks and
 actors take ``state`` (and ``action``) by those names; the DDPG family stores the probability row, not the sampled index,
 as the action of a discrete environment (openai_gym.py:121-122); distributed frameworks pull the newest weights once
-per episode and not per step (``manual_sync`` / ``set_sync``, :92-94, :139).
+per episode and not per step (``manual_sync`` / ``set_sync``, :92-94, :138).
 Pinned: ``tests/golden/ref_auto_dataset.npz`` -- two cart-pole episodes collected by the unmodified discrete dataset with
 the reference's DQN acting; the dataset here collects the same transitions bit for bit (tests/test_auto_cpu.py).
 Different: the reference's continuous dataset indexes ``[0]`` into the tensor ``act_with_noise`` returns for a plain actor
@@ -158,7 +158,7 @@ def gym_env_dataset_creator(frame, env_config):
 
 
 def generate_env_config(config: Dict[str, Any] = None):
-    """The example config: CartPole-v1 for training and testing (openai_gym.py:275-296)."""
+    """The example config: CartPole-v1 for training and testing (openai_gym.py:272-293)."""
     config = deepcopy(config) if config else {}
     part = {"env_name": "CartPole-v1", "render_every_episode": 100, "act_kwargs": {}}
     return fill_default({"env": "openai_gym", "train_env_config": dict(part), "test_env_config": dict(part)}, config)

@@ -155,7 +155,7 @@ class DistributedLauncher(_EpisodeModule):
         return super().test_dataloader()
 
     def configure_optimizers(self):
-        return None                                   # the framework keeps its own optimizers (launcher.py:175-179)
+        return None                                   # the framework keeps its own optimizers (launcher.py:177-181)
 
     def _agreed_update_count(self, wanted: int) -> int:
         rank, world = _world()
@@ -177,7 +177,7 @@ class DistributedLauncher(_EpisodeModule):
             self.frame.update()
         if len(batch) > 0:
             # only the first episode's logs: ranks hold different numbers of episodes per batch, and the monitored key is
-            # reduced over the ranks (launcher.py:161-165)
+            # reduced over the ranks (launcher.py:162-166)
             self._log(batch[0].logs, sync_keys=(self._train_esm, self._test_esm))
         if _world()[1] > 1:
             dist.barrier()                            # leave the step together
