@@ -165,7 +165,7 @@ def generate_env_config(config: Dict[str, Any] = None):
 
 
 def launch_with(config, callbacks, dataset_creator):
-    """The recipe of openai_gym.py:299-343: keep the best models by ``total_reward``, stop after
+    """The recipe of openai_gym.py:295-343: keep the best models by ``total_reward``, stop after
     ``early_stopping_patience`` epochs without improvement, ``episode_per_epoch`` batches per epoch, ``max_episodes``
     batches in all; scalars go to ``<root_dir>/log/train_log/metrics.jsonl``."""
     root = config.get("root_dir") or "./trial"
