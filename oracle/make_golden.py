@@ -912,6 +912,35 @@ class AutoQNet(t.nn.Module):
         return self.fc2(t.relu(self.fc1(state)))
 
 
+class AutoSoftActor(t.nn.Module):
+    def __init__(self, state_dim, action_dim):
+        super().__init__()
+        self.fc = t.nn.Linear(state_dim, action_dim)
+
+    def forward(self, state):
+        return t.softmax(self.fc(state), dim=1)
+
+
+class AutoCritic(t.nn.Module):
+    def __init__(self, state_dim, action_dim=0):
+        super().__init__()
+        self.fc = t.nn.Linear(state_dim + action_dim, 1)
+
+    def forward(self, state, action=None):
+        return self.fc(state if action is None else t.cat([state, action], dim=1))
+
+
+class AutoPolicy(t.nn.Module):
+    def __init__(self, state_dim, action_num):
+        super().__init__()
+        self.fc = t.nn.Linear(state_dim, action_num)
+
+    def forward(self, state, action=None):
+        law = t.distributions.Categorical(logits=self.fc(state))
+        act = action if action is not None else law.sample().view(-1, 1)
+        return act, law.log_prob(act.flatten()).view(-1, 1), law.entropy().view(-1, 1)
+
+
 def gen_auto_dataset():
     """Two episodes collected by the UNMODIFIED ``RLGymDiscActDataset`` (machin/auto/envs/openai_gym.py:32-140) with the
     reference's DQN acting (epsilon 0.5, so that both the greedy and the random branch occur) on the cart-pole of
@@ -999,6 +1028,22 @@ def gen_auto_dataset():
         out[f"ep{e}_terminal"] = np.array([o["terminal"] for o in obs], dtype=np.bool_)
         out[f"ep{e}_total_reward"] = np.float64([log["total_reward"] for log in result.logs if "total_reward" in log][-1])
     out["epsilon_after"] = np.float64(dqn.epsilon)
+    # the other two branches of the discrete dataset: the DDPG family (the probability row is what gets stored,
+    # openai_gym.py:121-122) and the policy-gradient family (``act(...)[0]``), one episode each
+    globals().update(SoftActor=AutoSoftActor, Critic=AutoCritic, Policy=AutoPolicy)
+    for tag, algo, models, kwargs in (
+            ("ddpg", "DDPGPer", ["SoftActor", "SoftActor", "Critic", "Critic"], [{"state_dim": 4, "action_dim": 2}] * 4),
+            ("a2c", "A2C", ["Policy", "Critic"], [{"state_dim": 4, "action_num": 2}, {"state_dim": 4}])):
+        config = generate_algorithm_config(algo, {})
+        config["frame_config"]["models"], config["frame_config"]["model_kwargs"] = models, kwargs
+        t.manual_seed(21)
+        frame = init_algorithm_from_config(config)
+        dataset = RLGymDiscActDataset(frame, Env(seed=6), render_every_episode=10 ** 9)
+        t.manual_seed(22)
+        obs = next(dataset).observations
+        out[f"{tag}_state"] = np.concatenate([o["state"]["state"].numpy() for o in obs])
+        out[f"{tag}_action"] = np.concatenate([o["action"]["action"].numpy() for o in obs])
+        out[f"{tag}_terminal"] = np.array([o["terminal"] for o in obs], dtype=np.bool_)
     np.savez_compressed(os.path.join(OUT, "ref_auto_dataset.npz"), **out)
 
 

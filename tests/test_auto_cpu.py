@@ -535,3 +535,56 @@ def test_discrete_dataset_collects_the_reference_episodes(doubles):
         assert [o["terminal"] for o in obs] == list(ref[f"ep{e}_terminal"]) and all(isinstance(o["terminal"], bool) for o in obs)
         assert result.logs[-1] == {"total_reward": float(ref[f"ep{e}_total_reward"])}
     assert dqn.epsilon == float(ref["epsilon_after"])
+
+
+class AutoSoftActor(t.nn.Module):
+    def __init__(self, state_dim, action_dim):
+        super().__init__()
+        self.fc = t.nn.Linear(state_dim, action_dim)
+
+    def forward(self, state):
+        return t.softmax(self.fc(state), dim=1)
+
+
+class AutoCritic(t.nn.Module):
+    def __init__(self, state_dim, action_dim=0):
+        super().__init__()
+        self.fc = t.nn.Linear(state_dim + action_dim, 1)
+
+    def forward(self, state, action=None):
+        return self.fc(state if action is None else t.cat([state, action], dim=1))
+
+
+class AutoPolicy(t.nn.Module):
+    def __init__(self, state_dim, action_num):
+        super().__init__()
+        self.fc = t.nn.Linear(state_dim, action_num)
+
+    def forward(self, state, action=None):
+        law = t.distributions.Categorical(logits=self.fc(state))
+        act = action if action is not None else law.sample().view(-1, 1)
+        return act, law.log_prob(act.flatten()).view(-1, 1), law.entropy().view(-1, 1)
+
+
+@pytest.mark.parametrize("tag", ["ddpg", "a2c"])
+def test_discrete_dataset_other_branches_match_the_reference(doubles, tag):
+    """The DDPG family (stores the softened probability row it sampled from, openai_gym.py:121-122) and the
+    policy-gradient family (``act(...)[0]``) of the discrete dataset: one episode each against the unmodified reference's
+    (tests/golden/ref_auto_dataset.npz) -- same states bit for bit, same sampled actions / stored rows."""
+    from conftest import GOLDEN
+    from machin_b200.frame.algorithms import A2C, DDPGPer
+    ref = np.load(os.path.join(GOLDEN, "ref_auto_dataset.npz"))
+    cls, models, kwargs = {
+        "ddpg": (DDPGPer, ["AutoSoftActor", "AutoSoftActor", "AutoCritic", "AutoCritic"], [{"state_dim": 4, "action_dim": 2}] * 4),
+        "a2c": (A2C, ["AutoPolicy", "AutoCritic"], [{"state_dim": 4, "action_num": 2}, {"state_dim": 4}])}[tag]
+    cfg = cls.generate_config({})
+    cfg["frame_config"].update(models=models, model_kwargs=kwargs)
+    t.manual_seed(21)
+    frame = auto_config.init_algorithm_from_config(cfg, model_device="cpu")
+    dataset = openai_gym.RLGymDiscActDataset(frame, classic_control.CartPole(seed=6), render_every_episode=10 ** 9)
+    t.manual_seed(22)
+    obs = next(dataset).observations
+    assert np.array_equal(np.concatenate([o["state"]["state"].numpy() for o in obs]), ref[f"{tag}_state"])
+    action = np.concatenate([o["action"]["action"].numpy() for o in obs])
+    assert action.dtype == ref[f"{tag}_action"].dtype and np.array_equal(action, ref[f"{tag}_action"])
+    assert [o["terminal"] for o in obs] == list(ref[f"{tag}_terminal"])
